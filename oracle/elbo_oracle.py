@@ -1,0 +1,277 @@
+"""TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+Vectorised torch-CPU restatement of the reference's Monte-Carlo ELBO
+(`ProbabilisticModel.estimate_log_model_evidence`, /root/reference/brancher/variables.py:843-870,
+driven by `PathwiseDerivativeEstimator.__call__`, gradient_estimators.py:39-44) for the
+model families of BASELINE.json's configs.  Gradients come from torch autograd exactly as
+in the reference (`loss.backward()`, inference.py:100).  All element arithmetic is
+delegated to the same third-party code the reference calls -- `torch.distributions`
+(reference call sites distributions.py:108,122,166,180,310; pin `torch>=1.0.0`,
+requirements.txt:1; version in this image 2.11.0).
+
+What is *restated* (instead of executed from the reference) is the graph walk:
+  * ancestral sampling of q with reparameterisation `loc + eps*scale`
+    (variables.py:527-570, distributions.py:111-124 -> torch Normal.rsample),
+  * `scale = softplus(rho)` for learnable scales (geometric_ranges.py:48-57),
+  * q->p reassignment BY NAME, so that p's auto-created `<name>_loc/<name>_scale` roots
+    take q's values ("collision"/tied mode; utilities.py:282-309, variables.py:367-371),
+  * observed nodes summed over the data axis (variables.py:513-514), latent nodes kept
+    per-sample, analytic entropies (variables.py:156-162,744-749),
+  * the final `.mean()` over the sample axis (gradient_estimators.py:44).
+The reference materialises every operand at (S*B, ...) (variables.py:436-449); here the
+same contraction is a broadcasted matmul/einsum, which is what lets the oracle run at the
+BASELINE shapes.
+
+Every public function returns `(loss, grads)` with `loss = -ELBO` (inference.py:140-144) as a
+python float and `grads` a dict keyed by the REFERENCE's parameter names
+(`<var>_loc`, `<var>_scale` -- the latter is d loss / d rho, rho = softplus^-1(sigma)).
+"""
+import math
+
+import numpy as np
+import torch
+import torch.distributions as D
+import torch.nn.functional as F
+
+
+def _t(x, dtype, requires_grad=False):
+    if isinstance(x, torch.Tensor):
+        t = x.detach().to("cpu", dtype).clone()
+    else:
+        t = torch.tensor(np.asarray(x), dtype=dtype)
+    if requires_grad:
+        t.requires_grad_(True)
+    return t
+
+
+def softplus_inverse(sigma):
+    """rho such that softplus(rho) = sigma, as the reference stores learnable scales
+    (geometric_ranges.py:56-57, numpy fp64 then cast to fp32 by utilities.py:241-247)."""
+    return np.log(np.exp(np.asarray(sigma, dtype=np.float64)) - 1.0)
+
+
+class MeanFieldNormal:
+    """A set of mean-field Normal q variables (NormalVariable(loc, scale, name, learnable=True),
+    standard_variables.py:133-145) with their p-side Normal priors of the same names.
+
+    `params`: {name: (mu, rho)} arrays of the variable's event shape.
+    `eps`:    {name: array (S, *event)} standard-normal noise (injected).
+    `prior`:  None -> tied/collision mode (p's roots take q's values);
+              or {name: (loc, scale)} numeric -> declared prior (roots named distinctly).
+    """
+
+    def __init__(self, params, eps, prior=None, dtype=torch.float32):
+        self.dtype = dtype
+        self.names = sorted(params)
+        self.mu = {n: _t(params[n][0], dtype, True) for n in self.names}
+        self.rho = {n: _t(params[n][1], dtype, True) for n in self.names}
+        self.eps = {n: _t(eps[n], dtype) for n in self.names}
+        self.prior = prior
+        self.S = next(iter(self.eps.values())).shape[0]
+
+    def sample(self):
+        """w_s = mu + softplus(rho) * eps_s (torch Normal.rsample = loc + eps*scale)."""
+        self.sigma = {n: F.softplus(self.rho[n]) for n in self.names}
+        self.w = {n: self.mu[n].unsqueeze(0) + self.eps[n] * self.sigma[n].unsqueeze(0) for n in self.names}
+        return self.w
+
+    def log_prior(self):
+        """sum over variables and event dims of Normal(pi_loc, pi_scale).log_prob(w_s) -> [S]."""
+        total = 0.0
+        for n in self.names:
+            if self.prior is None:
+                loc, scale = self.mu[n], self.sigma[n]
+            else:
+                loc = _t(np.broadcast_to(self.prior[n][0], self.mu[n].shape).copy(), self.dtype)
+                scale = _t(np.broadcast_to(self.prior[n][1], self.mu[n].shape).copy(), self.dtype)
+            lp = D.Normal(loc.unsqueeze(0), scale.unsqueeze(0)).log_prob(self.w[n])
+            total = total + lp.reshape(self.S, -1).sum(dim=1)
+        return total
+
+    def entropy(self):
+        """sum over variables and event dims of Normal(mu, sigma).entropy() -> scalar
+        (variables.py:156-162: analytic entropy where torch has it)."""
+        total = 0.0
+        for n in self.names:
+            total = total + D.Normal(self.mu[n], self.sigma[n]).entropy().sum()
+        return total
+
+    def grads(self):
+        g = {}
+        for n in self.names:
+            g[n + "_loc"] = self.mu[n].grad.detach().numpy().copy()
+            g[n + "_scale"] = self.rho[n].grad.detach().numpy().copy()
+        return g
+
+
+def mean_field_prior_entropy(params, eps, prior=None, dtype=torch.float32):
+    """-(mean_s log p(w_s) + H[q]) alone: the K1 elementwise stage of the LogReg/BNN configs."""
+    q = MeanFieldNormal(params, eps, prior, dtype)
+    q.sample()
+    loss = -(q.log_prior().mean() + q.entropy())
+    loss.backward()
+    return float(loss.detach()), q.grads()
+
+
+def logreg_elbo(X, y, params, eps, prior=None, dtype=torch.float32, likelihood="binomial",
+                row_chunk=None, with_prior=True):
+    """Bayesian (multi-class) logistic regression, `minibatch_logistic_regression.py:27-43` shape.
+
+    X [B,F]; weights variable named "weights" with event shape [C,F] (C=1 for the Binomial
+    case, minibatch_logistic_regression.py:27-29); logits_sbc = sum_f W_scf X_bf  (BF.matmul(weights, x)).
+    likelihood: "binomial"  -> Binomial(total_count=1, logits).log_prob(y)  (C must be 1)
+                "bernoulli" -> Bernoulli(logits).log_prob(y)
+                "categorical" -> Categorical(logits).log_prob(label)     (distributions.py:294-311)
+    Observed node => summed over the data axis b (variables.py:513-514).
+    """
+    q = MeanFieldNormal(params, eps, prior, dtype)
+    w = q.sample()["weights"]                       # [S,C,F]
+    Xt = _t(X, dtype)
+    B = Xt.shape[0]
+    S = q.S
+    yt_all = _t(y, dtype if likelihood != "categorical" else torch.int64)
+    ll = torch.zeros(S, dtype=dtype)
+    step = row_chunk or B
+    for r0 in range(0, B, step):
+        xb = Xt[r0:r0 + step]
+        yb = yt_all[r0:r0 + step]
+        logits = torch.einsum("scf,bf->sbc", w, xb)
+        if likelihood == "binomial":
+            lp = D.Binomial(total_count=1, logits=logits[..., 0]).log_prob(yb.unsqueeze(0))
+        elif likelihood == "bernoulli":
+            lp = D.Bernoulli(logits=logits[..., 0]).log_prob(yb.unsqueeze(0))
+        elif likelihood == "categorical":
+            lp = D.Categorical(logits=logits).log_prob(yb.unsqueeze(0))
+        else:
+            raise ValueError(likelihood)
+        ll = ll + lp.sum(dim=1)
+    per_sample = ll
+    if with_prior:
+        per_sample = per_sample + q.log_prior()
+    elbo = per_sample.mean()
+    if with_prior:
+        elbo = elbo + q.entropy()
+    loss = -elbo
+    loss.backward()
+    return float(loss.detach()), q.grads()
+
+
+def bnn_elbo(X, y, params, eps, prior=None, dtype=torch.float32, sample_chunk=None, with_prior=True):
+    """One-hidden-layer Bayesian neural network, `development_playgrounds/MNIST_bayesian_neural_network.py:26-57`.
+
+    variables "weights1" [H,P], "b1" [H,1], "weights2" [C,H], "b2" [C,1];
+    h = tanh(W1 x + b1) (:38), a = W2 h + b2 (:39), k ~ Categorical(logits=a) (:40) observed
+    with integer labels y [B]; X [B,P].
+    """
+    q = MeanFieldNormal(params, eps, prior, dtype)
+    w = q.sample()
+    Xt = _t(X, dtype)
+    yt = _t(y, torch.int64)
+    S = q.S
+    step = sample_chunk or S
+    lls = []
+    for s0 in range(0, S, step):
+        sl = slice(s0, s0 + step)
+        pre = torch.einsum("shp,bp->sbh", w["weights1"][sl], Xt) + w["b1"][sl, :, 0].unsqueeze(1)
+        h = torch.tanh(pre)
+        a = torch.einsum("sch,sbh->sbc", w["weights2"][sl], h) + w["b2"][sl, :, 0].unsqueeze(1)
+        lp = D.Categorical(logits=a).log_prob(yt.unsqueeze(0))      # [s,B]
+        lls.append(lp.sum(dim=1))
+    per_sample = torch.cat(lls)
+    if with_prior:
+        per_sample = per_sample + q.log_prior()
+    elbo = per_sample.mean()
+    if with_prior:
+        elbo = elbo + q.entropy()
+    loss = -elbo
+    loss.backward()
+    return float(loss.detach()), q.grads()
+
+
+# ----------------------------------------------------------------------------------------------
+# README AR(1) (config C1): /root/reference/README.md:22-75 with y0 named 'y0' (README reuses 'x0')
+# and LogitNormalVariable defined as torch TransformedDistribution(Normal, SigmoidTransform)
+# following the LogNormal pattern (distributions.py:493-507); see SURVEY §8 a13.
+# ----------------------------------------------------------------------------------------------
+def ar1_elbo(y, params, eps, measure_noise=0.3, dtype=torch.float32):
+    """params keys (reference names): b_loc, b_scale, logit_b_post_value, x0_loc, x0_scale,
+    x{t}_mean_value (t>=1), x{t}_scale (t>=1); eps keys: "b" [S], "x0".."x{T-1}" [S].
+
+    Collision mode (every hyper-parameter is numeric on both sides): p's `x{t}_scale` root takes q's
+    learnable sigma_t, p's `b_loc/b_scale` take q's, so log p(b) - log q(b) cancels identically
+    (LogitNormal has no analytic entropy => entropy term is -log q(b), variables.py:156-162).
+    """
+    T = len(y)
+    P = {k: _t(v, dtype, True) for k, v in params.items()}
+    E = {k: _t(v, dtype) for k, v in eps.items()}
+    yt = _t(y, dtype)
+    sig_b = F.softplus(P["b_scale"])
+    base_b = D.Normal(P["b_loc"], sig_b)
+    qb = D.TransformedDistribution(base_b, [D.transforms.SigmoidTransform()])
+    u = P["b_loc"] + sig_b * E["b"]
+    b = torch.sigmoid(u)                                  # [S]
+    coef = torch.sigmoid(P["logit_b_post_value"])
+    sig = [F.softplus(P["x0_scale"])] + [F.softplus(P["x%d_scale" % t]) for t in range(1, T)]
+    x = [P["x0_loc"] + sig[0] * E["x0"]]
+    qloc = [P["x0_loc"].expand_as(x[0])]
+    for t in range(1, T):
+        m = coef * x[t - 1] + P["x%d_mean_value" % t]
+        qloc.append(m)
+        x.append(m + sig[t] * E["x%d" % t])
+    logp = qb.log_prob(b)                                  # p(b) with q's (collided) parameters
+    logp = logp + D.Normal(P["x0_loc"], sig[0]).log_prob(x[0])         # x0_loc/x0_scale collide as well
+    for t in range(1, T):
+        logp = logp + D.Normal(b * x[t - 1], sig[t]).log_prob(x[t])
+    for t in range(T):
+        logp = logp + D.Normal(x[t], torch.tensor(measure_noise, dtype=dtype)).log_prob(yt[t])
+    ent = -qb.log_prob(b)                                   # no analytic entropy -> -log q  [S]
+    for t in range(T):
+        ent = ent + D.Normal(qloc[t], sig[t]).entropy()
+    loss = -(logp + ent).mean()
+    loss.backward()
+    return float(loss.detach()), {k: v.grad.detach().numpy().copy() for k, v in P.items()}
+
+
+# ----------------------------------------------------------------------------------------------
+# SVGD direction (config C4): inference.py:301-324, vectorised.
+# ----------------------------------------------------------------------------------------------
+def svgd_direction(theta, grad, dtype=np.float64):
+    """theta, grad: [n,d] (grad = d loss/d theta = -d log p).  Returns (new_grad [n,d], bandwidth).
+
+    update_bandwidth (inference.py:317-324): bw = 2*median_{i!=j}(||theta_i-theta_j||)^2 / ln n
+    kernel (:284,304-307):   K_ij = exp(-||theta_i-theta_j||^2 / (2 bw))
+    interaction (:308-311):  I[j][i] = -(theta_i - theta_j) K[j][i] / bw  (indexed [index2][index1])
+    new grad (:312-315):     g_i = sum_j K[i][j] grad_j + I[i][j]
+                                 = (K @ grad)_i + sum_j -(theta_j - theta_i) K_ij / bw
+                                 = (K @ grad)_i + (rowsum(K)_i theta_i - (K @ theta)_i) / bw
+    (sign of the second term is the reference's, opposite to canonical SVGD; no 1/n.)
+    """
+    th = np.asarray(theta, dtype=dtype)
+    g = np.asarray(grad, dtype=dtype)
+    n = th.shape[0]
+    sq = (th * th).sum(1)
+    d2 = np.maximum(sq[:, None] + sq[None, :] - 2.0 * th @ th.T, 0.0)
+    np.fill_diagonal(d2, 0.0)
+    off = ~np.eye(n, dtype=bool)
+    dist = np.sqrt(d2[off])
+    bw = 2.0 * np.median(dist) ** 2 / np.log(n)
+    K = np.exp(-d2 / (2.0 * bw))
+    out = K @ g + (K.sum(1, keepdims=True) * th - K @ th) / bw
+    return out.astype(dtype), float(bw)
+
+
+def svgd_direction_loops(theta, grad):
+    """Literal O(n^2) loop transcription of the index pattern in inference.py:301-324 for tiny n,
+    used only to pin `svgd_direction`'s vectorised algebra (fp64 numpy)."""
+    th = np.asarray(theta, dtype=np.float64)
+    g = np.asarray(grad, dtype=np.float64)
+    n = th.shape[0]
+    dev = lambda a, b: float(((a - b) ** 2).sum())
+    dists = [math.sqrt(dev(th[i], th[j])) for i in range(n) for j in range(n) if i != j]
+    bw = 2 * np.median(dists) ** 2 / np.log(n)
+    kern = [[math.exp(-dev(th[p1], th[p2]) / (2 * bw)) for p1 in range(n)] for p2 in range(n)]
+    inter = [[-(th[p1] - th[p2]) * kern[p1][p2] / bw for p1 in range(n)] for p2 in range(n)]
+    out = np.zeros_like(th)
+    for i in range(n):
+        out[i] = sum(kern[i][j] * g[j] + inter[i][j] for j in range(n))
+    return out, float(bw)
