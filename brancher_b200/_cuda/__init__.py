@@ -1,0 +1,206 @@
+"""ctypes binding of the C-ABI library (include/brancher_cuda.h) -- the `brancher/_cuda` shim the north
+star asks for.  PyTorch is only the carrier of device memory and streams here: every compute call
+passes raw device pointers + the current CUDA stream to hand-written sm_100a kernels.
+
+There is NO CPU fallback: `lib()` raises if the shared library is missing, and every wrapper raises if
+a tensor is not a CUDA tensor.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbrancher_cuda.so")
+ABI_VERSION = 1
+
+_lib = None
+
+
+class BrancherCudaError(RuntimeError):
+    pass
+
+
+class MFVar(ctypes.Structure):
+    """struct brn_mf_var"""
+    _fields_ = [("mu", ctypes.c_void_p), ("rho", ctypes.c_void_p),
+                ("prior_loc", ctypes.c_void_p), ("prior_scale", ctypes.c_void_p),
+                ("eps", ctypes.c_void_p), ("dmu", ctypes.c_void_p), ("drho", ctypes.c_void_p),
+                ("numel", ctypes.c_int64), ("var_id", ctypes.c_uint32), ("tied", ctypes.c_int32)]
+
+
+class SampleRange(ctypes.Structure):
+    """struct brn_sample_range"""
+    _fields_ = [("s0", ctypes.c_int32), ("s_local", ctypes.c_int32), ("s_total", ctypes.c_int32),
+                ("_pad", ctypes.c_int32), ("seed", ctypes.c_uint64), ("offset", ctypes.c_uint64)]
+
+
+# name -> (restype, argtypes): every symbol include/brancher_cuda.h declares
+SYMBOLS = {
+    "brn_abi_version": (ctypes.c_int, []),
+    "brn_last_error": (ctypes.c_char_p, []),
+    "brn_last_variant": (ctypes.c_char_p, []),
+    "brn_philox_normal_fill": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint32,
+                                              ctypes.POINTER(SampleRange), ctypes.c_void_p]),
+    "brn_mf_normal_prior_entropy": (ctypes.c_int, [ctypes.POINTER(MFVar), ctypes.c_void_p, ctypes.c_void_p,
+                                                   ctypes.POINTER(SampleRange), ctypes.c_void_p, ctypes.c_void_p]),
+    "brn_bnn_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 5),
+    "brn_bnn_elbo_fwd_bwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 4 +
+                             [ctypes.POINTER(MFVar), ctypes.POINTER(SampleRange), ctypes.c_void_p, ctypes.c_size_t,
+                              ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "brn_linear_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "brn_linear_elbo_fwd_bwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
+                                               ctypes.c_int, ctypes.c_int, ctypes.POINTER(MFVar),
+                                               ctypes.POINTER(SampleRange), ctypes.c_void_p, ctypes.c_size_t,
+                                               ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+}
+
+
+def lib():
+    """Load (once) and return the C-ABI library; raise loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise BrancherCudaError(
+                "%s not found: build it with `python -m brancher_b200._cuda.build` "
+                "(brancher_b200 has no CPU fallback for the ELBO hot path)" % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        if handle.brn_abi_version() != ABI_VERSION:
+            raise BrancherCudaError("ABI mismatch: library %d, binding %d" % (handle.brn_abi_version(), ABI_VERSION))
+        _lib = handle
+    return _lib
+
+
+def _check(status, what):
+    if status != 0:
+        raise BrancherCudaError("%s failed (%d): %s" % (what, status, lib().brn_last_error().decode()))
+
+
+def last_variant():
+    return lib().brn_last_variant().decode()
+
+
+def _ptr(t, dtype=torch.float32, what="tensor"):
+    if t is None:
+        return None
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise BrancherCudaError("%s must be a CUDA tensor (no CPU fallback)" % what)
+    if t.dtype != dtype or not t.is_contiguous():
+        raise BrancherCudaError("%s must be contiguous %s, got %s contiguous=%s" % (what, dtype, t.dtype, t.is_contiguous()))
+    return t.data_ptr()
+
+
+def _stream(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+_workspaces = {}
+
+
+def _workspace(device, nbytes):
+    """Grow-only scratch buffer per device (kernels are stream-ordered on the current stream)."""
+    key = (device.type, device.index)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+class MeanFieldVar:
+    """Host-side description of one `brn_mf_var`.  mu/rho are flat views of the `<name>_loc` /
+    `<name>_scale` parameters; dmu/drho receive d loss / d param."""
+
+    def __init__(self, mu, rho, var_id, prior_loc=None, prior_scale=None, eps=None):
+        self.mu = mu.detach().reshape(-1).contiguous()
+        self.rho = rho.detach().reshape(-1).contiguous()
+        self.numel = self.mu.numel()
+        self.var_id = int(var_id)
+        self.tied = prior_loc is None
+        dev = self.mu.device
+
+        def full(p):
+            p = torch.as_tensor(p, dtype=torch.float32, device=dev)
+            return p.expand(mu.shape).reshape(-1).contiguous() if p.numel() != self.numel else p.reshape(-1).contiguous()
+
+        self.prior_loc = None if self.tied else full(prior_loc)
+        self.prior_scale = None if self.tied else full(prior_scale)
+        self.eps = None if eps is None else eps.detach().reshape(-1, self.numel).contiguous()
+        self.dmu = torch.zeros_like(self.mu)
+        self.drho = torch.zeros_like(self.rho)
+
+    def struct(self):
+        return MFVar(_ptr(self.mu, what="mu"), _ptr(self.rho, what="rho"),
+                     _ptr(self.prior_loc, what="prior_loc"), _ptr(self.prior_scale, what="prior_scale"),
+                     _ptr(self.eps, what="eps"), _ptr(self.dmu), _ptr(self.drho),
+                     self.numel, self.var_id, int(self.tied))
+
+
+def sample_range(s_total, s0=0, s_local=None, seed=0, offset=0):
+    s_local = s_total - s0 if s_local is None else s_local
+    return SampleRange(int(s0), int(s_local), int(s_total), 0, int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1))
+
+
+def _check_eps(v, r):
+    if v.eps is not None and v.eps.shape[0] != r.s_local:
+        raise BrancherCudaError("eps has %d samples, sample range has %d" % (v.eps.shape[0], r.s_local))
+
+
+def philox_normal(numel, var_id, r, device):
+    """[s_local, numel] standard normals, bit-identical to what the fused kernels generate."""
+    out = torch.empty((r.s_local, numel), dtype=torch.float32, device=device)
+    _check(lib().brn_philox_normal_fill(_ptr(out), numel, var_id, ctypes.byref(r), _stream(out.device)),
+           "brn_philox_normal_fill")
+    return out
+
+
+def mf_normal_prior_entropy(var, r, loss=None):
+    """K1a on one MeanFieldVar; accumulates into var.dmu/var.drho; returns the fp64 loss accumulator."""
+    dev = var.mu.device
+    loss = torch.zeros(1, dtype=torch.float64, device=dev) if loss is None else loss
+    _check_eps(var, r)
+    st = var.struct()
+    _check(lib().brn_mf_normal_prior_entropy(ctypes.byref(st), None, None, ctypes.byref(r),
+                                             _ptr(loss, torch.float64), _stream(dev)), "brn_mf_normal_prior_entropy")
+    return loss
+
+
+def bnn_elbo_fwd_bwd(X, y, vars4, r, with_prior=True, loss=None):
+    """K3.  X [B,P] fp32, y [B] int32, vars4 = MeanFieldVar for (weights1 [H,P], b1 [H], weights2 [C,H], b2 [C])."""
+    dev = X.device
+    B, P = X.shape
+    H = vars4[1].numel
+    C = vars4[3].numel
+    loss = torch.zeros(1, dtype=torch.float64, device=dev) if loss is None else loss
+    for v in vars4:
+        _check_eps(v, r)
+    nbytes = lib().brn_bnn_workspace_bytes(B, P, H, C, r.s_local)
+    ws = _workspace(dev, nbytes)
+    arr = (MFVar * 4)(*[v.struct() for v in vars4])
+    _check(lib().brn_bnn_elbo_fwd_bwd(_ptr(X, what="X"), _ptr(y, torch.int32, "y"), B, P, H, C, arr, ctypes.byref(r),
+                                      ws.data_ptr(), ws.numel(), int(with_prior), _ptr(loss, torch.float64),
+                                      _stream(dev)), "brn_bnn_elbo_fwd_bwd")
+    return loss
+
+
+BERNOULLI, CATEGORICAL = 0, 1
+
+
+def linear_elbo_fwd_bwd(X, y, likelihood, w, C, r, with_prior=True, loss=None):
+    """K2.  X [N,F] fp32; y [N] fp32 {0,1} (BERNOULLI, C=1) or int32 labels (CATEGORICAL); w MeanFieldVar [C,F]."""
+    dev = X.device
+    N, F = X.shape
+    loss = torch.zeros(1, dtype=torch.float64, device=dev) if loss is None else loss
+    _check_eps(w, r)
+    nbytes = lib().brn_linear_workspace_bytes(N, F, C, r.s_local)
+    ws = _workspace(dev, nbytes)
+    st = w.struct()
+    ydt = torch.float32 if likelihood == BERNOULLI else torch.int32
+    _check(lib().brn_linear_elbo_fwd_bwd(_ptr(X, what="X"), _ptr(y, ydt, "y"), likelihood, N, F, C, ctypes.byref(st),
+                                         ctypes.byref(r), ws.data_ptr(), ws.numel(), int(with_prior),
+                                         _ptr(loss, torch.float64), _stream(dev)), "brn_linear_elbo_fwd_bwd")
+    return loss

@@ -1,0 +1,243 @@
+// K3: Bayesian neural network P-H-C (tanh, Categorical likelihood) -- ELBO forward + pathwise backward.
+// See include/brancher_cuda.h (brn_bnn_elbo_fwd_bwd) for the contract and the reference lines replaced.
+//
+// Stage plan (shared by the "simt" and "tcgen05" variants; they differ in stages 2 and 4):
+//   1. noise + weight sampling          W_s = mu + softplus(rho) * eps_s                (HBM-bound)
+//   2. layer-1 GEMM per sample          pre_s[B,H] = X[B,P] . W1_s^T[P,H]               (GEMM)
+//   3. "mid": tanh, layer 2, log-softmax, ll, and backward down to d pre_s              (HBM-bound)
+//   4. layer-1 weight gradient          dW1_s[H,P] = dpre_s^T[H,B] . X[B,P]             (GEMM)
+//   5. sample-axis reduction + K1a      gw = sum_s dW_s, gwe = sum_s dW_s*eps_s, prior/entropy, chain rule
+#include "meanfield.cuh"
+#include "sgemm.cuh"
+
+namespace brn {
+
+constexpr int BNN_MAXC = 16;
+
+struct BnnLayout {
+    int B, P, H, C;
+    int64_t oW1, ob1, oW2, ob2, numel, ldw;
+    __host__ __device__ BnnLayout(int B_, int P_, int H_, int C_) : B(B_), P(P_), H(H_), C(C_) {
+        oW1 = 0;
+        ob1 = (int64_t)H * P;
+        oW2 = ob1 + H;
+        ob2 = oW2 + (int64_t)C * H;
+        numel = ob2 + C;
+        ldw = (numel + 3) / 4 * 4;
+    }
+};
+
+// One CTA = R rows of the batch for one sample; one thread per row.
+// pre (in):  X.W1_s^T without bias;  pre (out): d ll_s / d pre.
+__global__ void bnn_mid_kernel(float* __restrict__ pre, const float* __restrict__ W, float* __restrict__ dW,
+                               const int32_t* __restrict__ y, BnnLayout L, int R, float inv_S,
+                               double* __restrict__ loss) {
+    extern __shared__ float sm[];
+    const int H = L.H, C = L.C, B = L.B, HP = H + 1;
+    float* tile = sm;                    // [R][H+1]
+    float* W2s = tile + (size_t)R * HP;  // [C][H]
+    float* b1s = W2s + C * H;            // [H]
+    float* b2s = b1s + H;                // [C]
+    float* das = b2s + C;                // [R][C]
+    __shared__ double red[32];
+
+    const int s = blockIdx.y, b0 = blockIdx.x * R, t = threadIdx.x, nt = blockDim.x;
+    const float* Ws = W + (int64_t)s * L.ldw;
+    float* dWs = dW + (int64_t)s * L.ldw;
+    float* pre_s = pre + (int64_t)s * B * H;
+
+    for (int idx = t; idx < R * H; idx += nt) {
+        int r = idx / H, h = idx - r * H;
+        tile[r * HP + h] = (b0 + r < B) ? pre_s[(int64_t)(b0 + r) * H + h] : 0.f;
+    }
+    for (int idx = t; idx < C * H; idx += nt) W2s[idx] = Ws[L.oW2 + idx];
+    for (int idx = t; idx < H; idx += nt) b1s[idx] = Ws[L.ob1 + idx];
+    for (int idx = t; idx < C; idx += nt) b2s[idx] = Ws[L.ob2 + idx];
+    __syncthreads();
+
+    const int r = t;
+    const bool valid = (r < R) && (b0 + r < B);
+    float da[BNN_MAXC];
+    float ll = 0.f;
+    if (valid) {
+        float a[BNN_MAXC];
+#pragma unroll
+        for (int c = 0; c < BNN_MAXC; ++c) a[c] = 0.f;
+        for (int h = 0; h < H; ++h) {
+            float v = tanhf(tile[r * HP + h] + b1s[h]);
+            tile[r * HP + h] = v;
+#pragma unroll
+            for (int c = 0; c < BNN_MAXC; ++c)
+                if (c < C) a[c] = __fmaf_rn(W2s[c * H + h], v, a[c]);
+        }
+        float m = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < BNN_MAXC; ++c)
+            if (c < C) { a[c] += b2s[c]; m = fmaxf(m, a[c]); }
+        float se = 0.f;
+#pragma unroll
+        for (int c = 0; c < BNN_MAXC; ++c)
+            if (c < C) se += expf(a[c] - m);
+        const float lse = m + logf(se);
+        const int label = y[b0 + r];
+#pragma unroll
+        for (int c = 0; c < BNN_MAXC; ++c) {
+            if (c < C) {
+                float p = expf(a[c] - lse);
+                da[c] = (c == label ? 1.f : 0.f) - p;      // d ll / d a_c
+                if (c == label) ll = a[c] - lse;
+            } else da[c] = 0.f;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < BNN_MAXC; ++c) da[c] = 0.f;
+    }
+    if (r < R)
+        for (int c = 0; c < C; ++c) das[r * C + c] = da[c];
+    __syncthreads();
+
+    // dW2_s[c,h] += sum_r da_r[c] * h_r[h] ;  db2_s[c] += sum_r da_r[c]
+    for (int o = t; o < C * H; o += nt) {
+        int c = o / H, h = o - c * H;
+        float acc = 0.f;
+        for (int rr = 0; rr < R; ++rr) acc = __fmaf_rn(das[rr * C + c], tile[rr * HP + h], acc);
+        atomicAdd(&dWs[L.oW2 + o], acc);
+    }
+    for (int c = t; c < C; c += nt) {
+        float acc = 0.f;
+        for (int rr = 0; rr < R; ++rr) acc += das[rr * C + c];
+        atomicAdd(&dWs[L.ob2 + c], acc);
+    }
+    __syncthreads();
+
+    if (r < R) {
+        for (int h = 0; h < H; ++h) {
+            float hv = tile[r * HP + h];
+            float dh = 0.f;
+#pragma unroll
+            for (int c = 0; c < BNN_MAXC; ++c)
+                if (c < C) dh = __fmaf_rn(da[c], W2s[c * H + h], dh);
+            tile[r * HP + h] = dh * (1.f - hv * hv);
+        }
+    }
+    __syncthreads();
+
+    for (int h = t; h < H; h += nt) {
+        float acc = 0.f;
+        for (int rr = 0; rr < R; ++rr) acc += tile[rr * HP + h];
+        atomicAdd(&dWs[L.ob1 + h], acc);
+    }
+    for (int idx = t; idx < R * H; idx += nt) {
+        int rr = idx / H, h = idx - rr * H;
+        if (b0 + rr < B) pre_s[(int64_t)(b0 + rr) * H + h] = tile[rr * HP + h];
+    }
+    double tot = block_sum<double>((double)ll, red);
+    if (t == 0) atomicAdd(loss, -tot * (double)inv_S);
+}
+
+static size_t bnn_mid_smem(int R, int H, int C) {
+    return sizeof(float) * ((size_t)R * (H + 1) + (size_t)C * H + H + C + (size_t)R * C);
+}
+
+struct BnnWorkspace {
+    float *eps, *W, *dW, *pre, *gw, *gwe;
+    size_t bytes;
+    BnnWorkspace(void* base, const BnnLayout& L, int S) {
+        size_t off = 0;
+        auto take = [&](size_t nfloat) {
+            float* p = base ? reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off) : nullptr;
+            off += (nfloat * sizeof(float) + 255) / 256 * 256;
+            return p;
+        };
+        eps = take((size_t)S * L.ldw);
+        W = take((size_t)S * L.ldw);
+        dW = take((size_t)S * L.ldw);
+        pre = take((size_t)S * L.B * L.H);
+        gw = take(L.ldw);
+        gwe = take(L.ldw);
+        bytes = off;
+    }
+};
+
+}  // namespace brn
+
+using namespace brn;
+
+extern "C" size_t brn_bnn_workspace_bytes(int B, int P, int H, int C, int s_local) {
+    if (B <= 0 || P <= 0 || H <= 0 || C <= 0 || s_local < 0) return 0;
+    BnnLayout L(B, P, H, C);
+    return BnnWorkspace(nullptr, L, s_local).bytes;
+}
+
+extern "C" int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int P, int H, int C,
+                                    const brn_mf_var vars[4], const brn_sample_range* r, void* workspace,
+                                    size_t workspace_bytes, int with_prior, double* loss, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    BRN_CHECK_ARG(X && y && vars && r && loss, "brn_bnn_elbo_fwd_bwd: NULL pointer");
+    BRN_CHECK_ARG(B > 0 && P > 0 && H > 0 && C > 0, "brn_bnn_elbo_fwd_bwd: bad shape B=%d P=%d H=%d C=%d", B, P, H, C);
+    BRN_CHECK_ARG(C <= BNN_MAXC, "brn_bnn_elbo_fwd_bwd: C=%d exceeds the supported maximum %d", C, BNN_MAXC);
+    BRN_CHECK_ARG(r->s_local >= 0 && r->s_total > 0 && r->s0 >= 0 && r->s0 + r->s_local <= r->s_total,
+                  "bad sample range s0=%d s_local=%d s_total=%d", r->s0, r->s_local, r->s_total);
+    BnnLayout L(B, P, H, C);
+    const int64_t numels[4] = {(int64_t)H * P, H, (int64_t)C * H, C};
+    const int64_t offs[4] = {L.oW1, L.ob1, L.oW2, L.ob2};
+    for (int v = 0; v < 4; ++v) {
+        BRN_CHECK_ARG(vars[v].numel == numels[v], "vars[%d].numel=%lld, expected %lld", v, (long long)vars[v].numel,
+                      (long long)numels[v]);
+        BRN_CHECK_ARG(vars[v].mu && vars[v].rho && vars[v].dmu && vars[v].drho, "vars[%d]: NULL parameter pointer", v);
+        BRN_CHECK_ARG(!with_prior || vars[v].tied || (vars[v].prior_loc && vars[v].prior_scale),
+                      "vars[%d]: prior_loc/prior_scale required when not tied", v);
+    }
+    const int S = r->s_local;
+    if (S == 0) return 0;
+    BnnWorkspace ws(workspace, L, S);
+    BRN_CHECK_ARG(workspace && workspace_bytes >= ws.bytes, "workspace too small: %zu < %zu", workspace_bytes, ws.bytes);
+    set_variant("simt");
+
+    // 1. noise + weights
+    const float* eps_ptr[4];
+    int64_t eps_ld[4];
+    for (int v = 0; v < 4; ++v) {
+        if (vars[v].eps) {
+            eps_ptr[v] = vars[v].eps;
+            eps_ld[v] = numels[v];
+        } else {
+            if (int e = launch_philox_fill(ws.eps + offs[v], L.ldw, numels[v], vars[v].var_id, *r, stream)) return e;
+            eps_ptr[v] = ws.eps + offs[v];
+            eps_ld[v] = L.ldw;
+        }
+        if (int e = launch_sample_weights(vars[v].mu, vars[v].rho, eps_ptr[v], eps_ld[v], ws.W + offs[v], L.ldw,
+                                          numels[v], S, stream))
+            return e;
+    }
+    // 2. pre_s = X . W1_s^T
+    if (int e = launch_sgemm_batched<true, true>(X, P, 0, ws.W + L.oW1, P, L.ldw, ws.pre, H, (int64_t)B * H, B, H, P, S,
+                                                 stream))
+        return e;
+    // 3. mid
+    BRN_CUDA_OK(cudaMemset2DAsync(ws.dW + L.ob1, L.ldw * sizeof(float), 0, (L.numel - L.ob1) * sizeof(float), S, stream));
+    {
+        int R = 128;
+        while (R > 32 && bnn_mid_smem(R, H, C) > 200 * 1024) R -= 32;
+        size_t smem = bnn_mid_smem(R, H, C);
+        BRN_CHECK_ARG(smem <= 220 * 1024, "brn_bnn_elbo_fwd_bwd: hidden width H=%d too large for the mid kernel", H);
+        BRN_CUDA_OK(cudaFuncSetAttribute(bnn_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((B + R - 1) / R, S);
+        bnn_mid_kernel<<<grid, R, smem, stream>>>(ws.pre, ws.W, ws.dW, y, L, R, 1.0f / (float)r->s_total, loss);
+        BRN_LAUNCH_OK("bnn_mid_kernel");
+    }
+    // 4. dW1_s = dpre_s^T . X
+    if (int e = launch_sgemm_batched<false, false>(ws.pre, H, (int64_t)B * H, X, P, 0, ws.dW + L.oW1, P, L.ldw, H, P, B,
+                                                   S, stream))
+        return e;
+    // 5. reduce over samples + prior/entropy + chain rule
+    for (int v = 0; v < 4; ++v) {
+        if (int e = launch_reduce_over_samples(ws.dW + offs[v], L.ldw, eps_ptr[v], eps_ld[v], ws.gw + offs[v],
+                                               ws.gwe + offs[v], numels[v], S, stream))
+            return e;
+        if (int e = launch_mf_finalize(vars[v], eps_ptr[v], eps_ld[v], ws.gw + offs[v], ws.gwe + offs[v], *r, with_prior,
+                                       loss, stream))
+            return e;
+    }
+    return 0;
+}

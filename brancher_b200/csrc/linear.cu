@@ -1,0 +1,292 @@
+// K2: (multi-class) Bayesian logistic regression -- ELBO forward + pathwise backward in ONE pass over X.
+// See include/brancher_cuda.h (brn_linear_elbo_fwd_bwd).
+//
+// "Columns" j = (sample s, class c): Wmat [J = S*C, F].  A CTA owns one tile of 128 columns (whole
+// samples only) and walks a contiguous group of 128-row tiles of X:
+//   phase 1   L[128 rows, 128 cols]   = Xtile . Wtile^T                       (K = F)
+//   phase 2   ll += log-lik(L, y) ; dL = d ll / d L                            (registers / smem)
+//   phase 3   dWacc[128 cols, F]     += dL^T . Xtile                           (K = 128 rows)
+// dWacc lives in registers for the CTA's whole row group and is flushed once with atomics, so X is read
+// from HBM once per column tile (and those re-reads are L2 hits: column tiles of one row group are
+// scheduled together) and nothing of size S x N ever reaches memory.
+#include "meanfield.cuh"
+
+namespace brn {
+
+constexpr int LN_T = 128;            // tile edge (rows, columns, max features)
+constexpr int LN_LD = LN_T + 4;      // smem leading dimension (keeps float4 alignment)
+
+struct LinearArgs {
+    const float* X; const void* y; int64_t N; int F, C, S;
+    const float* W; float* dW;       // [S*C, F] contiguous
+    int tiles_per_group; int64_t n_row_tiles;
+    float inv_S; double* loss;
+};
+
+template <int LIK>   // 0: Bernoulli/Binomial(1) with float y, 1: Categorical with int32 labels
+__global__ void __launch_bounds__(256, 1) linear_fused_kernel(LinearArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    float (*Xs)[LN_LD] = reinterpret_cast<float (*)[LN_LD]>(sm);                       // [row][f]
+    float (*Ws)[LN_LD] = reinterpret_cast<float (*)[LN_LD]>(sm + LN_T * LN_LD);        // [f][col]
+    float (*Ls)[LN_LD] = reinterpret_cast<float (*)[LN_LD]>(sm + 2 * LN_T * LN_LD);    // [row][col]
+    float* ys = sm + 3 * LN_T * LN_LD;                                                 // [row] (bit-cast for labels)
+    __shared__ double red[32];
+
+    const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+    const int F = a.F, C = a.C;
+    const int spc = LN_T / C;                 // whole samples per column tile
+    const int ncols = spc * C;
+    const int s_base = blockIdx.x * spc;
+    const int64_t J = (int64_t)a.S * C, j0 = (int64_t)s_base * C;
+    const bool xvec = (F % 4 == 0) && ((uintptr_t)a.X % 16 == 0);
+
+    // W tile, transposed to [f][col]; zero outside
+    for (int idx = t; idx < LN_T * LN_T; idx += 256) {
+        int col = idx >> 7, f = idx & 127;
+        float v = 0.f;
+        if (col < ncols && j0 + col < J && f < F) v = a.W[(j0 + col) * F + f];
+        Ws[f][col] = v;
+    }
+
+    float acc2[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc2[i][j] = 0.f;
+    double ll_thread = 0.0;
+
+    const int64_t tile_begin = (int64_t)blockIdx.y * a.tiles_per_group;
+    const int64_t tile_end = min(a.n_row_tiles, tile_begin + a.tiles_per_group);
+    for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
+        const int64_t r0 = tile * LN_T;
+        __syncthreads();   // previous tile's phase 3 done with Xs / Ls
+        // ---- load X tile [128][F] (zero padded to 128 features / N rows)
+        if (xvec) {
+            for (int idx = t; idx < LN_T * (LN_T / 4); idx += 256) {
+                int row = idx >> 5, f4 = (idx & 31) * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r0 + row < a.N && f4 < F) v = *reinterpret_cast<const float4*>(a.X + (r0 + row) * F + f4);
+                *reinterpret_cast<float4*>(&Xs[row][f4]) = v;
+            }
+        } else {
+            for (int idx = t; idx < LN_T * LN_T; idx += 256) {
+                int row = idx >> 7, f = idx & 127;
+                Xs[row][f] = (r0 + row < a.N && f < F) ? a.X[(r0 + row) * F + f] : 0.f;
+            }
+        }
+        if (t < LN_T) {
+            float v = 0.f;
+            if (r0 + t < a.N) {
+                if (LIK == 0) v = reinterpret_cast<const float*>(a.y)[r0 + t];
+                else v = __int_as_float(reinterpret_cast<const int32_t*>(a.y)[r0 + t]);
+            }
+            ys[t] = v;
+        }
+        __syncthreads();
+
+        // ---- phase 1: logits
+        float acc[8][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        const int k4n = (F + 3) >> 2;
+        for (int k4 = 0; k4 < k4n; ++k4) {
+            float4 xa[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                int row = (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+                xa[i] = *reinterpret_cast<const float4*>(&Xs[row][k4 * 4]);
+            }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                float4 b0 = *reinterpret_cast<const float4*>(&Ws[k4 * 4 + kk][tx * 4]);
+                float4 b1 = *reinterpret_cast<const float4*>(&Ws[k4 * 4 + kk][64 + tx * 4]);
+                float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float av = kk == 0 ? xa[i].x : kk == 1 ? xa[i].y : kk == 2 ? xa[i].z : xa[i].w;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = __fmaf_rn(av, bv[j], acc[i][j]);
+                }
+            }
+        }
+
+        // ---- phase 2: log-likelihood and d ll / d logit
+        float ll_tile = 0.f;
+        if (LIK == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                int row = (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+                bool rv = r0 + row < a.N;
+                float yv = ys[row];
+                float d[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    int col = (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+                    bool ok = rv && col < ncols && (j0 + col) < J;
+                    float l = acc[i][j];
+                    float sp = log1pexpf(l);
+                    ll_tile += ok ? __fmaf_rn(yv, l, -sp) : 0.f;
+                    d[j] = ok ? yv - sigmoidf(l) : 0.f;
+                }
+                *reinterpret_cast<float4*>(&Ls[row][tx * 4]) = make_float4(d[0], d[1], d[2], d[3]);
+                *reinterpret_cast<float4*>(&Ls[row][64 + tx * 4]) = make_float4(d[4], d[5], d[6], d[7]);
+            }
+            __syncthreads();
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                int row = (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+                *reinterpret_cast<float4*>(&Ls[row][tx * 4]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+                *reinterpret_cast<float4*>(&Ls[row][64 + tx * 4]) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+            }
+            __syncthreads();
+            for (int item = t; item < LN_T * spc; item += 256) {
+                int sl = item % spc, row = item / spc;
+                float* lg = &Ls[row][sl * C];
+                bool ok = (r0 + row < a.N) && (s_base + sl < a.S);
+                if (!ok) {
+                    for (int c = 0; c < C; ++c) lg[c] = 0.f;
+                    continue;
+                }
+                int label = __float_as_int(ys[row]);
+                float m = -INFINITY;
+                for (int c = 0; c < C; ++c) m = fmaxf(m, lg[c]);
+                float se = 0.f;
+                for (int c = 0; c < C; ++c) se += expf(lg[c] - m);
+                float lse = m + logf(se);
+                for (int c = 0; c < C; ++c) {
+                    float l = lg[c];
+                    if (c == label) ll_tile += l - lse;
+                    lg[c] = (c == label ? 1.f : 0.f) - expf(l - lse);
+                }
+            }
+            // columns beyond ncols (tile padding) must not contribute to phase 3
+            if (ncols < LN_T)
+                for (int idx = t; idx < LN_T * (LN_T - ncols); idx += 256) {
+                    int row = idx / (LN_T - ncols), col = ncols + idx % (LN_T - ncols);
+                    Ls[row][col] = 0.f;
+                }
+            __syncthreads();
+        }
+        ll_thread += (double)ll_tile;
+
+        // ---- phase 3: dW[col, f] += sum_row dL[row, col] * X[row, f]
+#pragma unroll 4
+        for (int row = 0; row < LN_T; ++row) {
+            float4 a0 = *reinterpret_cast<const float4*>(&Ls[row][ty * 4]);
+            float4 a1 = *reinterpret_cast<const float4*>(&Ls[row][64 + ty * 4]);
+            float4 b0 = *reinterpret_cast<const float4*>(&Xs[row][tx * 4]);
+            float4 b1 = *reinterpret_cast<const float4*>(&Xs[row][64 + tx * 4]);
+            float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc2[i][j] = __fmaf_rn(av[i], bv[j], acc2[i][j]);
+        }
+    }
+
+    // ---- flush
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int col = (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        if (col >= ncols || j0 + col >= J) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int f = (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+            if (f < F) atomicAdd(&a.dW[(j0 + col) * F + f], acc2[i][j]);
+        }
+    }
+    double tot = block_sum<double>(ll_thread, red);
+    if (t == 0) atomicAdd(a.loss, -tot * (double)a.inv_S);
+}
+
+struct LinearWorkspace {
+    float *eps, *W, *dW, *gw, *gwe;
+    size_t bytes;
+    LinearWorkspace(void* base, int64_t numel, int S) {
+        size_t off = 0;
+        auto take = [&](size_t nfloat) {
+            float* p = base ? reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off) : nullptr;
+            off += (nfloat * sizeof(float) + 255) / 256 * 256;
+            return p;
+        };
+        eps = take((size_t)S * numel);
+        W = take((size_t)S * numel);
+        dW = take((size_t)S * numel);
+        gw = take(numel);
+        gwe = take(numel);
+        bytes = off;
+    }
+};
+
+}  // namespace brn
+
+using namespace brn;
+
+extern "C" size_t brn_linear_workspace_bytes(int64_t N, int F, int C, int s_local) {
+    if (N < 0 || F <= 0 || C <= 0 || s_local < 0) return 0;
+    return LinearWorkspace(nullptr, (int64_t)C * F, s_local).bytes;
+}
+
+extern "C" int brn_linear_elbo_fwd_bwd(const float* X, const void* y, int likelihood, int64_t N, int F, int C,
+                                       const brn_mf_var* w, const brn_sample_range* r, void* workspace,
+                                       size_t workspace_bytes, int with_prior, double* loss, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    BRN_CHECK_ARG(w && r && loss, "brn_linear_elbo_fwd_bwd: NULL pointer");
+    BRN_CHECK_ARG(N >= 0 && F > 0 && C > 0, "brn_linear_elbo_fwd_bwd: bad shape N=%lld F=%d C=%d", (long long)N, F, C);
+    BRN_CHECK_ARG(N == 0 || (X && y), "brn_linear_elbo_fwd_bwd: NULL data pointer");
+    BRN_CHECK_ARG(F <= LN_T, "brn_linear_elbo_fwd_bwd: F=%d exceeds the supported maximum %d", F, LN_T);
+    BRN_CHECK_ARG(C <= LN_T, "brn_linear_elbo_fwd_bwd: C=%d exceeds the supported maximum %d", C, LN_T);
+    BRN_CHECK_ARG(likelihood == 0 || likelihood == 1, "brn_linear_elbo_fwd_bwd: unknown likelihood %d", likelihood);
+    BRN_CHECK_ARG(likelihood == 1 || C == 1, "Bernoulli/Binomial likelihood needs C == 1 (got %d)", C);
+    BRN_CHECK_ARG(r->s_local >= 0 && r->s_total > 0 && r->s0 >= 0 && r->s0 + r->s_local <= r->s_total,
+                  "bad sample range s0=%d s_local=%d s_total=%d", r->s0, r->s_local, r->s_total);
+    const int64_t numel = (int64_t)C * F;
+    BRN_CHECK_ARG(w->numel == numel, "w->numel=%lld, expected C*F=%lld", (long long)w->numel, (long long)numel);
+    BRN_CHECK_ARG(w->mu && w->rho && w->dmu && w->drho, "w: NULL parameter pointer");
+    BRN_CHECK_ARG(!with_prior || w->tied || (w->prior_loc && w->prior_scale), "prior_loc/prior_scale required when not tied");
+    const int S = r->s_local;
+    if (S == 0) return 0;
+    LinearWorkspace ws(workspace, numel, S);
+    BRN_CHECK_ARG(workspace && workspace_bytes >= ws.bytes, "workspace too small: %zu < %zu", workspace_bytes, ws.bytes);
+    set_variant("simt");
+
+    const float* eps = w->eps;
+    if (!eps) {
+        if (int e = launch_philox_fill(ws.eps, numel, numel, w->var_id, *r, stream)) return e;
+        eps = ws.eps;
+    }
+    if (int e = launch_sample_weights(w->mu, w->rho, eps, numel, ws.W, numel, numel, S, stream)) return e;
+    BRN_CUDA_OK(cudaMemsetAsync(ws.dW, 0, sizeof(float) * (size_t)S * numel, stream));
+    if (N > 0) {
+        LinearArgs a;
+        a.X = X; a.y = y; a.N = N; a.F = F; a.C = C; a.S = S; a.W = ws.W; a.dW = ws.dW;
+        a.inv_S = 1.0f / (float)r->s_total; a.loss = loss;
+        const int spc = LN_T / C;
+        const int col_tiles = (S + spc - 1) / spc;
+        a.n_row_tiles = (N + LN_T - 1) / LN_T;
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        int64_t groups = sms / col_tiles;
+        if (groups < 1) groups = 1;
+        if (groups > a.n_row_tiles) groups = a.n_row_tiles;
+        a.tiles_per_group = (int)((a.n_row_tiles + groups - 1) / groups);
+        groups = (a.n_row_tiles + a.tiles_per_group - 1) / a.tiles_per_group;
+        const size_t smem = sizeof(float) * (3 * LN_T * LN_LD + LN_T);
+        dim3 grid(col_tiles, (unsigned)groups);
+        if (likelihood == 0) {
+            BRN_CUDA_OK(cudaFuncSetAttribute(linear_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            linear_fused_kernel<0><<<grid, 256, smem, stream>>>(a);
+        } else {
+            BRN_CUDA_OK(cudaFuncSetAttribute(linear_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            linear_fused_kernel<1><<<grid, 256, smem, stream>>>(a);
+        }
+        BRN_LAUNCH_OK("linear_fused_kernel");
+    }
+    if (int e = launch_reduce_over_samples(ws.dW, numel, eps, numel, ws.gw, ws.gwe, numel, S, stream)) return e;
+    return launch_mf_finalize(*w, eps, numel, ws.gw, ws.gwe, *r, with_prior, loss, stream);
+}

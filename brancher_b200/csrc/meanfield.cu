@@ -1,0 +1,190 @@
+// K1a: mean-field Normal sampling, prior log-prob, analytic entropy and their pathwise gradients.
+// HBM-bound elementwise + sample-axis reduction; one thread owns 4 consecutive elements (one Philox
+// call) and walks the local samples, so every global access is coalesced across the warp.
+#include "meanfield.cuh"
+
+namespace brn {
+
+__global__ void philox_fill_kernel(float* __restrict__ out, int64_t ld, int64_t numel, uint32_t var_id,
+                                   brn_sample_range r) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int s = blockIdx.y;
+    if (q * 4 >= numel) return;
+    Normal4 n = philox_normal4(r.seed, r.offset, var_id, (uint32_t)(r.s0 + s), (uint32_t)q);
+    float* o = out + (int64_t)s * ld + q * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (q * 4 + j < numel) o[j] = n.v[j];
+}
+
+int launch_philox_fill(float* out, int64_t ld, int64_t numel, uint32_t var_id, const brn_sample_range& r,
+                       cudaStream_t stream) {
+    if (numel <= 0 || r.s_local <= 0) return 0;
+    int64_t quads = (numel + 3) / 4;
+    dim3 grid((unsigned)((quads + 255) / 256), (unsigned)r.s_local);
+    philox_fill_kernel<<<grid, 256, 0, stream>>>(out, ld, numel, var_id, r);
+    BRN_LAUNCH_OK("philox_fill_kernel");
+    return 0;
+}
+
+__global__ void sample_weights_kernel(const float* __restrict__ mu, const float* __restrict__ rho,
+                                      const float* __restrict__ eps, int64_t lde, float* __restrict__ W, int64_t ldw,
+                                      int64_t numel) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int s = blockIdx.y;
+    if (i >= numel) return;
+    float sg = softplusf(rho[i]);
+    W[(int64_t)s * ldw + i] = __fmaf_rn(sg, eps[(int64_t)s * lde + i], mu[i]);
+}
+
+int launch_sample_weights(const float* mu, const float* rho, const float* eps, int64_t lde, float* W, int64_t ldw,
+                          int64_t numel, int s_local, cudaStream_t stream) {
+    if (numel <= 0 || s_local <= 0) return 0;
+    dim3 grid((unsigned)((numel + 255) / 256), (unsigned)s_local);
+    sample_weights_kernel<<<grid, 256, 0, stream>>>(mu, rho, eps, lde, W, ldw, numel);
+    BRN_LAUNCH_OK("sample_weights_kernel");
+    return 0;
+}
+
+// One thread per quad of elements; loops over the local samples.
+__global__ void __launch_bounds__(256)
+mf_finalize_kernel(brn_mf_var v, const float* __restrict__ eps, int64_t lde, const float* __restrict__ gw,
+                   const float* __restrict__ gwe, brn_sample_range r, int with_prior, double* __restrict__ loss) {
+    __shared__ double red[32];
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double elbo_thread = 0.0;
+    if (q * 4 < v.numel) {
+        const int nvalid = (int)min((int64_t)4, v.numel - q * 4);
+        float mu[4], sg[4], a[4], inv_b2[4], lp[4], dmu_acc[4], dsg_acc[4], rho[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int64_t i = q * 4 + j;
+            bool ok = j < nvalid;
+            mu[j] = ok ? v.mu[i] : 0.f;
+            rho[j] = ok ? v.rho[i] : 0.f;
+            sg[j] = softplusf(rho[j]);
+            a[j] = (ok && !v.tied) ? v.prior_loc[i] : 0.f;
+            float b = (ok && !v.tied) ? v.prior_scale[i] : 1.f;
+            inv_b2[j] = 1.0f / (b * b);
+            lp[j] = 0.f; dmu_acc[j] = 0.f; dsg_acc[j] = 0.f;
+        }
+        if (with_prior) {
+            for (int s = 0; s < r.s_local; ++s) {
+                float e[4];
+                if (eps) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) e[j] = j < nvalid ? eps[(int64_t)s * lde + q * 4 + j] : 0.f;
+                } else {
+                    Normal4 n = philox_normal4(r.seed, r.offset, v.var_id, (uint32_t)(r.s0 + s), (uint32_t)q);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) e[j] = n.v[j];
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (v.tied) {
+                        // log N(w; mu, sigma) with w = mu + sigma*eps  ==  -eps^2/2 - log sigma - c ;
+                        // d/dmu and the eps-dependent part of d/dsigma cancel identically.
+                        lp[j] += -0.5f * e[j] * e[j];
+                    } else {
+                        float d = __fmaf_rn(sg[j], e[j], mu[j]) - a[j];
+                        float gwp = -d * inv_b2[j];            // d logp / d w
+                        lp[j] += 0.5f * d * gwp;               // -d^2 / (2 b^2)
+                        dmu_acc[j] += gwp;
+                        dsg_acc[j] += gwp * e[j];
+                    }
+                }
+            }
+        }
+        const float inv_S = 1.0f / (float)r.s_total;
+        const float frac = (float)r.s_local * inv_S;   // share of the per-sample constants owned by this rank
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j >= nvalid) continue;
+            int64_t i = q * 4 + j;
+            float dE_dmu = 0.f, dE_dsg = 0.f;
+            if (with_prior) {
+                float log_sg = logf(sg[j]);
+                float entropy = 0.5f + BRN_HALF_LOG_2PI + log_sg;
+                float lp_const = v.tied ? (-log_sg - BRN_HALF_LOG_2PI)
+                                        : (-logf(v.prior_scale[i]) - BRN_HALF_LOG_2PI);
+                elbo_thread += (double)(lp[j] * inv_S) + (double)(frac * (lp_const + entropy));
+                dE_dmu = dmu_acc[j] * inv_S;
+                // tied: prior -1/sigma and entropy +1/sigma cancel
+                dE_dsg = v.tied ? 0.f : (dsg_acc[j] * inv_S + frac / sg[j]);
+            }
+            if (gw) dE_dmu += gw[i] * inv_S;
+            if (gwe) dE_dsg += gwe[i] * inv_S;
+            v.dmu[i] += -dE_dmu;
+            v.drho[i] += -dE_dsg * sigmoidf(rho[j]);
+        }
+    }
+    double tot = block_sum<double>(elbo_thread, red);
+    if (threadIdx.x == 0 && with_prior) atomicAdd(loss, -tot);
+}
+
+int launch_mf_finalize(const brn_mf_var& var, const float* eps, int64_t lde, const float* gw, const float* gwe,
+                       const brn_sample_range& r, int with_prior, double* loss, cudaStream_t stream) {
+    if (var.numel <= 0) return 0;
+    if (!eps && var.eps) { eps = var.eps; lde = var.numel; }
+    int64_t quads = (var.numel + 3) / 4;
+    unsigned grid = (unsigned)((quads + 255) / 256);
+    mf_finalize_kernel<<<grid, 256, 0, stream>>>(var, eps, lde, gw, gwe, r, with_prior, loss);
+    BRN_LAUNCH_OK("mf_finalize_kernel");
+    return 0;
+}
+
+__global__ void __launch_bounds__(256)
+reduce_over_samples_kernel(const float* __restrict__ dW, int64_t ld, const float* __restrict__ eps, int64_t lde,
+                           float* __restrict__ gw, float* __restrict__ gwe, int64_t numel, int s_local) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= numel) return;
+    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+    int s = 0;
+    for (; s + 1 < s_local; s += 2) {
+        float d0 = dW[(int64_t)s * ld + i], d1 = dW[(int64_t)(s + 1) * ld + i];
+        float e0 = eps[(int64_t)s * lde + i], e1 = eps[(int64_t)(s + 1) * lde + i];
+        a0 += d0; a1 += d1;
+        b0 = __fmaf_rn(d0, e0, b0); b1 = __fmaf_rn(d1, e1, b1);
+    }
+    if (s < s_local) {
+        float d0 = dW[(int64_t)s * ld + i], e0 = eps[(int64_t)s * lde + i];
+        a0 += d0; b0 = __fmaf_rn(d0, e0, b0);
+    }
+    gw[i] = a0 + a1;
+    gwe[i] = b0 + b1;
+}
+
+int launch_reduce_over_samples(const float* dW, int64_t ld, const float* eps, int64_t lde, float* gw, float* gwe,
+                               int64_t numel, int s_local, cudaStream_t stream) {
+    if (numel <= 0) return 0;
+    unsigned grid = (unsigned)((numel + 255) / 256);
+    reduce_over_samples_kernel<<<grid, 256, 0, stream>>>(dW, ld, eps, lde, gw, gwe, numel, s_local);
+    BRN_LAUNCH_OK("reduce_over_samples_kernel");
+    return 0;
+}
+
+}  // namespace brn
+
+using namespace brn;
+
+static int check_range(const brn_sample_range* r) {
+    BRN_CHECK_ARG(r != nullptr, "sample range is NULL");
+    BRN_CHECK_ARG(r->s_local >= 0 && r->s_total > 0 && r->s0 >= 0 && r->s0 + r->s_local <= r->s_total,
+                  "bad sample range s0=%d s_local=%d s_total=%d", r->s0, r->s_local, r->s_total);
+    return 0;
+}
+
+extern "C" int brn_philox_normal_fill(float* out, int64_t numel, uint32_t var_id, const brn_sample_range* r,
+                                      void* stream) {
+    if (check_range(r)) return -1;
+    BRN_CHECK_ARG(out != nullptr && numel >= 0, "brn_philox_normal_fill: bad output");
+    return launch_philox_fill(out, numel, numel, var_id, *r, (cudaStream_t)stream);
+}
+
+extern "C" int brn_mf_normal_prior_entropy(const brn_mf_var* var, const float* lik_gw, const float* lik_gwe,
+                                           const brn_sample_range* r, double* loss, void* stream) {
+    if (check_range(r)) return -1;
+    BRN_CHECK_ARG(var && var->mu && var->rho && var->dmu && var->drho && loss, "brn_mf_normal_prior_entropy: NULL pointer");
+    BRN_CHECK_ARG(var->tied || (var->prior_loc && var->prior_scale), "prior_loc/prior_scale required when not tied");
+    return launch_mf_finalize(*var, nullptr, 0, lik_gw, lik_gwe, *r, 1, loss, (cudaStream_t)stream);
+}

@@ -1,0 +1,24 @@
+// Mean-field Normal helpers shared by the likelihood families (K2/K3): noise materialisation,
+// weight sampling and the K1a prior+entropy / gradient-finalisation stage.
+#pragma once
+#include "common.cuh"
+
+namespace brn {
+
+// out[(s - s0) * ld + i] = N(0,1) for (var_id, global sample s, element i)
+int launch_philox_fill(float* out, int64_t ld, int64_t numel, uint32_t var_id, const brn_sample_range& r,
+                       cudaStream_t stream);
+
+// W[s*ldw + i] = mu[i] + softplus(rho[i]) * eps[s*lde + i]
+int launch_sample_weights(const float* mu, const float* rho, const float* eps, int64_t lde, float* W, int64_t ldw,
+                          int64_t numel, int s_local, cudaStream_t stream);
+
+// K1a (see brn_mf_normal_prior_entropy).  eps/lde override var.eps when non-NULL (workspace noise).
+int launch_mf_finalize(const brn_mf_var& var, const float* eps, int64_t lde, const float* gw, const float* gwe,
+                       const brn_sample_range& r, int with_prior, double* loss, cudaStream_t stream);
+
+// gw[i] = sum_s dW[s*ld+i], gwe[i] = sum_s dW[s*ld+i]*eps[s*lde+i]
+int launch_reduce_over_samples(const float* dW, int64_t ld, const float* eps, int64_t lde, float* gw, float* gwe,
+                               int64_t numel, int s_local, cudaStream_t stream);
+
+}  // namespace brn

@@ -1,0 +1,117 @@
+/* brancher_cuda.h -- C ABI of the B200-native Monte-Carlo ELBO / pathwise-gradient hot path.
+ *
+ * The reference (LucaAmbrogioni/Brancher, pure Python) has NO FFI / plugin interface; its boundary for
+ * this path is the Python object API.  This header is the native boundary the Python
+ * host mirror (`brancher_b200`, same class / method names as `brancher`) binds with ctypes.  Each entry
+ * point states which reference code it replaces (paths relative to the reference repo).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (torch); fp32 unless stated; row-major.
+ *  - `stream` is a cudaStream_t (0 = legacy default stream).  Calls only enqueue work.
+ *  - return 0 on success, <0 on error; `brn_last_error()` gives the message (thread-local).
+ *  - MC samples are indexed globally: this process evaluates samples [s0, s0+S_local) of S_total, so
+ *    results are invariant to how samples are sharded over GPUs.  Every output is a
+ *    PARTIAL already scaled by 1/S_total and ACCUMULATED (+=) into caller-zeroed buffers; summing the
+ *    partials of all ranks (NCCL all-reduce, done by the host) gives loss = -ELBO and d loss/d param.
+ *  - noise: `eps` != NULL -> caller-injected standard normals, layout [S_local, numel] per variable;
+ *    `eps` == NULL -> Philox4x32-10 keyed by (seed), counter (element/4, global sample, var_id, offset)
+ *    + Box-Muller, bit-identical to what `brn_philox_normal_fill` writes.
+ */
+#ifndef BRANCHER_CUDA_H
+#define BRANCHER_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BRN_ABI_VERSION 1
+
+/* One mean-field Normal variational variable  q(w) = N(mu, softplus(rho))  together with the Normal
+ * prior p(w) = N(prior_loc, prior_scale) of the same name.
+ * Replaces: NormalVariable(loc, scale, name, learnable=True) (brancher/standard_variables.py:133-145),
+ * its auto-created roots `<name>_loc`, `<name>_scale` with scale = softplus(rho)
+ * (standard_variables.py:57-68, geometric_ranges.py:48-57), Normal rsample / log_prob / entropy
+ * (distributions.py:111-124,170-181,155-168 -> torch.distributions.Normal).
+ * tied != 0 reproduces the reference's root-NAME collision: p's hyper-parameter roots take q's values
+ * (utilities.py:282-309, variables.py:367-371), so log p(w) = N(w; mu, sigma) and prior_* are ignored. */
+typedef struct brn_mf_var {
+    const float* mu;          /* [numel]            `<name>_loc`   parameter                       */
+    const float* rho;         /* [numel]            `<name>_scale` parameter (sigma = softplus)    */
+    const float* prior_loc;   /* [numel] or NULL when tied                                         */
+    const float* prior_scale; /* [numel] or NULL when tied                                         */
+    const float* eps;         /* [S_local, numel] injected noise, or NULL for Philox               */
+    float*       dmu;         /* [numel]  += d loss / d mu   (partial, scaled)                     */
+    float*       drho;        /* [numel]  += d loss / d rho  (partial, scaled)                     */
+    int64_t      numel;
+    uint32_t     var_id;      /* Philox stream id of this variable                                 */
+    int32_t      tied;
+} brn_mf_var;
+
+/* Which MC samples this call evaluates and how noise is produced. */
+typedef struct brn_sample_range {
+    int32_t  s0;        /* first global sample index                      */
+    int32_t  s_local;   /* samples evaluated by this call                 */
+    int32_t  s_total;   /* global number of samples (the .mean() divisor, gradient_estimators.py:44) */
+    int32_t  _pad;
+    uint64_t seed;      /* Philox key                                     */
+    uint64_t offset;    /* Philox counter word 3 (iteration number)       */
+} brn_sample_range;
+
+int         brn_abi_version(void);
+const char* brn_last_error(void);
+/* name of the kernel variant the last compute call dispatched to ("simt", "tcgen05", ...) */
+const char* brn_last_variant(void);
+
+/* eps[s - s0, i] for s in [s0, s0+s_local), i in [0, numel): exactly the normals the fused kernels
+ * generate for (seed, offset, var_id).  Replaces torch.distributions.normal._standard_normal as called by
+ * Normal.rsample under distributions.py:122. */
+int brn_philox_normal_fill(float* out, int64_t numel, uint32_t var_id, const brn_sample_range* r, void* stream);
+
+/* K1a -- prior + entropy of mean-field Normal variables, forward and backward in one launch:
+ *   loss  += -(1/S_total) sum_{s local} [ sum_i log N(w_si; prior) + sum_i H(N(mu_i, sigma_i)) ]
+ *   dmu/drho += matching gradients (through w = mu + sigma*eps, through the entropy and -- when tied --
+ *   through the prior's own parameters).
+ * If lik_gw / lik_gwe are non-NULL they hold the likelihood stage's raw sums
+ *   gw[i] = sum_s d ll_s / d w_si,  gwe[i] = sum_s eps_si * d ll_s / d w_si   (ELBO direction, unscaled)
+ * and are folded in:  dmu -= gw/S_total,  drho -= sigmoid(rho) * gwe/S_total.
+ * Replaces: RandomVariable.calculate_log_probability for the weight nodes (variables.py:486-520),
+ * Variable._get_entropy (variables.py:156-162) and their autograd backward. */
+int brn_mf_normal_prior_entropy(const brn_mf_var* var, const float* lik_gw, const float* lik_gwe,
+                                const brn_sample_range* r, double* loss, void* stream);
+
+/* K3 -- Bayesian neural network P-H-C (tanh), Categorical(logits) likelihood over B observed rows:
+ *   per sample s: W1_s = mu+sigma*eps (H x P), b1_s (H), W2_s (C x H), b2_s (C)
+ *   ll_s = sum_b log_softmax(W2_s tanh(W1_s x_b + b1_s) + b2_s)[y_b]
+ *   loss += -(1/S_total) sum_s ll_s ; plus prior/entropy of the four variables (K1a folded in);
+ *   dmu/drho of vars[0..3] = (weights1, b1, weights2, b2) accumulated.
+ * Replaces the whole graph walk of estimate_log_model_evidence (variables.py:843-870) for the model of
+ * development_playgrounds/MNIST_bayesian_neural_network.py:26-57: _get_sample (variables.py:527-570),
+ * _apply_link's (S*B, H, P) materialisation + bmm (variables.py:436-449), CategoricalDistribution
+ * log-prob (distributions.py:294-311), the data-axis sum (variables.py:513-514), the sample-axis mean
+ * (gradient_estimators.py:44) and loss.backward() (inference.py:100).
+ * X [B,P] fp32, y [B] int32 labels.  workspace: brn_bnn_workspace_bytes() bytes of scratch. */
+size_t brn_bnn_workspace_bytes(int B, int P, int H, int C, int s_local);
+int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int P, int H, int C,
+                         const brn_mf_var vars[4], const brn_sample_range* r,
+                         void* workspace, size_t workspace_bytes, int with_prior,
+                         double* loss, void* stream);
+
+/* K2 -- (multi-class) Bayesian logistic regression: logits_sbc = sum_f W_scf X_bf, W ~ q mean-field [C,F];
+ *   likelihood 0: Bernoulli / Binomial(total_count=1, logits) with y float {0,1}  (C == 1)
+ *   likelihood 1: Categorical(logits) with y int32 labels
+ * over N observed rows (summed, variables.py:513-514).  Same accumulation contract as K3.
+ * Replaces the graph walk for examples/minibatch_logistic_regression.py:27-43 /
+ * examples/MNIST_logistic_regression.py (BF.matmul(weights, x) -> Binomial / Categorical). */
+size_t brn_linear_workspace_bytes(int64_t N, int F, int C, int s_local);
+int brn_linear_elbo_fwd_bwd(const float* X, const void* y, int likelihood, int64_t N, int F, int C,
+                            const brn_mf_var* w, const brn_sample_range* r,
+                            void* workspace, size_t workspace_bytes, int with_prior,
+                            double* loss, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BRANCHER_CUDA_H */

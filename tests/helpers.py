@@ -41,3 +41,26 @@ def assert_close(got, want, what, rtol=RTOL, atol=ATOL, scale=None):
     bad = err > bound
     assert not bad.any(), "%s: max err %.3e (bound %.3e) at %s; %d/%d outside" % (
         what, err.max(), bound.flat[err.argmax()], np.unravel_index(err.argmax(), err.shape), bad.sum(), bad.size)
+
+
+def check_against_oracle(got_loss, got_grads, o32, o64, what=""):
+    """The parity rule of this repo (stated in DESIGN.md §Parity):
+
+    gate A  CUDA vs the fp64 evaluation of the reference's formulas:
+            |cuda - o64| <= ATOL*scale + RTOL*|o64|,  scale = max|o64| over the tensor (1 for the loss)
+    gate B  CUDA vs the fp32 evaluation (what the reference itself returns), allowing for the fp32
+            evaluation's own measured distance from fp64:
+            |cuda - o32| <= ATOL*scale + RTOL*|o32| + 2*max|o32 - o64|
+    """
+    l32, g32 = o32
+    l64, g64 = o64
+    assert_close(got_loss, l64, what + " loss vs fp64 oracle")
+    assert_close(got_loss, l32, what + " loss vs fp32 oracle", atol=ATOL + 2 * abs(l32 - l64))
+    for k in g64:
+        a = np.asarray(got_grads[k], dtype=np.float64).reshape(g64[k].shape)
+        # tensor scale; when the exact gradient is identically zero (tied prior + entropy) fp64 returns
+        # pure rounding noise, so the fp32 evaluation's magnitude and an absolute floor bound the scale
+        sc = max(np.abs(g64[k]).max(), np.abs(np.asarray(g32[k], dtype=np.float64)).max(), 1e-8)
+        assert_close(a, g64[k], "%s grad %s vs fp64 oracle" % (what, k), scale=sc)
+        noise = np.abs(np.asarray(g32[k], dtype=np.float64) - g64[k]).max()
+        assert_close(a, g32[k], "%s grad %s vs fp32 oracle" % (what, k), atol=ATOL + 2 * noise / sc, scale=sc)

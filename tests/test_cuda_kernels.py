@@ -1,0 +1,214 @@
+"""GPU parity tests of the C-ABI entry points against the oracle (tests/helpers.check_against_oracle)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_golden, mf_params, check_against_oracle, assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cu():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from brancher_b200 import _cuda
+    _cuda.lib()
+    return _cuda
+
+
+DEV = "cuda:0"
+
+
+def dev(a, dtype=torch.float32):
+    return torch.as_tensor(np.asarray(a), dtype=dtype).to(DEV).contiguous()
+
+
+def make_vars(cu, params, eps, names, prior=None, shapes=None):
+    out = []
+    for i, n in enumerate(names):
+        mu, rho = params[n]
+        e = None if eps is None else dev(eps[n]).reshape(np.asarray(eps[n]).shape[0], -1)
+        pl = ps = None
+        if prior is not None:
+            pl, ps = np.broadcast_to(prior[n][0], np.shape(mu)), np.broadcast_to(prior[n][1], np.shape(mu))
+            pl, ps = dev(pl.copy()), dev(ps.copy())
+        out.append(cu.MeanFieldVar(dev(mu), dev(rho), var_id=i, prior_loc=pl, prior_scale=ps, eps=e))
+    return out
+
+
+def grads_of(vars_, names, params):
+    g = {}
+    for v, n in zip(vars_, names):
+        g[n + "_loc"] = v.dmu.cpu().numpy().reshape(np.shape(params[n][0]))
+        g[n + "_scale"] = v.drho.cpu().numpy().reshape(np.shape(params[n][1]))
+    return g
+
+
+# ---------------------------------------------------------------------------------------------
+def test_philox_normals(cu):
+    r = cu.sample_range(64, seed=1234, offset=7)
+    z = cu.philox_normal(100003, 3, r, DEV)
+    assert z.shape == (64, 100003)
+    assert abs(z.mean().item()) < 2e-3 and abs(z.var().item() - 1) < 5e-3
+    assert abs((z ** 4).mean().item() - 3) < 5e-2          # kurtosis of a normal
+    z2 = cu.philox_normal(100003, 3, r, DEV)
+    assert torch.equal(z, z2)                               # counter-based: deterministic
+    # shard invariance: samples [16,48) generated alone equal rows 16..47 of the full draw
+    part = cu.philox_normal(100003, 3, cu.sample_range(64, s0=16, s_local=32, seed=1234, offset=7), DEV)
+    assert torch.equal(part, z[16:48])
+    other = cu.philox_normal(100003, 4, r, DEV)
+    assert abs(torch.corrcoef(torch.stack([z.flatten(), other.flatten()]))[0, 1].item()) < 1e-3
+
+
+@pytest.mark.parametrize("tied", [True, False])
+@pytest.mark.parametrize("numel,S", [(1, 1), (7, 5), (1000, 33)])
+def test_mf_prior_entropy(cu, tied, numel, S):
+    from oracle import elbo_oracle as O
+    rng = np.random.RandomState(numel + S)
+    params = {"w": (rng.randn(numel).astype("f4"), rng.randn(numel).astype("f4"))}
+    eps = {"w": rng.randn(S, numel).astype("f4")}
+    prior = None if tied else {"w": (rng.randn(numel).astype("f4"), (0.5 + rng.rand(numel)).astype("f4"))}
+    o32 = O.mean_field_prior_entropy(params, eps, prior)
+    o64 = O.mean_field_prior_entropy(params, eps, prior, dtype=torch.float64)
+    (v,) = make_vars(cu, params, eps, ["w"], prior)
+    loss = cu.mf_normal_prior_entropy(v, cu.sample_range(S))
+    check_against_oracle(loss.item(), grads_of([v], ["w"], params), o32, o64, "mf")
+
+
+BNN_NAMES = ["weights1", "b1", "weights2", "b2"]
+
+
+def run_bnn(cu, X, y, params, eps, prior=None, r=None, with_prior=True):
+    S = next(iter(eps.values())).shape[0] if eps is not None else r.s_local
+    vars4 = make_vars(cu, params, eps, BNN_NAMES, prior)
+    loss = cu.bnn_elbo_fwd_bwd(dev(X), dev(y, torch.int32), vars4, r or cu.sample_range(S), with_prior=with_prior)
+    return loss.item(), grads_of(vars4, BNN_NAMES, params), vars4
+
+
+@pytest.mark.parametrize("name", ["bnn_small", "bnn_small_wide"])
+def test_bnn_golden(cu, name):
+    """CUDA vs the live reference's own outputs and vs the oracle on the same inputs."""
+    from oracle import elbo_oracle as O
+    g = load_golden(name)
+    params = mf_params(g, BNN_NAMES)
+    X, y = g["raw"]["X"], g["raw"]["y"]
+    o32 = O.bnn_elbo(X, y, params, g["eps"])
+    o64 = O.bnn_elbo(X, y, params, g["eps"], dtype=torch.float64)
+    loss, grads, _ = run_bnn(cu, X, y, params, g["eps"])
+    check_against_oracle(loss, grads, o32, o64, name)
+    # and directly against the reference's fp32 numbers, with the reference's measured noise as slack
+    ref = (float(g["raw"]["loss"]), g["grad"])
+    check_against_oracle(loss, grads, ref, o64, name + " (reference)")
+
+
+def random_bnn(seed, B, P, H, C, S, sigma=0.05, mu_scale=0.3):
+    rng = np.random.RandomState(seed)
+    shapes = {"weights1": (H, P), "b1": (H, 1), "weights2": (C, H), "b2": (C, 1)}
+    X = rng.rand(B, P).astype("f4")
+    y = rng.randint(0, C, size=B)
+    from oracle.elbo_oracle import softplus_inverse
+    params = {n: ((mu_scale * rng.randn(*s) / np.sqrt(s[1])).astype("f4"),
+                  softplus_inverse(sigma * (1 + rng.rand(*s))).astype("f4")) for n, s in shapes.items()}
+    eps = {n: rng.randn(S, *s).astype("f4") for n, s in shapes.items()}
+    return X, y, params, eps, shapes
+
+
+@pytest.mark.parametrize("B,P,H,C,S", [(1, 1, 1, 1, 1), (5, 3, 2, 2, 3), (130, 37, 21, 5, 4), (257, 100, 33, 10, 3),
+                                       (64, 784, 100, 10, 2), (129, 130, 129, 16, 2)])
+@pytest.mark.parametrize("tied", [True, False])
+def test_bnn_random_shapes(cu, B, P, H, C, S, tied):
+    """ragged sizes: B not a multiple of the 128-row tile, H/P not multiples of 4, C up to the maximum."""
+    from oracle import elbo_oracle as O
+    X, y, params, eps, shapes = random_bnn(B * 7 + H, B, P, H, C, S)
+    prior = None if tied else {n: (0.0, 10.0) for n in shapes}
+    o32 = O.bnn_elbo(X, y, params, eps, prior)
+    o64 = O.bnn_elbo(X, y, params, eps, prior, dtype=torch.float64)
+    loss, grads, _ = run_bnn(cu, X, y, params, eps, prior)
+    check_against_oracle(loss, grads, o32, o64, "bnn %s" % ((B, P, H, C, S),))
+
+
+def test_bnn_philox_mode_and_shard_invariance(cu):
+    """eps == NULL: the kernel's own Philox normals, exported with brn_philox_normal_fill, fed to the
+    oracle; and the sum of two sample shards equals the unsharded evaluation."""
+    from oracle import elbo_oracle as O
+    B, P, H, C, S = 96, 50, 12, 4, 10
+    X, y, params, _, shapes = random_bnn(5, B, P, H, C, S)
+    r = cu.sample_range(S, seed=99, offset=3)
+    eps = {n: cu.philox_normal(int(np.prod(shapes[n])), i, r, DEV).cpu().numpy().reshape((S,) + shapes[n])
+           for i, n in enumerate(BNN_NAMES)}
+    o32 = O.bnn_elbo(X, y, params, eps)
+    o64 = O.bnn_elbo(X, y, params, eps, dtype=torch.float64)
+    loss, grads, _ = run_bnn(cu, X, y, params, None, r=r)
+    check_against_oracle(loss, grads, o32, o64, "bnn philox")
+    la, ga, _ = run_bnn(cu, X, y, params, None, r=cu.sample_range(S, s0=0, s_local=4, seed=99, offset=3))
+    lb, gb, _ = run_bnn(cu, X, y, params, None, r=cu.sample_range(S, s0=4, s_local=6, seed=99, offset=3))
+    assert_close(la + lb, loss, "sharded loss", rtol=1e-6)
+    for k in grads:
+        assert_close(ga[k] + gb[k], grads[k], "sharded grad " + k, rtol=1e-5, atol=1e-6, scale=np.abs(grads[k]).max())
+
+
+# ---------------------------------------------------------------------------------------------
+def run_linear(cu, X, y, params, eps, lik, C, prior=None, r=None):
+    S = eps["weights"].shape[0] if eps is not None else r.s_local
+    (w,) = make_vars(cu, params, eps, ["weights"], prior)
+    yd = dev(y, torch.float32 if lik == cu.BERNOULLI else torch.int32)
+    loss = cu.linear_elbo_fwd_bwd(dev(X), yd, lik, w, C, r or cu.sample_range(S))
+    return loss.item(), grads_of([w], ["weights"], params)
+
+
+@pytest.mark.parametrize("name,tied", [("logreg_tied", True), ("logreg_declared_prior", False)])
+def test_logreg_golden(cu, name, tied):
+    from oracle import elbo_oracle as O
+    g = load_golden(name)
+    params = mf_params(g, ["weights"])
+    X, y = g["raw"]["X"], g["raw"]["y"]
+    prior = None if tied else {"weights": (g["raw"]["prior_loc"], g["raw"]["prior_scale"])}
+    o32 = O.logreg_elbo(X, y, params, g["eps"], prior)
+    o64 = O.logreg_elbo(X, y, params, g["eps"], prior, dtype=torch.float64)
+    loss, grads = run_linear(cu, X, y, params, g["eps"], cu.BERNOULLI, 1, prior)
+    check_against_oracle(loss, grads, o32, o64, name)
+    check_against_oracle(loss, grads, (float(g["raw"]["loss"]), g["grad"]), o64, name + " (reference)")
+
+
+def test_softmax_regression_golden(cu):
+    from oracle import elbo_oracle as O
+    g = load_golden("softmax_reg")
+    params = mf_params(g, ["weights"])
+    X, y = g["raw"]["X"], g["raw"]["y"]
+    o32 = O.logreg_elbo(X, y, params, g["eps"], likelihood="categorical")
+    o64 = O.logreg_elbo(X, y, params, g["eps"], likelihood="categorical", dtype=torch.float64)
+    loss, grads = run_linear(cu, X, y, params, g["eps"], cu.CATEGORICAL, 3)
+    check_against_oracle(loss, grads, o32, o64, "softmax_reg")
+    check_against_oracle(loss, grads, (float(g["raw"]["loss"]), g["grad"]), o64, "softmax_reg (reference)")
+
+
+@pytest.mark.parametrize("N,F,C,S,lik", [(1, 1, 1, 1, "binomial"), (300, 7, 1, 5, "binomial"),
+                                         (1000, 128, 1, 130, "binomial"), (5000, 64, 1, 257, "binomial"),
+                                         (333, 20, 10, 14, "categorical"), (129, 128, 3, 50, "categorical")])
+def test_linear_random_shapes(cu, N, F, C, S, lik):
+    from oracle import elbo_oracle as O
+    rng = np.random.RandomState(N + F)
+    X = rng.randn(N, F).astype("f4")
+    y = rng.randint(0, 2 if C == 1 else C, size=N)
+    params = {"weights": ((0.3 * rng.randn(C, F)).astype("f4"), (rng.randn(C, F) - 1).astype("f4"))}
+    eps = {"weights": rng.randn(S, C, F).astype("f4")}
+    prior = {"weights": (0.0, 0.5)}
+    o32 = O.logreg_elbo(X, y, params, eps, prior, likelihood=lik)
+    o64 = O.logreg_elbo(X, y, params, eps, prior, likelihood=lik, dtype=torch.float64)
+    loss, grads = run_linear(cu, X, y, params, eps, cu.BERNOULLI if C == 1 and lik == "binomial" else cu.CATEGORICAL,
+                             C, prior)
+    check_against_oracle(loss, grads, o32, o64, "linear %s" % ((N, F, C, S, lik),))
+
+
+def test_linear_empty_rows(cu):
+    """N = 0: the ELBO is prior + entropy only."""
+    from oracle import elbo_oracle as O
+    rng = np.random.RandomState(0)
+    F, S = 9, 6
+    params = {"weights": (rng.randn(1, F).astype("f4"), rng.randn(1, F).astype("f4"))}
+    eps = {"weights": rng.randn(S, 1, F).astype("f4")}
+    prior = {"weights": (0.0, 0.5)}
+    o32 = O.mean_field_prior_entropy(params, eps, prior)
+    o64 = O.mean_field_prior_entropy(params, eps, prior, dtype=torch.float64)
+    loss, grads = run_linear(cu, np.zeros((0, F), "f4"), np.zeros((0,), "f4"), params, eps, cu.BERNOULLI, 1, prior)
+    check_against_oracle(loss, grads, o32, o64, "linear N=0")
