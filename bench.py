@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- ELBO+gradient throughput of the B200-native hot path, in BASELINE.json's metric:
+(MC samples x data rows) / s, beside the reference algorithm's CPU path on the same box.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload bnn|logreg]
+
+One "step" = one ELBO + pathwise-gradient evaluation (loss and d loss/d every variational parameter)
+of the workload on synthetic data.  Workloads:
+  bnn     C3  MNIST-shaped BNN 784-100-10, minibatch 1024, 256 MC samples per GPU     (default; the
+              config BASELINE.json's north_star quotes its target on)
+  logreg  C2  Bayesian logistic regression, 10^6 rows x 128 features, 1024 MC samples
+Multi-GPU: MC samples are sharded (bnn; weak scaling: 256 samples per GPU) or data rows are sharded
+(logreg; weak scaling: 10^6 rows per GPU); partial loss/gradients are all-reduced with NCCL.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ELBO+grad evals/sec (MC samples x data rows/s)"
+UNIT = "sample*rows/s"
+
+WORKLOADS = {
+    "bnn": dict(name="C3 BNN 784-100-10 tanh, Categorical; minibatch B=1024, S=256 MC samples per GPU, "
+                     "mean-field Normal q (mu=0, sigma=0.01), prior N(0,10) tied by name as in the playground",
+                B=1024, P=784, H=100, C=10, S=256),
+    "logreg": dict(name="C2 Bayesian logistic regression N=10^6 rows per GPU x F=128, S=1024 MC samples, "
+                        "Binomial(1, logits), q init mu=0 sigma=1, declared prior N(0,0.5)",
+                   N=1_000_000, F=128, C=1, S=1024),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16_burst=d["bf16_tflops"], bf16_sustained=d["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic workloads (host arrays; seeded)
+# ---------------------------------------------------------------------------------------------
+def synth_bnn(cfg, seed=0):
+    rng = np.random.RandomState(seed)
+    B, P, H, C = cfg["B"], cfg["P"], cfg["H"], cfg["C"]
+    X = rng.rand(B, P).astype(np.float32)
+    y = rng.randint(0, C, size=B).astype(np.int32)
+    shapes = {"weights1": (H, P), "b1": (H, 1), "weights2": (C, H), "b2": (C, 1)}
+    rho0 = float(np.log(np.exp(0.01) - 1.0))
+    params = {n: (np.zeros(s, np.float32), np.full(s, rho0, np.float32)) for n, s in shapes.items()}
+    return X, y, params, shapes
+
+
+def synth_logreg(cfg, seed=0, rows=None):
+    rng = np.random.default_rng(seed)
+    N, F = rows or cfg["N"], cfg["F"]
+    X = rng.standard_normal((N, F), dtype=np.float32)
+    w = (rng.standard_normal(F) / np.sqrt(F)).astype(np.float32)
+    y = (rng.random(N) < 1.0 / (1.0 + np.exp(-(X @ w)))).astype(np.float32)
+    rho0 = float(np.log(np.exp(1.0) - 1.0))
+    params = {"weights": (np.zeros((1, F), np.float32), np.full((1, F), rho0, np.float32))}
+    return X, y, params
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's CPU torch path
+# ---------------------------------------------------------------------------------------------
+def cpu_step_fn(workload, cfg, sample_S):
+    from oracle import elbo_oracle as O
+    rng = np.random.RandomState(1)
+    if workload == "bnn":
+        X, y, params, shapes = synth_bnn(cfg)
+        eps = {n: rng.standard_normal((sample_S,) + s).astype(np.float32) for n, s in shapes.items()}
+        rows = cfg["B"]
+        fn = lambda: O.bnn_elbo(X, y, params, eps, sample_chunk=8)
+    else:
+        rows = 65536
+        X, y, params = synth_logreg(cfg, rows=rows)
+        eps = {"weights": rng.standard_normal((sample_S, 1, cfg["F"])).astype(np.float32)}
+        fn = lambda: O.logreg_elbo(X, y, params, eps, prior={"weights": (0.0, 0.5)}, row_chunk=8192)
+    return fn, sample_S * rows, "oracle port (torch CPU fp32, %d threads) on %d MC samples x %d rows of the workload" % (
+        torch.get_num_threads(), sample_S, rows)
+
+
+def run_cpu_baseline(workload, cfg, budget_s=12.0):
+    S = 64 if workload == "bnn" else 64
+    fn, units, desc = cpu_step_fn(workload, cfg, S)
+    fn()
+    t0, n = time.perf_counter(), 0
+    while True:
+        fn(); n += 1
+        dt = time.perf_counter() - t0
+        if dt > budget_s:
+            break
+    return {"value": units * n / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": desc + "; %d evaluations in %.1f s" % (n, dt)}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = args.workload
+    cfg = WORKLOADS[wl]
+    S = 64
+    fn, units, desc = cpu_step_fn(wl, cfg, S)
+    for _ in range(args.warmup):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fn()
+    dt = time.perf_counter() - t0
+    val = units * args.steps / dt
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": cfg["name"], "sample_per_step": desc},
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": desc},
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def main_ours(args):
+    from brancher_b200 import _cuda as cu
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    cu.lib()
+    wl = args.workload
+    cfg = WORKLOADS[wl]
+    pk = peaks()
+
+    if wl == "bnn":
+        Xh, yh, params, shapes = synth_bnn(cfg)
+        names = ["weights1", "b1", "weights2", "b2"]
+        S_local, S_total = cfg["S"], cfg["S"] * world
+        s0 = rank * S_local
+        units_per_rank = S_local * cfg["B"]
+        algo_flops = {"bnn.gemm_fwd": 2.0 * S_local * cfg["B"] * cfg["H"] * cfg["P"],
+                      "bnn.gemm_bwd": 2.0 * S_local * cfg["B"] * cfg["H"] * cfg["P"]}
+        mvars = [cu.MeanFieldVar(torch.tensor(params[n][0], device=dev), torch.tensor(params[n][1], device=dev), var_id=i)
+                 for i, n in enumerate(names)]
+        X = torch.tensor(Xh, device=dev)
+        y = torch.tensor(yh, device=dev)
+        Xpin, ypin = torch.tensor(Xh).pin_memory(), torch.tensor(yh).pin_memory()
+        h2d = Xpin.numel() * 4 + ypin.numel() * 4
+
+        def device_step(it, Xd=X, yd=y):
+            r = cu.sample_range(S_total, s0=s0, s_local=S_local, seed=args.seed, offset=it)
+            for v in mvars:
+                v.dmu.zero_(); v.drho.zero_()
+            return cu.bnn_elbo_fwd_bwd(Xd, yd, mvars, r)
+    else:
+        rows = cfg["N"]
+        Xh, yh, params = synth_logreg(cfg, seed=rank)
+        S_local = S_total = cfg["S"]
+        s0 = 0
+        units_per_rank = S_local * rows
+        algo_flops = {"linear.fused": 4.0 * S_local * rows * cfg["F"]}
+        w = cu.MeanFieldVar(torch.tensor(params["weights"][0], device=dev), torch.tensor(params["weights"][1], device=dev),
+                            var_id=0, prior_loc=0.0, prior_scale=0.5)
+        mvars = [w]
+        X = torch.tensor(Xh, device=dev)
+        y = torch.tensor(yh, device=dev)
+        Xpin, ypin = torch.tensor(Xh).pin_memory(), torch.tensor(yh).pin_memory()
+        h2d = Xpin.numel() * 4 + ypin.numel() * 4
+
+        def device_step(it, Xd=X, yd=y):
+            r = cu.sample_range(S_total, seed=args.seed, offset=it)
+            w.dmu.zero_(); w.drho.zero_()
+            # rows are sharded: every rank holds the same samples; prior/entropy counted once (rank 0)
+            return cu.linear_elbo_fwd_bwd(Xd, yd, cu.BERNOULLI, w, 1, r, with_prior=(rank == 0))
+
+    nparam = sum(v.numel for v in mvars)
+    flat = torch.zeros(2 * nparam + 2, device=dev)
+
+    def reduce_partials(loss):
+        """all-reduce [grads | loss] across ranks (loss as a hi/lo fp32 pair to keep ~fp64 accuracy)."""
+        if world == 1:
+            return loss
+        off = 0
+        for v in mvars:
+            flat[off:off + v.numel] = v.dmu; off += v.numel
+            flat[off:off + v.numel] = v.drho; off += v.numel
+        hi = loss.float()
+        flat[off] = hi[0]; flat[off + 1] = (loss - hi.double()).float()[0]
+        dist.all_reduce(flat)
+        off = 0
+        for v in mvars:
+            v.dmu.copy_(flat[off:off + v.numel]); off += v.numel
+            v.drho.copy_(flat[off:off + v.numel]); off += v.numel
+        return flat[off].double() + flat[off + 1].double()
+
+    def step(it):
+        return reduce_partials(device_step(it))
+
+    def e2e_step(it):
+        Xd = Xpin.to(dev, non_blocking=True)
+        yd = ypin.to(dev, non_blocking=True)
+        loss = reduce_partials(device_step(it, Xd, yd))
+        return float(loss.item())          # device -> host read of the step's result
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)     # 256 MiB > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, profile=False):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        if profile:
+            cu.profile_reset(); cu.profile_enable(True)
+        l0 = cu.launch_count()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for i in range(steps):
+            flush.fill_(float(i))                   # L2 flush between timed iterations (not timed)
+            evs[i][0].record()
+            fn(warmup + i)
+            evs[i][1].record()
+        barrier()
+        launches = cu.launch_count() - l0
+        stages = {}
+        if profile:
+            stages = cu.profile_collect(); cu.profile_enable(False)
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), launches, stages
+
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ms, launches, stages = timed(step, args.steps, args.warmup, profile=True)
+    clk = clocks.stop()
+    ms_e2e, _, _ = timed(lambda i: e2e_step(i), max(3, min(args.steps, 10)), 3)
+    n_e2e = max(3, min(args.steps, 10))
+
+    if rank == 0:
+        units = units_per_rank * world
+        value = units * args.steps / (ms * 1e-3)
+        e2e_value = units * n_e2e / (ms_e2e * 1e-3)
+        dom = max(algo_flops, key=lambda k: stages.get(k, (0, 0))[0] if k in stages else 0)
+        dom_ms, dom_calls = stages.get(dom, (float("nan"), 1))
+        tf32x3_peak = pk["bf16_sustained"] / 2.0 / 3.0
+        achieved = algo_flops[dom] / (dom_ms / max(dom_calls, 1) * 1e-3) / 1e12
+        stage_share = {k: round(v[0] / ms, 4) for k, v in stages.items()}
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": cfg["name"], "noise": "Philox4x32-10 in-kernel", "l2": "256 MiB flush between timed steps",
+                          "variant": cu.last_variant(), "global_samples": S_total,
+                          "sharding": "MC samples" if wl == "bnn" else "data rows"},
+               "clocks": clk, "gpu_launches": int(launches),
+               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
+                       "ms_per_step": ms_e2e / n_e2e},
+               "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": tf32x3_peak, "unit": "TFLOP/s",
+                            "frac": achieved / tf32x3_peak, "traffic": None,
+                            "peak_note": "fp32-equivalent via 3xTF32 = bf16_tflops_sustained / 2 (TF32 rate) / 3 (split), "
+                                         + pk["source"],
+                            "stage_share_of_step": stage_share},
+               }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = run_cpu_baseline(wl, cfg)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="bnn", choices=sorted(WORKLOADS))
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_ours(a)

@@ -40,6 +40,13 @@ SYMBOLS = {
     "brn_abi_version": (ctypes.c_int, []),
     "brn_last_error": (ctypes.c_char_p, []),
     "brn_last_variant": (ctypes.c_char_p, []),
+    "brn_profile_enable": (None, [ctypes.c_int]),
+    "brn_profile_collect": (ctypes.c_int, []),
+    "brn_profile_num_stages": (ctypes.c_int, []),
+    "brn_profile_stage": (ctypes.c_char_p, [ctypes.c_int, ctypes.POINTER(ctypes.c_double),
+                                            ctypes.POINTER(ctypes.c_longlong)]),
+    "brn_profile_reset": (None, []),
+    "brn_launch_count": (ctypes.c_longlong, []),
     "brn_philox_normal_fill": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint32,
                                               ctypes.POINTER(SampleRange), ctypes.c_void_p]),
     "brn_mf_normal_prior_entropy": (ctypes.c_int, [ctypes.POINTER(MFVar), ctypes.c_void_p, ctypes.c_void_p,
@@ -78,6 +85,29 @@ def lib():
 def _check(status, what):
     if status != 0:
         raise BrancherCudaError("%s failed (%d): %s" % (what, status, lib().brn_last_error().decode()))
+
+
+def profile_enable(on=True):
+    lib().brn_profile_enable(int(on))
+
+
+def profile_reset():
+    lib().brn_profile_reset()
+
+
+def profile_collect():
+    """{stage: (total_ms, calls)} accumulated since the last reset (synchronises the recorded events)."""
+    _check(lib().brn_profile_collect(), "brn_profile_collect")
+    out = {}
+    for i in range(lib().brn_profile_num_stages()):
+        ms, calls = ctypes.c_double(), ctypes.c_longlong()
+        name = lib().brn_profile_stage(i, ctypes.byref(ms), ctypes.byref(calls))
+        out[name.decode()] = (ms.value, calls.value)
+    return out
+
+
+def launch_count():
+    return lib().brn_launch_count()
 
 
 def last_variant():

@@ -197,6 +197,8 @@ extern "C" int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int
     // 1. noise + weights
     const float* eps_ptr[4];
     int64_t eps_ld[4];
+    {
+    StageTimer st("bnn.sample_weights", stream);
     for (int v = 0; v < 4; ++v) {
         if (vars[v].eps) {
             eps_ptr[v] = vars[v].eps;
@@ -210,13 +212,18 @@ extern "C" int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int
                                           numels[v], S, stream))
             return e;
     }
+    }
     // 2. pre_s = X . W1_s^T
-    if (int e = launch_sgemm_batched<true, true>(X, P, 0, ws.W + L.oW1, P, L.ldw, ws.pre, H, (int64_t)B * H, B, H, P, S,
-                                                 stream))
-        return e;
+    {
+        StageTimer st("bnn.gemm_fwd", stream);
+        if (int e = launch_sgemm_batched<true, true>(X, P, 0, ws.W + L.oW1, P, L.ldw, ws.pre, H, (int64_t)B * H, B, H, P,
+                                                     S, stream))
+            return e;
+    }
     // 3. mid
     BRN_CUDA_OK(cudaMemset2DAsync(ws.dW + L.ob1, L.ldw * sizeof(float), 0, (L.numel - L.ob1) * sizeof(float), S, stream));
     {
+        StageTimer st("bnn.mid", stream);
         int R = 128;
         while (R > 32 && bnn_mid_smem(R, H, C) > 200 * 1024) R -= 32;
         size_t smem = bnn_mid_smem(R, H, C);
@@ -227,10 +234,14 @@ extern "C" int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int
         BRN_LAUNCH_OK("bnn_mid_kernel");
     }
     // 4. dW1_s = dpre_s^T . X
-    if (int e = launch_sgemm_batched<false, false>(ws.pre, H, (int64_t)B * H, X, P, 0, ws.dW + L.oW1, P, L.ldw, H, P, B,
-                                                   S, stream))
-        return e;
+    {
+        StageTimer st("bnn.gemm_bwd", stream);
+        if (int e = launch_sgemm_batched<false, false>(ws.pre, H, (int64_t)B * H, X, P, 0, ws.dW + L.oW1, P, L.ldw, H, P,
+                                                       B, S, stream))
+            return e;
+    }
     // 5. reduce over samples + prior/entropy + chain rule
+    StageTimer st5("bnn.reduce_finalize", stream);
     for (int v = 0; v < 4; ++v) {
         if (int e = launch_reduce_over_samples(ws.dW + offs[v], L.ldw, eps_ptr[v], eps_ld[v], ws.gw + offs[v],
                                                ws.gwe + offs[v], numels[v], S, stream))

@@ -16,6 +16,7 @@ namespace brn {
 // ---------------------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 void set_variant(const char* name);
+void count_launch(int n);
 
 #define BRN_CHECK_ARG(cond, ...)                 \
     do {                                         \
@@ -41,6 +42,7 @@ void set_variant(const char* name);
             brn::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));         \
             return -3;                                                                       \
         }                                                                                    \
+        brn::count_launch(1);                                                                \
     } while (0)
 
 // ---------------------------------------------------------------------------------------------
@@ -146,4 +148,17 @@ __device__ __forceinline__ T block_sum(T v, T* scratch) {
     return r;
 }
 
+}  // namespace brn
+
+// ---------------------------------------------------------------------------------------------
+// optional per-stage timing (CUDA events on the launch stream) and launch counting, for bench.py
+// ---------------------------------------------------------------------------------------------
+namespace brn {
+void count_launch(int n);
+struct StageTimer {      // RAII: records an event pair around a stage when profiling is enabled
+    int slot;
+    cudaStream_t stream;
+    StageTimer(const char* name, cudaStream_t s);
+    ~StageTimer();
+};
 }  // namespace brn

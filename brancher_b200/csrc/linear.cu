@@ -255,13 +255,16 @@ extern "C" int brn_linear_elbo_fwd_bwd(const float* X, const void* y, int likeli
     set_variant("simt");
 
     const float* eps = w->eps;
+    StageTimer* st = new StageTimer("linear.sample_weights", stream);
     if (!eps) {
         if (int e = launch_philox_fill(ws.eps, numel, numel, w->var_id, *r, stream)) return e;
         eps = ws.eps;
     }
     if (int e = launch_sample_weights(w->mu, w->rho, eps, numel, ws.W, numel, numel, S, stream)) return e;
     BRN_CUDA_OK(cudaMemsetAsync(ws.dW, 0, sizeof(float) * (size_t)S * numel, stream));
+    delete st;
     if (N > 0) {
+        StageTimer st2("linear.fused", stream);
         LinearArgs a;
         a.X = X; a.y = y; a.N = N; a.F = F; a.C = C; a.S = S; a.W = ws.W; a.dW = ws.dW;
         a.inv_S = 1.0f / (float)r->s_total; a.loss = loss;
@@ -287,6 +290,7 @@ extern "C" int brn_linear_elbo_fwd_bwd(const float* X, const void* y, int likeli
         }
         BRN_LAUNCH_OK("linear_fused_kernel");
     }
+    StageTimer st3("linear.reduce_finalize", stream);
     if (int e = launch_reduce_over_samples(ws.dW, numel, eps, numel, ws.gw, ws.gwe, numel, S, stream)) return e;
     return launch_mf_finalize(*w, eps, numel, ws.gw, ws.gwe, *r, with_prior, loss, stream);
 }

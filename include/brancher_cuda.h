@@ -111,6 +111,15 @@ int brn_linear_elbo_fwd_bwd(const float* X, const void* y, int likelihood, int64
                             void* workspace, size_t workspace_bytes, int with_prior,
                             double* loss, void* stream);
 
+/* ---- measurement hooks (bench.py): per-stage CUDA-event timing on the launch stream + launch count.
+ * No reference counterpart (the reference has no profiler). */
+void        brn_profile_enable(int on);
+int         brn_profile_collect(void);                 /* synchronises the recorded events, sums them */
+int         brn_profile_num_stages(void);
+const char* brn_profile_stage(int i, double* total_ms, long long* calls);
+void        brn_profile_reset(void);
+long long   brn_launch_count(void);                    /* kernels launched by this library so far */
+
 #ifdef __cplusplus
 }
 #endif
