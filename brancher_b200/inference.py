@@ -1,0 +1,118 @@
+"""Inference driver (mirror of brancher/inference.py:50-151): same signature and side effects.
+
+    inference.perform_inference(joint_model, number_iterations, number_samples, optimizer, lr=...,
+                                inference_method=ReverseKL(gradient_estimator=PathwiseDerivativeEstimator))
+
+Each iteration is: loss = inference_method.compute_loss(...) [one fused CUDA ELBO+gradient evaluation],
+isfinite check, loss.backward() [hands the kernel's gradients to .grad], optimizer step.
+
+Deliberate deviation: the reference appends the loss twice per iteration with different shapes and
+then crashes in np.array(loss_list) under numpy >= 1.24 (inference.py:105,108-109); here
+`diagnostics["loss curve"]` holds ONE scalar per iteration.
+"""
+import warnings
+from abc import ABC, abstractmethod
+
+import numpy as np
+import torch
+
+from brancher_b200 import gradient_estimators
+from brancher_b200.optimizers import ProbabilisticOptimizer
+
+
+def perform_inference(joint_model, number_iterations, number_samples=1, optimizer="Adam", input_values={},
+                      inference_method=None, posterior_model=None, sampler_model=None, pretraining_iterations=0,
+                      **opt_params):
+    if not inference_method:
+        warnings.warn("The inference method was not specified, using the default reverse KL variational inference")
+        inference_method = ReverseKL()
+    if not posterior_model:
+        posterior_model = joint_model.posterior_model
+    if not sampler_model:
+        sampler_model = getattr(inference_method, "sampler_model", None) or getattr(joint_model, "posterior_sampler", None)
+
+    joint_model.update_observed_submodel()
+
+    optimizers_list = []
+
+    def append_prob_optimizer(model):
+        prob_opt = ProbabilisticOptimizer(model, optimizer, **opt_params)
+        if prob_opt.optimizer:
+            optimizers_list.append(prob_opt)
+
+    append_prob_optimizer(posterior_model)
+    if inference_method.learnable_model:
+        append_prob_optimizer(joint_model)
+    if inference_method.learnable_sampler:
+        append_prob_optimizer(sampler_model)
+
+    inference_method.check_model_compatibility(joint_model, posterior_model, sampler_model)
+
+    try:
+        from tqdm import tqdm
+        iterator = tqdm(range(number_iterations))
+    except ImportError:   # pragma: no cover
+        iterator = range(number_iterations)
+
+    losses = []
+    for iteration in iterator:
+        loss = inference_method.compute_loss(joint_model, posterior_model, sampler_model, number_samples)
+        if torch.isfinite(loss.detach()).all().item():
+            for opt in optimizers_list:
+                opt.zero_grad()
+            loss.backward()
+            inference_method.correct_gradient(joint_model, posterior_model, sampler_model, number_samples)
+            optimizers_list[0].update()
+            if iteration > pretraining_iterations:
+                for opt in optimizers_list[1:]:
+                    opt.update()
+        else:
+            warnings.warn("Numerical error, skipping sample")
+        losses.append(loss.detach())
+    curve = torch.stack(losses).cpu().numpy() if losses else np.zeros((0,))
+    joint_model.diagnostics.update({"loss curve": curve})
+    inference_method.post_process(joint_model)
+
+
+class InferenceMethod(ABC):
+    learnable_model = False
+    needs_sampler = False
+    learnable_sampler = False
+
+    @abstractmethod
+    def check_model_compatibility(self, joint_model, posterior_model, sampler_model):
+        pass
+
+    @abstractmethod
+    def compute_loss(self, joint_model, posterior_model, sampler_model, number_samples, input_values={}):
+        pass
+
+    def correct_gradient(self, joint_model, posterior_model, sampler_model, number_samples, input_values={}):
+        pass
+
+    @abstractmethod
+    def post_process(self, joint_model):
+        pass
+
+
+class ReverseKL(InferenceMethod):
+    """loss = -ELBO (inference.py:129-151)."""
+
+    def __init__(self, gradient_estimator=gradient_estimators.PathwiseDerivativeEstimator):
+        self.learnable_model = True
+        self.needs_sampler = False
+        self.learnable_sampler = False
+        self.gradient_estimator = gradient_estimator
+
+    def check_model_compatibility(self, joint_model, posterior_model, sampler_model):
+        from brancher_b200 import lowering
+        lowering.get_plan(joint_model, posterior_model)       # raises UnsupportedModelError early
+
+    def compute_loss(self, joint_model, posterior_model, sampler_model, number_samples, input_values={}):
+        return -joint_model.estimate_log_model_evidence(number_samples=number_samples, method="ELBO",
+                                                        input_values=input_values, for_gradient=True,
+                                                        posterior_model=posterior_model,
+                                                        gradient_estimator=self.gradient_estimator)
+
+    def post_process(self, joint_model):
+        pass

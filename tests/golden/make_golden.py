@@ -27,6 +27,8 @@ from brancher import inference, distributions, geometric_ranges
 import brancher.functions as BF
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import model_zoo as zoo
 
 
 def inject(qvars, eps, transform=None):
@@ -60,82 +62,6 @@ def flat(prefix, d):
 
 
 # ---------------------------------------------------------------------------------------------
-def bnn(seed, B, P, H, C, S, q_sigma=0.01, q_mu_scale=0.0, tag="bnn_small"):
-    rng = np.random.RandomState(seed)
-    X = rng.rand(B, P, 1).astype("float32")
-    y = rng.randint(0, C, size=(B,))
-    x = RootVariable(X, "x", is_observed=True)
-    shapes = {"b1": (H, 1), "b2": (C, 1), "weights1": (H, P), "weights2": (C, H)}
-    pv = {n: NormalVariable(np.zeros(s), 10 * np.ones(s), n) for n, s in shapes.items()}
-    h = BF.tanh(BF.matmul(pv["weights1"], x) + pv["b1"])
-    a = BF.matmul(pv["weights2"], h) + pv["b2"]
-    k = CategoricalVariable(logits=a, name="k")
-    model = ProbabilisticModel([k])
-    k.observe(y)
-    mu0 = {n: (q_mu_scale * rng.randn(*s)).astype("float32") for n, s in shapes.items()}
-    sg0 = {n: (q_sigma * (1 + rng.rand(*s))).astype("float32") for n, s in shapes.items()}
-    Q = [NormalVariable(mu0[n].astype("float64"), sg0[n].astype("float64"), n, learnable=True) for n in shapes]
-    model.set_posterior_model(ProbabilisticModel(Q))
-    eps = {n: torch.tensor(rng.randn(S, 1, *s).astype("float32")) for n, s in shapes.items()}
-    inject(Q, eps)
-    loss, grads, values = loss_and_grads(model, S)
-    save(tag, X=X[:, :, 0], y=y, loss=loss,
-         **flat("eps_", {n: e.numpy()[:, 0] for n, e in eps.items()}),
-         **flat("param_", {n: v[0, 0] for n, v in values.items()}),
-         **flat("grad_", {n: g[0, 0] for n, g in grads.items()}))
-
-
-def logreg(seed, B, F, S, tied, tag):
-    rng = np.random.RandomState(seed)
-    X = rng.randn(B, F, 1).astype("float32")
-    wtrue = rng.randn(F) / np.sqrt(F)
-    y = (rng.rand(B) < 1 / (1 + np.exp(-X[:, :, 0] @ wtrue))).astype("float32").reshape(B, 1)
-    x = RootVariable(X, "x", is_observed=True)
-    if tied:   # numeric hyper-parameters on both sides: roots collide by name (every example does this)
-        weights = NormalVariable(np.zeros((1, F)), 0.5 * np.ones((1, F)), "weights")
-    else:      # p's roots named distinctly -> the declared prior N(0, 0.5) is what is evaluated
-        weights = NormalVariable(RootVariable(np.zeros((1, F)), "prior_loc"),
-                                 RootVariable(0.5 * np.ones((1, F)), "prior_scale"), "weights")
-    k = BinomialVariable(1, logits=BF.matmul(weights, x), name="k")
-    model = ProbabilisticModel([k])
-    k.observe(y)
-    mu0 = (0.3 * rng.randn(1, F)).astype("float32")
-    sg0 = (0.5 + rng.rand(1, F)).astype("float32")
-    Q = [NormalVariable(mu0.astype("float64"), sg0.astype("float64"), "weights", learnable=True)]
-    model.set_posterior_model(ProbabilisticModel(Q))
-    eps = {"weights": torch.tensor(rng.randn(S, 1, 1, F).astype("float32"))}
-    inject(Q, eps)
-    loss, grads, values = loss_and_grads(model, S)
-    save(tag, X=X[:, :, 0], y=y[:, 0], loss=loss, tied=int(tied),
-         prior_loc=np.zeros((1, F), "float32"), prior_scale=0.5 * np.ones((1, F), "float32"),
-         eps_weights=eps["weights"].numpy()[:, 0],
-         **flat("param_", {n: v[0, 0] for n, v in values.items()}),
-         **flat("grad_", {n: g[0, 0] for n, g in grads.items()}))
-
-
-def softmax_reg(seed, B, F, C, S, tag):
-    """MNIST_logistic_regression-shaped: Categorical(logits = W x), W [C,F]."""
-    rng = np.random.RandomState(seed)
-    X = rng.randn(B, F, 1).astype("float32")
-    y = rng.randint(0, C, size=(B,))
-    x = RootVariable(X, "x", is_observed=True)
-    weights = NormalVariable(np.zeros((C, F)), 10 * np.ones((C, F)), "weights")
-    k = CategoricalVariable(logits=BF.matmul(weights, x), name="k")
-    model = ProbabilisticModel([k])
-    k.observe(y)
-    mu0 = (0.3 * rng.randn(C, F)).astype("float32")
-    sg0 = (0.1 + 0.2 * rng.rand(C, F)).astype("float32")
-    Q = [NormalVariable(mu0.astype("float64"), sg0.astype("float64"), "weights", learnable=True)]
-    model.set_posterior_model(ProbabilisticModel(Q))
-    eps = {"weights": torch.tensor(rng.randn(S, 1, C, F).astype("float32"))}
-    inject(Q, eps)
-    loss, grads, values = loss_and_grads(model, S)
-    save(tag, X=X[:, :, 0], y=y, loss=loss, eps_weights=eps["weights"].numpy()[:, 0],
-         **flat("param_", {n: v[0, 0] for n, v in values.items()}),
-         **flat("grad_", {n: g[0, 0] for n, g in grads.items()}))
-
-
-# ---------------------------------------------------------------------------------------------
 class _LogitNormalDistribution(distributions.ContinuousDistribution, distributions.UnivariateDistribution):
     """Shim for the LogitNormal the README uses but the reference commented out
     (standard_variables.py:201-213): same pattern as LogNormalDistribution (distributions.py:493-507)
@@ -161,38 +87,51 @@ class _LogitNormalVariable(VariableConstructor):
         self.distribution = _LogitNormalDistribution()
 
 
-def ar1(seed, T, S, tag="ar1_readme"):
-    """README.md:22-75 model, y0 named 'y0'."""
-    rng = np.random.RandomState(seed)
-    driving, measure, btrue = 1.0, 0.3, 0.7
-    xs = [rng.randn() * driving]
-    for t in range(1, T):
-        xs.append(btrue * xs[-1] + driving * rng.randn())
-    ydata = np.array(xs) + measure * rng.randn(T)
-    x0 = NormalVariable(0., driving, "x0")
-    y0 = NormalVariable(x0, measure, "y0")
-    b = _LogitNormalVariable(0.5, 1., "b")
-    x, y = [x0], [y0]
-    for t in range(1, T):
-        x.append(NormalVariable(b * x[t - 1], driving, "x%d" % t))
-        y.append(NormalVariable(x[t], measure, "y%d" % t))
-    model = ProbabilisticModel(x + y)
-    for t, yt in enumerate(y):
-        yt.observe(float(ydata[t]))
-    Qb = _LogitNormalVariable(0.5, 0.5, "b", learnable=True)
-    logit_b_post = DeterministicVariable(0., "logit_b_post", learnable=True)
-    Qx = [NormalVariable(0., 1., "x0", learnable=True)]
-    Qx_mean = [DeterministicVariable(0., "x0_mean", learnable=True)]
-    for t in range(1, T):
-        Qx_mean.append(DeterministicVariable(0.1 * rng.randn(), "x%d_mean" % t, learnable=True))
-        Qx.append(NormalVariable(BF.sigmoid(logit_b_post) * Qx[t - 1] + Qx_mean[t], 1., "x%d" % t, learnable=True))
-    model.set_posterior_model(ProbabilisticModel([Qb] + Qx))
-    eps = {"b": torch.tensor(rng.randn(S, 1, 1, 1).astype("float32"))}
-    for t in range(T):
-        eps["x%d" % t] = torch.tensor(rng.randn(S, 1, 1, 1).astype("float32"))
-    inject([Qb] + Qx, eps, transform={"b": torch.sigmoid})
+NS = zoo.namespace("brancher")          # the model builders are shared with the brancher_b200 parity tests
+NS.LogitNormalVariable = _LogitNormalVariable
+
+
+def bnn(seed, B, P, H, C, S, q_sigma=0.01, q_mu_scale=0.0, tag="bnn_small"):
+    model, Q, d = zoo.bnn(NS, seed, B, P, H, C, q_sigma, q_mu_scale)
+    eps = {n: torch.tensor(d["rng"].randn(S, 1, *s).astype("float32")) for n, s in d["shapes"].items()}
+    inject(Q, eps)
     loss, grads, values = loss_and_grads(model, S)
-    save(tag, y=ydata.astype("float32"), loss=loss, measure_noise=measure,
+    save(tag, X=d["X"], y=d["y"], loss=loss,
+         **flat("eps_", {n: e.numpy()[:, 0] for n, e in eps.items()}),
+         **flat("param_", {n: v[0, 0] for n, v in values.items()}),
+         **flat("grad_", {n: g[0, 0] for n, g in grads.items()}))
+
+
+def logreg(seed, B, F, S, tied, tag):
+    model, Q, d = zoo.logreg(NS, seed, B, F, tied)
+    eps = {"weights": torch.tensor(d["rng"].randn(S, 1, 1, F).astype("float32"))}
+    inject(Q, eps)
+    loss, grads, values = loss_and_grads(model, S)
+    save(tag, X=d["X"], y=d["y"], loss=loss, tied=int(tied),
+         prior_loc=np.zeros((1, F), "float32"), prior_scale=0.5 * np.ones((1, F), "float32"),
+         eps_weights=eps["weights"].numpy()[:, 0],
+         **flat("param_", {n: v[0, 0] for n, v in values.items()}),
+         **flat("grad_", {n: g[0, 0] for n, g in grads.items()}))
+
+
+def softmax_reg(seed, B, F, C, S, tag):
+    model, Q, d = zoo.softmax_reg(NS, seed, B, F, C)
+    eps = {"weights": torch.tensor(d["rng"].randn(S, 1, C, F).astype("float32"))}
+    inject(Q, eps)
+    loss, grads, values = loss_and_grads(model, S)
+    save(tag, X=d["X"], y=d["y"], loss=loss, eps_weights=eps["weights"].numpy()[:, 0],
+         **flat("param_", {n: v[0, 0] for n, v in values.items()}),
+         **flat("grad_", {n: g[0, 0] for n, g in grads.items()}))
+
+
+def ar1(seed, T, S, tag="ar1_readme"):
+    model, Q, d = zoo.ar1(NS, seed, T)
+    eps = {"b": torch.tensor(d["rng"].randn(S, 1, 1, 1).astype("float32"))}
+    for t in range(T):
+        eps["x%d" % t] = torch.tensor(d["rng"].randn(S, 1, 1, 1).astype("float32"))
+    inject(Q, eps, transform={"b": torch.sigmoid})
+    loss, grads, values = loss_and_grads(model, S)
+    save(tag, y=d["y"], loss=loss, measure_noise=d["measure_noise"],
          **flat("eps_", {n: e.numpy().reshape(S) for n, e in eps.items()}),
          **flat("param_", {n: v.reshape(()) for n, v in values.items()}),
          **flat("grad_", {n: g.reshape(()) for n, g in grads.items()}))

@@ -1,0 +1,114 @@
+"""Model-construction code shared VERBATIM between the reference and brancher_b200.
+
+Every builder takes `ns`, a namespace exposing the public names of either package
+(`brancher.*` in tests/golden/make_golden.py, `brancher_b200.*` in the parity tests), and builds the
+model through that package's public API only -- the drop-in claim, executed.
+Each returns (model, q_variables, data dict).
+"""
+import types
+
+import numpy as np
+
+
+def namespace(pkg):
+    """pkg = 'brancher' (reference) or 'brancher_b200'."""
+    import importlib
+    V = importlib.import_module(pkg + ".variables")
+    SV = importlib.import_module(pkg + ".standard_variables")
+    ns = types.SimpleNamespace(
+        pkg=pkg, RootVariable=V.RootVariable, ProbabilisticModel=V.ProbabilisticModel,
+        NormalVariable=SV.NormalVariable, CategoricalVariable=SV.CategoricalVariable,
+        BinomialVariable=SV.BinomialVariable, DeterministicVariable=SV.DeterministicVariable,
+        LogNormalVariable=SV.LogNormalVariable, EmpiricalVariable=SV.EmpiricalVariable, RandomIndices=SV.RandomIndices,
+        LogitNormalVariable=getattr(SV, "LogitNormalVariable", None),
+        BF=importlib.import_module(pkg + ".functions"), inference=importlib.import_module(pkg + ".inference"))
+    return ns
+
+
+def bnn(ns, seed, B, P, H, C, q_sigma=0.01, q_mu_scale=0.0):
+    """development_playgrounds/MNIST_bayesian_neural_network.py:26-57 on synthetic data."""
+    rng = np.random.RandomState(seed)
+    X = rng.rand(B, P, 1).astype("float32")
+    y = rng.randint(0, C, size=(B,))
+    x = ns.RootVariable(X, "x", is_observed=True)
+    shapes = {"b1": (H, 1), "b2": (C, 1), "weights1": (H, P), "weights2": (C, H)}
+    pv = {n: ns.NormalVariable(np.zeros(s), 10 * np.ones(s), n) for n, s in shapes.items()}
+    h = ns.BF.tanh(ns.BF.matmul(pv["weights1"], x) + pv["b1"])
+    a = ns.BF.matmul(pv["weights2"], h) + pv["b2"]
+    k = ns.CategoricalVariable(logits=a, name="k")
+    model = ns.ProbabilisticModel([k])
+    k.observe(y)
+    mu0 = {n: (q_mu_scale * rng.randn(*s)).astype("float32") for n, s in shapes.items()}
+    sg0 = {n: (q_sigma * (1 + rng.rand(*s))).astype("float32") for n, s in shapes.items()}
+    Q = [ns.NormalVariable(mu0[n].astype("float64"), sg0[n].astype("float64"), n, learnable=True) for n in shapes]
+    model.set_posterior_model(ns.ProbabilisticModel(Q))
+    return model, Q, {"X": X[:, :, 0], "y": y, "shapes": shapes, "rng": rng}
+
+
+def logreg(ns, seed, B, F, tied):
+    """examples/minibatch_logistic_regression.py:27-43 shape, batch passed as an observed root
+    (development_playgrounds/bayesian_logistic_regression_playground.py:22-30)."""
+    rng = np.random.RandomState(seed)
+    X = rng.randn(B, F, 1).astype("float32")
+    wtrue = rng.randn(F) / np.sqrt(F)
+    y = (rng.rand(B) < 1 / (1 + np.exp(-X[:, :, 0] @ wtrue))).astype("float32").reshape(B, 1)
+    x = ns.RootVariable(X, "x", is_observed=True)
+    if tied:   # numeric hyper-parameters on both sides: roots collide by name (every example does this)
+        weights = ns.NormalVariable(np.zeros((1, F)), 0.5 * np.ones((1, F)), "weights")
+    else:      # p's roots named distinctly -> the declared prior N(0, 0.5) is what is evaluated
+        weights = ns.NormalVariable(ns.RootVariable(np.zeros((1, F)), "prior_loc"),
+                                    ns.RootVariable(0.5 * np.ones((1, F)), "prior_scale"), "weights")
+    k = ns.BinomialVariable(1, logits=ns.BF.matmul(weights, x), name="k")
+    model = ns.ProbabilisticModel([k])
+    k.observe(y)
+    mu0 = (0.3 * rng.randn(1, F)).astype("float32")
+    sg0 = (0.5 + rng.rand(1, F)).astype("float32")
+    Q = [ns.NormalVariable(mu0.astype("float64"), sg0.astype("float64"), "weights", learnable=True)]
+    model.set_posterior_model(ns.ProbabilisticModel(Q))
+    return model, Q, {"X": X[:, :, 0], "y": y[:, 0], "rng": rng}
+
+
+def softmax_reg(ns, seed, B, F, C):
+    """examples/MNIST_logistic_regression.py shape: Categorical(logits = W x), W [C,F]."""
+    rng = np.random.RandomState(seed)
+    X = rng.randn(B, F, 1).astype("float32")
+    y = rng.randint(0, C, size=(B,))
+    x = ns.RootVariable(X, "x", is_observed=True)
+    weights = ns.NormalVariable(np.zeros((C, F)), 10 * np.ones((C, F)), "weights")
+    k = ns.CategoricalVariable(logits=ns.BF.matmul(weights, x), name="k")
+    model = ns.ProbabilisticModel([k])
+    k.observe(y)
+    mu0 = (0.3 * rng.randn(C, F)).astype("float32")
+    sg0 = (0.1 + 0.2 * rng.rand(C, F)).astype("float32")
+    Q = [ns.NormalVariable(mu0.astype("float64"), sg0.astype("float64"), "weights", learnable=True)]
+    model.set_posterior_model(ns.ProbabilisticModel(Q))
+    return model, Q, {"X": X[:, :, 0], "y": y, "rng": rng}
+
+
+def ar1(ns, seed, T):
+    """README.md:22-75 model, y0 named 'y0' (the README reuses 'x0')."""
+    rng = np.random.RandomState(seed)
+    driving, measure, btrue = 1.0, 0.3, 0.7
+    xs = [rng.randn() * driving]
+    for t in range(1, T):
+        xs.append(btrue * xs[-1] + driving * rng.randn())
+    ydata = np.array(xs) + measure * rng.randn(T)
+    x0 = ns.NormalVariable(0., driving, "x0")
+    y0 = ns.NormalVariable(x0, measure, "y0")
+    b = ns.LogitNormalVariable(0.5, 1., "b")
+    x, y = [x0], [y0]
+    for t in range(1, T):
+        x.append(ns.NormalVariable(b * x[t - 1], driving, "x%d" % t))
+        y.append(ns.NormalVariable(x[t], measure, "y%d" % t))
+    model = ns.ProbabilisticModel(x + y)
+    for t, yt in enumerate(y):
+        yt.observe(float(ydata[t]))
+    Qb = ns.LogitNormalVariable(0.5, 0.5, "b", learnable=True)
+    logit_b_post = ns.DeterministicVariable(0., "logit_b_post", learnable=True)
+    Qx = [ns.NormalVariable(0., 1., "x0", learnable=True)]
+    Qx_mean = [ns.DeterministicVariable(0., "x0_mean", learnable=True)]
+    for t in range(1, T):
+        Qx_mean.append(ns.DeterministicVariable(0.1 * rng.randn(), "x%d_mean" % t, learnable=True))
+        Qx.append(ns.NormalVariable(ns.BF.sigmoid(logit_b_post) * Qx[t - 1] + Qx_mean[t], 1., "x%d" % t, learnable=True))
+    model.set_posterior_model(ns.ProbabilisticModel([Qb] + Qx))
+    return model, [Qb] + Qx, {"y": ydata.astype("float32"), "measure_noise": measure, "rng": rng}

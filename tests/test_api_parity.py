@@ -1,0 +1,128 @@
+"""GPU: the SAME model-construction code (tests/model_zoo.py) that produced the golden vectors with the
+reference package is run against brancher_b200; loss and every `.grad` must match the reference's
+outputs (stored in tests/golden/*.npz) and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import model_zoo as zoo
+from helpers import load_golden, mf_params, check_against_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ns():
+    assert torch.cuda.is_available()
+    from brancher_b200 import config
+    config.set_device("cuda:0")
+    return zoo.namespace("brancher_b200")
+
+
+def loss_and_grads(ns, model, S, eps):
+    """Drive our package exactly as the oracle harness drives the reference."""
+    from brancher_b200 import lowering
+    with lowering.inject_noise(eps):
+        loss = ns.inference.ReverseKL().compute_loss(model, model.posterior_model, None, S)
+    loss.backward()
+    grads = {v.name: v.link.parameter.grad.detach().cpu().numpy()[0, 0]
+             for v in model.posterior_model.flatten() if getattr(v, "learnable", False) and hasattr(v.link, "parameter")}
+    return float(loss.detach()), grads
+
+
+def params_match(model, g):
+    """Same construction code + same seeds => same initial parameters as the reference run."""
+    for v in model.posterior_model.flatten():
+        if getattr(v, "learnable", False) and hasattr(v.link, "parameter"):
+            np.testing.assert_allclose(v.link.parameter.detach().cpu().numpy()[0, 0].reshape(g["param"][v.name].shape),
+                                       g["param"][v.name], rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("tag,kw", [("bnn_small", dict(seed=1, B=12, P=20, H=7, C=4)),
+                                    ("bnn_small_wide", dict(seed=2, B=9, P=16, H=5, C=3, q_sigma=0.3, q_mu_scale=0.5))])
+def test_bnn_same_script_same_numbers(ns, tag, kw):
+    from oracle import elbo_oracle as O
+    g = load_golden(tag)
+    model, Q, d = zoo.bnn(ns, **kw)
+    params_match(model, g)
+    S = g["eps"]["b1"].shape[0]
+    loss, grads = loss_and_grads(ns, model, S, g["eps"])
+    names = ["weights1", "b1", "weights2", "b2"]
+    o64 = O.bnn_elbo(g["raw"]["X"], g["raw"]["y"], mf_params(g, names), g["eps"], dtype=torch.float64)
+    check_against_oracle(loss, grads, (float(g["raw"]["loss"]), g["grad"]), o64, tag + " via API vs reference")
+
+
+@pytest.mark.parametrize("tag,tied,seed", [("logreg_tied", True, 3), ("logreg_declared_prior", False, 4)])
+def test_logreg_same_script_same_numbers(ns, tag, tied, seed):
+    from oracle import elbo_oracle as O
+    g = load_golden(tag)
+    model, Q, d = zoo.logreg(ns, seed, B=40, F=8, tied=tied)
+    params_match(model, g)
+    prior = None if tied else {"weights": (g["raw"]["prior_loc"], g["raw"]["prior_scale"])}
+    loss, grads = loss_and_grads(ns, model, 16, g["eps"])
+    o64 = O.logreg_elbo(g["raw"]["X"], g["raw"]["y"], mf_params(g, ["weights"]), g["eps"], prior, dtype=torch.float64)
+    check_against_oracle(loss, grads, (float(g["raw"]["loss"]), g["grad"]), o64, tag + " via API vs reference")
+
+
+def test_softmax_regression_same_script_same_numbers(ns):
+    from oracle import elbo_oracle as O
+    g = load_golden("softmax_reg")
+    model, Q, d = zoo.softmax_reg(ns, 5, B=24, F=6, C=3)
+    params_match(model, g)
+    loss, grads = loss_and_grads(ns, model, 8, g["eps"])
+    o64 = O.logreg_elbo(g["raw"]["X"], g["raw"]["y"], mf_params(g, ["weights"]), g["eps"], likelihood="categorical",
+                        dtype=torch.float64)
+    check_against_oracle(loss, grads, (float(g["raw"]["loss"]), g["grad"]), o64, "softmax_reg via API vs reference")
+
+
+def test_perform_inference_logreg_posterior_mean(ns):
+    """End to end under independent (Philox) noise: perform_inference drives the loss down and the
+    posterior mean lands on the fp64 oracle-trained optimum within MC error."""
+    from brancher_b200 import config
+    config.set_seed(123)
+    model, Q, d = zoo.logreg(ns, 11, B=400, F=4, tied=False)
+    ns.inference.perform_inference(model, number_iterations=300, number_samples=64, optimizer="Adam", lr=0.05)
+    curve = model.diagnostics["loss curve"]
+    assert curve.shape == (300,) and np.isfinite(curve).all()
+    assert curve[-20:].mean() < curve[:20].mean()
+    mu = Q[0].roots["loc"].value.detach().cpu().numpy().reshape(-1)
+    # reference optimum: maximise the same ELBO with the fp64 oracle by plain Adam on CPU
+    from oracle import elbo_oracle as O
+    p = {"weights": (np.zeros((1, 4)), O.softplus_inverse(np.ones((1, 4))))}
+    t_mu = torch.tensor(p["weights"][0], dtype=torch.float64, requires_grad=True)
+    t_rho = torch.tensor(p["weights"][1], dtype=torch.float64, requires_grad=True)
+    opt = torch.optim.Adam([t_mu, t_rho], lr=0.05)
+    rng = np.random.RandomState(0)
+    for _ in range(300):
+        eps = {"weights": rng.randn(64, 1, 4)}
+        _, gr = O.logreg_elbo(d["X"], d["y"], {"weights": (t_mu.detach().numpy(), t_rho.detach().numpy())}, eps,
+                              prior={"weights": (0.0, 0.5)}, dtype=torch.float64)
+        opt.zero_grad()
+        t_mu.grad = torch.tensor(gr["weights_loc"]); t_rho.grad = torch.tensor(gr["weights_scale"])
+        opt.step()
+    sd = torch.nn.functional.softplus(t_rho).detach().numpy().reshape(-1)
+    assert np.all(np.abs(mu - t_mu.detach().numpy().reshape(-1)) < 4 * sd / np.sqrt(64) + 0.05)
+
+
+def test_minibatch_model_runs(ns):
+    """examples/minibatch_logistic_regression.py structure (RandomIndices + EmpiricalVariable)."""
+    rng = np.random.RandomState(0)
+    N, F = 50, 2
+    xin = np.concatenate([rng.normal(1.5, 1.5, (N // 2, F, 1)), rng.normal(-1.5, 1.5, (N // 2, F, 1))])
+    lab = np.concatenate([np.zeros((N // 2, 1)), np.ones((N // 2, 1))])
+    idx = ns.RandomIndices(dataset_size=N, batch_size=30, name="indices", is_observed=True)
+    x = ns.EmpiricalVariable(xin, indices=idx, name="x", is_observed=True)
+    labels = ns.EmpiricalVariable(lab, indices=idx, name="labels", is_observed=True)
+    w = ns.NormalVariable(np.zeros((1, F)), 0.5 * np.ones((1, F)), "weights")
+    k = ns.BinomialVariable(1, logits=ns.BF.matmul(w, x), name="k")
+    model = ns.ProbabilisticModel([k])
+    k.observe(labels)
+    Qw = ns.NormalVariable(np.zeros((1, F)), np.ones((1, F)), "weights", learnable=True)
+    model.set_posterior_model(ns.ProbabilisticModel([Qw]))
+    ns.inference.perform_inference(model, number_iterations=100, number_samples=50, optimizer="Adam", lr=0.05)
+    curve = model.diagnostics["loss curve"]
+    assert np.isfinite(curve).all() and curve[-10:].mean() < curve[:10].mean()
+    post = model._get_posterior_sample(50)
+    assert post[w].shape[0] == 50
+    mu = Qw.roots["loc"].value.detach().cpu().numpy().reshape(-1)
+    assert mu[0] < 0 and mu[1] < 0          # class 1 sits at negative coordinates

@@ -1,0 +1,109 @@
+"""CPU: host-side mirror -- model construction, shapes, graph lowering, error behaviour."""
+import numpy as np
+import pytest
+import torch
+
+import model_zoo as zoo
+
+
+@pytest.fixture(scope="module")
+def ns():
+    from brancher_b200 import config
+    config.set_device("cpu")
+    yield zoo.namespace("brancher_b200")
+    config.set_device("cuda:0" if torch.cuda.is_available() else "cpu")
+
+
+def test_shape_convention(ns):
+    from brancher_b200.utilities import coerce_to_dtype
+    assert coerce_to_dtype(1.5).shape == (1, 1, 1, 1)
+    assert coerce_to_dtype(np.zeros((3, 4))).shape == (1, 1, 3, 4)
+    assert coerce_to_dtype(np.zeros((7,)), is_observed=True).shape == (1, 7, 1, 1)
+    assert coerce_to_dtype(np.zeros((7, 5)), is_observed=True).shape == (1, 7, 5, 1)
+    assert coerce_to_dtype(np.zeros((7, 5, 1)), is_observed=True).shape == (1, 7, 5, 1)
+    assert coerce_to_dtype([1, 2]) == [1, 2]
+
+
+def test_auto_named_roots_and_softplus_storage(ns):
+    v = ns.NormalVariable(0.5, 2.0, "w", learnable=True)
+    names = sorted(p.name for p in v.parents)
+    assert names == ["w_loc", "w_scale"]
+    rho = v.roots["scale"].value
+    assert isinstance(rho, torch.nn.Parameter) and rho.shape == (1, 1, 1, 1)
+    np.testing.assert_allclose(torch.nn.functional.softplus(rho).item(), 2.0, rtol=1e-6)
+    np.testing.assert_allclose(rho.item(), np.log(np.exp(2.0) - 1), rtol=1e-6)
+
+
+def test_bnn_lowers_to_k3_tied(ns):
+    from brancher_b200 import lowering
+    model, Q, d = zoo.bnn(ns, 1, B=12, P=20, H=7, C=4)
+    plan = lowering.get_plan(model, model.posterior_model)
+    assert plan.family.startswith("bnn")
+    assert [s.name for s in plan.latents] == ["weights1", "b1", "weights2", "b2"]
+    assert [s.shape for s in plan.latents] == [(7, 20), (7, 1), (4, 7), (4, 1)]
+    assert all(s.tied for s in plan.latents)       # numeric hyper-parameters on both sides => name collision
+    assert lowering.get_plan(model, model.posterior_model) is plan      # cached
+
+
+@pytest.mark.parametrize("tied", [True, False])
+def test_logreg_lowers_to_k2(ns, tied):
+    from brancher_b200 import lowering
+    model, Q, d = zoo.logreg(ns, 3, B=40, F=8, tied=tied)
+    plan = lowering.get_plan(model, model.posterior_model)
+    assert plan.family.startswith("linear") and plan.C == 1
+    spec = plan.latents[0]
+    assert spec.tied == tied
+    if not tied:
+        np.testing.assert_allclose(spec.prior_scale.cpu().numpy().reshape(-1), 0.5)
+        np.testing.assert_allclose(spec.prior_loc.cpu().numpy().reshape(-1), 0.0)
+
+
+def test_unsupported_graph_raises(ns):
+    from brancher_b200 import lowering
+    x = ns.RootVariable(np.random.rand(5, 3, 1), "x", is_observed=True)
+    w = ns.NormalVariable(np.zeros((1, 3)), np.ones((1, 3)), "weights")
+    k = ns.BinomialVariable(1, logits=ns.BF.sin(ns.BF.matmul(w, x)), name="k")
+    model = ns.ProbabilisticModel([k])
+    k.observe(np.ones((5, 1)))
+    model.set_posterior_model(ns.ProbabilisticModel([ns.NormalVariable(np.zeros((1, 3)), np.ones((1, 3)), "weights",
+                                                                       learnable=True)]))
+    with pytest.raises(lowering.UnsupportedModelError):
+        lowering.get_plan(model, model.posterior_model)
+
+
+def test_no_cpu_fallback_for_elbo(ns):
+    model, Q, d = zoo.logreg(ns, 3, B=40, F=8, tied=True)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ns.inference.ReverseKL().compute_loss(model, model.posterior_model, None, 4)
+
+
+def test_eager_sampling_api(ns):
+    model, Q, d = zoo.bnn(ns, 1, B=12, P=20, H=7, C=4)
+    s = model._get_posterior_sample(3)
+    by_name = {v.name: t for v, t in s.items() if torch.is_tensor(t)}
+    assert by_name["weights1"].shape == (3, 1, 7, 20)
+    assert by_name["k"].shape == (3, 12, 4, 1)
+    lp = model.calculate_log_probability(model._get_sample(2))
+    assert lp.shape == (2, 1)          # observed node summed over the data axis
+    frame = model.get_sample(2)
+    assert frame.shape[0] == 2 and "k" in frame.columns
+
+
+def test_optimizer_collects_parameters(ns):
+    from brancher_b200.optimizers import ProbabilisticOptimizer
+    model, Q, d = zoo.bnn(ns, 1, B=12, P=20, H=7, C=4)
+    opt = ProbabilisticOptimizer(model.posterior_model, "SGD", lr=0.1)
+    assert len(list(opt.module.parameters())) == 8
+    assert sum(p.numel() for p in opt.module.parameters()) == 2 * (7 * 20 + 7 + 4 * 7 + 4)
+
+
+def test_shard_is_balanced_partition():
+    from brancher_b200 import distributed as D
+    for total, world in [(256, 8), (10, 3), (5, 8), (0, 2)]:
+        parts = [D.shard(total, world, r) for r in range(world)]
+        assert sum(c for _, c in parts) == total
+        pos = 0
+        for first, count in parts:
+            assert first == pos
+            pos += count
+        assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
