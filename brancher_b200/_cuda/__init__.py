@@ -47,6 +47,9 @@ SYMBOLS = {
                                             ctypes.POINTER(ctypes.c_longlong)]),
     "brn_profile_reset": (None, []),
     "brn_launch_count": (ctypes.c_longlong, []),
+    "brn_gemm_nt_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 3),
+    "brn_gemm_nt_3xtf32": (ctypes.c_int, [ctypes.c_void_p] * 3 + [ctypes.c_int] * 3 +
+                           [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "brn_philox_normal_fill": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint32,
                                               ctypes.POINTER(SampleRange), ctypes.c_void_p]),
     "brn_mf_normal_prior_entropy": (ctypes.c_int, [ctypes.POINTER(MFVar), ctypes.c_void_p, ctypes.c_void_p,
@@ -234,3 +237,14 @@ def linear_elbo_fwd_bwd(X, y, likelihood, w, C, r, with_prior=True, loss=None):
                                          ctypes.byref(r), ws.data_ptr(), ws.numel(), int(with_prior),
                                          _ptr(loss, torch.float64), _stream(dev)), "brn_linear_elbo_fwd_bwd")
     return loss
+
+
+def gemm_nt_3xtf32(A, B):
+    """D = A @ B.T on the tcgen05 path (3xTF32); A [M,K], B [N,K] fp32 CUDA tensors."""
+    M, K = A.shape
+    N = B.shape[0]
+    D = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    ws = _workspace(A.device, lib().brn_gemm_nt_workspace_bytes(M, N, K))
+    _check(lib().brn_gemm_nt_3xtf32(_ptr(A, what="A"), _ptr(B, what="B"), _ptr(D), M, N, K, ws.data_ptr(), ws.numel(),
+                                    _stream(A.device)), "brn_gemm_nt_3xtf32")
+    return D

@@ -1,0 +1,159 @@
+// Host side of the tcgen05 GEMM building block: TMA descriptor encoding (driver entry point resolved at
+// run time -- no link-time libcuda dependency), the TF32 hi/lo splitter, and a plain GEMM entry point
+// (brn_gemm_nt_3xtf32) used by the tests to validate the tensor-core path in isolation.
+#include "umma_gemm.cuh"
+
+#include <cudaTypedefs.h>
+
+namespace brn {
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+    return fn;
+}
+
+int make_tmap_2d_f32(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    auto fn = get_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return -4; }
+    if (((uintptr_t)base & 15) || (ld * sizeof(float)) % 16) {
+        set_error("TMA operand must be 16-byte aligned with a 16-byte multiple row pitch (base=%p ld=%llu)", (const void*)base,
+                  (unsigned long long)ld);
+        return -1;
+    }
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstr[1] = {ld * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)UG_BK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu ld=%llu box=%u)",
+                                       (int)r, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
+        return -4; }
+    return 0;
+}
+
+// hi/lo split of src [rows][cols] (row pitch lds) into dst_hi/dst_lo [rows][ldd]; optionally also the
+// transposed pair [cols][ldt].  Pad columns (>= cols) are not touched (TMA never reads them: the tensor map's
+// extent is `cols`).
+__global__ void split_tf32_kernel(const float* __restrict__ src, int64_t lds, int rows, int cols, float* __restrict__ hi,
+                                  float* __restrict__ lo, int64_t ldd, float* __restrict__ thi, float* __restrict__ tlo,
+                                  int64_t ldt) {
+    __shared__ float th[32][33], tl[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;       // 32 x 8
+    for (int i = ty; i < 32; i += 8) {
+        int r = r0 + i, c = c0 + tx;
+        float h = 0.f, l = 0.f;
+        if (r < rows && c < cols) {
+            umma::split_tf32(src[(int64_t)r * lds + c], h, l);
+            hi[(int64_t)r * ldd + c] = h;
+            lo[(int64_t)r * ldd + c] = l;
+        }
+        th[i][tx] = h; tl[i][tx] = l;
+    }
+    if (thi == nullptr) return;
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        int c = c0 + i, r = r0 + tx;
+        if (r < rows && c < cols) {
+            thi[(int64_t)c * ldt + r] = th[tx][i];
+            tlo[(int64_t)c * ldt + r] = tl[tx][i];
+        }
+    }
+}
+
+int launch_split_tf32(const float* src, int64_t lds, int rows, int cols, float* hi, float* lo, int64_t ldd, float* thi,
+                      float* tlo, int64_t ldt, cudaStream_t stream) {
+    if (rows <= 0 || cols <= 0) return 0;
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+    split_tf32_kernel<<<grid, block, 0, stream>>>(src, lds, rows, cols, hi, lo, ldd, thi, tlo, ldt);
+    BRN_LAUNCH_OK("split_tf32_kernel");
+    return 0;
+}
+
+template <int BN, class Epi>
+int launch_umma_nt(const float* Ah, const float* Al, int M, int64_t lda, const float* Bh, const float* Bl, int N, int64_t ldb,
+                   int K, int mode, int grid_hint, const typename Epi::Params& ep, cudaStream_t stream) {
+    CUtensorMap tAh, tAl, tBh, tBl;
+    if (int e = make_tmap_2d_f32(&tAh, Ah, M, K, lda, UG_BM)) return e;
+    if (int e = make_tmap_2d_f32(&tAl, Al, M, K, lda, UG_BM)) return e;
+    if (int e = make_tmap_2d_f32(&tBh, Bh, N, K, ldb, BN)) return e;
+    if (int e = make_tmap_2d_f32(&tBl, Bl, N, K, ldb, BN)) return e;
+    const int m_tiles = (M + UG_BM - 1) / UG_BM, n_tiles = (N + BN - 1) / BN, k_chunks = (K + UG_BK - 1) / UG_BK;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int grid;
+    if (mode == 0) {
+        grid = m_tiles * n_tiles < sms ? m_tiles * n_tiles : sms;
+    } else {
+        int G = sms / m_tiles;
+        if (G < 1) G = 1;
+        if (G > n_tiles) G = n_tiles;
+        grid = G * m_tiles;
+    }
+    if (grid_hint > 0 && grid_hint < grid && mode == 0) grid = grid_hint;
+    auto kern = umma_nt_3xtf32_kernel<BN, Epi>;
+    const int smem = UmmaSmem<BN>::TOTAL;
+    BRN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid, 64 + 32 * Epi::kEpiWarps, smem, stream>>>(tAh, tAl, tBh, tBl, m_tiles, n_tiles, k_chunks, mode, ep);
+    BRN_LAUNCH_OK("umma_nt_3xtf32_kernel");
+    return 0;
+}
+
+// explicit instantiations used elsewhere
+template int launch_umma_nt<224, EpiStoreBlocks>(const float*, const float*, int, int64_t, const float*, const float*, int,
+                                                 int64_t, int, int, int, const EpiStoreBlocks::Params&, cudaStream_t);
+
+}  // namespace brn
+
+using namespace brn;
+
+static size_t pad4(size_t n) { return (n + 3) / 4 * 4; }
+
+extern "C" size_t brn_gemm_nt_workspace_bytes(int M, int N, int K) {
+    size_t ld = pad4((size_t)K);
+    return sizeof(float) * 2 * ((size_t)M * ld + (size_t)N * ld) + 4096;
+}
+
+// D[M][N] (row-major, ldd = N) = A[M][K] . B[N][K]^T with 3xTF32 on tcgen05.
+extern "C" int brn_gemm_nt_3xtf32(const float* A, const float* B, float* D, int M, int N, int K, void* workspace,
+                                  size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    BRN_CHECK_ARG(A && B && D && workspace, "brn_gemm_nt_3xtf32: NULL pointer");
+    BRN_CHECK_ARG(M > 0 && N > 0 && K > 0, "brn_gemm_nt_3xtf32: bad shape");
+    BRN_CHECK_ARG(workspace_bytes >= brn_gemm_nt_workspace_bytes(M, N, K), "brn_gemm_nt_3xtf32: workspace too small");
+    const size_t ld = pad4((size_t)K);
+    float* base = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    float *Ah = base, *Al = Ah + (size_t)M * ld, *Bh = Al + (size_t)M * ld, *Bl = Bh + (size_t)N * ld;
+    if (int e = launch_split_tf32(A, K, M, K, Ah, Al, ld, nullptr, nullptr, 0, stream)) return e;
+    if (int e = launch_split_tf32(B, K, N, K, Bh, Bl, ld, nullptr, nullptr, 0, stream)) return e;
+    EpiStoreBlocks::Params ep;
+    ep.out = D; ep.M = M; ep.ldo = N; ep.blk_cols = 224; ep.blk_valid = 224; ep.blks_per_tile = 1;
+    ep.total_blks = (N + 223) / 224; ep.blk_stride = 224;
+    // the last column block may be partial: handled by an N-bound through blk_valid only when N % 224 == 0,
+    // otherwise the store policy needs the global column bound -> encode it via total_blks/blk_valid per tile
+    if (N % 224 != 0) {
+        // run full blocks with the generic policy, then the ragged tail as a second launch on a column view
+        const int full = N / 224;
+        if (full > 0) {
+            ep.total_blks = full;
+            if (int e = launch_umma_nt<224, EpiStoreBlocks>(Ah, Al, M, ld, Bh, Bl, full * 224, ld, K, 0, 0, ep, stream)) return e;
+        }
+        EpiStoreBlocks::Params et = ep;
+        et.out = D + (size_t)full * 224; et.blk_valid = N - full * 224; et.total_blks = 1;
+        set_variant("tcgen05");
+        return launch_umma_nt<224, EpiStoreBlocks>(Ah, Al, M, ld, Bh + (size_t)full * 224 * ld, Bl + (size_t)full * 224 * ld,
+                                                   N - full * 224, ld, K, 0, 0, et, stream);
+    }
+    set_variant("tcgen05");
+    return launch_umma_nt<224, EpiStoreBlocks>(Ah, Al, M, ld, Bh, Bl, N, ld, K, 0, 0, ep, stream);
+}

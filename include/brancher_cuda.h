@@ -111,6 +111,14 @@ int brn_linear_elbo_fwd_bwd(const float* X, const void* y, int likelihood, int64
                             void* workspace, size_t workspace_bytes, int with_prior,
                             double* loss, void* stream);
 
+/* Tensor-core building block, exposed for validation: D[M][N] = A[M][K] . B[N][K]^T (all row-major fp32)
+ * computed with tcgen05.mma kind::tf32 and the 3xTF32 hi/lo split (fp32-equivalent accuracy), TMA-fed.
+ * This is the contraction the reference performs as a batched torch.matmul inside _apply_link
+ * (variables.py:436-449 -> BF.matmul, functions.py:28-41). */
+size_t brn_gemm_nt_workspace_bytes(int M, int N, int K);
+int brn_gemm_nt_3xtf32(const float* A, const float* B, float* D, int M, int N, int K,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- measurement hooks (bench.py): per-stage CUDA-event timing on the launch stream + launch count.
  * No reference counterpart (the reference has no profiler). */
 void        brn_profile_enable(int on);
