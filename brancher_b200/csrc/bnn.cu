@@ -9,6 +9,8 @@
 //   5. sample-axis reduction + K1a      gw = sum_s dW_s, gwe = sum_s dW_s*eps_s, prior/entropy, chain rule
 #include "meanfield.cuh"
 #include "sgemm.cuh"
+#include "umma_gemm.cuh"
+#include <stdlib.h>
 
 namespace brn {
 
@@ -29,9 +31,13 @@ struct BnnLayout {
 
 // One CTA = R rows of the batch for one sample; one thread per row.
 // pre (in):  X.W1_s^T without bias;  pre (out): d ll_s / d pre.
+// If dpT_hi != NULL the result is written transposed and TF32-split instead of in place:
+//   dpT_{hi,lo}[(s*Hp + h) * ldB + b]   (rows h in [H, Hp) zero) -- the K-major B operand of the tcgen05
+//   weight-gradient GEMM.
 __global__ void bnn_mid_kernel(float* __restrict__ pre, const float* __restrict__ W, float* __restrict__ dW,
                                const int32_t* __restrict__ y, BnnLayout L, int R, float inv_S,
-                               double* __restrict__ loss) {
+                               double* __restrict__ loss, float* __restrict__ dpT_hi, float* __restrict__ dpT_lo,
+                               int Hp, int64_t ldB) {
     extern __shared__ float sm[];
     const int H = L.H, C = L.C, B = L.B, HP = H + 1;
     float* tile = sm;                    // [R][H+1]
@@ -127,20 +133,115 @@ __global__ void bnn_mid_kernel(float* __restrict__ pre, const float* __restrict_
         for (int rr = 0; rr < R; ++rr) acc += tile[rr * HP + h];
         atomicAdd(&dWs[L.ob1 + h], acc);
     }
-    for (int idx = t; idx < R * H; idx += nt) {
-        int rr = idx / H, h = idx - rr * H;
-        if (b0 + rr < B) pre_s[(int64_t)(b0 + rr) * H + h] = tile[rr * HP + h];
+    if (dpT_hi != nullptr) {
+        for (int idx = t; idx < Hp * R; idx += nt) {
+            int h = idx / R, rr = idx - h * R;
+            if (b0 + rr >= B) continue;
+            float hi = 0.f, lo = 0.f;
+            if (h < H) umma::split_tf32(tile[rr * HP + h], hi, lo);
+            int64_t o = ((int64_t)s * Hp + h) * ldB + b0 + rr;
+            dpT_hi[o] = hi;
+            dpT_lo[o] = lo;
+        }
+    } else {
+        for (int idx = t; idx < R * H; idx += nt) {
+            int rr = idx / H, h = idx - rr * H;
+            if (b0 + rr < B) pre_s[(int64_t)(b0 + rr) * H + h] = tile[rr * HP + h];
+        }
     }
     double tot = block_sum<double>((double)ll, red);
     if (t == 0) atomicAdd(loss, -tot * (double)inv_S);
 }
 
+// W1_s = mu + softplus(rho)*eps_s, TF32-split, in the padded K-major layout [S][Hp][ldP] (rows h >= H zero)
+__global__ void sample_w1_split_kernel(const float* __restrict__ mu, const float* __restrict__ rho,
+                                       const float* __restrict__ eps, int64_t lde, float* __restrict__ hi,
+                                       float* __restrict__ lo, int H, int P, int Hp, int64_t ldP) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x, h = blockIdx.y, s = blockIdx.z;
+    if (p >= P) return;
+    float vh = 0.f, vl = 0.f;
+    if (h < H) {
+        const int64_t i = (int64_t)h * P + p;
+        umma::split_tf32(__fmaf_rn(softplusf(rho[i]), eps[(int64_t)s * lde + i], mu[i]), vh, vl);
+    }
+    const int64_t o = ((int64_t)s * Hp + h) * ldP + p;
+    hi[o] = vh;
+    lo[o] = vl;
+}
+
+// Epilogue of the tcgen05 weight-gradient GEMM  D[p, (j, h)] = sum_b X[b, p] * dpre_{s_j}[b, h]:
+// fold the sample axis on chip, gw[h,p] += D, gwe[h,p] += D * eps_s[h,p], in registers across all the
+// sample tiles of this CTA (mode 1: fixed p-tile), one atomic flush at the end.  No per-sample weight
+// gradient ever reaches HBM.
+template <int HP, int NSAMP>
+struct EpiGradW1 {
+    static constexpr int kEpiWarps = 8;
+    static constexpr int HALF = HP / 2;
+    struct Params {
+        const float* eps; int64_t lde; float* gw; float* gwe; int P, H, S;
+    };
+    float agw[HALF], agwe[HALF];
+    int p;
+    __device__ void begin(const Params&, int, int) {
+#pragma unroll
+        for (int i = 0; i < HALF; ++i) { agw[i] = 0.f; agwe[i] = 0.f; }
+        p = -1;
+    }
+    __device__ void tile(const Params& ep, int mt, int nt, uint32_t tmem_base, int ew, int lane) {
+        const int q = (ew + 2) & 3, half = ew >> 2;
+        p = mt * UG_BM + q * 32 + lane;
+        const bool pv = p < ep.P;
+#pragma unroll 1
+        for (int j = 0; j < NSAMP; ++j) {
+            const int s = nt * NSAMP + j;
+            float v[HALF], w[HALF];
+            const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + j * HP + half * HALF;
+#pragma unroll
+            for (int c = 0; c < HALF; c += 8) {
+                umma::tmem_ld_32x8(t0 + c, v + c);
+                umma::tmem_ld_32x8(t0 + UG_CORR_COL + c, w + c);
+            }
+            umma::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < HALF; ++i) v[i] += w[i];
+            if (pv && s < ep.S) {
+                const float* e = ep.eps + (int64_t)s * ep.lde + p;
+#pragma unroll
+                for (int i = 0; i < HALF; ++i) {
+                    const int h = half * HALF + i;
+                    if (h < ep.H) {
+                        agw[i] += v[i];
+                        agwe[i] = __fmaf_rn(v[i], e[(int64_t)h * ep.P], agwe[i]);
+                    }
+                }
+            }
+        }
+    }
+    __device__ void end(const Params& ep, int ew, int lane) {
+        if (p < 0 || p >= ep.P) return;
+        const int half = ew >> 2;
+#pragma unroll
+        for (int i = 0; i < HALF; ++i) {
+            const int h = half * HALF + i;
+            if (h < ep.H) {
+                atomicAdd(&ep.gw[(int64_t)h * ep.P + p], agw[i]);
+                atomicAdd(&ep.gwe[(int64_t)h * ep.P + p], agwe[i]);
+            }
+        }
+    }
+};
+
 static size_t bnn_mid_smem(int R, int H, int C) {
     return sizeof(float) * ((size_t)R * (H + 1) + (size_t)C * H + H + C + (size_t)R * C);
 }
 
+constexpr int BNN_UMMA_HP = 112;     // padded hidden width of the instantiated tcgen05 variant
+constexpr int BNN_UMMA_NSAMP = 2;    // samples per MMA N tile (N = 224)
+
 struct BnnWorkspace {
     float *eps, *W, *dW, *pre, *gw, *gwe;
+    float *Xh, *Xl, *Xth, *Xtl, *Wh, *Wl, *dph, *dpl;   // tcgen05 variant: TF32-split operands
+    int64_t ldP, ldB;
     size_t bytes;
     BnnWorkspace(void* base, const BnnLayout& L, int S) {
         size_t off = 0;
@@ -155,6 +256,13 @@ struct BnnWorkspace {
         pre = take((size_t)S * L.B * L.H);
         gw = take(L.ldw);
         gwe = take(L.ldw);
+        ldP = (L.P + 3) / 4 * 4;
+        ldB = (L.B + 3) / 4 * 4;
+        Xh = take((size_t)L.B * ldP); Xl = take((size_t)L.B * ldP);
+        Xth = take((size_t)L.P * ldB); Xtl = take((size_t)L.P * ldB);
+        const size_t rowsW = (size_t)(S + BNN_UMMA_NSAMP) * BNN_UMMA_HP;
+        Wh = take(rowsW * ldP); Wl = take(rowsW * ldP);
+        dph = take(rowsW * ldB); dpl = take(rowsW * ldB);
         bytes = off;
     }
 };
@@ -192,33 +300,65 @@ extern "C" int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int
     if (S == 0) return 0;
     BnnWorkspace ws(workspace, L, S);
     BRN_CHECK_ARG(workspace && workspace_bytes >= ws.bytes, "workspace too small: %zu < %zu", workspace_bytes, ws.bytes);
-    set_variant("simt");
+    // variant: tcgen05 (TMA + 3xTF32 tensor-core GEMMs) when the padded hidden width matches the instantiated
+    // tile, else the fp32 SIMT GEMMs.  BRN_BNN_VARIANT=simt|tcgen05 forces one (tests compare both).
+    bool use_tc = (H > BNN_UMMA_HP - 16 && H <= BNN_UMMA_HP);
+    if (const char* env = getenv("BRN_BNN_VARIANT")) {
+        if (!strcmp(env, "simt")) use_tc = false;
+        else if (!strcmp(env, "tcgen05")) {
+            BRN_CHECK_ARG(H <= BNN_UMMA_HP, "BRN_BNN_VARIANT=tcgen05 needs H <= %d (got %d)", BNN_UMMA_HP, H);
+            use_tc = true;
+        }
+    }
+    set_variant(use_tc ? "tcgen05" : "simt");
+    constexpr int HP = BNN_UMMA_HP, NS = BNN_UMMA_NSAMP, BN = HP * NS;
 
     // 1. noise + weights
     const float* eps_ptr[4];
     int64_t eps_ld[4];
     {
-    StageTimer st("bnn.sample_weights", stream);
-    for (int v = 0; v < 4; ++v) {
-        if (vars[v].eps) {
-            eps_ptr[v] = vars[v].eps;
-            eps_ld[v] = numels[v];
-        } else {
-            if (int e = launch_philox_fill(ws.eps + offs[v], L.ldw, numels[v], vars[v].var_id, *r, stream)) return e;
-            eps_ptr[v] = ws.eps + offs[v];
-            eps_ld[v] = L.ldw;
+        StageTimer st("bnn.sample_weights", stream);
+        for (int v = 0; v < 4; ++v) {
+            if (vars[v].eps) {
+                eps_ptr[v] = vars[v].eps;
+                eps_ld[v] = numels[v];
+            } else {
+                if (int e = launch_philox_fill(ws.eps + offs[v], L.ldw, numels[v], vars[v].var_id, *r, stream)) return e;
+                eps_ptr[v] = ws.eps + offs[v];
+                eps_ld[v] = L.ldw;
+            }
+            if (use_tc && v == 0) {
+                dim3 grid((P + 255) / 256, HP, S);
+                sample_w1_split_kernel<<<grid, 256, 0, stream>>>(vars[0].mu, vars[0].rho, eps_ptr[0], eps_ld[0], ws.Wh, ws.Wl, H,
+                                                                 P, HP, ws.ldP);
+                BRN_LAUNCH_OK("sample_w1_split_kernel");
+                if (S % NS) {   // the odd tail tile reads one more (all-zero) sample block
+                    BRN_CUDA_OK(cudaMemsetAsync(ws.Wh + (size_t)S * HP * ws.ldP, 0, sizeof(float) * HP * ws.ldP, stream));
+                    BRN_CUDA_OK(cudaMemsetAsync(ws.Wl + (size_t)S * HP * ws.ldP, 0, sizeof(float) * HP * ws.ldP, stream));
+                }
+                if (int e = launch_split_tf32(X, P, B, P, ws.Xh, ws.Xl, ws.ldP, ws.Xth, ws.Xtl, ws.ldB, stream)) return e;
+                continue;
+            }
+            if (int e = launch_sample_weights(vars[v].mu, vars[v].rho, eps_ptr[v], eps_ld[v], ws.W + offs[v], L.ldw,
+                                              numels[v], S, stream))
+                return e;
         }
-        if (int e = launch_sample_weights(vars[v].mu, vars[v].rho, eps_ptr[v], eps_ld[v], ws.W + offs[v], L.ldw,
-                                          numels[v], S, stream))
-            return e;
-    }
     }
     // 2. pre_s = X . W1_s^T
     {
         StageTimer st("bnn.gemm_fwd", stream);
-        if (int e = launch_sgemm_batched<true, true>(X, P, 0, ws.W + L.oW1, P, L.ldw, ws.pre, H, (int64_t)B * H, B, H, P,
-                                                     S, stream))
-            return e;
+        if (use_tc) {
+            EpiStoreBlocks::Params ep;
+            ep.out = ws.pre; ep.M = B; ep.ldo = H; ep.blk_cols = HP; ep.blk_valid = H; ep.blks_per_tile = NS;
+            ep.total_blks = S; ep.blk_stride = (int64_t)B * H;
+            if (int e = launch_umma_nt<BN, EpiStoreBlocks>(ws.Xh, ws.Xl, B, ws.ldP, ws.Wh, ws.Wl, S * HP, ws.ldP, P, 0, 0, ep,
+                                                          stream))
+                return e;
+        } else {
+            if (int e = launch_sgemm_batched<true, true>(X, P, 0, ws.W + L.oW1, P, L.ldw, ws.pre, H, (int64_t)B * H, B, H, P,
+                                                         S, stream))
+                return e;
+        }
     }
     // 3. mid
     BRN_CUDA_OK(cudaMemset2DAsync(ws.dW + L.ob1, L.ldw * sizeof(float), 0, (L.numel - L.ob1) * sizeof(float), S, stream));
@@ -230,22 +370,38 @@ extern "C" int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int
         BRN_CHECK_ARG(smem <= 220 * 1024, "brn_bnn_elbo_fwd_bwd: hidden width H=%d too large for the mid kernel", H);
         BRN_CUDA_OK(cudaFuncSetAttribute(bnn_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid((B + R - 1) / R, S);
-        bnn_mid_kernel<<<grid, R, smem, stream>>>(ws.pre, ws.W, ws.dW, y, L, R, 1.0f / (float)r->s_total, loss);
+        bnn_mid_kernel<<<grid, R, smem, stream>>>(ws.pre, ws.W, ws.dW, y, L, R, 1.0f / (float)r->s_total, loss,
+                                                  use_tc ? ws.dph : nullptr, use_tc ? ws.dpl : nullptr, HP, ws.ldB);
         BRN_LAUNCH_OK("bnn_mid_kernel");
     }
-    // 4. dW1_s = dpre_s^T . X
+    // 4. dW1_s = dpre_s^T . X   (tcgen05: folded over samples in the GEMM epilogue -> gw, gwe directly)
     {
         StageTimer st("bnn.gemm_bwd", stream);
-        if (int e = launch_sgemm_batched<false, false>(ws.pre, H, (int64_t)B * H, X, P, 0, ws.dW + L.oW1, P, L.ldw, H, P,
-                                                       B, S, stream))
-            return e;
+        if (use_tc) {
+            if (S % NS) {
+                BRN_CUDA_OK(cudaMemsetAsync(ws.dph + (size_t)S * HP * ws.ldB, 0, sizeof(float) * HP * ws.ldB, stream));
+                BRN_CUDA_OK(cudaMemsetAsync(ws.dpl + (size_t)S * HP * ws.ldB, 0, sizeof(float) * HP * ws.ldB, stream));
+            }
+            BRN_CUDA_OK(cudaMemsetAsync(ws.gw + L.oW1, 0, sizeof(float) * numels[0], stream));
+            BRN_CUDA_OK(cudaMemsetAsync(ws.gwe + L.oW1, 0, sizeof(float) * numels[0], stream));
+            EpiGradW1<HP, NS>::Params ep;
+            ep.eps = eps_ptr[0]; ep.lde = eps_ld[0]; ep.gw = ws.gw + L.oW1; ep.gwe = ws.gwe + L.oW1; ep.P = P; ep.H = H; ep.S = S;
+            if (int e = launch_umma_nt<BN, EpiGradW1<HP, NS>>(ws.Xth, ws.Xtl, P, ws.ldB, ws.dph, ws.dpl, S * HP, ws.ldB, B, 1, 0,
+                                                              ep, stream))
+                return e;
+        } else {
+            if (int e = launch_sgemm_batched<false, false>(ws.pre, H, (int64_t)B * H, X, P, 0, ws.dW + L.oW1, P, L.ldw, H, P,
+                                                           B, S, stream))
+                return e;
+        }
     }
     // 5. reduce over samples + prior/entropy + chain rule
     StageTimer st5("bnn.reduce_finalize", stream);
     for (int v = 0; v < 4; ++v) {
-        if (int e = launch_reduce_over_samples(ws.dW + offs[v], L.ldw, eps_ptr[v], eps_ld[v], ws.gw + offs[v],
-                                               ws.gwe + offs[v], numels[v], S, stream))
-            return e;
+        if (!(use_tc && v == 0))
+            if (int e = launch_reduce_over_samples(ws.dW + offs[v], L.ldw, eps_ptr[v], eps_ld[v], ws.gw + offs[v],
+                                                   ws.gwe + offs[v], numels[v], S, stream))
+                return e;
         if (int e = launch_mf_finalize(vars[v], eps_ptr[v], eps_ld[v], ws.gw + offs[v], ws.gwe + offs[v], *r, with_prior,
                                        loss, stream))
             return e;

@@ -140,16 +140,27 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float (&v)[16]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// split an fp32 into two TF32-exact parts: hi = top 19 bits, lo = (x - hi) truncated likewise.
-// hi + lo == x up to 2^-22 |x|; both are exactly representable in TF32, so the tensor core's own
-// fp32->tf32 conversion (whatever its rounding) is the identity on them.
+// split an fp32 into two TF32-exact parts (round-to-nearest on the 13 dropped mantissa bits):
+//   hi = rn_tf32(x),  lo = rn_tf32(x - hi)      =>  |x - hi - lo| <= 2^-24 |x|
+// both are exactly representable in TF32, so the tensor core's own fp32->tf32 conversion (whatever its
+// rounding) is the identity on them; the dropped lo*lo product is O(2^-24) relative as well.
+__device__ __forceinline__ float rn_tf32(float x) {
+    return __uint_as_float((__float_as_uint(x) + 0x00001000u) & 0xFFFFE000u);
+}
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-    lo = __uint_as_float(__float_as_uint(x - hi) & 0xFFFFE000u);
+    hi = rn_tf32(x);
+    lo = rn_tf32(x - hi);
 }
 
 }  // namespace umma

@@ -79,40 +79,6 @@ int launch_split_tf32(const float* src, int64_t lds, int rows, int cols, float* 
     return 0;
 }
 
-template <int BN, class Epi>
-int launch_umma_nt(const float* Ah, const float* Al, int M, int64_t lda, const float* Bh, const float* Bl, int N, int64_t ldb,
-                   int K, int mode, int grid_hint, const typename Epi::Params& ep, cudaStream_t stream) {
-    CUtensorMap tAh, tAl, tBh, tBl;
-    if (int e = make_tmap_2d_f32(&tAh, Ah, M, K, lda, UG_BM)) return e;
-    if (int e = make_tmap_2d_f32(&tAl, Al, M, K, lda, UG_BM)) return e;
-    if (int e = make_tmap_2d_f32(&tBh, Bh, N, K, ldb, BN)) return e;
-    if (int e = make_tmap_2d_f32(&tBl, Bl, N, K, ldb, BN)) return e;
-    const int m_tiles = (M + UG_BM - 1) / UG_BM, n_tiles = (N + BN - 1) / BN, k_chunks = (K + UG_BK - 1) / UG_BK;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int grid;
-    if (mode == 0) {
-        grid = m_tiles * n_tiles < sms ? m_tiles * n_tiles : sms;
-    } else {
-        int G = sms / m_tiles;
-        if (G < 1) G = 1;
-        if (G > n_tiles) G = n_tiles;
-        grid = G * m_tiles;
-    }
-    if (grid_hint > 0 && grid_hint < grid && mode == 0) grid = grid_hint;
-    auto kern = umma_nt_3xtf32_kernel<BN, Epi>;
-    const int smem = UmmaSmem<BN>::TOTAL;
-    BRN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, 64 + 32 * Epi::kEpiWarps, smem, stream>>>(tAh, tAl, tBh, tBl, m_tiles, n_tiles, k_chunks, mode, ep);
-    BRN_LAUNCH_OK("umma_nt_3xtf32_kernel");
-    return 0;
-}
-
-// explicit instantiations used elsewhere
-template int launch_umma_nt<224, EpiStoreBlocks>(const float*, const float*, int, int64_t, const float*, const float*, int,
-                                                 int64_t, int, int, int, const EpiStoreBlocks::Params&, cudaStream_t);
-
 }  // namespace brn
 
 using namespace brn;

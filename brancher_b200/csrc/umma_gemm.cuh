@@ -15,6 +15,7 @@ namespace brn {
 constexpr int UG_BM = 128;        // rows of A per tile (TMEM lanes)
 constexpr int UG_BK = 32;         // fp32 elements per K chunk = 128 B = one swizzle row
 constexpr int UG_STAGES = 2;
+constexpr int UG_CORR_COL = 256;  // TMEM column offset of the correction accumulator
 
 template <int BN>
 struct UmmaSmem {
@@ -49,7 +50,12 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
                       const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                       int m_tiles, int n_tiles, int k_chunks, int mode, typename Epi::Params ep) {
     using SM = UmmaSmem<BN>;
-    constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    // two accumulators: [0, BN) main (A_hi.B_hi) and [UG_CORR_COL, +BN) correction (A_lo.B_hi + A_hi.B_lo).
+    // The tensor core truncates (round-toward-zero) the fp32 accumulator after every MMA -- measured on
+    // B200: relative bias -2.7e-8 per instruction -- so the tiny correction terms are kept out of the main
+    // chain (3x fewer truncations of the large partial sums) and added once, in RN, by the epilogue.
+    static_assert(BN <= UG_CORR_COL, "BN too large for the dual-accumulator layout");
+    constexpr uint32_t TMEM_COLS = 512;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) uint64_t full_bar[UG_STAGES], empty_bar[UG_STAGES], accum_full, accum_empty;
@@ -108,9 +114,9 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
                         const uint32_t ko = ks * 32;               // 8 tf32 = 32 bytes along K inside the swizzle row
                         const uint64_t dah = umma::smem_desc_k_sw128(ah + ko), dal = umma::smem_desc_k_sw128(al + ko);
                         const uint64_t dbh = umma::smem_desc_k_sw128(bh + ko), dbl = umma::smem_desc_k_sw128(bl + ko);
-                        umma::mma_tf32_ss(tmem_base, dal, dbh, idesc, (kc | ks) != 0);
-                        umma::mma_tf32_ss(tmem_base, dah, dbl, idesc, true);
-                        umma::mma_tf32_ss(tmem_base, dah, dbh, idesc, true);
+                        umma::mma_tf32_ss(tmem_base + UG_CORR_COL, dal, dbh, idesc, (kc | ks) != 0);
+                        umma::mma_tf32_ss(tmem_base + UG_CORR_COL, dah, dbl, idesc, true);
+                        umma::mma_tf32_ss(tmem_base, dah, dbh, idesc, (kc | ks) != 0);
                     }
                     umma::mma_commit(&empty_bar[stage]);           // smem stage reusable once these MMAs retire
                     if (++stage == UG_STAGES) { stage = 0; phase ^= 1; }
@@ -162,9 +168,12 @@ struct EpiStoreBlocks {
         const int row = mt * UG_BM + q * 32 + lane;
         const int ncols = p.blk_cols * p.blks_per_tile;
         for (int c0 = 0; c0 < ncols; c0 += 32) {
-            float v[32];
+            float v[32], w[32];
             umma::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
+            umma::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + UG_CORR_COL + c0, w);
             umma::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += w[i];
             if (row < p.M) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
@@ -179,5 +188,41 @@ struct EpiStoreBlocks {
         umma::tmem_ld_wait();
     }
 };
+
+int launch_split_tf32(const float* src, int64_t lds, int rows, int cols, float* hi, float* lo, int64_t ldd, float* thi,
+                      float* tlo, int64_t ldt, cudaStream_t stream);
+
+// A (hi/lo) [M][K] pitch lda, B (hi/lo) [N][K] pitch ldb; mode 0: units n-major round-robin over CTAs,
+// mode 1: every CTA keeps one m-tile and strides over n-tiles (epilogues that accumulate across units).
+template <int BN, class Epi>
+inline int launch_umma_nt(const float* Ah, const float* Al, int M, int64_t lda, const float* Bh, const float* Bl, int N, int64_t ldb,
+                   int K, int mode, int grid_hint, const typename Epi::Params& ep, cudaStream_t stream) {
+    CUtensorMap tAh, tAl, tBh, tBl;
+    if (int e = make_tmap_2d_f32(&tAh, Ah, M, K, lda, UG_BM)) return e;
+    if (int e = make_tmap_2d_f32(&tAl, Al, M, K, lda, UG_BM)) return e;
+    if (int e = make_tmap_2d_f32(&tBh, Bh, N, K, ldb, BN)) return e;
+    if (int e = make_tmap_2d_f32(&tBl, Bl, N, K, ldb, BN)) return e;
+    const int m_tiles = (M + UG_BM - 1) / UG_BM, n_tiles = (N + BN - 1) / BN, k_chunks = (K + UG_BK - 1) / UG_BK;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int grid;
+    if (mode == 0) {
+        grid = m_tiles * n_tiles < sms ? m_tiles * n_tiles : sms;
+    } else {
+        int G = sms / m_tiles;
+        if (G < 1) G = 1;
+        if (G > n_tiles) G = n_tiles;
+        grid = G * m_tiles;
+    }
+    if (grid_hint > 0 && grid_hint < grid && mode == 0) grid = grid_hint;
+    auto kern = umma_nt_3xtf32_kernel<BN, Epi>;
+    const int smem = UmmaSmem<BN>::TOTAL;
+    BRN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid, 64 + 32 * Epi::kEpiWarps, smem, stream>>>(tAh, tAl, tBh, tBl, m_tiles, n_tiles, k_chunks, mode, ep);
+    BRN_LAUNCH_OK("umma_nt_3xtf32_kernel");
+    return 0;
+}
+
 
 }  // namespace brn

@@ -212,3 +212,38 @@ def test_linear_empty_rows(cu):
     o64 = O.mean_field_prior_entropy(params, eps, prior, dtype=torch.float64)
     loss, grads = run_linear(cu, np.zeros((0, F), "f4"), np.zeros((0,), "f4"), params, eps, cu.BERNOULLI, 1, prior)
     check_against_oracle(loss, grads, o32, o64, "linear N=0")
+
+
+# ---------------------------------------------------------------------------------------------
+# K3 tcgen05 variant (TMA + 3xTF32 tensor-core GEMMs)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,P,H,C,S", [(128, 32, 100, 10, 2), (64, 784, 100, 10, 2), (300, 100, 112, 4, 3),
+                                       (257, 130, 97, 16, 5), (1024, 784, 100, 10, 4), (40, 33, 21, 3, 1),
+                                       (130, 37, 5, 2, 4)])
+@pytest.mark.parametrize("tied", [True, False])
+def test_bnn_tcgen05_variant(cu, monkeypatch, B, P, H, C, S, tied):
+    from oracle import elbo_oracle as O
+    monkeypatch.setenv("BRN_BNN_VARIANT", "tcgen05")
+    X, y, params, eps, shapes = random_bnn(B * 3 + H, B, P, H, C, S)
+    prior = None if tied else {n: (0.0, 10.0) for n in shapes}
+    o32 = O.bnn_elbo(X, y, params, eps, prior)
+    o64 = O.bnn_elbo(X, y, params, eps, prior, dtype=torch.float64)
+    loss, grads, _ = run_bnn(cu, X, y, params, eps, prior)
+    assert cu.last_variant() == "tcgen05"
+    check_against_oracle(loss, grads, o32, o64, "bnn tcgen05 %s" % ((B, P, H, C, S),))
+
+
+def test_bnn_variants_agree_philox(cu, monkeypatch):
+    """Same Philox noise through the SIMT and tcgen05 variants."""
+    B, P, H, C, S = 200, 96, 100, 10, 6
+    X, y, params, _, shapes = random_bnn(9, B, P, H, C, S)
+    r = cu.sample_range(S, seed=5, offset=2)
+    out = {}
+    for variant in ("simt", "tcgen05"):
+        monkeypatch.setenv("BRN_BNN_VARIANT", variant)
+        out[variant] = run_bnn(cu, X, y, params, None, r=r)
+        assert cu.last_variant() == variant
+    assert_close(out["tcgen05"][0], out["simt"][0], "loss", rtol=1e-6)
+    for k in out["simt"][1]:
+        sc = np.abs(out["simt"][1][k]).max()
+        assert_close(out["tcgen05"][1][k], out["simt"][1][k], "grad " + k, rtol=1e-5, atol=2e-6, scale=sc)
