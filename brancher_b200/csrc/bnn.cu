@@ -52,9 +52,16 @@ __global__ void bnn_mid_kernel(float* __restrict__ pre, const float* __restrict_
     float* dWs = dW + (int64_t)s * L.ldw;
     float* pre_s = pre + (int64_t)s * B * H;
 
-    for (int idx = t; idx < R * H; idx += nt) {
-        int r = idx / H, h = idx - r * H;
-        tile[r * HP + h] = (b0 + r < B) ? pre_s[(int64_t)(b0 + r) * H + h] : 0.f;
+    if (dpT_hi != nullptr) {     // tcgen05 variant: pre arrives transposed, [S][H][B]
+        for (int idx = t; idx < R * H; idx += nt) {
+            int h = idx / R, r = idx - h * R;
+            tile[r * HP + h] = (b0 + r < B) ? pre_s[(int64_t)h * B + b0 + r] : 0.f;
+        }
+    } else {
+        for (int idx = t; idx < R * H; idx += nt) {
+            int r = idx / H, h = idx - r * H;
+            tile[r * HP + h] = (b0 + r < B) ? pre_s[(int64_t)(b0 + r) * H + h] : 0.f;
+        }
     }
     for (int idx = t; idx < C * H; idx += nt) W2s[idx] = Ws[L.oW2 + idx];
     for (int idx = t; idx < H; idx += nt) b1s[idx] = Ws[L.ob1 + idx];
@@ -169,68 +176,6 @@ __global__ void sample_w1_split_kernel(const float* __restrict__ mu, const float
     lo[o] = vl;
 }
 
-// Epilogue of the tcgen05 weight-gradient GEMM  D[p, (j, h)] = sum_b X[b, p] * dpre_{s_j}[b, h]:
-// fold the sample axis on chip, gw[h,p] += D, gwe[h,p] += D * eps_s[h,p], in registers across all the
-// sample tiles of this CTA (mode 1: fixed p-tile), one atomic flush at the end.  No per-sample weight
-// gradient ever reaches HBM.
-template <int HP, int NSAMP>
-struct EpiGradW1 {
-    static constexpr int kEpiWarps = 8;
-    static constexpr int HALF = HP / 2;
-    struct Params {
-        const float* eps; int64_t lde; float* gw; float* gwe; int P, H, S;
-    };
-    float agw[HALF], agwe[HALF];
-    int p;
-    __device__ void begin(const Params&, int, int) {
-#pragma unroll
-        for (int i = 0; i < HALF; ++i) { agw[i] = 0.f; agwe[i] = 0.f; }
-        p = -1;
-    }
-    __device__ void tile(const Params& ep, int mt, int nt, uint32_t tmem_base, int ew, int lane) {
-        const int q = (ew + 2) & 3, half = ew >> 2;
-        p = mt * UG_BM + q * 32 + lane;
-        const bool pv = p < ep.P;
-#pragma unroll 1
-        for (int j = 0; j < NSAMP; ++j) {
-            const int s = nt * NSAMP + j;
-            float v[HALF], w[HALF];
-            const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + j * HP + half * HALF;
-#pragma unroll
-            for (int c = 0; c < HALF; c += 8) {
-                umma::tmem_ld_32x8(t0 + c, v + c);
-                umma::tmem_ld_32x8(t0 + UG_CORR_COL + c, w + c);
-            }
-            umma::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < HALF; ++i) v[i] += w[i];
-            if (pv && s < ep.S) {
-                const float* e = ep.eps + (int64_t)s * ep.lde + p;
-#pragma unroll
-                for (int i = 0; i < HALF; ++i) {
-                    const int h = half * HALF + i;
-                    if (h < ep.H) {
-                        agw[i] += v[i];
-                        agwe[i] = __fmaf_rn(v[i], e[(int64_t)h * ep.P], agwe[i]);
-                    }
-                }
-            }
-        }
-    }
-    __device__ void end(const Params& ep, int ew, int lane) {
-        if (p < 0 || p >= ep.P) return;
-        const int half = ew >> 2;
-#pragma unroll
-        for (int i = 0; i < HALF; ++i) {
-            const int h = half * HALF + i;
-            if (h < ep.H) {
-                atomicAdd(&ep.gw[(int64_t)h * ep.P + p], agw[i]);
-                atomicAdd(&ep.gwe[(int64_t)h * ep.P + p], agwe[i]);
-            }
-        }
-    }
-};
-
 static size_t bnn_mid_smem(int R, int H, int C) {
     return sizeof(float) * ((size_t)R * (H + 1) + (size_t)C * H + H + C + (size_t)R * C);
 }
@@ -312,6 +257,8 @@ extern "C" int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int
     }
     set_variant(use_tc ? "tcgen05" : "simt");
     constexpr int HP = BNN_UMMA_HP, NS = BNN_UMMA_NSAMP, BN = HP * NS;
+    int drain = 2;
+    if (const char* env = getenv("BRN_UMMA_DRAIN")) drain = atoi(env);
 
     // 1. noise + weights
     const float* eps_ptr[4];
@@ -348,11 +295,11 @@ extern "C" int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int
     {
         StageTimer st("bnn.gemm_fwd", stream);
         if (use_tc) {
-            EpiStoreBlocks::Params ep;
-            ep.out = ws.pre; ep.M = B; ep.ldo = H; ep.blk_cols = HP; ep.blk_valid = H; ep.blks_per_tile = NS;
-            ep.total_blks = S; ep.blk_stride = (int64_t)B * H;
-            if (int e = launch_umma_nt<BN, EpiStoreBlocks>(ws.Xh, ws.Xl, B, ws.ldP, ws.Wh, ws.Wl, S * HP, ws.ldP, P, 0, 0, ep,
-                                                          stream))
+            EpiStore::Params ep;      // pre^T: [S][H][B], coalesced across the warp's rows b
+            ep.out = ws.pre; ep.rows = B; ep.row_stride = 1; ep.col_stride = B; ep.blk_stride = (int64_t)B * H;
+            ep.blk_valid = H; ep.col_limit = 0; ep.total_blks = S;
+            if (int e = launch_umma_nt<BN, EpiStore>(ws.Xh, ws.Xl, B, ws.ldP, ws.Wh, ws.Wl, S * HP, ws.ldP, P, 0, drain, ep,
+                                                     stream))
                 return e;
         } else {
             if (int e = launch_sgemm_batched<true, true>(X, P, 0, ws.W + L.oW1, P, L.ldw, ws.pre, H, (int64_t)B * H, B, H, P,
@@ -382,12 +329,11 @@ extern "C" int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int
                 BRN_CUDA_OK(cudaMemsetAsync(ws.dph + (size_t)S * HP * ws.ldB, 0, sizeof(float) * HP * ws.ldB, stream));
                 BRN_CUDA_OK(cudaMemsetAsync(ws.dpl + (size_t)S * HP * ws.ldB, 0, sizeof(float) * HP * ws.ldB, stream));
             }
-            BRN_CUDA_OK(cudaMemsetAsync(ws.gw + L.oW1, 0, sizeof(float) * numels[0], stream));
-            BRN_CUDA_OK(cudaMemsetAsync(ws.gwe + L.oW1, 0, sizeof(float) * numels[0], stream));
-            EpiGradW1<HP, NS>::Params ep;
-            ep.eps = eps_ptr[0]; ep.lde = eps_ld[0]; ep.gw = ws.gw + L.oW1; ep.gwe = ws.gwe + L.oW1; ep.P = P; ep.H = H; ep.S = S;
-            if (int e = launch_umma_nt<BN, EpiGradW1<HP, NS>>(ws.Xth, ws.Xtl, P, ws.ldB, ws.dph, ws.dpl, S * HP, ws.ldB, B, 1, 0,
-                                                              ep, stream))
+            EpiStore::Params ep;      // dW1_s[h][p] = D[p, (s, h)]
+            ep.out = ws.dW + L.oW1; ep.rows = P; ep.row_stride = 1; ep.col_stride = P; ep.blk_stride = L.ldw;
+            ep.blk_valid = H; ep.col_limit = 0; ep.total_blks = S;
+            if (int e = launch_umma_nt<BN, EpiStore>(ws.Xth, ws.Xtl, P, ws.ldB, ws.dph, ws.dpl, S * HP, ws.ldB, B, 0, drain, ep,
+                                                     stream))
                 return e;
         } else {
             if (int e = launch_sgemm_batched<false, false>(ws.pre, H, (int64_t)B * H, X, P, 0, ws.dW + L.oW1, P, L.ldw, H, P,
@@ -398,8 +344,7 @@ extern "C" int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int
     // 5. reduce over samples + prior/entropy + chain rule
     StageTimer st5("bnn.reduce_finalize", stream);
     for (int v = 0; v < 4; ++v) {
-        if (!(use_tc && v == 0))
-            if (int e = launch_reduce_over_samples(ws.dW + offs[v], L.ldw, eps_ptr[v], eps_ld[v], ws.gw + offs[v],
+        if (int e = launch_reduce_over_samples(ws.dW + offs[v], L.ldw, eps_ptr[v], eps_ld[v], ws.gw + offs[v],
                                                    ws.gwe + offs[v], numels[v], S, stream))
                 return e;
         if (int e = launch_mf_finalize(vars[v], eps_ptr[v], eps_ld[v], ws.gw + offs[v], ws.gwe + offs[v], *r, with_prior,

@@ -4,6 +4,7 @@
 #include "umma_gemm.cuh"
 
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 namespace brn {
 
@@ -102,24 +103,11 @@ extern "C" int brn_gemm_nt_3xtf32(const float* A, const float* B, float* D, int 
     float *Ah = base, *Al = Ah + (size_t)M * ld, *Bh = Al + (size_t)M * ld, *Bl = Bh + (size_t)N * ld;
     if (int e = launch_split_tf32(A, K, M, K, Ah, Al, ld, nullptr, nullptr, 0, stream)) return e;
     if (int e = launch_split_tf32(B, K, N, K, Bh, Bl, ld, nullptr, nullptr, 0, stream)) return e;
-    EpiStoreBlocks::Params ep;
-    ep.out = D; ep.M = M; ep.ldo = N; ep.blk_cols = 224; ep.blk_valid = 224; ep.blks_per_tile = 1;
-    ep.total_blks = (N + 223) / 224; ep.blk_stride = 224;
-    // the last column block may be partial: handled by an N-bound through blk_valid only when N % 224 == 0,
-    // otherwise the store policy needs the global column bound -> encode it via total_blks/blk_valid per tile
-    if (N % 224 != 0) {
-        // run full blocks with the generic policy, then the ragged tail as a second launch on a column view
-        const int full = N / 224;
-        if (full > 0) {
-            ep.total_blks = full;
-            if (int e = launch_umma_nt<224, EpiStoreBlocks>(Ah, Al, M, ld, Bh, Bl, full * 224, ld, K, 0, 0, ep, stream)) return e;
-        }
-        EpiStoreBlocks::Params et = ep;
-        et.out = D + (size_t)full * 224; et.blk_valid = N - full * 224; et.total_blks = 1;
-        set_variant("tcgen05");
-        return launch_umma_nt<224, EpiStoreBlocks>(Ah, Al, M, ld, Bh + (size_t)full * 224 * ld, Bl + (size_t)full * 224 * ld,
-                                                   N - full * 224, ld, K, 0, 0, et, stream);
-    }
+    EpiStore::Params ep;
+    ep.out = D; ep.rows = M; ep.row_stride = N; ep.col_stride = 1; ep.blk_stride = 112; ep.blk_valid = 112;
+    ep.col_limit = N; ep.total_blks = (N + 111) / 112;
     set_variant("tcgen05");
-    return launch_umma_nt<224, EpiStoreBlocks>(Ah, Al, M, ld, Bh, Bl, N, ld, K, 0, 0, ep, stream);
+    int drain = 2;
+    if (const char* env = getenv("BRN_UMMA_DRAIN")) drain = atoi(env);
+    return launch_umma_nt<224, EpiStore>(Ah, Al, M, ld, Bh, Bl, N, ld, K, 0, drain, ep, stream);
 }

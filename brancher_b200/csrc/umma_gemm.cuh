@@ -3,9 +3,14 @@
 // Operands arrive pre-split in HBM as TF32-exact pairs (hi, lo) -- see umma::split_tf32 -- and are moved
 // by TMA (128-byte swizzle) into a multi-stage shared-memory ring; one elected thread issues
 //     D += A_lo.B_hi^T ; D += A_hi.B_lo^T ; D += A_hi.B_hi^T      (tcgen05.mma kind::tf32, M=128, N=BN, K=8)
-// accumulating in TMEM; epilogue warps read the accumulator with tcgen05.ld and hand it to an epilogue
-// policy (store / fused gradient reduction).  Persistent: each CTA walks a list of (m-tile, n-tile)
-// units; TMA producer, MMA issuer and epilogue are separate warps synchronised only by mbarriers.
+// accumulating in TMEM.  Persistent: each CTA walks a list of (m-tile, n-tile) units; TMA producer, MMA
+// issuer and epilogue are separate warps synchronised only by mbarriers.
+//
+// Accuracy: the tensor core TRUNCATES (round-toward-zero) its fp32 accumulator after every instruction
+// (measured on B200: relative bias -2.7e-8 .. -5e-8 per MMA, i.e. -1e-5 after K=1024), which is outside the
+// 1e-5 parity budget.  The accumulation chain in TMEM is therefore kept short: every `drain_chunks` K chunks
+// the MMA warp switches to the other of two TMEM accumulator buffers and the epilogue warps drain the
+// finished one into fp32 REGISTERS with round-to-nearest adds, fully overlapped with the next block's MMAs.
 #pragma once
 #include "common.cuh"
 #include "umma.cuh"
@@ -15,7 +20,8 @@ namespace brn {
 constexpr int UG_BM = 128;        // rows of A per tile (TMEM lanes)
 constexpr int UG_BK = 32;         // fp32 elements per K chunk = 128 B = one swizzle row
 constexpr int UG_STAGES = 2;
-constexpr int UG_CORR_COL = 256;  // TMEM column offset of the correction accumulator
+constexpr int UG_BUF_COLS = 256;  // TMEM column stride between the two accumulator buffers
+constexpr int UG_EPI_WARPS = 8;   // epilogue warps: 4 TMEM lane quarters x 2 column halves
 
 template <int BN>
 struct UmmaSmem {
@@ -45,20 +51,17 @@ struct UnitIter {
 };
 
 template <int BN, class Epi>
-__global__ void __launch_bounds__(64 + 32 * Epi::kEpiWarps, 1)
+__global__ void __launch_bounds__(64 + 32 * UG_EPI_WARPS, 1)
 umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                       const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
-                      int m_tiles, int n_tiles, int k_chunks, int mode, typename Epi::Params ep) {
+                      int m_tiles, int n_tiles, int k_chunks, int drain_chunks, int mode, typename Epi::Params ep) {
     using SM = UmmaSmem<BN>;
-    // two accumulators: [0, BN) main (A_hi.B_hi) and [UG_CORR_COL, +BN) correction (A_lo.B_hi + A_hi.B_lo).
-    // The tensor core truncates (round-toward-zero) the fp32 accumulator after every MMA -- measured on
-    // B200: relative bias -2.7e-8 per instruction -- so the tiny correction terms are kept out of the main
-    // chain (3x fewer truncations of the large partial sums) and added once, in RN, by the epilogue.
-    static_assert(BN <= UG_CORR_COL, "BN too large for the dual-accumulator layout");
+    constexpr int CPT = BN / 2;                    // accumulator columns per epilogue thread
+    static_assert(BN <= UG_BUF_COLS && CPT % 16 == 0, "unsupported N tile");
     constexpr uint32_t TMEM_COLS = 512;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    __shared__ __align__(8) uint64_t full_bar[UG_STAGES], empty_bar[UG_STAGES], accum_full, accum_empty;
+    __shared__ __align__(8) uint64_t full_bar[UG_STAGES], empty_bar[UG_STAGES], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -67,8 +70,7 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
         umma::tma_prefetch_desc(&tmAh); umma::tma_prefetch_desc(&tmAl);
         umma::tma_prefetch_desc(&tmBh); umma::tma_prefetch_desc(&tmBl);
         for (int s = 0; s < UG_STAGES; ++s) { umma::mbar_init(&full_bar[s], 1); umma::mbar_init(&empty_bar[s], 1); }
-        umma::mbar_init(&accum_full, 1);
-        umma::mbar_init(&accum_empty, Epi::kEpiWarps);
+        for (int b = 0; b < 2; ++b) { umma::mbar_init(&acc_full[b], 1); umma::mbar_init(&acc_empty[b], UG_EPI_WARPS); }
         umma::fence_barrier_init();
     }
     if (warp == 1) umma::tmem_alloc(&tmem_base_slot, TMEM_COLS);
@@ -100,47 +102,72 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
         // ===================== MMA issuer =====================
         if (lane == 0) {
             constexpr uint32_t idesc = umma::idesc_tf32(UG_BM, BN);
-            int stage = 0; uint32_t phase = 0, acc_phase = 0;
+            int stage = 0; uint32_t phase = 0, blk = 0;
             for (UnitIter it(m_tiles, n_tiles, mode); it.valid(); it.next()) {
-                umma::mbar_wait(&accum_empty, acc_phase ^ 1);      // epilogue has drained the accumulator
-                umma::tc_fence_after();
-                for (int kc = 0; kc < k_chunks; ++kc) {
-                    umma::mbar_wait(&full_bar[stage], phase);
+                for (int kc0 = 0; kc0 < k_chunks; kc0 += drain_chunks, ++blk) {
+                    const uint32_t buf = blk & 1, use = (blk >> 1) & 1;
+                    umma::mbar_wait(&acc_empty[buf], use ^ 1);     // epilogue has drained this buffer's previous use
                     umma::tc_fence_after();
-                    const uint32_t st = umma::smem_u32(smem + stage * SM::STAGE_BYTES);
-                    const uint32_t ah = st, al = st + SM::A_BYTES, bh = st + 2 * SM::A_BYTES, bl = bh + SM::B_BYTES;
+                    const uint32_t d_tmem = tmem_base + buf * UG_BUF_COLS;
+                    const int kc1 = min(kc0 + drain_chunks, k_chunks);
+                    for (int kc = kc0; kc < kc1; ++kc) {
+                        umma::mbar_wait(&full_bar[stage], phase);
+                        umma::tc_fence_after();
+                        const uint32_t st = umma::smem_u32(smem + stage * SM::STAGE_BYTES);
+                        const uint32_t ah = st, al = st + SM::A_BYTES, bh = st + 2 * SM::A_BYTES, bl = bh + SM::B_BYTES;
 #pragma unroll
-                    for (int ks = 0; ks < UG_BK / 8; ++ks) {
-                        const uint32_t ko = ks * 32;               // 8 tf32 = 32 bytes along K inside the swizzle row
-                        const uint64_t dah = umma::smem_desc_k_sw128(ah + ko), dal = umma::smem_desc_k_sw128(al + ko);
-                        const uint64_t dbh = umma::smem_desc_k_sw128(bh + ko), dbl = umma::smem_desc_k_sw128(bl + ko);
-                        umma::mma_tf32_ss(tmem_base + UG_CORR_COL, dal, dbh, idesc, (kc | ks) != 0);
-                        umma::mma_tf32_ss(tmem_base + UG_CORR_COL, dah, dbl, idesc, true);
-                        umma::mma_tf32_ss(tmem_base, dah, dbh, idesc, (kc | ks) != 0);
+                        for (int ks = 0; ks < UG_BK / 8; ++ks) {
+                            const uint32_t ko = ks * 32;           // 8 tf32 = 32 bytes along K inside the swizzle row
+                            const uint64_t dah = umma::smem_desc_k_sw128(ah + ko), dal = umma::smem_desc_k_sw128(al + ko);
+                            const uint64_t dbh = umma::smem_desc_k_sw128(bh + ko), dbl = umma::smem_desc_k_sw128(bl + ko);
+                            umma::mma_tf32_ss(d_tmem, dal, dbh, idesc, kc != kc0 || ks != 0);
+                            umma::mma_tf32_ss(d_tmem, dah, dbl, idesc, true);
+                            umma::mma_tf32_ss(d_tmem, dah, dbh, idesc, true);
+                        }
+                        umma::mma_commit(&empty_bar[stage]);       // smem stage reusable once these MMAs retire
+                        if (++stage == UG_STAGES) { stage = 0; phase ^= 1; }
                     }
-                    umma::mma_commit(&empty_bar[stage]);           // smem stage reusable once these MMAs retire
-                    if (++stage == UG_STAGES) { stage = 0; phase ^= 1; }
+                    umma::mma_commit(&acc_full[buf]);
                 }
-                umma::mma_commit(&accum_full);
-                acc_phase ^= 1;
             }
         }
     } else {
         // ===================== epilogue warps =====================
         const int ew = warp - 2;
-        Epi epi;
-        epi.begin(ep, ew, lane);
-        uint32_t acc_phase = 0;
+        const int q = warp & 3;                   // TMEM lane quarter this warp may access (warp id % 4)
+        const int hf = ew >> 2;                   // column half
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + hf * CPT;
+        uint32_t blk = 0;
         for (UnitIter it(m_tiles, n_tiles, mode); it.valid(); it.next()) {
-            umma::mbar_wait(&accum_full, acc_phase);
-            umma::tc_fence_after();
-            epi.tile(ep, it.mt(), it.nt(), tmem_base, ew, lane);   // must end with tmem_ld_wait()
-            umma::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) umma::mbar_arrive(&accum_empty);
-            acc_phase ^= 1;
+            float r[CPT];
+#pragma unroll
+            for (int i = 0; i < CPT; ++i) r[i] = 0.f;
+            for (int kc0 = 0; kc0 < k_chunks; kc0 += drain_chunks, ++blk) {
+                const uint32_t buf = blk & 1, use = (blk >> 1) & 1;
+                umma::mbar_wait(&acc_full[buf], use);
+                umma::tc_fence_after();
+                const uint32_t t0 = t_lane + buf * UG_BUF_COLS;
+#pragma unroll
+                for (int c = 0; c + 32 <= CPT; c += 32) {
+                    float v[32];
+                    umma::tmem_ld_32x32(t0 + c, v);
+                    umma::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) r[c + i] += v[i];
+                }
+                if (CPT % 32) {
+                    float v[16];
+                    umma::tmem_ld_32x16(t0 + (CPT / 32) * 32, v);
+                    umma::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) r[(CPT / 32) * 32 + i] += v[i];
+                }
+                umma::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive(&acc_empty[buf]);
+            }
+            Epi::finish(ep, r, it.mt() * UG_BM + q * 32 + lane, it.nt() * 2 + hf);
         }
-        epi.end(ep, ew, lane);
     }
     umma::tc_fence_before();
     __syncthreads();
@@ -151,41 +178,27 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------------
-// epilogue policies
+// epilogue policy: strided store.  An epilogue thread owns one tile row and one half of the tile's
+// columns = one "block" of CPT columns (for K3: one MC sample):
+//     out[blk * blk_stride + row * row_stride + col * col_stride]      col < valid(blk), row < rows
+// row_stride == 1 gives the transposed (coalesced across the warp) store both K3 GEMMs use.
 // ------------------------------------------------------------------------------------------------
-// Store the tile to a row-major matrix organised in column blocks (one block per sample for K3's layer 1):
-//   column c of n-tile nt  ->  block j = nt*blks_per_tile + c / blk_cols,  h = c % blk_cols
-//   out[j * blk_stride + row * ldo + h]   for row < M, j < total_blks, h < blk_valid
-struct EpiStoreBlocks {
-    static constexpr int kEpiWarps = 4;
+struct EpiStore {
     struct Params {
-        float* out; int M; int64_t ldo; int blk_cols, blk_valid, blks_per_tile, total_blks; int64_t blk_stride;
+        float* out; int rows; int64_t row_stride, col_stride, blk_stride;
+        int blk_valid;      // valid columns per block ...
+        int col_limit;      // ... or, if > 0, total valid columns counted across consecutive blocks
+        int total_blks;
     };
-    __device__ void begin(const Params&, int, int) {}
-    __device__ void end(const Params&, int, int) {}
-    __device__ void tile(const Params& p, int mt, int nt, uint32_t tmem_base, int ew, int lane) {
-        const int q = (ew + 2) & 3;                     // TMEM lane quarter this warp may access (warp id % 4)
-        const int row = mt * UG_BM + q * 32 + lane;
-        const int ncols = p.blk_cols * p.blks_per_tile;
-        for (int c0 = 0; c0 < ncols; c0 += 32) {
-            float v[32], w[32];
-            umma::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
-            umma::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + UG_CORR_COL + c0, w);
-            umma::tmem_ld_wait();
+    template <int CPT>
+    static __device__ __forceinline__ void finish(const Params& p, float (&r)[CPT], int row, int blk) {
+        if (row >= p.rows || blk >= p.total_blks) return;
+        int valid = p.blk_valid;
+        if (p.col_limit > 0) valid = min(CPT, p.col_limit - blk * CPT);
+        float* o = p.out + (int64_t)blk * p.blk_stride + (int64_t)row * p.row_stride;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += w[i];
-            if (row < p.M) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    int c = c0 + i;
-                    int j = c / p.blk_cols, h = c - j * p.blk_cols;
-                    int blk = nt * p.blks_per_tile + j;
-                    if (c < ncols && h < p.blk_valid && blk < p.total_blks)
-                        p.out[(int64_t)blk * p.blk_stride + (int64_t)row * p.ldo + h] = v[i];
-                }
-            }
-        }
-        umma::tmem_ld_wait();
+        for (int i = 0; i < CPT; ++i)
+            if (i < valid) o[(int64_t)i * p.col_stride] = r[i];
     }
 };
 
@@ -193,10 +206,11 @@ int launch_split_tf32(const float* src, int64_t lds, int rows, int cols, float* 
                       float* tlo, int64_t ldt, cudaStream_t stream);
 
 // A (hi/lo) [M][K] pitch lda, B (hi/lo) [N][K] pitch ldb; mode 0: units n-major round-robin over CTAs,
-// mode 1: every CTA keeps one m-tile and strides over n-tiles (epilogues that accumulate across units).
+// mode 1: every CTA keeps one m-tile and strides over n-tiles.
 template <int BN, class Epi>
-inline int launch_umma_nt(const float* Ah, const float* Al, int M, int64_t lda, const float* Bh, const float* Bl, int N, int64_t ldb,
-                   int K, int mode, int grid_hint, const typename Epi::Params& ep, cudaStream_t stream) {
+inline int launch_umma_nt(const float* Ah, const float* Al, int M, int64_t lda, const float* Bh, const float* Bl, int N,
+                          int64_t ldb, int K, int mode, int drain_chunks, const typename Epi::Params& ep,
+                          cudaStream_t stream) {
     CUtensorMap tAh, tAl, tBh, tBl;
     if (int e = make_tmap_2d_f32(&tAh, Ah, M, K, lda, UG_BM)) return e;
     if (int e = make_tmap_2d_f32(&tAl, Al, M, K, lda, UG_BM)) return e;
@@ -215,14 +229,14 @@ inline int launch_umma_nt(const float* Ah, const float* Al, int M, int64_t lda, 
         if (G > n_tiles) G = n_tiles;
         grid = G * m_tiles;
     }
-    if (grid_hint > 0 && grid_hint < grid && mode == 0) grid = grid_hint;
+    if (drain_chunks < 1) drain_chunks = 2;
     auto kern = umma_nt_3xtf32_kernel<BN, Epi>;
     const int smem = UmmaSmem<BN>::TOTAL;
     BRN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, 64 + 32 * Epi::kEpiWarps, smem, stream>>>(tAh, tAl, tBh, tBl, m_tiles, n_tiles, k_chunks, mode, ep);
+    kern<<<grid, 64 + 32 * UG_EPI_WARPS, smem, stream>>>(tAh, tAl, tBh, tBl, m_tiles, n_tiles, k_chunks, drain_chunks, mode,
+                                                         ep);
     BRN_LAUNCH_OK("umma_nt_3xtf32_kernel");
     return 0;
 }
-
 
 }  // namespace brn
