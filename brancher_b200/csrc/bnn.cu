@@ -184,7 +184,7 @@ constexpr int BNN_UMMA_HP = 112;     // padded hidden width of the instantiated 
 constexpr int BNN_UMMA_NSAMP = 2;    // samples per MMA N tile (N = 224)
 
 struct BnnWorkspace {
-    float *eps, *W, *dW, *pre, *gw, *gwe;
+    float *eps, *W, *dW, *pre, *stats;
     float *Xh, *Xl, *Xth, *Xtl, *Wh, *Wl, *dph, *dpl;   // tcgen05 variant: TF32-split operands
     int64_t ldP, ldB;
     size_t bytes;
@@ -199,8 +199,7 @@ struct BnnWorkspace {
         W = take((size_t)S * L.ldw);
         dW = take((size_t)S * L.ldw);
         pre = take((size_t)S * L.B * L.H);
-        gw = take(L.ldw);
-        gwe = take(L.ldw);
+        stats = take(4 * (size_t)L.ldw);
         ldP = (L.P + 3) / 4 * 4;
         ldB = (L.B + 3) / 4 * 4;
         Xh = take((size_t)L.B * ldP); Xl = take((size_t)L.B * ldP);
@@ -343,13 +342,9 @@ extern "C" int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int
     }
     // 5. reduce over samples + prior/entropy + chain rule
     StageTimer st5("bnn.reduce_finalize", stream);
-    for (int v = 0; v < 4; ++v) {
-        if (int e = launch_reduce_over_samples(ws.dW + offs[v], L.ldw, eps_ptr[v], eps_ld[v], ws.gw + offs[v],
-                                                   ws.gwe + offs[v], numels[v], S, stream))
-                return e;
-        if (int e = launch_mf_finalize(vars[v], eps_ptr[v], eps_ld[v], ws.gw + offs[v], ws.gwe + offs[v], *r, with_prior,
-                                       loss, stream))
+    for (int v = 0; v < 4; ++v)
+        if (int e = launch_mf_reduce_finalize(vars[v], eps_ptr[v], eps_ld[v], ws.dW + offs[v], L.ldw, ws.stats, *r, with_prior,
+                                              loss, stream))
             return e;
-    }
     return 0;
 }

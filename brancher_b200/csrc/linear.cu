@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(256, 1) linear_fused_kernel(LinearArgs a) {
 }
 
 struct LinearWorkspace {
-    float *eps, *W, *dW, *gw, *gwe;
+    float *eps, *W, *dW, *stats;
     size_t bytes;
     LinearWorkspace(void* base, int64_t numel, int S) {
         size_t off = 0;
@@ -216,8 +216,7 @@ struct LinearWorkspace {
         eps = take((size_t)S * numel);
         W = take((size_t)S * numel);
         dW = take((size_t)S * numel);
-        gw = take(numel);
-        gwe = take(numel);
+        stats = take(4 * (size_t)((numel + 3) / 4 * 4));
         bytes = off;
     }
 };
@@ -291,6 +290,5 @@ extern "C" int brn_linear_elbo_fwd_bwd(const float* X, const void* y, int likeli
         BRN_LAUNCH_OK("linear_fused_kernel");
     }
     StageTimer st3("linear.reduce_finalize", stream);
-    if (int e = launch_reduce_over_samples(ws.dW, numel, eps, numel, ws.gw, ws.gwe, numel, S, stream)) return e;
-    return launch_mf_finalize(*w, eps, numel, ws.gw, ws.gwe, *r, with_prior, loss, stream);
+    return launch_mf_reduce_finalize(*w, eps, numel, ws.dW, numel, ws.stats, *r, with_prior, loss, stream);
 }

@@ -163,6 +163,118 @@ int launch_reduce_over_samples(const float* dW, int64_t ld, const float* eps, in
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// stage 5, parallel version
+// ---------------------------------------------------------------------------------------------
+constexpr int MF_SCHUNK = 16;     // samples per block
+
+__global__ void __launch_bounds__(128)
+mf_stats_kernel(const float* __restrict__ eps, int64_t lde, const float* __restrict__ dW, int64_t ldd, int64_t numel,
+                int64_t npad, brn_sample_range r, uint32_t var_id, int vec, float* __restrict__ stats) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q * 4 >= numel) return;
+    const int s_begin = blockIdx.y * MF_SCHUNK, s_end = min(r.s_local, s_begin + MF_SCHUNK);
+    const int nvalid = (int)min((int64_t)4, numel - q * 4);
+    float gw[4] = {0.f, 0.f, 0.f, 0.f}, gwe[4] = {0.f, 0.f, 0.f, 0.f}, e1[4] = {0.f, 0.f, 0.f, 0.f}, e2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int s = s_begin; s < s_end; ++s) {
+        float e[4], d[4] = {0.f, 0.f, 0.f, 0.f};
+        if (eps) {
+            if (vec) {
+                float4 t = *reinterpret_cast<const float4*>(eps + (int64_t)s * lde + q * 4);
+                e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) e[j] = j < nvalid ? eps[(int64_t)s * lde + q * 4 + j] : 0.f;
+            }
+        } else {
+            Normal4 n = philox_normal4(r.seed, r.offset, var_id, (uint32_t)(r.s0 + s), (uint32_t)q);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) e[j] = j < nvalid ? n.v[j] : 0.f;
+        }
+        if (dW) {
+            if (vec) {
+                float4 t = *reinterpret_cast<const float4*>(dW + (int64_t)s * ldd + q * 4);
+                d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) d[j] = j < nvalid ? dW[(int64_t)s * ldd + q * 4 + j] : 0.f;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            gw[j] += d[j];
+            gwe[j] = __fmaf_rn(d[j], e[j], gwe[j]);
+            e1[j] += e[j];
+            e2[j] = __fmaf_rn(e[j], e[j], e2[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (j >= nvalid) continue;
+        const int64_t i = q * 4 + j;
+        if (dW) { atomicAdd(&stats[i], gw[j]); atomicAdd(&stats[npad + i], gwe[j]); }
+        atomicAdd(&stats[2 * npad + i], e1[j]);
+        atomicAdd(&stats[3 * npad + i], e2[j]);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+mf_finalize2_kernel(brn_mf_var v, const float* __restrict__ stats, int64_t npad, brn_sample_range r, int with_prior,
+                    double* __restrict__ loss) {
+    __shared__ double red[32];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double elbo_thread = 0.0;
+    if (i < v.numel) {
+        const float mu = v.mu[i], rho = v.rho[i], sg = softplusf(rho);
+        const float gw = stats[i], gwe = stats[npad + i], e1 = stats[2 * npad + i], e2 = stats[3 * npad + i];
+        const float inv_S = 1.0f / (float)r.s_total, n = (float)r.s_local, frac = n * inv_S;
+        float dE_dmu = gw * inv_S, dE_dsg = gwe * inv_S;
+        if (with_prior) {
+            const float log_sg = logf(sg);
+            const float entropy = 0.5f + BRN_HALF_LOG_2PI + log_sg;
+            if (v.tied) {
+                // log N(w; mu, sigma), w = mu + sigma*eps  ==  -eps^2/2 - log sigma - c ; its mu- and sigma-gradients
+                // cancel against themselves / the entropy identically.
+                elbo_thread = (double)(-0.5f * e2 * inv_S) + (double)(frac * (entropy - log_sg - BRN_HALF_LOG_2PI));
+            } else {
+                const float a = v.prior_loc[i], b = v.prior_scale[i], inv_b2 = 1.0f / (b * b);
+                const float c0 = mu - a;
+                // sum_s (c0 + sg*eps_s)^2, sum_s (c0 + sg*eps_s), sum_s (c0 + sg*eps_s)*eps_s from (n, e1, e2)
+                const float sd2 = n * c0 * c0 + 2.f * c0 * sg * e1 + sg * sg * e2;
+                const float sd = n * c0 + sg * e1;
+                const float sde = c0 * e1 + sg * e2;
+                elbo_thread = (double)(-0.5f * sd2 * inv_b2 * inv_S) + (double)(frac * (entropy - logf(b) - BRN_HALF_LOG_2PI));
+                dE_dmu += -sd * inv_b2 * inv_S;
+                dE_dsg += -sde * inv_b2 * inv_S + frac / sg;
+            }
+        }
+        v.dmu[i] += -dE_dmu;
+        v.drho[i] += -dE_dsg * sigmoidf(rho);
+    }
+    double tot = block_sum<double>(elbo_thread, red);
+    if (threadIdx.x == 0 && with_prior) atomicAdd(loss, -tot);
+}
+
+int launch_mf_reduce_finalize(const brn_mf_var& var, const float* eps, int64_t lde, const float* dW, int64_t ldd,
+                              float* stats, const brn_sample_range& r, int with_prior, double* loss, cudaStream_t stream) {
+    if (var.numel <= 0) return 0;
+    if (!eps && var.eps) { eps = var.eps; lde = var.numel; }
+    const int64_t npad = (var.numel + 3) / 4 * 4;
+    BRN_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(float) * 4 * npad, stream));
+    if (r.s_local > 0) {
+        const int64_t quads = npad / 4;
+        const int vec = (!eps || (((uintptr_t)eps % 16 == 0) && lde % 4 == 0)) &&
+                        (!dW || (((uintptr_t)dW % 16 == 0) && ldd % 4 == 0)) && (var.numel % 4 == 0);
+        dim3 grid((unsigned)((quads + 127) / 128), (unsigned)((r.s_local + MF_SCHUNK - 1) / MF_SCHUNK));
+        mf_stats_kernel<<<grid, 128, 0, stream>>>(eps, lde, dW, ldd, var.numel, npad, r, var.var_id, vec, stats);
+        BRN_LAUNCH_OK("mf_stats_kernel");
+    }
+    mf_finalize2_kernel<<<(unsigned)((var.numel + 255) / 256), 256, 0, stream>>>(var, stats, npad, r, with_prior, loss);
+    BRN_LAUNCH_OK("mf_finalize2_kernel");
+    return 0;
+}
+
 }  // namespace brn
 
 using namespace brn;

@@ -21,4 +21,11 @@ int launch_mf_finalize(const brn_mf_var& var, const float* eps, int64_t lde, con
 int launch_reduce_over_samples(const float* dW, int64_t ld, const float* eps, int64_t lde, float* gw, float* gwe,
                                int64_t numel, int s_local, cudaStream_t stream);
 
+// Stage 5 of the likelihood families, HBM-bound and parallel over (elements x sample chunks):
+//   stats kernel : gw = sum_s dW_s, gwe = sum_s dW_s*eps_s, e1 = sum_s eps_s, e2 = sum_s eps_s^2   (atomics into `stats`)
+//   finalize     : prior log-prob / entropy in closed form from (e1, e2), chain rule through softplus, loss.
+// `stats` is a caller-provided scratch of 4*pad4(numel) floats (zeroed here).  dW may be NULL (prior/entropy only).
+int launch_mf_reduce_finalize(const brn_mf_var& var, const float* eps, int64_t lde, const float* dW, int64_t ldd,
+                              float* stats, const brn_sample_range& r, int with_prior, double* loss, cudaStream_t stream);
+
 }  // namespace brn
