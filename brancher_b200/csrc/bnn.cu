@@ -176,6 +176,228 @@ __global__ void sample_w1_split_kernel(const float* __restrict__ mu, const float
     lo[o] = vl;
 }
 
+__global__ void softplus_kernel(const float* __restrict__ rho, float* __restrict__ sigma, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) sigma[i] = softplusf(rho[i]);
+}
+
+// Fused noise + weight sampling + TF32 split for layer 1 (P % 4 == 0): one thread = 4 consecutive weights of one
+// sample.  eps comes from Philox (and is also written out for stage 5) or from the injected tensor.
+//   Wh/Wl[(s*Hp + h)*ldP + p] = split(mu + sigma*eps) ;  rows h in [H, Hp) = 0
+__global__ void __launch_bounds__(256)
+sample_w1_fused_kernel(const float* __restrict__ mu, const float* __restrict__ sigma, const float* __restrict__ eps_in,
+                       int64_t lde_in, float* __restrict__ eps_out, int64_t lde_out, float* __restrict__ hi,
+                       float* __restrict__ lo, int H, int P, int Hp, int64_t ldP, brn_sample_range r, uint32_t var_id) {
+    const int64_t qq = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // quad index in the padded [Hp][P] matrix
+    const int s = blockIdx.y;
+    if (qq * 4 >= (int64_t)Hp * P) return;
+    const int h = (int)((qq * 4) / P), p = (int)((qq * 4) - (int64_t)h * P);
+    float4 vh = make_float4(0.f, 0.f, 0.f, 0.f), vl = vh;
+    if (h < H) {
+        const int64_t i = (int64_t)h * P + p;
+        float4 e;
+        if (eps_in) {
+            e = *reinterpret_cast<const float4*>(eps_in + (int64_t)s * lde_in + i);
+        } else {
+            Normal4 n = philox_normal4(r.seed, r.offset, var_id, (uint32_t)(r.s0 + s), (uint32_t)(i >> 2));
+            e = make_float4(n.v[0], n.v[1], n.v[2], n.v[3]);
+            *reinterpret_cast<float4*>(eps_out + (int64_t)s * lde_out + i) = e;
+        }
+        const float4 m = *reinterpret_cast<const float4*>(mu + i);
+        const float4 sg = *reinterpret_cast<const float4*>(sigma + i);
+        umma::split_tf32(__fmaf_rn(sg.x, e.x, m.x), vh.x, vl.x);
+        umma::split_tf32(__fmaf_rn(sg.y, e.y, m.y), vh.y, vl.y);
+        umma::split_tf32(__fmaf_rn(sg.z, e.z, m.z), vh.z, vl.z);
+        umma::split_tf32(__fmaf_rn(sg.w, e.w, m.w), vh.w, vl.w);
+    }
+    const int64_t o = ((int64_t)s * Hp + h) * ldP + p;
+    *reinterpret_cast<float4*>(hi + o) = vh;
+    *reinterpret_cast<float4*>(lo + o) = vl;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// "mid" stage, fast version: one CTA = 128 batch rows of one sample, 256 threads = 2 threads per row (each owns
+// half of the hidden units).  Everything between the two layer-1 GEMMs happens here in shared memory:
+//   h = tanh(pre + b1), a = W2 h + b2, log-softmax, ll, da, dW2 / db2 (reduced over the 128 rows),
+//   dh = W2^T da, dpre = dh (1 - h^2), db1.
+// TC: `pre` arrives transposed [S][H][B] (tcgen05 GEMM output) and dpre leaves transposed + TF32-split
+// ([S*Hp][ldB] hi/lo, rows h >= H zero), both coalesced along the batch axis; else `pre` is [S][B][H] and is
+// overwritten in place.
+// ---------------------------------------------------------------------------------------------------
+constexpr int MID_R = 128;
+
+struct MidSmem {
+    int HP1;              // odd row pitch of the tile -> conflict-free column and row access
+    size_t tile, w2, b1, b2, das, apart, total;   // offsets in floats
+    __host__ __device__ MidSmem(int H, int C) {
+        HP1 = H | 1;
+        tile = 0;
+        w2 = tile + (size_t)MID_R * HP1;
+        b1 = w2 + (size_t)C * H;
+        b2 = b1 + H;
+        das = (b2 + C + 3) / 4 * 4;          // float4-aligned
+        apart = das + MID_R * 16;
+        total = apart + MID_R * 16;
+    }
+};
+
+template <bool TC>
+__global__ void __launch_bounds__(256)
+bnn_mid2_kernel(float* __restrict__ pre, const float* __restrict__ W, float* __restrict__ dW,
+                const int32_t* __restrict__ y, BnnLayout L, float inv_S, double* __restrict__ loss,
+                float* __restrict__ dpT_hi, float* __restrict__ dpT_lo, int Hp, int64_t ldB) {
+    extern __shared__ __align__(16) float sm[];
+    const int H = L.H, C = L.C, B = L.B;
+    const MidSmem M(H, C);
+    const int HP1 = M.HP1;
+    float* tile = sm + M.tile;
+    float* W2s = sm + M.w2;
+    float* b1s = sm + M.b1;
+    float* b2s = sm + M.b2;
+    float* das = sm + M.das;      // [128][16]
+    float* apart = sm + M.apart;  // [128][16]
+    __shared__ double red[32];
+
+    const int s = blockIdx.y, b0 = blockIdx.x * MID_R, t = threadIdx.x;
+    const int r = t & (MID_R - 1), half = t >> 7;
+    const float* Ws = W + (int64_t)s * L.ldw;
+    float* dWs = dW + (int64_t)s * L.ldw;
+    float* pre_s = pre + (int64_t)s * B * H;
+    const bool row_ok = b0 + r < B;
+
+    // ---- P0: stage the tile
+    if (TC) {
+        for (int h = half; h < H; h += 2) tile[r * HP1 + h] = row_ok ? pre_s[(int64_t)h * B + b0 + r] : 0.f;
+    } else {
+        for (int idx = t; idx < MID_R * H; idx += 256) {
+            int rr = idx / H, h = idx - rr * H;
+            tile[rr * HP1 + h] = (b0 + rr < B) ? pre_s[(int64_t)(b0 + rr) * H + h] : 0.f;
+        }
+    }
+    for (int idx = t; idx < C * H; idx += 256) W2s[idx] = Ws[L.oW2 + idx];
+    for (int idx = t; idx < H; idx += 256) b1s[idx] = Ws[L.ob1 + idx];
+    for (int idx = t; idx < C; idx += 256) b2s[idx] = Ws[L.ob2 + idx];
+    __syncthreads();
+
+    // ---- P1: hidden activations + logits (each thread: its half of the hidden units)
+    const int Hh = (H + 1) >> 1, h0 = half * Hh, h1 = min(H, h0 + Hh);
+    float a[BNN_MAXC];
+#pragma unroll
+    for (int c = 0; c < BNN_MAXC; ++c) a[c] = 0.f;
+    for (int h = h0; h < h1; ++h) {
+        float v = tanhf(tile[r * HP1 + h] + b1s[h]);
+        tile[r * HP1 + h] = v;
+#pragma unroll
+        for (int c = 0; c < BNN_MAXC; ++c)
+            if (c < C) a[c] = __fmaf_rn(W2s[c * H + h], v, a[c]);
+    }
+    if (half == 1) {
+#pragma unroll
+        for (int c = 0; c < BNN_MAXC; ++c) apart[r * 16 + c] = a[c];
+    }
+    __syncthreads();
+    float da[BNN_MAXC];
+    float ll = 0.f;
+    if (half == 0) {
+        if (row_ok) {
+            float m = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < BNN_MAXC; ++c)
+                if (c < C) { a[c] += apart[r * 16 + c] + b2s[c]; m = fmaxf(m, a[c]); }
+            float se = 0.f;
+#pragma unroll
+            for (int c = 0; c < BNN_MAXC; ++c)
+                if (c < C) se += expf(a[c] - m);
+            const float lse = m + logf(se);
+            const int label = y[b0 + r];
+#pragma unroll
+            for (int c = 0; c < BNN_MAXC; ++c) {
+                if (c < C) {
+                    da[c] = (c == label ? 1.f : 0.f) - expf(a[c] - lse);      // d ll / d a_c
+                    if (c == label) ll = a[c] - lse;
+                } else da[c] = 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < BNN_MAXC; ++c) da[c] = 0.f;
+        }
+#pragma unroll
+        for (int c = 0; c < BNN_MAXC; ++c) das[r * 16 + c] = da[c];
+    }
+    __syncthreads();
+
+    // ---- P2: dW2_s[c,h] += sum_r da_r[c] h_r[h] ; db2_s[c] += sum_r da_r[c]
+    {
+        const int g = half;                           // class group: classes [8g, 8g+8)
+        if (8 * g < C) {
+            for (int hh = r; hh < H; hh += MID_R) {
+                float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+                for (int rr = 0; rr < MID_R; ++rr) {
+                    const float hv = tile[rr * HP1 + hh];
+                    const float4 d0 = *reinterpret_cast<const float4*>(&das[rr * 16 + 8 * g]);
+                    const float4 d1 = *reinterpret_cast<const float4*>(&das[rr * 16 + 8 * g + 4]);
+                    acc[0] = __fmaf_rn(d0.x, hv, acc[0]); acc[1] = __fmaf_rn(d0.y, hv, acc[1]);
+                    acc[2] = __fmaf_rn(d0.z, hv, acc[2]); acc[3] = __fmaf_rn(d0.w, hv, acc[3]);
+                    acc[4] = __fmaf_rn(d1.x, hv, acc[4]); acc[5] = __fmaf_rn(d1.y, hv, acc[5]);
+                    acc[6] = __fmaf_rn(d1.z, hv, acc[6]); acc[7] = __fmaf_rn(d1.w, hv, acc[7]);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (8 * g + j < C) atomicAdd(&dWs[L.oW2 + (int64_t)(8 * g + j) * H + hh], acc[j]);
+            }
+        }
+        if (t < C) {
+            float acc = 0.f;
+            for (int rr = 0; rr < MID_R; ++rr) acc += das[rr * 16 + t];
+            atomicAdd(&dWs[L.ob2 + t], acc);
+        }
+    }
+    __syncthreads();
+
+    // ---- P3: dpre = (W2^T da) (1 - h^2)
+    if (half == 1) {
+#pragma unroll
+        for (int c = 0; c < BNN_MAXC; ++c) da[c] = das[r * 16 + c];
+    }
+    for (int h = h0; h < h1; ++h) {
+        const float hv = tile[r * HP1 + h];
+        float dh = 0.f;
+#pragma unroll
+        for (int c = 0; c < BNN_MAXC; ++c)
+            if (c < C) dh = __fmaf_rn(da[c], W2s[c * H + h], dh);
+        tile[r * HP1 + h] = dh * (1.f - hv * hv);
+    }
+    __syncthreads();
+
+    // ---- P4: db1_s[h] += sum_r dpre_r[h] ; write dpre
+    for (int hh = r; hh < H; hh += MID_R) {
+        float acc = 0.f;
+        const int r0 = half * (MID_R / 2);
+#pragma unroll 8
+        for (int rr = r0; rr < r0 + MID_R / 2; ++rr) acc += tile[rr * HP1 + hh];
+        atomicAdd(&dWs[L.ob1 + hh], acc);
+    }
+    if (TC) {
+        if (row_ok) {
+            for (int h = half; h < Hp; h += 2) {
+                float hi = 0.f, lo = 0.f;
+                if (h < H) umma::split_tf32(tile[r * HP1 + h], hi, lo);
+                const int64_t o = ((int64_t)s * Hp + h) * ldB + b0 + r;
+                dpT_hi[o] = hi;
+                dpT_lo[o] = lo;
+            }
+        }
+    } else {
+        for (int idx = t; idx < MID_R * H; idx += 256) {
+            int rr = idx / H, h = idx - rr * H;
+            if (b0 + rr < B) pre_s[(int64_t)(b0 + rr) * H + h] = tile[rr * HP1 + h];
+        }
+    }
+    double tot = block_sum<double>((double)ll, red);
+    if (t == 0) atomicAdd(loss, -tot * (double)inv_S);
+}
+
 static size_t bnn_mid_smem(int R, int H, int C) {
     return sizeof(float) * ((size_t)R * (H + 1) + (size_t)C * H + H + C + (size_t)R * C);
 }
@@ -184,7 +406,7 @@ constexpr int BNN_UMMA_HP = 112;     // padded hidden width of the instantiated 
 constexpr int BNN_UMMA_NSAMP = 2;    // samples per MMA N tile (N = 224)
 
 struct BnnWorkspace {
-    float *eps, *W, *dW, *pre, *stats;
+    float *eps, *W, *dW, *pre, *stats, *sigma;
     float *Xh, *Xl, *Xth, *Xtl, *Wh, *Wl, *dph, *dpl;   // tcgen05 variant: TF32-split operands
     int64_t ldP, ldB;
     size_t bytes;
@@ -200,6 +422,7 @@ struct BnnWorkspace {
         dW = take((size_t)S * L.ldw);
         pre = take((size_t)S * L.B * L.H);
         stats = take(4 * (size_t)L.ldw);
+        sigma = take(L.ldw);
         ldP = (L.P + 3) / 4 * 4;
         ldB = (L.B + 3) / 4 * 4;
         Xh = take((size_t)L.B * ldP); Xl = take((size_t)L.B * ldP);
@@ -269,15 +492,29 @@ extern "C" int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int
                 eps_ptr[v] = vars[v].eps;
                 eps_ld[v] = numels[v];
             } else {
-                if (int e = launch_philox_fill(ws.eps + offs[v], L.ldw, numels[v], vars[v].var_id, *r, stream)) return e;
+                if (!(use_tc && v == 0))      // layer-1 noise of the tcgen05 variant is generated by the fused sampler
+                    if (int e = launch_philox_fill(ws.eps + offs[v], L.ldw, numels[v], vars[v].var_id, *r, stream)) return e;
                 eps_ptr[v] = ws.eps + offs[v];
                 eps_ld[v] = L.ldw;
             }
             if (use_tc && v == 0) {
-                dim3 grid((P + 255) / 256, HP, S);
-                sample_w1_split_kernel<<<grid, 256, 0, stream>>>(vars[0].mu, vars[0].rho, eps_ptr[0], eps_ld[0], ws.Wh, ws.Wl, H,
-                                                                 P, HP, ws.ldP);
-                BRN_LAUNCH_OK("sample_w1_split_kernel");
+                const bool fast = (P % 4 == 0) && ((uintptr_t)vars[0].mu % 16 == 0) &&
+                                  (!vars[0].eps || ((uintptr_t)vars[0].eps % 16 == 0));
+                if (fast) {
+                    softplus_kernel<<<(unsigned)((numels[0] + 255) / 256), 256, 0, stream>>>(vars[0].rho, ws.sigma, numels[0]);
+                    BRN_LAUNCH_OK("softplus_kernel");
+                    dim3 grid((unsigned)(((int64_t)HP * P / 4 + 255) / 256), S);
+                    sample_w1_fused_kernel<<<grid, 256, 0, stream>>>(vars[0].mu, ws.sigma, vars[0].eps, numels[0], ws.eps + offs[0],
+                                                                     L.ldw, ws.Wh, ws.Wl, H, P, HP, ws.ldP, *r, vars[0].var_id);
+                    BRN_LAUNCH_OK("sample_w1_fused_kernel");
+                } else {
+                    if (!vars[0].eps)
+                        if (int e = launch_philox_fill(ws.eps + offs[0], L.ldw, numels[0], vars[0].var_id, *r, stream)) return e;
+                    dim3 grid((P + 255) / 256, HP, S);
+                    sample_w1_split_kernel<<<grid, 256, 0, stream>>>(vars[0].mu, vars[0].rho, eps_ptr[0], eps_ld[0], ws.Wh, ws.Wl,
+                                                                     H, P, HP, ws.ldP);
+                    BRN_LAUNCH_OK("sample_w1_split_kernel");
+                }
                 if (S % NS) {   // the odd tail tile reads one more (all-zero) sample block
                     BRN_CUDA_OK(cudaMemsetAsync(ws.Wh + (size_t)S * HP * ws.ldP, 0, sizeof(float) * HP * ws.ldP, stream));
                     BRN_CUDA_OK(cudaMemsetAsync(ws.Wl + (size_t)S * HP * ws.ldP, 0, sizeof(float) * HP * ws.ldP, stream));
@@ -310,15 +547,33 @@ extern "C" int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int
     BRN_CUDA_OK(cudaMemset2DAsync(ws.dW + L.ob1, L.ldw * sizeof(float), 0, (L.numel - L.ob1) * sizeof(float), S, stream));
     {
         StageTimer st("bnn.mid", stream);
-        int R = 128;
-        while (R > 32 && bnn_mid_smem(R, H, C) > 200 * 1024) R -= 32;
-        size_t smem = bnn_mid_smem(R, H, C);
-        BRN_CHECK_ARG(smem <= 220 * 1024, "brn_bnn_elbo_fwd_bwd: hidden width H=%d too large for the mid kernel", H);
-        BRN_CUDA_OK(cudaFuncSetAttribute(bnn_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dim3 grid((B + R - 1) / R, S);
-        bnn_mid_kernel<<<grid, R, smem, stream>>>(ws.pre, ws.W, ws.dW, y, L, R, 1.0f / (float)r->s_total, loss,
-                                                  use_tc ? ws.dph : nullptr, use_tc ? ws.dpl : nullptr, HP, ws.ldB);
-        BRN_LAUNCH_OK("bnn_mid_kernel");
+        const MidSmem ms(H, C);
+        const size_t smem2 = ms.total * sizeof(float);
+        if (smem2 <= 200 * 1024) {
+            dim3 grid((B + MID_R - 1) / MID_R, S);
+            if (use_tc) {
+                BRN_CUDA_OK(cudaFuncSetAttribute(bnn_mid2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+                bnn_mid2_kernel<true><<<grid, 256, smem2, stream>>>(ws.pre, ws.W, ws.dW, y, L, 1.0f / (float)r->s_total, loss,
+                                                                    ws.dph, ws.dpl, HP, ws.ldB);
+            } else {
+                BRN_CUDA_OK(cudaFuncSetAttribute(bnn_mid2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+                bnn_mid2_kernel<false><<<grid, 256, smem2, stream>>>(ws.pre, ws.W, ws.dW, y, L, 1.0f / (float)r->s_total, loss,
+                                                                     nullptr, nullptr, HP, ws.ldB);
+            }
+            BRN_LAUNCH_OK("bnn_mid2_kernel");
+        } else {
+            // very wide hidden layers: the one-thread-per-row kernel with fewer rows per CTA (SIMT variant only)
+            BRN_CHECK_ARG(!use_tc, "internal: tcgen05 variant with H=%d", H);
+            int R = 128;
+            while (R > 32 && bnn_mid_smem(R, H, C) > 200 * 1024) R -= 32;
+            size_t smem = bnn_mid_smem(R, H, C);
+            BRN_CHECK_ARG(smem <= 220 * 1024, "brn_bnn_elbo_fwd_bwd: hidden width H=%d too large for the mid kernel", H);
+            BRN_CUDA_OK(cudaFuncSetAttribute(bnn_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            dim3 grid((B + R - 1) / R, S);
+            bnn_mid_kernel<<<grid, R, smem, stream>>>(ws.pre, ws.W, ws.dW, y, L, R, 1.0f / (float)r->s_total, loss, nullptr,
+                                                      nullptr, HP, ws.ldB);
+            BRN_LAUNCH_OK("bnn_mid_kernel");
+        }
     }
     // 4. dW1_s = dpre_s^T . X   (tcgen05: folded over samples in the GEMM epilogue -> gw, gwe directly)
     {
