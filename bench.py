@@ -59,7 +59,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -202,8 +202,9 @@ def main_ours(args):
         units_per_rank = S_local * cfg["B"]
         algo_flops = {"bnn.gemm_fwd": 2.0 * S_local * cfg["B"] * cfg["H"] * cfg["P"],
                       "bnn.gemm_bwd": 2.0 * S_local * cfg["B"] * cfg["H"] * cfg["P"]}
-        mvars = [cu.MeanFieldVar(torch.tensor(params[n][0], device=dev), torch.tensor(params[n][1], device=dev), var_id=i)
-                 for i, n in enumerate(names)]
+        gflat, gviews = cu.flat_grad_views([int(np.prod(shapes[n])) for n in names], dev)
+        mvars = [cu.MeanFieldVar(torch.tensor(params[n][0], device=dev), torch.tensor(params[n][1], device=dev), var_id=i,
+                                 dmu=gviews[i][0], drho=gviews[i][1]) for i, n in enumerate(names)]
         X = torch.tensor(Xh, device=dev)
         y = torch.tensor(yh, device=dev)
         Xpin, ypin = torch.tensor(Xh).pin_memory(), torch.tensor(yh).pin_memory()
@@ -211,8 +212,7 @@ def main_ours(args):
 
         def device_step(it, Xd=X, yd=y):
             r = cu.sample_range(S_total, s0=s0, s_local=S_local, seed=args.seed, offset=it)
-            for v in mvars:
-                v.dmu.zero_(); v.drho.zero_()
+            gflat.zero_()
             return cu.bnn_elbo_fwd_bwd(Xd, yd, mvars, r)
     else:
         rows = cfg["N"]
@@ -221,8 +221,9 @@ def main_ours(args):
         s0 = 0
         units_per_rank = S_local * rows
         algo_flops = {"linear.fused": 4.0 * S_local * rows * cfg["F"]}
+        gflat, gviews = cu.flat_grad_views([cfg["F"]], dev)
         w = cu.MeanFieldVar(torch.tensor(params["weights"][0], device=dev), torch.tensor(params["weights"][1], device=dev),
-                            var_id=0, prior_loc=0.0, prior_scale=0.5)
+                            var_id=0, prior_loc=0.0, prior_scale=0.5, dmu=gviews[0][0], drho=gviews[0][1])
         mvars = [w]
         X = torch.tensor(Xh, device=dev)
         y = torch.tensor(yh, device=dev)
@@ -231,29 +232,19 @@ def main_ours(args):
 
         def device_step(it, Xd=X, yd=y):
             r = cu.sample_range(S_total, seed=args.seed, offset=it)
-            w.dmu.zero_(); w.drho.zero_()
+            gflat.zero_()
             # rows are sharded: every rank holds the same samples; prior/entropy counted once (rank 0)
             return cu.linear_elbo_fwd_bwd(Xd, yd, cu.BERNOULLI, w, 1, r, with_prior=(rank == 0))
 
-    nparam = sum(v.numel for v in mvars)
-    flat = torch.zeros(2 * nparam + 2, device=dev)
-
     def reduce_partials(loss):
-        """all-reduce [grads | loss] across ranks (loss as a hi/lo fp32 pair to keep ~fp64 accuracy)."""
+        """all-reduce [grads | loss_hi, loss_lo] across ranks IN PLACE: one NCCL collective on the flat gradient
+        buffer the kernels accumulated into (the loss travels as a hi/lo fp32 pair to keep ~fp64 accuracy)."""
         if world == 1:
             return loss
-        off = 0
-        for v in mvars:
-            flat[off:off + v.numel] = v.dmu; off += v.numel
-            flat[off:off + v.numel] = v.drho; off += v.numel
         hi = loss.float()
-        flat[off] = hi[0]; flat[off + 1] = (loss - hi.double()).float()[0]
-        dist.all_reduce(flat)
-        off = 0
-        for v in mvars:
-            v.dmu.copy_(flat[off:off + v.numel]); off += v.numel
-            v.drho.copy_(flat[off:off + v.numel]); off += v.numel
-        return flat[off].double() + flat[off + 1].double()
+        gflat[-4:-2] = torch.cat([hi, (loss - hi.double()).float()])
+        dist.all_reduce(gflat)
+        return gflat[-4].double() + gflat[-3].double()
 
     def step(it):
         return reduce_partials(device_step(it))
@@ -337,8 +328,8 @@ def main_ours(args):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="bnn", choices=sorted(WORKLOADS))
     ap.add_argument("--seed", type=int, default=0)

@@ -148,7 +148,7 @@ class MeanFieldVar:
     """Host-side description of one `brn_mf_var`.  mu/rho are flat views of the `<name>_loc` /
     `<name>_scale` parameters; dmu/drho receive d loss / d param."""
 
-    def __init__(self, mu, rho, var_id, prior_loc=None, prior_scale=None, eps=None):
+    def __init__(self, mu, rho, var_id, prior_loc=None, prior_scale=None, eps=None, dmu=None, drho=None):
         self.mu = mu.detach().reshape(-1).contiguous()
         self.rho = rho.detach().reshape(-1).contiguous()
         self.numel = self.mu.numel()
@@ -163,14 +163,28 @@ class MeanFieldVar:
         self.prior_loc = None if self.tied else full(prior_loc)
         self.prior_scale = None if self.tied else full(prior_scale)
         self.eps = None if eps is None else eps.detach().reshape(-1, self.numel).contiguous()
-        self.dmu = torch.zeros_like(self.mu)
-        self.drho = torch.zeros_like(self.rho)
+        # gradient sinks: caller-provided (zeroed) views, e.g. slices of one flat buffer, or fresh zeros
+        self.dmu = torch.zeros_like(self.mu) if dmu is None else dmu
+        self.drho = torch.zeros_like(self.rho) if drho is None else drho
 
     def struct(self):
         return MFVar(_ptr(self.mu, what="mu"), _ptr(self.rho, what="rho"),
                      _ptr(self.prior_loc, what="prior_loc"), _ptr(self.prior_scale, what="prior_scale"),
                      _ptr(self.eps, what="eps"), _ptr(self.dmu), _ptr(self.drho),
                      self.numel, self.var_id, int(self.tied))
+
+
+def flat_grad_views(numels, device):
+    """One zeroed flat fp32 buffer [dmu_0 | drho_0 | dmu_1 | ...] (each block padded to 4 floats = 16 B) and its
+    per-variable (dmu, drho) views: a single memset and a single all-reduce payload instead of 2 per variable.
+    The last 4 floats are spare: the multi-GPU reduction carries the fp64 loss there as a (hi, lo) fp32 pair."""
+    pad = lambda n: (n + 3) // 4 * 4
+    flat = torch.zeros(sum(2 * pad(n) for n in numels) + 4, dtype=torch.float32, device=device)
+    views, off = [], 0
+    for n in numels:
+        views.append((flat[off:off + n], flat[off + pad(n):off + pad(n) + n]))
+        off += 2 * pad(n)
+    return flat, views
 
 
 def sample_range(s_total, s0=0, s_local=None, seed=0, offset=0):

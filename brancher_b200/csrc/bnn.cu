@@ -190,10 +190,10 @@ sample_w1_fused_kernel(const float* __restrict__ mu, const float* __restrict__ s
                        float* __restrict__ lo, int H, int P, int Hp, int64_t ldP, brn_sample_range r, uint32_t var_id) {
     const int64_t qq = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // quad index in the padded [Hp][P] matrix
     const int s = blockIdx.y;
-    if (qq * 4 >= (int64_t)Hp * P) return;
+    if (qq * 4 >= (int64_t)H * P) return;      // pad rows h in [H, Hp) are never written (their accumulator columns are discarded)
     const int h = (int)((qq * 4) / P), p = (int)((qq * 4) - (int64_t)h * P);
     float4 vh = make_float4(0.f, 0.f, 0.f, 0.f), vl = vh;
-    if (h < H) {
+    {
         const int64_t i = (int64_t)h * P + p;
         float4 e;
         if (eps_in) {
@@ -398,12 +398,194 @@ bnn_mid2_kernel(float* __restrict__ pre, const float* __restrict__ W, float* __r
     if (t == 0) atomicAdd(loss, -tot * (double)inv_S);
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// "mid" stage of the tcgen05 variant, instruction-lean version: one CTA = 128 batch rows of one sample, ONE thread
+// per row.  `pre` arrives transposed [S][H][B] and is read straight from global memory (coalesced along the batch
+// axis, no staging pass); the hidden activations live in a [H][129] shared tile (conflict-free both per row and
+// per hidden unit); W2 is kept TRANSPOSED and padded to CT classes ([H][CT], zero pad) so one hidden unit's
+// column is CT/4 broadcast LDS.128 instead of C scalar loads.  CT = C rounded up to a multiple of 4.
+//   P1  h = tanh(pre + b1), a = W2 h            P2  dW2[c,h] = sum_r da[r,c] h[r,h], db2
+//   P3  dpre = (W2^T da)(1 - h^2) -> TF32 split, transposed store   P4  db1
+// Pad rows h in [H, Hp) of dpT are NOT written: they only feed accumulator columns the GEMM epilogue discards.
+// ---------------------------------------------------------------------------------------------------
+constexpr int MID3_R = 128, MID3_TP = 129;
+
+struct Mid3Smem {
+    size_t tile, w2t, b1, b2, das, total;   // offsets in floats
+    __host__ __device__ Mid3Smem(int H, int CT) {
+        tile = 0;
+        w2t = ((size_t)H * MID3_TP + 3) / 4 * 4;
+        b1 = w2t + (size_t)H * CT;
+        b2 = b1 + ((size_t)H + 3) / 4 * 4;
+        das = b2 + CT;
+        total = das + (size_t)MID3_R * CT;
+    }
+};
+
+template <int CT>
+__global__ void __launch_bounds__(MID3_R)
+bnn_mid3_kernel(const float* __restrict__ pre, const float* __restrict__ W, float* __restrict__ dW,
+                const int32_t* __restrict__ y, BnnLayout L, float inv_S, double* __restrict__ loss,
+                float* __restrict__ dpT_hi, float* __restrict__ dpT_lo, int Hp, int64_t ldB) {
+    extern __shared__ __align__(16) float sm[];
+    const int H = L.H, C = L.C, B = L.B;
+    const Mid3Smem M(H, CT);
+    float* tile = sm + M.tile;
+    float* W2t = sm + M.w2t;
+    float* b1s = sm + M.b1;
+    float* b2s = sm + M.b2;
+    float* das = sm + M.das;
+    __shared__ double red[32];
+    constexpr int C4 = CT / 4;
+
+    const int s = blockIdx.y, b0 = blockIdx.x * MID3_R, t = threadIdx.x;
+    const float* Ws = W + (int64_t)s * L.ldw;
+    float* dWs = dW + (int64_t)s * L.ldw;
+    const bool row_ok = b0 + t < B;
+    const float* pcol = pre + (int64_t)s * B * H + (row_ok ? b0 + t : 0);
+
+    for (int idx = t; idx < H * CT; idx += MID3_R) {
+        const int h = idx / CT, c = idx - h * CT;
+        W2t[idx] = c < C ? Ws[L.oW2 + (int64_t)c * H + h] : 0.f;
+    }
+    for (int idx = t; idx < H; idx += MID3_R) b1s[idx] = Ws[L.ob1 + idx];
+    if (t < CT) b2s[t] = t < C ? Ws[L.ob2 + t] : 0.f;
+    __syncthreads();
+
+    // ---- P1
+    float a[CT];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) a[c] = 0.f;
+#pragma unroll 4
+    for (int h = 0; h < H; ++h) {
+        const float v = tanhf(pcol[(int64_t)h * B] + b1s[h]);
+        tile[h * MID3_TP + t] = v;
+        const float4* w4 = reinterpret_cast<const float4*>(W2t + h * CT);
+#pragma unroll
+        for (int q = 0; q < C4; ++q) {
+            const float4 w = w4[q];
+            a[4 * q + 0] = __fmaf_rn(w.x, v, a[4 * q + 0]);
+            a[4 * q + 1] = __fmaf_rn(w.y, v, a[4 * q + 1]);
+            a[4 * q + 2] = __fmaf_rn(w.z, v, a[4 * q + 2]);
+            a[4 * q + 3] = __fmaf_rn(w.w, v, a[4 * q + 3]);
+        }
+    }
+    float da[CT];
+    float ll = 0.f;
+    if (row_ok) {
+        float m = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < CT; ++c)
+            if (c < C) { a[c] += b2s[c]; m = fmaxf(m, a[c]); }
+        float se = 0.f;
+#pragma unroll
+        for (int c = 0; c < CT; ++c)
+            if (c < C) se += expf(a[c] - m);
+        const float lse = m + logf(se);
+        const int label = y[b0 + t];
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+            if (c < C) {
+                da[c] = (c == label ? 1.f : 0.f) - expf(a[c] - lse);      // d ll / d a_c
+                if (c == label) ll = a[c] - lse;
+            } else da[c] = 0.f;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < CT; ++c) da[c] = 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < C4; ++q)
+        reinterpret_cast<float4*>(das + t * CT)[q] = make_float4(da[4 * q], da[4 * q + 1], da[4 * q + 2], da[4 * q + 3]);
+    __syncthreads();
+
+    // ---- P2: thread = hidden unit
+    for (int hh = t; hh < H; hh += MID3_R) {
+        float acc[CT];
+#pragma unroll
+        for (int c = 0; c < CT; ++c) acc[c] = 0.f;
+#pragma unroll 4
+        for (int rr = 0; rr < MID3_R; ++rr) {
+            const float hv = tile[hh * MID3_TP + rr];
+            const float4* d4 = reinterpret_cast<const float4*>(das + rr * CT);
+#pragma unroll
+            for (int q = 0; q < C4; ++q) {
+                const float4 d = d4[q];
+                acc[4 * q + 0] = __fmaf_rn(d.x, hv, acc[4 * q + 0]);
+                acc[4 * q + 1] = __fmaf_rn(d.y, hv, acc[4 * q + 1]);
+                acc[4 * q + 2] = __fmaf_rn(d.z, hv, acc[4 * q + 2]);
+                acc[4 * q + 3] = __fmaf_rn(d.w, hv, acc[4 * q + 3]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CT; ++c)
+            if (c < C) atomicAdd(&dWs[L.oW2 + (int64_t)c * H + hh], acc[c]);
+    }
+    if (t < C) {
+        float acc = 0.f;
+        for (int rr = 0; rr < MID3_R; ++rr) acc += das[rr * CT + t];
+        atomicAdd(&dWs[L.ob2 + t], acc);
+    }
+    __syncthreads();
+
+    // ---- P3: thread = row again
+    {
+        float* ohi = dpT_hi + (int64_t)s * Hp * ldB + b0 + t;
+        float* olo = dpT_lo + (int64_t)s * Hp * ldB + b0 + t;
+#pragma unroll 4
+        for (int h = 0; h < H; ++h) {
+            const float hv = tile[h * MID3_TP + t];
+            const float4* w4 = reinterpret_cast<const float4*>(W2t + h * CT);
+            float dh = 0.f;
+#pragma unroll
+            for (int q = 0; q < C4; ++q) {
+                const float4 w = w4[q];
+                dh = __fmaf_rn(da[4 * q + 0], w.x, dh);
+                dh = __fmaf_rn(da[4 * q + 1], w.y, dh);
+                dh = __fmaf_rn(da[4 * q + 2], w.z, dh);
+                dh = __fmaf_rn(da[4 * q + 3], w.w, dh);
+            }
+            const float dp = dh * (1.f - hv * hv);
+            tile[h * MID3_TP + t] = dp;
+            if (row_ok) {
+                float hi, lo;
+                umma::split_tf32(dp, hi, lo);
+                ohi[(int64_t)h * ldB] = hi;
+                olo[(int64_t)h * ldB] = lo;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- P4
+    for (int hh = t; hh < H; hh += MID3_R) {
+        float acc = 0.f;
+#pragma unroll 8
+        for (int rr = 0; rr < MID3_R; ++rr) acc += tile[hh * MID3_TP + rr];
+        atomicAdd(&dWs[L.ob1 + hh], acc);
+    }
+    double tot = block_sum<double>((double)ll, red);
+    if (t == 0) atomicAdd(loss, -tot * (double)inv_S);
+}
+
+template <int CT>
+static int launch_mid3(const float* pre, const float* W, float* dW, const int32_t* y, const BnnLayout& L, int S, float inv_S,
+                       double* loss, float* dph, float* dpl, int Hp, int64_t ldB, cudaStream_t stream) {
+    const size_t smem = Mid3Smem(L.H, CT).total * sizeof(float);
+    BRN_CUDA_OK(cudaFuncSetAttribute(bnn_mid3_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((L.B + MID3_R - 1) / MID3_R, S);
+    bnn_mid3_kernel<CT><<<grid, MID3_R, smem, stream>>>(pre, W, dW, y, L, inv_S, loss, dph, dpl, Hp, ldB);
+    BRN_LAUNCH_OK("bnn_mid3_kernel");
+    return 0;
+}
+
 static size_t bnn_mid_smem(int R, int H, int C) {
     return sizeof(float) * ((size_t)R * (H + 1) + (size_t)C * H + H + C + (size_t)R * C);
 }
 
-constexpr int BNN_UMMA_HP = 112;     // padded hidden width of the instantiated tcgen05 variant
-constexpr int BNN_UMMA_NSAMP = 2;    // samples per MMA N tile (N = 224)
+constexpr int BNN_UMMA_HP = 104;     // padded hidden width of the instantiated tcgen05 variant (multiple of 8)
+constexpr int BNN_UMMA_NSAMP = 2;    // samples per MMA N tile (N = 208)
 
 struct BnnWorkspace {
     float *eps, *W, *dW, *pre, *stats, *sigma;
@@ -503,7 +685,7 @@ extern "C" int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int
                 if (fast) {
                     softplus_kernel<<<(unsigned)((numels[0] + 255) / 256), 256, 0, stream>>>(vars[0].rho, ws.sigma, numels[0]);
                     BRN_LAUNCH_OK("softplus_kernel");
-                    dim3 grid((unsigned)(((int64_t)HP * P / 4 + 255) / 256), S);
+                    dim3 grid((unsigned)(((int64_t)H * P / 4 + 255) / 256), S);
                     sample_w1_fused_kernel<<<grid, 256, 0, stream>>>(vars[0].mu, ws.sigma, vars[0].eps, numels[0], ws.eps + offs[0],
                                                                      L.ldw, ws.Wh, ws.Wl, H, P, HP, ws.ldP, *r, vars[0].var_id);
                     BRN_LAUNCH_OK("sample_w1_fused_kernel");
@@ -547,31 +729,31 @@ extern "C" int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int
     BRN_CUDA_OK(cudaMemset2DAsync(ws.dW + L.ob1, L.ldw * sizeof(float), 0, (L.numel - L.ob1) * sizeof(float), S, stream));
     {
         StageTimer st("bnn.mid", stream);
+        const float inv_S = 1.0f / (float)r->s_total;
         const MidSmem ms(H, C);
         const size_t smem2 = ms.total * sizeof(float);
-        if (smem2 <= 200 * 1024) {
+        if (use_tc) {
+            int e = 0;
+            if (C <= 4) e = launch_mid3<4>(ws.pre, ws.W, ws.dW, y, L, S, inv_S, loss, ws.dph, ws.dpl, HP, ws.ldB, stream);
+            else if (C <= 8) e = launch_mid3<8>(ws.pre, ws.W, ws.dW, y, L, S, inv_S, loss, ws.dph, ws.dpl, HP, ws.ldB, stream);
+            else if (C <= 12) e = launch_mid3<12>(ws.pre, ws.W, ws.dW, y, L, S, inv_S, loss, ws.dph, ws.dpl, HP, ws.ldB, stream);
+            else e = launch_mid3<16>(ws.pre, ws.W, ws.dW, y, L, S, inv_S, loss, ws.dph, ws.dpl, HP, ws.ldB, stream);
+            if (e) return e;
+        } else if (smem2 <= 200 * 1024) {
             dim3 grid((B + MID_R - 1) / MID_R, S);
-            if (use_tc) {
-                BRN_CUDA_OK(cudaFuncSetAttribute(bnn_mid2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-                bnn_mid2_kernel<true><<<grid, 256, smem2, stream>>>(ws.pre, ws.W, ws.dW, y, L, 1.0f / (float)r->s_total, loss,
-                                                                    ws.dph, ws.dpl, HP, ws.ldB);
-            } else {
-                BRN_CUDA_OK(cudaFuncSetAttribute(bnn_mid2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-                bnn_mid2_kernel<false><<<grid, 256, smem2, stream>>>(ws.pre, ws.W, ws.dW, y, L, 1.0f / (float)r->s_total, loss,
-                                                                     nullptr, nullptr, HP, ws.ldB);
-            }
+            BRN_CUDA_OK(cudaFuncSetAttribute(bnn_mid2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            bnn_mid2_kernel<false><<<grid, 256, smem2, stream>>>(ws.pre, ws.W, ws.dW, y, L, inv_S, loss, nullptr, nullptr, HP,
+                                                                 ws.ldB);
             BRN_LAUNCH_OK("bnn_mid2_kernel");
         } else {
             // very wide hidden layers: the one-thread-per-row kernel with fewer rows per CTA (SIMT variant only)
-            BRN_CHECK_ARG(!use_tc, "internal: tcgen05 variant with H=%d", H);
             int R = 128;
             while (R > 32 && bnn_mid_smem(R, H, C) > 200 * 1024) R -= 32;
             size_t smem = bnn_mid_smem(R, H, C);
             BRN_CHECK_ARG(smem <= 220 * 1024, "brn_bnn_elbo_fwd_bwd: hidden width H=%d too large for the mid kernel", H);
             BRN_CUDA_OK(cudaFuncSetAttribute(bnn_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             dim3 grid((B + R - 1) / R, S);
-            bnn_mid_kernel<<<grid, R, smem, stream>>>(ws.pre, ws.W, ws.dW, y, L, R, 1.0f / (float)r->s_total, loss, nullptr,
-                                                      nullptr, HP, ws.ldB);
+            bnn_mid_kernel<<<grid, R, smem, stream>>>(ws.pre, ws.W, ws.dW, y, L, R, inv_S, loss, nullptr, nullptr, HP, ws.ldB);
             BRN_LAUNCH_OK("bnn_mid_kernel");
         }
     }

@@ -57,7 +57,7 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
                       int m_tiles, int n_tiles, int k_chunks, int drain_chunks, int mode, typename Epi::Params ep) {
     using SM = UmmaSmem<BN>;
     constexpr int CPT = BN / 2;                    // accumulator columns per epilogue thread
-    static_assert(BN <= UG_BUF_COLS && CPT % 16 == 0, "unsupported N tile");
+    static_assert(BN <= UG_BUF_COLS && BN % 16 == 0 && CPT % 8 == 0, "unsupported N tile");
     constexpr uint32_t TMEM_COLS = 512;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -155,12 +155,19 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
 #pragma unroll
                     for (int i = 0; i < 32; ++i) r[c + i] += v[i];
                 }
-                if (CPT % 32) {
+                if (CPT % 32 >= 16) {
                     float v[16];
                     umma::tmem_ld_32x16(t0 + (CPT / 32) * 32, v);
                     umma::tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 16; ++i) r[(CPT / 32) * 32 + i] += v[i];
+                }
+                if (CPT % 16 == 8) {
+                    float v[8];
+                    umma::tmem_ld_32x8(t0 + (CPT / 16) * 16, v);
+                    umma::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) r[(CPT / 16) * 16 + i] += v[i];
                 }
                 umma::tc_fence_before();
                 __syncwarp();

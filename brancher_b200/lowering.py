@@ -127,14 +127,14 @@ class MeanFieldSpec:
     def parameters(self):
         return [self.loc_root.value, self.scale_root.value]
 
-    def make(self, cu, var_id, eps):
+    def make(self, cu, var_id, eps, sinks=(None, None)):
         mu, rho = self.loc_root.value, self.scale_root.value
         if not self.tied:
             pl = self.prior_loc.expand(mu.shape).reshape(-1).contiguous()
             ps = self.prior_scale.expand(mu.shape).reshape(-1).contiguous()
         else:
             pl = ps = None
-        return cu.MeanFieldVar(mu, rho, var_id=var_id, prior_loc=pl, prior_scale=ps, eps=eps)
+        return cu.MeanFieldVar(mu, rho, var_id=var_id, prior_loc=pl, prior_scale=ps, eps=eps, dmu=sinks[0], drho=sinks[1])
 
 
 class _FusedELBO(torch.autograd.Function):
@@ -183,7 +183,8 @@ class Plan:
         params = [p for spec in self.latents for p in spec.parameters()]
 
         def runner():
-            mvars = [spec.make(cu, i, eps) for i, (spec, eps) in enumerate(zip(self.latents, self._eps(S_local, s0)))]
+            _, sinks = cu.flat_grad_views([int(np.prod(spec.shape)) for spec in self.latents], config.device)
+            mvars = [spec.make(cu, i, eps, sk) for i, (spec, eps, sk) in enumerate(zip(self.latents, self._eps(S_local, s0), sinks))]
             loss = self._launch(cu, mvars, r, empirical_samples)
             grads = []
             for spec, v in zip(self.latents, mvars):
