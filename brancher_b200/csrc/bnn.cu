@@ -400,31 +400,36 @@ bnn_mid2_kernel(float* __restrict__ pre, const float* __restrict__ W, float* __r
 
 
 // ---------------------------------------------------------------------------------------------------
-// "mid" stage of the tcgen05 variant, instruction-lean version: one CTA = 128 batch rows of one sample, ONE thread
-// per row.  `pre` arrives transposed [S][H][B] and is read straight from global memory (coalesced along the batch
-// axis, no staging pass); the hidden activations live in a [H][129] shared tile (conflict-free both per row and
-// per hidden unit); W2 is kept TRANSPOSED and padded to CT classes ([H][CT], zero pad) so one hidden unit's
-// column is CT/4 broadcast LDS.128 instead of C scalar loads.  CT = C rounded up to a multiple of 4.
+// "mid" stage of the tcgen05 variant, instruction-lean version: one CTA = 128 batch rows of one sample, TWO threads
+// per row (256 threads; thread `half` owns one half of the hidden units).  `pre` arrives transposed [S][H][B] and
+// is read straight from global memory (coalesced along the batch axis, software-pipelined, no staging pass); the
+// hidden activations live in a [H][129] shared tile (conflict-free both per row and per hidden unit); W2 is kept
+// TRANSPOSED and padded to CT classes ([H][CT], zero pad) so one hidden unit's column is CT/4 broadcast LDS.128
+// instead of C scalar loads, and all multiply-adds are packed FFMA2 (two fp32 FMAs per issue slot, sm_100).
+// CT = C rounded up to a multiple of 4.
 //   P1  h = tanh(pre + b1), a = W2 h            P2  dW2[c,h] = sum_r da[r,c] h[r,h], db2
 //   P3  dpre = (W2^T da)(1 - h^2) -> TF32 split, transposed store   P4  db1
 // Pad rows h in [H, Hp) of dpT are NOT written: they only feed accumulator columns the GEMM epilogue discards.
 // ---------------------------------------------------------------------------------------------------
-constexpr int MID3_R = 128, MID3_TP = 129;
+constexpr int MID3_R = 128, MID3_TP = 129, MID3_THREADS = 256;
 
 struct Mid3Smem {
-    size_t tile, w2t, b1, b2, das, total;   // offsets in floats
+    size_t tile, w2t, b1, b2, das, apart, total;   // offsets in floats
     __host__ __device__ Mid3Smem(int H, int CT) {
         tile = 0;
         w2t = ((size_t)H * MID3_TP + 3) / 4 * 4;
         b1 = w2t + (size_t)H * CT;
         b2 = b1 + ((size_t)H + 3) / 4 * 4;
         das = b2 + CT;
-        total = das + (size_t)MID3_R * CT;
+        apart = das + (size_t)MID3_R * CT;
+        total = apart + (size_t)MID3_R * CT;
     }
 };
 
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
 template <int CT>
-__global__ void __launch_bounds__(MID3_R)
+__global__ void __launch_bounds__(MID3_THREADS)
 bnn_mid3_kernel(const float* __restrict__ pre, const float* __restrict__ W, float* __restrict__ dW,
                 const int32_t* __restrict__ y, BnnLayout L, float inv_S, double* __restrict__ loss,
                 float* __restrict__ dpT_hi, float* __restrict__ dpT_lo, int Hp, int64_t ldB) {
@@ -436,91 +441,137 @@ bnn_mid3_kernel(const float* __restrict__ pre, const float* __restrict__ W, floa
     float* b1s = sm + M.b1;
     float* b2s = sm + M.b2;
     float* das = sm + M.das;
+    float* apart = sm + M.apart;
     __shared__ double red[32];
-    constexpr int C4 = CT / 4;
+    constexpr int C4 = CT / 4, C2 = CT / 2;
 
     const int s = blockIdx.y, b0 = blockIdx.x * MID3_R, t = threadIdx.x;
+    const int r = t & (MID3_R - 1), half = t >> 7;            // half is warp-uniform
     const float* Ws = W + (int64_t)s * L.ldw;
     float* dWs = dW + (int64_t)s * L.ldw;
-    const bool row_ok = b0 + t < B;
-    const float* pcol = pre + (int64_t)s * B * H + (row_ok ? b0 + t : 0);
+    const bool row_ok = b0 + r < B;
+    const float* pcol = pre + (int64_t)s * B * H + (row_ok ? b0 + r : 0);
+    const int Hh = (H + 1) >> 1, hbeg = half * Hh, hend = min(H, hbeg + Hh);
 
-    for (int idx = t; idx < H * CT; idx += MID3_R) {
+    for (int idx = t; idx < H * CT; idx += MID3_THREADS) {
         const int h = idx / CT, c = idx - h * CT;
         W2t[idx] = c < C ? Ws[L.oW2 + (int64_t)c * H + h] : 0.f;
     }
-    for (int idx = t; idx < H; idx += MID3_R) b1s[idx] = Ws[L.ob1 + idx];
+    for (int idx = t; idx < H; idx += MID3_THREADS) b1s[idx] = Ws[L.ob1 + idx];
     if (t < CT) b2s[t] = t < C ? Ws[L.ob2 + t] : 0.f;
     __syncthreads();
 
-    // ---- P1
-    float a[CT];
+    // ---- P1 (this thread: hidden units [hbeg, hend) of row r)
+    float2 a2[C2];
 #pragma unroll
-    for (int c = 0; c < CT; ++c) a[c] = 0.f;
-#pragma unroll 4
-    for (int h = 0; h < H; ++h) {
-        const float v = tanhf(pcol[(int64_t)h * B] + b1s[h]);
-        tile[h * MID3_TP + t] = v;
+    for (int c = 0; c < C2; ++c) a2[c] = make_float2(0.f, 0.f);
+    // software pipeline over chunks of PF hidden units: the (latency-bound) global loads of chunk k+1 are in flight
+    // while chunk k is evaluated; inside a chunk the PF tanh chains are independent (branch-free body -> ILP).
+    constexpr int PF = 10;
+    auto p1_unit = [&](int h, float xv) {
+        const float v = tanhf(xv + b1s[h]);
+        tile[h * MID3_TP + r] = v;
+        const float2 v2 = make_float2(v, v);
         const float4* w4 = reinterpret_cast<const float4*>(W2t + h * CT);
 #pragma unroll
         for (int q = 0; q < C4; ++q) {
             const float4 w = w4[q];
-            a[4 * q + 0] = __fmaf_rn(w.x, v, a[4 * q + 0]);
-            a[4 * q + 1] = __fmaf_rn(w.y, v, a[4 * q + 1]);
-            a[4 * q + 2] = __fmaf_rn(w.z, v, a[4 * q + 2]);
-            a[4 * q + 3] = __fmaf_rn(w.w, v, a[4 * q + 3]);
+            a2[2 * q + 0] = ffma2(make_float2(w.x, w.y), v2, a2[2 * q + 0]);
+            a2[2 * q + 1] = ffma2(make_float2(w.z, w.w), v2, a2[2 * q + 1]);
         }
+    };
+    {
+        const int nmain = (hend - hbeg) / PF * PF, hmain = hbeg + nmain;
+        float x[PF];
+        if (nmain > 0) {
+#pragma unroll
+            for (int j = 0; j < PF; ++j) x[j] = pcol[(int64_t)(hbeg + j) * B];
+        }
+        for (int h0 = hbeg; h0 < hmain; h0 += PF) {
+            float xn[PF];
+            if (h0 + PF < hmain) {
+#pragma unroll
+                for (int j = 0; j < PF; ++j) xn[j] = pcol[(int64_t)(h0 + PF + j) * B];
+            }
+#pragma unroll
+            for (int j = 0; j < PF; ++j) p1_unit(h0 + j, x[j]);
+#pragma unroll
+            for (int j = 0; j < PF; ++j) x[j] = xn[j];
+        }
+        for (int h = hmain; h < hend; ++h) p1_unit(h, pcol[(int64_t)h * B]);
     }
+    if (half == 1) {
+#pragma unroll
+        for (int q = 0; q < C4; ++q)
+            reinterpret_cast<float4*>(apart + r * CT)[q] = make_float4(a2[2 * q].x, a2[2 * q].y, a2[2 * q + 1].x, a2[2 * q + 1].y);
+    }
+    __syncthreads();
     float da[CT];
     float ll = 0.f;
-    if (row_ok) {
-        float m = -INFINITY;
+    if (half == 0) {
+        float a[CT];
 #pragma unroll
-        for (int c = 0; c < CT; ++c)
-            if (c < C) { a[c] += b2s[c]; m = fmaxf(m, a[c]); }
-        float se = 0.f;
-#pragma unroll
-        for (int c = 0; c < CT; ++c)
-            if (c < C) se += expf(a[c] - m);
-        const float lse = m + logf(se);
-        const int label = y[b0 + t];
-#pragma unroll
-        for (int c = 0; c < CT; ++c) {
-            if (c < C) {
-                da[c] = (c == label ? 1.f : 0.f) - expf(a[c] - lse);      // d ll / d a_c
-                if (c == label) ll = a[c] - lse;
-            } else da[c] = 0.f;
+        for (int q = 0; q < C4; ++q) {
+            const float4 o = reinterpret_cast<const float4*>(apart + r * CT)[q];
+            a[4 * q + 0] = a2[2 * q].x + o.x; a[4 * q + 1] = a2[2 * q].y + o.y;
+            a[4 * q + 2] = a2[2 * q + 1].x + o.z; a[4 * q + 3] = a2[2 * q + 1].y + o.w;
         }
-    } else {
+        if (row_ok) {
+            float m = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < CT; ++c) da[c] = 0.f;
+            for (int c = 0; c < CT; ++c)
+                if (c < C) { a[c] += b2s[c]; m = fmaxf(m, a[c]); }
+            float se = 0.f;
+#pragma unroll
+            for (int c = 0; c < CT; ++c)
+                if (c < C) se += expf(a[c] - m);
+            const float lse = m + logf(se);
+            const int label = y[b0 + r];
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {
+                if (c < C) {
+                    da[c] = (c == label ? 1.f : 0.f) - expf(a[c] - lse);      // d ll / d a_c
+                    if (c == label) ll = a[c] - lse;
+                } else da[c] = 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < CT; ++c) da[c] = 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < C4; ++q)
+            reinterpret_cast<float4*>(das + r * CT)[q] = make_float4(da[4 * q], da[4 * q + 1], da[4 * q + 2], da[4 * q + 3]);
     }
-#pragma unroll
-    for (int q = 0; q < C4; ++q)
-        reinterpret_cast<float4*>(das + t * CT)[q] = make_float4(da[4 * q], da[4 * q + 1], da[4 * q + 2], da[4 * q + 3]);
     __syncthreads();
-
-    // ---- P2: thread = hidden unit
-    for (int hh = t; hh < H; hh += MID3_R) {
-        float acc[CT];
+    if (half == 1) {
 #pragma unroll
-        for (int c = 0; c < CT; ++c) acc[c] = 0.f;
+        for (int q = 0; q < C4; ++q) {
+            const float4 d = reinterpret_cast<const float4*>(das + r * CT)[q];
+            da[4 * q] = d.x; da[4 * q + 1] = d.y; da[4 * q + 2] = d.z; da[4 * q + 3] = d.w;
+        }
+    }
+
+    // ---- P2: thread = (hidden unit hh, class half g): classes [g*C2, g*C2 + C2)
+    for (int idx = t; idx < 2 * H; idx += MID3_THREADS) {
+        const int hh = idx >> 1, g = idx & 1;
+        float2 acc[C4];
+#pragma unroll
+        for (int q = 0; q < C4; ++q) acc[q] = make_float2(0.f, 0.f);
+        const float* dbase = das + g * C2;
 #pragma unroll 4
         for (int rr = 0; rr < MID3_R; ++rr) {
             const float hv = tile[hh * MID3_TP + rr];
-            const float4* d4 = reinterpret_cast<const float4*>(das + rr * CT);
+            const float2 hv2 = make_float2(hv, hv);
+            const float2* d2 = reinterpret_cast<const float2*>(dbase + rr * CT);
 #pragma unroll
-            for (int q = 0; q < C4; ++q) {
-                const float4 d = d4[q];
-                acc[4 * q + 0] = __fmaf_rn(d.x, hv, acc[4 * q + 0]);
-                acc[4 * q + 1] = __fmaf_rn(d.y, hv, acc[4 * q + 1]);
-                acc[4 * q + 2] = __fmaf_rn(d.z, hv, acc[4 * q + 2]);
-                acc[4 * q + 3] = __fmaf_rn(d.w, hv, acc[4 * q + 3]);
-            }
+            for (int q = 0; q < C4; ++q) acc[q] = ffma2(d2[q], hv2, acc[q]);
         }
 #pragma unroll
-        for (int c = 0; c < CT; ++c)
-            if (c < C) atomicAdd(&dWs[L.oW2 + (int64_t)c * H + hh], acc[c]);
+        for (int q = 0; q < C4; ++q) {
+            const int c = g * C2 + 2 * q;
+            if (c < C) atomicAdd(&dWs[L.oW2 + (int64_t)c * H + hh], acc[q].x);
+            if (c + 1 < C) atomicAdd(&dWs[L.oW2 + (int64_t)(c + 1) * H + hh], acc[q].y);
+        }
     }
     if (t < C) {
         float acc = 0.f;
@@ -529,40 +580,48 @@ bnn_mid3_kernel(const float* __restrict__ pre, const float* __restrict__ W, floa
     }
     __syncthreads();
 
-    // ---- P3: thread = row again
+    // ---- P3: thread = (row, hidden half) again
     {
-        float* ohi = dpT_hi + (int64_t)s * Hp * ldB + b0 + t;
-        float* olo = dpT_lo + (int64_t)s * Hp * ldB + b0 + t;
-#pragma unroll 4
-        for (int h = 0; h < H; ++h) {
-            const float hv = tile[h * MID3_TP + t];
+        float* ohi = dpT_hi + (int64_t)s * Hp * ldB + b0 + r;
+        float* olo = dpT_lo + (int64_t)s * Hp * ldB + b0 + r;
+        float2 da2[C2];
+#pragma unroll
+        for (int c = 0; c < C2; ++c) da2[c] = make_float2(da[2 * c], da[2 * c + 1]);
+        auto p3_unit = [&](int h) {
+            const float hv = tile[h * MID3_TP + r];
             const float4* w4 = reinterpret_cast<const float4*>(W2t + h * CT);
-            float dh = 0.f;
+            float2 p0 = make_float2(0.f, 0.f), p1 = make_float2(0.f, 0.f);     // two independent packed chains
 #pragma unroll
             for (int q = 0; q < C4; ++q) {
                 const float4 w = w4[q];
-                dh = __fmaf_rn(da[4 * q + 0], w.x, dh);
-                dh = __fmaf_rn(da[4 * q + 1], w.y, dh);
-                dh = __fmaf_rn(da[4 * q + 2], w.z, dh);
-                dh = __fmaf_rn(da[4 * q + 3], w.w, dh);
+                p0 = ffma2(da2[2 * q + 0], make_float2(w.x, w.y), p0);
+                p1 = ffma2(da2[2 * q + 1], make_float2(w.z, w.w), p1);
             }
+            const float dh = (p0.x + p0.y) + (p1.x + p1.y);
             const float dp = dh * (1.f - hv * hv);
-            tile[h * MID3_TP + t] = dp;
+            tile[h * MID3_TP + r] = dp;
+            float hi, lo;
+            umma::split_tf32(dp, hi, lo);
             if (row_ok) {
-                float hi, lo;
-                umma::split_tf32(dp, hi, lo);
                 ohi[(int64_t)h * ldB] = hi;
                 olo[(int64_t)h * ldB] = lo;
             }
+        };
+        const int h4 = hbeg + (hend - hbeg) / 4 * 4;
+        for (int h0 = hbeg; h0 < h4; h0 += 4) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) p3_unit(h0 + j);
         }
+        for (int h = h4; h < hend; ++h) p3_unit(h);
     }
     __syncthreads();
 
-    // ---- P4
-    for (int hh = t; hh < H; hh += MID3_R) {
+    // ---- P4: thread = (hidden unit, row half)
+    for (int idx = t; idx < 2 * H; idx += MID3_THREADS) {
+        const int hh = idx >> 1, r0 = (idx & 1) * (MID3_R / 2);
         float acc = 0.f;
 #pragma unroll 8
-        for (int rr = 0; rr < MID3_R; ++rr) acc += tile[hh * MID3_TP + rr];
+        for (int rr = r0; rr < r0 + MID3_R / 2; ++rr) acc += tile[hh * MID3_TP + rr];
         atomicAdd(&dWs[L.ob1 + hh], acc);
     }
     double tot = block_sum<double>((double)ll, red);
@@ -575,7 +634,7 @@ static int launch_mid3(const float* pre, const float* W, float* dW, const int32_
     const size_t smem = Mid3Smem(L.H, CT).total * sizeof(float);
     BRN_CUDA_OK(cudaFuncSetAttribute(bnn_mid3_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((L.B + MID3_R - 1) / MID3_R, S);
-    bnn_mid3_kernel<CT><<<grid, MID3_R, smem, stream>>>(pre, W, dW, y, L, inv_S, loss, dph, dpl, Hp, ldB);
+    bnn_mid3_kernel<CT><<<grid, MID3_THREADS, smem, stream>>>(pre, W, dW, y, L, inv_S, loss, dph, dpl, Hp, ldB);
     BRN_LAUNCH_OK("bnn_mid3_kernel");
     return 0;
 }
