@@ -36,6 +36,10 @@ WORKLOADS = {
     "logreg": dict(name="C2 Bayesian logistic regression N=10^6 rows per GPU x F=128, S=1024 MC samples, "
                         "Binomial(1, logits), q init mu=0 sigma=1, declared prior N(0,0.5)",
                    N=1_000_000, F=128, C=1, S=1024),
+    "svgd": dict(name="C4 SVGD Bayesian logistic regression: n=4096 particles per GPU-job (sharded over GPUs), d=F=128, "
+                      "B=65536 rows, prior N(0,1); one step = per-particle loss+grad (K4a) + all-gather + pairwise RBF "
+                      "direction with exact median bandwidth (K4b)",
+                 n=4096, F=128, C=1, B=65536),
 }
 
 
@@ -59,7 +63,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -75,6 +79,15 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         self.thread.join(timeout=2)
+        note = None
+        if not self.lines:      # region shorter than nvidia-smi's start-up: one-shot sample right after it
+            try:
+                self.lines = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                             "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                            timeout=20).stdout.strip().splitlines()
+                note = "one-shot sample immediately after the timed region"
+            except Exception:
+                pass
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
@@ -88,8 +101,11 @@ class ClockSampler:
             for n, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+               "samples": len(sm), "reasons": sorted(reasons)}
+        if note:
+            out["note"] = note
+        return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -128,6 +144,15 @@ def cpu_step_fn(workload, cfg, sample_S):
         eps = {n: rng.standard_normal((sample_S,) + s).astype(np.float32) for n, s in shapes.items()}
         rows = cfg["B"]
         fn = lambda: O.bnn_elbo(X, y, params, eps, sample_chunk=8)
+    elif workload == "svgd":
+        rows = 8192
+        X, y, _ = synth_logreg(cfg, rows=rows)
+        theta = rng.standard_normal((sample_S, 1, cfg["F"])).astype(np.float32)
+        prior = (np.zeros((1, cfg["F"]), np.float32), np.ones((1, cfg["F"]), np.float32))
+
+        def fn():
+            _, G = O.particles_loss_grad(X, y, theta, prior, likelihood="binomial")
+            return O.svgd_direction(theta.reshape(sample_S, -1), G.reshape(sample_S, -1), dtype=np.float32)
     else:
         rows = 65536
         X, y, params = synth_logreg(cfg, rows=rows)
@@ -138,7 +163,7 @@ def cpu_step_fn(workload, cfg, sample_S):
 
 
 def run_cpu_baseline(workload, cfg, budget_s=12.0):
-    S = 64 if workload == "bnn" else 64
+    S = 512 if workload == "svgd" else 64
     fn, units, desc = cpu_step_fn(workload, cfg, S)
     fn()
     t0, n = time.perf_counter(), 0
@@ -157,7 +182,7 @@ def main_reference(args):
         return
     wl = args.workload
     cfg = WORKLOADS[wl]
-    S = 64
+    S = 512 if wl == "svgd" else 64
     fn, units, desc = cpu_step_fn(wl, cfg, S)
     for _ in range(args.warmup):
         fn()
@@ -214,6 +239,39 @@ def main_ours(args):
             r = cu.sample_range(S_total, s0=s0, s_local=S_local, seed=args.seed, offset=it)
             gflat.zero_()
             return cu.bnn_elbo_fwd_bwd(Xd, yd, mvars, r)
+    elif wl == "svgd":
+        # particles sharded over ranks (weak scaling: n particles per rank), data replicated; the pairwise stage needs
+        # all particles: all-gather theta and G (2 MB each per rank), every rank computes its rows of K and the update
+        n_local, F, Bv = cfg["n"], cfg["F"], cfg["B"]
+        n_total = n_local * world
+        Xh, yh, _ = synth_logreg(cfg, seed=0, rows=Bv)
+        rng = np.random.RandomState(100 + rank)
+        theta_local = torch.tensor(rng.standard_normal((n_local, F)).astype(np.float32), device=dev)
+        pl, ps = torch.zeros(F, device=dev), torch.ones(F, device=dev)
+        X = torch.tensor(Xh, device=dev)
+        y = torch.tensor(yh, device=dev)
+        Xpin, ypin = torch.tensor(Xh).pin_memory(), torch.tensor(yh).pin_memory()
+        h2d = Xpin.numel() * 4 + ypin.numel() * 4
+        units_per_rank = n_local * Bv
+        algo_flops = {"particles.loglik_grad": 4.0 * n_local * Bv * F, "svgd.update": 2.0 * n_local * n_total * (F + 1),
+                      "svgd.pairwise_d2": 3.0 * n_total * n_total * F}
+        mvars = []
+        gflat = torch.zeros(4, device=dev)
+        theta_all = torch.empty((n_total, F), device=dev)
+        G_all = torch.empty((n_total, F), device=dev)
+        svgd_out = [None]
+        S_total = n_total
+
+        def device_step(it, Xd=X, yd=y):
+            loss, G = cu.linear_particles_loss_grad(Xd, yd, cu.BERNOULLI, theta_local, 1, pl, ps)
+            if world > 1:
+                dist.all_gather_into_tensor(theta_all, theta_local)
+                dist.all_gather_into_tensor(G_all, G)
+                th, gg = theta_all, G_all
+            else:
+                th, gg = theta_local, G
+            svgd_out[0], _ = cu.svgd_direction(th, gg, row0=rank * n_local, rows=n_local)
+            return loss
     else:
         rows = cfg["N"]
         Xh, yh, params = synth_logreg(cfg, seed=rank)
@@ -307,8 +365,8 @@ def main_ours(args):
                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                "config": {"workload": cfg["name"], "noise": "Philox4x32-10 in-kernel", "l2": "256 MiB flush between timed steps",
-                          "variant": cu.last_variant(), "global_samples": S_total,
-                          "sharding": "MC samples" if wl == "bnn" else "data rows"},
+                          "variant": cu.last_variant(), "global_samples_or_particles": S_total,
+                          "sharding": {"bnn": "MC samples", "logreg": "data rows", "svgd": "particles"}[wl]},
                "clocks": clk, "gpu_launches": int(launches),
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
                        "ms_per_step": ms_e2e / n_e2e},
@@ -328,7 +386,7 @@ def main_ours(args):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="bnn", choices=sorted(WORKLOADS))

@@ -63,6 +63,13 @@ SYMBOLS = {
                                                ctypes.c_int, ctypes.c_int, ctypes.POINTER(MFVar),
                                                ctypes.POINTER(SampleRange), ctypes.c_void_p, ctypes.c_size_t,
                                                ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "brn_linear_particles_loss_grad": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
+                                                      ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                      ctypes.c_void_p]),
+    "brn_svgd_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    "brn_svgd_direction": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 5 +
+                           [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
 }
 
 
@@ -251,6 +258,37 @@ def linear_elbo_fwd_bwd(X, y, likelihood, w, C, r, with_prior=True, loss=None):
                                          ctypes.byref(r), ws.data_ptr(), ws.numel(), int(with_prior),
                                          _ptr(loss, torch.float64), _stream(dev)), "brn_linear_elbo_fwd_bwd")
     return loss
+
+
+def linear_particles_loss_grad(X, y, likelihood, theta, C, prior_loc=None, prior_scale=None, loss=None):
+    """K4a.  theta [n, C*F] particles -> (loss fp64 [1] accumulator, G [n, C*F] = d loss / d theta)."""
+    dev = X.device
+    N, F = X.shape
+    n = theta.shape[0]
+    theta = theta.reshape(n, -1)
+    loss = torch.zeros(1, dtype=torch.float64, device=dev) if loss is None else loss
+    G = torch.empty_like(theta)
+    ydt = torch.float32 if likelihood == BERNOULLI else torch.int32
+    _check(lib().brn_linear_particles_loss_grad(_ptr(X, what="X"), _ptr(y, ydt, "y"), likelihood, N, F, C,
+                                                _ptr(theta, what="theta"), n, _ptr(prior_loc, what="prior_loc"),
+                                                _ptr(prior_scale, what="prior_scale"), _ptr(G), _ptr(loss, torch.float64),
+                                                _stream(dev)), "brn_linear_particles_loss_grad")
+    return loss, G
+
+
+def svgd_direction(theta, grad, row0=0, rows=None, bandwidth=None):
+    """K4b.  theta, grad [n, d] (all particles) -> (out [rows, d], bandwidth device float [1]).  bandwidth=None applies
+    the reference's median heuristic (inference.py:317-324); pass a device tensor to reuse a fixed bandwidth."""
+    n, d = theta.shape
+    rows = n - row0 if rows is None else rows
+    dev = theta.device
+    update = bandwidth is None
+    bw = torch.zeros(1, dtype=torch.float32, device=dev) if update else bandwidth
+    out = torch.empty((rows, d), dtype=torch.float32, device=dev)
+    ws = _workspace(dev, lib().brn_svgd_workspace_bytes(n, d))
+    _check(lib().brn_svgd_direction(_ptr(theta, what="theta"), _ptr(grad, what="grad"), n, d, row0, rows, int(update),
+                                    _ptr(bw), _ptr(out), ws.data_ptr(), ws.numel(), _stream(dev)), "brn_svgd_direction")
+    return out, bw
 
 
 def gemm_nt_3xtf32(A, B):

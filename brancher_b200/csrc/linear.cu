@@ -221,9 +221,85 @@ struct LinearWorkspace {
     }
 };
 
+// particles: G = -(d ll / d theta) - d log N(theta; a, b) / d theta ; loss += sum -log N(theta; a, b)
+__global__ void __launch_bounds__(256)
+particles_prior_kernel(const float* __restrict__ theta, const float* __restrict__ prior_loc, const float* __restrict__ prior_scale,
+                       int64_t numel, int64_t total, float* __restrict__ G, double* __restrict__ loss) {
+    __shared__ double red[32];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double nlp = 0.0;
+    if (i < total) {
+        float g = -G[i];
+        if (prior_loc) {
+            const int64_t e = i % numel;
+            const float a = prior_loc[e], b = prior_scale[e], df = theta[i] - a, inv_b2 = 1.0f / (b * b);
+            g = __fmaf_rn(df, inv_b2, g);
+            nlp = (double)(0.5f * df * df * inv_b2 + logf(b) + BRN_HALF_LOG_2PI);
+        }
+        G[i] = g;
+    }
+    double tot = block_sum<double>(nlp, red);
+    if (threadIdx.x == 0 && prior_loc) atomicAdd(loss, tot);
+}
+
 }  // namespace brn
 
 using namespace brn;
+
+static int launch_linear_fused(const float* X, const void* y, int likelihood, int64_t N, int F, int C, int S, const float* W,
+                               float* dW, float inv_S, double* loss, cudaStream_t stream) {
+    LinearArgs a;
+    a.X = X; a.y = y; a.N = N; a.F = F; a.C = C; a.S = S; a.W = W; a.dW = dW;
+    a.inv_S = inv_S; a.loss = loss;
+    const int spc = LN_T / C;
+    const int col_tiles = (S + spc - 1) / spc;
+    a.n_row_tiles = (N + LN_T - 1) / LN_T;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t groups = sms / col_tiles;
+    if (groups < 1) groups = 1;
+    if (groups > a.n_row_tiles) groups = a.n_row_tiles;
+    a.tiles_per_group = (int)((a.n_row_tiles + groups - 1) / groups);
+    groups = (a.n_row_tiles + a.tiles_per_group - 1) / a.tiles_per_group;
+    const size_t smem = sizeof(float) * (3 * LN_T * LN_LD + LN_T);
+    dim3 grid(col_tiles, (unsigned)groups);
+    if (likelihood == 0) {
+        BRN_CUDA_OK(cudaFuncSetAttribute(linear_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        linear_fused_kernel<0><<<grid, 256, smem, stream>>>(a);
+    } else {
+        BRN_CUDA_OK(cudaFuncSetAttribute(linear_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        linear_fused_kernel<1><<<grid, 256, smem, stream>>>(a);
+    }
+    BRN_LAUNCH_OK("linear_fused_kernel");
+    return 0;
+}
+
+extern "C" int brn_linear_particles_loss_grad(const float* X, const void* y, int likelihood, int64_t N, int F, int C,
+                                              const float* theta, int n, const float* prior_loc, const float* prior_scale,
+                                              float* G, double* loss, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    BRN_CHECK_ARG(theta && G && loss, "brn_linear_particles_loss_grad: NULL pointer");
+    BRN_CHECK_ARG(N >= 0 && F > 0 && C > 0 && n >= 0, "brn_linear_particles_loss_grad: bad shape N=%lld F=%d C=%d n=%d",
+                  (long long)N, F, C, n);
+    BRN_CHECK_ARG(N == 0 || (X && y), "brn_linear_particles_loss_grad: NULL data pointer");
+    BRN_CHECK_ARG(F <= LN_T && C <= LN_T, "brn_linear_particles_loss_grad: F=%d / C=%d exceed the supported maximum %d", F, C, LN_T);
+    BRN_CHECK_ARG(likelihood == 0 || likelihood == 1, "brn_linear_particles_loss_grad: unknown likelihood %d", likelihood);
+    BRN_CHECK_ARG(likelihood == 1 || C == 1, "Bernoulli/Binomial likelihood needs C == 1 (got %d)", C);
+    BRN_CHECK_ARG((prior_loc == nullptr) == (prior_scale == nullptr), "prior_loc and prior_scale must both be given or both NULL");
+    if (n == 0) return 0;
+    set_variant("simt");
+    const int64_t numel = (int64_t)C * F, total = numel * n;
+    BRN_CUDA_OK(cudaMemsetAsync(G, 0, sizeof(float) * (size_t)total, stream));
+    if (N > 0) {
+        StageTimer st("particles.loglik_grad", stream);
+        if (int e = launch_linear_fused(X, y, likelihood, N, F, C, n, theta, G, 1.0f, loss, stream)) return e;
+    }
+    StageTimer st2("particles.prior", stream);
+    particles_prior_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(theta, prior_loc, prior_scale, numel, total, G, loss);
+    BRN_LAUNCH_OK("particles_prior_kernel");
+    return 0;
+}
 
 extern "C" size_t brn_linear_workspace_bytes(int64_t N, int F, int C, int s_local) {
     if (N < 0 || F <= 0 || C <= 0 || s_local < 0) return 0;
@@ -264,30 +340,7 @@ extern "C" int brn_linear_elbo_fwd_bwd(const float* X, const void* y, int likeli
     delete st;
     if (N > 0) {
         StageTimer st2("linear.fused", stream);
-        LinearArgs a;
-        a.X = X; a.y = y; a.N = N; a.F = F; a.C = C; a.S = S; a.W = ws.W; a.dW = ws.dW;
-        a.inv_S = 1.0f / (float)r->s_total; a.loss = loss;
-        const int spc = LN_T / C;
-        const int col_tiles = (S + spc - 1) / spc;
-        a.n_row_tiles = (N + LN_T - 1) / LN_T;
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        int64_t groups = sms / col_tiles;
-        if (groups < 1) groups = 1;
-        if (groups > a.n_row_tiles) groups = a.n_row_tiles;
-        a.tiles_per_group = (int)((a.n_row_tiles + groups - 1) / groups);
-        groups = (a.n_row_tiles + a.tiles_per_group - 1) / a.tiles_per_group;
-        const size_t smem = sizeof(float) * (3 * LN_T * LN_LD + LN_T);
-        dim3 grid(col_tiles, (unsigned)groups);
-        if (likelihood == 0) {
-            BRN_CUDA_OK(cudaFuncSetAttribute(linear_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            linear_fused_kernel<0><<<grid, 256, smem, stream>>>(a);
-        } else {
-            BRN_CUDA_OK(cudaFuncSetAttribute(linear_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            linear_fused_kernel<1><<<grid, 256, smem, stream>>>(a);
-        }
-        BRN_LAUNCH_OK("linear_fused_kernel");
+        if (int e = launch_linear_fused(X, y, likelihood, N, F, C, S, ws.W, ws.dW, 1.0f / (float)r->s_total, loss, stream)) return e;
     }
     StageTimer st3("linear.reduce_finalize", stream);
     return launch_mf_reduce_finalize(*w, eps, numel, ws.dW, numel, ws.stats, *r, with_prior, loss, stream);

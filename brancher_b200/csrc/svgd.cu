@@ -1,0 +1,334 @@
+// K4: Stein variational gradient descent direction -- pairwise RBF kernel + "repulsive" term as a tiled n^2 kernel.
+// See include/brancher_cuda.h (brn_svgd_direction) for the contract and the reference lines replaced
+// (brancher/inference.py:301-324, four nested Python loops over numpy scalars).
+//
+//   D2_ij = ||theta_i - theta_j||^2                                    svgd_d2_kernel     (n^2 d, direct differences)
+//   bw    = 2 median_{i != j}(sqrt D2_ij)^2 / ln n                     svgd_select_*      (exact radix select)
+//   out_i = sum_j K_ij (g_j - theta_j / bw) + theta_i rowsum_i(K) / bw svgd_update_kernel (K_ij = exp(-D2_ij / 2bw))
+//
+// The median is EXACT (np.median semantics: mean of the two middle order statistics): because D2 is symmetric the
+// multiset {D2_ij : i != j} is the multiset {D2_ij : i < j} with every element doubled, which has the same median,
+// so the select runs over the m = n(n-1)/2 upper-triangle values.  Non-negative floats order like their bit
+// patterns: three histogram passes (12 + 12 + 8 bits) pin the k-th smallest value, one more pass finds its successor.
+#include "common.cuh"
+
+namespace brn {
+
+constexpr int SV_T = 64;        // D2 tile edge
+constexpr int SV_KC = 32;       // feature chunk
+
+// D2[i][j] for a 64x64 tile; 256 threads, 4x4 outputs per thread.
+__global__ void __launch_bounds__(256) svgd_d2_kernel(const float* __restrict__ theta, int n, int d, float* __restrict__ D2) {
+    __shared__ float As[SV_KC][SV_T + 4], Bs[SV_KC][SV_T + 4];      // [k][row]
+    const int i0 = blockIdx.y * SV_T, j0 = blockIdx.x * SV_T;
+    const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+    for (int k0 = 0; k0 < d; k0 += SV_KC) {
+        __syncthreads();
+        for (int idx = t; idx < SV_T * SV_KC; idx += 256) {
+            const int row = idx / SV_KC, k = idx - row * SV_KC;
+            const bool kok = k0 + k < d;
+            As[k][row] = (kok && i0 + row < n) ? theta[(int64_t)(i0 + row) * d + k0 + k] : 0.f;
+            Bs[k][row] = (kok && j0 + row < n) ? theta[(int64_t)(j0 + row) * d + k0 + k] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < SV_KC; ++k) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const float df = av[a] - bv[b];
+                    acc[a][b] = __fmaf_rn(df, df, acc[a][b]);
+                }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int i = i0 + ty * 4 + a;
+        if (i >= n) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int j = j0 + tx * 4 + b;
+            if (j < n) D2[(int64_t)i * n + j] = acc[a][b];
+        }
+    }
+}
+
+struct SelectState {
+    unsigned long long rank;     // remaining 0-based rank inside the current prefix bucket
+    unsigned long long cnt_le;   // pass 4: #{v <= selected}
+    uint32_t prefix;             // high bits fixed so far (value of the k1-th smallest after the 3rd scan)
+    uint32_t next;               // pass 4: min{v > selected} (bit pattern)
+};
+
+// histogram of bits [shift, shift+nbits) over upper-triangle elements whose higher bits equal state->prefix
+__global__ void __launch_bounds__(256) svgd_select_hist_kernel(const float* __restrict__ D2, int n, int shift, int nbits,
+                                                               int first, const SelectState* __restrict__ st,
+                                                               unsigned int* __restrict__ hist) {
+    extern __shared__ unsigned int sh[];
+    const int nb = 1 << nbits;
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) sh[b] = 0u;
+    __syncthreads();
+    const uint32_t prefix = first ? 0u : st->prefix;
+    const int hshift = shift + nbits;
+    const int64_t total = (int64_t)n * n;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < total; base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = base + threadIdx.x;
+        bool take = false;
+        uint32_t bin = 0;
+        if (e < total) {
+            const int i = (int)(e / n), j = (int)(e - (int64_t)i * n);
+            if (i < j) {
+                const uint32_t v = __float_as_uint(D2[e]);
+                if (first || (hshift < 32 && (v >> hshift) == (prefix >> hshift))) {
+                    take = true;
+                    bin = (v >> shift) & (uint32_t)(nb - 1);
+                }
+            }
+        }
+        // warp-aggregated shared atomics: distances concentrate in a handful of bins
+        const unsigned active = __ballot_sync(0xffffffffu, take);
+        if (take) {
+            const unsigned peers = __match_any_sync(active, bin);
+            if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sh[bin], (unsigned)__popc(peers));
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < nb; b += blockDim.x)
+        if (sh[b]) atomicAdd(&hist[b], sh[b]);
+}
+
+// one block: walk the histogram to the bin holding the wanted rank, extend the prefix, clear the histogram
+__global__ void svgd_select_scan_kernel(int shift, int nbits, int first, unsigned long long k, SelectState* st,
+                                        unsigned int* hist) {
+    if (threadIdx.x == 0) {
+        unsigned long long rank = first ? k : st->rank;
+        uint32_t prefix = first ? 0u : st->prefix;
+        const int nb = 1 << nbits;
+        int b = 0;
+        for (; b < nb - 1; ++b) {
+            const unsigned long long c = hist[b];
+            if (rank < c) break;
+            rank -= c;
+        }
+        st->rank = rank;
+        st->prefix = prefix | ((uint32_t)b << shift);
+        st->cnt_le = 0ull;
+        st->next = 0x7f800000u;       // +inf
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < (1 << nbits); b += blockDim.x) hist[b] = 0u;
+}
+
+// pass 4: count of values <= selected and the smallest value above it
+__global__ void __launch_bounds__(256) svgd_select_succ_kernel(const float* __restrict__ D2, int n, SelectState* st) {
+    const uint32_t sel = st->prefix;
+    unsigned long long cnt = 0ull;
+    uint32_t nxt = 0x7f800000u;
+    const int64_t total = (int64_t)n * n;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(e / n), j = (int)(e - (int64_t)i * n);
+        if (i < j) {
+            const uint32_t v = __float_as_uint(D2[e]);
+            if (v <= sel) ++cnt;
+            else nxt = min(nxt, v);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        nxt = min(nxt, __shfl_xor_sync(0xffffffffu, nxt, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (cnt) atomicAdd(&st->cnt_le, cnt);
+        atomicMin(&st->next, nxt);
+    }
+}
+
+// bw = 2 * median(dist)^2 / ln n with median = (sqrt(v_k1) + sqrt(v_k2)) / 2   (np.median of float32 distances)
+__global__ void svgd_bandwidth_kernel(const SelectState* st, unsigned long long k2, int n, float* bw) {
+    if (threadIdx.x == 0) {
+        const float v1 = __uint_as_float(st->prefix);
+        const float v2 = st->cnt_le >= k2 + 1ull ? v1 : __uint_as_float(st->next);
+        const float med = 0.5f * (sqrtf(v1) + sqrtf(v2));
+        *bw = (float)(2.0 * (double)(med * med) / log((double)n));
+    }
+}
+
+// out[i, :] (+)= sum_j K_ij (g_j - theta_j / bw) + theta_i rowsum_i(K) / bw over this CTA's j range.
+// CTA: 32 rows x 128 columns, 128 threads (4 rows x 8 columns each), j tiles of 32; grid = (row tiles, d chunks, j splits).
+constexpr int SU_TI = 32, SU_TJ = 32, SU_TD = 128;
+
+__global__ void __launch_bounds__(128)
+svgd_update_kernel(const float* __restrict__ theta, const float* __restrict__ grad, const float* __restrict__ D2, int n, int d,
+                   int row0, int rows, const float* __restrict__ bw_ptr, float* __restrict__ out, int j_per_split) {
+    __shared__ __align__(16) float Ks[SU_TJ][SU_TI + 4];     // [jj][ii]
+    __shared__ __align__(16) float Vs[SU_TJ][SU_TD + 4];     // [jj][col]
+    __shared__ float rs_s[SU_TI];
+    const int t = threadIdx.x, tx = t & 15, ty = t >> 4;     // ty: 0..7 -> rows ty*4.., tx: cols tx*4.. and 64+tx*4..
+    const int i0 = row0 + blockIdx.x * SU_TI, c0 = blockIdx.y * SU_TD;
+    const int jbeg = blockIdx.z * j_per_split, jend = min(n, jbeg + j_per_split);
+    const int iend = row0 + rows;
+    const float bw = *bw_ptr, inv_bw = 1.0f / bw, nh = -0.5f / bw;
+    float acc[4][8];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
+    float rs[4] = {0.f, 0.f, 0.f, 0.f};
+
+    for (int j0 = jbeg; j0 < jend; j0 += SU_TJ) {
+        __syncthreads();
+        for (int idx = t; idx < SU_TI * SU_TJ; idx += 128) {
+            const int ii = idx >> 5, jj = idx & 31;
+            float kv = 0.f;
+            if (i0 + ii < iend && j0 + jj < jend) kv = expf(nh * D2[(int64_t)(i0 + ii) * n + j0 + jj]);
+            Ks[jj][ii] = kv;
+        }
+        for (int idx = t; idx < SU_TJ * (SU_TD / 4); idx += 128) {
+            const int jj = idx >> 5, c4 = (idx & 31) * 4;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (j0 + jj < jend) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int c = c0 + c4 + q;
+                    if (c < d) {
+                        const int64_t o = (int64_t)(j0 + jj) * d + c;
+                        v[q] = __fmaf_rn(-theta[o], inv_bw, grad[o]);
+                    }
+                }
+            }
+            *reinterpret_cast<float4*>(&Vs[jj][c4]) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int jj = 0; jj < SU_TJ; ++jj) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&Ks[jj][ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Vs[jj][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Vs[jj][64 + tx * 4]);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                if (tx == 0) rs[a] += av[a];
+#pragma unroll
+                for (int b = 0; b < 8; ++b) acc[a][b] = __fmaf_rn(av[a], bv[b], acc[a][b]);
+            }
+        }
+    }
+    if (tx == 0) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) rs_s[ty * 4 + a] = rs[a];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int i = i0 + ty * 4 + a;
+        if (i >= iend) continue;
+        const float w = rs_s[ty * 4 + a] * inv_bw;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int c = c0 + (b < 4 ? tx * 4 + b : 64 + tx * 4 + (b - 4));
+            if (c >= d) continue;
+            const float v = __fmaf_rn(theta[(int64_t)i * d + c], w, acc[a][b]);
+            float* o = out + (int64_t)(i - row0) * d + c;
+            if (gridDim.z == 1) *o = v;
+            else atomicAdd(o, v);
+        }
+    }
+}
+
+struct SvgdWorkspace {
+    float* D2;
+    unsigned int* hist;
+    SelectState* st;
+    size_t bytes;
+    SvgdWorkspace(void* base, int n) {
+        size_t off = 0;
+        auto take = [&](size_t nbytes) {
+            char* p = base ? reinterpret_cast<char*>(base) + off : nullptr;
+            off += (nbytes + 255) / 256 * 256;
+            return p;
+        };
+        D2 = reinterpret_cast<float*>(take(sizeof(float) * (size_t)n * n));
+        hist = reinterpret_cast<unsigned int*>(take(sizeof(unsigned int) * 4096));
+        st = reinterpret_cast<SelectState*>(take(sizeof(SelectState)));
+        bytes = off;
+    }
+};
+
+}  // namespace brn
+
+using namespace brn;
+
+extern "C" size_t brn_svgd_workspace_bytes(int n, int d) {
+    if (n <= 0 || d <= 0) return 0;
+    return SvgdWorkspace(nullptr, n).bytes;
+}
+
+extern "C" int brn_svgd_direction(const float* theta, const float* grad, int n, int d, int row0, int rows,
+                                  int update_bandwidth, float* bandwidth, float* out, void* workspace,
+                                  size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    BRN_CHECK_ARG(theta && grad && bandwidth && (out || rows == 0), "brn_svgd_direction: NULL pointer");
+    BRN_CHECK_ARG(n >= 2 && d > 0, "brn_svgd_direction: need n >= 2 particles and d > 0 (got n=%d d=%d)", n, d);
+    BRN_CHECK_ARG(row0 >= 0 && rows >= 0 && row0 + rows <= n, "brn_svgd_direction: bad row range [%d, %d) of %d", row0,
+                  row0 + rows, n);
+    SvgdWorkspace ws(workspace, n);
+    BRN_CHECK_ARG(workspace && workspace_bytes >= ws.bytes, "workspace too small: %zu < %zu", workspace_bytes, ws.bytes);
+    set_variant("simt");
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    {
+        StageTimer st("svgd.pairwise_d2", stream);
+        dim3 grid((n + SV_T - 1) / SV_T, (n + SV_T - 1) / SV_T);
+        svgd_d2_kernel<<<grid, 256, 0, stream>>>(theta, n, d, ws.D2);
+        BRN_LAUNCH_OK("svgd_d2_kernel");
+    }
+    if (update_bandwidth) {
+        StageTimer st("svgd.median_bandwidth", stream);
+        const unsigned long long m = (unsigned long long)n * (unsigned long long)(n - 1) / 2ull;
+        const unsigned long long k1 = (m - 1ull) / 2ull, k2 = m / 2ull;
+        BRN_CUDA_OK(cudaMemsetAsync(ws.hist, 0, sizeof(unsigned int) * 4096, stream));
+        const int64_t total = (int64_t)n * n;
+        int64_t hblocks = (total + 255) / 256;
+        if (hblocks > (int64_t)sms * 8) hblocks = (int64_t)sms * 8;
+        const int hgrid = (int)hblocks;
+        const int shifts[3] = {20, 8, 0}, nbits[3] = {12, 12, 8};
+        for (int lv = 0; lv < 3; ++lv) {
+            svgd_select_hist_kernel<<<hgrid, 256, sizeof(unsigned int) << nbits[lv], stream>>>(ws.D2, n, shifts[lv], nbits[lv],
+                                                                                             lv == 0, ws.st, ws.hist);
+            BRN_LAUNCH_OK("svgd_select_hist_kernel");
+            svgd_select_scan_kernel<<<1, 256, 0, stream>>>(shifts[lv], nbits[lv], lv == 0, k1, ws.st, ws.hist);
+            BRN_LAUNCH_OK("svgd_select_scan_kernel");
+        }
+        svgd_select_succ_kernel<<<hgrid, 256, 0, stream>>>(ws.D2, n, ws.st);
+        BRN_LAUNCH_OK("svgd_select_succ_kernel");
+        svgd_bandwidth_kernel<<<1, 32, 0, stream>>>(ws.st, k2, n, bandwidth);
+        BRN_LAUNCH_OK("svgd_bandwidth_kernel");
+    }
+    if (rows > 0) {
+        StageTimer st("svgd.update", stream);
+        const int row_tiles = (rows + SU_TI - 1) / SU_TI, d_chunks = (d + SU_TD - 1) / SU_TD;
+        int splits = (2 * sms) / (row_tiles * d_chunks);
+        const int max_splits = (n + 4 * SU_TJ - 1) / (4 * SU_TJ);
+        if (splits > max_splits) splits = max_splits;
+        if (splits < 1) splits = 1;
+        int j_per_split = ((n + splits - 1) / splits + SU_TJ - 1) / SU_TJ * SU_TJ;
+        splits = (n + j_per_split - 1) / j_per_split;
+        if (splits > 1) BRN_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)rows * d, stream));
+        dim3 grid(row_tiles, d_chunks, splits);
+        svgd_update_kernel<<<grid, 128, 0, stream>>>(theta, grad, ws.D2, n, d, row0, rows, bandwidth, out, j_per_split);
+        BRN_LAUNCH_OK("svgd_update_kernel");
+    }
+    return 0;
+}

@@ -309,6 +309,103 @@ def lower(joint, posterior):
                                 "(linear K2, bnn K3); likelihood link: %s" % k.partial_links["logits"].string)
 
 
+# ---------------------------------------------------------------------------------------------------
+# particle ensembles (SVGD, K4)
+# ---------------------------------------------------------------------------------------------------
+class _ParticleLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, runner, *params):
+        loss, G = runner()
+        ctx.G, ctx.shapes = G, [p.shape for p in params]
+        return loss.to(torch.float32).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        return (None,) + tuple(g * ctx.G[i].reshape(sh) for i, sh in enumerate(ctx.shapes))
+
+
+class ParticlePlan:
+    """SVGD over (multi-class) logistic-regression particles: the joint model is the linear family (K2's graph), every
+    particle is a ProbabilisticModel holding ONE learnable RootVariable named like the weights latent
+    (development_playgrounds/SVGD_logistic_regression.py:34-48)."""
+    family = "particles (K4)"
+
+    def __init__(self, joint, particles, k, W, x_var, likelihood, C):
+        self.joint, self.particles, self.k, self.x_var, self.likelihood, self.C = joint, particles, k, x_var, likelihood, C
+        lp = W.partial_links
+        loc, sc_sp = _as_root(lp["loc"].expr), _softplus_root(lp["scale"].expr)
+        sc = sc_sp or _as_root(lp["scale"].expr)
+        if loc is None or sc is None:
+            raise UnsupportedModelError("particle family: the prior's loc/scale must be constants")
+        self.shape = tuple(loc._value.shape[2:])
+        full = lambda t: t.detach().to(torch.float32).expand((1, 1) + self.shape).reshape(-1).contiguous()
+        self.prior_loc = full(loc.value)
+        self.prior_scale = full(torch.nn.functional.softplus(sc.value) if sc_sp is not None else sc.value)
+        self.roots = []
+        for p in particles:
+            roots = [v for v in p._flatten() if isinstance(v, RootVariable) and v.name == W.name]
+            if len(roots) != 1 or tuple(roots[0]._value.shape[2:]) != self.shape:
+                raise UnsupportedModelError("every particle must hold one root named %r of shape %s" % (W.name, self.shape))
+            self.roots.append(roots[0])
+
+    def parameters(self):
+        return [r.value for r in self.roots]
+
+    def stacked(self):
+        return torch.stack([p.detach().reshape(-1) for p in self.parameters()]).contiguous()
+
+    def loss(self, empirical):
+        if config.device.type != "cuda":
+            raise RuntimeError("brancher_b200 evaluates particle losses only on CUDA devices (no CPU fallback)")
+        from brancher_b200 import _cuda as cu
+        cu.lib()
+
+        def runner():
+            X = _data_matrix(empirical[self.x_var], "x")
+            yv = empirical[self.k].reshape(-1)
+            y = yv.to(torch.float32).contiguous() if self.likelihood == cu.BERNOULLI else yv.to(torch.int32).contiguous()
+            return cu.linear_particles_loss_grad(X, y, self.likelihood, self.stacked(), self.C, self.prior_loc, self.prior_scale)
+
+        return _ParticleLoss.apply(runner, *self.parameters())
+
+
+def lower_particles(joint, particles):
+    from brancher_b200 import _cuda as cu
+    latents = _latent_random_variables(joint)
+    liks = _observed_likelihood_nodes(joint)
+    if len(liks) != 1 or len(latents) != 1:
+        raise UnsupportedModelError("particle family needs one observed likelihood node and one latent weight matrix")
+    k, W = liks[0], latents[0]
+    kind = k.distribution.kind
+    if kind not in ("binomial", "bernoulli", "categorical") or "logits" not in k.partial_links:
+        raise UnsupportedModelError("particle family: likelihood %r is not lowered" % kind)
+    if kind == "binomial":
+        tc = _as_root(k.partial_links["total_count"].expr)
+        if tc is None or tc.value.numel() != 1 or float(tc.value.reshape(-1)[0]) != 1.0:
+            raise UnsupportedModelError("Binomial likelihood is lowered only for total_count=1")
+    logits = k.partial_links["logits"].expr
+    if not (_is_call(logits, "matmul", 2) and _var(logits.args[0]) is W and _is_data(_var(logits.args[1]))):
+        raise UnsupportedModelError("particle family: logits must be BF.matmul(weights, x)")
+    if W.distribution.kind != "normal":
+        raise UnsupportedModelError("particle family: only a Normal prior on the weights is lowered")
+    shape = tuple(W.partial_links["loc"].expr.var._value.shape[2:]) if _as_root(W.partial_links["loc"].expr) else ()
+    if len(shape) != 2:
+        raise UnsupportedModelError("particle family: weights must be a [C, F] matrix")
+    C = shape[0]
+    if kind != "categorical" and C != 1:
+        raise UnsupportedModelError("Binomial/Bernoulli logistic regression needs weights of shape [1, F]")
+    return ParticlePlan(joint, particles, k, W, _var(logits.args[1]), cu.CATEGORICAL if kind == "categorical" else cu.BERNOULLI, C)
+
+
+def get_particle_plan(joint, particles):
+    key = ("particles",) + tuple(id(p) for p in particles)
+    plan = joint._plans.get(key)
+    if plan is None:
+        plan = lower_particles(joint, list(particles))
+        joint._plans[key] = plan
+    return plan
+
+
 def get_plan(joint, posterior):
     key = id(posterior)
     plan = joint._plans.get(key)

@@ -111,6 +111,27 @@ int brn_linear_elbo_fwd_bwd(const float* X, const void* y, int likelihood, int64
                             void* workspace, size_t workspace_bytes, int with_prior,
                             double* loss, void* stream);
 
+/* K4 -- Stein variational gradient descent (SVGD).
+ * (a) per-particle loss and gradient for (multi-class) logistic-regression particles theta [n, C*F]:
+ *       loss += sum_k [ -sum_rows log-lik(theta_k) - sum log N(theta_k; prior_loc, prior_scale) ]     (prior optional)
+ *       G[k]  = d loss / d theta_k                                                     (overwritten, [n, C*F])
+ *     Replaces SteinVariationalGradientDescent.compute_loss + loss.backward() (inference.py:292-299, 100) for the
+ *     model of development_playgrounds/SVGD_logistic_regression.py:34-48 (one ProbabilisticModel per particle).
+ * (b) the SVGD direction for particles [row0, row0+rows) given ALL n particles and gradients (all-gathered by the
+ *     host when particles are sharded over GPUs):
+ *       D2_ij = ||theta_i - theta_j||^2 ; bw = 2 median_{i != j}(sqrt D2_ij)^2 / ln n   (exact np.median semantics)
+ *       K_ij = exp(-D2_ij / (2 bw)) ; out_i = sum_j K_ij grad_j + (rowsum_i(K) theta_i - sum_j K_ij theta_j) / bw
+ *     -- the reference's sign convention for the second term (attractive; canonical SVGD has the opposite sign) and
+ *     no 1/n, exactly as SteinVariationalGradientDescent.correct_gradient / update_bandwidth compute it with four
+ *     nested Python loops (inference.py:301-324).  `bandwidth` is a DEVICE float: written when update_bandwidth != 0,
+ *     read otherwise.  out [rows, d] is overwritten. */
+int brn_linear_particles_loss_grad(const float* X, const void* y, int likelihood, int64_t N, int F, int C,
+                                   const float* theta, int n, const float* prior_loc, const float* prior_scale,
+                                   float* G, double* loss, void* stream);
+size_t brn_svgd_workspace_bytes(int n, int d);
+int brn_svgd_direction(const float* theta, const float* grad, int n, int d, int row0, int rows, int update_bandwidth,
+                       float* bandwidth, float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Tensor-core building block, exposed for validation: D[M][N] = A[M][K] . B[N][K]^T (all row-major fp32)
  * computed with tcgen05.mma kind::tf32 and the 3xTF32 hi/lo split (fp32-equivalent accuracy), TMA-fed.
  * This is the contraction the reference performs as a batched torch.matmul inside _apply_link

@@ -233,6 +233,31 @@ def ar1_elbo(y, params, eps, measure_noise=0.3, dtype=torch.float32):
 
 
 # ----------------------------------------------------------------------------------------------
+# SVGD particle loss (config C4): SteinVariationalGradientDescent.compute_loss, inference.py:292-299:
+#   loss = sum_particles -joint.calculate_log_probability(sample_k)   (prior + summed observed log-lik)
+# ----------------------------------------------------------------------------------------------
+def particles_loss_grad(X, y, theta, prior=None, dtype=torch.float32, likelihood="categorical"):
+    """theta [n, C, F] particles of (multi-class) logistic regression; prior = (loc, scale) arrays [C,F] or None.
+    Returns (loss, G [n, C, F] = d loss / d theta)."""
+    Xt = _t(X, dtype)
+    th = _t(theta, dtype, requires_grad=True)
+    logits = torch.einsum("ncf,bf->nbc", th, Xt)
+    if Xt.shape[0] == 0:                         # empty minibatch: torch.distributions cannot validate 0-row logits
+        ll = (th * 0).sum()
+    elif likelihood == "categorical":
+        yt = torch.as_tensor(np.asarray(y), dtype=torch.long)
+        ll = D.Categorical(logits=logits).log_prob(yt[None, :]).sum()
+    else:
+        yt = _t(y, dtype)
+        ll = D.Binomial(total_count=1, logits=logits[..., 0]).log_prob(yt[None, :]).sum()
+    loss = -ll
+    if prior is not None:
+        loss = loss - D.Normal(_t(prior[0], dtype), _t(prior[1], dtype)).log_prob(th).sum()
+    loss.backward()
+    return float(loss.detach()), th.grad.detach().numpy().copy()
+
+
+# ----------------------------------------------------------------------------------------------
 # SVGD direction (config C4): inference.py:301-324, vectorised (SURVEY §8 a21).
 # ----------------------------------------------------------------------------------------------
 def svgd_direction(theta, grad, dtype=np.float64):

@@ -154,6 +154,21 @@ def svgd(seed, n, d, tag="svgd_small"):
     save(tag, theta=theta, grad=grad, out=out, bandwidth=float(m.bandwidth))
 
 
+def svgd_model(seed, B, F, C, n, tag="svgd_softmax"):
+    """One full SVGD gradient evaluation through the reference: compute_loss (inference.py:292-299), backward,
+    correct_gradient (:301-315) on the softmax-regression particles of the playground."""
+    model, particles, d = zoo.svgd_softmax(NS, seed, B, F, C, n)
+    m = inference.SteinVariationalGradientDescent()
+    model.update_observed_submodel()
+    loss = m.compute_loss(model, particles, None, 1)
+    loss.backward()
+    raw = np.stack([list(p.flatten())[0].value.grad.detach().numpy().reshape(C, F).copy() for p in particles])
+    m.correct_gradient(model, particles, None, 1)
+    out = np.stack([list(p.flatten())[0].value.grad.detach().numpy().reshape(C, F).copy() for p in particles])
+    save(tag, X=d["X"], y=d["y"], theta=d["theta"], loss=float(loss.detach().sum()), raw_grad=raw, out=out,
+         bandwidth=float(m.bandwidth), prior_loc=np.zeros((C, F), "float32"), prior_scale=10 * np.ones((C, F), "float32"))
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     bnn(1, B=12, P=20, H=7, C=4, S=6, tag="bnn_small")
@@ -163,3 +178,4 @@ if __name__ == "__main__":
     softmax_reg(5, B=24, F=6, C=3, S=8, tag="softmax_reg")
     ar1(6, T=20, S=32, tag="ar1_readme")
     svgd(7, n=7, d=5, tag="svgd_small")
+    svgd_model(8, B=30, F=5, C=3, n=6, tag="svgd_softmax")

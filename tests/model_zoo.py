@@ -85,6 +85,23 @@ def softmax_reg(ns, seed, B, F, C):
     return model, Q, {"X": X[:, :, 0], "y": y, "rng": rng}
 
 
+def svgd_softmax(ns, seed, B, F, C, n):
+    """development_playgrounds/SVGD_logistic_regression.py:34-48: softmax regression, one single-root
+    ProbabilisticModel per particle (logits= instead of the playground's broken softmax_p=)."""
+    rng = np.random.RandomState(seed)
+    X = rng.randn(B, F, 1).astype("float32")
+    y = rng.randint(0, C, size=(B,))
+    x = ns.RootVariable(X, "x", is_observed=True)
+    weights = ns.NormalVariable(np.zeros((C, F)), 10 * np.ones((C, F)), "weights")
+    k = ns.CategoricalVariable(logits=ns.BF.matmul(weights, x), name="k")
+    model = ns.ProbabilisticModel([k])
+    k.observe(y)
+    theta0 = rng.randn(n, C, F).astype("float32")
+    particles = [ns.ProbabilisticModel([ns.RootVariable(theta0[i].astype("float64"), name="weights", learnable=True)])
+                 for i in range(n)]
+    return model, particles, {"X": X[:, :, 0], "y": y, "theta": theta0, "rng": rng}
+
+
 def ar1(ns, seed, T):
     """README.md:22-75 model, y0 named 'y0' (the README reuses 'x0')."""
     rng = np.random.RandomState(seed)

@@ -107,3 +107,16 @@ def test_shard_is_balanced_partition():
             assert first == pos
             pos += count
         assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
+
+
+def test_svgd_particles_lower_to_k4(ns):
+    """The SVGD playground's particle ensemble is recognised by the graph matcher (no GPU needed)."""
+    from brancher_b200 import lowering
+    model, particles, d = zoo.svgd_softmax(ns, 8, B=30, F=5, C=3, n=6)
+    plan = lowering.get_particle_plan(model, particles)
+    assert plan.family == "particles (K4)" and plan.shape == (3, 5) and plan.C == 3
+    assert plan.stacked().shape == (6, 15)
+    np.testing.assert_allclose(plan.prior_scale.numpy(), 10.0, rtol=1e-6)
+    bad = [ns.ProbabilisticModel([ns.RootVariable(np.zeros((2, 2)), name="weights", learnable=True)])]
+    with pytest.raises(lowering.UnsupportedModelError):
+        lowering.lower_particles(model, bad)
