@@ -63,6 +63,9 @@ SYMBOLS = {
                                                ctypes.c_int, ctypes.c_int, ctypes.POINTER(MFVar),
                                                ctypes.POINTER(SampleRange), ctypes.c_void_p, ctypes.c_size_t,
                                                ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "brn_dag_elbo_fwd_bwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                            ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                            ctypes.POINTER(SampleRange), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "brn_linear_particles_loss_grad": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
                                                       ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
@@ -258,6 +261,23 @@ def linear_elbo_fwd_bwd(X, y, likelihood, w, C, r, with_prior=True, loss=None):
                                          ctypes.byref(r), ws.data_ptr(), ws.numel(), int(with_prior),
                                          _ptr(loss, torch.float64), _stream(dev)), "brn_linear_elbo_fwd_bwd")
     return loss
+
+
+def dag_elbo_fwd_bwd(ops, n_ops, n_slots, params, data, n_rows, eps, n_eps, r, loss=None):
+    """K1.  ops: uint8 CUDA tensor holding n_ops packed `brn_dag_op` records (24 bytes each); params [n_params] fp32;
+    data [n_rows, n_cols] fp32 or None; eps [s_local, n_eps] fp32 or None (Philox).  Returns (loss fp64 [1], dparams)."""
+    dev = ops.device
+    if ops.dtype != torch.uint8 or ops.numel() != 24 * n_ops:
+        raise BrancherCudaError("ops must be a uint8 tensor of %d bytes" % (24 * n_ops))
+    loss = torch.zeros(1, dtype=torch.float64, device=dev) if loss is None else loss
+    dparams = torch.zeros_like(params)
+    n_cols = 0 if data is None else data.shape[1]
+    if eps is not None and (eps.shape[0] != r.s_local or eps.shape[1] != n_eps):
+        raise BrancherCudaError("eps must be [s_local=%d, n_eps=%d], got %s" % (r.s_local, n_eps, tuple(eps.shape)))
+    _check(lib().brn_dag_elbo_fwd_bwd(_ptr(ops, torch.uint8, "ops"), n_ops, n_slots, _ptr(params, what="params"), params.numel(),
+                                      _ptr(data, what="data"), n_cols, n_rows, _ptr(eps, what="eps"), n_eps, ctypes.byref(r),
+                                      _ptr(dparams), _ptr(loss, torch.float64), _stream(dev)), "brn_dag_elbo_fwd_bwd")
+    return loss, dparams
 
 
 def linear_particles_loss_grad(X, y, likelihood, theta, C, prior_loc=None, prior_scale=None, loss=None):

@@ -253,7 +253,7 @@ def _is_data(var):
                                                     var.distribution.kind in ("deterministic", "empirical"))
 
 
-def lower(joint, posterior):
+def _lower_dense(joint, posterior):
     from brancher_b200 import _cuda as cu
     q_names = {v.name for v in posterior._flatten()}
     q_by_name = {v.name: v for v in posterior._flatten()}
@@ -307,6 +307,275 @@ def lower(joint, posterior):
                     return BNNPlan(joint, posterior, k, [spec(W1), spec(b1), spec(W2), spec(b2)], x)
     raise UnsupportedModelError("model graph is not recognised by any fused kernel family "
                                 "(linear K2, bnn K3); likelihood link: %s" % k.partial_links["logits"].string)
+
+
+
+# ---------------------------------------------------------------------------------------------------
+# K1: scalar-DAG family
+# ---------------------------------------------------------------------------------------------------
+_DAG = dict(CONST=0, PARAM=1, DATA=2, EPS=3, ADD=4, SUB=5, MUL=6, DIV=7, NEG=8, POWI=9, EXP=10, LOG=11, LOG1P=12,
+            SIGMOID=13, SOFTPLUS=14, TANH=15, SIN=16, COS=17, RELU=18, SQRT=19, ABS=20, CLAMP_UNIT=21, NORMAL_LP=22,
+            NORMAL_ENTROPY=23, ACC_SAMPLE=24, ACC_ROW=25)             # include/brancher_cuda.h: enum brn_dag_opcode
+_DAG_BINARY = {"add": "ADD", "sub": "SUB", "mul": "MUL", "truediv": "DIV"}
+_DAG_UNARY = {"exp": "EXP", "log": "LOG", "log1p": "LOG1P", "sigmoid": "SIGMOID", "softplus": "SOFTPLUS", "tanh": "TANH",
+              "sin": "SIN", "cos": "COS", "relu": "RELU", "sqrt": "SQRT", "abs": "ABS", "neg": "NEG"}
+_DAG_LOC_SCALE = ("normal", "lognormal", "logitnormal")
+DAG_MAX_SLOTS, DAG_MAX_PARAMS = 2048, 2048
+
+
+class DagProgram:
+    """Straight-line SSA program for brn_dag_elbo_fwd_bwd (one op = (opcode, dst, a, b, c, imm))."""
+
+    def __init__(self):
+        self.ops, self.n_slots = [], 0
+        self.params, self._pidx = [], {}      # nn.Parameter (numel 1) per PARAM index
+        self.columns = []                     # observed Variable per DATA column
+        self.col_rows = []                    # rows of that column at lowering time (1 = broadcast)
+        self.eps_names = []                   # q variable name per EPS stream
+        self.rowdep = {}                      # slot -> depends on a multi-row DATA column
+
+    def emit(self, op, a=0, b=0, c=0, imm=0.0, rowdep=None):
+        dst = self.n_slots
+        self.n_slots += 1
+        self.ops.append((_DAG[op], dst, a, b, c, float(imm)))
+        if rowdep is None:
+            rowdep = any(self.rowdep.get(x, False) for x in (a, b, c)) if op not in ("CONST", "PARAM", "DATA", "EPS") else False
+        self.rowdep[dst] = rowdep
+        return dst
+
+    def const(self, v):
+        return self.emit("CONST", imm=float(v))
+
+    def param(self, p):
+        if p.numel() != 1:
+            raise UnsupportedModelError("scalar-DAG family: learnable parameters must be scalars (got shape %s)" % (tuple(p.shape),))
+        if id(p) not in self._pidx:
+            self._pidx[id(p)] = len(self.params)
+            self.params.append(p)
+        return self.emit("PARAM", a=self._pidx[id(p)])
+
+    def data(self, var, rows):
+        self.columns.append(var)
+        self.col_rows.append(rows)
+        return self.emit("DATA", a=len(self.columns) - 1, rowdep=rows > 1)
+
+    def eps(self, name):
+        self.eps_names.append(name)
+        return self.emit("EPS", a=len(self.eps_names) - 1)
+
+    def table(self):
+        t = np.zeros(len(self.ops), dtype=np.dtype([("opcode", "<i4"), ("dst", "<i4"), ("a", "<i4"), ("b", "<i4"),
+                                                    ("c", "<i4"), ("imm", "<f4")]))
+        for i, o in enumerate(self.ops):
+            t[i] = o
+        return t
+
+
+def _observed_tensor(var):
+    t = var._observed_value if isinstance(var, RandomVariable) else var._value
+    if not torch.is_tensor(t):
+        raise UnsupportedModelError("scalar-DAG family: observed value of %r is not a tensor" % var.name)
+    if t.dim() < 2 or t.shape[0] != 1 or int(np.prod(t.shape[2:])) != 1:
+        raise UnsupportedModelError("scalar-DAG family: observed %r must hold scalars per data row (shape %s)" % (var.name, tuple(t.shape)))
+    return t
+
+
+class DagPlan(Plan):
+    family = "dag (K1)"
+
+    def __init__(self, joint, posterior):
+        super().__init__(joint, posterior)
+        P = self.prog = DagProgram()
+        q_vars = posterior._flatten()
+        self.q_by_name = {v.name: v for v in q_vars}
+        if len(self.q_by_name) != len(q_vars):
+            raise UnsupportedModelError("scalar-DAG family: duplicate variable names in the posterior model")
+        self._q, self._p, self._qinfo = {}, {}, {}
+        # q sampling, in name order (noise stream k = k-th sampled q variable in this order)
+        for v in q_vars:
+            self.q_value(v)
+        terms = []
+        # log p(x, z) with q's samples re-assigned BY NAME (utilities.py:282-309), roots included
+        for v in joint._flatten():
+            if not isinstance(v, RandomVariable) or v.distribution.kind in ("deterministic", "empirical"):
+                continue
+            kind = v.distribution.kind
+            if kind not in _DAG_LOC_SCALE:
+                raise UnsupportedModelError("scalar-DAG family: distribution %r of %r is not lowered" % (kind, v.name))
+            x = self.p_value(v)
+            loc = self.compile(v.partial_links["loc"].expr, self.p_value)
+            scale = self.compile(v.partial_links["scale"].expr, self.p_value)
+            lp = self.log_prob(kind, x, loc, scale)
+            if P.rowdep[lp] and not v.is_observed:
+                raise UnsupportedModelError("scalar-DAG family: latent %r has a per-row log-probability (local latents are "
+                                            "not lowered)" % v.name)
+            terms.append(("ACC_ROW" if P.rowdep[lp] else "ACC_SAMPLE", lp))
+        # entropy of q: analytic where torch has it, else -log q (variables.py:156-162, 744-749)
+        for v in q_vars:
+            info = self._qinfo.get(v.name)
+            if info is None:
+                continue
+            kind, loc, scale, z = info
+            if kind == "normal":
+                h = P.emit("NORMAL_ENTROPY", a=scale)
+            elif kind == "lognormal":
+                h = P.emit("ADD", a=P.emit("NORMAL_ENTROPY", a=scale), b=loc)
+            else:
+                h = P.emit("NEG", a=self.log_prob(kind, z, loc, scale))
+            if P.rowdep[h]:
+                raise UnsupportedModelError("scalar-DAG family: q variable %r depends on per-row data (amortised posteriors are "
+                                            "not lowered)" % v.name)
+            terms.append(("ACC_SAMPLE", h))
+        for op, slot in terms:
+            P.emit(op, a=slot)
+        if P.n_slots > DAG_MAX_SLOTS or len(P.params) > DAG_MAX_PARAMS:
+            raise UnsupportedModelError("scalar-DAG family: program too large (%d slots, %d parameters)" % (P.n_slots, len(P.params)))
+        rows = [r for r in P.col_rows if r > 1]
+        if rows and any(r != rows[0] for r in rows):
+            raise UnsupportedModelError("scalar-DAG family: observed variables disagree on the number of data rows %s" % sorted(set(rows)))
+        self.n_rows = rows[0] if rows else 1
+        self._ops_dev = None
+
+    # -- values ------------------------------------------------------------------------------------
+    def _root_value(self, var):
+        P = self.prog
+        if var.is_observed:
+            return P.data(var, _observed_tensor(var).shape[1])
+        if var.learnable:
+            return P.param(var._value)
+        t = var._value
+        if not torch.is_tensor(t) or t.numel() != 1:
+            raise UnsupportedModelError("scalar-DAG family: constant %r is not a scalar" % var.name)
+        return P.const(float(t.reshape(-1)[0]))
+
+    def q_value(self, var):
+        if id(var) in self._q:
+            return self._q[id(var)]
+        P = self.prog
+        if isinstance(var, RootVariable):
+            slot = self._root_value(var)
+        elif var.distribution.kind == "deterministic":
+            slot = self.compile(var.partial_links["value"].expr, self.q_value)
+        elif var.distribution.kind in _DAG_LOC_SCALE:
+            kind = var.distribution.kind
+            loc = self.compile(var.partial_links["loc"].expr, self.q_value)
+            scale = self.compile(var.partial_links["scale"].expr, self.q_value)
+            u = P.emit("ADD", a=loc, b=P.emit("MUL", a=P.eps(var.name), b=scale))       # torch Normal.rsample: loc + eps * scale
+            slot = u if kind == "normal" else P.emit("EXP" if kind == "lognormal" else "SIGMOID", a=u)
+            self._qinfo[var.name] = (kind, loc, scale, slot)
+        else:
+            raise UnsupportedModelError("scalar-DAG family: q variable %r (%s) is not lowered" % (var.name, var.distribution.kind))
+        self._q[id(var)] = slot
+        return slot
+
+    def p_value(self, var):
+        if id(var) in self._p:
+            return self._p[id(var)]
+        P = self.prog
+        if var.name in self.q_by_name and not var.is_observed:
+            slot = self.q_value(self.q_by_name[var.name])               # by-name re-assignment (collision quirk included)
+        elif isinstance(var, RootVariable):
+            slot = self._root_value(var)
+        elif var.distribution.kind == "deterministic" and not var.has_observed_value:
+            slot = self.compile(var.partial_links["value"].expr, self.p_value)      # incl. observed regressors (observed root)
+        elif var.is_observed:
+            if not var.has_observed_value:
+                raise UnsupportedModelError("scalar-DAG family: %r is observed through a random dataset" % var.name)
+            slot = P.data(var, _observed_tensor(var).shape[1])
+        else:
+            raise UnsupportedModelError("latent variable %r has no counterpart in the posterior model" % var.name)
+        self._p[id(var)] = slot
+        return slot
+
+    # -- expressions -------------------------------------------------------------------------------
+    def compile(self, e, value_of):
+        P = self.prog
+        if isinstance(e, VarRef):
+            return value_of(e.var)
+        if isinstance(e, Const) or isinstance(e, (int, float, np.floating, np.integer)):
+            v = e.value if isinstance(e, Const) else e
+            if isinstance(v, np.ndarray) or torch.is_tensor(v):
+                if int(np.prod(v.shape)) != 1:
+                    raise UnsupportedModelError("scalar-DAG family: non-scalar constant in a link")
+                v = float(np.asarray(v).reshape(-1)[0])
+            if not isinstance(v, (int, float, np.floating, np.integer)):
+                raise UnsupportedModelError("scalar-DAG family: constant %r in a link" % (v,))
+            return P.const(v)
+        if isinstance(e, Call) and not e.kwargs:
+            if e.name in _DAG_BINARY and len(e.args) == 2:
+                return P.emit(_DAG_BINARY[e.name], a=self.compile(e.args[0], value_of), b=self.compile(e.args[1], value_of))
+            if e.name == "pow" and len(e.args) == 2:
+                ex = e.args[1].value if isinstance(e.args[1], Const) else e.args[1]
+                if isinstance(ex, (int, float, np.floating, np.integer)):
+                    return P.emit("POWI", a=self.compile(e.args[0], value_of), imm=float(ex))
+            if e.name in _DAG_UNARY and len(e.args) == 1:
+                return P.emit(_DAG_UNARY[e.name], a=self.compile(e.args[0], value_of))
+        raise UnsupportedModelError("scalar-DAG family: link expression %s is not lowered" % getattr(e, "name", type(e).__name__))
+
+    def log_prob(self, kind, x, loc, scale):
+        """The op sequence torch evaluates: Normal.log_prob, and TransformedDistribution.log_prob =
+        base.log_prob(T^-1(y)) - log|det J| for ExpTransform / SigmoidTransform (distributions.py:493-507 pattern)."""
+        P = self.prog
+        if kind == "normal":
+            return P.emit("NORMAL_LP", a=x, b=loc, c=scale)
+        if kind == "lognormal":
+            lx = P.emit("LOG", a=x)                                   # ExpTransform: inv = log y, log|det J| = x
+            return P.emit("SUB", a=P.emit("NORMAL_LP", a=lx, b=loc, c=scale), b=lx)
+        yc = P.emit("CLAMP_UNIT", a=x)                                # SigmoidTransform._inverse: clamp, log y - log1p(-y)
+        u = P.emit("SUB", a=P.emit("LOG", a=yc), b=P.emit("LOG1P", a=P.emit("NEG", a=yc)))
+        ladj = P.emit("SUB", a=P.emit("NEG", a=P.emit("SOFTPLUS", a=P.emit("NEG", a=u))), b=P.emit("SOFTPLUS", a=u))
+        return P.emit("SUB", a=P.emit("NORMAL_LP", a=u, b=loc, c=scale), b=ladj)
+
+    # -- evaluation --------------------------------------------------------------------------------
+    def elbo(self, number_samples, empirical_samples):
+        if config.device.type != "cuda":
+            raise RuntimeError("brancher_b200 evaluates the ELBO only on CUDA devices (no CPU fallback); "
+                               "config.device is %s" % config.device)
+        from brancher_b200 import _cuda as cu
+        cu.lib()
+        P = self.prog
+        s0, S_local = distributed.shard(number_samples)
+        r = cu.sample_range(number_samples, s0=s0, s_local=S_local, seed=config.seed, offset=config.next_offset())
+        params = list(P.params)
+
+        def runner():
+            dev = config.device
+            if self._ops_dev is None or self._ops_dev.device != dev:
+                self._ops_dev = torch.from_numpy(P.table().view(np.uint8)).to(dev)
+            cols = []
+            for var, rows in zip(P.columns, P.col_rows):
+                t = empirical_samples[var] if var in empirical_samples else _observed_tensor(var)
+                t = t.reshape(-1).to(torch.float32)
+                if t.numel() != rows:
+                    raise ValueError("observed %r now has %d rows, the lowered plan expects %d" % (var.name, t.numel(), rows))
+                cols.append(t.expand(self.n_rows) if rows == 1 else t)
+            data = torch.stack(cols, dim=1).contiguous() if cols else None
+            eps = None
+            if _INJECTED is not None:
+                missing = [n for n in P.eps_names if n not in _INJECTED]
+                if missing:
+                    raise KeyError("inject_noise: no noise given for q variables %s" % missing)
+                eps = torch.stack([torch.as_tensor(_INJECTED[n], dtype=torch.float32, device=dev).reshape(-1)[s0:s0 + S_local]
+                                   for n in P.eps_names], dim=1).contiguous()
+            pvec = torch.stack([p.detach().reshape(()) for p in params]) if params else torch.zeros(0, device=dev)
+            loss, g = cu.dag_elbo_fwd_bwd(self._ops_dev, len(P.ops), P.n_slots, pvec, data, self.n_rows, eps, len(P.eps_names), r)
+            loss, grads = distributed.all_reduce_partials(loss, [g])
+            g = grads[0]
+            return loss, [g[i].reshape(p.shape) if p.requires_grad else None for i, p in enumerate(params)]
+
+        return _FusedELBO.apply(runner, *params)
+
+
+def lower(joint, posterior):
+    """Pick the kernel family: the dense families (K2 linear, K3 BNN) by pattern, else the scalar-DAG family (K1)."""
+    try:
+        return _lower_dense(joint, posterior)
+    except UnsupportedModelError as dense_err:
+        try:
+            return DagPlan(joint, posterior)
+        except UnsupportedModelError as dag_err:
+            raise UnsupportedModelError("model graph is not recognised by any fused kernel family.\n  dense (K2/K3): %s\n"
+                                        "  scalar DAG (K1): %s" % (dense_err, dag_err)) from None
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -111,6 +111,40 @@ int brn_linear_elbo_fwd_bwd(const float* X, const void* y, int likelihood, int64
                             void* workspace, size_t workspace_bytes, int with_prior,
                             double* loss, void* stream);
 
+/* K1 -- generic scalar-DAG ELBO: fused reparameterised sampling + log-probs + reduction over samples and data rows +
+ * backward, for models whose variables are scalars (README.md:22-75 AR(1); examples/logNormal_normal.py;
+ * examples/multivariate_regression.py).  The host flattens (joint, posterior) into a straight-line SSA program;
+ * every op writes slot `dst` from slots a/b/c (or an immediate):
+ *   leaves   CONST imm | PARAM params[a] | DATA data[row, a] | EPS standard normal of noise stream a for this sample
+ *            (injected eps[s, a], or Philox(var_id = a, element 0))
+ *   math     ADD SUB MUL DIV NEG POWI(imm) EXP LOG LOG1P SIGMOID SOFTPLUS(torch threshold 20) TANH SIN COS RELU SQRT ABS
+ *            CLAMP_UNIT (torch SigmoidTransform's clamp to [tiny, 1-eps])
+ *   density  NORMAL_LP(x=a, loc=b, scale=c) = torch Normal.log_prob ; NORMAL_ENTROPY(scale=a)
+ *   reduce   ACC_SAMPLE a (latent log-prob / entropy term: once per sample) | ACC_ROW a (observed node: summed over
+ *            the data axis, variables.py:513-514)
+ *   loss += -(1/S_total) sum_{s local} [ sum ACC_SAMPLE + sum_rows ACC_ROW ] ; dparams[i] += d loss / d params[i].
+ * LogNormal / LogitNormal sampling and densities are composed from these ops exactly in the order torch's
+ * TransformedDistribution evaluates them (distributions.py:493-507 pattern).
+ * Replaces the Python graph walk of estimate_log_model_evidence (variables.py:843-870, 486-570, 718-749) and
+ * loss.backward() for this model class. */
+enum brn_dag_opcode {
+    BRN_DAG_CONST = 0, BRN_DAG_PARAM = 1, BRN_DAG_DATA = 2, BRN_DAG_EPS = 3,
+    BRN_DAG_ADD = 4, BRN_DAG_SUB = 5, BRN_DAG_MUL = 6, BRN_DAG_DIV = 7, BRN_DAG_NEG = 8, BRN_DAG_POWI = 9,
+    BRN_DAG_EXP = 10, BRN_DAG_LOG = 11, BRN_DAG_LOG1P = 12, BRN_DAG_SIGMOID = 13, BRN_DAG_SOFTPLUS = 14, BRN_DAG_TANH = 15,
+    BRN_DAG_SIN = 16, BRN_DAG_COS = 17, BRN_DAG_RELU = 18, BRN_DAG_SQRT = 19, BRN_DAG_ABS = 20, BRN_DAG_CLAMP_UNIT = 21,
+    BRN_DAG_NORMAL_LP = 22, BRN_DAG_NORMAL_ENTROPY = 23, BRN_DAG_ACC_SAMPLE = 24, BRN_DAG_ACC_ROW = 25
+};
+typedef struct brn_dag_op {
+    int32_t opcode, dst, a, b, c;
+    float   imm;
+} brn_dag_op;
+#define BRN_DAG_MAX_SLOTS 2048
+#define BRN_DAG_MAX_PARAMS 2048
+/* ops: DEVICE array [n_ops]; params/dparams [n_params]; data [n_rows, n_cols] (n_rows >= 1); eps [s_local, n_eps] or NULL */
+int brn_dag_elbo_fwd_bwd(const brn_dag_op* ops, int n_ops, int n_slots, const float* params, int n_params,
+                         const float* data, int n_cols, int n_rows, const float* eps, int n_eps,
+                         const brn_sample_range* r, float* dparams, double* loss, void* stream);
+
 /* K4 -- Stein variational gradient descent (SVGD).
  * (a) per-particle loss and gradient for (multi-class) logistic-regression particles theta [n, C*F]:
  *       loss += sum_k [ -sum_rows log-lik(theta_k) - sum log N(theta_k; prior_loc, prior_scale) ]     (prior optional)

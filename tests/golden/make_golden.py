@@ -137,6 +137,19 @@ def ar1(seed, T, S, tag="ar1_readme"):
          **flat("grad_", {n: g.reshape(()) for n, g in grads.items()}))
 
 
+def scalar_model(builder, tag, S, transforms, **kw):
+    """Scalar-DAG family (K1): every q variable is a scalar; noise injected per variable by name."""
+    model, Q, d = builder(NS, **kw)
+    eps = {q.name: torch.tensor(d["rng"].randn(S, 1, 1, 1).astype("float32")) for q in Q}
+    inject(Q, eps, transform={n: t for n, t in transforms.items()})
+    loss, grads, values = loss_and_grads(model, S)
+    extra = {k: v for k, v in d.items() if k != "rng"}
+    save(tag, loss=loss, **extra,
+         **flat("eps_", {n: e.numpy().reshape(S) for n, e in eps.items()}),
+         **flat("param_", {n: v.reshape(()) for n, v in values.items()}),
+         **flat("grad_", {n: g.reshape(()) for n, g in grads.items()}))
+
+
 def svgd(seed, n, d, tag="svgd_small"):
     """SteinVariationalGradientDescent.correct_gradient (inference.py:301-324) on n particles of dim d
     with arbitrary incoming gradients."""
@@ -178,4 +191,6 @@ if __name__ == "__main__":
     softmax_reg(5, B=24, F=6, C=3, S=8, tag="softmax_reg")
     ar1(6, T=20, S=32, tag="ar1_readme")
     svgd(7, n=7, d=5, tag="svgd_small")
+    scalar_model(zoo.lognormal_normal, "lognormal_normal", S=24, transforms={"nu": torch.exp}, seed=10, N=20)
+    scalar_model(zoo.multivariate_regression, "multivariate_regression", S=16, transforms={"nu": torch.exp}, seed=11, n=50)
     svgd_model(8, B=30, F=5, C=3, n=6, tag="svgd_softmax")

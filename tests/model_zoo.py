@@ -102,6 +102,44 @@ def svgd_softmax(ns, seed, B, F, C, n):
     return model, particles, {"X": X[:, :, 0], "y": y, "theta": theta0, "rng": rng}
 
 
+def lognormal_normal(ns, seed, N):
+    """examples/logNormal_normal.py:11-30 with synthetic observations (N rows)."""
+    rng = np.random.RandomState(seed)
+    data = (-2.0 + 1.0 * rng.randn(N, 1, 1)).astype("float32")
+    nu = ns.LogNormalVariable(0., 1., "nu")
+    mu = ns.NormalVariable(0., 10., "mu")
+    x = ns.NormalVariable(mu, nu, "x")
+    model = ns.ProbabilisticModel([x])
+    x.observe(data)
+    Qnu = ns.LogNormalVariable(0., 1., "nu", learnable=True)
+    Qmu = ns.NormalVariable(0., 1., "mu", learnable=True)
+    model.set_posterior_model(ns.ProbabilisticModel([Qmu, Qnu]))
+    return model, [Qmu, Qnu], {"x": data[:, 0, 0], "rng": rng}
+
+
+def multivariate_regression(ns, seed, n):
+    """examples/multivariate_regression.py:11-44: observed deterministic regressors, 4 Normal weights, LogNormal noise."""
+    rng = np.random.RandomState(seed)
+    x_range = np.linspace(-1., 1., n)
+    x1v, x2v = np.sin(2 * np.pi * 2 * x_range), x_range
+    x1 = ns.DeterministicVariable(x1v, name="x1", is_observed=True)
+    x2 = ns.DeterministicVariable(x2v, name="x2", is_observed=True)
+    b = ns.NormalVariable(0., 1., name="b")
+    w1 = ns.NormalVariable(0., 1., name="w1")
+    w2 = ns.NormalVariable(0., 1., name="w2")
+    w12 = ns.NormalVariable(0., 1., name="w12")
+    nu = ns.LogNormalVariable(0.2, 0.5, name="nu")
+    mean = b + w1 * x1 + w2 * x2 + w12 * x1 * x2
+    y = ns.NormalVariable(mean, nu, name="y")
+    model = ns.ProbabilisticModel([y])
+    Q = [ns.NormalVariable(0.1 * k, 1., name=nm, learnable=True) for k, nm in enumerate(["b", "w1", "w2", "w12"])]
+    Q.append(ns.LogNormalVariable(0.2, 0.5, name="nu", learnable=True))
+    model.set_posterior_model(ns.ProbabilisticModel(Q))
+    ydata = (0.3 + 0.8 * x1v - 0.5 * x2v + 0.2 * x1v * x2v + 0.4 * rng.randn(n)).astype("float32")
+    y.observe(ydata.reshape(n, 1, 1))
+    return model, Q, {"y": ydata, "x1": x1v.astype("float32"), "x2": x2v.astype("float32"), "rng": rng}
+
+
 def ar1(ns, seed, T):
     """README.md:22-75 model, y0 named 'y0' (the README reuses 'x0')."""
     rng = np.random.RandomState(seed)

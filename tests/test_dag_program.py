@@ -1,0 +1,130 @@
+"""K1 scalar-DAG family.
+CPU: the host compile (brancher_b200.lowering.DagPlan) evaluated by the numpy interpreter (oracle/dag_interp.py) must
+reproduce the live reference's loss and gradients (tests/golden/*.npz) -- this pins BOTH the compile and the interpreter.
+GPU: the same programs through brn_dag_elbo_fwd_bwd vs the goldens and vs the fp64 interpreter."""
+import numpy as np
+import pytest
+import torch
+
+import model_zoo as zoo
+from helpers import load_golden, assert_close
+
+CASES = {
+    "ar1_readme": (zoo.ar1, dict(seed=6, T=20)),
+    "lognormal_normal": (zoo.lognormal_normal, dict(seed=10, N=20)),
+    "multivariate_regression": (zoo.multivariate_regression, dict(seed=11, n=50)),
+}
+
+
+def build(tag, device):
+    from brancher_b200 import config, lowering
+    config.set_device(device)
+    ns = zoo.namespace("brancher_b200")
+    builder, kw = CASES[tag]
+    model, Q, d = builder(ns, **kw)
+    plan = lowering.get_plan(model, model.posterior_model)
+    names = {id(v._value): v.name for v in model.posterior_model.flatten()
+             if getattr(v, "learnable", False) and isinstance(getattr(v, "_value", None), torch.nn.Parameter)}
+    return ns, model, plan, names
+
+
+def interp(plan, names, g, dtype=np.float64):
+    from oracle import dag_interp
+    P = plan.prog
+    eps = np.stack([g["eps"][n] for n in P.eps_names], 1)
+    pv = np.array([g["param"][names[id(p)]].reshape(()) for p in P.params])
+    from brancher_b200.lowering import _observed_tensor
+    cols = [np.broadcast_to(_observed_tensor(c).cpu().numpy().reshape(-1), (plan.n_rows,)) for c in P.columns]
+    data = np.stack(cols, 1) if cols else None
+    loss, dp = dag_interp.run(P.ops, P.n_slots, pv, data, eps, dtype=dtype)
+    return loss, {names[id(p)]: dp[i] for i, p in enumerate(P.params)}
+
+
+@pytest.mark.parametrize("tag", sorted(CASES))
+def test_compiled_program_matches_reference_on_cpu(tag):
+    g = load_golden(tag)
+    ns, model, plan, names = build(tag, "cpu")
+    assert plan.family == "dag (K1)"
+    assert set(names.values()) == set(g["param"])            # same learnable names as the reference
+    for p in plan.prog.params:                               # same initial values (same construction script)
+        np.testing.assert_allclose(float(p.detach()), float(g["param"][names[id(p)]]), rtol=1e-6, atol=1e-7)
+    loss, grads = interp(plan, names, g)
+    assert_close(loss, g["raw"]["loss"], tag + " loss", rtol=2e-5, atol=2e-6)
+    sc = max(abs(float(v)) for v in g["grad"].values())
+    for k, v in g["grad"].items():
+        assert_close(grads[k], v.reshape(()), tag + " grad " + k, rtol=2e-5, atol=2e-6, scale=sc)
+
+
+def test_unsupported_scalar_graphs_raise():
+    from brancher_b200 import config, lowering
+    config.set_device("cpu")
+    ns = zoo.namespace("brancher_b200")
+    # local latent per data row: z_b ~ N(0,1) with an amortised q that depends on the observed rows
+    x = ns.DeterministicVariable(np.linspace(0, 1, 5), name="x", is_observed=True)
+    z = ns.NormalVariable(0., 1., "z")
+    y = ns.NormalVariable(z * x, 1., "y")
+    model = ns.ProbabilisticModel([y])
+    y.observe(np.zeros((5, 1, 1), "float32"))
+    Qz = ns.NormalVariable(ns.DeterministicVariable(0., "a", learnable=True) * x, 1., "z", learnable=True)
+    model.set_posterior_model(ns.ProbabilisticModel([Qz]))
+    with pytest.raises(lowering.UnsupportedModelError):
+        lowering.get_plan(model, model.posterior_model)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", sorted(CASES))
+def test_dag_kernel_matches_reference(tag):
+    from brancher_b200 import lowering
+    g = load_golden(tag)
+    ns, model, plan, names = build(tag, "cuda:0")
+    S = next(iter(g["eps"].values())).shape[0]
+    with lowering.inject_noise(g["eps"]):
+        loss = ns.inference.ReverseKL().compute_loss(model, model.posterior_model, None, S)
+    loss.backward()
+    l64, g64 = interp(plan, names, g)
+    assert_close(float(loss.detach()), g["raw"]["loss"], tag + " loss vs reference", rtol=2e-5, atol=2e-6)
+    assert_close(float(loss.detach()), l64, tag + " loss vs fp64 interpreter")
+    sc = max(abs(float(v)) for v in g["grad"].values())
+    for p in plan.prog.params:
+        k = names[id(p)]
+        got = float(p.grad.reshape(()))
+        assert_close(got, g["grad"][k].reshape(()), tag + " grad %s vs reference" % k, rtol=2e-5, atol=2e-6, scale=sc)
+        assert_close(got, g64[k], tag + " grad %s vs fp64 interpreter" % k, scale=sc)
+
+
+@pytest.mark.gpu
+def test_dag_philox_mode_and_shard_invariance():
+    """Philox noise: re-materialise the same eps with brn_philox_normal_fill and compare with the injected-noise run;
+    evaluate in two sample shards and check the partial sums add up."""
+    from brancher_b200 import _cuda as cu, config, lowering
+    ns, model, plan, names = build("multivariate_regression", "cuda:0")
+    P, S, dev = plan.prog, 37, torch.device("cuda:0")
+    ops = torch.from_numpy(P.table().view(np.uint8)).to(dev)
+    pvec = torch.stack([p.detach().reshape(()) for p in P.params])
+    data = torch.stack([lowering._observed_tensor(c).reshape(-1).float().expand(plan.n_rows) for c in P.columns], 1).contiguous()
+    r = cu.sample_range(S, seed=11, offset=3)
+    loss, gr = cu.dag_elbo_fwd_bwd(ops, len(P.ops), P.n_slots, pvec, data, plan.n_rows, None, len(P.eps_names), r)
+    eps = torch.cat([cu.philox_normal(1, k, r, dev) for k in range(len(P.eps_names))], 1).contiguous()
+    loss2, gr2 = cu.dag_elbo_fwd_bwd(ops, len(P.ops), P.n_slots, pvec, data, plan.n_rows, eps, len(P.eps_names), r)
+    assert_close(loss.item(), loss2.item(), "philox vs injected loss", rtol=1e-6, atol=1e-6)
+    assert_close(gr.cpu().numpy(), gr2.cpu().numpy(), "philox vs injected grads", rtol=1e-6, atol=1e-6, scale=float(gr2.abs().max()))
+    lsum, gsum = torch.zeros(1, dtype=torch.float64, device=dev), torch.zeros_like(gr)
+    for s0, n in [(0, 20), (20, 17)]:
+        rr = cu.sample_range(S, s0=s0, s_local=n, seed=11, offset=3)
+        l, g_ = cu.dag_elbo_fwd_bwd(ops, len(P.ops), P.n_slots, pvec, data, plan.n_rows, None, len(P.eps_names), rr)
+        lsum += l; gsum += g_
+    assert_close(lsum.item(), loss.item(), "sharded loss", rtol=1e-6, atol=1e-6)
+    assert_close(gsum.cpu().numpy(), gr.cpu().numpy(), "sharded grads", rtol=1e-5, atol=1e-6, scale=float(gr.abs().max()))
+
+
+@pytest.mark.gpu
+def test_ar1_perform_inference_readme_config():
+    """BASELINE config C1: README AR(1), T=20, 300 MC samples, SGD -- loss must decrease."""
+    from brancher_b200 import config
+    config.set_device("cuda:0")
+    ns = zoo.namespace("brancher_b200")
+    model, Q, d = zoo.ar1(ns, 6, 20)
+    ns.inference.perform_inference(model, number_iterations=60, number_samples=300, optimizer="SGD", lr=0.001)
+    curve = model.diagnostics["loss curve"]
+    assert curve.shape == (60,) and np.isfinite(curve).all()
+    assert curve[-10:].mean() < curve[:10].mean()
