@@ -201,8 +201,8 @@ sample_w1_fused_kernel(const float* __restrict__ mu, const float* __restrict__ s
         } else {
             Normal4 n = philox_normal4(r.seed, r.offset, var_id, (uint32_t)(r.s0 + s), (uint32_t)(i >> 2));
             e = make_float4(n.v[0], n.v[1], n.v[2], n.v[3]);
-            *reinterpret_cast<float4*>(eps_out + (int64_t)s * lde_out + i) = e;
         }
+        *reinterpret_cast<float4*>(eps_out + (int64_t)s * lde_out + i) = e;     // stage 5 reads all noise from the workspace
         const float4 m = *reinterpret_cast<const float4*>(mu + i);
         const float4 sg = *reinterpret_cast<const float4*>(sigma + i);
         umma::split_tf32(__fmaf_rn(sg.x, e.x, m.x), vh.x, vl.x);
@@ -644,6 +644,7 @@ static size_t bnn_mid_smem(int R, int H, int C) {
 }
 
 constexpr int BNN_UMMA_HP = 104;     // padded hidden width of the instantiated tcgen05 variant (multiple of 8)
+constexpr int BNN_UMMA_BK = 16;      // K chunk: 16 floats (64-byte swizzle), 5-stage TMA ring
 constexpr int BNN_UMMA_NSAMP = 2;    // samples per MMA N tile (N = 208)
 
 struct BnnWorkspace {
@@ -723,49 +724,38 @@ extern "C" int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int
     int drain = 2;
     if (const char* env = getenv("BRN_UMMA_DRAIN")) drain = atoi(env);
 
-    // 1. noise + weights
-    const float* eps_ptr[4];
-    int64_t eps_ld[4];
+    // 1. noise + weights.  All noise (injected or Philox) ends up in ws.eps [S][ldw] and all sampled weights in ws.W,
+    //    the four variables back to back inside a row, so stage 5 is one launch over the concatenated range.
     {
         StageTimer st("bnn.sample_weights", stream);
-        for (int v = 0; v < 4; ++v) {
-            if (vars[v].eps) {
-                eps_ptr[v] = vars[v].eps;
-                eps_ld[v] = numels[v];
+        if (use_tc) {
+            const bool fast = (P % 4 == 0) && ((uintptr_t)vars[0].mu % 16 == 0) &&
+                              (!vars[0].eps || ((uintptr_t)vars[0].eps % 16 == 0));
+            if (fast) {
+                softplus_kernel<<<(unsigned)((numels[0] + 255) / 256), 256, 0, stream>>>(vars[0].rho, ws.sigma, numels[0]);
+                BRN_LAUNCH_OK("softplus_kernel");
+                dim3 grid((unsigned)(((int64_t)H * P / 4 + 255) / 256), S);
+                sample_w1_fused_kernel<<<grid, 256, 0, stream>>>(vars[0].mu, ws.sigma, vars[0].eps, numels[0], ws.eps + offs[0],
+                                                                 L.ldw, ws.Wh, ws.Wl, H, P, HP, ws.ldP, *r, vars[0].var_id);
+                BRN_LAUNCH_OK("sample_w1_fused_kernel");
             } else {
-                if (!(use_tc && v == 0))      // layer-1 noise of the tcgen05 variant is generated by the fused sampler
-                    if (int e = launch_philox_fill(ws.eps + offs[v], L.ldw, numels[v], vars[v].var_id, *r, stream)) return e;
-                eps_ptr[v] = ws.eps + offs[v];
-                eps_ld[v] = L.ldw;
+                if (vars[0].eps)
+                    BRN_CUDA_OK(cudaMemcpy2DAsync(ws.eps + offs[0], L.ldw * sizeof(float), vars[0].eps, numels[0] * sizeof(float),
+                                                  numels[0] * sizeof(float), S, cudaMemcpyDeviceToDevice, stream));
+                else if (int e = launch_philox_fill(ws.eps + offs[0], L.ldw, numels[0], vars[0].var_id, *r, stream)) return e;
+                dim3 grid((P + 255) / 256, HP, S);
+                sample_w1_split_kernel<<<grid, 256, 0, stream>>>(vars[0].mu, vars[0].rho, ws.eps + offs[0], L.ldw, ws.Wh, ws.Wl, H, P,
+                                                                 HP, ws.ldP);
+                BRN_LAUNCH_OK("sample_w1_split_kernel");
             }
-            if (use_tc && v == 0) {
-                const bool fast = (P % 4 == 0) && ((uintptr_t)vars[0].mu % 16 == 0) &&
-                                  (!vars[0].eps || ((uintptr_t)vars[0].eps % 16 == 0));
-                if (fast) {
-                    softplus_kernel<<<(unsigned)((numels[0] + 255) / 256), 256, 0, stream>>>(vars[0].rho, ws.sigma, numels[0]);
-                    BRN_LAUNCH_OK("softplus_kernel");
-                    dim3 grid((unsigned)(((int64_t)H * P / 4 + 255) / 256), S);
-                    sample_w1_fused_kernel<<<grid, 256, 0, stream>>>(vars[0].mu, ws.sigma, vars[0].eps, numels[0], ws.eps + offs[0],
-                                                                     L.ldw, ws.Wh, ws.Wl, H, P, HP, ws.ldP, *r, vars[0].var_id);
-                    BRN_LAUNCH_OK("sample_w1_fused_kernel");
-                } else {
-                    if (!vars[0].eps)
-                        if (int e = launch_philox_fill(ws.eps + offs[0], L.ldw, numels[0], vars[0].var_id, *r, stream)) return e;
-                    dim3 grid((P + 255) / 256, HP, S);
-                    sample_w1_split_kernel<<<grid, 256, 0, stream>>>(vars[0].mu, vars[0].rho, eps_ptr[0], eps_ld[0], ws.Wh, ws.Wl,
-                                                                     H, P, HP, ws.ldP);
-                    BRN_LAUNCH_OK("sample_w1_split_kernel");
-                }
-                if (S % NS) {   // the odd tail tile reads one more (all-zero) sample block
-                    BRN_CUDA_OK(cudaMemsetAsync(ws.Wh + (size_t)S * HP * ws.ldP, 0, sizeof(float) * HP * ws.ldP, stream));
-                    BRN_CUDA_OK(cudaMemsetAsync(ws.Wl + (size_t)S * HP * ws.ldP, 0, sizeof(float) * HP * ws.ldP, stream));
-                }
-                if (int e = launch_split_tf32(X, P, B, P, ws.Xh, ws.Xl, ws.ldP, ws.Xth, ws.Xtl, ws.ldB, stream)) return e;
-                continue;
+            if (S % NS) {   // the odd tail tile reads one more sample block: keep it finite
+                BRN_CUDA_OK(cudaMemsetAsync(ws.Wh + (size_t)S * HP * ws.ldP, 0, sizeof(float) * HP * ws.ldP, stream));
+                BRN_CUDA_OK(cudaMemsetAsync(ws.Wl + (size_t)S * HP * ws.ldP, 0, sizeof(float) * HP * ws.ldP, stream));
             }
-            if (int e = launch_sample_weights(vars[v].mu, vars[v].rho, eps_ptr[v], eps_ld[v], ws.W + offs[v], L.ldw,
-                                              numels[v], S, stream))
-                return e;
+            if (int e = launch_split_tf32(X, P, B, P, ws.Xh, ws.Xl, ws.ldP, ws.Xth, ws.Xtl, ws.ldB, stream)) return e;
+            if (int e = launch_sample_multi(vars + 1, offs + 1, 3, ws.eps, ws.W, L.ldw, *r, stream)) return e;
+        } else {
+            if (int e = launch_sample_multi(vars, offs, 4, ws.eps, ws.W, L.ldw, *r, stream)) return e;
         }
     }
     // 2. pre_s = X . W1_s^T
@@ -775,7 +765,7 @@ extern "C" int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int
             EpiStore::Params ep;      // pre^T: [S][H][B], coalesced across the warp's rows b
             ep.out = ws.pre; ep.rows = B; ep.row_stride = 1; ep.col_stride = B; ep.blk_stride = (int64_t)B * H;
             ep.blk_valid = H; ep.col_limit = 0; ep.total_blks = S;
-            if (int e = launch_umma_nt<BN, EpiStore>(ws.Xh, ws.Xl, B, ws.ldP, ws.Wh, ws.Wl, S * HP, ws.ldP, P, 0, drain, ep,
+            if (int e = launch_umma_nt<BN, BNN_UMMA_BK, EpiStore>(ws.Xh, ws.Xl, B, ws.ldP, ws.Wh, ws.Wl, S * HP, ws.ldP, P, 0, drain, ep,
                                                      stream))
                 return e;
         } else {
@@ -827,7 +817,7 @@ extern "C" int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int
             EpiStore::Params ep;      // dW1_s[h][p] = D[p, (s, h)]
             ep.out = ws.dW + L.oW1; ep.rows = P; ep.row_stride = 1; ep.col_stride = P; ep.blk_stride = L.ldw;
             ep.blk_valid = H; ep.col_limit = 0; ep.total_blks = S;
-            if (int e = launch_umma_nt<BN, EpiStore>(ws.Xth, ws.Xtl, P, ws.ldB, ws.dph, ws.dpl, S * HP, ws.ldB, B, 0, drain, ep,
+            if (int e = launch_umma_nt<BN, BNN_UMMA_BK, EpiStore>(ws.Xth, ws.Xtl, P, ws.ldB, ws.dph, ws.dpl, S * HP, ws.ldB, B, 0, drain, ep,
                                                      stream))
                 return e;
         } else {
@@ -836,11 +826,10 @@ extern "C" int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int
                 return e;
         }
     }
-    // 5. reduce over samples + prior/entropy + chain rule
+    // 5. reduce over samples + prior/entropy + chain rule: one stats launch + one finalize launch for all four variables
     StageTimer st5("bnn.reduce_finalize", stream);
-    for (int v = 0; v < 4; ++v)
-        if (int e = launch_mf_reduce_finalize(vars[v], eps_ptr[v], eps_ld[v], ws.dW + offs[v], L.ldw, ws.stats, *r, with_prior,
-                                              loss, stream))
-            return e;
+    if (int e = launch_mf_reduce_finalize_multi(vars, offs, 4, L.numel, ws.eps, L.ldw, ws.dW, L.ldw, ws.stats, *r, with_prior, loss,
+                                                stream))
+        return e;
     return 0;
 }

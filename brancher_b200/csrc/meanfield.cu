@@ -175,6 +175,7 @@ mf_stats_kernel(const float* __restrict__ eps, int64_t lde, const float* __restr
     if (q * 4 >= numel) return;
     const int s_begin = blockIdx.y * MF_SCHUNK, s_end = min(r.s_local, s_begin + MF_SCHUNK);
     const int nvalid = (int)min((int64_t)4, numel - q * 4);
+    vec = vec && nvalid == 4;          // `vec` = pitches/bases allow float4; the ragged last quad goes scalar
     float gw[4] = {0.f, 0.f, 0.f, 0.f}, gwe[4] = {0.f, 0.f, 0.f, 0.f}, e1[4] = {0.f, 0.f, 0.f, 0.f}, e2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
     for (int s = s_begin; s < s_end; ++s) {
@@ -265,13 +266,142 @@ int launch_mf_reduce_finalize(const brn_mf_var& var, const float* eps, int64_t l
     if (r.s_local > 0) {
         const int64_t quads = npad / 4;
         const int vec = (!eps || (((uintptr_t)eps % 16 == 0) && lde % 4 == 0)) &&
-                        (!dW || (((uintptr_t)dW % 16 == 0) && ldd % 4 == 0)) && (var.numel % 4 == 0);
+                        (!dW || (((uintptr_t)dW % 16 == 0) && ldd % 4 == 0));
         dim3 grid((unsigned)((quads + 127) / 128), (unsigned)((r.s_local + MF_SCHUNK - 1) / MF_SCHUNK));
         mf_stats_kernel<<<grid, 128, 0, stream>>>(eps, lde, dW, ldd, var.numel, npad, r, var.var_id, vec, stats);
         BRN_LAUNCH_OK("mf_stats_kernel");
     }
     mf_finalize2_kernel<<<(unsigned)((var.numel + 255) / 256), 256, 0, stream>>>(var, stats, npad, r, with_prior, loss);
     BRN_LAUNCH_OK("mf_finalize2_kernel");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage 5 for several variables laid out back to back in one [S][ld] block (the BNN workspace): ONE stats launch
+// over the concatenated element range and ONE finalize launch that looks the variable up per element.
+// ---------------------------------------------------------------------------------------------
+struct MfMulti {
+    brn_mf_var v[4];
+    int64_t off[4];
+    int n;
+};
+
+__global__ void __launch_bounds__(256)
+mf_finalize_multi_kernel(MfMulti m, const float* __restrict__ stats, int64_t npad, int64_t total, brn_sample_range r,
+                         int with_prior, double* __restrict__ loss) {
+    __shared__ double red[32];
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double elbo_thread = 0.0;
+    if (g < total) {
+        int k = 0;
+#pragma unroll
+        for (int j = 1; j < 4; ++j)
+            if (j < m.n && g >= m.off[j]) k = j;
+        const brn_mf_var& v = m.v[k];
+        const int64_t i = g - m.off[k];
+        if (i < v.numel) {
+            const float mu = v.mu[i], rho = v.rho[i], sg = softplusf(rho);
+            const float gw = stats[g], gwe = stats[npad + g], e1 = stats[2 * npad + g], e2 = stats[3 * npad + g];
+            const float inv_S = 1.0f / (float)r.s_total, n = (float)r.s_local, frac = n * inv_S;
+            float dE_dmu = gw * inv_S, dE_dsg = gwe * inv_S;
+            if (with_prior) {
+                const float log_sg = logf(sg);
+                const float entropy = 0.5f + BRN_HALF_LOG_2PI + log_sg;
+                if (v.tied) {
+                    elbo_thread = (double)(-0.5f * e2 * inv_S) + (double)(frac * (entropy - log_sg - BRN_HALF_LOG_2PI));
+                } else {
+                    const float a = v.prior_loc[i], b = v.prior_scale[i], inv_b2 = 1.0f / (b * b);
+                    const float c0 = mu - a;
+                    const float sd2 = n * c0 * c0 + 2.f * c0 * sg * e1 + sg * sg * e2;
+                    const float sd = n * c0 + sg * e1;
+                    const float sde = c0 * e1 + sg * e2;
+                    elbo_thread = (double)(-0.5f * sd2 * inv_b2 * inv_S) + (double)(frac * (entropy - logf(b) - BRN_HALF_LOG_2PI));
+                    dE_dmu += -sd * inv_b2 * inv_S;
+                    dE_dsg += -sde * inv_b2 * inv_S + frac / sg;
+                }
+            }
+            v.dmu[i] += -dE_dmu;
+            v.drho[i] += -dE_dsg * sigmoidf(rho);
+        }
+    }
+    double tot = block_sum<double>(elbo_thread, red);
+    if (threadIdx.x == 0 && with_prior) atomicAdd(loss, -tot);
+}
+
+int launch_mf_reduce_finalize_multi(const brn_mf_var* vars, const int64_t* offs, int nvars, int64_t total, const float* eps,
+                                    int64_t lde, const float* dW, int64_t ldd, float* stats, const brn_sample_range& r,
+                                    int with_prior, double* loss, cudaStream_t stream) {
+    if (nvars <= 0 || nvars > 4 || total <= 0) { set_error("launch_mf_reduce_finalize_multi: bad variable count %d", nvars); return -1; }
+    const int64_t npad = (total + 3) / 4 * 4;
+    BRN_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(float) * 4 * npad, stream));
+    if (r.s_local > 0) {
+        const int64_t quads = npad / 4;
+        const int vec = (((uintptr_t)eps % 16 == 0) && lde % 4 == 0) && (!dW || (((uintptr_t)dW % 16 == 0) && ldd % 4 == 0));
+        dim3 grid((unsigned)((quads + 127) / 128), (unsigned)((r.s_local + MF_SCHUNK - 1) / MF_SCHUNK));
+        mf_stats_kernel<<<grid, 128, 0, stream>>>(eps, lde, dW, ldd, total, npad, r, 0u, vec, stats);
+        BRN_LAUNCH_OK("mf_stats_kernel");
+    }
+    MfMulti m;
+    m.n = nvars;
+    for (int k = 0; k < 4; ++k) {
+        m.v[k] = vars[k < nvars ? k : nvars - 1];
+        m.off[k] = offs[k < nvars ? k : nvars - 1];
+    }
+    mf_finalize_multi_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(m, stats, npad, total, r, with_prior, loss);
+    BRN_LAUNCH_OK("mf_finalize_multi_kernel");
+    return 0;
+}
+
+// several small variables sampled in one launch: eps (injected or Philox) -> eps_out[s*ld + off_k + i] and
+// W[s*ld + off_k + i] = mu + softplus(rho) * eps
+struct SampleMulti {
+    const float* mu[4]; const float* rho[4]; const float* eps_in[4];
+    int64_t off[4], numel[4];
+    uint32_t var_id[4];
+    int n;
+};
+
+__global__ void __launch_bounds__(256)
+sample_multi_kernel(SampleMulti m, int64_t total, float* __restrict__ eps_out, float* __restrict__ W, int64_t ld,
+                    brn_sample_range r) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.y;
+    if (g >= total) return;
+    int k = 0;
+    int64_t base = 0;
+    bool found = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (!found && j < m.n) {
+            if (g < base + m.numel[j]) { k = j; found = true; }
+            else base += m.numel[j];
+        }
+    }
+    if (!found) return;
+    const int64_t i = g - base;
+    const float e = m.eps_in[k] ? m.eps_in[k][(int64_t)s * m.numel[k] + i]
+                                : philox_normal1(r.seed, r.offset, m.var_id[k], (uint32_t)(r.s0 + s), i);
+    const int64_t o = (int64_t)s * ld + m.off[k] + i;
+    eps_out[o] = e;
+    W[o] = __fmaf_rn(softplusf(m.rho[k][i]), e, m.mu[k][i]);
+}
+
+int launch_sample_multi(const brn_mf_var* vars, const int64_t* offs, int nvars, float* eps_out, float* W, int64_t ld,
+                        const brn_sample_range& r, cudaStream_t stream) {
+    if (nvars <= 0 || nvars > 4) { set_error("launch_sample_multi: bad variable count %d", nvars); return -1; }
+    SampleMulti m;
+    m.n = nvars;
+    int64_t total = 0;
+    for (int k = 0; k < 4; ++k) {
+        const int kk = k < nvars ? k : nvars - 1;
+        m.mu[k] = vars[kk].mu; m.rho[k] = vars[kk].rho; m.eps_in[k] = vars[kk].eps;
+        m.off[k] = offs[kk]; m.numel[k] = vars[kk].numel; m.var_id[k] = vars[kk].var_id;
+        if (k < nvars) total += vars[k].numel;
+    }
+    if (total <= 0 || r.s_local <= 0) return 0;
+    dim3 grid((unsigned)((total + 255) / 256), (unsigned)r.s_local);
+    sample_multi_kernel<<<grid, 256, 0, stream>>>(m, total, eps_out, W, ld, r);
+    BRN_LAUNCH_OK("sample_multi_kernel");
     return 0;
 }
 

@@ -28,4 +28,14 @@ int launch_reduce_over_samples(const float* dW, int64_t ld, const float* eps, in
 int launch_mf_reduce_finalize(const brn_mf_var& var, const float* eps, int64_t lde, const float* dW, int64_t ldd,
                               float* stats, const brn_sample_range& r, int with_prior, double* loss, cudaStream_t stream);
 
+// The same for up to 4 variables stored back to back inside one [S][ld] block (`offs` = element offset of each
+// variable inside a row, `total` = end of the last one): one stats launch + one finalize launch.
+int launch_mf_reduce_finalize_multi(const brn_mf_var* vars, const int64_t* offs, int nvars, int64_t total, const float* eps,
+                                    int64_t lde, const float* dW, int64_t ldd, float* stats, const brn_sample_range& r,
+                                    int with_prior, double* loss, cudaStream_t stream);
+
+// eps (injected var.eps or Philox) -> eps_out[s*ld + offs[k] + i], W[...] = mu + softplus(rho)*eps for up to 4 variables
+int launch_sample_multi(const brn_mf_var* vars, const int64_t* offs, int nvars, float* eps_out, float* W, int64_t ld,
+                        const brn_sample_range& r, cudaStream_t stream);
+
 }  // namespace brn

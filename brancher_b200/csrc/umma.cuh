@@ -78,15 +78,20 @@ __device__ __forceinline__ void tc_fence_after() {
 // Shared-memory matrix descriptor, K-major operand, SWIZZLE_128B: rows of 128 B (32 tf32), 8-row atoms
 // of 1024 B (SBO), 16-byte chunks XOR-swizzled by (row % 8) -- exactly what a TMA box of inner extent
 // 128 B with CU_TENSOR_MAP_SWIZZLE_128B writes.  `addr` = tile base (1024-B aligned) + k byte offset.
-__device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t addr) {
+// SW = swizzle span in bytes = bytes of one K-chunk row: 128 (32 tf32, SWIZZLE_128B, layout code 2) or 64 (16 tf32,
+// SWIZZLE_64B, layout code 4); 8-row atoms of 8*SW bytes (SBO).
+template <int SW>
+__device__ __forceinline__ uint64_t smem_desc_k(uint32_t addr) {
+    static_assert(SW == 128 || SW == 64, "unsupported swizzle span");
     uint64_t d = 0;
     d |= (uint64_t)((addr & 0x3FFFFu) >> 4);          // start address           bits [0,14)
     d |= (uint64_t)1 << 16;                           // LBO (unused, 16 B)      bits [16,30)
-    d |= (uint64_t)(1024u >> 4) << 32;                // SBO = 1024 B            bits [32,46)
+    d |= (uint64_t)((8u * SW) >> 4) << 32;            // SBO = 8 rows            bits [32,46)
     d |= (uint64_t)1 << 46;                           // descriptor version 1    bits [46,48)
-    d |= (uint64_t)2 << 61;                           // SWIZZLE_128B            bits [61,64)
+    d |= (uint64_t)(SW == 128 ? 2 : 4) << 61;         // SWIZZLE_128B / _64B     bits [61,64)
     return d;
 }
+__device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t addr) { return smem_desc_k<128>(addr); }
 
 // Instruction descriptor for kind::tf32, fp32 accumulate, K-major A and B, dense.
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
@@ -166,7 +171,8 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 }  // namespace umma
 
 // Host: encode a 2-D fp32 row-major tensor [rows][cols] (row stride ld elements) for TMA tiles of
-// box_rows x 32 floats with 128-byte swizzle and zero OOB fill.  Returns 0 on success.
-int make_tmap_2d_f32(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+// box_rows x box_cols floats (box_cols = 32: 128-byte swizzle, 16: 64-byte swizzle) with zero OOB fill.
+int make_tmap_2d_f32(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                     uint32_t box_cols);
 
 }  // namespace brn

@@ -20,7 +20,8 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
     return fn;
 }
 
-int make_tmap_2d_f32(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+int make_tmap_2d_f32(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                     uint32_t box_cols) {
     auto fn = get_encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return -4; }
     if (((uintptr_t)base & 15) || (ld * sizeof(float)) % 16) {
@@ -30,10 +31,12 @@ int make_tmap_2d_f32(CUtensorMap* out, const float* base, uint64_t rows, uint64_
     }
     cuuint64_t gdim[2] = {cols, rows};
     cuuint64_t gstr[1] = {ld * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)UG_BK, box_rows};
+    if (box_cols != 32 && box_cols != 16) { set_error("TMA box must be 32 or 16 floats wide (got %u)", box_cols); return -1; }
+    cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu ld=%llu box=%u)",
                                        (int)r, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
@@ -109,5 +112,7 @@ extern "C" int brn_gemm_nt_3xtf32(const float* A, const float* B, float* D, int 
     set_variant("tcgen05");
     int drain = 2;
     if (const char* env = getenv("BRN_UMMA_DRAIN")) drain = atoi(env);
-    return launch_umma_nt<224, EpiStore>(Ah, Al, M, ld, Bh, Bl, N, ld, K, 0, drain, ep, stream);
+    if (const char* env = getenv("BRN_UMMA_BK"))
+        if (atoi(env) == 32) return launch_umma_nt<224, 32, EpiStore>(Ah, Al, M, ld, Bh, Bl, N, ld, K, 0, drain, ep, stream);
+    return launch_umma_nt<224, 16, EpiStore>(Ah, Al, M, ld, Bh, Bl, N, ld, K, 0, drain, ep, stream);
 }

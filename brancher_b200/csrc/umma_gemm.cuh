@@ -18,17 +18,20 @@
 namespace brn {
 
 constexpr int UG_BM = 128;        // rows of A per tile (TMEM lanes)
-constexpr int UG_BK = 32;         // fp32 elements per K chunk = 128 B = one swizzle row
-constexpr int UG_STAGES = 2;
+// BK = fp32 elements per K chunk = one swizzle row: 32 (128 B, 2-stage ring) or 16 (64 B swizzle, 5-stage ring).  The
+// finer chunk keeps 4 loads in flight while one is consumed: the 2-stage ring left the tensor pipe idle ~35 % of the
+// time waiting for the next 86 KB stage (ncu: profiles/r1a_*), the 5-stage ring hides that latency.
 constexpr int UG_BUF_COLS = 256;  // TMEM column stride between the two accumulator buffers
 constexpr int UG_EPI_WARPS = 8;   // epilogue warps: 4 TMEM lane quarters x 2 column halves
 
-template <int BN>
+template <int BN, int BK>
 struct UmmaSmem {
-    static constexpr int A_BYTES = UG_BM * UG_BK * 4;       // 16 KB
-    static constexpr int B_BYTES = BN * UG_BK * 4;
+    static constexpr int A_BYTES = UG_BM * BK * 4;
+    static constexpr int B_BYTES = BN * BK * 4;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    static constexpr int TOTAL = UG_STAGES * STAGE_BYTES + 1024;   // + alignment slack
+    static constexpr int STAGES = BK == 32 ? 2 : (5 * STAGE_BYTES + 1024 <= 227 * 1024 ? 5 : 4);
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024;   // + alignment slack
+    static_assert(A_BYTES % (8 * BK * 4) == 0 && B_BYTES % (8 * BK * 4) == 0, "tiles must be whole swizzle atoms");
 };
 
 // which (m-tile, n-tile) units a CTA processes, identically enumerated by every warp role
@@ -50,12 +53,13 @@ struct UnitIter {
     __device__ int nt() const { return mode == 0 ? u / m_tiles : u; }
 };
 
-template <int BN, class Epi>
+template <int BN, int BK, class Epi>
 __global__ void __launch_bounds__(64 + 32 * UG_EPI_WARPS, 1)
 umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                       const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                       int m_tiles, int n_tiles, int k_chunks, int drain_chunks, int mode, typename Epi::Params ep) {
-    using SM = UmmaSmem<BN>;
+    using SM = UmmaSmem<BN, BK>;
+    constexpr int UG_STAGES = SM::STAGES, UG_BK = BK, SW = BK * 4;
     constexpr int CPT = BN / 2;                    // accumulator columns per epilogue thread
     static_assert(BN <= UG_BUF_COLS && BN % 16 == 0 && CPT % 8 == 0, "unsupported N tile");
     constexpr uint32_t TMEM_COLS = 512;
@@ -118,8 +122,8 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
 #pragma unroll
                         for (int ks = 0; ks < UG_BK / 8; ++ks) {
                             const uint32_t ko = ks * 32;           // 8 tf32 = 32 bytes along K inside the swizzle row
-                            const uint64_t dah = umma::smem_desc_k_sw128(ah + ko), dal = umma::smem_desc_k_sw128(al + ko);
-                            const uint64_t dbh = umma::smem_desc_k_sw128(bh + ko), dbl = umma::smem_desc_k_sw128(bl + ko);
+                            const uint64_t dah = umma::smem_desc_k<SW>(ah + ko), dal = umma::smem_desc_k<SW>(al + ko);
+                            const uint64_t dbh = umma::smem_desc_k<SW>(bh + ko), dbl = umma::smem_desc_k<SW>(bl + ko);
                             umma::mma_tf32_ss(d_tmem, dal, dbh, idesc, kc != kc0 || ks != 0);
                             umma::mma_tf32_ss(d_tmem, dah, dbl, idesc, true);
                             umma::mma_tf32_ss(d_tmem, dah, dbh, idesc, true);
@@ -214,16 +218,17 @@ int launch_split_tf32(const float* src, int64_t lds, int rows, int cols, float* 
 
 // A (hi/lo) [M][K] pitch lda, B (hi/lo) [N][K] pitch ldb; mode 0: units n-major round-robin over CTAs,
 // mode 1: every CTA keeps one m-tile and strides over n-tiles.
-template <int BN, class Epi>
+template <int BN, int BK, class Epi>
 inline int launch_umma_nt(const float* Ah, const float* Al, int M, int64_t lda, const float* Bh, const float* Bl, int N,
                           int64_t ldb, int K, int mode, int drain_chunks, const typename Epi::Params& ep,
                           cudaStream_t stream) {
     CUtensorMap tAh, tAl, tBh, tBl;
-    if (int e = make_tmap_2d_f32(&tAh, Ah, M, K, lda, UG_BM)) return e;
-    if (int e = make_tmap_2d_f32(&tAl, Al, M, K, lda, UG_BM)) return e;
-    if (int e = make_tmap_2d_f32(&tBh, Bh, N, K, ldb, BN)) return e;
-    if (int e = make_tmap_2d_f32(&tBl, Bl, N, K, ldb, BN)) return e;
-    const int m_tiles = (M + UG_BM - 1) / UG_BM, n_tiles = (N + BN - 1) / BN, k_chunks = (K + UG_BK - 1) / UG_BK;
+    if (int e = make_tmap_2d_f32(&tAh, Ah, M, K, lda, UG_BM, BK)) return e;
+    if (int e = make_tmap_2d_f32(&tAl, Al, M, K, lda, UG_BM, BK)) return e;
+    if (int e = make_tmap_2d_f32(&tBh, Bh, N, K, ldb, BN, BK)) return e;
+    if (int e = make_tmap_2d_f32(&tBl, Bl, N, K, ldb, BN, BK)) return e;
+    const int m_tiles = (M + UG_BM - 1) / UG_BM, n_tiles = (N + BN - 1) / BN, k_chunks = (K + BK - 1) / BK;
+    drain_chunks = drain_chunks * 32 / BK;        // `drain_chunks` is given in units of 32 K elements
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -236,9 +241,9 @@ inline int launch_umma_nt(const float* Ah, const float* Al, int M, int64_t lda, 
         if (G > n_tiles) G = n_tiles;
         grid = G * m_tiles;
     }
-    if (drain_chunks < 1) drain_chunks = 2;
-    auto kern = umma_nt_3xtf32_kernel<BN, Epi>;
-    const int smem = UmmaSmem<BN>::TOTAL;
+    if (drain_chunks < 1) drain_chunks = 2 * 32 / BK;
+    auto kern = umma_nt_3xtf32_kernel<BN, BK, Epi>;
+    const int smem = UmmaSmem<BN, BK>::TOTAL;
     BRN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kern<<<grid, 64 + 32 * UG_EPI_WARPS, smem, stream>>>(tAh, tAl, tBh, tBl, m_tiles, n_tiles, k_chunks, drain_chunks, mode,
                                                          ep);
