@@ -587,6 +587,8 @@ bnn_mid3_kernel(const float* __restrict__ pre, const float* __restrict__ W, floa
         float2 da2[C2];
 #pragma unroll
         for (int c = 0; c < C2; ++c) da2[c] = make_float2(da[2 * c], da[2 * c + 1]);
+        ohi += (int64_t)hbeg * ldB;          // walk the output rows by pointer increments (no 64-bit multiply per h)
+        olo += (int64_t)hbeg * ldB;
         auto p3_unit = [&](int h) {
             const float hv = tile[h * MID3_TP + r];
             const float4* w4 = reinterpret_cast<const float4*>(W2t + h * CT);
@@ -603,9 +605,11 @@ bnn_mid3_kernel(const float* __restrict__ pre, const float* __restrict__ W, floa
             float hi, lo;
             umma::split_tf32(dp, hi, lo);
             if (row_ok) {
-                ohi[(int64_t)h * ldB] = hi;
-                olo[(int64_t)h * ldB] = lo;
+                *ohi = hi;
+                *olo = lo;
             }
+            ohi += ldB;
+            olo += ldB;
         };
         const int h4 = hbeg + (hend - hbeg) / 4 * 4;
         for (int h0 = hbeg; h0 < h4; h0 += 4) {
@@ -814,11 +818,22 @@ extern "C" int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int
                 BRN_CUDA_OK(cudaMemsetAsync(ws.dph + (size_t)S * HP * ws.ldB, 0, sizeof(float) * HP * ws.ldB, stream));
                 BRN_CUDA_OK(cudaMemsetAsync(ws.dpl + (size_t)S * HP * ws.ldB, 0, sizeof(float) * HP * ws.ldB, stream));
             }
+            // K-split tail (see UnitIter): the dW1 blocks of the samples in the split n-tiles take atomic partial sums
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            const UmmaSplitPlan plan = umma_plan<BN, BNN_UMMA_BK>(P, S * HP, B, sms, true);
+            if (plan.first_split_ntile >= 0) {
+                const int s_first = plan.first_split_ntile * NS;
+                if (s_first < S)
+                    BRN_CUDA_OK(cudaMemset2DAsync(ws.dW + (size_t)s_first * L.ldw + L.oW1, L.ldw * sizeof(float), 0,
+                                                  (size_t)H * P * sizeof(float), S - s_first, stream));
+            }
             EpiStore::Params ep;      // dW1_s[h][p] = D[p, (s, h)]
             ep.out = ws.dW + L.oW1; ep.rows = P; ep.row_stride = 1; ep.col_stride = P; ep.blk_stride = L.ldw;
             ep.blk_valid = H; ep.col_limit = 0; ep.total_blks = S;
             if (int e = launch_umma_nt<BN, BNN_UMMA_BK, EpiStore>(ws.Xth, ws.Xtl, P, ws.ldB, ws.dph, ws.dpl, S * HP, ws.ldB, B, 0, drain, ep,
-                                                     stream))
+                                                     stream, true))
                 return e;
         } else {
             if (int e = launch_sgemm_batched<false, false>(ws.pre, H, (int64_t)B * H, X, P, 0, ws.dW + L.oW1, P, L.ldw, H, P,

@@ -177,7 +177,7 @@ mf_stats_kernel(const float* __restrict__ eps, int64_t lde, const float* __restr
     const int nvalid = (int)min((int64_t)4, numel - q * 4);
     vec = vec && nvalid == 4;          // `vec` = pitches/bases allow float4; the ragged last quad goes scalar
     float gw[4] = {0.f, 0.f, 0.f, 0.f}, gwe[4] = {0.f, 0.f, 0.f, 0.f}, e1[4] = {0.f, 0.f, 0.f, 0.f}, e2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
+#pragma unroll 8
     for (int s = s_begin; s < s_end; ++s) {
         float e[4], d[4] = {0.f, 0.f, 0.f, 0.f};
         if (eps) {

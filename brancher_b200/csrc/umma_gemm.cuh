@@ -34,30 +34,53 @@ struct UmmaSmem {
     static_assert(A_BYTES % (8 * BK * 4) == 0 && B_BYTES % (8 * BK * 4) == 0, "tiles must be whole swizzle atoms");
 };
 
-// which (m-tile, n-tile) units a CTA processes, identically enumerated by every warp role
+// which (m-tile, n-tile, K range) units a CTA processes, identically enumerated by every warp role.
+// mode 0: units n-major (concurrently running CTAs share the B tile), round-robin over CTAs.  When the last round
+//         would be nearly empty (T = units % grid <= grid/2) those T tail units are instead SPLIT ALONG K over the whole
+//         grid (J = grid/T slices each) and accumulated with atomics into a caller-zeroed output: a [7 x 128]-unit
+//         problem on 148 CTAs costs 6 + 1/J unit-times instead of 7.
+// mode 1: a CTA keeps its m-tile and strides over n-tiles.
 struct UnitIter {
-    int m_tiles, n_tiles, mode;
+    int m_tiles, n_tiles, k_chunks, mode;
     int u, step, end, mt_fixed;
-    __device__ UnitIter(int m_tiles_, int n_tiles_, int mode_) : m_tiles(m_tiles_), n_tiles(n_tiles_), mode(mode_) {
-        if (mode == 0) {            // units n-major: concurrently running CTAs share the B (n) tile
+    int tail_u, tail_j, J;
+    bool has_tail;
+    __device__ UnitIter(int m_tiles_, int n_tiles_, int k_chunks_, int mode_, int split_T, int full_units)
+        : m_tiles(m_tiles_), n_tiles(n_tiles_), k_chunks(k_chunks_), mode(mode_), tail_u(0), tail_j(0), J(1), has_tail(false) {
+        if (mode == 0) {
             u = blockIdx.x; step = gridDim.x; end = m_tiles * n_tiles; mt_fixed = -1;
-        } else {                    // a CTA keeps its m-tile and strides over n-tiles
+            if (split_T > 0) {
+                end = full_units;
+                J = min((int)gridDim.x / split_T, k_chunks);
+                has_tail = (int)blockIdx.x < split_T * J;
+                tail_u = full_units + (int)blockIdx.x % split_T;
+                tail_j = (int)blockIdx.x / split_T;
+            }
+        } else {
             mt_fixed = blockIdx.x % m_tiles;
             int g = blockIdx.x / m_tiles, G = gridDim.x / m_tiles;
             u = g; step = G; end = (g < G) ? n_tiles : 0;
         }
     }
-    __device__ bool valid() const { return u < end; }
-    __device__ void next() { u += step; }
-    __device__ int mt() const { return mode == 0 ? u % m_tiles : mt_fixed; }
-    __device__ int nt() const { return mode == 0 ? u / m_tiles : u; }
+    __device__ bool in_tail() const { return u >= end; }
+    __device__ bool valid() const { return u < end || has_tail; }
+    __device__ void next() {
+        if (u < end) u += step;
+        else has_tail = false;
+    }
+    __device__ int unit() const { return u < end ? u : tail_u; }
+    __device__ int mt() const { return mode == 0 ? unit() % m_tiles : mt_fixed; }
+    __device__ int nt() const { return mode == 0 ? unit() / m_tiles : u; }
+    __device__ int kc_begin() const { return u < end ? 0 : (int)((long long)tail_j * k_chunks / J); }
+    __device__ int kc_end() const { return u < end ? k_chunks : (int)((long long)(tail_j + 1) * k_chunks / J); }
 };
 
 template <int BN, int BK, class Epi>
 __global__ void __launch_bounds__(64 + 32 * UG_EPI_WARPS, 1)
 umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                       const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
-                      int m_tiles, int n_tiles, int k_chunks, int drain_chunks, int mode, typename Epi::Params ep) {
+                      int m_tiles, int n_tiles, int k_chunks, int drain_chunks, int mode, int split_T, int full_units,
+                      typename Epi::Params ep) {
     using SM = UmmaSmem<BN, BK>;
     constexpr int UG_STAGES = SM::STAGES, UG_BK = BK, SW = BK * 4;
     constexpr int CPT = BN / 2;                    // accumulator columns per epilogue thread
@@ -87,9 +110,10 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (UnitIter it(m_tiles, n_tiles, mode); it.valid(); it.next()) {
+            for (UnitIter it(m_tiles, n_tiles, k_chunks, mode, split_T, full_units); it.valid(); it.next()) {
                 const int m0 = it.mt() * UG_BM, n0 = it.nt() * BN;
-                for (int kc = 0; kc < k_chunks; ++kc) {
+                const int kcb = it.kc_begin(), kce = it.kc_end();
+                for (int kc = kcb; kc < kce; ++kc) {
                     umma::mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* st = smem + stage * SM::STAGE_BYTES;
                     umma::mbar_arrive_expect_tx(&full_bar[stage], SM::STAGE_BYTES);
@@ -107,13 +131,14 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
         if (lane == 0) {
             constexpr uint32_t idesc = umma::idesc_tf32(UG_BM, BN);
             int stage = 0; uint32_t phase = 0, blk = 0;
-            for (UnitIter it(m_tiles, n_tiles, mode); it.valid(); it.next()) {
-                for (int kc0 = 0; kc0 < k_chunks; kc0 += drain_chunks, ++blk) {
+            for (UnitIter it(m_tiles, n_tiles, k_chunks, mode, split_T, full_units); it.valid(); it.next()) {
+                const int kcb = it.kc_begin(), kce = it.kc_end();
+                for (int kc0 = kcb; kc0 < kce; kc0 += drain_chunks, ++blk) {
                     const uint32_t buf = blk & 1, use = (blk >> 1) & 1;
                     umma::mbar_wait(&acc_empty[buf], use ^ 1);     // epilogue has drained this buffer's previous use
                     umma::tc_fence_after();
                     const uint32_t d_tmem = tmem_base + buf * UG_BUF_COLS;
-                    const int kc1 = min(kc0 + drain_chunks, k_chunks);
+                    const int kc1 = min(kc0 + drain_chunks, kce);
                     for (int kc = kc0; kc < kc1; ++kc) {
                         umma::mbar_wait(&full_bar[stage], phase);
                         umma::tc_fence_after();
@@ -142,11 +167,12 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
         const int hf = ew >> 2;                   // column half
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + hf * CPT;
         uint32_t blk = 0;
-        for (UnitIter it(m_tiles, n_tiles, mode); it.valid(); it.next()) {
+        for (UnitIter it(m_tiles, n_tiles, k_chunks, mode, split_T, full_units); it.valid(); it.next()) {
             float r[CPT];
 #pragma unroll
             for (int i = 0; i < CPT; ++i) r[i] = 0.f;
-            for (int kc0 = 0; kc0 < k_chunks; kc0 += drain_chunks, ++blk) {
+            const int kcb = it.kc_begin(), kce = it.kc_end();
+            for (int kc0 = kcb; kc0 < kce; kc0 += drain_chunks, ++blk) {
                 const uint32_t buf = blk & 1, use = (blk >> 1) & 1;
                 umma::mbar_wait(&acc_full[buf], use);
                 umma::tc_fence_after();
@@ -177,7 +203,7 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
                 __syncwarp();
                 if (lane == 0) umma::mbar_arrive(&acc_empty[buf]);
             }
-            Epi::finish(ep, r, it.mt() * UG_BM + q * 32 + lane, it.nt() * 2 + hf);
+            Epi::finish(ep, r, it.mt() * UG_BM + q * 32 + lane, it.nt() * 2 + hf, it.in_tail());
         }
     }
     umma::tc_fence_before();
@@ -202,26 +228,55 @@ struct EpiStore {
         int total_blks;
     };
     template <int CPT>
-    static __device__ __forceinline__ void finish(const Params& p, float (&r)[CPT], int row, int blk) {
+    static __device__ __forceinline__ void finish(const Params& p, float (&r)[CPT], int row, int blk, bool accumulate) {
         if (row >= p.rows || blk >= p.total_blks) return;
         int valid = p.blk_valid;
         if (p.col_limit > 0) valid = min(CPT, p.col_limit - blk * CPT);
         float* o = p.out + (int64_t)blk * p.blk_stride + (int64_t)row * p.row_stride;
+        if (accumulate) {          // K-split tail unit: partial sums into the caller-zeroed block
 #pragma unroll
-        for (int i = 0; i < CPT; ++i)
-            if (i < valid) o[(int64_t)i * p.col_stride] = r[i];
+            for (int i = 0; i < CPT; ++i)
+                if (i < valid) atomicAdd(&o[(int64_t)i * p.col_stride], r[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < CPT; ++i)
+                if (i < valid) o[(int64_t)i * p.col_stride] = r[i];
+        }
     }
 };
 
 int launch_split_tf32(const float* src, int64_t lds, int rows, int cols, float* hi, float* lo, int64_t ldd, float* thi,
                       float* tlo, int64_t ldt, cudaStream_t stream);
 
+// Work split of mode 0 on `sms` CTAs: grid size, and -- when the last round-robin round would be at most half full --
+// the K-split of the tail units (see UnitIter).  first_split_ntile = first n-tile whose output blocks receive atomic
+// partial sums and must be ZEROED by the caller before the launch (-1: no split).
+struct UmmaSplitPlan {
+    int grid, split_T, full_units, first_split_ntile;
+};
+template <int BN, int BK>
+inline UmmaSplitPlan umma_plan(int M, int N, int K, int sms, bool allow_split) {
+    const int m_tiles = (M + UG_BM - 1) / UG_BM, n_tiles = (N + BN - 1) / BN, k_chunks = (K + BK - 1) / BK;
+    const int U = m_tiles * n_tiles;
+    UmmaSplitPlan p;
+    p.grid = U < sms ? U : sms;
+    p.split_T = 0; p.full_units = U; p.first_split_ntile = -1;
+    const int T = U % p.grid;
+    if (allow_split && U > p.grid && T > 0 && 2 * T <= p.grid && k_chunks >= 2 * (p.grid / T)) {
+        p.split_T = T;
+        p.full_units = U - T;
+        p.first_split_ntile = p.full_units / m_tiles;
+    }
+    return p;
+}
+
 // A (hi/lo) [M][K] pitch lda, B (hi/lo) [N][K] pitch ldb; mode 0: units n-major round-robin over CTAs,
-// mode 1: every CTA keeps one m-tile and strides over n-tiles.
+// mode 1: every CTA keeps one m-tile and strides over n-tiles.  allow_split: the caller has zeroed the output blocks of
+// n-tiles >= umma_plan(...).first_split_ntile (mode 0 only).
 template <int BN, int BK, class Epi>
 inline int launch_umma_nt(const float* Ah, const float* Al, int M, int64_t lda, const float* Bh, const float* Bl, int N,
                           int64_t ldb, int K, int mode, int drain_chunks, const typename Epi::Params& ep,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, bool allow_split = false) {
     CUtensorMap tAh, tAl, tBh, tBl;
     if (int e = make_tmap_2d_f32(&tAh, Ah, M, K, lda, UG_BM, BK)) return e;
     if (int e = make_tmap_2d_f32(&tAl, Al, M, K, lda, UG_BM, BK)) return e;
@@ -232,9 +287,10 @@ inline int launch_umma_nt(const float* Ah, const float* Al, int M, int64_t lda, 
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int grid;
+    int grid, split_T = 0, full_units = m_tiles * n_tiles;
     if (mode == 0) {
-        grid = m_tiles * n_tiles < sms ? m_tiles * n_tiles : sms;
+        const UmmaSplitPlan pl = umma_plan<BN, BK>(M, N, K, sms, allow_split);
+        grid = pl.grid; split_T = pl.split_T; full_units = pl.full_units;
     } else {
         int G = sms / m_tiles;
         if (G < 1) G = 1;
@@ -246,7 +302,7 @@ inline int launch_umma_nt(const float* Ah, const float* Al, int M, int64_t lda, 
     const int smem = UmmaSmem<BN, BK>::TOTAL;
     BRN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kern<<<grid, 64 + 32 * UG_EPI_WARPS, smem, stream>>>(tAh, tAl, tBh, tBl, m_tiles, n_tiles, k_chunks, drain_chunks, mode,
-                                                         ep);
+                                                         split_T, full_units, ep);
     BRN_LAUNCH_OK("umma_nt_3xtf32_kernel");
     return 0;
 }

@@ -233,6 +233,20 @@ def test_bnn_tcgen05_variant(cu, monkeypatch, B, P, H, C, S, tied):
     check_against_oracle(loss, grads, o32, o64, "bnn tcgen05 %s" % ((B, P, H, C, S),))
 
 
+def test_bnn_tcgen05_ksplit_tail(cu, monkeypatch):
+    """Enough units (7 m-tiles x 22 n-tiles = 154 > 148 CTAs) that the backward GEMM K-splits its 6 tail units over the
+    grid and accumulates them with atomics (UnitIter in csrc/umma_gemm.cuh)."""
+    from oracle import elbo_oracle as O
+    monkeypatch.setenv("BRN_BNN_VARIANT", "tcgen05")
+    B, P, H, C, S = 1024, 784, 100, 10, 44
+    X, y, params, eps, shapes = random_bnn(77, B, P, H, C, S)
+    o32 = O.bnn_elbo(X, y, params, eps, None, sample_chunk=4)
+    o64 = O.bnn_elbo(X, y, params, eps, None, dtype=torch.float64, sample_chunk=4)
+    loss, grads, _ = run_bnn(cu, X, y, params, eps, None)
+    assert cu.last_variant() == "tcgen05"
+    check_against_oracle(loss, grads, o32, o64, "bnn tcgen05 k-split tail")
+
+
 def test_bnn_variants_agree_philox(cu, monkeypatch):
     """Same Philox noise through the SIMT and tcgen05 variants."""
     B, P, H, C, S = 200, 96, 100, 10, 6
