@@ -10,6 +10,8 @@
 // from HBM once per column tile (and those re-reads are L2 hits: column tiles of one row group are
 // scheduled together) and nothing of size S x N ever reaches memory.
 #include "meanfield.cuh"
+#include "umma_gemm.cuh"
+#include <stdlib.h>
 
 namespace brn {
 
@@ -203,10 +205,29 @@ __global__ void __launch_bounds__(256, 1) linear_fused_kernel(LinearArgs a) {
     if (t == 0) atomicAdd(a.loss, -tot * (double)a.inv_S);
 }
 
+constexpr int LT_BN1 = 208;       // logits GEMM: samples per n-tile
+constexpr int LT_BN2 = 128;       // gradient GEMM: features per n-tile (F <= 128)
+constexpr int LT_BK = 16;
+
+// rows per chunk of the tcgen05 path: whole 128-row tiles such that (m-tiles x n-tiles) fills ~2 rounds of the grid
+static int linear_tc_chunk_rows(int S, int sms) {
+    const int n_tiles = (S + LT_BN1 - 1) / LT_BN1;
+    int rounds = 8;
+    if (const char* env = getenv("BRN_LINEAR_ROUNDS")) rounds = atoi(env) > 0 ? atoi(env) : rounds;
+    int mt = rounds * sms / n_tiles;
+    if (mt < 1) mt = 1;
+    if (mt > 512) mt = 512;
+    return mt * 128;
+}
+
 struct LinearWorkspace {
     float *eps, *W, *dW, *stats;
+    // tcgen05 variant (Bernoulli, C == 1): TF32-split operands
+    float *Wh, *Wl, *Xh, *Xl, *Xth, *Xtl, *dTh, *dTl, *dWpart;
+    int64_t ldF, ldN, ldNB;
+    int nb, slices;
     size_t bytes;
-    LinearWorkspace(void* base, int64_t numel, int S) {
+    LinearWorkspace(void* base, int64_t numel, int S, int64_t N = 0, int F = 0, bool tc = false, int sms = 148) {
         size_t off = 0;
         auto take = [&](size_t nfloat) {
             float* p = base ? reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off) : nullptr;
@@ -217,9 +238,34 @@ struct LinearWorkspace {
         W = take((size_t)S * numel);
         dW = take((size_t)S * numel);
         stats = take(4 * (size_t)((numel + 3) / 4 * 4));
+        Wh = Wl = Xh = Xl = Xth = Xtl = dTh = dTl = dWpart = nullptr;
+        ldF = ldN = ldNB = 0; nb = 0; slices = 0;
+        if (tc) {
+            ldF = (F + 3) / 4 * 4;
+            ldN = (N + 3) / 4 * 4;
+            nb = linear_tc_chunk_rows(S, sms);
+            if (nb > N) nb = (int)((N + 127) / 128 * 128);
+            ldNB = nb;
+            const int m2 = (S + UG_BM - 1) / UG_BM;
+            slices = (2 * m2 <= sms) ? sms / m2 : 1;
+            Wh = take((size_t)S * ldF); Wl = take((size_t)S * ldF);
+            Xh = take((size_t)N * ldF); Xl = take((size_t)N * ldF);
+            Xth = take((size_t)F * ldN); Xtl = take((size_t)F * ldN);
+            dTh = take((size_t)S * ldNB); dTl = take((size_t)S * ldNB);
+            dWpart = take((size_t)slices * S * F);
+        }
         bytes = off;
     }
 };
+
+// dW[i] = sum_j part[j * stride + i]
+__global__ void sum_slices_kernel(const float* __restrict__ part, int slices, int64_t stride, int64_t n, float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float acc = 0.f;
+    for (int j = 0; j < slices; ++j) acc += part[(int64_t)j * stride + i];
+    out[i] = acc;
+}
 
 // particles: G = -(d ll / d theta) - d log N(theta; a, b) / d theta ; loss += sum -log N(theta; a, b)
 __global__ void __launch_bounds__(256)
@@ -240,6 +286,15 @@ particles_prior_kernel(const float* __restrict__ theta, const float* __restrict_
     }
     double tot = block_sum<double>(nlp, red);
     if (threadIdx.x == 0 && prior_loc) atomicAdd(loss, tot);
+}
+
+static bool linear_use_tc(int likelihood, int64_t N, int F, int C, int S) {
+    bool tc = likelihood == 0 && C == 1 && F % 4 == 0 && F <= LT_BN2 && N >= 4096 && S >= 64;
+    if (const char* env = getenv("BRN_LINEAR_VARIANT")) {
+        if (!strcmp(env, "simt")) tc = false;
+        else if (!strcmp(env, "tcgen05")) tc = likelihood == 0 && C == 1 && F % 4 == 0 && F <= LT_BN2 && N >= 1 && S >= 1;
+    }
+    return tc;
 }
 
 }  // namespace brn
@@ -303,7 +358,12 @@ extern "C" int brn_linear_particles_loss_grad(const float* X, const void* y, int
 
 extern "C" size_t brn_linear_workspace_bytes(int64_t N, int F, int C, int s_local) {
     if (N < 0 || F <= 0 || C <= 0 || s_local < 0) return 0;
-    return LinearWorkspace(nullptr, (int64_t)C * F, s_local).bytes;
+    // sized for the larger of the two variants (the likelihood is not known here): tcgen05 buffers whenever C == 1
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const bool tc = C == 1 && F % 4 == 0 && F <= LT_BN2 && N >= 1 && s_local >= 1;
+    return LinearWorkspace(nullptr, (int64_t)C * F, s_local, N, F, tc, sms).bytes;
 }
 
 extern "C" int brn_linear_elbo_fwd_bwd(const float* X, const void* y, int likelihood, int64_t N, int F, int C,
@@ -325,9 +385,13 @@ extern "C" int brn_linear_elbo_fwd_bwd(const float* X, const void* y, int likeli
     BRN_CHECK_ARG(!with_prior || w->tied || (w->prior_loc && w->prior_scale), "prior_loc/prior_scale required when not tied");
     const int S = r->s_local;
     if (S == 0) return 0;
-    LinearWorkspace ws(workspace, numel, S);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const bool use_tc = linear_use_tc(likelihood, N, F, C, S);
+    LinearWorkspace ws(workspace, numel, S, N, F, use_tc, sms);
     BRN_CHECK_ARG(workspace && workspace_bytes >= ws.bytes, "workspace too small: %zu < %zu", workspace_bytes, ws.bytes);
-    set_variant("simt");
+    set_variant(use_tc ? "tcgen05" : "simt");
 
     const float* eps = w->eps;
     StageTimer* st = new StageTimer("linear.sample_weights", stream);
@@ -336,11 +400,44 @@ extern "C" int brn_linear_elbo_fwd_bwd(const float* X, const void* y, int likeli
         eps = ws.eps;
     }
     if (int e = launch_sample_weights(w->mu, w->rho, eps, numel, ws.W, numel, numel, S, stream)) return e;
-    BRN_CUDA_OK(cudaMemsetAsync(ws.dW, 0, sizeof(float) * (size_t)S * numel, stream));
+    if (!use_tc) BRN_CUDA_OK(cudaMemsetAsync(ws.dW, 0, sizeof(float) * (size_t)S * numel, stream));
     delete st;
-    if (N > 0) {
+    if (N > 0 && use_tc) {
+        // ---- tcgen05 variant: per row chunk, (1) logits GEMM with the Bernoulli likelihood fused in its epilogue
+        //      (writes d = y - sigmoid(l) transposed + TF32-split), (2) gradient GEMM dW[s,f] += d^T X, K-split over
+        //      the grid with per-slice accumulation (no atomics); finally the slices are summed.
+        int drain = 2;
+        if (const char* env = getenv("BRN_UMMA_DRAIN")) drain = atoi(env);
+        {
+            StageTimer sp("linear.split_operands", stream);
+            if (int e = launch_split_tf32(ws.W, F, S, F, ws.Wh, ws.Wl, ws.ldF, nullptr, nullptr, 0, stream)) return e;
+            if (int e = launch_split_tf32(X, F, (int)N, F, ws.Xh, ws.Xl, ws.ldF, ws.Xth, ws.Xtl, ws.ldN, stream)) return e;
+            BRN_CUDA_OK(cudaMemsetAsync(ws.dWpart, 0, sizeof(float) * (size_t)ws.slices * S * F, stream));
+        }
+        StageTimer st2("linear.fused", stream);
+        for (int64_t r0 = 0; r0 < N; r0 += ws.nb) {
+            const int nb = (int)((N - r0 < ws.nb) ? (N - r0) : ws.nb);
+            EpiBernoulli::Params e1;
+            e1.y = reinterpret_cast<const float*>(y) + r0; e1.dT_hi = ws.dTh; e1.dT_lo = ws.dTl; e1.rows = nb; e1.cols = S;
+            e1.ld = ws.ldNB; e1.loss = loss; e1.neg_inv_S = -1.0f / (float)r->s_total;
+            if (int e = launch_umma_nt<LT_BN1, LT_BK, EpiBernoulli>(ws.Xh + r0 * ws.ldF, ws.Xl + r0 * ws.ldF, nb, ws.ldF, ws.Wh, ws.Wl, S,
+                                                                     ws.ldF, F, 0, drain, e1, stream))
+                return e;
+            // K tail of the last chunk: the TMA box zero-fills columns >= nb of d^T (tensor map extent = nb)
+            EpiAccum::Params e2;
+            e2.out = ws.dWpart; e2.rows = S; e2.cols = F; e2.ld = F; e2.slice_stride = (int64_t)S * F;
+            if (int e = launch_umma_nt<LT_BN2, LT_BK, EpiAccum>(ws.dTh, ws.dTl, S, ws.ldNB, ws.Xth + r0, ws.Xtl + r0, F, ws.ldN, nb, 0,
+                                                                 drain, e2, stream, ws.slices > 1))
+                return e;
+        }
+        const int64_t tot = (int64_t)S * F;
+        sum_slices_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(ws.dWpart, ws.slices, tot, tot, ws.dW);
+        BRN_LAUNCH_OK("sum_slices_kernel");
+    } else if (N > 0) {
         StageTimer st2("linear.fused", stream);
         if (int e = launch_linear_fused(X, y, likelihood, N, F, C, S, ws.W, ws.dW, 1.0f / (float)r->s_total, loss, stream)) return e;
+    } else if (use_tc) {
+        BRN_CUDA_OK(cudaMemsetAsync(ws.dW, 0, sizeof(float) * (size_t)S * numel, stream));
     }
     StageTimer st3("linear.reduce_finalize", stream);
     return launch_mf_reduce_finalize(*w, eps, numel, ws.dW, numel, ws.stats, *r, with_prior, loss, stream);

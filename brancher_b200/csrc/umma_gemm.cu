@@ -51,7 +51,7 @@ __global__ void split_tf32_kernel(const float* __restrict__ src, int64_t lds, in
                                   float* __restrict__ lo, int64_t ldd, float* __restrict__ thi, float* __restrict__ tlo,
                                   int64_t ldt) {
     __shared__ float th[32][33], tl[32][33];
-    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int c0 = blockIdx.y * 32, r0 = blockIdx.x * 32;       // row tiles on grid.x: rows may be millions
     const int tx = threadIdx.x, ty = threadIdx.y;       // 32 x 8
     for (int i = ty; i < 32; i += 8) {
         int r = r0 + i, c = c0 + tx;
@@ -77,7 +77,7 @@ __global__ void split_tf32_kernel(const float* __restrict__ src, int64_t lds, in
 int launch_split_tf32(const float* src, int64_t lds, int rows, int cols, float* hi, float* lo, int64_t ldd, float* thi,
                       float* tlo, int64_t ldt, cudaStream_t stream) {
     if (rows <= 0 || cols <= 0) return 0;
-    dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+    dim3 grid((rows + 31) / 32, (cols + 31) / 32), block(32, 8);
     split_tf32_kernel<<<grid, block, 0, stream>>>(src, lds, rows, cols, hi, lo, ldd, thi, tlo, ldt);
     BRN_LAUNCH_OK("split_tf32_kernel");
     return 0;

@@ -71,6 +71,7 @@ struct UnitIter {
     __device__ int unit() const { return u < end ? u : tail_u; }
     __device__ int mt() const { return mode == 0 ? unit() % m_tiles : mt_fixed; }
     __device__ int nt() const { return mode == 0 ? unit() / m_tiles : u; }
+    __device__ int slice() const { return u < end ? 0 : tail_j; }
     __device__ int kc_begin() const { return u < end ? 0 : (int)((long long)tail_j * k_chunks / J); }
     __device__ int kc_end() const { return u < end ? k_chunks : (int)((long long)(tail_j + 1) * k_chunks / J); }
 };
@@ -203,7 +204,7 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
                 __syncwarp();
                 if (lane == 0) umma::mbar_arrive(&acc_empty[buf]);
             }
-            Epi::finish(ep, r, it.mt() * UG_BM + q * 32 + lane, it.nt() * 2 + hf, it.in_tail());
+            Epi::finish(ep, r, it.mt() * UG_BM + q * 32 + lane, it.nt() * 2 + hf, it.in_tail(), it.slice());
         }
     }
     umma::tc_fence_before();
@@ -228,7 +229,7 @@ struct EpiStore {
         int total_blks;
     };
     template <int CPT>
-    static __device__ __forceinline__ void finish(const Params& p, float (&r)[CPT], int row, int blk, bool accumulate) {
+    static __device__ __forceinline__ void finish(const Params& p, float (&r)[CPT], int row, int blk, bool accumulate, int /*slice*/) {
         if (row >= p.rows || blk >= p.total_blks) return;
         int valid = p.blk_valid;
         if (p.col_limit > 0) valid = min(CPT, p.col_limit - blk * CPT);
@@ -242,6 +243,75 @@ struct EpiStore {
             for (int i = 0; i < CPT; ++i)
                 if (i < valid) o[(int64_t)i * p.col_stride] = r[i];
         }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// epilogue policy: K-slice accumulation without atomics.  Unit (row tile, column half) of K-slice j owns
+//     out[j * slice_stride + row * ld + col]   and adds its result to what is there (stream-ordered launches of the
+// same shape accumulate chunk after chunk; a final pass sums the slices).  Deterministic, unlike atomics.
+// ------------------------------------------------------------------------------------------------
+struct EpiAccum {
+    struct Params {
+        float* out; int rows, cols; int64_t ld, slice_stride;
+    };
+    template <int CPT>
+    static __device__ __forceinline__ void finish(const Params& p, float (&r)[CPT], int row, int blk, bool, int slice) {
+        if (row >= p.rows) return;
+        float* o = p.out + (int64_t)slice * p.slice_stride + (int64_t)row * p.ld + (int64_t)blk * CPT;
+        const int valid = min(CPT, p.cols - blk * CPT);
+        if (valid == CPT && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+            for (int i = 0; i < CPT; i += 4) {
+                float4 v = *reinterpret_cast<float4*>(o + i);
+                v.x += r[i]; v.y += r[i + 1]; v.z += r[i + 2]; v.w += r[i + 3];
+                *reinterpret_cast<float4*>(o + i) = v;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < CPT; ++i)
+                if (i < valid) o[i] += r[i];
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// epilogue policy: Bernoulli / Binomial(1) likelihood fused behind the logits GEMM (K2):
+//   D[row n, col s] = logit;  ll += y_n l - log(1 + e^l);  d = y_n - sigmoid(l)
+//   d is written TF32-split and TRANSPOSED: dT_{hi,lo}[s * ld + n]  (the K-major A operand of the gradient GEMM;
+//   coalesced across the warp's 32 rows).  log1p(e^-|l|) is evaluated as log(1 + e): its absolute error (< 6e-8)
+//   is far below the fp32 resolution of the terms it is added to.
+// ------------------------------------------------------------------------------------------------
+struct EpiBernoulli {
+    struct Params {
+        const float* y; float* dT_hi; float* dT_lo; int rows, cols; int64_t ld; double* loss; float neg_inv_S;
+    };
+    template <int CPT>
+    static __device__ __forceinline__ void finish(const Params& p, float (&r)[CPT], int row, int blk, bool, int) {
+        const bool row_ok = row < p.rows;
+        const float yv = row_ok ? p.y[row] : 0.f;
+        const int valid = row_ok ? min(CPT, p.cols - blk * CPT) : 0;
+        float ll = 0.f;
+        float* ohi = p.dT_hi + (int64_t)blk * CPT * p.ld + row;
+        float* olo = p.dT_lo + (int64_t)blk * CPT * p.ld + row;
+#pragma unroll          // full unroll: r[] must stay in registers (a partial unroll indexes it dynamically -> local memory)
+        for (int i = 0; i < CPT; ++i) {
+            if (i < valid) {
+                const float l = r[i];
+                const float e = __expf(-fabsf(l));
+                const float inv = __frcp_rn(1.f + e);
+                const float sig = l >= 0.f ? inv : e * inv;
+                ll += __fmaf_rn(yv, l, -(fmaxf(l, 0.f) + __logf(1.f + e)));
+                float hi, lo;
+                umma::split_tf32(yv - sig, hi, lo);
+                ohi[(int64_t)i * p.ld] = hi;
+                olo[(int64_t)i * p.ld] = lo;
+            }
+        }
+        double tot = (double)ll;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        if ((threadIdx.x & 31) == 0 && tot != 0.0) atomicAdd(p.loss, tot * (double)p.neg_inv_S);
     }
 };
 
@@ -266,6 +336,11 @@ inline UmmaSplitPlan umma_plan(int M, int N, int K, int sms, bool allow_split) {
         p.split_T = T;
         p.full_units = U - T;
         p.first_split_ntile = p.full_units / m_tiles;
+    } else if (allow_split && 2 * U <= sms && k_chunks >= 2 * (sms / U)) {
+        p.grid = sms / U * U;           // every unit is K-split over sms/U CTAs
+        p.split_T = U;
+        p.full_units = 0;
+        p.first_split_ntile = 0;
     }
     return p;
 }

@@ -200,6 +200,25 @@ def test_linear_random_shapes(cu, N, F, C, S, lik):
     check_against_oracle(loss, grads, o32, o64, "linear %s" % ((N, F, C, S, lik),))
 
 
+@pytest.mark.parametrize("N,F,S,tied", [(1, 4, 1, True), (300, 8, 5, False), (1000, 128, 70, False), (5000, 128, 300, True),
+                                         (20000, 64, 130, False)])
+def test_linear_tcgen05_variant(cu, monkeypatch, N, F, S, tied):
+    """K2 on the tensor cores: logits GEMM with the Bernoulli likelihood fused in its epilogue + K-split gradient GEMM."""
+    from oracle import elbo_oracle as O
+    monkeypatch.setenv("BRN_LINEAR_VARIANT", "tcgen05")
+    rng = np.random.RandomState(N + F + S)
+    X = rng.randn(N, F).astype("f4")
+    y = rng.randint(0, 2, size=N)
+    params = {"weights": ((0.3 * rng.randn(1, F)).astype("f4"), (rng.randn(1, F) - 1).astype("f4"))}
+    eps = {"weights": rng.randn(S, 1, F).astype("f4")}
+    prior = None if tied else {"weights": (0.0, 0.5)}
+    o32 = O.logreg_elbo(X, y, params, eps, prior, row_chunk=4096)
+    o64 = O.logreg_elbo(X, y, params, eps, prior, dtype=torch.float64, row_chunk=4096)
+    loss, grads = run_linear(cu, X, y, params, eps, cu.BERNOULLI, 1, prior)
+    assert cu.last_variant() == "tcgen05"
+    check_against_oracle(loss, grads, o32, o64, "linear tcgen05 N=%d F=%d S=%d" % (N, F, S))
+
+
 def test_linear_empty_rows(cu):
     """N = 0: the ELBO is prior + entropy only."""
     from oracle import elbo_oracle as O
