@@ -189,6 +189,60 @@ def bnn_elbo(X, y, params, eps, prior=None, dtype=torch.float32, sample_chunk=No
 
 
 # ----------------------------------------------------------------------------------------------
+# Amortised VAE (config C5): /root/reference/examples/VAE_playground.py:30-80
+# ----------------------------------------------------------------------------------------------
+def vae_elbo(X, enc, dec, eps, sd_offset=0.1, dtype=torch.float32, row_chunk=None):
+    """Amortised VAE with ReLU-MLP encoder / decoder, z ~ N(0, I), x ~ Binomial(1, logits) (VAE_playground.py:65-76).
+
+    X [B, D] in {0,1}; eps [S, B, L] injected noise of Qz; enc / dec: dicts of numpy arrays
+      enc: "W" list of hidden weights [n_out, n_in] (torch.nn.Linear layout), "b" list of biases, "W_mean","b_mean",
+           "W_sd","b_sd"  (mean = l3(h), sd = softplus(l4(h)) + 0.1, VAE_playground.py:44-46)
+      dec: "W","b" hidden lists, "W_out","b_out"  (logits = l3(h), :58-62)
+    The minibatch is the SAME B rows for every MC sample.  What the reference computes (SURVEY §8 a'):
+      x is not observed in p  => no data-axis sum (variables.py:513-514) => mean over S AND B (gradient_estimators.py:44);
+      log p(z) = sum_lat N(z;0,1); H[Qz] analytic = sum_lat (1/2 + c + log sd) (variables.py:156-162);
+      H[Qx] = log(S): EmpiricalDistribution._get_entropy sees the S-times-tiled dataset's leading axis
+      (distributions.py:464-473).
+    Returns (loss, grads) with grads keyed "enc.W.0", "enc.b.0", ..., "enc.W_mean", ..., "dec.W_out", "dec.b_out".
+    """
+    Xt = _t(X, dtype)
+    et = _t(eps, dtype)
+    S, B, L = et.shape
+    P = {}
+    for side, net in (("enc", enc), ("dec", dec)):
+        for k, v in net.items():
+            if isinstance(v, (list, tuple)):
+                for i, a in enumerate(v):
+                    P["%s.%s.%d" % (side, k, i)] = _t(a, dtype, True)
+            else:
+                P["%s.%s" % (side, k)] = _t(v, dtype, True)
+    n_enc, n_dec = len(enc["W"]), len(dec["W"])
+    c = 0.5 * math.log(2 * math.pi)
+    step = row_chunk or B
+    total = 0.0
+    for b0 in range(0, B, step):
+        xb, eb = Xt[b0:b0 + step], et[:, b0:b0 + step]
+        h = xb
+        for i in range(n_enc):
+            h = torch.relu(F.linear(h, P["enc.W.%d" % i], P["enc.b.%d" % i]))
+        mean = F.linear(h, P["enc.W_mean"], P["enc.b_mean"])
+        sd = F.softplus(F.linear(h, P["enc.W_sd"], P["enc.b_sd"])) + sd_offset
+        z = mean.unsqueeze(0) + eb * sd.unsqueeze(0)                                   # Normal.rsample: loc + eps*scale
+        g = z
+        for i in range(n_dec):
+            g = torch.relu(F.linear(g, P["dec.W.%d" % i], P["dec.b.%d" % i]))
+        logits = F.linear(g, P["dec.W_out"], P["dec.b_out"])                          # [S, b, D]
+        ll = D.Binomial(total_count=1, logits=logits).log_prob(xb.unsqueeze(0)).sum(-1)     # [S, b]
+        lpz = D.Normal(torch.zeros((), dtype=dtype), torch.ones((), dtype=dtype)).log_prob(z).sum(-1)
+        ent = D.Normal(mean, sd).entropy().sum(-1).unsqueeze(0)                        # [1, b]
+        part = -(ll + lpz + ent).sum() / (S * B)
+        part.backward()
+        total += float(part.detach())
+    loss = total - math.log(S)
+    return loss, {k: v.grad.numpy().copy() for k, v in P.items()}
+
+
+# ----------------------------------------------------------------------------------------------
 # README AR(1) (config C1): /root/reference/README.md:22-75 with y0 named 'y0' (README reuses 'x0')
 # and LogitNormalVariable defined as torch TransformedDistribution(Normal, SigmoidTransform)
 # following the LogNormal pattern (distributions.py:493-507); see SURVEY §8 a13.

@@ -150,6 +150,49 @@ def scalar_model(builder, tag, S, transforms, **kw):
          **flat("grad_", {n: g.reshape(()) for n, g in grads.items()}))
 
 
+def vae_nets(d):
+    """numpy view of the torch modules of zoo.vae_modules in the oracle's / C-ABI's layout."""
+    enc, dec = d["enc"], d["dec"]
+    n = lambda t: t.detach().cpu().numpy().copy()
+    e = {"W": [n(l.weight) for l in enc.hidden], "b": [n(l.bias) for l in enc.hidden], "W_mean": n(enc.l_mean.weight),
+         "b_mean": n(enc.l_mean.bias), "W_sd": n(enc.l_sd.weight), "b_sd": n(enc.l_sd.bias)}
+    dd = {"W": [n(l.weight) for l in dec.hidden], "b": [n(l.bias) for l in dec.hidden], "W_out": n(dec.l_out.weight),
+          "b_out": n(dec.l_out.bias)}
+    return e, dd
+
+
+def vae_grads(d):
+    enc, dec = d["enc"], d["dec"]
+    g = lambda t: t.grad.detach().cpu().numpy().copy()
+    out = {}
+    for side, net, heads in (("enc", enc, (("W_mean", "l_mean"), ("W_sd", "l_sd"))), ("dec", dec, (("W_out", "l_out"),))):
+        for i, l in enumerate(net.hidden):
+            out["%s.W.%d" % (side, i)] = g(l.weight)
+            out["%s.b.%d" % (side, i)] = g(l.bias)
+        for key, attr in heads:
+            out["%s.%s" % (side, key)] = g(getattr(net, attr).weight)
+            out["%s.b%s" % (side, key[1:])] = g(getattr(net, attr).bias)
+    return out
+
+
+def vae(seed, B, D, L, h_enc, h_dec, S, tag):
+    model, Q, d = zoo.vae(NS, seed, B, D, L, h_enc, h_dec)
+    eps = torch.tensor(d["rng"].randn(S, B, L).astype("float32"))
+    inject(Q, {"z": eps})
+    loss = inference.ReverseKL().compute_loss(model, model.posterior_model, None, S)
+    loss.backward()
+    e, dd = vae_nets(d)
+    flatnet = {}
+    for side, net in (("enc", e), ("dec", dd)):
+        for k, v in net.items():
+            if isinstance(v, list):
+                for i, a in enumerate(v):
+                    flatnet["param_%s.%s.%d" % (side, k, i)] = a
+            else:
+                flatnet["param_%s.%s" % (side, k)] = v
+    save(tag, X=d["X"], loss=float(loss.detach()), eps_z=eps.numpy(), **flatnet, **flat("grad_", vae_grads(d)))
+
+
 def svgd(seed, n, d, tag="svgd_small"):
     """SteinVariationalGradientDescent.correct_gradient (inference.py:301-324) on n particles of dim d
     with arbitrary incoming gradients."""

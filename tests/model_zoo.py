@@ -167,3 +167,62 @@ def ar1(ns, seed, T):
         Qx.append(ns.NormalVariable(ns.BF.sigmoid(logit_b_post) * Qx[t - 1] + Qx_mean[t], 1., "x%d" % t, learnable=True))
     model.set_posterior_model(ns.ProbabilisticModel([Qb] + Qx))
     return model, [Qb] + Qx, {"y": ydata.astype("float32"), "measure_noise": measure, "rng": rng}
+
+
+def vae_modules(D, L, h_enc, h_dec, seed):
+    """Encoder / decoder of examples/VAE_playground.py:30-63 (ReLU MLPs; encoder heads mean and softplus(.)+0.1) with
+    configurable widths; plain torch.nn so both packages wrap the same objects with BF.BrancherFunction."""
+    import torch
+    import torch.nn as nn
+
+    class EncoderArchitecture(nn.Module):
+        def __init__(self):
+            super().__init__()
+            dims = [D] + list(h_enc)
+            self.hidden = nn.ModuleList([nn.Linear(a, b) for a, b in zip(dims[:-1], dims[1:])])
+            self.f = nn.ReLU()
+            self.l_mean = nn.Linear(dims[-1], L)
+            self.l_sd = nn.Linear(dims[-1], L)
+            self.softplus = nn.Softplus()
+
+        def __call__(self, x):
+            h = x.squeeze(-1)
+            for l in self.hidden:
+                h = self.f(l(h))
+            return {"mean": self.l_mean(h), "sd": self.softplus(self.l_sd(h)) + 0.1}
+
+    class DecoderArchitecture(nn.Module):
+        def __init__(self):
+            super().__init__()
+            dims = [L] + list(h_dec)
+            self.hidden = nn.ModuleList([nn.Linear(a, b) for a, b in zip(dims[:-1], dims[1:])])
+            self.f = nn.ReLU()
+            self.l_out = nn.Linear(dims[-1], D)
+
+        def __call__(self, z):
+            h = z
+            for l in self.hidden:
+                h = self.f(l(h))
+            return {"mean": self.l_out(h)}
+
+    torch.manual_seed(seed)
+    return EncoderArchitecture(), DecoderArchitecture()
+
+
+def vae(ns, seed, B, D, L, h_enc, h_dec):
+    """examples/VAE_playground.py:65-80 on synthetic binarised data; the minibatch is the fixed index list 0..B-1 shared
+    by all MC samples (EmpiricalVariable(indices=...), distributions.py:443-455)."""
+    rng = np.random.RandomState(seed)
+    dataset = (rng.rand(B, D, 1) < 0.5).astype("int32")
+    enc, dec = vae_modules(D, L, h_enc, h_dec, seed)
+    encoder = ns.BF.BrancherFunction(enc)
+    decoder = ns.BF.BrancherFunction(dec)
+    z = ns.NormalVariable(np.zeros((L,)), np.ones((L,)), name="z")
+    decoder_output = ns.DeterministicVariable(decoder(z), name="decoder_output")
+    x = ns.BinomialVariable(total_count=1, logits=decoder_output["mean"], name="x")
+    model = ns.ProbabilisticModel([x, z])
+    Qx = ns.EmpiricalVariable(dataset, indices=list(range(B)), name="x", is_observed=True)
+    encoder_output = ns.DeterministicVariable(encoder(Qx), name="encoder_output")
+    Qz = ns.NormalVariable(encoder_output["mean"], encoder_output["sd"], name="z")
+    model.set_posterior_model(ns.ProbabilisticModel([Qx, Qz]))
+    return model, [Qz], {"X": dataset[:, :, 0].astype("float32"), "enc": enc, "dec": dec, "rng": rng}
