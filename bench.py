@@ -2,7 +2,7 @@
 """bench.py -- ELBO+gradient throughput of the B200-native hot path, in BASELINE.json's metric:
 (MC samples x data rows) / s, beside the reference algorithm's CPU path on the same box.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload bnn|logreg]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload bnn|logreg|svgd|vae]
 
 One "step" = one ELBO + pathwise-gradient evaluation (loss and d loss/d every variational parameter)
 of the workload on synthetic data.  Workloads:
@@ -40,6 +40,10 @@ WORKLOADS = {
                       "B=65536 rows, prior N(0,1); one step = per-particle loss+grad (K4a) + all-gather + pairwise RBF "
                       "direction with exact median bandwidth (K4b)",
                  n=4096, F=128, C=1, B=65536),
+    "vae": dict(name="C5 amortised VAE (VAE_playground.py shape): encoder 784-256-512-(2+2, softplus+0.1), decoder 2-512-256-784, "
+                     "ReLU, z~N(0,I), x~Binomial(1,logits); synthetic x~Bernoulli(0.5); batch B=4096 rows per GPU, S=16 MC samples "
+                     "per datapoint (same batch for every sample)",
+                B=4096, D=784, L=2, h_enc=(256, 512), h_dec=(512, 256), S=16),
 }
 
 
@@ -133,6 +137,30 @@ def synth_logreg(cfg, seed=0, rows=None):
     return X, y, params
 
 
+def synth_vae(cfg, seed=0, rows=None):
+    """torch.nn.Linear default init (U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weights and biases), x ~ Bernoulli(0.5)."""
+    rng = np.random.RandomState(seed)
+    B, D, L = rows or cfg["B"], cfg["D"], cfg["L"]
+    X = (rng.rand(B, D) < 0.5).astype(np.float32)
+
+    def lin(n_in, n_out):
+        k = 1.0 / np.sqrt(n_in)
+        return rng.uniform(-k, k, (n_out, n_in)).astype(np.float32), rng.uniform(-k, k, (n_out,)).astype(np.float32)
+
+    def mlp(dims):
+        wb = [lin(a, b) for a, b in zip(dims[:-1], dims[1:])]
+        return [w for w, _ in wb], [b for _, b in wb]
+
+    eW, eb = mlp([D] + list(cfg["h_enc"]))
+    Wm, bm = lin(cfg["h_enc"][-1], L)
+    Ws, bs = lin(cfg["h_enc"][-1], L)
+    dW, db = mlp([L] + list(cfg["h_dec"]))
+    Wo, bo = lin(cfg["h_dec"][-1], D)
+    enc = {"W": eW, "b": eb, "W_mean": Wm, "b_mean": bm, "W_sd": Ws, "b_sd": bs}
+    dec = {"W": dW, "b": db, "W_out": Wo, "b_out": bo}
+    return X, enc, dec
+
+
 # ---------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference's CPU torch path
 # ---------------------------------------------------------------------------------------------
@@ -144,6 +172,11 @@ def cpu_step_fn(workload, cfg, sample_S):
         eps = {n: rng.standard_normal((sample_S,) + s).astype(np.float32) for n, s in shapes.items()}
         rows = cfg["B"]
         fn = lambda: O.bnn_elbo(X, y, params, eps, sample_chunk=8)
+    elif workload == "vae":
+        rows = 1024
+        X, enc, dec = synth_vae(cfg, rows=rows)
+        eps = rng.standard_normal((sample_S, rows, cfg["L"])).astype(np.float32)
+        fn = lambda: O.vae_elbo(X, enc, dec, eps)
     elif workload == "svgd":
         rows = 8192
         X, y, _ = synth_logreg(cfg, rows=rows)
@@ -162,8 +195,11 @@ def cpu_step_fn(workload, cfg, sample_S):
         torch.get_num_threads(), sample_S, rows)
 
 
+CPU_SAMPLE_S = {"svgd": 512, "vae": 4}      # MC samples (particles) of the bounded CPU sample; default 64
+
+
 def run_cpu_baseline(workload, cfg, budget_s=12.0):
-    S = 512 if workload == "svgd" else 64
+    S = CPU_SAMPLE_S.get(workload, 64)
     fn, units, desc = cpu_step_fn(workload, cfg, S)
     fn()
     t0, n = time.perf_counter(), 0
@@ -182,7 +218,7 @@ def main_reference(args):
         return
     wl = args.workload
     cfg = WORKLOADS[wl]
-    S = 512 if wl == "svgd" else 64
+    S = CPU_SAMPLE_S.get(wl, 64)
     fn, units, desc = cpu_step_fn(wl, cfg, S)
     for _ in range(args.warmup):
         fn()
@@ -239,6 +275,34 @@ def main_ours(args):
             r = cu.sample_range(S_total, s0=s0, s_local=S_local, seed=args.seed, offset=it)
             gflat.zero_()
             return cu.bnn_elbo_fwd_bwd(Xd, yd, mvars, r)
+    elif wl == "vae":
+        # batch rows sharded over ranks (weak scaling: B rows per GPU); every rank evaluates all S samples of its rows;
+        # one all-reduce of the flat gradient buffer (669 k floats) + loss
+        B, S_local = cfg["B"], cfg["S"]
+        S_total = S_local
+        Xh, ench, dech = synth_vae(cfg, seed=rank)
+        _, enc0, dec0 = (Xh, ench, dech) if rank == 0 else synth_vae(cfg, seed=0)       # identical weights on every rank
+        t = lambda a: torch.tensor(a, device=dev)
+        net = cu.VaeNet([(t(W), t(b)) for W, b in zip(enc0["W"], enc0["b"])], (t(enc0["W_mean"]), t(enc0["b_mean"])),
+                        (t(enc0["W_sd"]), t(enc0["b_sd"])), [(t(W), t(b)) for W, b in zip(dec0["W"], dec0["b"])],
+                        (t(dec0["W_out"]), t(dec0["b_out"])))
+        net.zero_grads()
+        gflat = net.flat
+        mvars = []
+        X = t(Xh)
+        y = None
+        Xpin, ypin = torch.tensor(Xh).pin_memory(), None
+        h2d = Xpin.numel() * 4
+        units_per_rank = S_local * B
+        Rr = float(S_local) * B
+        he, hd, Dp, Lz = cfg["h_enc"], cfg["h_dec"], cfg["D"], cfg["L"]
+        dec_mac = sum(a * b for a, b in zip(hd[:-1], hd[1:])) + hd[-1] * Dp          # GEMM layers of the decoder
+        algo_flops = {"vae.decoder_fwd": 2.0 * Rr * dec_mac, "vae.decoder_bwd": 4.0 * Rr * dec_mac}
+
+        def device_step(it, Xd=X, yd=None):
+            r = cu.sample_range(S_total, seed=args.seed, offset=it)
+            gflat.zero_()
+            return cu.vae_elbo_fwd_bwd(Xd, net, r, row0=rank * B, B_total=B * world, add_constant=(rank == 0))
     elif wl == "svgd":
         # particles sharded over ranks (weak scaling: n particles per rank), data replicated; the pairwise stage needs
         # all particles: all-gather theta and G (2 MB each per rank), every rank computes its rows of K and the update
@@ -309,7 +373,7 @@ def main_ours(args):
 
     def e2e_step(it):
         Xd = Xpin.to(dev, non_blocking=True)
-        yd = ypin.to(dev, non_blocking=True)
+        yd = ypin.to(dev, non_blocking=True) if ypin is not None else None
         loss = reduce_partials(device_step(it, Xd, yd))
         return float(loss.item())          # device -> host read of the step's result
 
@@ -366,7 +430,7 @@ def main_ours(args):
                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                "config": {"workload": cfg["name"], "noise": "Philox4x32-10 in-kernel", "l2": "256 MiB flush between timed steps",
                           "variant": cu.last_variant(), "global_samples_or_particles": S_total,
-                          "sharding": {"bnn": "MC samples", "logreg": "data rows", "svgd": "particles"}[wl]},
+                          "sharding": {"bnn": "MC samples", "logreg": "data rows", "svgd": "particles", "vae": "batch rows"}[wl]},
                "clocks": clk, "gpu_launches": int(launches),
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
                        "ms_per_step": ms_e2e / n_e2e},

@@ -35,6 +35,23 @@ class SampleRange(ctypes.Structure):
                 ("_pad", ctypes.c_int32), ("seed", ctypes.c_uint64), ("offset", ctypes.c_uint64)]
 
 
+VAE_MAX_HIDDEN = 6
+
+
+class DenseLayer(ctypes.Structure):
+    """struct brn_dense_layer"""
+    _fields_ = [("W", ctypes.c_void_p), ("b", ctypes.c_void_p), ("dW", ctypes.c_void_p), ("db", ctypes.c_void_p),
+                ("n_in", ctypes.c_int32), ("n_out", ctypes.c_int32)]
+
+
+class VaeModel(ctypes.Structure):
+    """struct brn_vae_model"""
+    _fields_ = [("D", ctypes.c_int32), ("L", ctypes.c_int32), ("n_enc", ctypes.c_int32), ("n_dec", ctypes.c_int32),
+                ("sd_offset", ctypes.c_float), ("_pad", ctypes.c_int32),
+                ("enc", DenseLayer * VAE_MAX_HIDDEN), ("enc_mean", DenseLayer), ("enc_sd", DenseLayer),
+                ("dec", DenseLayer * VAE_MAX_HIDDEN), ("dec_out", DenseLayer)]
+
+
 # name -> (restype, argtypes): every symbol include/brancher_cuda.h declares
 SYMBOLS = {
     "brn_abi_version": (ctypes.c_int, []),
@@ -70,6 +87,11 @@ SYMBOLS = {
                                                       ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                       ctypes.c_void_p]),
+    "brn_vae_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(VaeModel), ctypes.c_int, ctypes.c_int]),
+    "brn_vae_elbo_fwd_bwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
+                                            ctypes.POINTER(VaeModel), ctypes.c_void_p, ctypes.c_uint32,
+                                            ctypes.POINTER(SampleRange), ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
+                                            ctypes.c_void_p, ctypes.c_void_p]),
     "brn_svgd_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
     "brn_svgd_direction": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 5 +
                            [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
@@ -309,6 +331,89 @@ def svgd_direction(theta, grad, row0=0, rows=None, bandwidth=None):
     _check(lib().brn_svgd_direction(_ptr(theta, what="theta"), _ptr(grad, what="grad"), n, d, row0, rows, int(update),
                                     _ptr(bw), _ptr(out), ws.data_ptr(), ws.numel(), _stream(dev)), "brn_svgd_direction")
     return out, bw
+
+
+class VaeNet:
+    """Host-side description of `brn_vae_model`: lists of (W [n_out,n_in], b [n_out]) CUDA tensors.
+
+    enc = [(W,b), ...] hidden layers, enc_mean / enc_sd = (W,b) heads; dec = [(W,b), ...] hidden layers, dec_out = (W,b).
+    Gradients (d loss / d W, d loss / d b) are accumulated into `grads`, a dict with the same structure of zeroed
+    tensors (`zero_grads()` makes one flat buffer, so a multi-GPU reduction is a single all-reduce)."""
+
+    def __init__(self, enc, enc_mean, enc_sd, dec, dec_out, sd_offset=0.1):
+        c = lambda wb: (wb[0].detach().contiguous(), wb[1].detach().reshape(-1).contiguous())
+        self.enc, self.dec = [c(l) for l in enc], [c(l) for l in dec]
+        self.enc_mean, self.enc_sd, self.dec_out = c(enc_mean), c(enc_sd), c(dec_out)
+        self.sd_offset = float(sd_offset)
+        if not (1 <= len(self.enc) <= VAE_MAX_HIDDEN and 1 <= len(self.dec) <= VAE_MAX_HIDDEN):
+            raise BrancherCudaError("VAE family: 1..%d hidden layers per network" % VAE_MAX_HIDDEN)
+        self.D = self.enc[0][0].shape[1]
+        self.L = self.enc_mean[0].shape[0]
+        self.flat = None
+        self.grads = None
+
+    def layers(self):
+        return self.enc + [self.enc_mean, self.enc_sd] + self.dec + [self.dec_out]
+
+    def zero_grads(self):
+        dev = self.enc[0][0].device
+        pad = lambda n: (n + 3) // 4 * 4
+        total = sum(pad(W.numel()) + pad(b.numel()) for W, b in self.layers()) + 4
+        if self.flat is None:
+            self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+            self.grads, off = [], 0
+            for W, b in self.layers():
+                gW = self.flat[off:off + W.numel()].view(W.shape); off += pad(W.numel())
+                gb = self.flat[off:off + b.numel()]; off += pad(b.numel())
+                self.grads.append((gW, gb))
+        else:
+            self.flat.zero_()
+        return self.grads
+
+    def struct(self):
+        if self.grads is None:
+            self.zero_grads()
+        m = VaeModel()
+        m.D, m.L, m.n_enc, m.n_dec, m.sd_offset = self.D, self.L, len(self.enc), len(self.dec), self.sd_offset
+
+        def fill(dst, wb, g):
+            W, b = wb
+            dst.W, dst.b = _ptr(W, what="W"), _ptr(b, what="b")
+            dst.dW, dst.db = _ptr(g[0], what="dW"), _ptr(g[1], what="db")
+            dst.n_out, dst.n_in = W.shape
+
+        k = 0
+        for i, wb in enumerate(self.enc):
+            fill(m.enc[i], wb, self.grads[k]); k += 1
+        fill(m.enc_mean, self.enc_mean, self.grads[k]); k += 1
+        fill(m.enc_sd, self.enc_sd, self.grads[k]); k += 1
+        for i, wb in enumerate(self.dec):
+            fill(m.dec[i], wb, self.grads[k]); k += 1
+        fill(m.dec_out, self.dec_out, self.grads[k])
+        return m
+
+
+def vae_elbo_fwd_bwd(X, net, r, eps=None, var_id=0, row0=0, B_total=None, add_constant=True, loss=None):
+    """K5.  X [B,D] fp32 in {0,1}; net: VaeNet (gradients accumulate into net.grads); eps [s_local,B,L] or None (Philox)."""
+    dev = X.device
+    B, D = X.shape
+    if D != net.D:
+        raise BrancherCudaError("X has %d columns, the encoder expects %d" % (D, net.D))
+    B_total = B if B_total is None else B_total
+    loss = torch.zeros(1, dtype=torch.float64, device=dev) if loss is None else loss
+    if eps is not None:
+        eps = eps.detach().to(torch.float32).contiguous()
+        if tuple(eps.shape) != (r.s_local, B, net.L):
+            raise BrancherCudaError("eps has shape %s, expected %s" % (tuple(eps.shape), (r.s_local, B, net.L)))
+    m = net.struct()
+    nbytes = lib().brn_vae_workspace_bytes(ctypes.byref(m), B, r.s_local)
+    if nbytes == 0 and r.s_local > 0:
+        raise BrancherCudaError("brn_vae_workspace_bytes: %s" % lib().brn_last_error().decode())
+    ws = _workspace(dev, nbytes)
+    _check(lib().brn_vae_elbo_fwd_bwd(_ptr(X, what="X"), B, int(row0), int(B_total), ctypes.byref(m), _ptr(eps, what="eps"),
+                                      int(var_id), ctypes.byref(r), ws.data_ptr(), ws.numel(), int(add_constant),
+                                      _ptr(loss, torch.float64), _stream(dev)), "brn_vae_elbo_fwd_bwd")
+    return loss
 
 
 def gemm_nt_3xtf32(A, B):

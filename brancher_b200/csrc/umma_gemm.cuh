@@ -40,6 +40,8 @@ struct UmmaSmem {
 //         grid (J = grid/T slices each) and accumulated with atomics into a caller-zeroed output: a [7 x 128]-unit
 //         problem on 148 CTAs costs 6 + 1/J unit-times instead of 7.
 // mode 1: a CTA keeps its m-tile and strides over n-tiles.
+// mode 2: units m-major (concurrently running CTAs share the A tile: tall-skinny problems whose A operand is the large
+//         one, e.g. [rows x features] activations against a small weight matrix), round-robin, no K split.
 struct UnitIter {
     int m_tiles, n_tiles, k_chunks, mode;
     int u, step, end, mt_fixed;
@@ -47,7 +49,7 @@ struct UnitIter {
     bool has_tail;
     __device__ UnitIter(int m_tiles_, int n_tiles_, int k_chunks_, int mode_, int split_T, int full_units)
         : m_tiles(m_tiles_), n_tiles(n_tiles_), k_chunks(k_chunks_), mode(mode_), tail_u(0), tail_j(0), J(1), has_tail(false) {
-        if (mode == 0) {
+        if (mode == 0 || mode == 2) {
             u = blockIdx.x; step = gridDim.x; end = m_tiles * n_tiles; mt_fixed = -1;
             if (split_T > 0) {
                 end = full_units;
@@ -69,8 +71,8 @@ struct UnitIter {
         else has_tail = false;
     }
     __device__ int unit() const { return u < end ? u : tail_u; }
-    __device__ int mt() const { return mode == 0 ? unit() % m_tiles : mt_fixed; }
-    __device__ int nt() const { return mode == 0 ? unit() / m_tiles : u; }
+    __device__ int mt() const { return mode == 0 ? unit() % m_tiles : (mode == 2 ? unit() / n_tiles : mt_fixed); }
+    __device__ int nt() const { return mode == 0 ? unit() / m_tiles : (mode == 2 ? unit() % n_tiles : u); }
     __device__ int slice() const { return u < end ? 0 : tail_j; }
     __device__ int kc_begin() const { return u < end ? 0 : (int)((long long)tail_j * k_chunks / J); }
     __device__ int kc_end() const { return u < end ? k_chunks : (int)((long long)(tail_j + 1) * k_chunks / J); }
@@ -363,8 +365,8 @@ inline int launch_umma_nt(const float* Ah, const float* Al, int M, int64_t lda, 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int grid, split_T = 0, full_units = m_tiles * n_tiles;
-    if (mode == 0) {
-        const UmmaSplitPlan pl = umma_plan<BN, BK>(M, N, K, sms, allow_split);
+    if (mode == 0 || mode == 2) {
+        const UmmaSplitPlan pl = umma_plan<BN, BK>(M, N, K, sms, allow_split && mode == 0);
         grid = pl.grid; split_T = pl.split_T; full_units = pl.full_units;
     } else {
         int G = sms / m_tiles;

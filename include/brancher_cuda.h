@@ -166,6 +166,47 @@ size_t brn_svgd_workspace_bytes(int n, int d);
 int brn_svgd_direction(const float* theta, const float* grad, int n, int d, int row0, int rows, int update_bandwidth,
                        float* bandwidth, float* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* K5 -- amortised variational auto-encoder (examples/VAE_playground.py:30-80):
+ *   encoder  h_0 = relu(W_0 x + b_0), ..., h_last ; mean = W_mean h_last + b_mean ; sd = softplus(W_sd h_last + b_sd) + sd_offset
+ *   Qz = Normal(mean, sd) (amortised: its parameters are links, not roots), z = mean + sd*eps      (Normal.rsample)
+ *   decoder  g_0 = relu(V_0 z + c_0), ..., g_last ; logits = V_out g_last + c_out ; x ~ Binomial(1, logits)
+ *   p(z) = N(0, 1).  All weights are SHARED by the MC samples (nn.Module parameters, learnable_model=True,
+ *   inference.py:129-139), so the contractions are ordinary [rows x features] GEMMs over rows = s_local * B.
+ * Objective exactly as the reference evaluates it (SURVEY.md 8a'): x is not observed in p => no data-axis sum
+ * (variables.py:513-514) => the estimator's .mean() runs over samples AND rows (gradient_estimators.py:44):
+ *   loss += -(1/(s_total*B_total)) sum_{s local, b local} [ sum_pix (x l - log(1+e^l)) + sum_lat log N(z;0,1)
+ *                                                           + sum_lat (1/2 + log sqrt(2 pi) + log sd_b) ]
+ *           - log(s_total) * (add_constant != 0)      <- H[Qx] of EmpiricalDistribution._get_entropy (distributions.py:464-473)
+ * and every layer's dW / db += d loss / d parameter (partials: rows [row0, row0+B) of B_total and samples
+ * [s0, s0+s_local) of s_total; summing the partials of all ranks gives the full-batch result).
+ * The SAME B rows are used by every MC sample (EmpiricalVariable(indices=...), distributions.py:443-455).
+ * W layout = torch.nn.Linear.weight: [n_out][n_in] row-major.  X [B][D] fp32 in {0,1}.
+ * eps: [s_local][B][L] injected noise or NULL -> Philox (element (row0+b)*L + l of stream var_id, global sample s).
+ * Replaces the graph walk of estimate_log_model_evidence (variables.py:843-870) for this model: _get_sample with
+ * BrancherFunction(nn.Module) links (functions.py:28-41, variables.py:436-449), Normal/Binomial log-probs
+ * (distributions.py:476-490,561-575), analytic entropy (variables.py:156-162) and loss.backward() (inference.py:100). */
+#define BRN_VAE_MAX_HIDDEN 6
+typedef struct brn_dense_layer {
+    const float* W;   /* [n_out][n_in] */
+    const float* b;   /* [n_out]       */
+    float*       dW;  /* += d loss / d W */
+    float*       db;  /* += d loss / d b */
+    int32_t      n_in, n_out;
+} brn_dense_layer;
+typedef struct brn_vae_model {
+    int32_t D, L, n_enc, n_dec;        /* pixels, latent size, hidden layers of encoder / decoder (each >= 1) */
+    float   sd_offset;                 /* 0.1 in the example */
+    int32_t _pad;
+    brn_dense_layer enc[BRN_VAE_MAX_HIDDEN];
+    brn_dense_layer enc_mean, enc_sd;  /* heads: n_out = L */
+    brn_dense_layer dec[BRN_VAE_MAX_HIDDEN];
+    brn_dense_layer dec_out;           /* n_out = D */
+} brn_vae_model;
+size_t brn_vae_workspace_bytes(const brn_vae_model* m, int B, int s_local);
+int brn_vae_elbo_fwd_bwd(const float* X, int B, int64_t row0, int64_t B_total, const brn_vae_model* m,
+                         const float* eps, uint32_t var_id, const brn_sample_range* r,
+                         void* workspace, size_t workspace_bytes, int add_constant, double* loss, void* stream);
+
 /* Tensor-core building block, exposed for validation: D[M][N] = A[M][K] . B[N][K]^T (all row-major fp32)
  * computed with tcgen05.mma kind::tf32 and the 3xTF32 hi/lo split (fp32-equivalent accuracy), TMA-fed.
  * This is the contraction the reference performs as a batched torch.matmul inside _apply_link

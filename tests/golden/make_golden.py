@@ -237,3 +237,5 @@ if __name__ == "__main__":
     scalar_model(zoo.lognormal_normal, "lognormal_normal", S=24, transforms={"nu": torch.exp}, seed=10, N=20)
     scalar_model(zoo.multivariate_regression, "multivariate_regression", S=16, transforms={"nu": torch.exp}, seed=11, n=50)
     svgd_model(8, B=30, F=5, C=3, n=6, tag="svgd_softmax")
+    vae(12, B=6, D=12, L=2, h_enc=(5, 7), h_dec=(7, 5), S=3, tag="vae_small")
+    vae(13, B=10, D=20, L=3, h_enc=(9,), h_dec=(6, 8, 5), S=4, tag="vae_deep")

@@ -64,3 +64,18 @@ def check_against_oracle(got_loss, got_grads, o32, o64, what=""):
         assert_close(a, g64[k], "%s grad %s vs fp64 oracle" % (what, k), scale=sc)
         noise = np.abs(np.asarray(g32[k], dtype=np.float64) - g64[k]).max()
         assert_close(a, g32[k], "%s grad %s vs fp32 oracle" % (what, k), atol=ATOL + 2 * noise / sc, scale=sc)
+
+
+def vae_nets(g):
+    """(enc, dec) dicts in the oracle's / C-ABI's layout from golden 'param_enc.*' / 'param_dec.*' entries."""
+    nets = {"enc": {"W": [], "b": []}, "dec": {"W": [], "b": []}}
+    for k in sorted(g["param"]):
+        side, rest = k.split(".", 1)
+        if rest.startswith(("W.", "b.")):
+            nets[side][rest[0]].append((int(rest[2:]), g["param"][k]))
+        else:
+            nets[side][rest] = g["param"][k]
+    for side in nets:
+        for wb in ("W", "b"):
+            nets[side][wb] = [a for _, a in sorted(nets[side][wb], key=lambda t: t[0])]
+    return nets["enc"], nets["dec"]
