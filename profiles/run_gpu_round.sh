@@ -1,17 +1,22 @@
 #!/bin/bash
 # One gpurun call: GPU parity tests, bench lines per workload, ncu launch list and one --set full capture per top kernel.
-# usage (from the repo root, under gpurun):  bash profiles/run_gpu_round.sh <tag>
+# usage (from the repo root, under gpurun):  bash profiles/run_gpu_round.sh <tag> [quick]
 TAG=${1:-r1x}
+MODE=${2:-full}
 O=gpurun_out
 mkdir -p $O
-timeout 900 python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest_gpu.txt 2>&1; echo "pytest rc=$?" >> $O/${TAG}_pytest_gpu.txt
+timeout 1200 python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest_gpu.txt 2>&1; echo "pytest rc=$?" >> $O/${TAG}_pytest_gpu.txt
 tail -3 $O/${TAG}_pytest_gpu.txt
-for wl in bnn logreg svgd; do
+for wl in bnn logreg svgd vae; do
   timeout 600 python bench.py --workload $wl --steps 50 --warmup 5 > $O/${TAG}_bench_$wl.json 2> $O/${TAG}_bench_$wl.err
-  tail -c 600 $O/${TAG}_bench_$wl.json
+  tail -c 900 $O/${TAG}_bench_$wl.json
 done
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches_bnn.csv \
-  python bench.py --workload bnn --steps 5 --warmup 3 --no-cpu-baseline > $O/${TAG}_ncu_bnn.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'umma_nt|bnn_mid' -s 8 -c 3 -f -o $O/${TAG}_prof_bnn \
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $O/${TAG}_bench_reference.json 2>&1
+[ "$MODE" = quick ] && exit 0
+for wl in bnn vae; do
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches_$wl.csv \
+  python bench.py --workload $wl --steps 5 --warmup 3 --no-cpu-baseline > $O/${TAG}_ncu_$wl.log 2>&1
+done
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'umma_nt|bnn_mid|sample_w1|mf_stats' -s 12 -c 6 -f -o $O/${TAG}_prof_bnn \
   python bench.py --workload bnn --steps 3 --warmup 3 --no-cpu-baseline > $O/${TAG}_ncu_full_bnn.log 2>&1
 ls -la $O
