@@ -11,6 +11,7 @@
 #include "sgemm.cuh"
 #include "umma_gemm.cuh"
 #include <stdlib.h>
+#include <type_traits>
 
 namespace brn {
 
@@ -643,6 +644,347 @@ static int launch_mid3(const float* pre, const float* W, float* dW, const int32_
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// "mid" stage of the tcgen05 variant on the warp-level tensor cores (mma.sync m16n8k8 tf32, 3xTF32 split): the three
+// small per-sample contractions of layer 2 are matrix products with one tiny dimension (C <= 16),
+//   A  a[b, c]    = sum_h h[b, h] W2[c, h]           M = rows,  N = 16 classes, K = HP hidden
+//   B  dh[b, h]   = sum_c da[b, c] W2[c, h]          M = rows,  N = HP hidden,  K = 16 classes
+//   C  dW2[c, h]  = sum_b da[b, c] h[b, h]           M = 16 classes, N = HP hidden, K = 128 rows
+// and cost ~10 k thread instructions per row as scalar FMAs (bnn_mid3_kernel: issue-bound, 140 us at C3).  Here one CTA
+// = 128 batch rows of one sample, 8 warps, warp w = rows [16w, 16w+16) = one MMA m-tile.  The fragment layouts are
+// chained without any shuffles by permuting the contraction index: the k-columns (t, t+4) of an A fragment are mapped
+// to the consecutive pair (2t, 2t+1) of hidden units (phase A) / classes (phase B), which is exactly how the C fragment
+// of the previous product holds them.  Only phase C needs transposed operands and goes through shared memory
+// (tile[h][b] pitch 132, das[b][c] pitch 24: both conflict-free for the fragment loads).
+// Accuracy: fp32-equivalent via the 3-product split; the hi*hi products and the two correction products accumulate in
+// separate chains of at most 16 MMAs.
+// ---------------------------------------------------------------------------------------------------
+constexpr int MID4_R = 128, MID4_TP = 132, MID4_DP = 24, MID4_THREADS = 256;
+
+template <int HP>
+struct Mid4Smem {
+    static constexpr int KS = HP / 8;
+    // offsets in floats (all multiples of 4)
+    static constexpr size_t fragA = 0;                                    // [KS][2][32] float4
+    static constexpr size_t fragB = fragA + (size_t)KS * 2 * 32 * 4;      // [KS][2][32] float4
+    static constexpr size_t tile = fragB + (size_t)KS * 2 * 32 * 4;       // [HP][132]
+    static constexpr size_t das = tile + (size_t)HP * MID4_TP;            // [128][24] TF32 hi part of da
+    static constexpr size_t das_lo = das + (size_t)MID4_R * MID4_DP;      // [128][24]
+    static constexpr size_t b1 = das_lo + (size_t)MID4_R * MID4_DP;       // [HP]
+    static constexpr size_t db1 = b1 + HP;                                // [8 warps][HP] per-warp column sums of dpre
+    static constexpr size_t b2 = db1 + 8 * HP;                            // [16]
+    static constexpr size_t total = b2 + 16;
+};
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const float (&a)[4], float b0, float b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
+          "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+
+// tanh with ~1e-7 absolute error, 13 issue slots, branch-free: odd polynomial below 0.25 (truncation < 1e-8 relative),
+// 1 - 2 / (1 + e^{2x}) above (ex2.approx / rcp.approx: absolute error ~2e-7 on a value >= 0.24).
+__device__ __forceinline__ float tanh_fast(float x) {
+    const float x2 = x * x;
+    float p = 0.021869488536155203f;                 //  62/2835
+    p = __fmaf_rn(p, x2, -0.053968253968253971f);    // -17/315
+    p = __fmaf_rn(p, x2, 0.13333333333333333f);      //   2/15
+    p = __fmaf_rn(p, x2, -0.33333333333333333f);     //  -1/3
+    const float small = __fmaf_rn(x * x2, p, x);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));
+    const float big = 1.f - __fdividef(2.f, 1.f + e);
+    return fabsf(x) < 0.25f ? small : big;
+}
+
+// hi = x rounded to TF32; lo = the exact remainder, NOT re-rounded: mma.sync reads only the TF32 bits of an operand
+// register, i.e. truncates lo (relative error <= 2^-21 of x, sign uncorrelated with x) -- used for mma.sync operands only.
+__device__ __forceinline__ void split_tf32_trunc_lo(float x, float& hi, float& lo) {
+    hi = umma::rn_tf32(x);
+    lo = x - hi;
+}
+
+template <int HP, bool FULL>      // FULL: B is a multiple of 128 (no row guards anywhere)
+__global__ void __launch_bounds__(MID4_THREADS, 2)
+bnn_mid4_kernel(const float* __restrict__ pre, const float* __restrict__ W, float* __restrict__ dW,
+                const int32_t* __restrict__ y, BnnLayout L, float inv_S, double* __restrict__ loss,
+                float* __restrict__ dpT_hi, float* __restrict__ dpT_lo, int64_t ldB) {
+    using M = Mid4Smem<HP>;
+    constexpr int KS = M::KS;
+    extern __shared__ __align__(16) float sm[];
+    float4* fragA = reinterpret_cast<float4*>(sm + M::fragA);
+    float4* fragB = reinterpret_cast<float4*>(sm + M::fragB);
+    float* tile = sm + M::tile;
+    float* das_hi = sm + M::das;
+    float* das_lo = sm + M::das_lo;
+    float* b1s = sm + M::b1;
+    float* db1s = sm + M::db1;
+    float* b2s = sm + M::b2;
+    __shared__ double red[32];
+
+    const int H = L.H, C = L.C, B = L.B;
+    const int s = blockIdx.y, b0 = blockIdx.x * MID4_R, tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const float* Ws = W + (int64_t)s * L.ldw;
+    float* dWs = dW + (int64_t)s * L.ldw;
+    const float* W2 = Ws + L.oW2;
+
+    // ---- phase A loads first (their latency overlaps the weight staging): pre[h][row] for this thread's 2 rows x 2*KS
+    // hidden units.  Rows >= B and hidden units >= H are CLAMPED to valid addresses, not masked: invalid rows get da = 0
+    // below, and hidden units >= H meet zero weights in both fragment sets and are never stored.
+    const int r0 = 16 * warp + g, r1 = r0 + 8;                 // this thread's two rows inside the CTA block
+    const bool ok0 = FULL || b0 + r0 < B, ok1 = FULL || b0 + r1 < B;
+    float hA[KS][4];
+    {
+        const float* pc0 = pre + (int64_t)s * B * H + (ok0 ? b0 + r0 : B - 1);
+        const float* pc1 = pre + (int64_t)s * B * H + (ok1 ? b0 + r1 : B - 1);
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+            const int h0 = min(8 * k + 2 * t, H - 1), h1 = min(8 * k + 2 * t + 1, H - 1);
+            hA[k][0] = pc0[(int64_t)h0 * B];
+            hA[k][1] = pc1[(int64_t)h0 * B];
+            hA[k][2] = pc0[(int64_t)h1 * B];
+            hA[k][3] = pc1[(int64_t)h1 * B];
+        }
+    }
+
+    // ---- stage the per-sample layer-2 weights as ready-made (hi, lo) B fragments
+    for (int idx = tid; idx < KS * 2 * 32; idx += MID4_THREADS) {
+        const int ln = idx & 31, q = (idx >> 5) & 1, k = idx >> 6, gg = ln >> 2, tt = ln & 3;
+        {   // phase A: B[k = hidden, n = class]: b0 = W2[8q + g][8k + 2t], b1 = W2[8q + g][8k + 2t + 1]
+            const int c = 8 * q + gg, h0 = 8 * k + 2 * tt;
+            const float w0 = (c < C && h0 < H) ? W2[(int64_t)c * H + h0] : 0.f;
+            const float w1 = (c < C && h0 + 1 < H) ? W2[(int64_t)c * H + h0 + 1] : 0.f;
+            float4 f;
+            umma::split_tf32(w0, f.x, f.z);
+            umma::split_tf32(w1, f.y, f.w);
+            fragA[idx] = f;
+        }
+        {   // phase B: B[k = class, n = hidden]: b0 = W2[8q + 2t][8k + g], b1 = W2[8q + 2t + 1][8k + g]   (k = n-tile j)
+            const int c0 = 8 * q + 2 * tt, h = 8 * k + gg;
+            const float w0 = (c0 < C && h < H) ? W2[(int64_t)c0 * H + h] : 0.f;
+            const float w1 = (c0 + 1 < C && h < H) ? W2[(int64_t)(c0 + 1) * H + h] : 0.f;
+            float4 f;
+            umma::split_tf32(w0, f.x, f.z);
+            umma::split_tf32(w1, f.y, f.w);
+            fragB[idx] = f;
+        }
+    }
+    for (int idx = tid; idx < HP; idx += MID4_THREADS) b1s[idx] = idx < H ? Ws[L.ob1 + idx] : 0.f;
+    if (tid < 16) b2s[tid] = tid < C ? Ws[L.ob2 + tid] : 0.f;
+    __syncthreads();
+
+    // ---- phase A: h = tanh(pre + b1) (kept in A-fragment registers and in the smem tile), a = h W2^T
+    float ahh[2][4], acr[2][4];
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ahh[q][i] = acr[q][i] = 0.f;
+    {
+        float* tp = tile + (2 * t) * MID4_TP + r0;
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+            const float2 bb = *reinterpret_cast<const float2*>(b1s + 8 * k + 2 * t);
+            float hi[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float v = tanh_fast(hA[k][i] + (i < 2 ? bb.x : bb.y));
+                hA[k][i] = v;
+                split_tf32_trunc_lo(v, hi[i], lo[i]);
+            }
+            tp[k * 8 * MID4_TP] = hA[k][0];
+            tp[k * 8 * MID4_TP + 8] = hA[k][1];
+            tp[k * 8 * MID4_TP + MID4_TP] = hA[k][2];
+            tp[k * 8 * MID4_TP + MID4_TP + 8] = hA[k][3];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const float4 f = fragA[(k * 2 + q) * 32 + lane];
+                mma_tf32(ahh[q], hi, f.x, f.y);
+                mma_tf32(acr[q], lo, f.x, f.y);
+                mma_tf32(acr[q], hi, f.z, f.w);
+            }
+        }
+    }
+
+    // ---- log-softmax over the classes: row r0 holds classes {2t, 2t+1, 8+2t, 9+2t} in a[q][0..1], row r1 in a[q][2..3]
+    float dahi[2][4], dalo[2][4];            // phase-B A fragments: (r0, class 2t), (r1, 2t), (r0, 2t+1), (r1, 2t+1)
+    float ll = 0.f;
+    {
+        const int lab0 = ok0 ? y[b0 + r0] : -1, lab1 = ok1 ? y[b0 + r1] : -1;
+        float a[2][4];
+        float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int c = 8 * q + 2 * t + (i & 1);
+                a[q][i] = c < C ? ahh[q][i] + acr[q][i] + b2s[c] : -INFINITY;
+                if (i < 2) m0 = fmaxf(m0, a[q][i]);
+                else m1 = fmaxf(m1, a[q][i]);
+            }
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+        float ex[2][4];
+        float se0 = 0.f, se1 = 0.f;
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                ex[q][i] = expf(a[q][i] - (i < 2 ? m0 : m1));            // exp(-inf) = 0 for the pad classes
+                if (i < 2) se0 += ex[q][i];
+                else se1 += ex[q][i];
+            }
+        se0 += __shfl_xor_sync(0xffffffffu, se0, 1); se0 += __shfl_xor_sync(0xffffffffu, se0, 2);
+        se1 += __shfl_xor_sync(0xffffffffu, se1, 1); se1 += __shfl_xor_sync(0xffffffffu, se1, 2);
+        const float lse0 = m0 + logf(se0), lse1 = m1 + logf(se1);
+        const float inv0 = 1.f / se0, inv1 = 1.f / se1;
+        float da[2][4];
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int c = 8 * q + 2 * t + (i & 1);
+                const bool ok = (i < 2 ? ok0 : ok1) && c < C;
+                const int lab = i < 2 ? lab0 : lab1;
+                const float lse = i < 2 ? lse0 : lse1;
+                const float sm_ = ex[q][i] * (i < 2 ? inv0 : inv1);
+                da[q][i] = ok ? (c == lab ? 1.f : 0.f) - sm_ : 0.f;              // d ll / d a_c
+                if (ok && c == lab) ll += a[q][i] - lse;
+            }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            split_tf32_trunc_lo(da[q][0], dahi[q][0], dalo[q][0]);
+            split_tf32_trunc_lo(da[q][2], dahi[q][1], dalo[q][1]);
+            split_tf32_trunc_lo(da[q][1], dahi[q][2], dalo[q][2]);
+            split_tf32_trunc_lo(da[q][3], dahi[q][3], dalo[q][3]);
+            *reinterpret_cast<float2*>(das_hi + r0 * MID4_DP + 8 * q + 2 * t) = make_float2(dahi[q][0], dahi[q][2]);
+            *reinterpret_cast<float2*>(das_hi + r1 * MID4_DP + 8 * q + 2 * t) = make_float2(dahi[q][1], dahi[q][3]);
+            *reinterpret_cast<float2*>(das_lo + r0 * MID4_DP + 8 * q + 2 * t) = make_float2(dalo[q][0], dalo[q][2]);
+            *reinterpret_cast<float2*>(das_lo + r1 * MID4_DP + 8 * q + 2 * t) = make_float2(dalo[q][1], dalo[q][3]);
+        }
+    }
+
+    // ---- phase B: dh = da W2, dpre = dh (1 - h^2) -> TF32 split, transposed store; db1 column sums
+    {
+        // output pointers walk down the hidden axis: element (h0 = 2t [+1], row r0 [+8]) of this sample's block
+        float* ohi0 = dpT_hi + ((int64_t)s * HP + 2 * t) * ldB + b0 + r0;
+        float* olo0 = dpT_lo + ((int64_t)s * HP + 2 * t) * ldB + b0 + r0;
+        float* ohi1 = ohi0 + ldB;
+        float* olo1 = olo0 + ldB;
+        const int64_t step = 8 * ldB;
+#pragma unroll
+        for (int j = 0; j < KS; ++j) {
+            float dhh[4] = {0.f, 0.f, 0.f, 0.f}, dcr[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const float4 f = fragB[(j * 2 + q) * 32 + lane];
+                mma_tf32(dhh, dahi[q], f.x, f.y);
+                mma_tf32(dcr, dalo[q], f.x, f.y);
+                mma_tf32(dcr, dahi[q], f.z, f.w);
+            }
+            // C fragment: (r0, h0), (r0, h0+1), (r1, h0), (r1, h0+1) with h0 = 8j + 2t  <->  hA[j][0], [2], [1], [3]
+            const int h0 = 8 * j + 2 * t;
+            float dp[4];
+            dp[0] = (dhh[0] + dcr[0]) * __fmaf_rn(-hA[j][0], hA[j][0], 1.f);
+            dp[1] = (dhh[1] + dcr[1]) * __fmaf_rn(-hA[j][2], hA[j][2], 1.f);
+            dp[2] = (dhh[2] + dcr[2]) * __fmaf_rn(-hA[j][1], hA[j][1], 1.f);
+            dp[3] = (dhh[3] + dcr[3]) * __fmaf_rn(-hA[j][3], hA[j][3], 1.f);
+            float hi[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) umma::split_tf32(dp[i], hi[i], lo[i]);
+            // hidden units >= H: dp == 0 there (zero fragB weights) and the pad rows of dpT exist -> no guard needed
+            if (ok0) { ohi0[0] = hi[0]; olo0[0] = lo[0]; ohi1[0] = hi[1]; olo1[0] = lo[1]; }
+            if (ok1) { ohi0[8] = hi[2]; olo0[8] = lo[2]; ohi1[8] = hi[3]; olo1[8] = lo[3]; }
+            ohi0 += step; olo0 += step; ohi1 += step; olo1 += step;
+            float c0 = dp[0] + dp[2], c1 = dp[1] + dp[3];        // column sums over this warp's 16 rows
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+                c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+                c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+            }
+            if (g == 0) *reinterpret_cast<float2*>(db1s + warp * HP + h0) = make_float2(c0, c1);   // per-warp partial
+        }
+    }
+    __syncthreads();
+
+    // ---- phase C: dW2[c, h] = sum_b da[b, c] h[b, h] over the CTA's 128 rows; warp w owns hidden n-tiles w and w + 8
+    auto phase_c = [&](auto ntag) {
+        constexpr int NT = decltype(ntag)::value;
+        float chh[NT][4], ccr[NT][4];
+#pragma unroll
+        for (int q = 0; q < NT; ++q)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) chh[q][i] = ccr[q][i] = 0.f;
+        const float* dh_ = das_hi + t * MID4_DP + g;
+        const float* dl_ = das_lo + t * MID4_DP + g;
+        const float* tb = tile + (8 * warp + g) * MID4_TP + t;
+#pragma unroll 4
+        for (int kb = 0; kb < MID4_R / 8; ++kb) {
+            // A = da^T: (class g, row 8kb+t), (class g+8, row 8kb+t), (class g, row 8kb+t+4), (class g+8, row 8kb+t+4)
+            float ahi[4], alo[4];
+            ahi[0] = dh_[kb * 8 * MID4_DP];
+            ahi[1] = dh_[kb * 8 * MID4_DP + 8];
+            ahi[2] = dh_[(kb * 8 + 4) * MID4_DP];
+            ahi[3] = dh_[(kb * 8 + 4) * MID4_DP + 8];
+            alo[0] = dl_[kb * 8 * MID4_DP];
+            alo[1] = dl_[kb * 8 * MID4_DP + 8];
+            alo[2] = dl_[(kb * 8 + 4) * MID4_DP];
+            alo[3] = dl_[(kb * 8 + 4) * MID4_DP + 8];
+#pragma unroll
+            for (int q = 0; q < NT; ++q) {
+                float bh0, bl0, bh1, bl1;
+                split_tf32_trunc_lo(tb[q * 64 * MID4_TP + kb * 8], bh0, bl0);          // B = h: (row 8kb+t, hidden 8j+g)
+                split_tf32_trunc_lo(tb[q * 64 * MID4_TP + kb * 8 + 4], bh1, bl1);
+                mma_tf32(chh[q], ahi, bh0, bh1);
+                mma_tf32(ccr[q], alo, bh0, bh1);
+                mma_tf32(ccr[q], ahi, bl0, bl1);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NT; ++q) {
+            const int h0 = 8 * (warp + 8 * q) + 2 * t;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int c = g + (i >= 2 ? 8 : 0), h = h0 + (i & 1);
+                if (c < C && h < H) atomicAdd(&dWs[L.oW2 + (int64_t)c * H + h], chh[q][i] + ccr[q][i]);
+            }
+        }
+    };
+    if (warp + 8 < KS) phase_c(std::integral_constant<int, 2>());
+    else if (warp < KS) phase_c(std::integral_constant<int, 1>());
+    if (warp == 7 && lane < C) {
+        float acc = 0.f;
+        for (int rr = 0; rr < MID4_R; ++rr) acc += das_hi[rr * MID4_DP + lane] + das_lo[rr * MID4_DP + lane];
+        atomicAdd(&dWs[L.ob2 + lane], acc);
+    }
+    for (int idx = tid; idx < H; idx += MID4_THREADS) {
+        float acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < MID4_THREADS / 32; ++w) acc += db1s[w * HP + idx];
+        atomicAdd(&dWs[L.ob1 + idx], acc);
+    }
+    double tot = block_sum<double>((double)ll, red);
+    if (tid == 0) atomicAdd(loss, -tot * (double)inv_S);
+}
+
+template <int HP>
+static int launch_mid4(const float* pre, const float* W, float* dW, const int32_t* y, const BnnLayout& L, int S, float inv_S,
+                       double* loss, float* dph, float* dpl, int64_t ldB, cudaStream_t stream) {
+    const size_t smem = Mid4Smem<HP>::total * sizeof(float);
+    dim3 grid((L.B + MID4_R - 1) / MID4_R, S);
+    if (L.B % MID4_R == 0) {
+        BRN_CUDA_OK(cudaFuncSetAttribute(bnn_mid4_kernel<HP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        bnn_mid4_kernel<HP, true><<<grid, MID4_THREADS, smem, stream>>>(pre, W, dW, y, L, inv_S, loss, dph, dpl, ldB);
+    } else {
+        BRN_CUDA_OK(cudaFuncSetAttribute(bnn_mid4_kernel<HP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        bnn_mid4_kernel<HP, false><<<grid, MID4_THREADS, smem, stream>>>(pre, W, dW, y, L, inv_S, loss, dph, dpl, ldB);
+    }
+    BRN_LAUNCH_OK("bnn_mid4_kernel");
+    return 0;
+}
+
 static size_t bnn_mid_smem(int R, int H, int C) {
     return sizeof(float) * ((size_t)R * (H + 1) + (size_t)C * H + H + C + (size_t)R * C);
 }
@@ -785,7 +1127,11 @@ extern "C" int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int
         const float inv_S = 1.0f / (float)r->s_total;
         const MidSmem ms(H, C);
         const size_t smem2 = ms.total * sizeof(float);
-        if (use_tc) {
+        bool mid4 = true;        // BRN_BNN_MID=3 selects the scalar-FMA kernel (kept for A/B measurements and tests)
+        if (const char* env = getenv("BRN_BNN_MID")) mid4 = atoi(env) != 3;
+        if (use_tc && mid4) {
+            if (int e = launch_mid4<HP>(ws.pre, ws.W, ws.dW, y, L, S, inv_S, loss, ws.dph, ws.dpl, ws.ldB, stream)) return e;
+        } else if (use_tc) {
             int e = 0;
             if (C <= 4) e = launch_mid3<4>(ws.pre, ws.W, ws.dW, y, L, S, inv_S, loss, ws.dph, ws.dpl, HP, ws.ldB, stream);
             else if (C <= 8) e = launch_mid3<8>(ws.pre, ws.W, ws.dW, y, L, S, inv_S, loss, ws.dph, ws.dpl, HP, ws.ldB, stream);

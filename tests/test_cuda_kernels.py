@@ -240,9 +240,12 @@ def test_linear_empty_rows(cu):
                                        (257, 130, 97, 16, 5), (1024, 784, 100, 10, 4), (40, 33, 21, 3, 1),
                                        (130, 37, 5, 2, 4)])
 @pytest.mark.parametrize("tied", [True, False])
-def test_bnn_tcgen05_variant(cu, monkeypatch, B, P, H, C, S, tied):
+@pytest.mark.parametrize("mid", ["4", "3"])
+def test_bnn_tcgen05_variant(cu, monkeypatch, B, P, H, C, S, tied, mid):
+    """mid = 4: layer 2 on the warp-level tensor cores (mma.sync 3xTF32, default); 3: the scalar-FMA kernel."""
     from oracle import elbo_oracle as O
     monkeypatch.setenv("BRN_BNN_VARIANT", "tcgen05")
+    monkeypatch.setenv("BRN_BNN_MID", mid)
     X, y, params, eps, shapes = random_bnn(B * 3 + H, B, P, H, C, S)
     prior = None if tied else {n: (0.0, 10.0) for n in shapes}
     o32 = O.bnn_elbo(X, y, params, eps, prior)
