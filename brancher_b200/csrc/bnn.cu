@@ -203,7 +203,8 @@ sample_w1_fused_kernel(const float* __restrict__ mu, const float* __restrict__ s
             Normal4 n = philox_normal4(r.seed, r.offset, var_id, (uint32_t)(r.s0 + s), (uint32_t)(i >> 2));
             e = make_float4(n.v[0], n.v[1], n.v[2], n.v[3]);
         }
-        *reinterpret_cast<float4*>(eps_out + (int64_t)s * lde_out + i) = e;     // stage 5 reads all noise from the workspace
+        // stage 5 reads injected noise from the workspace; Philox noise is regenerated there instead (eps_out == NULL)
+        if (eps_out) *reinterpret_cast<float4*>(eps_out + (int64_t)s * lde_out + i) = e;
         const float4 m = *reinterpret_cast<const float4*>(mu + i);
         const float4 sg = *reinterpret_cast<const float4*>(sigma + i);
         umma::split_tf32(__fmaf_rn(sg.x, e.x, m.x), vh.x, vl.x);
@@ -1070,8 +1071,11 @@ extern "C" int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int
     int drain = 2;
     if (const char* env = getenv("BRN_UMMA_DRAIN")) drain = atoi(env);
 
-    // 1. noise + weights.  All noise (injected or Philox) ends up in ws.eps [S][ldw] and all sampled weights in ws.W,
-    //    the four variables back to back inside a row, so stage 5 is one launch over the concatenated range.
+    // 1. noise + weights.  Noise ends up in ws.eps [S][ldw] and all sampled weights in ws.W, the four variables back to
+    //    back inside a row, so stage 5 is one launch over the concatenated range.  Optional (tcgen05 variant, Philox
+    //    mode, BRN_BNN_REGEN_EPS=1): the layer-1 noise (98.6 % of the elements) is never stored -- stage 5 regenerates it
+    //    from the same Philox counters (80 MB less written and read per evaluation at the C3 size).
+    int64_t regen_numel0 = 0;
     {
         StageTimer st("bnn.sample_weights", stream);
         if (use_tc) {
@@ -1081,8 +1085,15 @@ extern "C" int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int
                 softplus_kernel<<<(unsigned)((numels[0] + 255) / 256), 256, 0, stream>>>(vars[0].rho, ws.sigma, numels[0]);
                 BRN_LAUNCH_OK("softplus_kernel");
                 dim3 grid((unsigned)(((int64_t)H * P / 4 + 255) / 256), S);
-                sample_w1_fused_kernel<<<grid, 256, 0, stream>>>(vars[0].mu, ws.sigma, vars[0].eps, numels[0], ws.eps + offs[0],
-                                                                 L.ldw, ws.Wh, ws.Wl, H, P, HP, ws.ldP, *r, vars[0].var_id);
+                // BRN_BNN_REGEN_EPS=1: do not store the Philox noise of layer 1, regenerate it in stage 5.  Measured on B200
+                // (profiles/r1e_*): the sampler is issue-bound, not write-bound (47 us either way) and the regenerating
+                // stats kernel is 5 us slower, so storing stays the default; the switch saves 80 MB of workspace.
+                const char* rg = getenv("BRN_BNN_REGEN_EPS");
+                const bool regen = !vars[0].eps && rg && atoi(rg);
+                if (regen) regen_numel0 = numels[0];
+                sample_w1_fused_kernel<<<grid, 256, 0, stream>>>(vars[0].mu, ws.sigma, vars[0].eps, numels[0],
+                                                                 regen ? nullptr : ws.eps + offs[0], L.ldw, ws.Wh, ws.Wl, H, P,
+                                                                 HP, ws.ldP, *r, vars[0].var_id);
                 BRN_LAUNCH_OK("sample_w1_fused_kernel");
             } else {
                 if (vars[0].eps)
@@ -1190,7 +1201,7 @@ extern "C" int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int
     // 5. reduce over samples + prior/entropy + chain rule: one stats launch + one finalize launch for all four variables
     StageTimer st5("bnn.reduce_finalize", stream);
     if (int e = launch_mf_reduce_finalize_multi(vars, offs, 4, L.numel, ws.eps, L.ldw, ws.dW, L.ldw, ws.stats, *r, with_prior, loss,
-                                                stream))
+                                                stream, regen_numel0))
         return e;
     return 0;
 }

@@ -169,10 +169,15 @@ extern "C" int brn_dag_elbo_fwd_bwd(const brn_dag_op* ops, int n_ops, int n_slot
     set_variant("simt");
     StageTimer st("dag.fused", stream);
     const int64_t total = (int64_t)r->s_local * n_rows;
-    const unsigned grid = (unsigned)((total + 127) / 128);
+    // The value/adjoint arrays live in thread-local memory (2 * n_slots lines of 128 B per warp).  Small problems (the
+    // README AR(1): 300 samples) run ONE WARP PER CTA so that (a) the work spreads over as many SMs as there are warps and
+    // (b) each SM's L1 holds its warp's whole local frame -- with 128-thread CTAs the frame of ~700 slots spilled to L2 and
+    // every interpreted op paid an L2 round trip (563 us per evaluation, measured; profiles/r1e_bench_ar1.json).
+    const int block = total <= (int64_t)32 * 148 * 8 ? 32 : 128;
+    const unsigned grid = (unsigned)((total + block - 1) / block);
     const size_t smem = sizeof(float) * (size_t)(n_params > 0 ? n_params : 1);
 #define BRN_DAG_LAUNCH(MAXS)                                                                                             \
-    dag_elbo_kernel<MAXS><<<grid, 128, smem, stream>>>(ops, n_ops, n_slots, params, n_params, data, n_cols, n_rows, eps, \
+    dag_elbo_kernel<MAXS><<<grid, block, smem, stream>>>(ops, n_ops, n_slots, params, n_params, data, n_cols, n_rows, eps, \
                                                        n_eps, *r, dparams, loss)
     if (n_slots <= 128) BRN_DAG_LAUNCH(128);
     else if (n_slots <= 512) BRN_DAG_LAUNCH(512);

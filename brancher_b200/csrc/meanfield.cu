@@ -170,7 +170,8 @@ constexpr int MF_SCHUNK = 16;     // samples per block
 
 __global__ void __launch_bounds__(128)
 mf_stats_kernel(const float* __restrict__ eps, int64_t lde, const float* __restrict__ dW, int64_t ldd, int64_t numel,
-                int64_t npad, brn_sample_range r, uint32_t var_id, int vec, float* __restrict__ stats) {
+                int64_t npad, brn_sample_range r, uint32_t var_id, int vec, int64_t philox_quads,
+                float* __restrict__ stats) {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q * 4 >= numel) return;
     const int s_begin = blockIdx.y * MF_SCHUNK, s_end = min(r.s_local, s_begin + MF_SCHUNK);
@@ -180,7 +181,7 @@ mf_stats_kernel(const float* __restrict__ eps, int64_t lde, const float* __restr
 #pragma unroll 8
     for (int s = s_begin; s < s_end; ++s) {
         float e[4], d[4] = {0.f, 0.f, 0.f, 0.f};
-        if (eps) {
+        if (eps && q >= philox_quads) {     // quads below philox_quads are regenerated (never stored): same counters as the sampler
             if (vec) {
                 float4 t = *reinterpret_cast<const float4*>(eps + (int64_t)s * lde + q * 4);
                 e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w;
@@ -268,7 +269,7 @@ int launch_mf_reduce_finalize(const brn_mf_var& var, const float* eps, int64_t l
         const int vec = (!eps || (((uintptr_t)eps % 16 == 0) && lde % 4 == 0)) &&
                         (!dW || (((uintptr_t)dW % 16 == 0) && ldd % 4 == 0));
         dim3 grid((unsigned)((quads + 127) / 128), (unsigned)((r.s_local + MF_SCHUNK - 1) / MF_SCHUNK));
-        mf_stats_kernel<<<grid, 128, 0, stream>>>(eps, lde, dW, ldd, var.numel, npad, r, var.var_id, vec, stats);
+        mf_stats_kernel<<<grid, 128, 0, stream>>>(eps, lde, dW, ldd, var.numel, npad, r, var.var_id, vec, 0, stats);
         BRN_LAUNCH_OK("mf_stats_kernel");
     }
     mf_finalize2_kernel<<<(unsigned)((var.numel + 255) / 256), 256, 0, stream>>>(var, stats, npad, r, with_prior, loss);
@@ -330,7 +331,13 @@ mf_finalize_multi_kernel(MfMulti m, const float* __restrict__ stats, int64_t npa
 
 int launch_mf_reduce_finalize_multi(const brn_mf_var* vars, const int64_t* offs, int nvars, int64_t total, const float* eps,
                                     int64_t lde, const float* dW, int64_t ldd, float* stats, const brn_sample_range& r,
-                                    int with_prior, double* loss, cudaStream_t stream) {
+                                    int with_prior, double* loss, cudaStream_t stream, int64_t philox_numel0) {
+    // philox_numel0 > 0: the noise of the first philox_numel0 elements (variable 0, which must start at offset 0) was
+    // never stored -- the stats kernel regenerates it from the same Philox counters the sampler used.
+    if (philox_numel0 > 0 && (offs[0] != 0 || philox_numel0 % 4 != 0 || philox_numel0 > vars[0].numel)) {
+        set_error("launch_mf_reduce_finalize_multi: bad regenerated-noise range %lld", (long long)philox_numel0);
+        return -1;
+    }
     if (nvars <= 0 || nvars > 4 || total <= 0) { set_error("launch_mf_reduce_finalize_multi: bad variable count %d", nvars); return -1; }
     const int64_t npad = (total + 3) / 4 * 4;
     BRN_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(float) * 4 * npad, stream));
@@ -338,7 +345,7 @@ int launch_mf_reduce_finalize_multi(const brn_mf_var* vars, const int64_t* offs,
         const int64_t quads = npad / 4;
         const int vec = (((uintptr_t)eps % 16 == 0) && lde % 4 == 0) && (!dW || (((uintptr_t)dW % 16 == 0) && ldd % 4 == 0));
         dim3 grid((unsigned)((quads + 127) / 128), (unsigned)((r.s_local + MF_SCHUNK - 1) / MF_SCHUNK));
-        mf_stats_kernel<<<grid, 128, 0, stream>>>(eps, lde, dW, ldd, total, npad, r, 0u, vec, stats);
+        mf_stats_kernel<<<grid, 128, 0, stream>>>(eps, lde, dW, ldd, total, npad, r, vars[0].var_id, vec, philox_numel0 / 4, stats);
         BRN_LAUNCH_OK("mf_stats_kernel");
     }
     MfMulti m;

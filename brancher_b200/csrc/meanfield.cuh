@@ -32,7 +32,7 @@ int launch_mf_reduce_finalize(const brn_mf_var& var, const float* eps, int64_t l
 // variable inside a row, `total` = end of the last one): one stats launch + one finalize launch.
 int launch_mf_reduce_finalize_multi(const brn_mf_var* vars, const int64_t* offs, int nvars, int64_t total, const float* eps,
                                     int64_t lde, const float* dW, int64_t ldd, float* stats, const brn_sample_range& r,
-                                    int with_prior, double* loss, cudaStream_t stream);
+                                    int with_prior, double* loss, cudaStream_t stream, int64_t philox_numel0 = 0);
 
 // eps (injected var.eps or Philox) -> eps_out[s*ld + offs[k] + i], W[...] = mu + softplus(rho)*eps for up to 4 variables
 int launch_sample_multi(const brn_mf_var* vars, const int64_t* offs, int nvars, float* eps_out, float* W, int64_t ld,
