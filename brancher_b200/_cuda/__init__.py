@@ -52,6 +52,14 @@ class VaeModel(ctypes.Structure):
                 ("dec", DenseLayer * VAE_MAX_HIDDEN), ("dec_out", DenseLayer)]
 
 
+class WvgdArgs(ctypes.Structure):
+    """struct brn_wvgd_args"""
+    _fields_ = [(n, ctypes.c_void_p) for n in
+                ("loc", "rho", "theta", "prior_loc", "prior_scale", "owner0", "owner1", "ll0", "ll1", "G0", "eps0", "eps1",
+                 "Z0", "Z1", "dloc", "drho", "dtheta", "counts", "loss")] + \
+               [(n, ctypes.c_int32) for n in ("P", "S", "d", "rho_per_elem", "biased", "_pad")]
+
+
 # name -> (restype, argtypes): every symbol include/brancher_cuda.h declares
 SYMBOLS = {
     "brn_abi_version": (ctypes.c_int, []),
@@ -92,6 +100,13 @@ SYMBOLS = {
                                             ctypes.POINTER(VaeModel), ctypes.c_void_p, ctypes.c_uint32,
                                             ctypes.POINTER(SampleRange), ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
                                             ctypes.c_void_p, ctypes.c_void_p]),
+    "brn_wvgd_sample_assign": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p] +
+                               [ctypes.c_int] * 6 + [ctypes.POINTER(SampleRange), ctypes.c_void_p, ctypes.c_void_p,
+                                                     ctypes.c_void_p, ctypes.c_void_p]),
+    "brn_linear_vectors_loglik_grad": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
+                                                      ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "brn_wvgd_reduce": (ctypes.c_int, [ctypes.POINTER(WvgdArgs), ctypes.c_void_p]),
     "brn_svgd_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
     "brn_svgd_direction": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 5 +
                            [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
@@ -331,6 +346,64 @@ def svgd_direction(theta, grad, row0=0, rows=None, bandwidth=None):
     _check(lib().brn_svgd_direction(_ptr(theta, what="theta"), _ptr(grad, what="grad"), n, d, row0, rows, int(update),
                                     _ptr(bw), _ptr(out), ws.data_ptr(), ws.numel(), _stream(dev)), "brn_svgd_direction")
     return out, bw
+
+
+def linear_vectors_loglik_grad(X, y, likelihood, V, C, want_grad=True):
+    """K6b.  V [n, C*F] weight vectors -> (ll fp64 [n], G [n, C*F] = -d ll / d V or None)."""
+    dev = X.device
+    N, F = X.shape
+    n = V.shape[0]
+    V = V.reshape(n, -1)
+    ll = torch.empty(n, dtype=torch.float64, device=dev)
+    G = torch.empty_like(V) if want_grad else None
+    ydt = torch.float32 if likelihood == BERNOULLI else torch.int32
+    _check(lib().brn_linear_vectors_loglik_grad(_ptr(X, what="X"), _ptr(y, ydt, "y"), likelihood, N, F, C, _ptr(V, what="V"), n,
+                                                _ptr(G), _ptr(ll, torch.float64), _stream(dev)), "brn_linear_vectors_loglik_grad")
+    return ll, G
+
+
+def wvgd_sample_assign(loc, rho, theta, S, F_last, r, draw, eps=None, first_column_only=True):
+    """K6a.  loc, theta [P,d]; rho [P] or [P,d]; eps [P,S,d] or None (Philox) -> (Z [P,S,d], eps [P,S,d], owner int32 [P,S])."""
+    P, d = loc.shape
+    dev = loc.device
+    Z = torch.empty((P, S, d), dtype=torch.float32, device=dev)
+    eps_out = torch.empty_like(Z) if eps is None else None
+    owner = torch.empty((P, S), dtype=torch.int32, device=dev)
+    if eps is not None and tuple(eps.shape) != (P, S, d):
+        raise BrancherCudaError("eps has shape %s, expected %s" % (tuple(eps.shape), (P, S, d)))
+    _check(lib().brn_wvgd_sample_assign(_ptr(loc, what="loc"), _ptr(rho, what="rho"), int(rho.dim() == 2), _ptr(theta, what="theta"),
+                                        _ptr(eps, what="eps"), P, S, d, F_last, int(first_column_only), draw, ctypes.byref(r),
+                                        _ptr(Z), _ptr(eps_out), _ptr(owner, torch.int32), _stream(dev)), "brn_wvgd_sample_assign")
+    return Z, (eps if eps is not None else eps_out), owner
+
+
+def wvgd_loss_grad(X, y, likelihood, C, loc, rho, theta, S, r, eps0=None, eps1=None, prior=None, biased=False,
+                   first_column_only=True, loss=None):
+    """K6: one WassersteinVariationalGradientDescent.compute_loss + backward (inference.py:203-229) for P (sampler, particle)
+    pairs.  loc, theta [P, C*F]; rho [P] or [P, C*F]; prior = (loc [C*F], scale [C*F]) or None (tied).
+    Returns (loss fp64 [1], dloc [P,d], drho [P,d] per element, dtheta [P,d], counts int32 [P,2])."""
+    P, d = loc.shape
+    dev = loc.device
+    F_last = d // C
+    Z0, e0, o0 = wvgd_sample_assign(loc, rho, theta, S, F_last, r, 0, eps0, first_column_only)
+    Z1, e1, o1 = wvgd_sample_assign(loc, rho, theta, S, F_last, r, 1, eps1, first_column_only)
+    ll0, G0 = linear_vectors_loglik_grad(X, y, likelihood, Z0.reshape(P * S, d), C, True)
+    ll1, _ = linear_vectors_loglik_grad(X, y, likelihood, Z1.reshape(P * S, d), C, False)
+    loss = torch.zeros(1, dtype=torch.float64, device=dev) if loss is None else loss
+    dloc, drho, dtheta = torch.empty_like(loc), torch.empty_like(loc), torch.empty_like(loc)
+    counts = torch.empty((P, 2), dtype=torch.int32, device=dev)
+    a = WvgdArgs()
+    a.loc, a.rho, a.theta = _ptr(loc), _ptr(rho), _ptr(theta, what="theta")
+    a.prior_loc = None if prior is None else _ptr(prior[0], what="prior_loc")
+    a.prior_scale = None if prior is None else _ptr(prior[1], what="prior_scale")
+    a.owner0, a.owner1 = _ptr(o0, torch.int32), _ptr(o1, torch.int32)
+    a.ll0, a.ll1, a.G0 = _ptr(ll0, torch.float64), _ptr(ll1, torch.float64), _ptr(G0)
+    a.eps0, a.eps1, a.Z0, a.Z1 = _ptr(e0), _ptr(e1), _ptr(Z0), _ptr(Z1)
+    a.dloc, a.drho, a.dtheta = _ptr(dloc), _ptr(drho), _ptr(dtheta)
+    a.counts, a.loss = _ptr(counts, torch.int32), _ptr(loss, torch.float64)
+    a.P, a.S, a.d, a.rho_per_elem, a.biased = P, S, d, int(rho.dim() == 2), int(biased)
+    _check(lib().brn_wvgd_reduce(ctypes.byref(a), _stream(dev)), "brn_wvgd_reduce")
+    return loss, dloc, drho, dtheta, counts
 
 
 class VaeNet:

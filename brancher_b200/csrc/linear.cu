@@ -23,6 +23,7 @@ struct LinearArgs {
     const float* W; float* dW;       // [S*C, F] contiguous
     int tiles_per_group; int64_t n_row_tiles;
     float inv_S; double* loss;
+    double* ll_cols;                 // optional [S]: per-sample log-likelihood sums (K6), += ; loss may then be NULL
 };
 
 template <int LIK>   // 0: Bernoulli/Binomial(1) with float y, 1: Categorical with int32 labels
@@ -56,6 +57,11 @@ __global__ void __launch_bounds__(256, 1) linear_fused_kernel(LinearArgs a) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc2[i][j] = 0.f;
     double ll_thread = 0.0;
+    double llc[8];                   // LIK == 0 with ll_cols: this thread's 8 columns, summed over its rows and tiles
+#pragma unroll
+    for (int j = 0; j < 8; ++j) llc[j] = 0.0;
+    __shared__ double llcol_s[LN_T];  // LIK == 1 with ll_cols: per sample of the tile
+    if (a.ll_cols && t < LN_T) llcol_s[t] = 0.0;
 
     const int64_t tile_begin = (int64_t)blockIdx.y * a.tiles_per_group;
     const int64_t tile_end = min(a.n_row_tiles, tile_begin + a.tiles_per_group);
@@ -129,7 +135,9 @@ __global__ void __launch_bounds__(256, 1) linear_fused_kernel(LinearArgs a) {
                     bool ok = rv && col < ncols && (j0 + col) < J;
                     float l = acc[i][j];
                     float sp = log1pexpf(l);
-                    ll_tile += ok ? __fmaf_rn(yv, l, -sp) : 0.f;
+                    const float lv = ok ? __fmaf_rn(yv, l, -sp) : 0.f;
+                    ll_tile += lv;
+                    if (a.ll_cols) llc[j] += (double)lv;
                     d[j] = ok ? yv - sigmoidf(l) : 0.f;
                 }
                 *reinterpret_cast<float4*>(&Ls[row][tx * 4]) = make_float4(d[0], d[1], d[2], d[3]);
@@ -160,7 +168,10 @@ __global__ void __launch_bounds__(256, 1) linear_fused_kernel(LinearArgs a) {
                 float lse = m + logf(se);
                 for (int c = 0; c < C; ++c) {
                     float l = lg[c];
-                    if (c == label) ll_tile += l - lse;
+                    if (c == label) {
+                        ll_tile += l - lse;
+                        if (a.ll_cols) atomicAdd(&llcol_s[sl], (double)(l - lse));
+                    }
                     lg[c] = (c == label ? 1.f : 0.f) - expf(l - lse);
                 }
             }
@@ -174,7 +185,8 @@ __global__ void __launch_bounds__(256, 1) linear_fused_kernel(LinearArgs a) {
         }
         ll_thread += (double)ll_tile;
 
-        // ---- phase 3: dW[col, f] += sum_row dL[row, col] * X[row, f]
+        // ---- phase 3: dW[col, f] += sum_row dL[row, col] * X[row, f]   (skipped when only the log-likelihoods are wanted)
+        if (a.dW == nullptr) continue;
 #pragma unroll 4
         for (int row = 0; row < LN_T; ++row) {
             float4 a0 = *reinterpret_cast<const float4*>(&Ls[row][ty * 4]);
@@ -191,8 +203,21 @@ __global__ void __launch_bounds__(256, 1) linear_fused_kernel(LinearArgs a) {
     }
 
     // ---- flush
+    if (a.ll_cols) {
+        if (LIK == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int col = (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+                if (col < ncols && j0 + col < J && llc[j] != 0.0) atomicAdd(&a.ll_cols[j0 + col], llc[j]);
+            }
+        } else {
+            __syncthreads();
+            if (t < spc && s_base + t < a.S && llcol_s[t] != 0.0) atomicAdd(&a.ll_cols[s_base + t], llcol_s[t]);
+        }
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
+        if (a.dW == nullptr) break;
         int col = (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
         if (col >= ncols || j0 + col >= J) continue;
 #pragma unroll
@@ -202,7 +227,7 @@ __global__ void __launch_bounds__(256, 1) linear_fused_kernel(LinearArgs a) {
         }
     }
     double tot = block_sum<double>(ll_thread, red);
-    if (t == 0) atomicAdd(a.loss, -tot * (double)a.inv_S);
+    if (t == 0 && a.loss) atomicAdd(a.loss, -tot * (double)a.inv_S);
 }
 
 constexpr int LT_BN1 = 208;       // logits GEMM: samples per n-tile
@@ -302,10 +327,10 @@ static bool linear_use_tc(int likelihood, int64_t N, int F, int C, int S) {
 using namespace brn;
 
 static int launch_linear_fused(const float* X, const void* y, int likelihood, int64_t N, int F, int C, int S, const float* W,
-                               float* dW, float inv_S, double* loss, cudaStream_t stream) {
+                               float* dW, float inv_S, double* loss, cudaStream_t stream, double* ll_cols = nullptr) {
     LinearArgs a;
     a.X = X; a.y = y; a.N = N; a.F = F; a.C = C; a.S = S; a.W = W; a.dW = dW;
-    a.inv_S = inv_S; a.loss = loss;
+    a.inv_S = inv_S; a.loss = loss; a.ll_cols = ll_cols;
     const int spc = LN_T / C;
     const int col_tiles = (S + spc - 1) / spc;
     a.n_row_tiles = (N + LN_T - 1) / LN_T;
@@ -353,6 +378,34 @@ extern "C" int brn_linear_particles_loss_grad(const float* X, const void* y, int
     StageTimer st2("particles.prior", stream);
     particles_prior_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(theta, prior_loc, prior_scale, numel, total, G, loss);
     BRN_LAUNCH_OK("particles_prior_kernel");
+    return 0;
+}
+
+// K6 (b): per-vector log-likelihoods (and optionally their gradients) of n weight vectors, one fused pass over X
+extern "C" int brn_linear_vectors_loglik_grad(const float* X, const void* y, int likelihood, int64_t N, int F, int C,
+                                              const float* V, int n, float* G, double* ll, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    BRN_CHECK_ARG(V && ll, "brn_linear_vectors_loglik_grad: NULL pointer");
+    BRN_CHECK_ARG(N >= 0 && F > 0 && C > 0 && n >= 0, "brn_linear_vectors_loglik_grad: bad shape N=%lld F=%d C=%d n=%d",
+                  (long long)N, F, C, n);
+    BRN_CHECK_ARG(N == 0 || (X && y), "brn_linear_vectors_loglik_grad: NULL data pointer");
+    BRN_CHECK_ARG(F <= LN_T && C <= LN_T, "brn_linear_vectors_loglik_grad: F=%d / C=%d exceed the supported maximum %d", F, C, LN_T);
+    BRN_CHECK_ARG(likelihood == 0 || likelihood == 1, "brn_linear_vectors_loglik_grad: unknown likelihood %d", likelihood);
+    BRN_CHECK_ARG(likelihood == 1 || C == 1, "Bernoulli/Binomial likelihood needs C == 1 (got %d)", C);
+    if (n == 0) return 0;
+    set_variant("simt");
+    const int64_t total = (int64_t)C * F * n;
+    BRN_CUDA_OK(cudaMemsetAsync(ll, 0, sizeof(double) * (size_t)n, stream));
+    if (G) BRN_CUDA_OK(cudaMemsetAsync(G, 0, sizeof(float) * (size_t)total, stream));
+    if (N > 0) {
+        StageTimer st("vectors.loglik_grad", stream);
+        if (int e = launch_linear_fused(X, y, likelihood, N, F, C, n, V, G, 1.0f, nullptr, stream, ll)) return e;
+        if (G) {       // the fused kernel accumulates +d ll / d V; the ABI returns the loss gradient -d ll / d V
+            particles_prior_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(V, nullptr, nullptr, (int64_t)C * F, total, G,
+                                                                                       nullptr);
+            BRN_LAUNCH_OK("particles_prior_kernel");
+        }
+    }
     return 0;
 }
 

@@ -601,6 +601,7 @@ class ParticlePlan:
 
     def __init__(self, joint, particles, k, W, x_var, likelihood, C):
         self.joint, self.particles, self.k, self.x_var, self.likelihood, self.C = joint, particles, k, x_var, likelihood, C
+        self.W = W
         lp = W.partial_links
         loc, sc_sp = _as_root(lp["loc"].expr), _softplus_root(lp["scale"].expr)
         sc = sc_sp or _as_root(lp["scale"].expr)
@@ -664,6 +665,103 @@ def lower_particles(joint, particles):
     if kind != "categorical" and C != 1:
         raise UnsupportedModelError("Binomial/Bernoulli logistic regression needs weights of shape [1, F]")
     return ParticlePlan(joint, particles, k, W, _var(logits.args[1]), cu.CATEGORICAL if kind == "categorical" else cu.BERNOULLI, C)
+
+
+class _WvgdLoss(torch.autograd.Function):
+    """params = [theta_0.., loc_0.., rho_0..]; the runner returns the loss and one gradient per parameter."""
+    @staticmethod
+    def forward(ctx, runner, *params):
+        loss, grads = runner()
+        ctx.grads = grads
+        return loss.to(torch.float32).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        return (None,) + tuple(g * x for x in ctx.grads)
+
+
+class WvgdPlan:
+    """WVGD over (multi-class) logistic-regression ensembles (development_playgrounds/WVGD_logistic_regression.py:33-58): the
+    joint model is the linear family, particle k holds one learnable root named like the weights latent, sampler k one
+    learnable Normal of the same name whose loc/scale are roots (scale a scalar or a full tensor)."""
+    family = "wvgd (K6)"
+
+    def __init__(self, pplan, samplers):
+        self.pplan = pplan
+        W_name = pplan.roots[0].name
+        if len(samplers) != len(pplan.particles):
+            raise UnsupportedModelError("WVGD needs one variational sampler per particle")
+        self.loc_roots, self.scale_roots = [], []
+        q_names = set()
+        for smp in samplers:
+            qs = [v for v in smp._flatten() if isinstance(v, RandomVariable) and v.name == W_name]
+            if len(qs) != 1 or qs[0].distribution.kind != "normal":
+                raise UnsupportedModelError("every WVGD sampler must hold one Normal variable named %r" % W_name)
+            lq = qs[0].partial_links
+            loc, sc = _as_root(lq["loc"].expr), _softplus_root(lq["scale"].expr)
+            if loc is None or sc is None or tuple(loc._value.shape[2:]) != pplan.shape:
+                raise UnsupportedModelError("WVGD sampler %r: loc/scale must be learnable roots of the particle's shape" % W_name)
+            if sc._value.numel() not in (1, loc._value.numel()):
+                raise UnsupportedModelError("WVGD sampler %r: scale must be a scalar or match the weights' shape" % W_name)
+            self.loc_roots.append(loc)
+            self.scale_roots.append(sc)
+            q_names |= {loc.name, sc.name}
+        if len({r._value.numel() for r in self.scale_roots}) != 1:
+            raise UnsupportedModelError("WVGD samplers must agree on the shape of their scale parameter")
+        # tied mode: the prior's auto-named hyper-parameter roots collide with the samplers' (utilities.py:282-309)
+        lp = pplan.W.partial_links
+        p_loc, p_sc = _as_root(lp["loc"].expr), (_softplus_root(lp["scale"].expr) or _as_root(lp["scale"].expr))
+        tied = {p_loc.name in q_names, p_sc.name in q_names}
+        if len(tied) != 1:
+            raise UnsupportedModelError("WVGD: prior loc/scale roots are tied to the samplers inconsistently")
+        self.tied = tied.pop()
+
+    def parameters(self):
+        return [r.value for r in self.pplan.roots] + [r.value for r in self.loc_roots] + [r.value for r in self.scale_roots]
+
+    def loss(self, empirical, number_samples, biased, first_column_only):
+        if config.device.type != "cuda":
+            raise RuntimeError("brancher_b200 evaluates the WVGD loss only on CUDA devices (no CPU fallback)")
+        from brancher_b200 import _cuda as cu
+        cu.lib()
+        pp = self.pplan
+        n = len(pp.roots)
+        params = self.parameters()
+        r = cu.sample_range(number_samples, seed=config.seed, offset=config.next_offset())
+
+        def runner():
+            X = _data_matrix(empirical[pp.x_var], "x")
+            yv = empirical[pp.k].reshape(-1)
+            y = yv.to(torch.float32).contiguous() if pp.likelihood == cu.BERNOULLI else yv.to(torch.int32).contiguous()
+            theta = pp.stacked()
+            loc = torch.stack([p.value.detach().reshape(-1) for p in self.loc_roots]).contiguous()
+            scalar = self.scale_roots[0]._value.numel() == 1
+            rho = torch.stack([p.value.detach().reshape(-1) for p in self.scale_roots]).contiguous()
+            rho = rho.reshape(n) if scalar else rho
+            eps0 = eps1 = None
+            if _INJECTED is not None:          # {"elbo": [n,S,*shape], "particle": [n,S,*shape]}
+                cv = lambda a: torch.as_tensor(a, dtype=torch.float32, device=theta.device).reshape(n, number_samples, -1).contiguous()
+                eps0, eps1 = cv(_INJECTED["elbo"]), cv(_INJECTED["particle"])
+            prior = None if self.tied else (pp.prior_loc, pp.prior_scale)
+            loss, dloc, drho, dth, counts = cu.wvgd_loss_grad(X, y, pp.likelihood, pp.C, loc, rho, theta, number_samples, r, eps0, eps1,
+                                                              prior=prior, biased=biased, first_column_only=first_column_only)
+            self.accepted = counts
+            drho = drho.sum(1, keepdim=True) if scalar else drho
+            grads = [dth[i].reshape(params[i].shape) for i in range(n)]
+            grads += [dloc[i].reshape(params[n + i].shape) for i in range(n)]
+            grads += [drho[i].reshape(params[2 * n + i].shape) for i in range(n)]
+            return loss, grads
+
+        return _WvgdLoss.apply(runner, *params)
+
+
+def get_wvgd_plan(joint, particles, samplers):
+    key = ("wvgd",) + tuple(id(p) for p in particles) + tuple(id(s) for s in samplers)
+    plan = joint._plans.get(key)
+    if plan is None:
+        plan = WvgdPlan(get_particle_plan(joint, particles), list(samplers))
+        joint._plans[key] = plan
+    return plan
 
 
 def get_particle_plan(joint, particles):

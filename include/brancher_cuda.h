@@ -207,6 +207,46 @@ int brn_vae_elbo_fwd_bwd(const float* X, int B, int64_t row0, int64_t B_total, c
                          const float* eps, uint32_t var_id, const brn_sample_range* r,
                          void* workspace, size_t workspace_bytes, int add_constant, double* loss, void* stream);
 
+/* K6 -- Wasserstein variational gradient descent (WassersteinVariationalGradientDescent, brancher/inference.py:154-248)
+ * for ensembles of P (sampler, particle) pairs over one weight tensor of d = C*F elements -- the model class of
+ * development_playgrounds/WVGD_logistic_regression.py:33-58: sampler k is q_k = N(loc_k, softplus(rho_k)), particle k a
+ * learnable root theta_k.  One loss evaluation = three calls, each replacing P (or P^2) Python graph walks:
+ * (a) brn_wvgd_sample_assign, once per noise draw (draw 0: sampler ELBOs, draw 1: particle loss; inference.py:203-212):
+ *       Z[k,s,:] = loc_k + sigma_k * eps[k,s,:]              (eps injected, or Philox with var_id = 2k + draw -> eps_out)
+ *       owner[k,s] = argmin_j cost(Z[k,s], theta_j)          (first minimal index)
+ *     The truncation rule of sampler k accepts sample s iff owner[k,s] == k (inference.py:188-194; rejection with
+ *     max_itr = 1, transformations.py:28-43 -- samples are masked, never compacted).  first_column_only != 0 reproduces
+ *     the reference's numpy cost (utilities.py:125-126: only index 0 of the last axis, F_last elements apart, enters
+ *     the squared distance); 0 = full squared distance.
+ * (b) brn_linear_vectors_loglik_grad: ll[i] = sum_rows log-lik(data | weights = V[i]) and G[i] = -d ll[i] / d V[i] for
+ *     n = P*S weight vectors in one fused pass over X (same kernel as K4a; G may be NULL).
+ * (c) brn_wvgd_reduce: per sampler k, over its accepted samples A_k (draw 0) and A'_k (draw 1):
+ *       loss += -mean_{A_k}[ll + log prior(z)]  +  sum_{A'_k} w_s ||theta_k - z'_s||^2
+ *       w = softmax_{A'_k}(ll' + log prior(z') - log q_k(z'))   (1/S if biased)         (variables.py:821-841)
+ *       dloc_k, drho_k: pathwise gradient of the first term (the entropy's detached-mean normaliser has no gradient:
+ *       transformations.py:17-20 detaches the root samples as well); dtheta_k = 2 sum w_s (theta_k - z'_s).
+ *     prior_loc == NULL: tied mode (p's auto-named roots take q_k's values, utilities.py:282-309).  A sampler with no
+ *     accepted sample contributes nothing to the corresponding term (the reference re-draws until one is accepted);
+ *     counts[k] = {|A_k|, |A'_k|}.  All outputs are overwritten except loss (+=). */
+typedef struct brn_wvgd_args {
+    const float *loc, *rho, *theta;          /* [P,d], [P,d] or [P] (rho_per_elem = 0), [P,d] */
+    const float *prior_loc, *prior_scale;    /* [d] or NULL (tied) */
+    const int32_t *owner0, *owner1;          /* [P,S] from (a), draws 0 and 1 */
+    const double *ll0, *ll1;                 /* [P,S] from (b) */
+    const float *G0;                         /* [P,S,d] from (b), draw 0 */
+    const float *eps0, *eps1, *Z0, *Z1;      /* [P,S,d] */
+    float *dloc, *drho, *dtheta;             /* [P,d] each (drho per element: sum it for a scalar rho) */
+    int32_t *counts;                         /* [P,2] */
+    double *loss;                            /* [1] += */
+    int32_t P, S, d, rho_per_elem, biased, _pad;
+} brn_wvgd_args;
+int brn_wvgd_sample_assign(const float* loc, const float* rho, int rho_per_elem, const float* theta, const float* eps,
+                           int P, int S, int d, int F_last, int first_column_only, int draw, const brn_sample_range* r,
+                           float* Z, float* eps_out, int32_t* owner, void* stream);
+int brn_linear_vectors_loglik_grad(const float* X, const void* y, int likelihood, int64_t N, int F, int C,
+                                   const float* V, int n, float* G, double* ll, void* stream);
+int brn_wvgd_reduce(const brn_wvgd_args* a, void* stream);
+
 /* Tensor-core building block, exposed for validation: D[M][N] = A[M][K] . B[N][K]^T (all row-major fp32)
  * computed with tcgen05.mma kind::tf32 and the 3xTF32 hi/lo split (fp32-equivalent accuracy), TMA-fed.
  * This is the contraction the reference performs as a batched torch.matmul inside _apply_link

@@ -354,3 +354,79 @@ def svgd_direction_loops(theta, grad):
     for i in range(n):
         out[i] = sum(kern[i][j] * g[j] + inter[i][j] for j in range(n))
     return out, float(bw)
+
+
+# ----------------------------------------------------------------------------------------------
+# WVGD: WassersteinVariationalGradientDescent.compute_loss, inference.py:154-229, for the model class of
+# development_playgrounds/WVGD_logistic_regression.py (one Normal sampler + one root particle per ensemble member).
+# ----------------------------------------------------------------------------------------------
+def voronoi_owner(z, theta, first_column_only=True):
+    """z [m, C, F] samples, theta [n, C, F] particle locations -> owner [m] = argmin_j cost(z, theta_j).
+
+    The reference evaluates its cost on NUMPY arrays (inference.py:177-186): `sum_from_dim` then takes
+    `np.sum(x, axis=(1, ..., ndim-2))[:, 0]` (utilities.py:125-126), i.e. for values of shape (S,1,C,F) it sums over the
+    C axis and keeps ONLY index 0 of the last axis: cost = sum_c (z[c,0] - theta_j[c,0])^2.  `first_column_only=True`
+    reproduces that; False is the evident intent (full squared distance).  fp32 like the reference's arrays;
+    np.argmin = first minimal index (inference.py:188-189)."""
+    z = np.asarray(z, np.float32)
+    th = np.asarray(theta, np.float32)
+    if first_column_only:
+        z, th = z[:, :, :1], th[:, :, :1]
+    d2 = ((z[:, None] - th[None]) ** 2).sum(axis=(2, 3), dtype=np.float32)
+    return np.argmin(d2, axis=1)
+
+
+def wvgd_loss(X, y, theta, loc, rho, eps_elbo, eps_particle, prior=None, dtype=torch.float32, likelihood="categorical",
+              biased=False, first_column_only=True):
+    """theta, loc [n,C,F]; rho [n] (scalar scale per sampler) or [n,C,F]; eps_* [n,S,C,F] (two independent draws per
+    sampler: one for the sampler ELBO, one for the particle loss -- inference.py:203-212).
+
+    Per sampler k, with z = loc_k + softplus(rho_k) eps and A_k = {s : voronoi_owner(z_s) == k} (rejection with max_itr=1,
+    transformations.py:28-43; the caller must supply noise with at least one accepted sample per draw):
+      -ELBO_k = -mean_{A_k}[ log p(z, data) - log q_k(z) + mean_{A_k} log q_k(z.detach()) ]
+                (entropy of a transformed model = -truncated log-prob, variables.py:744-749, whose for_gradient branch adds the
+                 detached-mean normaliser, transformations.py:12-22; PathwiseDerivativeEstimator .mean(), gradient_estimators.py:44)
+      particle_k = sum_{A'_k} w_s ||theta_k - z'_s.detach()||^2, w = softmax_{A'_k}(log p(z', data) - log q_k(z'))  (1/S if biased)
+                (inference.py:211-229, variables.py:821-841)
+    prior=None: tied mode (p's auto-named weights_loc/weights_scale roots take q_k's values, utilities.py:282-309), else the
+    declared (loc, scale).  Returns (loss, {"loc": [n,C,F], "rho": like rho, "theta": [n,C,F]}, accepted counts [n,2])."""
+    Xt = _t(X, dtype)
+    n = len(theta)
+    th = _t(theta, dtype, True)
+    lc = _t(loc, dtype, True)
+    rh = _t(rho, dtype, True)
+    e1, e2 = _t(eps_elbo, dtype), _t(eps_particle, dtype)
+    if likelihood == "categorical":
+        yt = torch.as_tensor(np.asarray(y), dtype=torch.long)
+        loglik = lambda z: D.Categorical(logits=torch.einsum("scf,bf->sbc", z, Xt)).log_prob(yt[None, :]).sum(1)
+    else:
+        yt = _t(y, dtype)
+        loglik = lambda z: D.Binomial(total_count=1, logits=torch.einsum("scf,bf->sbc", z, Xt)[..., 0]).log_prob(yt[None, :]).sum(1)
+    total = 0.0
+    counts = np.zeros((n, 2), np.int64)
+    for k in range(n):
+        sg = F.softplus(rh[k])
+        q = D.Normal(lc[k], sg.expand_as(lc[k]))
+        pr = q if prior is None else D.Normal(_t(prior[0], dtype), _t(prior[1], dtype))
+        # sampler ELBO
+        z = lc[k] + sg * e1[k]
+        acc = torch.as_tensor(voronoi_owner(z.detach().float().numpy(), th.detach().float().numpy(), first_column_only) == k)
+        counts[k, 0] = int(acc.sum())
+        za = z[acc]
+        logq = q.log_prob(za).sum((1, 2))
+        norm = -q.log_prob(za.detach()).sum((1, 2)).mean().detach()     # `nondiff_values` detaches the root samples too
+        elbo = (loglik(za) + pr.log_prob(za).sum((1, 2)) - (logq + norm)).mean()
+        # particle loss (fresh draw, everything about the samples detached)
+        z2 = (lc[k] + sg * e2[k]).detach()
+        acc2 = torch.as_tensor(voronoi_owner(z2.float().numpy(), th.detach().float().numpy(), first_column_only) == k)
+        counts[k, 1] = int(acc2.sum())
+        z2a = z2[acc2]
+        if biased:
+            w = torch.full((z2a.shape[0],), 1.0 / eps_particle.shape[1], dtype=dtype)
+        else:
+            logw = (loglik(z2a) + pr.log_prob(z2a).sum((1, 2)) - q.log_prob(z2a).sum((1, 2))).detach()
+            w = torch.softmax(logw, 0)
+        ploss = (w * ((th[k][None] - z2a) ** 2).sum((1, 2))).sum()
+        total = total - elbo + ploss
+    total.backward()
+    return float(total.detach()), {"loc": lc.grad.numpy().copy(), "rho": rh.grad.numpy().copy(), "theta": th.grad.numpy().copy()}, counts

@@ -225,7 +225,41 @@ def svgd_model(seed, B, F, C, n, tag="svgd_softmax"):
          bandwidth=float(m.bandwidth), prior_loc=np.zeros((C, F), "float32"), prior_scale=10 * np.ones((C, F), "float32"))
 
 
+def wvgd(seed, B, F, C, n, S, tag="wvgd_softmax", tied=True):
+    """One WassersteinVariationalGradientDescent.compute_loss + backward (inference.py:203-229) through the reference:
+    per-sampler truncated ELBOs + importance-weighted particle loss.  Two noise draws per sampler (ELBO, particle loss),
+    injected in call order; the generator asserts no sampler needed a rejection re-draw."""
+    model, particles, samplers, d = zoo.wvgd_softmax(NS, seed, B, F, C, n)
+    rng = d["rng"]
+    eps = rng.randn(n, 2, S, C, F).astype("float32")
+    used = [[] for _ in range(n)]
+    for k, smp in enumerate(samplers):
+        v = [v for v in smp.flatten() if v.name == "weights"][0]
+
+        def f(differentiable, _k=k, **p):
+            e = torch.tensor(eps[_k, len(used[_k])]).reshape(S, 1, C, F)
+            used[_k].append(1)
+            return p["loc"] + e * p["scale"]
+        v.distribution._get_sample = f
+    m = inference.WassersteinVariationalGradientDescent(variational_samplers=samplers, particles=particles, biased=False)
+    model.update_observed_submodel()
+    loss = m.compute_loss(model, particles, m.sampler_model, S)
+    loss.backward()
+    assert all(len(u) == 2 for u in used), "a sampler re-drew (no accepted sample): pick another seed %s" % [len(u) for u in used]
+    by = lambda smp, name: [v for v in smp.flatten() if v.name == name][0]
+    g_loc = np.stack([by(s_, "weights_loc").link.parameter.grad.numpy().reshape(C, F) for s_ in samplers])
+    g_rho = np.stack([by(s_, "weights_scale").link.parameter.grad.numpy().reshape(()) for s_ in samplers])
+    rho = np.stack([by(s_, "weights_scale").link.parameter.detach().numpy().reshape(()) for s_ in samplers])
+    g_theta = np.stack([by(p_, "weights").value.grad.numpy().reshape(C, F) for p_ in particles])
+    save(tag, X=d["X"], y=d["y"], theta=d["theta"], loc=d["loc"], rho=rho, eps_elbo=eps[:, 0], eps_particle=eps[:, 1],
+         loss=float(loss.detach()), grad_loc=g_loc, grad_rho=g_rho, grad_theta=g_theta)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "wvgd":
+        wvgd(21, B=30, F=4, C=3, n=3, S=20, tag="wvgd_softmax")
+        wvgd(22, B=16, F=5, C=2, n=4, S=24, tag="wvgd_softmax4")
+        sys.exit(0)
     torch.manual_seed(0)
     bnn(1, B=12, P=20, H=7, C=4, S=6, tag="bnn_small")
     bnn(2, B=9, P=16, H=5, C=3, S=5, q_sigma=0.3, q_mu_scale=0.5, tag="bnn_small_wide")
@@ -239,3 +273,5 @@ if __name__ == "__main__":
     svgd_model(8, B=30, F=5, C=3, n=6, tag="svgd_softmax")
     vae(12, B=6, D=12, L=2, h_enc=(5, 7), h_dec=(7, 5), S=3, tag="vae_small")
     vae(13, B=10, D=20, L=3, h_enc=(9,), h_dec=(6, 8, 5), S=4, tag="vae_deep")
+    wvgd(21, B=30, F=4, C=3, n=3, S=20, tag="wvgd_softmax")
+    wvgd(22, B=16, F=5, C=2, n=4, S=24, tag="wvgd_softmax4")

@@ -226,3 +226,23 @@ def vae(ns, seed, B, D, L, h_enc, h_dec):
     Qz = ns.NormalVariable(encoder_output["mean"], encoder_output["sd"], name="z")
     model.set_posterior_model(ns.ProbabilisticModel([Qx, Qz]))
     return model, [Qz], {"X": dataset[:, :, 0].astype("float32"), "enc": enc, "dec": dec, "rng": rng}
+
+
+def wvgd_softmax(ns, seed, B, F, C, n, spread=1.0, q_sigma=0.3):
+    """development_playgrounds/WVGD_logistic_regression.py:33-58: softmax regression; one single-root particle model and
+    one single-Normal sampler model (learnable loc/scale, same variable name "weights") per particle."""
+    rng = np.random.RandomState(seed)
+    X = rng.randn(B, F, 1).astype("float32")
+    y = rng.randint(0, C, size=(B,))
+    x = ns.RootVariable(X, "x", is_observed=True)
+    weights = ns.NormalVariable(np.zeros((C, F)), 10 * np.ones((C, F)), "weights")
+    k = ns.CategoricalVariable(logits=ns.BF.matmul(weights, x), name="k")
+    model = ns.ProbabilisticModel([k])
+    k.observe(y)
+    theta0 = (spread * rng.randn(n, C, F)).astype("float32")
+    loc0 = (theta0 + 0.05 * rng.randn(n, C, F)).astype("float32")
+    particles = [ns.ProbabilisticModel([ns.RootVariable(theta0[i].astype("float64"), name="weights", learnable=True)])
+                 for i in range(n)]
+    samplers = [ns.ProbabilisticModel([ns.NormalVariable(loc=loc0[i].astype("float64"), scale=q_sigma, name="weights",
+                                                         learnable=True)]) for i in range(n)]
+    return model, particles, samplers, {"X": X[:, :, 0], "y": y, "theta": theta0, "loc": loc0, "q_sigma": q_sigma, "rng": rng}

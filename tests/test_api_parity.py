@@ -6,7 +6,7 @@ import pytest
 import torch
 
 import model_zoo as zoo
-from helpers import load_golden, mf_params, check_against_oracle
+from helpers import load_golden, mf_params, check_against_oracle, assert_close
 
 pytestmark = pytest.mark.gpu
 
@@ -157,3 +157,43 @@ def test_svgd_perform_inference_runs(ns):
     after = np.stack([list(p.flatten())[0].value.detach().cpu().numpy() for p in particles])
     assert curve.shape == (20,) and np.isfinite(curve).all() and curve[-1] < curve[0]
     assert np.abs(after - before).max() > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag,n,B,F,C,S,seed", [("wvgd_softmax", 3, 30, 4, 3, 20, 21), ("wvgd_softmax4", 4, 16, 5, 2, 24, 22)])
+def test_wvgd_api_matches_reference(tag, n, B, F, C, S, seed):
+    """The reference's WVGD script shape through the mirrored API: WassersteinVariationalGradientDescent.compute_loss +
+    backward land the reference's gradients in every sampler / particle parameter."""
+    import os
+    from helpers import GOLDEN
+    from brancher_b200 import config, lowering
+    config.set_device("cuda:0")
+    ns = zoo.namespace("brancher_b200")
+    g = np.load(os.path.join(GOLDEN, tag + ".npz"))
+    model, particles, samplers, d = zoo.wvgd_softmax(ns, seed, B, F, C, n)
+    m = ns.inference.WassersteinVariationalGradientDescent(variational_samplers=samplers, particles=particles, biased=False)
+    m.check_model_compatibility(model, particles, m.sampler_model)
+    with lowering.inject_noise({"elbo": g["eps_elbo"], "particle": g["eps_particle"]}):
+        loss = m.compute_loss(model, particles, m.sampler_model, S)
+    loss.backward()
+    assert_close(float(loss.detach()), g["loss"], tag + " loss", rtol=2e-5, atol=2e-6)
+    by = lambda mdl, name: [v for v in mdl.flatten() if v.name == name][0]
+    got_loc = np.stack([by(s_, "weights_loc").value.grad.cpu().numpy().reshape(C, F) for s_ in samplers])
+    got_rho = np.stack([by(s_, "weights_scale").value.grad.cpu().numpy().reshape(()) for s_ in samplers])
+    got_th = np.stack([by(p_, "weights").value.grad.cpu().numpy().reshape(C, F) for p_ in particles])
+    for got, key in ((got_loc, "grad_loc"), (got_rho, "grad_rho"), (got_th, "grad_theta")):
+        assert_close(got, g[key], tag + " " + key, rtol=2e-5, atol=2e-6, scale=np.abs(g[key]).max())
+
+
+@pytest.mark.gpu
+def test_wvgd_perform_inference_runs():
+    from brancher_b200 import config
+    config.set_device("cuda:0")
+    ns = zoo.namespace("brancher_b200")
+    model, particles, samplers, d = zoo.wvgd_softmax(ns, 23, 40, 4, 3, 4)
+    m = ns.inference.WassersteinVariationalGradientDescent(variational_samplers=samplers, particles=particles)
+    ns.inference.perform_inference(model, inference_method=m, number_iterations=30, number_samples=50, optimizer="Adam", lr=0.01,
+                                   posterior_model=particles)
+    curve = model.diagnostics["loss curve"]
+    assert curve.shape == (30,) and np.isfinite(curve).all()
+    assert curve[-5:].mean() < curve[:5].mean()

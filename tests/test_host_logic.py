@@ -120,3 +120,23 @@ def test_svgd_particles_lower_to_k4(ns):
     bad = [ns.ProbabilisticModel([ns.RootVariable(np.zeros((2, 2)), name="weights", learnable=True)])]
     with pytest.raises(lowering.UnsupportedModelError):
         lowering.lower_particles(model, bad)
+
+
+def test_wvgd_lowering_and_no_cpu_fallback():
+    """WVGD ensembles lower to the K6 plan on the host (tied prior detected by root-name collision) and refuse to run on CPU."""
+    import model_zoo as zoo
+    from brancher_b200 import config, lowering
+    config.set_device("cpu")
+    ns = zoo.namespace("brancher_b200")
+    model, particles, samplers, d = zoo.wvgd_softmax(ns, 21, 30, 4, 3, 3)
+    m = ns.inference.WassersteinVariationalGradientDescent(variational_samplers=samplers, particles=particles)
+    m.check_model_compatibility(model, particles, m.sampler_model)
+    plan = lowering.get_wvgd_plan(model, particles, samplers)
+    assert plan.family == "wvgd (K6)" and plan.tied
+    assert [tuple(p.shape) for p in plan.parameters()] == [(1, 1, 3, 4)] * 6 + [(1, 1, 1, 1)] * 3
+    with pytest.raises(RuntimeError):
+        m.compute_loss(model, particles, m.sampler_model, 5)
+    with pytest.raises(lowering.UnsupportedModelError):
+        lowering.get_wvgd_plan(model, particles, samplers[:2])
+    with pytest.raises(NotImplementedError):
+        ns.inference.WassersteinVariationalGradientDescent(samplers, particles, cost_function=lambda a, b: 0)
