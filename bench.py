@@ -391,11 +391,12 @@ def main_ours(args):
         gflat = torch.zeros(4, device=dev)
         theta_all = torch.empty((n_total, F), device=dev)
         G_all = torch.empty((n_total, F), device=dev)
-        svgd_out = [None]
+        svgd_out = [None, None]
         S_total = n_total
 
         def device_step(it, Xd=X, yd=y):
             loss, G = cu.linear_particles_loss_grad(Xd, yd, cu.BERNOULLI, theta_local, 1, pl, ps)
+            svgd_out[1] = cu.last_variant()
             if world > 1:
                 dist.all_gather_into_tensor(theta_all, theta_local)
                 dist.all_gather_into_tensor(G_all, G)
@@ -517,7 +518,8 @@ def main_ours(args):
                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                "config": {"workload": cfg["name"], "noise": "Philox4x32-10 in-kernel", "l2": "256 MiB flush between timed steps",
-                          "variant": cu.last_variant(), "global_samples_or_particles": S_total,
+                          "variant": (svgd_out[1] + " (K4a) + simt (K4b)") if wl == "svgd" else cu.last_variant(),
+                          "global_samples_or_particles": S_total,
                           "sharding": {"bnn": "MC samples", "logreg": "data rows", "svgd": "particles", "vae": "batch rows",
                                        "ar1": "MC samples"}[wl]},
                "clocks": clk, "gpu_launches": int(launches),

@@ -94,7 +94,8 @@ SYMBOLS = {
     "brn_linear_particles_loss_grad": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
                                                       ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                                      ctypes.c_void_p]),
+                                                      ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "brn_linear_particles_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "brn_vae_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(VaeModel), ctypes.c_int, ctypes.c_int]),
     "brn_vae_elbo_fwd_bwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
                                             ctypes.POINTER(VaeModel), ctypes.c_void_p, ctypes.c_uint32,
@@ -326,9 +327,12 @@ def linear_particles_loss_grad(X, y, likelihood, theta, C, prior_loc=None, prior
     loss = torch.zeros(1, dtype=torch.float64, device=dev) if loss is None else loss
     G = torch.empty_like(theta)
     ydt = torch.float32 if likelihood == BERNOULLI else torch.int32
+    nbytes = lib().brn_linear_particles_workspace_bytes(N, F, C, n) if likelihood == BERNOULLI else 0
+    ws = _workspace(dev, nbytes) if nbytes else None
     _check(lib().brn_linear_particles_loss_grad(_ptr(X, what="X"), _ptr(y, ydt, "y"), likelihood, N, F, C,
                                                 _ptr(theta, what="theta"), n, _ptr(prior_loc, what="prior_loc"),
                                                 _ptr(prior_scale, what="prior_scale"), _ptr(G), _ptr(loss, torch.float64),
+                                                ws.data_ptr() if ws is not None else None, nbytes,
                                                 _stream(dev)), "brn_linear_particles_loss_grad")
     return loss, G
 

@@ -245,41 +245,51 @@ static int linear_tc_chunk_rows(int S, int sms) {
     return mt * 128;
 }
 
-struct LinearWorkspace {
-    float *eps, *W, *dW, *stats;
-    // tcgen05 variant (Bernoulli, C == 1): TF32-split operands
+// TF32-split operands and scratch of the tcgen05 variant (Bernoulli, C == 1); S = weight vectors (MC samples or particles)
+struct LinearTcBuffers {
     float *Wh, *Wl, *Xh, *Xl, *Xth, *Xtl, *dTh, *dTl, *dWpart;
     int64_t ldF, ldN, ldNB;
     int nb, slices;
+    template <class Take>
+    void carve(Take&& take, int S, int64_t N, int F, int sms) {
+        ldF = (F + 3) / 4 * 4;
+        ldN = (N + 3) / 4 * 4;
+        nb = linear_tc_chunk_rows(S, sms);
+        if (nb > N) nb = (int)((N + 127) / 128 * 128);
+        ldNB = nb;
+        const int m2 = (S + UG_BM - 1) / UG_BM;
+        slices = (2 * m2 <= sms) ? sms / m2 : 1;
+        Wh = take((size_t)S * ldF); Wl = take((size_t)S * ldF);
+        Xh = take((size_t)N * ldF); Xl = take((size_t)N * ldF);
+        Xth = take((size_t)F * ldN); Xtl = take((size_t)F * ldN);
+        dTh = take((size_t)S * ldNB); dTl = take((size_t)S * ldNB);
+        dWpart = take((size_t)slices * S * F);
+    }
+};
+
+struct WorkspaceCarver {
+    void* base; size_t off = 0;
+    explicit WorkspaceCarver(void* b) : base(b) {}
+    float* operator()(size_t nfloat) {
+        float* p = base ? reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off) : nullptr;
+        off += (nfloat * sizeof(float) + 255) / 256 * 256;
+        return p;
+    }
+};
+
+struct LinearWorkspace {
+    float *eps, *W, *dW, *stats;
+    LinearTcBuffers tc;
     size_t bytes;
-    LinearWorkspace(void* base, int64_t numel, int S, int64_t N = 0, int F = 0, bool tc = false, int sms = 148) {
-        size_t off = 0;
-        auto take = [&](size_t nfloat) {
-            float* p = base ? reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off) : nullptr;
-            off += (nfloat * sizeof(float) + 255) / 256 * 256;
-            return p;
-        };
+    LinearWorkspace(void* base, int64_t numel, int S, int64_t N = 0, int F = 0, bool use_tc = false, int sms = 148) {
+        WorkspaceCarver take(base);
         eps = take((size_t)S * numel);
         W = take((size_t)S * numel);
         dW = take((size_t)S * numel);
         stats = take(4 * (size_t)((numel + 3) / 4 * 4));
-        Wh = Wl = Xh = Xl = Xth = Xtl = dTh = dTl = dWpart = nullptr;
-        ldF = ldN = ldNB = 0; nb = 0; slices = 0;
-        if (tc) {
-            ldF = (F + 3) / 4 * 4;
-            ldN = (N + 3) / 4 * 4;
-            nb = linear_tc_chunk_rows(S, sms);
-            if (nb > N) nb = (int)((N + 127) / 128 * 128);
-            ldNB = nb;
-            const int m2 = (S + UG_BM - 1) / UG_BM;
-            slices = (2 * m2 <= sms) ? sms / m2 : 1;
-            Wh = take((size_t)S * ldF); Wl = take((size_t)S * ldF);
-            Xh = take((size_t)N * ldF); Xl = take((size_t)N * ldF);
-            Xth = take((size_t)F * ldN); Xtl = take((size_t)F * ldN);
-            dTh = take((size_t)S * ldNB); dTl = take((size_t)S * ldNB);
-            dWpart = take((size_t)slices * S * F);
-        }
-        bytes = off;
+        tc = LinearTcBuffers();
+        if (use_tc) tc.carve(take, S, N, F, sms);
+        bytes = take.off;
     }
 };
 
@@ -355,9 +365,58 @@ static int launch_linear_fused(const float* X, const void* y, int likelihood, in
     return 0;
 }
 
+// tcgen05 variant of the fused Bernoulli log-likelihood + gradient for S weight vectors W [S, F] (N > 0):
+//   per row chunk, (1) logits GEMM with the Bernoulli likelihood fused in its epilogue (writes d = y - sigmoid(l)
+//   transposed + TF32-split; loss += loss_scale * sum ll), (2) gradient GEMM dW[s,f] += d^T X, K-split over the grid
+//   with per-slice accumulation (no atomics); finally the slices are summed into dW [S, F] = + d ll / d W.
+static int launch_linear_tc(const float* X, const float* y, int64_t N, int F, int S, const float* W, float* dW, float loss_scale,
+                            double* loss, const LinearTcBuffers& b, const char* stage_split, const char* stage_fused,
+                            cudaStream_t stream) {
+    int drain = 2;
+    if (const char* env = getenv("BRN_UMMA_DRAIN")) drain = atoi(env);
+    {
+        StageTimer sp(stage_split, stream);
+        if (int e = launch_split_tf32(W, F, S, F, b.Wh, b.Wl, b.ldF, nullptr, nullptr, 0, stream)) return e;
+        if (int e = launch_split_tf32(X, F, (int)N, F, b.Xh, b.Xl, b.ldF, b.Xth, b.Xtl, b.ldN, stream)) return e;
+        BRN_CUDA_OK(cudaMemsetAsync(b.dWpart, 0, sizeof(float) * (size_t)b.slices * S * F, stream));
+    }
+    StageTimer st2(stage_fused, stream);
+    for (int64_t r0 = 0; r0 < N; r0 += b.nb) {
+        const int nb = (int)((N - r0 < b.nb) ? (N - r0) : b.nb);
+        EpiBernoulli::Params e1;
+        e1.y = y + r0; e1.dT_hi = b.dTh; e1.dT_lo = b.dTl; e1.rows = nb; e1.cols = S;
+        e1.ld = b.ldNB; e1.loss = loss; e1.neg_inv_S = loss_scale;
+        if (int e = launch_umma_nt<LT_BN1, LT_BK, EpiBernoulli>(b.Xh + r0 * b.ldF, b.Xl + r0 * b.ldF, nb, b.ldF, b.Wh, b.Wl, S,
+                                                                 b.ldF, F, 0, drain, e1, stream))
+            return e;
+        // K tail of the last chunk: the TMA box zero-fills columns >= nb of d^T (tensor map extent = nb)
+        EpiAccum::Params e2;
+        e2.out = b.dWpart; e2.rows = S; e2.cols = F; e2.ld = F; e2.slice_stride = (int64_t)S * F;
+        if (int e = launch_umma_nt<LT_BN2, LT_BK, EpiAccum>(b.dTh, b.dTl, S, b.ldNB, b.Xth + r0, b.Xtl + r0, F, b.ldN, nb, 0,
+                                                             drain, e2, stream, b.slices > 1))
+            return e;
+    }
+    const int64_t tot = (int64_t)S * F;
+    sum_slices_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(b.dWpart, b.slices, tot, tot, dW);
+    BRN_LAUNCH_OK("sum_slices_kernel");
+    return 0;
+}
+
+extern "C" size_t brn_linear_particles_workspace_bytes(int64_t N, int F, int C, int n) {
+    if (N < 0 || F <= 0 || C <= 0 || n < 0) return 0;
+    if (!(C == 1 && F % 4 == 0 && F <= LT_BN2 && N >= 1 && n >= 1)) return 0;      // only the tcgen05 variant needs scratch
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    WorkspaceCarver take(nullptr);
+    LinearTcBuffers b;
+    b.carve(take, n, N, F, sms);
+    return take.off;
+}
+
 extern "C" int brn_linear_particles_loss_grad(const float* X, const void* y, int likelihood, int64_t N, int F, int C,
                                               const float* theta, int n, const float* prior_loc, const float* prior_scale,
-                                              float* G, double* loss, void* stream_) {
+                                              float* G, double* loss, void* workspace, size_t workspace_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     BRN_CHECK_ARG(theta && G && loss, "brn_linear_particles_loss_grad: NULL pointer");
     BRN_CHECK_ARG(N >= 0 && F > 0 && C > 0 && n >= 0, "brn_linear_particles_loss_grad: bad shape N=%lld F=%d C=%d n=%d",
@@ -368,12 +427,27 @@ extern "C" int brn_linear_particles_loss_grad(const float* X, const void* y, int
     BRN_CHECK_ARG(likelihood == 1 || C == 1, "Bernoulli/Binomial likelihood needs C == 1 (got %d)", C);
     BRN_CHECK_ARG((prior_loc == nullptr) == (prior_scale == nullptr), "prior_loc and prior_scale must both be given or both NULL");
     if (n == 0) return 0;
-    set_variant("simt");
+    // tcgen05 variant (the K2 GEMM pair with the particles as the weight vectors) when the caller provides scratch
+    const bool use_tc = workspace != nullptr && N > 0 && linear_use_tc(likelihood, N, F, C, n);
+    set_variant(use_tc ? "tcgen05" : "simt");
     const int64_t numel = (int64_t)C * F, total = numel * n;
-    BRN_CUDA_OK(cudaMemsetAsync(G, 0, sizeof(float) * (size_t)total, stream));
-    if (N > 0) {
-        StageTimer st("particles.loglik_grad", stream);
-        if (int e = launch_linear_fused(X, y, likelihood, N, F, C, n, theta, G, 1.0f, loss, stream)) return e;
+    if (use_tc) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        WorkspaceCarver take(workspace);
+        LinearTcBuffers b;
+        b.carve(take, n, N, F, sms);
+        BRN_CHECK_ARG(workspace_bytes >= take.off, "workspace too small: %zu < %zu", workspace_bytes, take.off);
+        if (int e = launch_linear_tc(X, reinterpret_cast<const float*>(y), N, F, n, theta, G, -1.0f, loss, b,
+                                     "particles.split_operands", "particles.loglik_grad", stream))
+            return e;
+    } else {
+        BRN_CUDA_OK(cudaMemsetAsync(G, 0, sizeof(float) * (size_t)total, stream));
+        if (N > 0) {
+            StageTimer st("particles.loglik_grad", stream);
+            if (int e = launch_linear_fused(X, y, likelihood, N, F, C, n, theta, G, 1.0f, loss, stream)) return e;
+        }
     }
     StageTimer st2("particles.prior", stream);
     particles_prior_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(theta, prior_loc, prior_scale, numel, total, G, loss);
@@ -456,36 +530,9 @@ extern "C" int brn_linear_elbo_fwd_bwd(const float* X, const void* y, int likeli
     if (!use_tc) BRN_CUDA_OK(cudaMemsetAsync(ws.dW, 0, sizeof(float) * (size_t)S * numel, stream));
     delete st;
     if (N > 0 && use_tc) {
-        // ---- tcgen05 variant: per row chunk, (1) logits GEMM with the Bernoulli likelihood fused in its epilogue
-        //      (writes d = y - sigmoid(l) transposed + TF32-split), (2) gradient GEMM dW[s,f] += d^T X, K-split over
-        //      the grid with per-slice accumulation (no atomics); finally the slices are summed.
-        int drain = 2;
-        if (const char* env = getenv("BRN_UMMA_DRAIN")) drain = atoi(env);
-        {
-            StageTimer sp("linear.split_operands", stream);
-            if (int e = launch_split_tf32(ws.W, F, S, F, ws.Wh, ws.Wl, ws.ldF, nullptr, nullptr, 0, stream)) return e;
-            if (int e = launch_split_tf32(X, F, (int)N, F, ws.Xh, ws.Xl, ws.ldF, ws.Xth, ws.Xtl, ws.ldN, stream)) return e;
-            BRN_CUDA_OK(cudaMemsetAsync(ws.dWpart, 0, sizeof(float) * (size_t)ws.slices * S * F, stream));
-        }
-        StageTimer st2("linear.fused", stream);
-        for (int64_t r0 = 0; r0 < N; r0 += ws.nb) {
-            const int nb = (int)((N - r0 < ws.nb) ? (N - r0) : ws.nb);
-            EpiBernoulli::Params e1;
-            e1.y = reinterpret_cast<const float*>(y) + r0; e1.dT_hi = ws.dTh; e1.dT_lo = ws.dTl; e1.rows = nb; e1.cols = S;
-            e1.ld = ws.ldNB; e1.loss = loss; e1.neg_inv_S = -1.0f / (float)r->s_total;
-            if (int e = launch_umma_nt<LT_BN1, LT_BK, EpiBernoulli>(ws.Xh + r0 * ws.ldF, ws.Xl + r0 * ws.ldF, nb, ws.ldF, ws.Wh, ws.Wl, S,
-                                                                     ws.ldF, F, 0, drain, e1, stream))
-                return e;
-            // K tail of the last chunk: the TMA box zero-fills columns >= nb of d^T (tensor map extent = nb)
-            EpiAccum::Params e2;
-            e2.out = ws.dWpart; e2.rows = S; e2.cols = F; e2.ld = F; e2.slice_stride = (int64_t)S * F;
-            if (int e = launch_umma_nt<LT_BN2, LT_BK, EpiAccum>(ws.dTh, ws.dTl, S, ws.ldNB, ws.Xth + r0, ws.Xtl + r0, F, ws.ldN, nb, 0,
-                                                                 drain, e2, stream, ws.slices > 1))
-                return e;
-        }
-        const int64_t tot = (int64_t)S * F;
-        sum_slices_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(ws.dWpart, ws.slices, tot, tot, ws.dW);
-        BRN_LAUNCH_OK("sum_slices_kernel");
+        if (int e = launch_linear_tc(X, reinterpret_cast<const float*>(y), N, F, S, ws.W, ws.dW, -1.0f / (float)r->s_total, loss,
+                                     ws.tc, "linear.split_operands", "linear.fused", stream))
+            return e;
     } else if (N > 0) {
         StageTimer st2("linear.fused", stream);
         if (int e = launch_linear_fused(X, y, likelihood, N, F, C, S, ws.W, ws.dW, 1.0f / (float)r->s_total, loss, stream)) return e;

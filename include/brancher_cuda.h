@@ -159,9 +159,12 @@ int brn_dag_elbo_fwd_bwd(const brn_dag_op* ops, int n_ops, int n_slots, const fl
  *     no 1/n, exactly as SteinVariationalGradientDescent.correct_gradient / update_bandwidth compute it with four
  *     nested Python loops (inference.py:301-324).  `bandwidth` is a DEVICE float: written when update_bandwidth != 0,
  *     read otherwise.  out [rows, d] is overwritten. */
+/*     workspace: brn_linear_particles_workspace_bytes() bytes of scratch selects the tcgen05 variant (the K2 GEMM pair
+ *     with the particles as weight vectors; Bernoulli, C == 1, F % 4 == 0, large N and n); NULL / 0 runs the SIMT kernel. */
+size_t brn_linear_particles_workspace_bytes(int64_t N, int F, int C, int n);
 int brn_linear_particles_loss_grad(const float* X, const void* y, int likelihood, int64_t N, int F, int C,
                                    const float* theta, int n, const float* prior_loc, const float* prior_scale,
-                                   float* G, double* loss, void* stream);
+                                   float* G, double* loss, void* workspace, size_t workspace_bytes, void* stream);
 size_t brn_svgd_workspace_bytes(int n, int d);
 int brn_svgd_direction(const float* theta, const float* grad, int n, int d, int row0, int rows, int update_bandwidth,
                        float* bandwidth, float* out, void* workspace, size_t workspace_bytes, void* stream);

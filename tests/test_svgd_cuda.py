@@ -106,3 +106,23 @@ def test_particles_loss_grad_vs_oracle(cu, N, F, C, n, lik):
     loss, G = cu.linear_particles_loss_grad(dev(X).reshape(N, F), yd, code, dev(theta).reshape(n, -1), C)
     assert_close(loss.item(), l64, "particles loss (no prior)")
     assert_close(G.cpu().numpy().reshape(g64.shape), g64, "particles grad (no prior)", scale=max(np.abs(g64).max(), 1e-8))
+
+
+@pytest.mark.parametrize("N,F,n,force", [(300, 128, 130, True), (1000, 20, 70, True), (5000, 128, 200, False), (4200, 64, 257, False)])
+def test_particles_loss_grad_tcgen05_variant(cu, monkeypatch, N, F, n, force):
+    """K4a through the K2 tcgen05 GEMM pair (particles as the weight vectors): ragged row/particle counts, both the
+    automatic selection (large N, n) and the forced one at small shapes; same tolerance as the SIMT path."""
+    from oracle import elbo_oracle as O
+    if force:
+        monkeypatch.setenv("BRN_LINEAR_VARIANT", "tcgen05")
+    rng = np.random.RandomState(N + n)
+    X = rng.randn(N, F).astype("f4")
+    theta = (0.5 * rng.randn(n, 1, F)).astype("f4")
+    pl, ps = (0.1 * rng.randn(1, F)).astype("f4"), (0.5 + rng.rand(1, F)).astype("f4")
+    y = (rng.rand(N) < 0.5).astype("f4")
+    l64, g64 = O.particles_loss_grad(X, y, theta, (pl, ps), dtype=torch.float64, likelihood="binomial")
+    loss, G = cu.linear_particles_loss_grad(dev(X), dev(y), cu.BERNOULLI, dev(theta).reshape(n, -1), 1, dev(pl).reshape(-1),
+                                            dev(ps).reshape(-1))
+    assert cu.last_variant() == "tcgen05"
+    assert_close(loss.item(), l64, "particles loss (tcgen05)")
+    assert_close(G.cpu().numpy().reshape(g64.shape), g64, "particles grad (tcgen05)", scale=np.abs(g64).max())
