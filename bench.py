@@ -441,6 +441,12 @@ def main_ours(args):
         return reduce_partials(device_step(it))
 
     def e2e_step(it):
+        if wl == "logreg":
+            # public host-fed entry: row slabs copied on a side stream while the previous slab is evaluated
+            r = cu.sample_range(S_total, seed=args.seed, offset=it)
+            gflat.zero_()
+            loss = cu.linear_elbo_fwd_bwd_host(Xpin, ypin, cu.BERNOULLI, w, 1, r, dev, with_prior=(rank == 0))
+            return float(reduce_partials(loss).item())
         Xd = Xpin.to(dev, non_blocking=True)
         yd = ypin.to(dev, non_blocking=True) if ypin is not None else None
         loss = reduce_partials(device_step(it, Xd, yd))

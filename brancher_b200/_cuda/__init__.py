@@ -301,6 +301,49 @@ def linear_elbo_fwd_bwd(X, y, likelihood, w, C, r, with_prior=True, loss=None):
     return loss
 
 
+_host_feed = {}
+
+
+def linear_elbo_fwd_bwd_host(X_host, y_host, likelihood, w, C, r, device, with_prior=True, loss=None, slabs=8):
+    """K2 fed from pinned HOST buffers (the minibatch loader's side of the path, distributions.py:410-462): the rows are
+    cut into `slabs` slabs and slab i+1 is copied host->device on a side stream while slab i is being evaluated, through
+    two device staging buffers.  Every slab call regenerates the same weight samples from the Philox range `r`, the
+    gradients and the loss accumulate (+=) across the calls and the prior/entropy terms are counted once, so the result
+    equals one call on the whole [N, F] matrix up to fp32 summation order."""
+    if not (X_host.is_pinned() and y_host.is_pinned()):
+        raise BrancherCudaError("linear_elbo_fwd_bwd_host: X_host and y_host must be pinned host tensors")
+    N, F = X_host.shape
+    loss = torch.zeros(1, dtype=torch.float64, device=device) if loss is None else loss
+    if N == 0:
+        return linear_elbo_fwd_bwd(torch.empty((0, F), device=device), torch.empty((0,), dtype=y_host.dtype, device=device),
+                                   likelihood, w, C, r, with_prior, loss)
+    slabs = max(1, min(int(slabs), (N + 127) // 128))
+    rows = ((N + slabs - 1) // slabs + 127) // 128 * 128
+    key = (device.type, device.index, rows, F, y_host.dtype)
+    st = _host_feed.get(key)
+    if st is None:
+        st = {"copy": torch.cuda.Stream(device), "X": [torch.empty((rows, F), device=device) for _ in range(2)],
+              "y": [torch.empty((rows,), dtype=y_host.dtype, device=device) for _ in range(2)],
+              "ready": [torch.cuda.Event() for _ in range(2)], "done": [torch.cuda.Event() for _ in range(2)]}
+        _host_feed[key] = st
+    main = torch.cuda.current_stream(device)
+    st["copy"].wait_stream(main)            # staging buffers may still be read by an earlier evaluation
+    i = 0
+    for r0 in range(0, N, rows):
+        n, b = min(rows, N - r0), i & 1
+        with torch.cuda.stream(st["copy"]):
+            if i >= 2:
+                st["copy"].wait_event(st["done"][b])
+            st["X"][b][:n].copy_(X_host[r0:r0 + n], non_blocking=True)
+            st["y"][b][:n].copy_(y_host[r0:r0 + n], non_blocking=True)
+            st["ready"][b].record(st["copy"])
+        main.wait_event(st["ready"][b])
+        linear_elbo_fwd_bwd(st["X"][b][:n], st["y"][b][:n], likelihood, w, C, r, with_prior and i == 0, loss)
+        st["done"][b].record(main)
+        i += 1
+    return loss
+
+
 def dag_elbo_fwd_bwd(ops, n_ops, n_slots, params, data, n_rows, eps, n_eps, r, loss=None):
     """K1.  ops: uint8 CUDA tensor holding n_ops packed `brn_dag_op` records (24 bytes each); params [n_params] fp32;
     data [n_rows, n_cols] fp32 or None; eps [s_local, n_eps] fp32 or None (Philox).  Returns (loss fp64 [1], dparams)."""

@@ -230,7 +230,8 @@ __global__ void __launch_bounds__(256, 1) linear_fused_kernel(LinearArgs a) {
     if (t == 0 && a.loss) atomicAdd(a.loss, -tot * (double)a.inv_S);
 }
 
-constexpr int LT_BN1 = 208;       // logits GEMM: samples per n-tile
+constexpr int LT_BN1 = 256;       // logits GEMM: samples per n-tile (16 epilogue warps x 64 columns)
+constexpr int LT_EW1 = 16;
 constexpr int LT_BN2 = 128;       // gradient GEMM: features per n-tile (F <= 128)
 constexpr int LT_BK = 16;
 
@@ -386,7 +387,7 @@ static int launch_linear_tc(const float* X, const float* y, int64_t N, int F, in
         EpiBernoulli::Params e1;
         e1.y = y + r0; e1.dT_hi = b.dTh; e1.dT_lo = b.dTl; e1.rows = nb; e1.cols = S;
         e1.ld = b.ldNB; e1.loss = loss; e1.neg_inv_S = loss_scale;
-        if (int e = launch_umma_nt<LT_BN1, LT_BK, EpiBernoulli>(b.Xh + r0 * b.ldF, b.Xl + r0 * b.ldF, nb, b.ldF, b.Wh, b.Wl, S,
+        if (int e = launch_umma_nt<LT_BN1, LT_BK, EpiBernoulli, LT_EW1>(b.Xh + r0 * b.ldF, b.Xl + r0 * b.ldF, nb, b.ldF, b.Wh, b.Wl, S,
                                                                  b.ldF, F, 0, drain, e1, stream))
             return e;
         // K tail of the last chunk: the TMA box zero-fills columns >= nb of d^T (tensor map extent = nb)

@@ -78,15 +78,18 @@ struct UnitIter {
     __device__ int kc_end() const { return u < end ? k_chunks : (int)((long long)(tail_j + 1) * k_chunks / J); }
 };
 
-template <int BN, int BK, class Epi>
-__global__ void __launch_bounds__(64 + 32 * UG_EPI_WARPS, 1)
+// EW = epilogue warps (8 or 16): 4 TMEM lane quarters x EW/4 column blocks of CPT = BN / (EW/4) columns.  16 warps halve the
+// per-thread register footprint (BN = 256 becomes possible) and double the issue-level parallelism of a heavy epilogue.
+template <int BN, int BK, class Epi, int EW = UG_EPI_WARPS>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                       const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                       int m_tiles, int n_tiles, int k_chunks, int drain_chunks, int mode, int split_T, int full_units,
                       typename Epi::Params ep) {
     using SM = UmmaSmem<BN, BK>;
     constexpr int UG_STAGES = SM::STAGES, UG_BK = BK, SW = BK * 4;
-    constexpr int CPT = BN / 2;                    // accumulator columns per epilogue thread
+    constexpr int CPT = BN / (EW / 4);             // accumulator columns per epilogue thread
+    static_assert(EW == 8 || EW == 16, "8 or 16 epilogue warps");
     static_assert(BN <= UG_BUF_COLS && BN % 16 == 0 && CPT % 8 == 0, "unsupported N tile");
     constexpr uint32_t TMEM_COLS = 512;
     extern __shared__ uint8_t smem_raw[];
@@ -100,7 +103,7 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
         umma::tma_prefetch_desc(&tmAh); umma::tma_prefetch_desc(&tmAl);
         umma::tma_prefetch_desc(&tmBh); umma::tma_prefetch_desc(&tmBl);
         for (int s = 0; s < UG_STAGES; ++s) { umma::mbar_init(&full_bar[s], 1); umma::mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < 2; ++b) { umma::mbar_init(&acc_full[b], 1); umma::mbar_init(&acc_empty[b], UG_EPI_WARPS); }
+        for (int b = 0; b < 2; ++b) { umma::mbar_init(&acc_full[b], 1); umma::mbar_init(&acc_empty[b], EW); }
         umma::fence_barrier_init();
     }
     if (warp == 1) umma::tmem_alloc(&tmem_base_slot, TMEM_COLS);
@@ -167,7 +170,7 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
         // ===================== epilogue warps =====================
         const int ew = warp - 2;
         const int q = warp & 3;                   // TMEM lane quarter this warp may access (warp id % 4)
-        const int hf = ew >> 2;                   // column half
+        const int hf = ew >> 2;                   // column block (half / quarter of the tile)
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + hf * CPT;
         uint32_t blk = 0;
         for (UnitIter it(m_tiles, n_tiles, k_chunks, mode, split_T, full_units); it.valid(); it.next()) {
@@ -180,20 +183,22 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
                 umma::mbar_wait(&acc_full[buf], use);
                 umma::tc_fence_after();
                 const uint32_t t0 = t_lane + buf * UG_BUF_COLS;
+                constexpr int C32 = EW == 16 ? 0 : CPT / 32 * 32;     // 16 warps: 16-column pieces only (register budget 112)
 #pragma unroll
-                for (int c = 0; c + 32 <= CPT; c += 32) {
+                for (int c = 0; c + 32 <= C32; c += 32) {
                     float v[32];
                     umma::tmem_ld_32x32(t0 + c, v);
                     umma::tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 32; ++i) r[c + i] += v[i];
                 }
-                if (CPT % 32 >= 16) {
+#pragma unroll
+                for (int c = C32; c + 16 <= CPT; c += 16) {
                     float v[16];
-                    umma::tmem_ld_32x16(t0 + (CPT / 32) * 32, v);
+                    umma::tmem_ld_32x16(t0 + c, v);
                     umma::tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) r[(CPT / 32) * 32 + i] += v[i];
+                    for (int i = 0; i < 16; ++i) r[c + i] += v[i];
                 }
                 if (CPT % 16 == 8) {
                     float v[8];
@@ -206,7 +211,7 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
                 __syncwarp();
                 if (lane == 0) umma::mbar_arrive(&acc_empty[buf]);
             }
-            Epi::finish(ep, r, it.mt() * UG_BM + q * 32 + lane, it.nt() * 2 + hf, it.in_tail(), it.slice());
+            Epi::finish(ep, r, it.mt() * UG_BM + q * 32 + lane, it.nt() * (EW / 4) + hf, it.in_tail(), it.slice());
         }
     }
     umma::tc_fence_before();
@@ -288,26 +293,47 @@ struct EpiBernoulli {
     struct Params {
         const float* y; float* dT_hi; float* dT_lo; int rows, cols; int64_t ld; double* loss; float neg_inv_S;
     };
+    // one element: log-likelihood term and the TF32-split gradient d = y - sigmoid(l).  MUFU ex2 / rcp / lg2 (absolute errors
+    // ~1e-7, far inside the parity budget), no slow-path calls: the epilogue warps are the pace-setter of this GEMM (K = F
+    // is short), so every instruction here is on the critical path (profiles/r1g_ncu_full_logreg_summary.txt).
+    static __device__ __forceinline__ float element(float l, float yv, float& hi, float& lo) {
+        float e, inv, lg;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * fabsf(l)));
+        const float ope = 1.f + e;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(ope));
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(ope));
+        const float sig = l >= 0.f ? inv : e * inv;
+        umma::split_tf32(yv - sig, hi, lo);
+        return __fmaf_rn(yv, l, -__fmaf_rn(lg, 0.6931471805599453f, fmaxf(l, 0.f)));
+    }
     template <int CPT>
     static __device__ __forceinline__ void finish(const Params& p, float (&r)[CPT], int row, int blk, bool, int) {
         const bool row_ok = row < p.rows;
         const float yv = row_ok ? p.y[row] : 0.f;
         const int valid = row_ok ? min(CPT, p.cols - blk * CPT) : 0;
         float ll = 0.f;
-        float* ohi = p.dT_hi + (int64_t)blk * CPT * p.ld + row;
-        float* olo = p.dT_lo + (int64_t)blk * CPT * p.ld + row;
+        const int64_t ld = p.ld;
+        float* ohi = p.dT_hi + (int64_t)blk * CPT * ld + row;
+        const int64_t lo_off = p.dT_lo - p.dT_hi;      // element offset between the two buffers (same allocation)
+        if (valid == CPT) {
 #pragma unroll          // full unroll: r[] must stay in registers (a partial unroll indexes it dynamically -> local memory)
-        for (int i = 0; i < CPT; ++i) {
-            if (i < valid) {
-                const float l = r[i];
-                const float e = __expf(-fabsf(l));
-                const float inv = __frcp_rn(1.f + e);
-                const float sig = l >= 0.f ? inv : e * inv;
-                ll += __fmaf_rn(yv, l, -(fmaxf(l, 0.f) + __logf(1.f + e)));
+            for (int i = 0; i < CPT; ++i) {
                 float hi, lo;
-                umma::split_tf32(yv - sig, hi, lo);
-                ohi[(int64_t)i * p.ld] = hi;
-                olo[(int64_t)i * p.ld] = lo;
+                ll += element(r[i], yv, hi, lo);
+                ohi[0] = hi;
+                ohi[lo_off] = lo;
+                ohi += ld;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < CPT; ++i) {
+                if (i < valid) {
+                    float hi, lo;
+                    ll += element(r[i], yv, hi, lo);
+                    ohi[0] = hi;
+                    ohi[lo_off] = lo;
+                }
+                ohi += ld;
             }
         }
         double tot = (double)ll;
@@ -350,7 +376,7 @@ inline UmmaSplitPlan umma_plan(int M, int N, int K, int sms, bool allow_split) {
 // A (hi/lo) [M][K] pitch lda, B (hi/lo) [N][K] pitch ldb; mode 0: units n-major round-robin over CTAs,
 // mode 1: every CTA keeps one m-tile and strides over n-tiles.  allow_split: the caller has zeroed the output blocks of
 // n-tiles >= umma_plan(...).first_split_ntile (mode 0 only).
-template <int BN, int BK, class Epi>
+template <int BN, int BK, class Epi, int EW = UG_EPI_WARPS>
 inline int launch_umma_nt(const float* Ah, const float* Al, int M, int64_t lda, const float* Bh, const float* Bl, int N,
                           int64_t ldb, int K, int mode, int drain_chunks, const typename Epi::Params& ep,
                           cudaStream_t stream, bool allow_split = false) {
@@ -375,10 +401,10 @@ inline int launch_umma_nt(const float* Ah, const float* Al, int M, int64_t lda, 
         grid = G * m_tiles;
     }
     if (drain_chunks < 1) drain_chunks = 2 * 32 / BK;
-    auto kern = umma_nt_3xtf32_kernel<BN, BK, Epi>;
+    auto kern = umma_nt_3xtf32_kernel<BN, BK, Epi, EW>;
     const int smem = UmmaSmem<BN, BK>::TOTAL;
     BRN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, 64 + 32 * UG_EPI_WARPS, smem, stream>>>(tAh, tAl, tBh, tBl, m_tiles, n_tiles, k_chunks, drain_chunks, mode,
+    kern<<<grid, 64 + 32 * EW, smem, stream>>>(tAh, tAl, tBh, tBl, m_tiles, n_tiles, k_chunks, drain_chunks, mode,
                                                          split_T, full_units, ep);
     BRN_LAUNCH_OK("umma_nt_3xtf32_kernel");
     return 0;
