@@ -80,6 +80,7 @@ SYMBOLS = {
     "brn_mf_normal_prior_entropy": (ctypes.c_int, [ctypes.POINTER(MFVar), ctypes.c_void_p, ctypes.c_void_p,
                                                    ctypes.POINTER(SampleRange), ctypes.c_void_p, ctypes.c_void_p]),
     "brn_bnn_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 5),
+    "brn_set_data_ready_event": (None, [ctypes.c_void_p]),
     "brn_bnn_elbo_fwd_bwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 4 +
                              [ctypes.POINTER(MFVar), ctypes.POINTER(SampleRange), ctypes.c_void_p, ctypes.c_size_t,
                               ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
@@ -264,8 +265,10 @@ def mf_normal_prior_entropy(var, r, loss=None):
     return loss
 
 
-def bnn_elbo_fwd_bwd(X, y, vars4, r, with_prior=True, loss=None):
-    """K3.  X [B,P] fp32, y [B] int32, vars4 = MeanFieldVar for (weights1 [H,P], b1 [H], weights2 [C,H], b2 [C])."""
+def bnn_elbo_fwd_bwd(X, y, vars4, r, with_prior=True, loss=None, data_ready=None):
+    """K3.  X [B,P] fp32, y [B] int32, vars4 = MeanFieldVar for (weights1 [H,P], b1 [H], weights2 [C,H], b2 [C]).
+    data_ready: a torch.cuda.Event recorded on the stream that is still copying X / y to the device; the evaluation waits
+    for it only before its first read of the minibatch, so noise generation and weight sampling overlap the copy."""
     dev = X.device
     B, P = X.shape
     H = vars4[1].numel
@@ -276,6 +279,8 @@ def bnn_elbo_fwd_bwd(X, y, vars4, r, with_prior=True, loss=None):
     nbytes = lib().brn_bnn_workspace_bytes(B, P, H, C, r.s_local)
     ws = _workspace(dev, nbytes)
     arr = (MFVar * 4)(*[v.struct() for v in vars4])
+    if data_ready is not None:
+        lib().brn_set_data_ready_event(ctypes.c_void_p(data_ready.cuda_event))
     _check(lib().brn_bnn_elbo_fwd_bwd(_ptr(X, what="X"), _ptr(y, torch.int32, "y"), B, P, H, C, arr, ctypes.byref(r),
                                       ws.data_ptr(), ws.numel(), int(with_prior), _ptr(loss, torch.float64),
                                       _stream(dev)), "brn_bnn_elbo_fwd_bwd")

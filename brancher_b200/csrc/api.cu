@@ -32,6 +32,16 @@ static long long g_launches = 0;
 
 void count_launch(int n) { g_launches += n; }
 
+// ---- "data ready" event: lets the host overlap the host->device copy of a minibatch with the sampling stage --------
+static thread_local cudaEvent_t g_data_ready = nullptr;
+int wait_data_ready(cudaStream_t stream) {
+    if (!g_data_ready) return 0;
+    cudaError_t e = cudaStreamWaitEvent(stream, g_data_ready, 0);
+    g_data_ready = nullptr;
+    if (e != cudaSuccess) { set_error("cudaStreamWaitEvent(data ready): %s", cudaGetErrorString(e)); return -2; }
+    return 0;
+}
+
 static int stage_slot(const char* name) {
     for (size_t i = 0; i < g_stages.size(); ++i)
         if (strcmp(g_stages[i]->name, name) == 0) return (int)i;
@@ -89,6 +99,8 @@ extern "C" void brn_profile_reset(void) {
     for (auto* r : brn::g_stages) { r->total_ms = 0.0; r->calls = 0; r->used = 0; }
 }
 extern "C" long long brn_launch_count(void) { return brn::g_launches; }
+
+extern "C" void brn_set_data_ready_event(void* event) { brn::g_data_ready = (cudaEvent_t)event; }
 
 extern "C" int brn_abi_version(void) { return BRN_ABI_VERSION; }
 extern "C" const char* brn_last_error(void) { return brn::g_err; }

@@ -155,6 +155,8 @@ __device__ __forceinline__ T block_sum(T v, T* scratch) {
 // ---------------------------------------------------------------------------------------------
 namespace brn {
 void count_launch(int n);
+int wait_data_ready(cudaStream_t stream);    // consumes the event of brn_set_data_ready_event (no-op when none is pending)
+
 struct StageTimer {      // RAII: records an event pair around a stage when profiling is enabled
     int slot;
     cudaStream_t stream;

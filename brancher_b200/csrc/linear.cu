@@ -249,7 +249,7 @@ static int linear_tc_chunk_rows(int S, int sms) {
 // TF32-split operands and scratch of the tcgen05 variant (Bernoulli, C == 1); S = weight vectors (MC samples or particles)
 struct LinearTcBuffers {
     float *Wh, *Wl, *Xh, *Xl, *Xth, *Xtl, *dTh, *dTl, *dWpart;
-    int64_t ldF, ldN, ldNB;
+    int64_t ldF, ldN, ldNB, n_chunks;
     int nb, slices;
     template <class Take>
     void carve(Take&& take, int S, int64_t N, int F, int sms) {
@@ -262,7 +262,11 @@ struct LinearTcBuffers {
         slices = (2 * m2 <= sms) ? sms / m2 : 1;
         Wh = take((size_t)S * ldF); Wl = take((size_t)S * ldF);
         Xh = take((size_t)N * ldF); Xl = take((size_t)N * ldF);
-        Xth = take((size_t)F * ldN); Xtl = take((size_t)F * ldN);
+        // X^T is stored PER ROW CHUNK, [chunk][F][nb]: the 128 feature rows of a gradient-GEMM B tile are then nb*4 bytes
+        // apart (one or two MB in total) instead of N*4 bytes (4 MB pitch at N = 10^6: 128 rows = 128 different 2 MB pages
+        // per TMA request -- measured: the gradient GEMM spent 71 % of its time waiting for those loads)
+        n_chunks = nb > 0 ? (N + nb - 1) / nb : 0;
+        Xth = take((size_t)n_chunks * F * ldNB); Xtl = take((size_t)n_chunks * F * ldNB);
         dTh = take((size_t)S * ldNB); dTl = take((size_t)S * ldNB);
         dWpart = take((size_t)slices * S * F);
     }
@@ -378,7 +382,13 @@ static int launch_linear_tc(const float* X, const float* y, int64_t N, int F, in
     {
         StageTimer sp(stage_split, stream);
         if (int e = launch_split_tf32(W, F, S, F, b.Wh, b.Wl, b.ldF, nullptr, nullptr, 0, stream)) return e;
-        if (int e = launch_split_tf32(X, F, (int)N, F, b.Xh, b.Xl, b.ldF, b.Xth, b.Xtl, b.ldN, stream)) return e;
+        for (int64_t c = 0; c < b.n_chunks; ++c) {
+            const int64_t r0 = c * b.nb;
+            const int nb = (int)((N - r0 < b.nb) ? (N - r0) : b.nb);
+            if (int e = launch_split_tf32(X + r0 * F, F, nb, F, b.Xh + r0 * b.ldF, b.Xl + r0 * b.ldF, b.ldF,
+                                          b.Xth + c * F * b.ldNB, b.Xtl + c * F * b.ldNB, b.ldNB, stream))
+                return e;
+        }
         BRN_CUDA_OK(cudaMemsetAsync(b.dWpart, 0, sizeof(float) * (size_t)b.slices * S * F, stream));
     }
     StageTimer st2(stage_fused, stream);
@@ -393,7 +403,8 @@ static int launch_linear_tc(const float* X, const float* y, int64_t N, int F, in
         // K tail of the last chunk: the TMA box zero-fills columns >= nb of d^T (tensor map extent = nb)
         EpiAccum::Params e2;
         e2.out = b.dWpart; e2.rows = S; e2.cols = F; e2.ld = F; e2.slice_stride = (int64_t)S * F;
-        if (int e = launch_umma_nt<LT_BN2, LT_BK, EpiAccum>(b.dTh, b.dTl, S, b.ldNB, b.Xth + r0, b.Xtl + r0, F, b.ldN, nb, 0,
+        const int64_t xt = (r0 / b.nb) * F * b.ldNB;
+        if (int e = launch_umma_nt<LT_BN2, LT_BK, EpiAccum>(b.dTh, b.dTl, S, b.ldNB, b.Xth + xt, b.Xtl + xt, F, b.ldNB, nb, 0,
                                                              drain, e2, stream, b.slices > 1))
             return e;
     }

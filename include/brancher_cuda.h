@@ -94,6 +94,11 @@ int brn_mf_normal_prior_entropy(const brn_mf_var* var, const float* lik_gw, cons
  * (gradient_estimators.py:44) and loss.backward() (inference.py:100).
  * X [B,P] fp32, y [B] int32 labels.  workspace: brn_bnn_workspace_bytes() bytes of scratch. */
 size_t brn_bnn_workspace_bytes(int B, int P, int H, int C, int s_local);
+/* Optional overlap of the minibatch copy with the sampling stage: `event` (cudaEvent_t, recorded by the caller on the
+ * stream that copies X / y to the device) is waited for by the NEXT brn_bnn_elbo_fwd_bwd of this host thread immediately
+ * before its first read of X and y -- noise generation and weight sampling run while the copy is in flight -- and is
+ * then forgotten.  Replaces the host-side minibatch hand-over of EmpiricalDistribution._get_sample (distributions.py:410-462). */
+void brn_set_data_ready_event(void* event);
 int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int P, int H, int C,
                          const brn_mf_var vars[4], const brn_sample_range* r,
                          void* workspace, size_t workspace_bytes, int with_prior,

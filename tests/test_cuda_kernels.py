@@ -219,6 +219,30 @@ def test_linear_tcgen05_variant(cu, monkeypatch, N, F, S, tied):
     check_against_oracle(loss, grads, o32, o64, "linear tcgen05 N=%d F=%d S=%d" % (N, F, S))
 
 
+@pytest.mark.parametrize("N,F,S,slabs", [(1000, 16, 9, 3), (20000, 128, 96, 4), (700, 8, 5, 50)])
+def test_linear_host_fed_pipeline(cu, N, F, S, slabs):
+    """linear_elbo_fwd_bwd_host: pinned host rows copied slab by slab on a side stream while the previous slab is being
+    evaluated; injected noise, so the result must match the oracle on the whole matrix (ragged last slab, more slabs
+    requested than 128-row tiles, both kernel variants)."""
+    from oracle import elbo_oracle as O
+    rng = np.random.RandomState(N + S)
+    X = rng.randn(N, F).astype("f4")
+    y = rng.randint(0, 2, size=N).astype("f4")
+    params = {"weights": ((0.3 * rng.randn(1, F)).astype("f4"), (rng.randn(1, F) - 1).astype("f4"))}
+    eps = {"weights": rng.randn(S, 1, F).astype("f4")}
+    prior = {"weights": (0.0, 0.5)}
+    o32 = O.logreg_elbo(X, y, params, eps, prior, row_chunk=4096)
+    o64 = O.logreg_elbo(X, y, params, eps, prior, dtype=torch.float64, row_chunk=4096)
+    (w,) = make_vars(cu, params, eps, ["weights"], prior)
+    Xp, yp = torch.tensor(X).pin_memory(), torch.tensor(y).pin_memory()
+    for _ in range(2):          # second pass reuses the staging buffers while the first may still be in flight
+        w.dmu.zero_(); w.drho.zero_()
+        loss = cu.linear_elbo_fwd_bwd_host(Xp, yp, cu.BERNOULLI, w, 1, cu.sample_range(S), torch.device("cuda:0"), slabs=slabs)
+        check_against_oracle(loss.item(), grads_of([w], ["weights"], params), o32, o64, "host-fed linear N=%d" % N)
+    with pytest.raises(cu.BrancherCudaError):
+        cu.linear_elbo_fwd_bwd_host(torch.tensor(X), yp, cu.BERNOULLI, w, 1, cu.sample_range(S), torch.device("cuda:0"))
+
+
 def test_linear_empty_rows(cu):
     """N = 0: the ELBO is prior + entropy only."""
     from oracle import elbo_oracle as O
