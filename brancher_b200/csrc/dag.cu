@@ -28,16 +28,52 @@ constexpr int DAG_MAX_PARAMS = BRN_DAG_MAX_PARAMS;     // shared-memory gradient
 
 __device__ __forceinline__ float dag_powi(float x, float p) { return powf(x, p); }
 
-template <int MAXS>      // value / adjoint slots per thread (thread-local memory)
+// One interpreted op costs a chain of dependent latencies (fetch -> decode -> operand loads -> ALU -> store), and a C1-sized
+// problem has only ~10 warps to hide them, so the interpreter is built to shorten that chain:
+//   * the program is packed to 16 bytes per op and staged in SHARED memory once per CTA (one broadcast LDS.128 per op);
+//   * the next op is fetched while the current one executes, and both slot operands (and, in the reverse sweep, the
+//     adjoint of dst) are loaded BEFORE the opcode switch so they overlap the indirect branch.
+struct __align__(16) PackedOp { uint32_t w0, w1, c; float imm; };      // w0 = opcode | dst << 8 ; w1 = a | b << 16
+
+//   * SMEM_FRAME (one warp per CTA, small programs): the value and adjoint frames live in SHARED memory, [slot][lane].
+//     Thread-local frames are written once and read later (SSA), and local stores do not allocate in L1: every operand read
+//     was an L2 round trip -- ~600 cycles per interpreted op at C1, where 10 warps cannot hide it (profiles/r1f_bench_ar1.json).
+template <int MAXS, bool SMEM_FRAME>      // MAXS: value / adjoint slots per thread when the frames are thread-local
 __global__ void __launch_bounds__(128)
 dag_elbo_kernel(const brn_dag_op* __restrict__ ops, int n_ops, int n_slots, const float* __restrict__ params, int n_params,
                 const float* __restrict__ data, int n_cols, int B, const float* __restrict__ eps, int n_eps,
                 brn_sample_range r, float* __restrict__ dparams, double* __restrict__ loss) {
-    extern __shared__ float sgrad[];          // [n_params]
+    extern __shared__ __align__(16) unsigned char dag_smem[];
+    PackedOp* sops = reinterpret_cast<PackedOp*>(dag_smem);                    // [n_ops]
+    float* sgrad = reinterpret_cast<float*>(dag_smem + sizeof(PackedOp) * (size_t)n_ops);   // [n_params]
     __shared__ double red[32];
-    float v[MAXS];
-    float adj[MAXS];
+    float vloc[SMEM_FRAME ? 1 : MAXS];
+    float aloc[SMEM_FRAME ? 1 : MAXS];
+    // shared frames start after sgrad, 128-byte aligned; [slot][lane] -> conflict-free, one wavefront per access
+    float* const fbase = reinterpret_cast<float*>(
+        (reinterpret_cast<uintptr_t>(sgrad + n_params) + 127) & ~(uintptr_t)127) + threadIdx.x;
+    float* const vsm = fbase;
+    float* const asm_ = fbase + (size_t)n_slots * 32;
+    auto V = [&](int i) -> float& {
+        if constexpr (SMEM_FRAME) return vsm[i * 32];
+        else return vloc[i];
+    };
+    auto A = [&](int i) -> float& {
+        if constexpr (SMEM_FRAME) return asm_[i * 32];
+        else return aloc[i];
+    };
+    const int last_slot = n_slots - 1;
     for (int i = threadIdx.x; i < n_params; i += blockDim.x) sgrad[i] = 0.f;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n_ops; i += blockDim.x) {
+        const brn_dag_op o = ops[i];
+        PackedOp q;
+        q.w0 = (uint32_t)o.opcode | ((uint32_t)o.dst << 8);
+        q.w1 = ((uint32_t)o.a & 0xffffu) | ((uint32_t)o.b << 16);
+        q.c = (uint32_t)o.c;
+        q.imm = o.imm;
+        sops[i] = q;
+    }
     __syncthreads();
 
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -49,8 +85,14 @@ dag_elbo_kernel(const brn_dag_op* __restrict__ ops, int n_ops, int n_slots, cons
 
     if (active) {
         // ---------------- forward
+        uint4 nxt = *reinterpret_cast<const uint4*>(&sops[0]);
         for (int i = 0; i < n_ops; ++i) {
-            const brn_dag_op o = ops[i];
+            const uint4 w = nxt;
+            nxt = *reinterpret_cast<const uint4*>(&sops[min(i + 1, n_ops - 1)]);
+            struct { int opcode, dst, a, b, c; float imm; } o;
+            o.opcode = (int)(w.x & 0xffu); o.dst = (int)(w.x >> 8); o.a = (int)(w.y & 0xffffu); o.b = (int)(w.y >> 16);
+            o.c = (int)w.z; o.imm = __uint_as_float(w.w);
+            const float va = V(min(o.a, last_slot)), vb = V(min(o.b, last_slot));       // operand loads overlap the branch
             float x = 0.f;
             switch (o.opcode) {
                 case DAG_CONST: x = o.imm; break;
@@ -60,81 +102,87 @@ dag_elbo_kernel(const brn_dag_op* __restrict__ ops, int n_ops, int n_slots, cons
                     x = eps ? eps[(int64_t)s * n_eps + o.a]
                             : philox_normal1(r.seed, r.offset, (uint32_t)o.a, (uint32_t)(r.s0 + s), 0);
                     break;
-                case DAG_ADD: x = v[o.a] + v[o.b]; break;
-                case DAG_SUB: x = v[o.a] - v[o.b]; break;
-                case DAG_MUL: x = v[o.a] * v[o.b]; break;
-                case DAG_DIV: x = v[o.a] / v[o.b]; break;
-                case DAG_NEG: x = -v[o.a]; break;
-                case DAG_POWI: x = dag_powi(v[o.a], o.imm); break;
-                case DAG_EXP: x = expf(v[o.a]); break;
-                case DAG_LOG: x = logf(v[o.a]); break;
-                case DAG_LOG1P: x = log1pf(v[o.a]); break;
-                case DAG_SIGMOID: x = sigmoidf(v[o.a]); break;
-                case DAG_SOFTPLUS: x = softplusf(v[o.a]); break;
-                case DAG_TANH: x = tanhf(v[o.a]); break;
-                case DAG_SIN: x = sinf(v[o.a]); break;
-                case DAG_COS: x = cosf(v[o.a]); break;
-                case DAG_RELU: x = fmaxf(v[o.a], 0.f); break;
-                case DAG_SQRT: x = sqrtf(v[o.a]); break;
-                case DAG_ABS: x = fabsf(v[o.a]); break;
-                case DAG_CLAMP_UNIT: x = fminf(fmaxf(v[o.a], 1.17549435e-38f), 1.0f - 1.1920929e-07f); break;
+                case DAG_ADD: x = va + vb; break;
+                case DAG_SUB: x = va - vb; break;
+                case DAG_MUL: x = va * vb; break;
+                case DAG_DIV: x = va / vb; break;
+                case DAG_NEG: x = -va; break;
+                case DAG_POWI: x = dag_powi(va, o.imm); break;
+                case DAG_EXP: x = expf(va); break;
+                case DAG_LOG: x = logf(va); break;
+                case DAG_LOG1P: x = log1pf(va); break;
+                case DAG_SIGMOID: x = sigmoidf(va); break;
+                case DAG_SOFTPLUS: x = softplusf(va); break;
+                case DAG_TANH: x = tanhf(va); break;
+                case DAG_SIN: x = sinf(va); break;
+                case DAG_COS: x = cosf(va); break;
+                case DAG_RELU: x = fmaxf(va, 0.f); break;
+                case DAG_SQRT: x = sqrtf(va); break;
+                case DAG_ABS: x = fabsf(va); break;
+                case DAG_CLAMP_UNIT: x = fminf(fmaxf(va, 1.17549435e-38f), 1.0f - 1.1920929e-07f); break;
                 case DAG_NORMAL_LP: {      // torch Normal.log_prob: -((x-mu)^2)/(2 sigma^2) - log sigma - log sqrt(2 pi)
-                    const float df = v[o.a] - v[o.b], sg = v[o.c];
+                    const float df = va - vb, sg = V(o.c);
                     x = -(df * df) / (2.f * (sg * sg)) - logf(sg) - BRN_HALF_LOG_2PI;
                     break;
                 }
-                case DAG_NORMAL_ENTROPY: x = 0.5f + BRN_HALF_LOG_2PI + logf(v[o.a]); break;
-                case DAG_ACC_SAMPLE: if (b == 0) acc += v[o.a]; break;
-                case DAG_ACC_ROW: acc += v[o.a]; break;
+                case DAG_NORMAL_ENTROPY: x = 0.5f + BRN_HALF_LOG_2PI + logf(va); break;
+                case DAG_ACC_SAMPLE: if (b == 0) acc += va; break;
+                case DAG_ACC_ROW: acc += va; break;
                 default: break;
             }
-            v[o.dst] = x;
+            V(o.dst) = x;
         }
         // ---------------- reverse: d loss / d slot, loss = -(1/S) * acc
-        for (int i = 0; i < n_slots; ++i) adj[i] = 0.f;
+        for (int i = 0; i < n_slots; ++i) A(i) = 0.f;
+        nxt = *reinterpret_cast<const uint4*>(&sops[n_ops - 1]);
         for (int i = n_ops - 1; i >= 0; --i) {
-            const brn_dag_op o = ops[i];
-            const float g = adj[o.dst];
+            const uint4 w = nxt;
+            nxt = *reinterpret_cast<const uint4*>(&sops[max(i - 1, 0)]);
+            struct { int opcode, dst, a, b, c; float imm; } o;
+            o.opcode = (int)(w.x & 0xffu); o.dst = (int)(w.x >> 8); o.a = (int)(w.y & 0xffffu); o.b = (int)(w.y >> 16);
+            o.c = (int)w.z; o.imm = __uint_as_float(w.w);
+            const float g = A(o.dst);
+            const float va = V(min(o.a, last_slot)), vb = V(min(o.b, last_slot));
             switch (o.opcode) {
-                case DAG_ACC_SAMPLE: if (b == 0) adj[o.a] -= inv_S; break;
-                case DAG_ACC_ROW: adj[o.a] -= inv_S; break;
+                case DAG_ACC_SAMPLE: if (b == 0) A(o.a) -= inv_S; break;
+                case DAG_ACC_ROW: A(o.a) -= inv_S; break;
                 case DAG_PARAM: if (g != 0.f) atomicAdd(&sgrad[o.a], g); break;
-                case DAG_ADD: adj[o.a] += g; adj[o.b] += g; break;
-                case DAG_SUB: adj[o.a] += g; adj[o.b] -= g; break;
-                case DAG_MUL: { const float xa = v[o.a], xb = v[o.b]; adj[o.a] += g * xb; adj[o.b] += g * xa; break; }
+                case DAG_ADD: A(o.a) += g; A(o.b) += g; break;
+                case DAG_SUB: A(o.a) += g; A(o.b) -= g; break;
+                case DAG_MUL: { const float xa = va, xb = vb; A(o.a) += g * xb; A(o.b) += g * xa; break; }
                 case DAG_DIV: {
-                    const float inv = 1.f / v[o.b];
-                    adj[o.a] += g * inv;
-                    adj[o.b] -= g * v[o.dst] * inv;
+                    const float inv = 1.f / vb;
+                    A(o.a) += g * inv;
+                    A(o.b) -= g * V(o.dst) * inv;
                     break;
                 }
-                case DAG_NEG: adj[o.a] -= g; break;
-                case DAG_POWI: adj[o.a] += g * o.imm * dag_powi(v[o.a], o.imm - 1.f); break;
-                case DAG_EXP: adj[o.a] += g * v[o.dst]; break;
-                case DAG_LOG: adj[o.a] += g / v[o.a]; break;
-                case DAG_LOG1P: adj[o.a] += g / (1.f + v[o.a]); break;
-                case DAG_SIGMOID: { const float y = v[o.dst]; adj[o.a] += g * y * (1.f - y); break; }
-                case DAG_SOFTPLUS: adj[o.a] += g * (v[o.a] > 20.f ? 1.f : sigmoidf(v[o.a])); break;
-                case DAG_TANH: { const float y = v[o.dst]; adj[o.a] += g * (1.f - y * y); break; }
-                case DAG_SIN: adj[o.a] += g * cosf(v[o.a]); break;
-                case DAG_COS: adj[o.a] -= g * sinf(v[o.a]); break;
-                case DAG_RELU: adj[o.a] += v[o.a] > 0.f ? g : 0.f; break;
-                case DAG_SQRT: adj[o.a] += g * 0.5f / v[o.dst]; break;
-                case DAG_ABS: adj[o.a] += v[o.a] >= 0.f ? g : -g; break;
+                case DAG_NEG: A(o.a) -= g; break;
+                case DAG_POWI: A(o.a) += g * o.imm * dag_powi(va, o.imm - 1.f); break;
+                case DAG_EXP: A(o.a) += g * V(o.dst); break;
+                case DAG_LOG: A(o.a) += g / va; break;
+                case DAG_LOG1P: A(o.a) += g / (1.f + va); break;
+                case DAG_SIGMOID: { const float y = V(o.dst); A(o.a) += g * y * (1.f - y); break; }
+                case DAG_SOFTPLUS: A(o.a) += g * (va > 20.f ? 1.f : sigmoidf(va)); break;
+                case DAG_TANH: { const float y = V(o.dst); A(o.a) += g * (1.f - y * y); break; }
+                case DAG_SIN: A(o.a) += g * cosf(va); break;
+                case DAG_COS: A(o.a) -= g * sinf(va); break;
+                case DAG_RELU: A(o.a) += va > 0.f ? g : 0.f; break;
+                case DAG_SQRT: A(o.a) += g * 0.5f / V(o.dst); break;
+                case DAG_ABS: A(o.a) += va >= 0.f ? g : -g; break;
                 case DAG_CLAMP_UNIT: {
-                    const float xa = v[o.a];
-                    adj[o.a] += (xa >= 1.17549435e-38f && xa <= 1.0f - 1.1920929e-07f) ? g : 0.f;
+                    const float xa = va;
+                    A(o.a) += (xa >= 1.17549435e-38f && xa <= 1.0f - 1.1920929e-07f) ? g : 0.f;
                     break;
                 }
                 case DAG_NORMAL_LP: {
-                    const float df = v[o.a] - v[o.b], sg = v[o.c], inv_var = 1.f / (sg * sg);
+                    const float df = va - vb, sg = V(o.c), inv_var = 1.f / (sg * sg);
                     const float t = g * df * inv_var;
-                    adj[o.a] -= t;
-                    adj[o.b] += t;
-                    adj[o.c] += g * (df * df * inv_var - 1.f) / sg;
+                    A(o.a) -= t;
+                    A(o.b) += t;
+                    A(o.c) += g * (df * df * inv_var - 1.f) / sg;
                     break;
                 }
-                case DAG_NORMAL_ENTROPY: adj[o.a] += g / v[o.a]; break;
+                case DAG_NORMAL_ENTROPY: A(o.a) += g / va; break;
                 default: break;     // CONST / DATA / EPS: leaves
             }
         }
@@ -175,13 +223,24 @@ extern "C" int brn_dag_elbo_fwd_bwd(const brn_dag_op* ops, int n_ops, int n_slot
     // every interpreted op paid an L2 round trip (563 us per evaluation, measured; profiles/r1e_bench_ar1.json).
     const int block = total <= (int64_t)32 * 148 * 8 ? 32 : 128;
     const unsigned grid = (unsigned)((total + block - 1) / block);
-    const size_t smem = sizeof(float) * (size_t)(n_params > 0 ? n_params : 1);
-#define BRN_DAG_LAUNCH(MAXS)                                                                                             \
-    dag_elbo_kernel<MAXS><<<grid, block, smem, stream>>>(ops, n_ops, n_slots, params, n_params, data, n_cols, n_rows, eps, \
-                                                       n_eps, *r, dparams, loss)
-    if (n_slots <= 128) BRN_DAG_LAUNCH(128);
-    else if (n_slots <= 512) BRN_DAG_LAUNCH(512);
-    else BRN_DAG_LAUNCH(BRN_DAG_MAX_SLOTS);
+    size_t smem = sizeof(PackedOp) * (size_t)n_ops + sizeof(float) * (size_t)(n_params > 0 ? n_params : 1);
+    BRN_CHECK_ARG(smem <= 96 * 1024, "brn_dag_elbo_fwd_bwd: program of %d ops does not fit in shared memory", n_ops);
+    BRN_CHECK_ARG(n_cols <= 65536 && n_eps <= 65536, "brn_dag_elbo_fwd_bwd: n_cols=%d / n_eps=%d exceed the 16-bit operand field",
+                  n_cols, n_eps);
+    // frames in shared memory when one warp per CTA is used and both frames fit beside the program
+    const size_t frames = 2 * (size_t)n_slots * 32 * sizeof(float) + 128;
+    const bool smem_frame = block == 32 && smem + frames <= 220 * 1024;
+    if (smem_frame) smem += frames;
+#define BRN_DAG_LAUNCH(MAXS, SF)                                                                                          \
+    {                                                                                                                     \
+        BRN_CUDA_OK(cudaFuncSetAttribute(dag_elbo_kernel<MAXS, SF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        dag_elbo_kernel<MAXS, SF><<<grid, block, smem, stream>>>(ops, n_ops, n_slots, params, n_params, data, n_cols, n_rows, \
+                                                                 eps, n_eps, *r, dparams, loss);                           \
+    }
+    if (smem_frame) BRN_DAG_LAUNCH(128, true)
+    else if (n_slots <= 128) BRN_DAG_LAUNCH(128, false)
+    else if (n_slots <= 512) BRN_DAG_LAUNCH(512, false)
+    else BRN_DAG_LAUNCH(BRN_DAG_MAX_SLOTS, false)
 #undef BRN_DAG_LAUNCH
     BRN_LAUNCH_OK("dag_elbo_kernel");
     return 0;

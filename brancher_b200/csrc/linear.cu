@@ -238,7 +238,7 @@ constexpr int LT_BK = 16;
 // rows per chunk of the tcgen05 path: whole 128-row tiles such that (m-tiles x n-tiles) fills ~2 rounds of the grid
 static int linear_tc_chunk_rows(int S, int sms) {
     const int n_tiles = (S + LT_BN1 - 1) / LT_BN1;
-    int rounds = 8;
+    int rounds = 12;     // measured at C2 on B200 (profiles/r1k_*, r1l_*): 2: 7.06 ms, 4: 5.90, 8: 5.43, 12: 5.14, 16: 5.19, 24: 5.14
     if (const char* env = getenv("BRN_LINEAR_ROUNDS")) rounds = atoi(env) > 0 ? atoi(env) : rounds;
     int mt = rounds * sms / n_tiles;
     if (mt < 1) mt = 1;
