@@ -166,58 +166,72 @@ int launch_reduce_over_samples(const float* dW, int64_t ld, const float* eps, in
 // ---------------------------------------------------------------------------------------------
 // stage 5, parallel version
 // ---------------------------------------------------------------------------------------------
-constexpr int MF_SCHUNK = 16;     // samples per block
+// CTA = 32 quads (128 consecutive elements: every load of a warp is one 512-byte row segment) x 8 sample groups; sample group y
+// walks samples y, y+8, ...; the 8 partial sums per element are combined in shared memory and STORED -- each element is owned
+// by exactly one CTA, so there are neither atomics nor a zeroing pass.  (The first version split the sample axis over
+// the grid and issued 16 global atomics per thread: 5.1 M atomics per C3 evaluation, 53 us for 160 MB.)
+constexpr int MF_QUADS = 32, MF_SGROUPS = 8;
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(MF_QUADS * MF_SGROUPS)
 mf_stats_kernel(const float* __restrict__ eps, int64_t lde, const float* __restrict__ dW, int64_t ldd, int64_t numel,
                 int64_t npad, brn_sample_range r, uint32_t var_id, int vec, int64_t philox_quads,
                 float* __restrict__ stats) {
-    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q * 4 >= numel) return;
-    const int s_begin = blockIdx.y * MF_SCHUNK, s_end = min(r.s_local, s_begin + MF_SCHUNK);
-    const int nvalid = (int)min((int64_t)4, numel - q * 4);
+    __shared__ float4 part[4][MF_SGROUPS][MF_QUADS];
+    const int tx = threadIdx.x & (MF_QUADS - 1), ty = threadIdx.x / MF_QUADS;
+    const int64_t q = (int64_t)blockIdx.x * MF_QUADS + tx;
+    const bool live = q * 4 < numel;
+    const int nvalid = live ? (int)min((int64_t)4, numel - q * 4) : 0;
     vec = vec && nvalid == 4;          // `vec` = pitches/bases allow float4; the ragged last quad goes scalar
     float gw[4] = {0.f, 0.f, 0.f, 0.f}, gwe[4] = {0.f, 0.f, 0.f, 0.f}, e1[4] = {0.f, 0.f, 0.f, 0.f}, e2[4] = {0.f, 0.f, 0.f, 0.f};
+    if (live) {
 #pragma unroll 8
-    for (int s = s_begin; s < s_end; ++s) {
-        float e[4], d[4] = {0.f, 0.f, 0.f, 0.f};
-        if (eps && q >= philox_quads) {     // quads below philox_quads are regenerated (never stored): same counters as the sampler
-            if (vec) {
-                float4 t = *reinterpret_cast<const float4*>(eps + (int64_t)s * lde + q * 4);
-                e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w;
+        for (int s = ty; s < r.s_local; s += MF_SGROUPS) {
+            float e[4], d[4] = {0.f, 0.f, 0.f, 0.f};
+            if (eps && q >= philox_quads) {     // quads below philox_quads are regenerated (never stored): same counters as the sampler
+                if (vec) {
+                    float4 t = *reinterpret_cast<const float4*>(eps + (int64_t)s * lde + q * 4);
+                    e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) e[j] = j < nvalid ? eps[(int64_t)s * lde + q * 4 + j] : 0.f;
+                }
             } else {
+                Normal4 n = philox_normal4(r.seed, r.offset, var_id, (uint32_t)(r.s0 + s), (uint32_t)q);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) e[j] = j < nvalid ? eps[(int64_t)s * lde + q * 4 + j] : 0.f;
+                for (int j = 0; j < 4; ++j) e[j] = j < nvalid ? n.v[j] : 0.f;
             }
-        } else {
-            Normal4 n = philox_normal4(r.seed, r.offset, var_id, (uint32_t)(r.s0 + s), (uint32_t)q);
+            if (dW) {
+                if (vec) {
+                    float4 t = *reinterpret_cast<const float4*>(dW + (int64_t)s * ldd + q * 4);
+                    d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
+                } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) e[j] = j < nvalid ? n.v[j] : 0.f;
-        }
-        if (dW) {
-            if (vec) {
-                float4 t = *reinterpret_cast<const float4*>(dW + (int64_t)s * ldd + q * 4);
-                d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) d[j] = j < nvalid ? dW[(int64_t)s * ldd + q * 4 + j] : 0.f;
+                    for (int j = 0; j < 4; ++j) d[j] = j < nvalid ? dW[(int64_t)s * ldd + q * 4 + j] : 0.f;
+                }
             }
-        }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            gw[j] += d[j];
-            gwe[j] = __fmaf_rn(d[j], e[j], gwe[j]);
-            e1[j] += e[j];
-            e2[j] = __fmaf_rn(e[j], e[j], e2[j]);
+            for (int j = 0; j < 4; ++j) {
+                gw[j] += d[j];
+                gwe[j] = __fmaf_rn(d[j], e[j], gwe[j]);
+                e1[j] += e[j];
+                e2[j] = __fmaf_rn(e[j], e[j], e2[j]);
+            }
         }
     }
+    part[0][ty][tx] = make_float4(gw[0], gw[1], gw[2], gw[3]);
+    part[1][ty][tx] = make_float4(gwe[0], gwe[1], gwe[2], gwe[3]);
+    part[2][ty][tx] = make_float4(e1[0], e1[1], e1[2], e1[3]);
+    part[3][ty][tx] = make_float4(e2[0], e2[1], e2[2], e2[3]);
+    __syncthreads();
+    // 4 statistics x 128 elements per CTA: thread t sums the 8 group partials of (statistic t / 128, element t % 128)
+    for (int t = threadIdx.x; t < 4 * MF_QUADS * 4; t += MF_QUADS * MF_SGROUPS) {
+        const int k = t / (MF_QUADS * 4), el = t % (MF_QUADS * 4);
+        const int64_t i = (int64_t)blockIdx.x * MF_QUADS * 4 + el;
+        if (i >= numel || (k < 2 && !dW)) continue;
+        float acc = 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        if (j >= nvalid) continue;
-        const int64_t i = q * 4 + j;
-        if (dW) { atomicAdd(&stats[i], gw[j]); atomicAdd(&stats[npad + i], gwe[j]); }
-        atomicAdd(&stats[2 * npad + i], e1[j]);
-        atomicAdd(&stats[3 * npad + i], e2[j]);
+        for (int y = 0; y < MF_SGROUPS; ++y) acc += reinterpret_cast<const float*>(&part[k][y][el >> 2])[el & 3];
+        stats[(int64_t)k * npad + i] = acc;
     }
 }
 
@@ -263,13 +277,14 @@ int launch_mf_reduce_finalize(const brn_mf_var& var, const float* eps, int64_t l
     if (var.numel <= 0) return 0;
     if (!eps && var.eps) { eps = var.eps; lde = var.numel; }
     const int64_t npad = (var.numel + 3) / 4 * 4;
-    BRN_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(float) * 4 * npad, stream));
+    // the stats kernel stores every statistic it owns; zero only what it will not write
+    if (r.s_local <= 0 || !dW) BRN_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(float) * 4 * npad, stream));
     if (r.s_local > 0) {
         const int64_t quads = npad / 4;
         const int vec = (!eps || (((uintptr_t)eps % 16 == 0) && lde % 4 == 0)) &&
                         (!dW || (((uintptr_t)dW % 16 == 0) && ldd % 4 == 0));
-        dim3 grid((unsigned)((quads + 127) / 128), (unsigned)((r.s_local + MF_SCHUNK - 1) / MF_SCHUNK));
-        mf_stats_kernel<<<grid, 128, 0, stream>>>(eps, lde, dW, ldd, var.numel, npad, r, var.var_id, vec, 0, stats);
+        const unsigned grid = (unsigned)((quads + MF_QUADS - 1) / MF_QUADS);
+        mf_stats_kernel<<<grid, MF_QUADS * MF_SGROUPS, 0, stream>>>(eps, lde, dW, ldd, var.numel, npad, r, var.var_id, vec, 0, stats);
         BRN_LAUNCH_OK("mf_stats_kernel");
     }
     mf_finalize2_kernel<<<(unsigned)((var.numel + 255) / 256), 256, 0, stream>>>(var, stats, npad, r, with_prior, loss);
@@ -340,12 +355,12 @@ int launch_mf_reduce_finalize_multi(const brn_mf_var* vars, const int64_t* offs,
     }
     if (nvars <= 0 || nvars > 4 || total <= 0) { set_error("launch_mf_reduce_finalize_multi: bad variable count %d", nvars); return -1; }
     const int64_t npad = (total + 3) / 4 * 4;
-    BRN_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(float) * 4 * npad, stream));
+    if (r.s_local <= 0 || !dW) BRN_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(float) * 4 * npad, stream));
     if (r.s_local > 0) {
         const int64_t quads = npad / 4;
         const int vec = (((uintptr_t)eps % 16 == 0) && lde % 4 == 0) && (!dW || (((uintptr_t)dW % 16 == 0) && ldd % 4 == 0));
-        dim3 grid((unsigned)((quads + 127) / 128), (unsigned)((r.s_local + MF_SCHUNK - 1) / MF_SCHUNK));
-        mf_stats_kernel<<<grid, 128, 0, stream>>>(eps, lde, dW, ldd, total, npad, r, vars[0].var_id, vec, philox_numel0 / 4, stats);
+        const unsigned grid = (unsigned)((quads + MF_QUADS - 1) / MF_QUADS);
+        mf_stats_kernel<<<grid, MF_QUADS * MF_SGROUPS, 0, stream>>>(eps, lde, dW, ldd, total, npad, r, vars[0].var_id, vec, philox_numel0 / 4, stats);
         BRN_LAUNCH_OK("mf_stats_kernel");
     }
     MfMulti m;
