@@ -106,18 +106,64 @@ __global__ void __launch_bounds__(256) svgd_select_hist_kernel(const float* __re
         if (sh[b]) atomicAdd(&hist[b], sh[b]);
 }
 
-// one block: walk the histogram to the bin holding the wanted rank, extend the prefix, clear the histogram
-__global__ void svgd_select_scan_kernel(int shift, int nbits, int first, unsigned long long k, SelectState* st,
-                                        unsigned int* hist) {
-    if (threadIdx.x == 0) {
-        unsigned long long rank = first ? k : st->rank;
-        uint32_t prefix = first ? 0u : st->prefix;
-        const int nb = 1 << nbits;
-        int b = 0;
-        for (; b < nb - 1; ++b) {
-            const unsigned long long c = hist[b];
-            if (rank < c) break;
-            rank -= c;
+// one block of 1024 threads: find the bin holding the wanted rank with a block-wide prefix scan of the histogram (thread t owns
+// `per` consecutive bins), extend the prefix, clear the histogram.  (The first version walked the 4096 bins with ONE thread:
+// 4096 dependent L2 loads = 112 us per level, 14 % of the whole SVGD step -- profiles/r1g_launches_svgd_summary.txt.)
+constexpr int SCAN_THREADS = 1024;
+__global__ void __launch_bounds__(SCAN_THREADS) svgd_select_scan_kernel(int shift, int nbits, int first, unsigned long long k,
+                                                                        SelectState* st, unsigned int* hist) {
+    __shared__ unsigned long long warp_tot[SCAN_THREADS / 32];
+    __shared__ unsigned long long s_rank;
+    __shared__ int s_bin;
+    const int nb = 1 << nbits, per = (nb + SCAN_THREADS - 1) / SCAN_THREADS;      // per <= 4 (nbits <= 12)
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const unsigned long long rank0 = first ? k : st->rank;
+    const uint32_t prefix = first ? 0u : st->prefix;
+    unsigned int c[4] = {0u, 0u, 0u, 0u};
+    unsigned long long loc = 0ull;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int b = t * per + j;
+        if (j < per && b < nb) c[j] = hist[b];
+        loc += c[j];
+    }
+    unsigned long long inc = loc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long up = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += up;
+    }
+    if (lane == 31) warp_tot[w] = inc;
+    if (t == 0) { s_bin = -1; s_rank = 0ull; }
+    __syncthreads();
+    if (w == 0) {
+        unsigned long long x = warp_tot[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long up = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += up;
+        }
+        warp_tot[lane] = x;          // inclusive prefix over warps
+    }
+    __syncthreads();
+    const unsigned long long excl = inc - loc + (w > 0 ? warp_tot[w - 1] : 0ull);
+    if (rank0 >= excl && rank0 < excl + loc) {             // exactly one thread (bins are disjoint, counts are non-negative)
+        unsigned long long r = rank0 - excl;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j < per && s_bin < 0) {
+                if (r < c[j]) { s_bin = t * per + j; s_rank = r; }
+                else r -= c[j];
+            }
+        }
+    }
+    __syncthreads();
+    if (t == 0) {
+        int b = s_bin;
+        unsigned long long rank = s_rank;
+        if (b < 0) {                 // rank beyond the histogram total (cannot happen for a consistent state): last bin, as the
+            b = nb - 1;              // serial walk did
+            rank = rank0 - (warp_tot[SCAN_THREADS / 32 - 1] - hist[nb - 1]);
         }
         st->rank = rank;
         st->prefix = prefix | ((uint32_t)b << shift);
@@ -125,7 +171,7 @@ __global__ void svgd_select_scan_kernel(int shift, int nbits, int first, unsigne
         st->next = 0x7f800000u;       // +inf
     }
     __syncthreads();
-    for (int b = threadIdx.x; b < (1 << nbits); b += blockDim.x) hist[b] = 0u;
+    for (int b = t; b < nb; b += SCAN_THREADS) hist[b] = 0u;
 }
 
 // pass 4: count of values <= selected and the smallest value above it
@@ -308,7 +354,7 @@ extern "C" int brn_svgd_direction(const float* theta, const float* grad, int n, 
             svgd_select_hist_kernel<<<hgrid, 256, sizeof(unsigned int) << nbits[lv], stream>>>(ws.D2, n, shifts[lv], nbits[lv],
                                                                                              lv == 0, ws.st, ws.hist);
             BRN_LAUNCH_OK("svgd_select_hist_kernel");
-            svgd_select_scan_kernel<<<1, 256, 0, stream>>>(shifts[lv], nbits[lv], lv == 0, k1, ws.st, ws.hist);
+            svgd_select_scan_kernel<<<1, SCAN_THREADS, 0, stream>>>(shifts[lv], nbits[lv], lv == 0, k1, ws.st, ws.hist);
             BRN_LAUNCH_OK("svgd_select_scan_kernel");
         }
         svgd_select_succ_kernel<<<hgrid, 256, 0, stream>>>(ws.D2, n, ws.st);
