@@ -79,26 +79,31 @@ __global__ void __launch_bounds__(256) svgd_select_hist_kernel(const float* __re
     __syncthreads();
     const uint32_t prefix = first ? 0u : st->prefix;
     const int hshift = shift + nbits;
-    const int64_t total = (int64_t)n * n;
-    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < total; base += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t e = base + threadIdx.x;
-        bool take = false;
-        uint32_t bin = 0;
-        if (e < total) {
-            const int i = (int)(e / n), j = (int)(e - (int64_t)i * n);
-            if (i < j) {
-                const uint32_t v = __float_as_uint(D2[e]);
+    // rows are dealt round-robin to the CTAs; a row's upper-triangle part (j > i) is read coalesced -- the lower triangle is
+    // never touched and no index division is needed
+    // (rows q and n-2-q are handled together: their upper-triangle lengths add up to n-1, which balances the CTAs)
+    for (int q2 = 2 * blockIdx.x; q2 < n - 1; q2 += 2 * gridDim.x)
+    for (int h = 0; h < 2; ++h) {
+        const int i = h == 0 ? q2 / 2 : n - 2 - q2 / 2;
+        if (h == 1 && i <= q2 / 2) continue;
+        const float* row = D2 + (int64_t)i * n;
+        for (int jb = i + 1; jb < n; jb += blockDim.x) {      // warp-uniform trip count: the ballot below needs all lanes
+            const int j = jb + threadIdx.x;
+            bool take = false;
+            uint32_t bin = 0;
+            if (j < n) {
+                const uint32_t v = __float_as_uint(row[j]);
                 if (first || (hshift < 32 && (v >> hshift) == (prefix >> hshift))) {
                     take = true;
                     bin = (v >> shift) & (uint32_t)(nb - 1);
                 }
             }
-        }
-        // warp-aggregated shared atomics: distances concentrate in a handful of bins
-        const unsigned active = __ballot_sync(0xffffffffu, take);
-        if (take) {
-            const unsigned peers = __match_any_sync(active, bin);
-            if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sh[bin], (unsigned)__popc(peers));
+            // warp-aggregated shared atomics: distances concentrate in a handful of bins
+            const unsigned active = __ballot_sync(0xffffffffu, take);
+            if (take) {
+                const unsigned peers = __match_any_sync(active, bin);
+                if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sh[bin], (unsigned)__popc(peers));
+            }
         }
     }
     __syncthreads();
@@ -179,11 +184,13 @@ __global__ void __launch_bounds__(256) svgd_select_succ_kernel(const float* __re
     const uint32_t sel = st->prefix;
     unsigned long long cnt = 0ull;
     uint32_t nxt = 0x7f800000u;
-    const int64_t total = (int64_t)n * n;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        const int i = (int)(e / n), j = (int)(e - (int64_t)i * n);
-        if (i < j) {
-            const uint32_t v = __float_as_uint(D2[e]);
+    for (int q2 = 2 * blockIdx.x; q2 < n - 1; q2 += 2 * gridDim.x)
+    for (int h = 0; h < 2; ++h) {
+        const int i = h == 0 ? q2 / 2 : n - 2 - q2 / 2;
+        if (h == 1 && i <= q2 / 2) continue;
+        const float* row = D2 + (int64_t)i * n;
+        for (int j = i + 1 + threadIdx.x; j < n; j += blockDim.x) {
+            const uint32_t v = __float_as_uint(row[j]);
             if (v <= sel) ++cnt;
             else nxt = min(nxt, v);
         }
