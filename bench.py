@@ -20,6 +20,10 @@ import sys
 import threading
 import time
 
+# stdout carries exactly ONE JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION (set in this image)
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 import numpy as np
 import torch
 
@@ -241,6 +245,7 @@ CPU_SAMPLE_S = {"svgd": 512, "vae": 4, "ar1": 300}      # MC samples (particles)
 
 
 def run_cpu_baseline(workload, cfg, budget_s=12.0):
+    use_all_host_threads()
     S = CPU_SAMPLE_S.get(workload, 64)
     fn, units, desc = cpu_step_fn(workload, cfg, S)
     fn()
@@ -254,8 +259,16 @@ def run_cpu_baseline(workload, cfg, budget_s=12.0):
             "sample": desc + "; %d evaluations in %.1f s" % (n, dt)}
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is specified as "all the host threads it can use"."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if torch.get_num_threads() < n:
+        torch.set_num_threads(n)
+
+
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
+    use_all_host_threads()
     if rank != 0:
         return
     wl = args.workload
