@@ -20,9 +20,18 @@ import sys
 import threading
 import time
 
-# stdout carries exactly ONE JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION (set in this image)
-if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+# stdout carries exactly ONE JSON line.  NCCL prints its version banner to stdout on the multi-GPU boxes, so file descriptor 1 is
+# pointed at stderr for the whole run and the result line is written to a private duplicate of the original stdout.
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
     os.environ["NCCL_DEBUG"] = "WARN"
+sys.stdout.flush()
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj):
+    os.write(_RESULT_FD, (json.dumps(obj) + "\n").encode())
+
 
 import numpy as np
 import torch
@@ -288,7 +297,7 @@ def main_reference(args):
            "config": {"workload": cfg["name"], "sample_per_step": desc},
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": desc},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit(out)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -562,7 +571,7 @@ def main_ours(args):
                }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = run_cpu_baseline(wl, cfg)
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
