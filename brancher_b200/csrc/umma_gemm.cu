@@ -106,13 +106,21 @@ extern "C" int brn_gemm_nt_3xtf32(const float* A, const float* B, float* D, int 
     float *Ah = base, *Al = Ah + (size_t)M * ld, *Bh = Al + (size_t)M * ld, *Bl = Bh + (size_t)N * ld;
     if (int e = launch_split_tf32(A, K, M, K, Ah, Al, ld, nullptr, nullptr, 0, stream)) return e;
     if (int e = launch_split_tf32(B, K, N, K, Bh, Bl, ld, nullptr, nullptr, 0, stream)) return e;
-    EpiStore::Params ep;
-    ep.out = D; ep.rows = M; ep.row_stride = N; ep.col_stride = 1; ep.blk_stride = 112; ep.blk_valid = 112;
-    ep.col_limit = N; ep.total_blks = (N + 111) / 112;
     set_variant("tcgen05");
     int drain = 2;
     if (const char* env = getenv("BRN_UMMA_DRAIN")) drain = atoi(env);
+    // N tile / epilogue warps: 224 x 8 by default; BRN_GEMM_BN = 208 | 256 select the other instantiated shapes (tile-shape
+    // measurements, profiles/gemm_bn_sweep.py)
+    int bn = 224;
+    if (const char* env = getenv("BRN_GEMM_BN")) bn = atoi(env);
+    const int cpt = bn == 256 ? 64 : bn / 2;          // accumulator columns per epilogue thread = one output block
+    EpiStore::Params ep;
+    ep.out = D; ep.rows = M; ep.row_stride = N; ep.col_stride = 1; ep.blk_stride = cpt; ep.blk_valid = cpt;
+    ep.col_limit = N; ep.total_blks = (N + cpt - 1) / cpt;
+    StageTimer st("gemm.umma", stream);
     if (const char* env = getenv("BRN_UMMA_BK"))
         if (atoi(env) == 32) return launch_umma_nt<224, 32, EpiStore>(Ah, Al, M, ld, Bh, Bl, N, ld, K, 0, drain, ep, stream);
+    if (bn == 208) return launch_umma_nt<208, 16, EpiStore>(Ah, Al, M, ld, Bh, Bl, N, ld, K, 0, drain, ep, stream);
+    if (bn == 256) return launch_umma_nt<256, 16, EpiStore, 16>(Ah, Al, M, ld, Bh, Bl, N, ld, K, 0, drain, ep, stream);
     return launch_umma_nt<224, 16, EpiStore>(Ah, Al, M, ld, Bh, Bl, N, ld, K, 0, drain, ep, stream);
 }
