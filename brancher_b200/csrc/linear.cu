@@ -379,6 +379,10 @@ static int launch_linear_tc(const float* X, const float* y, int64_t N, int F, in
                             cudaStream_t stream) {
     int drain = 2;
     if (const char* env = getenv("BRN_UMMA_DRAIN")) drain = atoi(env);
+    // d^T crosses HBM as plain fp32 and is split into (hi, lo) inside the gradient GEMM (SPLIT_A); BRN_LINEAR_SPLIT_A=0 restores
+    // the pre-split operand pair (A/B measurements, tests)
+    bool split_a = true;
+    if (const char* env = getenv("BRN_LINEAR_SPLIT_A")) split_a = atoi(env) != 0;
     {
         StageTimer sp(stage_split, stream);
         if (int e = launch_split_tf32(W, F, S, F, b.Wh, b.Wl, b.ldF, nullptr, nullptr, 0, stream)) return e;
@@ -395,7 +399,7 @@ static int launch_linear_tc(const float* X, const float* y, int64_t N, int F, in
     for (int64_t r0 = 0; r0 < N; r0 += b.nb) {
         const int nb = (int)((N - r0 < b.nb) ? (N - r0) : b.nb);
         EpiBernoulli::Params e1;
-        e1.y = y + r0; e1.dT_hi = b.dTh; e1.dT_lo = b.dTl; e1.rows = nb; e1.cols = S;
+        e1.y = y + r0; e1.dT_hi = b.dTh; e1.dT_lo = split_a ? nullptr : b.dTl; e1.rows = nb; e1.cols = S;
         e1.ld = b.ldNB; e1.loss = loss; e1.neg_inv_S = loss_scale;
         if (int e = launch_umma_nt<LT_BN1, LT_BK, EpiBernoulli, LT_EW1>(b.Xh + r0 * b.ldF, b.Xl + r0 * b.ldF, nb, b.ldF, b.Wh, b.Wl, S,
                                                                  b.ldF, F, 0, drain, e1, stream))
@@ -404,8 +408,12 @@ static int launch_linear_tc(const float* X, const float* y, int64_t N, int F, in
         EpiAccum::Params e2;
         e2.out = b.dWpart; e2.rows = S; e2.cols = F; e2.ld = F; e2.slice_stride = (int64_t)S * F;
         const int64_t xt = (r0 / b.nb) * F * b.ldNB;
-        if (int e = launch_umma_nt<LT_BN2, LT_BK, EpiAccum>(b.dTh, b.dTl, S, b.ldNB, b.Xth + xt, b.Xtl + xt, F, b.ldNB, nb, 0,
-                                                             drain, e2, stream, b.slices > 1))
+        if (split_a) {
+            if (int e = launch_umma_nt<LT_BN2, LT_BK, EpiAccum, UG_EPI_WARPS, true>(b.dTh, nullptr, S, b.ldNB, b.Xth + xt, b.Xtl + xt, F,
+                                                                                    b.ldNB, nb, 0, drain, e2, stream, b.slices > 1))
+                return e;
+        } else if (int e = launch_umma_nt<LT_BN2, LT_BK, EpiAccum>(b.dTh, b.dTl, S, b.ldNB, b.Xth + xt, b.Xtl + xt, F, b.ldNB, nb, 0,
+                                                                    drain, e2, stream, b.slices > 1))
             return e;
     }
     const int64_t tot = (int64_t)S * F;

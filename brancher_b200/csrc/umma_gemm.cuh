@@ -80,8 +80,13 @@ struct UnitIter {
 
 // EW = epilogue warps (8 or 16): 4 TMEM lane quarters x EW/4 column blocks of CPT = BN / (EW/4) columns.  16 warps halve the
 // per-thread register footprint (BN = 256 becomes possible) and double the issue-level parallelism of a heavy epilogue.
-template <int BN, int BK, class Epi, int EW = UG_EPI_WARPS>
-__global__ void __launch_bounds__(64 + 32 * EW, 1)
+// SPLIT_A: the A operand arrives as ONE plain fp32 matrix (tensor map tmAh; tmAl unused).  TMA drops the fp32 tile into the
+// A_hi slot of the stage and four converter warps split it in place -- hi = rn_tf32(x) stays, lo = rn_tf32(x - hi) goes to
+// the same (swizzled) offset of the A_lo slot -- before the MMA warp may read the stage.  An operand that is produced by a
+// previous kernel and consumed once (K2: d = y - sigmoid(l)) then crosses HBM as 4 instead of 8 bytes per element.
+constexpr int UG_CONV_WARPS = 4;
+template <int BN, int BK, class Epi, int EW = UG_EPI_WARPS, bool SPLIT_A = false>
+__global__ void __launch_bounds__(64 + 32 * EW + (SPLIT_A ? 32 * UG_CONV_WARPS : 0), 1)
 umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                       const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                       int m_tiles, int n_tiles, int k_chunks, int drain_chunks, int mode, int split_T, int full_units,
@@ -99,6 +104,7 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) uint64_t full_bar[UG_STAGES], empty_bar[UG_STAGES], acc_full[2], acc_empty[2];
+    __shared__ __align__(8) uint64_t conv_bar[SPLIT_A ? UG_STAGES : 1];       // stage converted (SPLIT_A): UG_CONV_WARPS arrivals
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -108,6 +114,8 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
         umma::tma_prefetch_desc(&tmBh); umma::tma_prefetch_desc(&tmBl);
         for (int s = 0; s < UG_STAGES; ++s) { umma::mbar_init(&full_bar[s], 1); umma::mbar_init(&empty_bar[s], 1); }
         for (int b = 0; b < 2; ++b) { umma::mbar_init(&acc_full[b], 1); umma::mbar_init(&acc_empty[b], EW); }
+        if (SPLIT_A)
+            for (int s = 0; s < UG_STAGES; ++s) umma::mbar_init(&conv_bar[s], UG_CONV_WARPS);
         umma::fence_barrier_init();
     }
     if (warp == 1) umma::tmem_alloc(&tmem_base_slot, TMEM_COLS);
@@ -126,10 +134,11 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
                 for (int kc = kcb; kc < kce; ++kc) {
                     umma::mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* st = smem + stage * SM::STAGE_BYTES;
-                    umma::mbar_arrive_expect_tx(&full_bar[stage], SM::STAGE_BYTES - (skip_blo ? SM::B_BYTES : 0));
+                    umma::mbar_arrive_expect_tx(&full_bar[stage], SM::STAGE_BYTES - (skip_blo ? SM::B_BYTES : 0) -
+                                                                      (SPLIT_A ? SM::A_BYTES : 0));
                     const int k0 = kc * UG_BK;
                     umma::tma_load_2d(st, &tmAh, &full_bar[stage], k0, m0);
-                    umma::tma_load_2d(st + SM::A_BYTES, &tmAl, &full_bar[stage], k0, m0);
+                    if (!SPLIT_A) umma::tma_load_2d(st + SM::A_BYTES, &tmAl, &full_bar[stage], k0, m0);
                     umma::tma_load_2d(st + 2 * SM::A_BYTES, &tmBh, &full_bar[stage], k0, n0);
                     if (!skip_blo) umma::tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES, &tmBl, &full_bar[stage], k0, n0);
                     if (++stage == UG_STAGES) { stage = 0; phase ^= 1; }
@@ -150,7 +159,7 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
                     const uint32_t d_tmem = tmem_base + buf * UG_BUF_COLS;
                     const int kc1 = min(kc0 + drain_chunks, kce);
                     for (int kc = kc0; kc < kc1; ++kc) {
-                        umma::mbar_wait(&full_bar[stage], phase);
+                        umma::mbar_wait(SPLIT_A ? &conv_bar[stage] : &full_bar[stage], phase);
                         umma::tc_fence_after();
                         const uint32_t st = umma::smem_u32(smem + stage * SM::STAGE_BYTES);
                         const uint32_t ah = st, al = st + SM::A_BYTES, bh = st + 2 * SM::A_BYTES, bl = bh + SM::B_BYTES;
@@ -168,6 +177,32 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
                     }
                     umma::mma_commit(&acc_full[buf]);
                 }
+            }
+        }
+    } else if (SPLIT_A && warp >= 2 + EW) {
+        // ===================== converter warps (SPLIT_A) =====================
+        // 128 threads, A_BYTES / 16 float4 per stage; element-wise and in place, so the swizzle TMA applied is irrelevant
+        const int ct = threadIdx.x - 32 * (2 + EW);
+        int stage = 0; uint32_t phase = 0;
+        for (UnitIter it(m_tiles, n_tiles, k_chunks, mode, split_T, full_units); it.valid(); it.next()) {
+            const int kcb = it.kc_begin(), kce = it.kc_end();
+            for (int kc = kcb; kc < kce; ++kc) {
+                umma::mbar_wait(&full_bar[stage], phase);
+                float4* ah = reinterpret_cast<float4*>(smem + stage * SM::STAGE_BYTES);
+                float4* al = reinterpret_cast<float4*>(smem + stage * SM::STAGE_BYTES + SM::A_BYTES);
+#pragma unroll
+                for (int j = ct; j < SM::A_BYTES / 16; j += 32 * UG_CONV_WARPS) {
+                    const float4 x = ah[j];
+                    float4 h, l;
+                    umma::split_tf32(x.x, h.x, l.x); umma::split_tf32(x.y, h.y, l.y);
+                    umma::split_tf32(x.z, h.z, l.z); umma::split_tf32(x.w, h.w, l.w);
+                    ah[j] = h;
+                    al[j] = l;
+                }
+                umma::fence_proxy_async();        // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive(&conv_bar[stage]);
+                if (++stage == UG_STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else {
@@ -300,14 +335,14 @@ struct EpiBernoulli {
     // one element: log-likelihood term and the TF32-split gradient d = y - sigmoid(l).  MUFU ex2 / rcp / lg2 (absolute errors
     // ~1e-7, far inside the parity budget), no slow-path calls: the epilogue warps are the pace-setter of this GEMM (K = F
     // is short), so every instruction here is on the critical path (profiles/r1g_ncu_full_logreg_summary.txt).
-    static __device__ __forceinline__ float element(float l, float yv, float& hi, float& lo) {
+    static __device__ __forceinline__ float element(float l, float yv, float& d) {
         float e, inv, lg;
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * fabsf(l)));
         const float ope = 1.f + e;
         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(ope));
         asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(ope));
         const float sig = l >= 0.f ? inv : e * inv;
-        umma::split_tf32(yv - sig, hi, lo);
+        d = yv - sig;
         return __fmaf_rn(yv, l, -__fmaf_rn(lg, 0.6931471805599453f, fmaxf(l, 0.f)));
     }
     template <int CPT>
@@ -318,22 +353,25 @@ struct EpiBernoulli {
         float ll = 0.f;
         const int64_t ld = p.ld;
         float* ohi = p.dT_hi + (int64_t)blk * CPT * ld + row;
-        const int64_t lo_off = p.dT_lo - p.dT_hi;      // element offset between the two buffers (same allocation)
-        if (valid == CPT) {
+        if (!p.dT_lo) {
+            // plain fp32 d^T (dT_hi): the gradient GEMM splits it on the fly (SPLIT_A) -- half the bytes through HBM
 #pragma unroll          // full unroll: r[] must stay in registers (a partial unroll indexes it dynamically -> local memory)
             for (int i = 0; i < CPT; ++i) {
-                float hi, lo;
-                ll += element(r[i], yv, hi, lo);
-                ohi[0] = hi;
-                ohi[lo_off] = lo;
+                if (i < valid) {
+                    float d;
+                    ll += element(r[i], yv, d);
+                    ohi[0] = d;
+                }
                 ohi += ld;
             }
         } else {
+            const int64_t lo_off = p.dT_lo - p.dT_hi;      // element offset between the two buffers (same allocation)
 #pragma unroll
             for (int i = 0; i < CPT; ++i) {
                 if (i < valid) {
-                    float hi, lo;
-                    ll += element(r[i], yv, hi, lo);
+                    float d, hi, lo;
+                    ll += element(r[i], yv, d);
+                    umma::split_tf32(d, hi, lo);
                     ohi[0] = hi;
                     ohi[lo_off] = lo;
                 }
@@ -380,13 +418,13 @@ inline UmmaSplitPlan umma_plan(int M, int N, int K, int sms, bool allow_split) {
 // A (hi/lo) [M][K] pitch lda, B (hi/lo) [N][K] pitch ldb; mode 0: units n-major round-robin over CTAs,
 // mode 1: every CTA keeps one m-tile and strides over n-tiles.  allow_split: the caller has zeroed the output blocks of
 // n-tiles >= umma_plan(...).first_split_ntile (mode 0 only).
-template <int BN, int BK, class Epi, int EW = UG_EPI_WARPS>
+template <int BN, int BK, class Epi, int EW = UG_EPI_WARPS, bool SPLIT_A = false>
 inline int launch_umma_nt(const float* Ah, const float* Al, int M, int64_t lda, const float* Bh, const float* Bl, int N,
                           int64_t ldb, int K, int mode, int drain_chunks, const typename Epi::Params& ep,
                           cudaStream_t stream, bool allow_split = false) {
     CUtensorMap tAh, tAl, tBh, tBl;
     if (int e = make_tmap_2d_f32(&tAh, Ah, M, K, lda, UG_BM, BK)) return e;
-    if (int e = make_tmap_2d_f32(&tAl, Al, M, K, lda, UG_BM, BK)) return e;
+    if (int e = make_tmap_2d_f32(&tAl, SPLIT_A ? Ah : Al, M, K, lda, UG_BM, BK)) return e;      // SPLIT_A: unused
     if (int e = make_tmap_2d_f32(&tBh, Bh, N, K, ldb, BN, BK)) return e;
     if (int e = make_tmap_2d_f32(&tBl, Bl, N, K, ldb, BN, BK)) return e;
     const int m_tiles = (M + UG_BM - 1) / UG_BM, n_tiles = (N + BN - 1) / BN, k_chunks = (K + BK - 1) / BK;
@@ -406,10 +444,10 @@ inline int launch_umma_nt(const float* Ah, const float* Al, int M, int64_t lda, 
     }
     if (drain_chunks < 1) drain_chunks = 2 * 32 / BK;
     if (const char* env = getenv("BRN_UMMA_SKIP_BLO")) mode |= atoi(env) ? 0x100 : 0;
-    auto kern = umma_nt_3xtf32_kernel<BN, BK, Epi, EW>;
+    auto kern = umma_nt_3xtf32_kernel<BN, BK, Epi, EW, SPLIT_A>;
     const int smem = UmmaSmem<BN, BK>::TOTAL;
     BRN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, 64 + 32 * EW, smem, stream>>>(tAh, tAl, tBh, tBl, m_tiles, n_tiles, k_chunks, drain_chunks, mode,
+    kern<<<grid, 64 + 32 * EW + (SPLIT_A ? 32 * UG_CONV_WARPS : 0), smem, stream>>>(tAh, tAl, tBh, tBl, m_tiles, n_tiles, k_chunks, drain_chunks, mode,
                                                          split_T, full_units, ep);
     BRN_LAUNCH_OK("umma_nt_3xtf32_kernel");
     return 0;

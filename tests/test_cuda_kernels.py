@@ -202,10 +202,14 @@ def test_linear_random_shapes(cu, N, F, C, S, lik):
 
 @pytest.mark.parametrize("N,F,S,tied", [(1, 4, 1, True), (300, 8, 5, False), (1000, 128, 70, False), (5000, 128, 300, True),
                                          (20000, 64, 130, False)])
-def test_linear_tcgen05_variant(cu, monkeypatch, N, F, S, tied):
-    """K2 on the tensor cores: logits GEMM with the Bernoulli likelihood fused in its epilogue + K-split gradient GEMM."""
+@pytest.mark.parametrize("split_a", ["1", "0"])
+def test_linear_tcgen05_variant(cu, monkeypatch, N, F, S, tied, split_a):
+    """K2 on the tensor cores: logits GEMM with the Bernoulli likelihood fused in its epilogue + K-split gradient GEMM.
+    split_a = 1 (default): d^T crosses HBM as plain fp32 and converter warps split it inside the gradient GEMM;
+    0: the epilogue writes the TF32 (hi, lo) pair."""
     from oracle import elbo_oracle as O
     monkeypatch.setenv("BRN_LINEAR_VARIANT", "tcgen05")
+    monkeypatch.setenv("BRN_LINEAR_SPLIT_A", split_a)
     rng = np.random.RandomState(N + F + S)
     X = rng.randn(N, F).astype("f4")
     y = rng.randint(0, 2, size=N)
