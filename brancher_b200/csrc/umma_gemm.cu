@@ -58,8 +58,10 @@ __global__ void split_tf32_kernel(const float* __restrict__ src, int64_t lds, in
         float h = 0.f, l = 0.f;
         if (r < rows && c < cols) {
             umma::split_tf32(src[(int64_t)r * lds + c], h, l);
-            hi[(int64_t)r * ldd + c] = h;
-            lo[(int64_t)r * ldd + c] = l;
+            if (hi) {               // row-major pair optional (an operand read in place needs only the transposed pair)
+                hi[(int64_t)r * ldd + c] = h;
+                lo[(int64_t)r * ldd + c] = l;
+            }
         }
         th[i][tx] = h; tl[i][tx] = l;
     }
@@ -72,6 +74,31 @@ __global__ void split_tf32_kernel(const float* __restrict__ src, int64_t lds, in
             tlo[(int64_t)c * ldt + r] = tl[tx][i];
         }
     }
+}
+
+// plain transpose: dst [cols][ldt] = src [rows][lds]^T  (operands the GEMM splits on the fly, SPLIT mask in umma_gemm.cuh)
+__global__ void transpose_f32_kernel(const float* __restrict__ src, int64_t lds, int rows, int cols, float* __restrict__ dst,
+                                     int64_t ldt) {
+    __shared__ float t[32][33];
+    const int c0 = blockIdx.y * 32, r0 = blockIdx.x * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;       // 32 x 8
+    for (int i = ty; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + tx;
+        t[i][tx] = (r < rows && c < cols) ? src[(int64_t)r * lds + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c0 + i, r = r0 + tx;
+        if (r < rows && c < cols) dst[(int64_t)c * ldt + r] = t[tx][i];
+    }
+}
+
+int launch_transpose_f32(const float* src, int64_t lds, int rows, int cols, float* dst, int64_t ldt, cudaStream_t stream) {
+    if (rows <= 0 || cols <= 0) return 0;
+    dim3 grid((rows + 31) / 32, (cols + 31) / 32), block(32, 8);
+    transpose_f32_kernel<<<grid, block, 0, stream>>>(src, lds, rows, cols, dst, ldt);
+    BRN_LAUNCH_OK("transpose_f32_kernel");
+    return 0;
 }
 
 int launch_split_tf32(const float* src, int64_t lds, int rows, int cols, float* hi, float* lo, int64_t ldd, float* thi,

@@ -84,15 +84,18 @@ struct UnitIter {
 // A_hi slot of the stage and four converter warps split it in place -- hi = rn_tf32(x) stays, lo = rn_tf32(x - hi) goes to
 // the same (swizzled) offset of the A_lo slot -- before the MMA warp may read the stage.  An operand that is produced by a
 // previous kernel and consumed once (K2: d = y - sigmoid(l)) then crosses HBM as 4 instead of 8 bytes per element.
-constexpr int UG_CONV_WARPS = 4;
-template <int BN, int BK, class Epi, int EW = UG_EPI_WARPS, bool SPLIT_A = false>
-__global__ void __launch_bounds__(64 + 32 * EW + (SPLIT_A ? 32 * UG_CONV_WARPS : 0), 1)
+// SPLIT is a bit mask: 1 = the A operand, 2 = the B operand arrives plain (tensor map tmBh; tmBl unused).
+// CW = converter warps (2 keep a 16-epilogue-warp kernel at 640 threads = 96 registers per thread).
+template <int BN, int BK, class Epi, int EW = UG_EPI_WARPS, int SPLIT = 0, int CW = 4>
+__global__ void __launch_bounds__(64 + 32 * EW + (SPLIT ? 32 * CW : 0), 1)
 umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                       const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                       int m_tiles, int n_tiles, int k_chunks, int drain_chunks, int mode, int split_T, int full_units,
                       typename Epi::Params ep) {
     using SM = UmmaSmem<BN, BK>;
     constexpr int UG_STAGES = SM::STAGES, UG_BK = BK, SW = BK * 4;
+    constexpr bool SPLIT_A = (SPLIT & 1) != 0, SPLIT_B = (SPLIT & 2) != 0;
+    constexpr int UG_CONV_WARPS = CW;
     // TIMING EXPERIMENT ONLY (BRN_UMMA_SKIP_BLO=1, wrong results): the producer does not load the B_lo tile, i.e. 32 % fewer
     // bytes per K chunk through L2 with the MMA work unchanged -- tells whether the kernel is paced by its operand feed.
     const bool skip_blo = (mode & 0x100) != 0;
@@ -104,7 +107,7 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) uint64_t full_bar[UG_STAGES], empty_bar[UG_STAGES], acc_full[2], acc_empty[2];
-    __shared__ __align__(8) uint64_t conv_bar[SPLIT_A ? UG_STAGES : 1];       // stage converted (SPLIT_A): UG_CONV_WARPS arrivals
+    __shared__ __align__(8) uint64_t conv_bar[SPLIT ? UG_STAGES : 1];       // stage converted (SPLIT_A): UG_CONV_WARPS arrivals
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -114,7 +117,7 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
         umma::tma_prefetch_desc(&tmBh); umma::tma_prefetch_desc(&tmBl);
         for (int s = 0; s < UG_STAGES; ++s) { umma::mbar_init(&full_bar[s], 1); umma::mbar_init(&empty_bar[s], 1); }
         for (int b = 0; b < 2; ++b) { umma::mbar_init(&acc_full[b], 1); umma::mbar_init(&acc_empty[b], EW); }
-        if (SPLIT_A)
+        if (SPLIT)
             for (int s = 0; s < UG_STAGES; ++s) umma::mbar_init(&conv_bar[s], UG_CONV_WARPS);
         umma::fence_barrier_init();
     }
@@ -134,13 +137,14 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
                 for (int kc = kcb; kc < kce; ++kc) {
                     umma::mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* st = smem + stage * SM::STAGE_BYTES;
-                    umma::mbar_arrive_expect_tx(&full_bar[stage], SM::STAGE_BYTES - (skip_blo ? SM::B_BYTES : 0) -
+                    umma::mbar_arrive_expect_tx(&full_bar[stage], SM::STAGE_BYTES - ((skip_blo || SPLIT_B) ? SM::B_BYTES : 0) -
                                                                       (SPLIT_A ? SM::A_BYTES : 0));
                     const int k0 = kc * UG_BK;
                     umma::tma_load_2d(st, &tmAh, &full_bar[stage], k0, m0);
                     if (!SPLIT_A) umma::tma_load_2d(st + SM::A_BYTES, &tmAl, &full_bar[stage], k0, m0);
                     umma::tma_load_2d(st + 2 * SM::A_BYTES, &tmBh, &full_bar[stage], k0, n0);
-                    if (!skip_blo) umma::tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES, &tmBl, &full_bar[stage], k0, n0);
+                    if (!skip_blo && !SPLIT_B)
+                        umma::tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES, &tmBl, &full_bar[stage], k0, n0);
                     if (++stage == UG_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -159,7 +163,7 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
                     const uint32_t d_tmem = tmem_base + buf * UG_BUF_COLS;
                     const int kc1 = min(kc0 + drain_chunks, kce);
                     for (int kc = kc0; kc < kc1; ++kc) {
-                        umma::mbar_wait(SPLIT_A ? &conv_bar[stage] : &full_bar[stage], phase);
+                        umma::mbar_wait(SPLIT ? &conv_bar[stage] : &full_bar[stage], phase);
                         umma::tc_fence_after();
                         const uint32_t st = umma::smem_u32(smem + stage * SM::STAGE_BYTES);
                         const uint32_t ah = st, al = st + SM::A_BYTES, bh = st + 2 * SM::A_BYTES, bl = bh + SM::B_BYTES;
@@ -179,7 +183,7 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
                 }
             }
         }
-    } else if (SPLIT_A && warp >= 2 + EW) {
+    } else if (SPLIT && warp >= 2 + EW) {
         // ===================== converter warps (SPLIT_A) =====================
         // 128 threads, A_BYTES / 16 float4 per stage; element-wise and in place, so the swizzle TMA applied is irrelevant
         const int ct = threadIdx.x - 32 * (2 + EW);
@@ -188,17 +192,22 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
             const int kcb = it.kc_begin(), kce = it.kc_end();
             for (int kc = kcb; kc < kce; ++kc) {
                 umma::mbar_wait(&full_bar[stage], phase);
-                float4* ah = reinterpret_cast<float4*>(smem + stage * SM::STAGE_BYTES);
-                float4* al = reinterpret_cast<float4*>(smem + stage * SM::STAGE_BYTES + SM::A_BYTES);
-#pragma unroll
-                for (int j = ct; j < SM::A_BYTES / 16; j += 32 * UG_CONV_WARPS) {
-                    const float4 x = ah[j];
-                    float4 h, l;
-                    umma::split_tf32(x.x, h.x, l.x); umma::split_tf32(x.y, h.y, l.y);
-                    umma::split_tf32(x.z, h.z, l.z); umma::split_tf32(x.w, h.w, l.w);
-                    ah[j] = h;
-                    al[j] = l;
-                }
+                auto convert = [&](uint8_t* hi_slot, int slot_bytes) {
+                    float4* xh = reinterpret_cast<float4*>(hi_slot);
+                    float4* xl = reinterpret_cast<float4*>(hi_slot + slot_bytes);
+#pragma unroll 4
+                    for (int j = ct; j < slot_bytes / 16; j += 32 * UG_CONV_WARPS) {
+                        const float4 x = xh[j];
+                        float4 h, l;
+                        umma::split_tf32(x.x, h.x, l.x); umma::split_tf32(x.y, h.y, l.y);
+                        umma::split_tf32(x.z, h.z, l.z); umma::split_tf32(x.w, h.w, l.w);
+                        xh[j] = h;
+                        xl[j] = l;
+                    }
+                };
+                uint8_t* st = smem + stage * SM::STAGE_BYTES;
+                if (SPLIT_A) convert(st, SM::A_BYTES);
+                if (SPLIT_B) convert(st + 2 * SM::A_BYTES, SM::B_BYTES);
                 umma::fence_proxy_async();        // generic-proxy writes -> visible to the tensor core's async-proxy reads
                 __syncwarp();
                 if (lane == 0) umma::mbar_arrive(&conv_bar[stage]);
@@ -387,6 +396,7 @@ struct EpiBernoulli {
 
 int launch_split_tf32(const float* src, int64_t lds, int rows, int cols, float* hi, float* lo, int64_t ldd, float* thi,
                       float* tlo, int64_t ldt, cudaStream_t stream);
+int launch_transpose_f32(const float* src, int64_t lds, int rows, int cols, float* dst, int64_t ldt, cudaStream_t stream);
 
 // Work split of mode 0 on `sms` CTAs: grid size, and -- when the last round-robin round would be at most half full --
 // the K-split of the tail units (see UnitIter).  first_split_ntile = first n-tile whose output blocks receive atomic
@@ -418,15 +428,15 @@ inline UmmaSplitPlan umma_plan(int M, int N, int K, int sms, bool allow_split) {
 // A (hi/lo) [M][K] pitch lda, B (hi/lo) [N][K] pitch ldb; mode 0: units n-major round-robin over CTAs,
 // mode 1: every CTA keeps one m-tile and strides over n-tiles.  allow_split: the caller has zeroed the output blocks of
 // n-tiles >= umma_plan(...).first_split_ntile (mode 0 only).
-template <int BN, int BK, class Epi, int EW = UG_EPI_WARPS, bool SPLIT_A = false>
+template <int BN, int BK, class Epi, int EW = UG_EPI_WARPS, int SPLIT = 0, int CW = 4>
 inline int launch_umma_nt(const float* Ah, const float* Al, int M, int64_t lda, const float* Bh, const float* Bl, int N,
                           int64_t ldb, int K, int mode, int drain_chunks, const typename Epi::Params& ep,
                           cudaStream_t stream, bool allow_split = false) {
     CUtensorMap tAh, tAl, tBh, tBl;
     if (int e = make_tmap_2d_f32(&tAh, Ah, M, K, lda, UG_BM, BK)) return e;
-    if (int e = make_tmap_2d_f32(&tAl, SPLIT_A ? Ah : Al, M, K, lda, UG_BM, BK)) return e;      // SPLIT_A: unused
+    if (int e = make_tmap_2d_f32(&tAl, (SPLIT & 1) ? Ah : Al, M, K, lda, UG_BM, BK)) return e;      // SPLIT & 1: unused
     if (int e = make_tmap_2d_f32(&tBh, Bh, N, K, ldb, BN, BK)) return e;
-    if (int e = make_tmap_2d_f32(&tBl, Bl, N, K, ldb, BN, BK)) return e;
+    if (int e = make_tmap_2d_f32(&tBl, (SPLIT & 2) ? Bh : Bl, N, K, ldb, BN, BK)) return e;        // SPLIT & 2: unused
     const int m_tiles = (M + UG_BM - 1) / UG_BM, n_tiles = (N + BN - 1) / BN, k_chunks = (K + BK - 1) / BK;
     drain_chunks = drain_chunks * 32 / BK;        // `drain_chunks` is given in units of 32 K elements
     int dev = 0, sms = 148;
@@ -444,10 +454,10 @@ inline int launch_umma_nt(const float* Ah, const float* Al, int M, int64_t lda, 
     }
     if (drain_chunks < 1) drain_chunks = 2 * 32 / BK;
     if (const char* env = getenv("BRN_UMMA_SKIP_BLO")) mode |= atoi(env) ? 0x100 : 0;
-    auto kern = umma_nt_3xtf32_kernel<BN, BK, Epi, EW, SPLIT_A>;
+    auto kern = umma_nt_3xtf32_kernel<BN, BK, Epi, EW, SPLIT, CW>;
     const int smem = UmmaSmem<BN, BK>::TOTAL;
     BRN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, 64 + 32 * EW + (SPLIT_A ? 32 * UG_CONV_WARPS : 0), smem, stream>>>(tAh, tAl, tBh, tBl, m_tiles, n_tiles, k_chunks, drain_chunks, mode,
+    kern<<<grid, 64 + 32 * EW + (SPLIT ? 32 * CW : 0), smem, stream>>>(tAh, tAl, tBh, tBl, m_tiles, n_tiles, k_chunks, drain_chunks, mode,
                                                          split_T, full_units, ep);
     BRN_LAUNCH_OK("umma_nt_3xtf32_kernel");
     return 0;

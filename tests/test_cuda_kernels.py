@@ -202,7 +202,7 @@ def test_linear_random_shapes(cu, N, F, C, S, lik):
 
 @pytest.mark.parametrize("N,F,S,tied", [(1, 4, 1, True), (300, 8, 5, False), (1000, 128, 70, False), (5000, 128, 300, True),
                                          (20000, 64, 130, False)])
-@pytest.mark.parametrize("split_a", ["1", "0"])
+@pytest.mark.parametrize("split_a", ["7", "0", "1", "5"])
 def test_linear_tcgen05_variant(cu, monkeypatch, N, F, S, tied, split_a):
     """K2 on the tensor cores: logits GEMM with the Bernoulli likelihood fused in its epilogue + K-split gradient GEMM.
     split_a = 1 (default): d^T crosses HBM as plain fp32 and converter warps split it inside the gradient GEMM;
