@@ -74,17 +74,30 @@ __device__ __forceinline__ float warp_colsum32(const float (&v)[32]) {
 }
 
 // write 4 consecutive columns of one row: TF32-split, row-major (vectorised when whole and aligned) + transposed
+// A NULL lo pointer means "this copy is ONE plain fp32 matrix" (the consuming GEMM splits it on the fly, SPLIT mask of
+// umma_gemm.cuh): row-major copies are always plain here, transposed copies are plain for gradient tensors.
 __device__ __forceinline__ void store_split4(const float (&v)[4], int nvalid, float* rh, float* rl, float* th, float* tl,
                                              int64_t ldt) {
     float h[4], l[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) umma::split_tf32(v[j], h[j], l[j]);
-    if (th) {
+    if (th && tl) {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
             if (j < nvalid) { th[(int64_t)j * ldt] = h[j]; tl[(int64_t)j * ldt] = l[j]; }
+    } else if (th) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j < nvalid) th[(int64_t)j * ldt] = v[j];
     }
-    if (nvalid >= 4) {
+    if (!rl) {
+        if (nvalid >= 4) *reinterpret_cast<float4*>(rh) = make_float4(v[0], v[1], v[2], v[3]);
+        else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (j < nvalid) rh[j] = v[j];
+        }
+    } else if (nvalid >= 4) {
         *reinterpret_cast<float4*>(rh) = make_float4(h[0], h[1], h[2], h[3]);
         *reinterpret_cast<float4*>(rl) = make_float4(l[0], l[1], l[2], l[3]);
     } else {
@@ -107,16 +120,17 @@ struct EpiDense {
         if (row >= p.rows || c0 >= p.cols) return;
         const int valid = min(CPT, p.cols - c0);
         float* rh = p.rm_hi + (int64_t)row * p.ld + c0;
-        float* rl = p.rm_lo + (int64_t)row * p.ld + c0;
+        float* rl = p.rm_lo ? p.rm_lo + (int64_t)row * p.ld + c0 : nullptr;
         float* th = p.t_hi + (int64_t)c0 * p.ldt + row;
-        float* tl = p.t_lo + (int64_t)c0 * p.ldt + row;
+        float* tl = p.t_lo ? p.t_lo + (int64_t)c0 * p.ldt + row : nullptr;
 #pragma unroll
         for (int i = 0; i < CPT; i += 4) {
             if (i < valid) {
                 float v[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) v[j] = (i + j < valid) ? fmaxf(r[i + j] + __ldg(p.bias + c0 + i + j), 0.f) : 0.f;
-                store_split4(v, valid - i, rh + i, rl + i, th + (int64_t)i * p.ldt, tl + (int64_t)i * p.ldt, p.ldt);
+                store_split4(v, valid - i, rh + i, rl ? rl + i : nullptr, th + (int64_t)i * p.ldt,
+                             tl ? tl + (int64_t)i * p.ldt : nullptr, p.ldt);
             }
         }
     }
@@ -143,9 +157,9 @@ struct EpiBern {
         // 31 elements from L1.  (Measured: reading the transposed copy instead -- coalesced, no reuse -- is 38 % SLOWER.)
         const float* x = p.X + (int64_t)(row_ok ? row % p.B : 0) * p.ldx + c0;
         float* rh = p.rm_hi + (int64_t)row * p.ld + c0;
-        float* rl = p.rm_lo + (int64_t)row * p.ld + c0;
+        float* rl = p.rm_lo ? p.rm_lo + (int64_t)row * p.ld + c0 : nullptr;
         float* th = p.t_hi + (int64_t)c0 * p.ldt + row;
-        float* tl = p.t_lo + (int64_t)c0 * p.ldt + row;
+        float* tl = p.t_lo ? p.t_lo + (int64_t)c0 * p.ldt + row : nullptr;
         float ll = 0.f;
         if (valid == CPT && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
             // full, aligned block (the common case).  The epilogue warps were stalled on the per-element x loads 57 % of the
@@ -186,7 +200,8 @@ struct EpiBern {
                                 ll += __fmaf_rn(xv, l, -__fmaf_rn(lg, 0.6931471805599453f, fmaxf(l, 0.f)));
                                 v[j] = xv - sig;
                             }
-                            store_split4(v, 4, rh + i, rl + i, th + (int64_t)i * p.ldt, tl + (int64_t)i * p.ldt, p.ldt);
+                            store_split4(v, 4, rh + i, rl ? rl + i : nullptr, th + (int64_t)i * p.ldt,
+                                         tl ? tl + (int64_t)i * p.ldt : nullptr, p.ldt);
                         }
 #pragma unroll
                         for (int j = 0; j < 4; ++j) d32[hb + 4 * q + j] = v[j];
@@ -218,8 +233,8 @@ struct EpiBern {
                             v[j] = xv - sig;
                         }
                     }
-                    store_split4(v, valid - i0 - i, rh + i0 + i, rl + i0 + i, th + (int64_t)(i0 + i) * p.ldt,
-                                 tl + (int64_t)(i0 + i) * p.ldt, p.ldt);
+                    store_split4(v, valid - i0 - i, rh + i0 + i, rl ? rl + i0 + i : nullptr, th + (int64_t)(i0 + i) * p.ldt,
+                                 tl ? tl + (int64_t)(i0 + i) * p.ldt : nullptr, p.ldt);
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) d32[i + j] = v[j];
@@ -272,8 +287,10 @@ struct EpiMask {
                                 if (col + j < valid) o[j] = v[j];
                         }
                     } else {
-                        store_split4(v, valid - col, p.rm_hi + (int64_t)row * p.ld + c0 + col, p.rm_lo + (int64_t)row * p.ld + c0 + col,
-                                     p.t_hi + (int64_t)(c0 + col) * p.ldt + row, p.t_lo + (int64_t)(c0 + col) * p.ldt + row, p.ldt);
+                        store_split4(v, valid - col, p.rm_hi + (int64_t)row * p.ld + c0 + col,
+                                     p.rm_lo ? p.rm_lo + (int64_t)row * p.ld + c0 + col : nullptr,
+                                     p.t_hi + (int64_t)(c0 + col) * p.ldt + row,
+                                     p.t_lo ? p.t_lo + (int64_t)(c0 + col) * p.ldt + row : nullptr, p.ldt);
                     }
                 }
 #pragma unroll
@@ -295,9 +312,13 @@ template <class Epi>
 static int launch_gemm(const float* Ah, const float* Al, int M, int64_t lda, const float* Bh, const float* Bl, int N, int64_t ldb,
                        int K, int mode, const typename Epi::Params& ep, cudaStream_t stream, bool allow_split = false) {
     switch (pick_bn(N)) {
-        case 128: return launch_umma_nt<128, VAE_BK, Epi>(Ah, Al, M, lda, Bh, Bl, N, ldb, K, mode, 2, ep, stream, allow_split);
-        case 176: return launch_umma_nt<176, VAE_BK, Epi>(Ah, Al, M, lda, Bh, Bl, N, ldb, K, mode, 2, ep, stream, allow_split);
-        default: return launch_umma_nt<208, VAE_BK, Epi>(Ah, Al, M, lda, Bh, Bl, N, ldb, K, mode, 2, ep, stream, allow_split);
+        // every A operand of K5 (activations, gradients; row-major or transposed) is one plain fp32 matrix: SPLIT = 1
+        case 128: return launch_umma_nt<128, VAE_BK, Epi, UG_EPI_WARPS, 1>(Ah, nullptr, M, lda, Bh, Bl, N, ldb, K, mode, 2, ep, stream,
+                                                                           allow_split);
+        case 176: return launch_umma_nt<176, VAE_BK, Epi, UG_EPI_WARPS, 1>(Ah, nullptr, M, lda, Bh, Bl, N, ldb, K, mode, 2, ep, stream,
+                                                                           allow_split);
+        default: return launch_umma_nt<208, VAE_BK, Epi, UG_EPI_WARPS, 1>(Ah, nullptr, M, lda, Bh, Bl, N, ldb, K, mode, 2, ep, stream,
+                                                                          allow_split);
     }
 }
 
@@ -316,7 +337,7 @@ __global__ void vae_heads_fwd_kernel(const float* __restrict__ a_hi, const float
     for (int l = 0; l < L; ++l) {
         float pm = 0.f, ps = 0.f;
         for (int j = lane; j < h; j += 32) {
-            const float a = a_hi[(int64_t)row * ld + j] + a_lo[(int64_t)row * ld + j];
+            const float a = a_hi[(int64_t)row * ld + j] + (a_lo ? a_lo[(int64_t)row * ld + j] : 0.f);
             pm = __fmaf_rn(a, Wm[(int64_t)l * h + j], pm);
             ps = __fmaf_rn(a, Ws[(int64_t)l * h + j], ps);
         }
@@ -367,10 +388,7 @@ vae_sample_dec0_kernel(const float* __restrict__ mean, const float* __restrict__
     for (int idx = tid; idx < 32 * h0; idx += 256) {            // row-major copy: consecutive threads -> consecutive columns
         const int rr = idx / h0, j = idx % h0, row = r0 + rr;
         if (row < R) {
-            float hi, lo;
-            umma::split_tf32(dec0_value(zs + rr * L, V0, c0, L, j), hi, lo);
-            a0.rm_hi[(int64_t)row * a0.ld + j] = hi;
-            a0.rm_lo[(int64_t)row * a0.ld + j] = lo;
+            a0.rm_hi[(int64_t)row * a0.ld + j] = dec0_value(zs + rr * L, V0, c0, L, j);       // row-major copy: plain fp32
         }
     }
     for (int idx = tid; idx < 32 * h0; idx += 256) {            // transposed copy: consecutive threads -> consecutive rows
@@ -495,7 +513,7 @@ vae_heads_bwd_kernel(const float* __restrict__ dmean, const float* __restrict__ 
             const int b = b0 + rr;
             float v = 0.f;
             if (jok && b < B) {
-                const float ahi = a_hi[(int64_t)b * lda + j], a = ahi + a_lo[(int64_t)b * lda + j];
+                const float ahi = a_hi[(int64_t)b * lda + j], a = ahi + (a_lo ? a_lo[(int64_t)b * lda + j] : 0.f);
                 float g = 0.f;
 #pragma unroll
                 for (int l = 0; l < LP; ++l) {
@@ -505,10 +523,7 @@ vae_heads_bwd_kernel(const float* __restrict__ dmean, const float* __restrict__ 
                     as[l] = __fmaf_rn(dsp[rr][l], a, as[l]);
                 }
                 v = ahi > 0.f ? g : 0.f;
-                float hi, lo;
-                umma::split_tf32(v, hi, lo);
-                dpre.rm_hi[(int64_t)b * dpre.ld + j] = hi;
-                dpre.rm_lo[(int64_t)b * dpre.ld + j] = lo;
+                dpre.rm_hi[(int64_t)b * dpre.ld + j] = v;          // gradient tensor: both copies plain fp32
                 colsum += v;
             }
             tile[w][rr][lane] = v;
@@ -517,10 +532,7 @@ vae_heads_bwd_kernel(const float* __restrict__ dmean, const float* __restrict__ 
         for (int i = 0; i < 32; ++i) {
             const int jj = c0 + i, b = b0 + lane;
             if (jj < h && b < B) {
-                float hi, lo;
-                umma::split_tf32(tile[w][lane][i], hi, lo);
-                dpre.t_hi[(int64_t)jj * dpre.ldt + b] = hi;
-                dpre.t_lo[(int64_t)jj * dpre.ldt + b] = lo;
+                dpre.t_hi[(int64_t)jj * dpre.ldt + b] = tile[w][lane][i];
             }
         }
         __syncwarp();
@@ -584,19 +596,21 @@ struct VaeWorkspace {
             return p;
         };
         auto take = [&](size_t nfloat) { return reinterpret_cast<float*>(takeb(nfloat * sizeof(float))); };
-        auto act = [&](VaeAct& a, int64_t rows, int n, bool with_t = true) {
+        // rm: ONE plain fp32 matrix (rm_lo == NULL: always the A operand of a SPLIT = 1 GEMM); t: the TF32 (hi, lo) pair for
+        // activations (B operand of the weight-gradient GEMM), one plain matrix for gradient tensors (its A operand)
+        auto act = [&](VaeAct& a, int64_t rows, int n, bool grad = false) {
             a.n = n; a.ld = pad4l(n); a.ldt = pad4l(rows);
-            a.rm_hi = take((size_t)rows * a.ld); a.rm_lo = take((size_t)rows * a.ld);
-            a.t_hi = with_t ? take((size_t)n * a.ldt) : nullptr; a.t_lo = with_t ? take((size_t)n * a.ldt) : nullptr;
+            a.rm_hi = take((size_t)rows * a.ld); a.rm_lo = nullptr;
+            a.t_hi = take((size_t)n * a.ldt); a.t_lo = grad ? nullptr : take((size_t)n * a.ldt);
         };
         const int64_t R = (int64_t)S * B;
         act(Xa, B, m.D);
-        for (int i = 0; i < m.n_enc; ++i) { act(enc_a[i], B, m.enc[i].n_out); act(enc_d[i], B, m.enc[i].n_out); }
+        for (int i = 0; i < m.n_enc; ++i) { act(enc_a[i], B, m.enc[i].n_out); act(enc_d[i], B, m.enc[i].n_out, true); }
         for (int i = 0; i < m.n_dec; ++i) {
             act(dec_a[i], R, m.dec[i].n_out);
-            if (i > 0) act(dec_d[i], R, m.dec[i].n_out);
+            if (i > 0) act(dec_d[i], R, m.dec[i].n_out, true);
         }
-        act(dL, R, m.D);
+        act(dL, R, m.D, true);
         ld0 = pad4l(m.dec[0].n_out);
         dpre0 = take((size_t)R * ld0);
         mean = take((size_t)B * m.L); sd = take((size_t)B * m.L); sdpre = take((size_t)B * m.L);
@@ -704,7 +718,9 @@ extern "C" int brn_vae_elbo_fwd_bwd(const float* X, int B, int64_t row0, int64_t
     // 0. TF32-split operands: X and every weight matrix a GEMM reads, in both K-major layouts
     {
         StageTimer st("vae.split_operands", stream);
-        if (int e = launch_split_tf32(X, D, B, D, ws.Xa.rm_hi, ws.Xa.rm_lo, ws.Xa.ld, ws.Xa.t_hi, ws.Xa.t_lo, ws.Xa.ldt, stream)) return e;
+        BRN_CUDA_OK(cudaMemcpy2DAsync(ws.Xa.rm_hi, ws.Xa.ld * sizeof(float), X, D * sizeof(float), D * sizeof(float), B,
+                                      cudaMemcpyDeviceToDevice, stream));         // plain row-major copy with the padded pitch
+        if (int e = launch_split_tf32(X, D, B, D, nullptr, nullptr, ws.Xa.ld, ws.Xa.t_hi, ws.Xa.t_lo, ws.Xa.ldt, stream)) return e;
         auto wsplit = [&](const brn_dense_layer& l, VaeWeights& w) {
             return launch_split_tf32(l.W, l.n_in, l.n_out, l.n_in, w.hi, w.lo, w.ld, w.t_hi, w.t_lo, w.ldt, stream);
         };
