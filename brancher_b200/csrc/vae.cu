@@ -313,11 +313,11 @@ static int launch_gemm(const float* Ah, const float* Al, int M, int64_t lda, con
                        int K, int mode, const typename Epi::Params& ep, cudaStream_t stream, bool allow_split = false) {
     switch (pick_bn(N)) {
         // every A operand of K5 (activations, gradients; row-major or transposed) is one plain fp32 matrix: SPLIT = 1
-        case 128: return launch_umma_nt<128, VAE_BK, Epi, UG_EPI_WARPS, 1>(Ah, nullptr, M, lda, Bh, Bl, N, ldb, K, mode, 2, ep, stream,
+        case 128: return launch_umma_nt<128, VAE_BK, Epi, UG_EPI_WARPS, 1, 2>(Ah, nullptr, M, lda, Bh, Bl, N, ldb, K, mode, 2, ep, stream,
                                                                            allow_split);
-        case 176: return launch_umma_nt<176, VAE_BK, Epi, UG_EPI_WARPS, 1>(Ah, nullptr, M, lda, Bh, Bl, N, ldb, K, mode, 2, ep, stream,
+        case 176: return launch_umma_nt<176, VAE_BK, Epi, UG_EPI_WARPS, 1, 2>(Ah, nullptr, M, lda, Bh, Bl, N, ldb, K, mode, 2, ep, stream,
                                                                            allow_split);
-        default: return launch_umma_nt<208, VAE_BK, Epi, UG_EPI_WARPS, 1>(Ah, nullptr, M, lda, Bh, Bl, N, ldb, K, mode, 2, ep, stream,
+        default: return launch_umma_nt<208, VAE_BK, Epi, UG_EPI_WARPS, 1, 2>(Ah, nullptr, M, lda, Bh, Bl, N, ldb, K, mode, 2, ep, stream,
                                                                           allow_split);
     }
 }
