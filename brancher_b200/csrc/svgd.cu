@@ -372,7 +372,8 @@ extern "C" int brn_svgd_direction(const float* theta, const float* grad, int n, 
     if (rows > 0) {
         StageTimer st("svgd.update", stream);
         const int row_tiles = (rows + SU_TI - 1) / SU_TI, d_chunks = (d + SU_TD - 1) / SU_TD;
-        int splits = (2 * sms) / (row_tiles * d_chunks);
+        // ~8 CTAs (32 warps) per SM: with 2 the kernel ran at 7 warps per SM and 9.5 TFLOP/s (profiles/r1n_launches_svgd_summary.txt)
+        int splits = (8 * sms) / (row_tiles * d_chunks);
         const int max_splits = (n + 4 * SU_TJ - 1) / (4 * SU_TJ);
         if (splits > max_splits) splits = max_splits;
         if (splits < 1) splits = 1;
