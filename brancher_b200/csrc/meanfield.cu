@@ -183,7 +183,38 @@ mf_stats_kernel(const float* __restrict__ eps, int64_t lde, const float* __restr
     const int nvalid = live ? (int)min((int64_t)4, numel - q * 4) : 0;
     vec = vec && nvalid == 4;          // `vec` = pitches/bases allow float4; the ragged last quad goes scalar
     float gw[4] = {0.f, 0.f, 0.f, 0.f}, gwe[4] = {0.f, 0.f, 0.f, 0.f}, e1[4] = {0.f, 0.f, 0.f, 0.f}, e2[4] = {0.f, 0.f, 0.f, 0.f};
-    if (live) {
+    if (live && vec && eps && dW && q >= philox_quads) {
+        // common case (stored noise, vectorisable): explicit batches of 8 samples = 16 independent 16-byte loads in flight per
+        // thread before the first use
+        const float4* e4p = reinterpret_cast<const float4*>(eps + q * 4);
+        const float4* d4p = reinterpret_cast<const float4*>(dW + q * 4);
+        const int64_t le4 = lde / 4, ld4 = ldd / 4;
+        for (int s0 = ty; s0 < r.s_local; s0 += 8 * MF_SGROUPS) {
+            float4 e4[8], d4[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int s = s0 + u * MF_SGROUPS;
+                if (s < r.s_local) {
+                    e4[u] = __ldg(e4p + (int64_t)s * le4);
+                    d4[u] = __ldg(d4p + (int64_t)s * ld4);
+                } else {
+                    e4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    d4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float e[4] = {e4[u].x, e4[u].y, e4[u].z, e4[u].w}, d[4] = {d4[u].x, d4[u].y, d4[u].z, d4[u].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    gw[j] += d[j];
+                    gwe[j] = __fmaf_rn(d[j], e[j], gwe[j]);
+                    e1[j] += e[j];
+                    e2[j] = __fmaf_rn(e[j], e[j], e2[j]);
+                }
+            }
+        }
+    } else if (live) {
 #pragma unroll 8
         for (int s = ty; s < r.s_local; s += MF_SGROUPS) {
             float e[4], d[4] = {0.f, 0.f, 0.f, 0.f};
