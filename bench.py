@@ -390,7 +390,7 @@ def main_ours(args):
 
         def device_step(it, Xd=X, yd=None):
             r = cu.sample_range(S_total, s0=s0, s_local=S_local, seed=args.seed, offset=it)
-            loss, g = cu.dag_elbo_fwd_bwd(ops, len(Pg.ops), Pg.n_slots, pvec, Xd, plan.n_rows, None, len(Pg.eps_names), r)
+            loss, g = cu.dag_elbo_fwd_bwd(ops, ops.numel() // 24, Pg.n_slots, pvec, Xd, plan.n_rows, None, len(Pg.eps_names), r)
             gflat[:pvec.numel()] = g
             return loss
     elif wl == "svgd":

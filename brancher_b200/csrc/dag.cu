@@ -21,7 +21,8 @@ enum DagOp : int32_t {
     DAG_SIGMOID = BRN_DAG_SIGMOID, DAG_SOFTPLUS = BRN_DAG_SOFTPLUS, DAG_TANH = BRN_DAG_TANH, DAG_SIN = BRN_DAG_SIN,
     DAG_COS = BRN_DAG_COS, DAG_RELU = BRN_DAG_RELU, DAG_SQRT = BRN_DAG_SQRT, DAG_ABS = BRN_DAG_ABS,
     DAG_CLAMP_UNIT = BRN_DAG_CLAMP_UNIT, DAG_NORMAL_LP = BRN_DAG_NORMAL_LP, DAG_NORMAL_ENTROPY = BRN_DAG_NORMAL_ENTROPY,
-    DAG_ACC_SAMPLE = BRN_DAG_ACC_SAMPLE, DAG_ACC_ROW = BRN_DAG_ACC_ROW
+    DAG_ACC_SAMPLE = BRN_DAG_ACC_SAMPLE, DAG_ACC_ROW = BRN_DAG_ACC_ROW,
+    DAG_UNIFORM_HEADER = BRN_DAG_UNIFORM_HEADER, DAG_LEVEL = BRN_DAG_LEVEL      // layout markers, not operations
 };
 
 constexpr int DAG_MAX_PARAMS = BRN_DAG_MAX_PARAMS;     // shared-memory gradient accumulators
@@ -81,110 +82,168 @@ dag_elbo_kernel(const brn_dag_op* __restrict__ ops, int n_ops, int n_slots, cons
     const bool active = gid < total;
     const int s = active ? (int)(gid / B) : 0, b = active ? (int)(gid - (int64_t)s * B) : 0;
     const float inv_S = 1.0f / (float)r.s_total;
+    const int lane = threadIdx.x & 31;
     float acc = 0.f;
+
+    struct Op { int opcode, dst, a, b, c; float imm; };
+    auto decode = [](const uint4& w) {
+        Op o;
+        o.opcode = (int)(w.x & 0xffu); o.dst = (int)(w.x >> 8); o.a = (int)(w.y & 0xffffu); o.b = (int)(w.y >> 16);
+        o.c = (int)w.z; o.imm = __uint_as_float(w.w);
+        return o;
+    };
+    auto fetch = [&](int i) { return *reinterpret_cast<const uint4*>(&sops[i]); };
+
+    // value of one op (va, vb = the a / b slot operands, already loaded)
+    auto fwd_op = [&](const Op& o, float va, float vb) -> float {
+        float x = 0.f;
+        switch (o.opcode) {
+            case DAG_CONST: x = o.imm; break;
+            case DAG_PARAM: x = params[o.a]; break;
+            case DAG_DATA: x = data[(int64_t)b * n_cols + o.a]; break;
+            case DAG_EPS:
+                x = eps ? eps[(int64_t)s * n_eps + o.a] : philox_normal1(r.seed, r.offset, (uint32_t)o.a, (uint32_t)(r.s0 + s), 0);
+                break;
+            case DAG_ADD: x = va + vb; break;
+            case DAG_SUB: x = va - vb; break;
+            case DAG_MUL: x = va * vb; break;
+            case DAG_DIV: x = va / vb; break;
+            case DAG_NEG: x = -va; break;
+            case DAG_POWI: x = dag_powi(va, o.imm); break;
+            case DAG_EXP: x = expf(va); break;
+            case DAG_LOG: x = logf(va); break;
+            case DAG_LOG1P: x = log1pf(va); break;
+            case DAG_SIGMOID: x = sigmoidf(va); break;
+            case DAG_SOFTPLUS: x = softplusf(va); break;
+            case DAG_TANH: x = tanhf(va); break;
+            case DAG_SIN: x = sinf(va); break;
+            case DAG_COS: x = cosf(va); break;
+            case DAG_RELU: x = fmaxf(va, 0.f); break;
+            case DAG_SQRT: x = sqrtf(va); break;
+            case DAG_ABS: x = fabsf(va); break;
+            case DAG_CLAMP_UNIT: x = fminf(fmaxf(va, 1.17549435e-38f), 1.0f - 1.1920929e-07f); break;
+            case DAG_NORMAL_LP: {      // torch Normal.log_prob: -((x-mu)^2)/(2 sigma^2) - log sigma - log sqrt(2 pi)
+                const float df = va - vb, sg = V(o.c);
+                x = -(df * df) / (2.f * (sg * sg)) - logf(sg) - BRN_HALF_LOG_2PI;
+                break;
+            }
+            case DAG_NORMAL_ENTROPY: x = 0.5f + BRN_HALF_LOG_2PI + logf(va); break;
+            case DAG_ACC_SAMPLE: if (b == 0) acc += va; break;
+            case DAG_ACC_ROW: acc += va; break;
+            default: break;
+        }
+        return x;
+    };
+    // adjoint propagation of one op: g = d loss / d dst; adds into this thread's adjoint copies of the operand slots
+    auto bwd_op = [&](const Op& o, float g, float va, float vb) {
+        switch (o.opcode) {
+            case DAG_ACC_SAMPLE: if (b == 0) A(o.a) -= inv_S; break;
+            case DAG_ACC_ROW: A(o.a) -= inv_S; break;
+            case DAG_PARAM: if (g != 0.f) atomicAdd(&sgrad[o.a], g); break;
+            case DAG_ADD: A(o.a) += g; A(o.b) += g; break;
+            case DAG_SUB: A(o.a) += g; A(o.b) -= g; break;
+            case DAG_MUL: A(o.a) += g * vb; A(o.b) += g * va; break;
+            case DAG_DIV: {
+                const float inv = 1.f / vb;
+                A(o.a) += g * inv;
+                A(o.b) -= g * V(o.dst) * inv;
+                break;
+            }
+            case DAG_NEG: A(o.a) -= g; break;
+            case DAG_POWI: A(o.a) += g * o.imm * dag_powi(va, o.imm - 1.f); break;
+            case DAG_EXP: A(o.a) += g * V(o.dst); break;
+            case DAG_LOG: A(o.a) += g / va; break;
+            case DAG_LOG1P: A(o.a) += g / (1.f + va); break;
+            case DAG_SIGMOID: { const float y = V(o.dst); A(o.a) += g * y * (1.f - y); break; }
+            case DAG_SOFTPLUS: A(o.a) += g * (va > 20.f ? 1.f : sigmoidf(va)); break;
+            case DAG_TANH: { const float y = V(o.dst); A(o.a) += g * (1.f - y * y); break; }
+            case DAG_SIN: A(o.a) += g * cosf(va); break;
+            case DAG_COS: A(o.a) -= g * sinf(va); break;
+            case DAG_RELU: A(o.a) += va > 0.f ? g : 0.f; break;
+            case DAG_SQRT: A(o.a) += g * 0.5f / V(o.dst); break;
+            case DAG_ABS: A(o.a) += va >= 0.f ? g : -g; break;
+            case DAG_CLAMP_UNIT: A(o.a) += (va >= 1.17549435e-38f && va <= 1.0f - 1.1920929e-07f) ? g : 0.f; break;
+            case DAG_NORMAL_LP: {
+                const float df = va - vb, sg = V(o.c), inv_var = 1.f / (sg * sg);
+                const float t = g * df * inv_var;
+                A(o.a) -= t;
+                A(o.b) += t;
+                A(o.c) += g * (df * df * inv_var - 1.f) / sg;
+                break;
+            }
+            case DAG_NORMAL_ENTROPY: A(o.a) += g / va; break;
+            default: break;     // CONST / DATA / EPS: leaves
+        }
+    };
+
+    // ---- table layout: [UNIFORM_HEADER (a = entries that follow)] { [LEVEL (a = ops in this level, b = ops in the previous
+    //      one)] ops... }*  then the per-sample ops.  Uniform ops depend on parameters and constants only.
+    int u_begin = 0, u_end = 0;
+    if ((sops[0].w0 & 0xffu) == DAG_UNIFORM_HEADER) { u_begin = 1; u_end = 1 + (int)(sops[0].w1 & 0xffffu); }
+    const int s_begin = SMEM_FRAME ? u_end : 0;       // thread-local frames: every thread evaluates the uniform ops itself
+
+    int last_marker = -1;
+    if constexpr (SMEM_FRAME) {
+        // ---------------- uniform forward: ONE evaluation per CTA, the lanes of the warp take the ops of a dependency level in
+        // parallel (a serial walk costs one full op latency per op, and C1 has too few warps to hide any of it); each result
+        // is broadcast into all 32 lane copies of its slot (rotated: conflict-free)
+        for (int i = u_begin; i < u_end;) {
+            const int cnt = (int)(sops[i].w1 & 0xffffu);
+            for (int k = i + 1 + lane; k <= i + cnt; k += 32) {
+                const Op o = decode(fetch(k));
+                const float x = fwd_op(o, V(min(o.a, last_slot)), V(min(o.b, last_slot)));
+                float* row = vsm - lane + (size_t)o.dst * 32;
+#pragma unroll 8
+                for (int j = 0; j < 32; ++j) row[(j + lane) & 31] = x;
+            }
+            __syncwarp();
+            last_marker = i;
+            i += cnt + 1;
+        }
+        for (int i = 0; i < n_slots; ++i) A(i) = 0.f;       // every lane (idle lanes help in the uniform reverse sweep)
+    }
 
     if (active) {
         // ---------------- forward
-        uint4 nxt = *reinterpret_cast<const uint4*>(&sops[0]);
-        for (int i = 0; i < n_ops; ++i) {
-            const uint4 w = nxt;
-            nxt = *reinterpret_cast<const uint4*>(&sops[min(i + 1, n_ops - 1)]);
-            struct { int opcode, dst, a, b, c; float imm; } o;
-            o.opcode = (int)(w.x & 0xffu); o.dst = (int)(w.x >> 8); o.a = (int)(w.y & 0xffffu); o.b = (int)(w.y >> 16);
-            o.c = (int)w.z; o.imm = __uint_as_float(w.w);
+        uint4 nxt = fetch(min(s_begin, n_ops - 1));
+        for (int i = s_begin; i < n_ops; ++i) {
+            const Op o = decode(nxt);
+            nxt = fetch(min(i + 1, n_ops - 1));
+            if (o.opcode >= DAG_UNIFORM_HEADER) continue;       // layout markers (thread-local frames walk the whole table)
             const float va = V(min(o.a, last_slot)), vb = V(min(o.b, last_slot));       // operand loads overlap the branch
-            float x = 0.f;
-            switch (o.opcode) {
-                case DAG_CONST: x = o.imm; break;
-                case DAG_PARAM: x = params[o.a]; break;
-                case DAG_DATA: x = data[(int64_t)b * n_cols + o.a]; break;
-                case DAG_EPS:
-                    x = eps ? eps[(int64_t)s * n_eps + o.a]
-                            : philox_normal1(r.seed, r.offset, (uint32_t)o.a, (uint32_t)(r.s0 + s), 0);
-                    break;
-                case DAG_ADD: x = va + vb; break;
-                case DAG_SUB: x = va - vb; break;
-                case DAG_MUL: x = va * vb; break;
-                case DAG_DIV: x = va / vb; break;
-                case DAG_NEG: x = -va; break;
-                case DAG_POWI: x = dag_powi(va, o.imm); break;
-                case DAG_EXP: x = expf(va); break;
-                case DAG_LOG: x = logf(va); break;
-                case DAG_LOG1P: x = log1pf(va); break;
-                case DAG_SIGMOID: x = sigmoidf(va); break;
-                case DAG_SOFTPLUS: x = softplusf(va); break;
-                case DAG_TANH: x = tanhf(va); break;
-                case DAG_SIN: x = sinf(va); break;
-                case DAG_COS: x = cosf(va); break;
-                case DAG_RELU: x = fmaxf(va, 0.f); break;
-                case DAG_SQRT: x = sqrtf(va); break;
-                case DAG_ABS: x = fabsf(va); break;
-                case DAG_CLAMP_UNIT: x = fminf(fmaxf(va, 1.17549435e-38f), 1.0f - 1.1920929e-07f); break;
-                case DAG_NORMAL_LP: {      // torch Normal.log_prob: -((x-mu)^2)/(2 sigma^2) - log sigma - log sqrt(2 pi)
-                    const float df = va - vb, sg = V(o.c);
-                    x = -(df * df) / (2.f * (sg * sg)) - logf(sg) - BRN_HALF_LOG_2PI;
-                    break;
-                }
-                case DAG_NORMAL_ENTROPY: x = 0.5f + BRN_HALF_LOG_2PI + logf(va); break;
-                case DAG_ACC_SAMPLE: if (b == 0) acc += va; break;
-                case DAG_ACC_ROW: acc += va; break;
-                default: break;
-            }
-            V(o.dst) = x;
+            V(o.dst) = fwd_op(o, va, vb);
         }
         // ---------------- reverse: d loss / d slot, loss = -(1/S) * acc
-        for (int i = 0; i < n_slots; ++i) A(i) = 0.f;
-        nxt = *reinterpret_cast<const uint4*>(&sops[n_ops - 1]);
-        for (int i = n_ops - 1; i >= 0; --i) {
-            const uint4 w = nxt;
-            nxt = *reinterpret_cast<const uint4*>(&sops[max(i - 1, 0)]);
-            struct { int opcode, dst, a, b, c; float imm; } o;
-            o.opcode = (int)(w.x & 0xffu); o.dst = (int)(w.x >> 8); o.a = (int)(w.y & 0xffffu); o.b = (int)(w.y >> 16);
-            o.c = (int)w.z; o.imm = __uint_as_float(w.w);
+        if constexpr (!SMEM_FRAME)
+            for (int i = 0; i < n_slots; ++i) A(i) = 0.f;
+        nxt = fetch(n_ops - 1);
+        for (int i = n_ops - 1; i >= s_begin; --i) {
+            const Op o = decode(nxt);
+            nxt = fetch(max(i - 1, 0));
+            if (o.opcode >= DAG_UNIFORM_HEADER) continue;
             const float g = A(o.dst);
             const float va = V(min(o.a, last_slot)), vb = V(min(o.b, last_slot));
-            switch (o.opcode) {
-                case DAG_ACC_SAMPLE: if (b == 0) A(o.a) -= inv_S; break;
-                case DAG_ACC_ROW: A(o.a) -= inv_S; break;
-                case DAG_PARAM: if (g != 0.f) atomicAdd(&sgrad[o.a], g); break;
-                case DAG_ADD: A(o.a) += g; A(o.b) += g; break;
-                case DAG_SUB: A(o.a) += g; A(o.b) -= g; break;
-                case DAG_MUL: { const float xa = va, xb = vb; A(o.a) += g * xb; A(o.b) += g * xa; break; }
-                case DAG_DIV: {
-                    const float inv = 1.f / vb;
-                    A(o.a) += g * inv;
-                    A(o.b) -= g * V(o.dst) * inv;
-                    break;
-                }
-                case DAG_NEG: A(o.a) -= g; break;
-                case DAG_POWI: A(o.a) += g * o.imm * dag_powi(va, o.imm - 1.f); break;
-                case DAG_EXP: A(o.a) += g * V(o.dst); break;
-                case DAG_LOG: A(o.a) += g / va; break;
-                case DAG_LOG1P: A(o.a) += g / (1.f + va); break;
-                case DAG_SIGMOID: { const float y = V(o.dst); A(o.a) += g * y * (1.f - y); break; }
-                case DAG_SOFTPLUS: A(o.a) += g * (va > 20.f ? 1.f : sigmoidf(va)); break;
-                case DAG_TANH: { const float y = V(o.dst); A(o.a) += g * (1.f - y * y); break; }
-                case DAG_SIN: A(o.a) += g * cosf(va); break;
-                case DAG_COS: A(o.a) -= g * sinf(va); break;
-                case DAG_RELU: A(o.a) += va > 0.f ? g : 0.f; break;
-                case DAG_SQRT: A(o.a) += g * 0.5f / V(o.dst); break;
-                case DAG_ABS: A(o.a) += va >= 0.f ? g : -g; break;
-                case DAG_CLAMP_UNIT: {
-                    const float xa = va;
-                    A(o.a) += (xa >= 1.17549435e-38f && xa <= 1.0f - 1.1920929e-07f) ? g : 0.f;
-                    break;
-                }
-                case DAG_NORMAL_LP: {
-                    const float df = va - vb, sg = V(o.c), inv_var = 1.f / (sg * sg);
-                    const float t = g * df * inv_var;
-                    A(o.a) -= t;
-                    A(o.b) += t;
-                    A(o.c) += g * (df * df * inv_var - 1.f) / sg;
-                    break;
-                }
-                case DAG_NORMAL_ENTROPY: A(o.a) += g / va; break;
-                default: break;     // CONST / DATA / EPS: leaves
+            bwd_op(o, g, va, vb);
+        }
+    }
+
+    if constexpr (SMEM_FRAME) {
+        // ---------------- uniform reverse, levels in descending order: the adjoint of a uniform slot is the SUM of its 32 lane
+        // copies (per-sample consumers and later uniform ops both add into per-lane copies)
+        __syncwarp();
+        for (int i = last_marker; i >= u_begin;) {
+            const int cnt = (int)(sops[i].w1 & 0xffffu), prev = (int)(sops[i].w1 >> 16);
+            for (int k = i + 1 + lane; k <= i + cnt; k += 32) {
+                const Op o = decode(fetch(k));
+                const float* row = asm_ - lane + (size_t)o.dst * 32;
+                float g = 0.f;
+#pragma unroll 8
+                for (int j = 0; j < 32; ++j) g += row[(j + lane) & 31];
+                bwd_op(o, g, V(min(o.a, last_slot)), V(min(o.b, last_slot)));
             }
+            __syncwarp();
+            if (i == u_begin) break;
+            i -= prev + 1;
         }
     }
     __syncthreads();

@@ -316,6 +316,7 @@ def _lower_dense(joint, posterior):
 _DAG = dict(CONST=0, PARAM=1, DATA=2, EPS=3, ADD=4, SUB=5, MUL=6, DIV=7, NEG=8, POWI=9, EXP=10, LOG=11, LOG1P=12,
             SIGMOID=13, SOFTPLUS=14, TANH=15, SIN=16, COS=17, RELU=18, SQRT=19, ABS=20, CLAMP_UNIT=21, NORMAL_LP=22,
             NORMAL_ENTROPY=23, ACC_SAMPLE=24, ACC_ROW=25)             # include/brancher_cuda.h: enum brn_dag_opcode
+_DAG_UNIFORM_HEADER, _DAG_LEVEL = 26, 27                                  # layout markers of the device table (not operations)
 _DAG_BINARY = {"add": "ADD", "sub": "SUB", "mul": "MUL", "truediv": "DIV"}
 _DAG_UNARY = {"exp": "EXP", "log": "LOG", "log1p": "LOG1P", "sigmoid": "SIGMOID", "softplus": "SOFTPLUS", "tanh": "TANH",
               "sin": "SIN", "cos": "COS", "relu": "RELU", "sqrt": "SQRT", "abs": "ABS", "neg": "NEG"}
@@ -381,10 +382,48 @@ class DagProgram:
         self.eps_names.append(name)
         return self.emit("EPS", a=len(self.eps_names) - 1)
 
+    def device_ops(self):
+        """The table the kernel walks (include/brancher_cuda.h: UNIFORM_HEADER / LEVEL markers): the sample-independent ops --
+        those that depend on parameters and constants only, e.g. softplus(rho), analytic entropies -- are hoisted to the
+        front and grouped by dependency level, so the kernel evaluates them once per CTA with the lanes of a warp working
+        on a level in parallel; the per-sample ops follow in their original (topological) order.  `self.ops` itself stays
+        the plain program (what oracle/dag_interp.py interprets)."""
+        inv = {v: k for k, v in _DAG.items()}
+        level = {}                       # slot -> dependency level of the uniform op that defines it
+        uniform, rest = [], []
+        for o in self.ops:
+            op, dst, a_, b_, c_ = inv[o[0]], o[1], o[2], o[3], o[4]
+            if op in ("CONST", "PARAM"):
+                lv = 0
+            elif op in ("EPS", "DATA", "ACC_SAMPLE", "ACC_ROW"):
+                lv = None
+            else:
+                ins = (a_, b_, c_) if op == "NORMAL_LP" else ((a_, b_) if op in ("ADD", "SUB", "MUL", "DIV") else (a_,))
+                lv = None if any(x not in level for x in ins) else 1 + max(level[x] for x in ins)
+            if lv is None:
+                rest.append(o)
+            else:
+                level[dst] = lv
+                uniform.append((lv, o))
+        if not uniform:
+            return list(self.ops)
+        out, prev = [], 0
+        for lv in sorted({l for l, _ in uniform}):
+            ops_lv = sorted((o for l, o in uniform if l == lv), key=lambda o: o[0])       # same opcodes side by side: less divergence
+            for k in range(0, len(ops_lv), 65535):
+                chunk = ops_lv[k:k + 65535]
+                out.append((_DAG_LEVEL, 0, len(chunk), prev, 0, 0.0))
+                out.extend(chunk)
+                prev = len(chunk)
+        if len(out) > 65535:             # header count is a 16-bit field: keep such programs in the plain layout
+            return list(self.ops)
+        return [(_DAG_UNIFORM_HEADER, 0, len(out), 0, 0, 0.0)] + out + rest
+
     def table(self):
-        t = np.zeros(len(self.ops), dtype=np.dtype([("opcode", "<i4"), ("dst", "<i4"), ("a", "<i4"), ("b", "<i4"),
-                                                    ("c", "<i4"), ("imm", "<f4")]))
-        for i, o in enumerate(self.ops):
+        ops = self.device_ops()
+        t = np.zeros(len(ops), dtype=np.dtype([("opcode", "<i4"), ("dst", "<i4"), ("a", "<i4"), ("b", "<i4"),
+                                               ("c", "<i4"), ("imm", "<f4")]))
+        for i, o in enumerate(ops):
             t[i] = o
         return t
 
@@ -576,7 +615,7 @@ class DagPlan(Plan):
                 eps = torch.stack([torch.as_tensor(_INJECTED[n], dtype=torch.float32, device=dev).reshape(-1)[s0:s0 + S_local]
                                    for n in P.eps_names], dim=1).contiguous()
             pvec = torch.stack([p.detach().reshape(()) for p in params]) if params else torch.zeros(0, device=dev)
-            loss, g = cu.dag_elbo_fwd_bwd(self._ops_dev, len(P.ops), P.n_slots, pvec, data, self.n_rows, eps, len(P.eps_names), r)
+            loss, g = cu.dag_elbo_fwd_bwd(self._ops_dev, self._ops_dev.numel() // 24, P.n_slots, pvec, data, self.n_rows, eps, len(P.eps_names), r)
             loss, grads = distributed.all_reduce_partials(loss, [g])
             g = grads[0]
             return loss, [g[i].reshape(p.shape) if p.requires_grad else None for i, p in enumerate(params)]

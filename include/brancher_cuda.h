@@ -137,7 +137,15 @@ enum brn_dag_opcode {
     BRN_DAG_ADD = 4, BRN_DAG_SUB = 5, BRN_DAG_MUL = 6, BRN_DAG_DIV = 7, BRN_DAG_NEG = 8, BRN_DAG_POWI = 9,
     BRN_DAG_EXP = 10, BRN_DAG_LOG = 11, BRN_DAG_LOG1P = 12, BRN_DAG_SIGMOID = 13, BRN_DAG_SOFTPLUS = 14, BRN_DAG_TANH = 15,
     BRN_DAG_SIN = 16, BRN_DAG_COS = 17, BRN_DAG_RELU = 18, BRN_DAG_SQRT = 19, BRN_DAG_ABS = 20, BRN_DAG_CLAMP_UNIT = 21,
-    BRN_DAG_NORMAL_LP = 22, BRN_DAG_NORMAL_ENTROPY = 23, BRN_DAG_ACC_SAMPLE = 24, BRN_DAG_ACC_ROW = 25
+    BRN_DAG_NORMAL_LP = 22, BRN_DAG_NORMAL_ENTROPY = 23, BRN_DAG_ACC_SAMPLE = 24, BRN_DAG_ACC_ROW = 25,
+    /* Optional layout markers (not operations).  A table may start with the sample-independent ("uniform") part of the
+     * program -- ops that depend on parameters and constants only -- grouped by dependency level:
+     *     UNIFORM_HEADER (a = number of entries that follow in the uniform segment)
+     *     { LEVEL (a = ops in this level, b = ops in the previous level) , ops of the level ... } *
+     *     per-sample ops
+     * The kernel evaluates the uniform segment once per CTA, the lanes of a warp taking the ops of a level in parallel,
+     * instead of once per (sample, row) thread. */
+    BRN_DAG_UNIFORM_HEADER = 26, BRN_DAG_LEVEL = 27
 };
 typedef struct brn_dag_op {
     int32_t opcode, dst, a, b, c;

@@ -103,15 +103,15 @@ def test_dag_philox_mode_and_shard_invariance():
     pvec = torch.stack([p.detach().reshape(()) for p in P.params])
     data = torch.stack([lowering._observed_tensor(c).reshape(-1).float().expand(plan.n_rows) for c in P.columns], 1).contiguous()
     r = cu.sample_range(S, seed=11, offset=3)
-    loss, gr = cu.dag_elbo_fwd_bwd(ops, len(P.ops), P.n_slots, pvec, data, plan.n_rows, None, len(P.eps_names), r)
+    loss, gr = cu.dag_elbo_fwd_bwd(ops, ops.numel() // 24, P.n_slots, pvec, data, plan.n_rows, None, len(P.eps_names), r)
     eps = torch.cat([cu.philox_normal(1, k, r, dev) for k in range(len(P.eps_names))], 1).contiguous()
-    loss2, gr2 = cu.dag_elbo_fwd_bwd(ops, len(P.ops), P.n_slots, pvec, data, plan.n_rows, eps, len(P.eps_names), r)
+    loss2, gr2 = cu.dag_elbo_fwd_bwd(ops, ops.numel() // 24, P.n_slots, pvec, data, plan.n_rows, eps, len(P.eps_names), r)
     assert_close(loss.item(), loss2.item(), "philox vs injected loss", rtol=1e-6, atol=1e-6)
     assert_close(gr.cpu().numpy(), gr2.cpu().numpy(), "philox vs injected grads", rtol=1e-6, atol=1e-6, scale=float(gr2.abs().max()))
     lsum, gsum = torch.zeros(1, dtype=torch.float64, device=dev), torch.zeros_like(gr)
     for s0, n in [(0, 20), (20, 17)]:
         rr = cu.sample_range(S, s0=s0, s_local=n, seed=11, offset=3)
-        l, g_ = cu.dag_elbo_fwd_bwd(ops, len(P.ops), P.n_slots, pvec, data, plan.n_rows, None, len(P.eps_names), rr)
+        l, g_ = cu.dag_elbo_fwd_bwd(ops, ops.numel() // 24, P.n_slots, pvec, data, plan.n_rows, None, len(P.eps_names), rr)
         lsum += l; gsum += g_
     assert_close(lsum.item(), loss.item(), "sharded loss", rtol=1e-6, atol=1e-6)
     assert_close(gsum.cpu().numpy(), gr.cpu().numpy(), "sharded grads", rtol=1e-5, atol=1e-6, scale=float(gr.abs().max()))
