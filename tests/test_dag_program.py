@@ -128,3 +128,38 @@ def test_ar1_perform_inference_readme_config():
     curve = model.diagnostics["loss curve"]
     assert curve.shape == (60,) and np.isfinite(curve).all()
     assert curve[-10:].mean() < curve[:10].mean()
+
+
+def _plain_table(P):
+    """Device table WITHOUT the uniform segment: the logical program as is."""
+    t = np.zeros(len(P.ops), dtype=P.table().dtype)
+    for i, o in enumerate(P.ops):
+        t[i] = o
+    return t
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,S", [("ar1_readme", 300), ("ar1_readme", 45000), ("multivariate_regression", 33),
+                                    ("multivariate_regression", 4000), ("lognormal_normal", 7)])
+def test_dag_uniform_segment_matches_plain_program(name, S):
+    """The hoisted, lane-parallel uniform segment (UNIFORM_HEADER / LEVEL layout) against the plain per-thread walk of the
+    same program, same Philox noise: small S runs the shared-memory-frame kernel (one warp per CTA, uniform phases active),
+    large S the thread-local-frame kernel (markers skipped, every thread evaluates the uniform ops itself)."""
+    from brancher_b200 import _cuda as cu, lowering
+    ns, model, plan, names = build(name, "cuda:0")
+    P, dev = plan.prog, torch.device("cuda:0")
+    layout = P.table()
+    assert layout[0]["opcode"] == 26 and len(layout) > len(P.ops)          # header + level markers present
+    pvec = torch.stack([p.detach().reshape(()) for p in P.params])
+    data = None
+    if P.columns:
+        data = torch.stack([lowering._observed_tensor(c).reshape(-1).float().expand(plan.n_rows) for c in P.columns], 1).contiguous()
+    r = cu.sample_range(S, seed=5, offset=2)
+    out = []
+    for t in (layout, _plain_table(P)):
+        ops = torch.from_numpy(t.view(np.uint8)).to(dev)
+        loss, gr = cu.dag_elbo_fwd_bwd(ops, ops.numel() // 24, P.n_slots, pvec, data, plan.n_rows, None, len(P.eps_names), r)
+        out.append((loss.item(), gr.cpu().numpy()))
+    assert_close(out[0][0], out[1][0], "%s S=%d loss: uniform segment vs plain" % (name, S), rtol=2e-6, atol=1e-6)
+    assert_close(out[0][1], out[1][1], "%s S=%d grads: uniform segment vs plain" % (name, S), rtol=1e-5, atol=1e-6,
+                 scale=float(np.abs(out[1][1]).max()))
