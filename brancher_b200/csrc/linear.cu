@@ -234,6 +234,7 @@ constexpr int LT_BN1 = 256;       // logits GEMM: samples per n-tile (16 epilogu
 constexpr int LT_EW1 = 16;
 constexpr int LT_BN2 = 128;       // gradient GEMM: features per n-tile (F <= 128)
 constexpr int LT_BK = 16;
+constexpr int LT_BK2 = 32;        // gradient GEMM: 128-byte operand rows (both operands are scattered K-major rows: half the requests)
 
 // rows per chunk of the tcgen05 path: whole 128-row tiles such that (m-tiles x n-tiles) fills ~2 rounds of the grid
 static int linear_tc_chunk_rows(int S, int sms) {
@@ -430,16 +431,16 @@ static int launch_linear_tc(const float* X, const float* y, int64_t N, int F, in
         const int64_t xt = (r0 / b.nb) * F * b.ldNB;
         int e = 0;
         if (d_plain && xt_plain)
-            e = launch_umma_nt<LT_BN2, LT_BK, EpiAccum, UG_EPI_WARPS, 3>(b.dTh, nullptr, S, b.ldNB, b.Xth + xt, nullptr, F, b.ldNB, nb, 0,
+            e = launch_umma_nt<LT_BN2, LT_BK2, EpiAccum, UG_EPI_WARPS, 3>(b.dTh, nullptr, S, b.ldNB, b.Xth + xt, nullptr, F, b.ldNB, nb, 0,
                                                                          drain, e2, stream, b.slices > 1);
         else if (d_plain)
-            e = launch_umma_nt<LT_BN2, LT_BK, EpiAccum, UG_EPI_WARPS, 1>(b.dTh, nullptr, S, b.ldNB, b.Xth + xt, b.Xtl + xt, F, b.ldNB, nb,
+            e = launch_umma_nt<LT_BN2, LT_BK2, EpiAccum, UG_EPI_WARPS, 1>(b.dTh, nullptr, S, b.ldNB, b.Xth + xt, b.Xtl + xt, F, b.ldNB, nb,
                                                                          0, drain, e2, stream, b.slices > 1);
         else if (xt_plain)
-            e = launch_umma_nt<LT_BN2, LT_BK, EpiAccum, UG_EPI_WARPS, 2>(b.dTh, b.dTl, S, b.ldNB, b.Xth + xt, nullptr, F, b.ldNB, nb, 0,
+            e = launch_umma_nt<LT_BN2, LT_BK2, EpiAccum, UG_EPI_WARPS, 2>(b.dTh, b.dTl, S, b.ldNB, b.Xth + xt, nullptr, F, b.ldNB, nb, 0,
                                                                          drain, e2, stream, b.slices > 1);
         else
-            e = launch_umma_nt<LT_BN2, LT_BK, EpiAccum>(b.dTh, b.dTl, S, b.ldNB, b.Xth + xt, b.Xtl + xt, F, b.ldNB, nb, 0, drain, e2,
+            e = launch_umma_nt<LT_BN2, LT_BK2, EpiAccum>(b.dTh, b.dTl, S, b.ldNB, b.Xth + xt, b.Xtl + xt, F, b.ldNB, nb, 0, drain, e2,
                                                         stream, b.slices > 1);
         if (e) return e;
     }

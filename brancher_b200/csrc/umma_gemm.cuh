@@ -29,7 +29,9 @@ struct UmmaSmem {
     static constexpr int A_BYTES = UG_BM * BK * 4;
     static constexpr int B_BYTES = BN * BK * 4;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    static constexpr int STAGES = BK == 32 ? 2 : (5 * STAGE_BYTES + 1024 <= 227 * 1024 ? 5 : 4);
+    static constexpr int MAX_STAGES = (227 * 1024 - 1024) / STAGE_BYTES;
+    static constexpr int STAGES = MAX_STAGES >= 5 ? 5 : MAX_STAGES;       // e.g. BN=208/BK=16: 5, BN=256/BK=16: 4, BN=128/BK=32: 3
+    static_assert(STAGES >= 2, "tile too large for a double-buffered ring");
     static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024;   // + alignment slack
     static_assert(A_BYTES % (8 * BK * 4) == 0 && B_BYTES % (8 * BK * 4) == 0, "tiles must be whole swizzle atoms");
 };
