@@ -55,6 +55,49 @@ def test_compiled_program_matches_reference_on_cpu(tag):
         assert_close(grads[k], v.reshape(()), tag + " grad " + k, rtol=2e-5, atol=2e-6, scale=sc)
 
 
+@pytest.mark.parametrize("tag", sorted(CASES))
+def test_device_table_layout(tag):
+    """Host logic of the device table (lowering.DagProgram.device_ops): common subexpressions are merged, the
+    sample-independent ops sit in the UNIFORM_HEADER / LEVEL segment with every operand defined in an EARLIER level, the
+    per-sample ops keep their order, and walking the table in device order (markers skipped) reproduces the plain
+    program's loss and gradients in the numpy interpreter."""
+    from oracle import dag_interp
+    from brancher_b200.lowering import _DAG, _observed_tensor
+    g = load_golden(tag)
+    ns, model, plan, names = build(tag, "cpu")
+    P = plan.prog
+    inv = {v: k for k, v in _DAG.items()}
+    pure = [o for o in P.ops if inv[o[0]] not in ("EPS", "DATA", "ACC_SAMPLE", "ACC_ROW")]
+    norm = lambda o: (o[0],) + (tuple(sorted(o[2:4])) if inv[o[0]] in ("ADD", "MUL") else tuple(o[2:4])) + tuple(o[4:])
+    assert len({norm(o) for o in pure}) == len(pure), "duplicate pure op survived CSE"
+    dev = P.device_ops()
+    assert dev[0][0] == 26 and sorted(o[1] for o in dev if o[0] < 26) == sorted(o[1] for o in P.ops)
+    n_uniform = dev[0][2]
+    seg, rest = dev[1:1 + n_uniform], dev[1 + n_uniform:]
+    assert [o for o in rest] == [o for o in P.ops if o in rest], "per-sample ops must keep their program order"
+    defined, i, prev = set(), 0, 0
+    while i < len(seg):
+        assert seg[i][0] == 27 and seg[i][3] == prev
+        cnt = seg[i][2]
+        level_ops = seg[i + 1:i + 1 + cnt]
+        for o in level_ops:
+            op = inv[o[0]]
+            assert op not in ("EPS", "DATA", "ACC_SAMPLE", "ACC_ROW")
+            ins = () if op in ("CONST", "PARAM") else ((o[2], o[3], o[4]) if op == "NORMAL_LP" else
+                                                       ((o[2], o[3]) if op in ("ADD", "SUB", "MUL", "DIV") else (o[2],)))
+            assert all(x in defined for x in ins), "operand of a uniform op is not defined in an earlier level"
+        defined |= {o[1] for o in level_ops}
+        prev, i = cnt, i + 1 + cnt
+    eps = np.stack([g["eps"][n] for n in P.eps_names], 1)
+    pv = np.array([g["param"][names[id(p)]].reshape(()) for p in P.params])
+    cols = [np.broadcast_to(_observed_tensor(c).cpu().numpy().reshape(-1), (plan.n_rows,)) for c in P.columns]
+    data = np.stack(cols, 1) if cols else None
+    l0, g0 = dag_interp.run(P.ops, P.n_slots, pv, data, eps)
+    l1, g1 = dag_interp.run([o for o in dev if o[0] < 26], P.n_slots, pv, data, eps)
+    np.testing.assert_allclose(l1, l0, rtol=1e-12)
+    np.testing.assert_allclose(g1, g0, rtol=1e-10, atol=1e-12)
+
+
 def test_unsupported_scalar_graphs_raise():
     from brancher_b200 import config, lowering
     config.set_device("cpu")
