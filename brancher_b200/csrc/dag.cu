@@ -85,10 +85,11 @@ dag_elbo_kernel(const brn_dag_op* __restrict__ ops, int n_ops, int n_slots, cons
     const int lane = threadIdx.x & 31;
     float acc = 0.f;
 
-    struct Op { int opcode, dst, a, b, c; float imm; };
+    struct Op { int opcode, flags, dst, a, b, c; float imm; };      // flags: fused accumulation of the result (1 sample, 2 row)
     auto decode = [](const uint4& w) {
         Op o;
-        o.opcode = (int)(w.x & 0xffu); o.dst = (int)(w.x >> 8); o.a = (int)(w.y & 0xffffu); o.b = (int)(w.y >> 16);
+        o.opcode = (int)(w.x & 0x3fu); o.flags = (int)((w.x >> 6) & 3u); o.dst = (int)(w.x >> 8);
+        o.a = (int)(w.y & 0xffffu); o.b = (int)(w.y >> 16);
         o.c = (int)w.z; o.imm = __uint_as_float(w.w);
         return o;
     };
@@ -179,7 +180,11 @@ dag_elbo_kernel(const brn_dag_op* __restrict__ ops, int n_ops, int n_slots, cons
     // ---- table layout: [UNIFORM_HEADER (a = entries that follow)] { [LEVEL (a = ops in this level, b = ops in the previous
     //      one)] ops... }*  then the per-sample ops.  Uniform ops depend on parameters and constants only.
     int u_begin = 0, u_end = 0;
-    if ((sops[0].w0 & 0xffu) == DAG_UNIFORM_HEADER) { u_begin = 1; u_end = 1 + (int)(sops[0].w1 & 0xffffu); }
+    int n_eps_ops = 0, n_data_ops = 0;                  // leading EPS / DATA ops of the per-sample segment (header fields b, c)
+    if ((sops[0].w0 & 0xffu) == DAG_UNIFORM_HEADER) {
+        u_begin = 1; u_end = 1 + (int)(sops[0].w1 & 0xffffu);
+        n_eps_ops = (int)(sops[0].w1 >> 16); n_data_ops = (int)sops[0].c;
+    }
     const int s_begin = SMEM_FRAME ? u_end : 0;       // thread-local frames: every thread evaluates the uniform ops itself
 
     int last_marker = -1;
@@ -204,24 +209,50 @@ dag_elbo_kernel(const brn_dag_op* __restrict__ ops, int n_ops, int n_slots, cons
     }
 
     if (active) {
+        // ---------------- leaves first (shared-memory frames): the noise draws and the data loads of a thread are independent
+        // of each other, so two branch-free loops let them overlap instead of paying one full latency per interpreted op
+        int s_fwd = s_begin;
+        if constexpr (SMEM_FRAME) {
+#pragma unroll 4
+            for (int i = s_fwd; i < s_fwd + n_eps_ops; ++i) {
+                const Op o = decode(fetch(i));
+                V(o.dst) = eps ? eps[(int64_t)s * n_eps + o.a] : philox_normal1(r.seed, r.offset, (uint32_t)o.a, (uint32_t)(r.s0 + s), 0);
+            }
+            s_fwd += n_eps_ops;
+#pragma unroll 4
+            for (int i = s_fwd; i < s_fwd + n_data_ops; ++i) {
+                const Op o = decode(fetch(i));
+                V(o.dst) = data[(int64_t)b * n_cols + o.a];
+            }
+            s_fwd += n_data_ops;
+        }
         // ---------------- forward
-        uint4 nxt = fetch(min(s_begin, n_ops - 1));
-        for (int i = s_begin; i < n_ops; ++i) {
+        uint4 nxt = fetch(min(s_fwd, n_ops - 1));
+        for (int i = s_fwd; i < n_ops; ++i) {
             const Op o = decode(nxt);
             nxt = fetch(min(i + 1, n_ops - 1));
             if (o.opcode >= DAG_UNIFORM_HEADER) continue;       // layout markers (thread-local frames walk the whole table)
             const float va = V(min(o.a, last_slot)), vb = V(min(o.b, last_slot));       // operand loads overlap the branch
-            V(o.dst) = fwd_op(o, va, vb);
+            const float x = fwd_op(o, va, vb);
+            V(o.dst) = x;
+            if (o.flags) {                                      // ACC_SAMPLE / ACC_ROW of this result, fused by the host
+                if ((o.flags & 1) && b == 0) acc += x;
+                if (o.flags & 2) acc += x;
+            }
         }
         // ---------------- reverse: d loss / d slot, loss = -(1/S) * acc
         if constexpr (!SMEM_FRAME)
             for (int i = 0; i < n_slots; ++i) A(i) = 0.f;
         nxt = fetch(n_ops - 1);
-        for (int i = n_ops - 1; i >= s_begin; --i) {
+        for (int i = n_ops - 1; i >= s_fwd; --i) {          // (leaves have no operands: nothing to propagate)
             const Op o = decode(nxt);
             nxt = fetch(max(i - 1, 0));
             if (o.opcode >= DAG_UNIFORM_HEADER) continue;
-            const float g = A(o.dst);
+            float g = A(o.dst);
+            if (o.flags) {
+                if ((o.flags & 1) && b == 0) g -= inv_S;
+                if (o.flags & 2) g -= inv_S;
+            }
             const float va = V(min(o.a, last_slot)), vb = V(min(o.b, last_slot));
             bwd_op(o, g, va, vb);
         }

@@ -407,6 +407,26 @@ class DagProgram:
                 uniform.append((lv, o))
         if not uniform:
             return list(self.ops)
+        # per-sample segment: the leaves (noise draws, data loads) first -- the kernel issues them back to back -- and every
+        # ACC_SAMPLE / ACC_ROW whose operand is produced by a per-sample non-leaf op is folded into that op as a flag
+        # (bit 6 / bit 7 of the opcode byte): one interpreted op less per accumulated term
+        eps_ops = [o for o in rest if inv[o[0]] == "EPS"]
+        data_ops = [o for o in rest if inv[o[0]] == "DATA"]
+        body = [o for o in rest if inv[o[0]] not in ("EPS", "DATA")]
+        producer = {o[1]: i for i, o in enumerate(body) if not inv[o[0]].startswith("ACC")}
+        fused, flags = set(), {}
+        for i, o in enumerate(body):
+            op = inv[o[0]]
+            if op.startswith("ACC") and o[2] in producer:
+                bit = 0x40 if op == "ACC_SAMPLE" else 0x80
+                j = producer[o[2]]
+                if not flags.get(j, 0) & bit:
+                    flags[j] = flags.get(j, 0) | bit
+                    fused.add(i)
+        body = [((o[0] | flags.get(i, 0),) + tuple(o[1:])) for i, o in enumerate(body) if i not in fused]
+        if len(eps_ops) > 65535 or len(data_ops) > 65535:
+            return list(self.ops)
+        rest = eps_ops + data_ops + body
         out, prev = [], 0
         for lv in sorted({l for l, _ in uniform}):
             ops_lv = sorted((o for l, o in uniform if l == lv), key=lambda o: o[0])       # same opcodes side by side: less divergence
@@ -417,7 +437,7 @@ class DagProgram:
                 prev = len(chunk)
         if len(out) > 65535:             # header count is a 16-bit field: keep such programs in the plain layout
             return list(self.ops)
-        return [(_DAG_UNIFORM_HEADER, 0, len(out), 0, 0, 0.0)] + out + rest
+        return [(_DAG_UNIFORM_HEADER, 0, len(out), len(eps_ops), len(data_ops), 0.0)] + out + rest
 
     def table(self):
         ops = self.device_ops()

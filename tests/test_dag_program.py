@@ -71,10 +71,28 @@ def test_device_table_layout(tag):
     norm = lambda o: (o[0],) + (tuple(sorted(o[2:4])) if inv[o[0]] in ("ADD", "MUL") else tuple(o[2:4])) + tuple(o[4:])
     assert len({norm(o) for o in pure}) == len(pure), "duplicate pure op survived CSE"
     dev = P.device_ops()
-    assert dev[0][0] == 26 and sorted(o[1] for o in dev if o[0] < 26) == sorted(o[1] for o in P.ops)
-    n_uniform = dev[0][2]
+    assert dev[0][0] == 26
+    n_uniform, n_eps_ops, n_data_ops = dev[0][2], dev[0][3], dev[0][4]
     seg, rest = dev[1:1 + n_uniform], dev[1 + n_uniform:]
-    assert [o for o in rest] == [o for o in P.ops if o in rest], "per-sample ops must keep their program order"
+    # per-sample segment: noise draws, then data loads, then the body in program order; an ACC whose operand is produced by
+    # a body op is folded into that op as a flag (bit 6: ACC_SAMPLE, bit 7: ACC_ROW of the opcode byte)
+    assert all(inv[o[0]] == "EPS" for o in rest[:n_eps_ops])
+    assert all(inv[o[0]] == "DATA" for o in rest[n_eps_ops:n_eps_ops + n_data_ops])
+    body = rest[n_eps_ops + n_data_ops:]
+    assert all(inv[o[0] & 0x3f] not in ("EPS", "DATA") for o in body)
+    expanded, extra = [], P.n_slots            # fused accumulations written out again (fresh dst slots)
+    for o in body:
+        expanded.append((o[0] & 0x3f,) + tuple(o[1:]))
+        for bit, acc in ((0x40, "ACC_SAMPLE"), (0x80, "ACC_ROW")):
+            if o[0] & bit:
+                expanded.append((_DAG[acc], extra, o[1], 0, 0, 0.0))
+                extra += 1
+    key = lambda o: (o[0],) + tuple(o[2:])      # an op up to its destination slot
+    uniform_dst = {o[1] for o in seg if o[0] < 26}
+    plain_body = [o for o in P.ops if o[1] not in uniform_dst and inv[o[0]] not in ("EPS", "DATA")]
+    assert sorted(key(o) for o in expanded) == sorted(key(o) for o in plain_body), "per-sample ops changed"
+    kept = [o[1] for o in expanded if o[1] < P.n_slots]
+    assert kept == [o[1] for o in plain_body if o[1] in set(kept)], "per-sample ops must keep their order"
     defined, i, prev = set(), 0, 0
     while i < len(seg):
         assert seg[i][0] == 27 and seg[i][3] == prev
@@ -88,12 +106,13 @@ def test_device_table_layout(tag):
             assert all(x in defined for x in ins), "operand of a uniform op is not defined in an earlier level"
         defined |= {o[1] for o in level_ops}
         prev, i = cnt, i + 1 + cnt
+    walk = [o for o in seg if o[0] < 26] + list(rest[:n_eps_ops + n_data_ops]) + expanded
     eps = np.stack([g["eps"][n] for n in P.eps_names], 1)
     pv = np.array([g["param"][names[id(p)]].reshape(()) for p in P.params])
     cols = [np.broadcast_to(_observed_tensor(c).cpu().numpy().reshape(-1), (plan.n_rows,)) for c in P.columns]
     data = np.stack(cols, 1) if cols else None
     l0, g0 = dag_interp.run(P.ops, P.n_slots, pv, data, eps)
-    l1, g1 = dag_interp.run([o for o in dev if o[0] < 26], P.n_slots, pv, data, eps)
+    l1, g1 = dag_interp.run(walk, extra, pv, data, eps)
     np.testing.assert_allclose(l1, l0, rtol=1e-12)
     np.testing.assert_allclose(g1, g0, rtol=1e-10, atol=1e-12)
 
@@ -192,7 +211,7 @@ def test_dag_uniform_segment_matches_plain_program(name, S):
     ns, model, plan, names = build(name, "cuda:0")
     P, dev = plan.prog, torch.device("cuda:0")
     layout = P.table()
-    assert layout[0]["opcode"] == 26 and len(layout) > len(P.ops)          # header + level markers present
+    assert layout[0]["opcode"] == 26 and (layout["opcode"] == 27).sum() >= 1        # header + level markers present
     pvec = torch.stack([p.detach().reshape(()) for p in P.params])
     data = None
     if P.columns:
