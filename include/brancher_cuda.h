@@ -140,9 +140,11 @@ enum brn_dag_opcode {
     BRN_DAG_NORMAL_LP = 22, BRN_DAG_NORMAL_ENTROPY = 23, BRN_DAG_ACC_SAMPLE = 24, BRN_DAG_ACC_ROW = 25,
     /* Optional layout markers (not operations).  A table may start with the sample-independent ("uniform") part of the
      * program -- ops that depend on parameters and constants only -- grouped by dependency level:
-     *     UNIFORM_HEADER (a = number of entries that follow in the uniform segment)
+     *     UNIFORM_HEADER (a = number of entries that follow in the uniform segment,
+     *                     b / c = number of EPS / DATA ops that lead the per-sample segment, in that order)
      *     { LEVEL (a = ops in this level, b = ops in the previous level) , ops of the level ... } *
-     *     per-sample ops
+     *     per-sample ops: EPS ops, DATA ops, then the rest in topological order
+     * Bits 6 / 7 of a per-sample op's opcode fold an ACC_SAMPLE / ACC_ROW of its result into the op (opcodes are < 64).
      * The kernel evaluates the uniform segment once per CTA, the lanes of a warp taking the ops of a level in parallel,
      * instead of once per (sample, row) thread. */
     BRN_DAG_UNIFORM_HEADER = 26, BRN_DAG_LEVEL = 27
