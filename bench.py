@@ -522,7 +522,12 @@ def main_ours(args):
 
     clocks = ClockSampler(local_rank)
     clocks.start()
-    ms, launches, stages = timed(step, args.steps, args.warmup, profile=True)
+    # Headline pass: EXACTLY K steps, nothing but the product's own launches in the timed region.  The per-stage CUDA events of
+    # the library (10 records per C3 step) cost ~29 us per step when they sit in that region (measured, profiles/r1z_*), so the
+    # stage split and the dominant kernel's duration come from a second, equally long pass with the events enabled; its own
+    # total normalises the shares.
+    ms, launches, _ = timed(step, args.steps, args.warmup, profile=False)
+    ms_prof, _, stages = timed(step, args.steps, 1, profile=True)
     clk = clocks.stop()
     ms_e2e, _, _ = timed(lambda i: e2e_step(i), max(3, min(args.steps, 10)), 3)
     n_e2e = max(3, min(args.steps, 10))
@@ -531,7 +536,7 @@ def main_ours(args):
         units = units_per_rank * world
         value = units * args.steps / (ms * 1e-3)
         e2e_value = units * n_e2e / (ms_e2e * 1e-3)
-        stage_share = {k: round(v[0] / ms, 4) for k, v in stages.items()}
+        stage_share = {k: round(v[0] / ms_prof, 4) for k, v in stages.items()}
         traffic = ncu_traffic()
         if algo_flops:
             dom = max(algo_flops, key=lambda k: stages.get(k, (0, 0))[0] if k in stages else 0)
@@ -560,6 +565,8 @@ def main_ours(args):
                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                "config": {"workload": cfg["name"], "noise": "Philox4x32-10 in-kernel", "l2": "256 MiB flush between timed steps",
+                          "stage_timing": "separate pass of the same K steps with the library's per-stage CUDA events on "
+                                          "(%.4f ms/step there); the headline region carries no such events" % (ms_prof / args.steps),
                           "variant": (svgd_out[1] + " (K4a) + simt (K4b)") if wl == "svgd" else cu.last_variant(),
                           "global_samples_or_particles": S_total,
                           "sharding": {"bnn": "MC samples", "logreg": "data rows", "svgd": "particles", "vae": "batch rows",

@@ -1111,7 +1111,8 @@ extern "C" int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int
                 BRN_CUDA_OK(cudaMemsetAsync(ws.Wh + (size_t)S * HP * ws.ldP, 0, sizeof(float) * HP * ws.ldP, stream));
                 BRN_CUDA_OK(cudaMemsetAsync(ws.Wl + (size_t)S * HP * ws.ldP, 0, sizeof(float) * HP * ws.ldP, stream));
             }
-            if (int e = launch_sample_multi(vars + 1, offs + 1, 3, ws.eps, ws.W, L.ldw, *r, stream)) return e;
+            // (also zeroes the per-sample gradient slots of b1 / W2 / b2, which the mid stage accumulates into)
+            if (int e = launch_sample_multi(vars + 1, offs + 1, 3, ws.eps, ws.W, L.ldw, *r, stream, ws.dW)) return e;
             // first read of the minibatch: everything above overlaps a host->device copy announced by brn_set_data_ready_event
             if (int e = wait_data_ready(stream)) return e;
             if (int e = launch_split_tf32(X, P, B, P, ws.Xh, ws.Xl, ws.ldP, ws.Xth, ws.Xtl, ws.ldB, stream)) return e;
@@ -1137,7 +1138,8 @@ extern "C" int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int
         }
     }
     // 3. mid
-    BRN_CUDA_OK(cudaMemset2DAsync(ws.dW + L.ob1, L.ldw * sizeof(float), 0, (L.numel - L.ob1) * sizeof(float), S, stream));
+    if (!use_tc)
+        BRN_CUDA_OK(cudaMemset2DAsync(ws.dW + L.ob1, L.ldw * sizeof(float), 0, (L.numel - L.ob1) * sizeof(float), S, stream));
     {
         StageTimer st("bnn.mid", stream);
         const float inv_S = 1.0f / (float)r->s_total;

@@ -416,7 +416,7 @@ struct SampleMulti {
 
 __global__ void __launch_bounds__(256)
 sample_multi_kernel(SampleMulti m, int64_t total, float* __restrict__ eps_out, float* __restrict__ W, int64_t ld,
-                    brn_sample_range r) {
+                    brn_sample_range r, float* __restrict__ grad_zero) {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int s = blockIdx.y;
     if (g >= total) return;
@@ -437,10 +437,11 @@ sample_multi_kernel(SampleMulti m, int64_t total, float* __restrict__ eps_out, f
     const int64_t o = (int64_t)s * ld + m.off[k] + i;
     eps_out[o] = e;
     W[o] = __fmaf_rn(softplusf(m.rho[k][i]), e, m.mu[k][i]);
+    if (grad_zero) grad_zero[o] = 0.f;        // per-sample gradient slot of the same element (accumulated into later): saves a memset node
 }
 
 int launch_sample_multi(const brn_mf_var* vars, const int64_t* offs, int nvars, float* eps_out, float* W, int64_t ld,
-                        const brn_sample_range& r, cudaStream_t stream) {
+                        const brn_sample_range& r, cudaStream_t stream, float* grad_zero) {
     if (nvars <= 0 || nvars > 4) { set_error("launch_sample_multi: bad variable count %d", nvars); return -1; }
     SampleMulti m;
     m.n = nvars;
@@ -453,7 +454,7 @@ int launch_sample_multi(const brn_mf_var* vars, const int64_t* offs, int nvars, 
     }
     if (total <= 0 || r.s_local <= 0) return 0;
     dim3 grid((unsigned)((total + 255) / 256), (unsigned)r.s_local);
-    sample_multi_kernel<<<grid, 256, 0, stream>>>(m, total, eps_out, W, ld, r);
+    sample_multi_kernel<<<grid, 256, 0, stream>>>(m, total, eps_out, W, ld, r, grad_zero);
     BRN_LAUNCH_OK("sample_multi_kernel");
     return 0;
 }

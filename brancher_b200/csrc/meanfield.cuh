@@ -36,6 +36,6 @@ int launch_mf_reduce_finalize_multi(const brn_mf_var* vars, const int64_t* offs,
 
 // eps (injected var.eps or Philox) -> eps_out[s*ld + offs[k] + i], W[...] = mu + softplus(rho)*eps for up to 4 variables
 int launch_sample_multi(const brn_mf_var* vars, const int64_t* offs, int nvars, float* eps_out, float* W, int64_t ld,
-                        const brn_sample_range& r, cudaStream_t stream);
+                        const brn_sample_range& r, cudaStream_t stream, float* grad_zero = nullptr);
 
 }  // namespace brn
