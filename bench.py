@@ -529,8 +529,8 @@ def main_ours(args):
     ms, launches, _ = timed(step, args.steps, args.warmup, profile=False)
     ms_prof, _, stages = timed(step, args.steps, 1, profile=True)
     clk = clocks.stop()
-    ms_e2e, _, _ = timed(lambda i: e2e_step(i), max(3, min(args.steps, 10)), 3)
-    n_e2e = max(3, min(args.steps, 10))
+    ms_e2e, _, _ = timed(lambda i: e2e_step(i), max(3, min(args.steps, 50)), 3)
+    n_e2e = max(3, min(args.steps, 50))
 
     if rank == 0:
         units = units_per_rank * world
