@@ -98,10 +98,6 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
     constexpr int UG_STAGES = SM::STAGES, UG_BK = BK, SW = BK * 4;
     constexpr bool SPLIT_A = (SPLIT & 1) != 0, SPLIT_B = (SPLIT & 2) != 0;
     constexpr int UG_CONV_WARPS = CW;
-    // TIMING EXPERIMENT ONLY (BRN_UMMA_SKIP_BLO=1, wrong results): the producer does not load the B_lo tile, i.e. 32 % fewer
-    // bytes per K chunk through L2 with the MMA work unchanged -- tells whether the kernel is paced by its operand feed.
-    const bool skip_blo = (mode & 0x100) != 0;
-    mode &= 0xff;
     constexpr int CPT = BN / (EW / 4);             // accumulator columns per epilogue thread
     static_assert(EW == 8 || EW == 16, "8 or 16 epilogue warps");
     static_assert(BN <= UG_BUF_COLS && BN % 16 == 0 && CPT % 8 == 0, "unsupported N tile");
@@ -139,13 +135,13 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
                 for (int kc = kcb; kc < kce; ++kc) {
                     umma::mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* st = smem + stage * SM::STAGE_BYTES;
-                    umma::mbar_arrive_expect_tx(&full_bar[stage], SM::STAGE_BYTES - ((skip_blo || SPLIT_B) ? SM::B_BYTES : 0) -
+                    umma::mbar_arrive_expect_tx(&full_bar[stage], SM::STAGE_BYTES - (SPLIT_B ? SM::B_BYTES : 0) -
                                                                       (SPLIT_A ? SM::A_BYTES : 0));
                     const int k0 = kc * UG_BK;
                     umma::tma_load_2d(st, &tmAh, &full_bar[stage], k0, m0);
                     if (!SPLIT_A) umma::tma_load_2d(st + SM::A_BYTES, &tmAl, &full_bar[stage], k0, m0);
                     umma::tma_load_2d(st + 2 * SM::A_BYTES, &tmBh, &full_bar[stage], k0, n0);
-                    if (!skip_blo && !SPLIT_B)
+                    if (!SPLIT_B)
                         umma::tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES, &tmBl, &full_bar[stage], k0, n0);
                     if (++stage == UG_STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -455,7 +451,6 @@ inline int launch_umma_nt(const float* Ah, const float* Al, int M, int64_t lda, 
         grid = G * m_tiles;
     }
     if (drain_chunks < 1) drain_chunks = 2 * 32 / BK;
-    if (const char* env = getenv("BRN_UMMA_SKIP_BLO")) mode |= atoi(env) ? 0x100 : 0;
     auto kern = umma_nt_3xtf32_kernel<BN, BK, Epi, EW, SPLIT, CW>;
     const int smem = UmmaSmem<BN, BK>::TOTAL;
     BRN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
