@@ -140,3 +140,24 @@ def test_wvgd_lowering_and_no_cpu_fallback():
         lowering.get_wvgd_plan(model, particles, samplers[:2])
     with pytest.raises(NotImplementedError):
         ns.inference.WassersteinVariationalGradientDescent(samplers, particles, cost_function=lambda a, b: 0)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) prints exactly ONE JSON line on stdout with the
+    keys the measurement contract names -- runs on CPU, bounded sample."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--workload", "ar1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["n_gpus"] == 1
+    for k in ("metric", "value", "unit", "steps", "warmup", "ms_per_step", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
