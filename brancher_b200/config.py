@@ -33,6 +33,17 @@ def set_seed(value):
     global seed, _iteration
     seed = int(value)
     _iteration = 0
+    global _minibatch_draws
+    _minibatch_draws = 0
+
+
+_minibatch_draws = 0     # Philox offset of the device-side minibatch sampler: bumped once per index set
+
+
+def next_minibatch_offset():
+    global _minibatch_draws
+    _minibatch_draws += 1
+    return _minibatch_draws
 
 
 def next_offset():

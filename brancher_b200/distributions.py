@@ -121,6 +121,17 @@ class EmpiricalDistribution(Distribution):
                 size = len(dataset)
             if size < self.batch_size:
                 raise ValueError("It is impossible to have more samples than the size of the dataset without replacement")
+            if (p is None and is_tensor(dataset) and dataset.is_cuda and 2 * self.batch_size <= size and self.batch_size <= 8192):
+                # device-side sampling (brn_minibatch_indices): the reference permutes all `size` row ids on the HOST for every
+                # iteration (np.random.choice(range(N), B, replace=False): ~140 ms at N = 10^6); here the
+                # distinct row ids are drawn by one small kernel and never leave the GPU.  Independent Philox stream per
+                # draw (config.seed, config.next_minibatch_offset()); same distribution, different RNG than numpy's.
+                from brancher_b200 import _cuda as cu
+                draw_dev = lambda: cu.minibatch_indices(size, self.batch_size, dataset.device, seed=config.seed,
+                                                        offset=config.next_minibatch_offset())
+                # one independent index set per leading (MC-sample) row of the dataset, as the reference draws them
+                rows = [dataset[n].index_select(0 if self.is_observed else 1, draw_dev()) for n in range(dataset.shape[0])]
+                return torch.stack(rows, dim=0)
             draw = lambda: np.random.choice(size, size=self.batch_size, replace=False, p=p)
             indices = draw() if is_discrete(dataset) else [draw() for _ in range(dataset.shape[0])]
         if not is_tensor(dataset):

@@ -160,6 +160,13 @@ int brn_dag_elbo_fwd_bwd(const brn_dag_op* ops, int n_ops, int n_slots, const fl
                          const float* data, int n_cols, int n_rows, const float* eps, int n_eps,
                          const brn_sample_range* r, float* dparams, double* loss, void* stream);
 
+/* Minibatch row indices drawn on the device, uniformly WITHOUT replacement: out [B] int64 holds B distinct values of
+ * [0, N) in random order, a pure function of (N, B, seed, offset) (Philox4x32-10; duplicates are resolved by sequential-
+ * rejection priority, see csrc/minibatch.cu).  Replaces np.random.choice(range(N), B, replace=False) of
+ * EmpiricalDistribution._get_sample (distributions.py:410-462).  Requires B <= min(N / 2, 8192).
+ * rounds (optional, device int): number of rejection rounds taken. */
+int brn_minibatch_indices(int64_t N, int B, uint64_t seed, uint64_t offset, int64_t* out, int* rounds, void* stream);
+
 /* K4 -- Stein variational gradient descent (SVGD).
  * (a) per-particle loss and gradient for (multi-class) logistic-regression particles theta [n, C*F]:
  *       loss += sum_k [ -sum_rows log-lik(theta_k) - sum log N(theta_k; prior_loc, prior_scale) ]     (prior optional)
