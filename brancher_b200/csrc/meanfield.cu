@@ -170,13 +170,52 @@ int launch_reduce_over_samples(const float* dW, int64_t ld, const float* eps, in
 // walks samples y, y+8, ...; the 8 partial sums per element are combined in shared memory and STORED -- each element is owned
 // by exactly one CTA, so there are neither atomics nor a zeroing pass.  (The first version split the sample axis over
 // the grid and issued 16 global atomics per thread: 5.1 M atomics per C3 evaluation, 53 us for 160 MB.)
+struct MfMulti {
+    brn_mf_var v[4];
+    int64_t off[4];
+    int n;
+};
+
+// closed-form prior / entropy terms and the chain rule to (mu, rho) for one element, given its sample-axis statistics;
+// returns the element's ELBO contribution (prior + entropy), accumulates -d ELBO / d param into the gradient sinks
+__device__ __forceinline__ double mf_finalize_element(const brn_mf_var& v, int64_t i, float gw, float gwe, float e1, float e2,
+                                                      const brn_sample_range& r, int with_prior) {
+    const float mu = v.mu[i], rho = v.rho[i], sg = softplusf(rho);
+    const float inv_S = 1.0f / (float)r.s_total, n = (float)r.s_local, frac = n * inv_S;
+    float dE_dmu = gw * inv_S, dE_dsg = gwe * inv_S;
+    double elbo = 0.0;
+    if (with_prior) {
+        const float log_sg = logf(sg);
+        const float entropy = 0.5f + BRN_HALF_LOG_2PI + log_sg;
+        if (v.tied) {
+            elbo = (double)(-0.5f * e2 * inv_S) + (double)(frac * (entropy - log_sg - BRN_HALF_LOG_2PI));
+        } else {
+            const float a = v.prior_loc[i], b = v.prior_scale[i], inv_b2 = 1.0f / (b * b);
+            const float c0 = mu - a;
+            const float sd2 = n * c0 * c0 + 2.f * c0 * sg * e1 + sg * sg * e2;
+            const float sd = n * c0 + sg * e1;
+            const float sde = c0 * e1 + sg * e2;
+            elbo = (double)(-0.5f * sd2 * inv_b2 * inv_S) + (double)(frac * (entropy - logf(b) - BRN_HALF_LOG_2PI));
+            dE_dmu += -sd * inv_b2 * inv_S;
+            dE_dsg += -sde * inv_b2 * inv_S + frac / sg;
+        }
+    }
+    v.dmu[i] += -dE_dmu;
+    v.drho[i] += -dE_dsg * sigmoidf(rho);
+    return elbo;
+}
+
 constexpr int MF_QUADS = 32, MF_SGROUPS = 8;
 
+// FUSE: the owning CTA also finalises its 128 elements (several variables back to back, MfMulti) instead of storing the
+// statistics for a second kernel: one launch and one dependent-launch gap less per evaluation.
+template <bool FUSE>
 __global__ void __launch_bounds__(MF_QUADS * MF_SGROUPS)
 mf_stats_kernel(const float* __restrict__ eps, int64_t lde, const float* __restrict__ dW, int64_t ldd, int64_t numel,
                 int64_t npad, brn_sample_range r, uint32_t var_id, int vec, int64_t philox_quads,
-                float* __restrict__ stats) {
+                float* __restrict__ stats, MfMulti m, int with_prior, double* __restrict__ loss) {
     __shared__ float4 part[4][MF_SGROUPS][MF_QUADS];
+    __shared__ double red[32];
     const int tx = threadIdx.x & (MF_QUADS - 1), ty = threadIdx.x / MF_QUADS;
     const int64_t q = (int64_t)blockIdx.x * MF_QUADS + tx;
     const bool live = q * 4 < numel;
@@ -254,6 +293,30 @@ mf_stats_kernel(const float* __restrict__ eps, int64_t lde, const float* __restr
     part[2][ty][tx] = make_float4(e1[0], e1[1], e1[2], e1[3]);
     part[3][ty][tx] = make_float4(e2[0], e2[1], e2[2], e2[3]);
     __syncthreads();
+    if constexpr (FUSE) {
+        double elbo = 0.0;
+        const int el = threadIdx.x;
+        const int64_t g = (int64_t)blockIdx.x * MF_QUADS * 4 + el;
+        if (el < MF_QUADS * 4 && g < numel) {
+            float st4[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float acc = 0.f;
+#pragma unroll
+                for (int y = 0; y < MF_SGROUPS; ++y) acc += reinterpret_cast<const float*>(&part[k][y][el >> 2])[el & 3];
+                st4[k] = acc;
+            }
+            int k = 0;
+#pragma unroll
+            for (int j = 1; j < 4; ++j)
+                if (j < m.n && g >= m.off[j]) k = j;
+            const int64_t i = g - m.off[k];
+            if (i < m.v[k].numel) elbo = mf_finalize_element(m.v[k], i, dW ? st4[0] : 0.f, dW ? st4[1] : 0.f, st4[2], st4[3], r, with_prior);
+        }
+        const double tot = block_sum<double>(elbo, red);
+        if (threadIdx.x == 0 && with_prior) atomicAdd(loss, -tot);
+        return;
+    }
     // 4 statistics x 128 elements per CTA: thread t sums the 8 group partials of (statistic t / 128, element t % 128)
     for (int t = threadIdx.x; t < 4 * MF_QUADS * 4; t += MF_QUADS * MF_SGROUPS) {
         const int k = t / (MF_QUADS * 4), el = t % (MF_QUADS * 4);
@@ -315,7 +378,8 @@ int launch_mf_reduce_finalize(const brn_mf_var& var, const float* eps, int64_t l
         const int vec = (!eps || (((uintptr_t)eps % 16 == 0) && lde % 4 == 0)) &&
                         (!dW || (((uintptr_t)dW % 16 == 0) && ldd % 4 == 0));
         const unsigned grid = (unsigned)((quads + MF_QUADS - 1) / MF_QUADS);
-        mf_stats_kernel<<<grid, MF_QUADS * MF_SGROUPS, 0, stream>>>(eps, lde, dW, ldd, var.numel, npad, r, var.var_id, vec, 0, stats);
+        mf_stats_kernel<false><<<grid, MF_QUADS * MF_SGROUPS, 0, stream>>>(eps, lde, dW, ldd, var.numel, npad, r, var.var_id, vec, 0, stats,
+                                                                           MfMulti(), 0, nullptr);
         BRN_LAUNCH_OK("mf_stats_kernel");
     }
     mf_finalize2_kernel<<<(unsigned)((var.numel + 255) / 256), 256, 0, stream>>>(var, stats, npad, r, with_prior, loss);
@@ -327,11 +391,6 @@ int launch_mf_reduce_finalize(const brn_mf_var& var, const float* eps, int64_t l
 // stage 5 for several variables laid out back to back in one [S][ld] block (the BNN workspace): ONE stats launch
 // over the concatenated element range and ONE finalize launch that looks the variable up per element.
 // ---------------------------------------------------------------------------------------------
-struct MfMulti {
-    brn_mf_var v[4];
-    int64_t off[4];
-    int n;
-};
 
 __global__ void __launch_bounds__(256)
 mf_finalize_multi_kernel(MfMulti m, const float* __restrict__ stats, int64_t npad, int64_t total, brn_sample_range r,
@@ -386,20 +445,23 @@ int launch_mf_reduce_finalize_multi(const brn_mf_var* vars, const int64_t* offs,
     }
     if (nvars <= 0 || nvars > 4 || total <= 0) { set_error("launch_mf_reduce_finalize_multi: bad variable count %d", nvars); return -1; }
     const int64_t npad = (total + 3) / 4 * 4;
-    if (r.s_local <= 0 || !dW) BRN_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(float) * 4 * npad, stream));
-    if (r.s_local > 0) {
-        const int64_t quads = npad / 4;
-        const int vec = (((uintptr_t)eps % 16 == 0) && lde % 4 == 0) && (!dW || (((uintptr_t)dW % 16 == 0) && ldd % 4 == 0));
-        const unsigned grid = (unsigned)((quads + MF_QUADS - 1) / MF_QUADS);
-        mf_stats_kernel<<<grid, MF_QUADS * MF_SGROUPS, 0, stream>>>(eps, lde, dW, ldd, total, npad, r, vars[0].var_id, vec, philox_numel0 / 4, stats);
-        BRN_LAUNCH_OK("mf_stats_kernel");
-    }
     MfMulti m;
     m.n = nvars;
     for (int k = 0; k < 4; ++k) {
         m.v[k] = vars[k < nvars ? k : nvars - 1];
         m.off[k] = offs[k < nvars ? k : nvars - 1];
     }
+    if (r.s_local > 0) {
+        // statistics + finalisation in ONE launch: every element is owned by exactly one CTA
+        const int64_t quads = npad / 4;
+        const int vec = (((uintptr_t)eps % 16 == 0) && lde % 4 == 0) && (!dW || (((uintptr_t)dW % 16 == 0) && ldd % 4 == 0));
+        const unsigned grid = (unsigned)((quads + MF_QUADS - 1) / MF_QUADS);
+        mf_stats_kernel<true><<<grid, MF_QUADS * MF_SGROUPS, 0, stream>>>(eps, lde, dW, ldd, total, npad, r, vars[0].var_id, vec,
+                                                                          philox_numel0 / 4, stats, m, with_prior, loss);
+        BRN_LAUNCH_OK("mf_stats_kernel");
+        return 0;
+    }
+    BRN_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(float) * 4 * npad, stream));
     mf_finalize_multi_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(m, stats, npad, total, r, with_prior, loss);
     BRN_LAUNCH_OK("mf_finalize_multi_kernel");
     return 0;
