@@ -320,7 +320,8 @@ _DAG_UNIFORM_HEADER, _DAG_LEVEL = 26, 27                                  # layo
 _DAG_BINARY = {"add": "ADD", "sub": "SUB", "mul": "MUL", "truediv": "DIV"}
 _DAG_UNARY = {"exp": "EXP", "log": "LOG", "log1p": "LOG1P", "sigmoid": "SIGMOID", "softplus": "SOFTPLUS", "tanh": "TANH",
               "sin": "SIN", "cos": "COS", "relu": "RELU", "sqrt": "SQRT", "abs": "ABS", "neg": "NEG"}
-_DAG_LOC_SCALE = ("normal", "lognormal", "logitnormal")
+_DAG_LOC_SCALE = ("normal", "lognormal", "logitnormal")      # kinds a q variable may have (pathwise sample from one normal draw)
+_DAG_LOC_SCALE_P = _DAG_LOC_SCALE + ("cauchy", "laplace")     # kinds of the joint model's nodes (log-probability only)
 DAG_MAX_SLOTS, DAG_MAX_PARAMS = 2048, 2048
 
 
@@ -477,7 +478,7 @@ class DagPlan(Plan):
             if not isinstance(v, RandomVariable) or v.distribution.kind in ("deterministic", "empirical"):
                 continue
             kind = v.distribution.kind
-            if kind not in _DAG_LOC_SCALE:
+            if kind not in _DAG_LOC_SCALE_P:
                 raise UnsupportedModelError("scalar-DAG family: distribution %r of %r is not lowered" % (kind, v.name))
             x = self.p_value(v)
             loc = self.compile(v.partial_links["loc"].expr, self.p_value)
@@ -598,6 +599,13 @@ class DagPlan(Plan):
         if kind == "lognormal":
             lx = P.emit("LOG", a=x)                                   # ExpTransform: inv = log y, log|det J| = x
             return P.emit("SUB", a=P.emit("NORMAL_LP", a=lx, b=loc, c=scale), b=lx)
+        if kind == "cauchy":            # torch Cauchy.log_prob: -log(pi) - log(scale) - log1p(((x - loc) / scale)^2)
+            zz = P.emit("DIV", a=P.emit("SUB", a=x, b=loc), b=scale)
+            t = P.emit("SUB", a=P.const(-float(np.log(np.pi))), b=P.emit("LOG", a=scale))
+            return P.emit("SUB", a=t, b=P.emit("LOG1P", a=P.emit("MUL", a=zz, b=zz)))
+        if kind == "laplace":           # torch Laplace.log_prob: -log(2 scale) - |x - loc| / scale
+            t = P.emit("NEG", a=P.emit("LOG", a=P.emit("MUL", a=P.const(2.0), b=scale)))
+            return P.emit("SUB", a=t, b=P.emit("DIV", a=P.emit("ABS", a=P.emit("SUB", a=x, b=loc)), b=scale))
         yc = P.emit("CLAMP_UNIT", a=x)                                # SigmoidTransform._inverse: clamp, log y - log1p(-y)
         u = P.emit("SUB", a=P.emit("LOG", a=yc), b=P.emit("LOG1P", a=P.emit("NEG", a=yc)))
         ladj = P.emit("SUB", a=P.emit("NEG", a=P.emit("SOFTPLUS", a=P.emit("NEG", a=u))), b=P.emit("SOFTPLUS", a=u))

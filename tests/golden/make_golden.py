@@ -260,6 +260,9 @@ if __name__ == "__main__":
         wvgd(21, B=30, F=4, C=3, n=3, S=20, tag="wvgd_softmax")
         wvgd(22, B=16, F=5, C=2, n=4, S=24, tag="wvgd_softmax4")
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "robust":
+        scalar_model(zoo.robust_regression, "robust_regression", S=16, transforms={"nu": torch.exp}, seed=14, n=40)
+        sys.exit(0)
     torch.manual_seed(0)
     bnn(1, B=12, P=20, H=7, C=4, S=6, tag="bnn_small")
     bnn(2, B=9, P=16, H=5, C=3, S=5, q_sigma=0.3, q_mu_scale=0.5, tag="bnn_small_wide")
@@ -270,6 +273,7 @@ if __name__ == "__main__":
     svgd(7, n=7, d=5, tag="svgd_small")
     scalar_model(zoo.lognormal_normal, "lognormal_normal", S=24, transforms={"nu": torch.exp}, seed=10, N=20)
     scalar_model(zoo.multivariate_regression, "multivariate_regression", S=16, transforms={"nu": torch.exp}, seed=11, n=50)
+    scalar_model(zoo.robust_regression, "robust_regression", S=16, transforms={"nu": torch.exp}, seed=14, n=40)
     svgd_model(8, B=30, F=5, C=3, n=6, tag="svgd_softmax")
     vae(12, B=6, D=12, L=2, h_enc=(5, 7), h_dec=(7, 5), S=3, tag="vae_small")
     vae(13, B=10, D=20, L=3, h_enc=(9,), h_dec=(6, 8, 5), S=4, tag="vae_deep")

@@ -20,6 +20,7 @@ def namespace(pkg):
         NormalVariable=SV.NormalVariable, CategoricalVariable=SV.CategoricalVariable,
         BinomialVariable=SV.BinomialVariable, DeterministicVariable=SV.DeterministicVariable,
         LogNormalVariable=SV.LogNormalVariable, EmpiricalVariable=SV.EmpiricalVariable, RandomIndices=SV.RandomIndices,
+        CauchyVariable=SV.CauchyVariable, LaplaceVariable=SV.LaplaceVariable,
         LogitNormalVariable=getattr(SV, "LogitNormalVariable", None),
         BF=importlib.import_module(pkg + ".functions"), inference=importlib.import_module(pkg + ".inference"))
     return ns
@@ -138,6 +139,26 @@ def multivariate_regression(ns, seed, n):
     ydata = (0.3 + 0.8 * x1v - 0.5 * x2v + 0.2 * x1v * x2v + 0.4 * rng.randn(n)).astype("float32")
     y.observe(ydata.reshape(n, 1, 1))
     return model, Q, {"y": ydata, "x1": x1v.astype("float32"), "x2": x2v.astype("float32"), "rng": rng}
+
+
+def robust_regression(ns, seed, n):
+    """Heavy-tailed variant of examples/multivariate_regression.py: Laplace priors on the weights
+    (standard_variables.py:171-183), Cauchy likelihood (standard_variables.py:156-168), LogNormal noise scale; mean-field
+    Normal / LogNormal posterior."""
+    rng = np.random.RandomState(seed)
+    xv = np.linspace(-1., 1., n)
+    x = ns.DeterministicVariable(xv, name="x", is_observed=True)
+    b = ns.LaplaceVariable(0., 1., name="b")
+    w = ns.LaplaceVariable(0., 2., name="w")
+    nu = ns.LogNormalVariable(-1., 0.5, name="nu")
+    y = ns.CauchyVariable(b + w * x, nu, name="y")
+    model = ns.ProbabilisticModel([y])
+    Q = [ns.NormalVariable(0.2, 0.7, name="b", learnable=True), ns.NormalVariable(-0.1, 0.9, name="w", learnable=True),
+         ns.LogNormalVariable(-1., 0.5, name="nu", learnable=True)]
+    model.set_posterior_model(ns.ProbabilisticModel(Q))
+    ydata = (0.3 + 0.8 * xv + 0.3 * rng.standard_cauchy(n)).astype("float32")
+    y.observe(ydata.reshape(n, 1, 1))
+    return model, Q, {"y": ydata, "x": xv.astype("float32"), "rng": rng}
 
 
 def ar1(ns, seed, T):

@@ -13,6 +13,7 @@ CASES = {
     "ar1_readme": (zoo.ar1, dict(seed=6, T=20)),
     "lognormal_normal": (zoo.lognormal_normal, dict(seed=10, N=20)),
     "multivariate_regression": (zoo.multivariate_regression, dict(seed=11, n=50)),
+    "robust_regression": (zoo.robust_regression, dict(seed=14, n=40)),        # Laplace priors, Cauchy likelihood
 }
 
 
