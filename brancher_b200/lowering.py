@@ -478,12 +478,15 @@ class DagPlan(Plan):
             if not isinstance(v, RandomVariable) or v.distribution.kind in ("deterministic", "empirical"):
                 continue
             kind = v.distribution.kind
-            if kind not in _DAG_LOC_SCALE_P:
+            if kind in ("binomial", "bernoulli"):
+                lp = self.bernoulli_log_prob(v)
+            elif kind in _DAG_LOC_SCALE_P:
+                x = self.p_value(v)
+                loc = self.compile(v.partial_links["loc"].expr, self.p_value)
+                scale = self.compile(v.partial_links["scale"].expr, self.p_value)
+                lp = self.log_prob(kind, x, loc, scale)
+            else:
                 raise UnsupportedModelError("scalar-DAG family: distribution %r of %r is not lowered" % (kind, v.name))
-            x = self.p_value(v)
-            loc = self.compile(v.partial_links["loc"].expr, self.p_value)
-            scale = self.compile(v.partial_links["scale"].expr, self.p_value)
-            lp = self.log_prob(kind, x, loc, scale)
             if P.rowdep[lp] and not v.is_observed:
                 raise UnsupportedModelError("scalar-DAG family: latent %r has a per-row log-probability (local latents are "
                                             "not lowered)" % v.name)
@@ -589,6 +592,28 @@ class DagPlan(Plan):
             if e.name in _DAG_UNARY and len(e.args) == 1:
                 return P.emit(_DAG_UNARY[e.name], a=self.compile(e.args[0], value_of))
         raise UnsupportedModelError("scalar-DAG family: link expression %s is not lowered" % getattr(e, "name", type(e).__name__))
+
+    def bernoulli_log_prob(self, v):
+        """Observed Bernoulli / Binomial(total_count = 1) node with a `logits` link, as torch evaluates it
+        (distributions.py:561-592; torch Binomial.log_prob with n = 1: the three lgamma terms vanish):
+            y l - (max(l, 0) + log1p(exp(-|l|)))."""
+        P = self.prog
+        links = v.partial_links
+        if not v.is_observed:
+            raise UnsupportedModelError("scalar-DAG family: discrete latent %r has no pathwise gradient (not lowered)" % v.name)
+        if "logits" not in links:
+            raise UnsupportedModelError("scalar-DAG family: %r must be parameterised by logits" % v.name)
+        if v.distribution.kind == "binomial":
+            n = _const_value(links["total_count"].expr)
+            if n is None:
+                root = _as_root(links["total_count"].expr)
+                n = float(root._value.reshape(-1)[0]) if root is not None and root._value.numel() == 1 else None
+            if n != 1.0:
+                raise UnsupportedModelError("scalar-DAG family: Binomial %r is lowered for total_count = 1 only" % v.name)
+        y = self.p_value(v)
+        l = self.compile(links["logits"].expr, self.p_value)
+        norm = P.emit("ADD", a=P.emit("RELU", a=l), b=P.emit("LOG1P", a=P.emit("EXP", a=P.emit("NEG", a=P.emit("ABS", a=l)))))
+        return P.emit("SUB", a=P.emit("MUL", a=y, b=l), b=norm)
 
     def log_prob(self, kind, x, loc, scale):
         """The op sequence torch evaluates: Normal.log_prob, and TransformedDistribution.log_prob =

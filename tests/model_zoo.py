@@ -161,6 +161,23 @@ def robust_regression(ns, seed, n):
     return model, Q, {"y": ydata, "x": xv.astype("float32"), "rng": rng}
 
 
+def scalar_logistic(ns, seed, n):
+    """One-feature Bayesian logistic regression written with scalar links (no matmul): Binomial(1, logits = w x + b) observed,
+    Normal priors and posterior -- the Bernoulli/Binomial node of distributions.py:561-592 in the scalar-DAG family."""
+    rng = np.random.RandomState(seed)
+    xv = np.linspace(-2., 2., n)
+    x = ns.DeterministicVariable(xv, name="x", is_observed=True)
+    w = ns.NormalVariable(0., 1., name="w")
+    b = ns.NormalVariable(0., 1., name="b")
+    k = ns.BinomialVariable(1, logits=w * x + b, name="k")
+    model = ns.ProbabilisticModel([k])
+    Q = [ns.NormalVariable(0.3, 0.6, name="w", learnable=True), ns.NormalVariable(-0.2, 0.8, name="b", learnable=True)]
+    model.set_posterior_model(ns.ProbabilisticModel(Q))
+    labels = (rng.rand(n) < 1.0 / (1.0 + np.exp(-(1.5 * xv - 0.3)))).astype("float32")
+    k.observe(labels.reshape(n, 1, 1))
+    return model, Q, {"k": labels, "x": xv.astype("float32"), "rng": rng}
+
+
 def ar1(ns, seed, T):
     """README.md:22-75 model, y0 named 'y0' (the README reuses 'x0')."""
     rng = np.random.RandomState(seed)

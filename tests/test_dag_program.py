@@ -14,6 +14,7 @@ CASES = {
     "lognormal_normal": (zoo.lognormal_normal, dict(seed=10, N=20)),
     "multivariate_regression": (zoo.multivariate_regression, dict(seed=11, n=50)),
     "robust_regression": (zoo.robust_regression, dict(seed=14, n=40)),        # Laplace priors, Cauchy likelihood
+    "scalar_logistic": (zoo.scalar_logistic, dict(seed=15, n=30)),            # observed Binomial(1, logits) node
 }
 
 
