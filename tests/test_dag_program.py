@@ -133,6 +133,22 @@ def test_unsupported_scalar_graphs_raise():
     model.set_posterior_model(ns.ProbabilisticModel([Qz]))
     with pytest.raises(lowering.UnsupportedModelError):
         lowering.get_plan(model, model.posterior_model)
+    # Binomial with total_count != 1 (needs lgamma terms) and a Cauchy q variable (needs a uniform noise stream): not lowered
+    x2 = ns.DeterministicVariable(np.linspace(-1, 1, 6), name="x", is_observed=True)
+    w = ns.NormalVariable(0., 1., "w")
+    k = ns.BinomialVariable(3, logits=w * x2, name="k")
+    m2 = ns.ProbabilisticModel([k])
+    k.observe(np.ones((6, 1, 1), "float32"))
+    m2.set_posterior_model(ns.ProbabilisticModel([ns.NormalVariable(0., 1., "w", learnable=True)]))
+    with pytest.raises(lowering.UnsupportedModelError):
+        lowering.get_plan(m2, m2.posterior_model)
+    w3 = ns.NormalVariable(0., 1., "w")
+    y3 = ns.NormalVariable(w3 * x2, 1., "y")
+    m3 = ns.ProbabilisticModel([y3])
+    y3.observe(np.zeros((6, 1, 1), "float32"))
+    m3.set_posterior_model(ns.ProbabilisticModel([ns.CauchyVariable(0., 1., "w", learnable=True)]))
+    with pytest.raises(lowering.UnsupportedModelError):
+        lowering.get_plan(m3, m3.posterior_model)
 
 
 @pytest.mark.gpu
