@@ -263,6 +263,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "robust":
         scalar_model(zoo.robust_regression, "robust_regression", S=16, transforms={"nu": torch.exp}, seed=14, n=40)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "op_zoo":
+        scalar_model(zoo.op_zoo, "op_zoo", S=12, transforms={"c": torch.exp}, seed=16, n=24)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "scalar_logistic":
         scalar_model(zoo.scalar_logistic, "scalar_logistic", S=20, transforms={}, seed=15, n=30)
         sys.exit(0)
@@ -278,6 +281,7 @@ if __name__ == "__main__":
     scalar_model(zoo.multivariate_regression, "multivariate_regression", S=16, transforms={"nu": torch.exp}, seed=11, n=50)
     scalar_model(zoo.robust_regression, "robust_regression", S=16, transforms={"nu": torch.exp}, seed=14, n=40)
     scalar_model(zoo.scalar_logistic, "scalar_logistic", S=20, transforms={}, seed=15, n=30)
+    scalar_model(zoo.op_zoo, "op_zoo", S=12, transforms={"c": torch.exp}, seed=16, n=24)
     svgd_model(8, B=30, F=5, C=3, n=6, tag="svgd_softmax")
     vae(12, B=6, D=12, L=2, h_enc=(5, 7), h_dec=(7, 5), S=3, tag="vae_small")
     vae(13, B=10, D=20, L=3, h_enc=(9,), h_dec=(6, 8, 5), S=4, tag="vae_deep")

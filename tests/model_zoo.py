@@ -178,6 +178,29 @@ def scalar_logistic(ns, seed, n):
     return model, Q, {"k": labels, "x": xv.astype("float32"), "rng": rng}
 
 
+def op_zoo(ns, seed, n):
+    """Regression whose mean exercises every unary / binary op of the scalar-DAG family that the example models do not
+    (sin, cos, tanh, relu, abs, sqrt, exp, log, log1p, sigmoid, softplus, pow, neg, div): functions.py:28-62 lifts each torch
+    function to a link, variables.py:246-295 the operators."""
+    rng = np.random.RandomState(seed)
+    xv = np.linspace(0.2, 2.0, n)
+    x = ns.DeterministicVariable(xv, name="x", is_observed=True)
+    a = ns.NormalVariable(0., 1., name="a")
+    b = ns.NormalVariable(0., 1., name="b")
+    c = ns.LogNormalVariable(0., 0.3, name="c")
+    BF = ns.BF
+    mean = (BF.sin(a * x) + BF.tanh(b) * BF.cos(x) + BF.relu(a - 0.1) - BF.abs(b) * 0.3 + BF.sqrt(c * x) + BF.exp(-c)
+            + a / (c + 1.0) + b ** 2 + BF.log1p(BF.exp(a)) * 0.1 + BF.sigmoid(b) + BF.softplus(a) * 0.2 + BF.log(c + 1.0))
+    y = ns.NormalVariable(mean, 0.5, name="y")
+    model = ns.ProbabilisticModel([y])
+    Q = [ns.NormalVariable(0.4, 0.5, name="a", learnable=True), ns.NormalVariable(-0.3, 0.6, name="b", learnable=True),
+         ns.LogNormalVariable(0.1, 0.3, name="c", learnable=True)]
+    model.set_posterior_model(ns.ProbabilisticModel(Q))
+    ydata = (1.0 + np.sin(0.5 * xv) + 0.5 * rng.randn(n)).astype("float32")
+    y.observe(ydata.reshape(n, 1, 1))
+    return model, Q, {"y": ydata, "x": xv.astype("float32"), "rng": rng}
+
+
 def ar1(ns, seed, T):
     """README.md:22-75 model, y0 named 'y0' (the README reuses 'x0')."""
     rng = np.random.RandomState(seed)

@@ -15,6 +15,7 @@ CASES = {
     "multivariate_regression": (zoo.multivariate_regression, dict(seed=11, n=50)),
     "robust_regression": (zoo.robust_regression, dict(seed=14, n=40)),        # Laplace priors, Cauchy likelihood
     "scalar_logistic": (zoo.scalar_logistic, dict(seed=15, n=30)),            # observed Binomial(1, logits) node
+    "op_zoo": (zoo.op_zoo, dict(seed=16, n=24)),                              # every unary / binary op of the family
 }
 
 
