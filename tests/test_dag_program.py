@@ -244,3 +244,29 @@ def test_dag_uniform_segment_matches_plain_program(name, S):
     assert_close(out[0][0], out[1][0], "%s S=%d loss: uniform segment vs plain" % (name, S), rtol=2e-6, atol=1e-6)
     assert_close(out[0][1], out[1][1], "%s S=%d grads: uniform segment vs plain" % (name, S), rtol=1e-5, atol=1e-6,
                  scale=float(np.abs(out[1][1]).max()))
+
+
+def test_bernoulli_node_lowers_like_binomial_one():
+    """BernulliVariable(logits=...) (distributions.py:578-592) and BinomialVariable(1, logits=...) (:561-575) have the same
+    log-probability: the scalar-DAG lowering must emit the same program for both (host logic, CPU)."""
+    from brancher_b200 import config, lowering
+    config.set_device("cpu")
+    ns = zoo.namespace("brancher_b200")
+    import importlib
+    SV = importlib.import_module("brancher_b200.standard_variables")
+
+    def build_with(make_k):
+        xv = np.linspace(-2., 2., 12)
+        x = ns.DeterministicVariable(xv, name="x", is_observed=True)
+        w = ns.NormalVariable(0., 1., name="w")
+        b = ns.NormalVariable(0., 1., name="b")
+        k = make_k(w * x + b)
+        model = ns.ProbabilisticModel([k])
+        model.set_posterior_model(ns.ProbabilisticModel([ns.NormalVariable(0.3, 0.6, name="w", learnable=True),
+                                                          ns.NormalVariable(-0.2, 0.8, name="b", learnable=True)]))
+        k.observe((xv > 0).astype("float32").reshape(12, 1, 1))
+        return lowering.get_plan(model, model.posterior_model).prog.ops
+
+    ops_bin = build_with(lambda l: ns.BinomialVariable(1, logits=l, name="k"))
+    ops_ber = build_with(lambda l: SV.BernulliVariable(logits=l, name="k"))
+    assert ops_bin == ops_ber and len(ops_bin) > 10
