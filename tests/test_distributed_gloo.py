@@ -66,3 +66,56 @@ def test_two_rank_sample_sharding_matches_single_process(tmp_path):
     assert abs(got["loss"].item() - want_loss) <= 1e-6 * abs(want_loss)      # hi/lo pair keeps ~fp64 through fp32 wire
     for g, k in zip(got["grads"], ["weights_loc", "weights_scale"]):
         np.testing.assert_allclose(g.numpy().reshape(-1), want_g[k].reshape(-1), rtol=1e-5, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------
+# C4: particles sharded over ranks -- each rank evaluates the loss gradients of ITS particles, all ranks all-gather theta
+# and G, and each computes its rows of the pairwise SVGD update from the gathered copies (bench.py's svgd
+# workload does exactly this with NCCL and the K4a / K4b kernels).
+# ---------------------------------------------------------------------------------------------------
+def _svgd_problem():
+    rng = np.random.RandomState(9)
+    N, F, C, n = 30, 5, 1, 6            # 3 particles per rank
+    X = rng.randn(N, F).astype("f4")
+    y = (rng.rand(N) < 0.5).astype("f4")
+    theta = (0.7 * rng.randn(n, C, F)).astype("f4")
+    prior = (np.zeros((C, F), "f4"), np.ones((C, F), "f4"))
+    return X, y, theta, prior
+
+
+def _svgd_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from brancher_b200 import distributed as D
+    from oracle import elbo_oracle as O
+    X, y, theta, prior = _svgd_problem()
+    n, d = theta.shape[0], theta.shape[1] * theta.shape[2]
+    p0, cnt = D.shard(n)
+    _, G_local = O.particles_loss_grad(X, y, theta[p0:p0 + cnt], prior, dtype=torch.float64, likelihood="binomial")
+    th_local = torch.tensor(theta[p0:p0 + cnt].reshape(cnt, d), dtype=torch.float64)
+    g_local = torch.tensor(G_local.reshape(cnt, d), dtype=torch.float64)
+    th_all, g_all = torch.empty((n, d), dtype=torch.float64), torch.empty((n, d), dtype=torch.float64)
+    dist.all_gather_into_tensor(th_all, th_local)
+    dist.all_gather_into_tensor(g_all, g_local)
+    full, bw = O.svgd_direction(th_all.numpy(), g_all.numpy())       # every rank: bandwidth from the gathered particles
+    mine = torch.tensor(full[p0:p0 + cnt])                            # ... and its own rows of the update
+    rows = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(rows, mine)
+    if rank == 0:
+        torch.save({"update": torch.cat(rows), "bw": bw}, out)
+    dist.destroy_process_group()
+
+
+def test_two_rank_particle_sharding_matches_single_process(tmp_path):
+    sys.path.insert(0, ROOT)
+    from oracle import elbo_oracle as O
+    out = str(tmp_path / "svgd.pt")
+    mp.spawn(_svgd_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)
+    X, y, theta, prior = _svgd_problem()
+    _, G = O.particles_loss_grad(X, y, theta, prior, dtype=torch.float64, likelihood="binomial")
+    n = theta.shape[0]
+    want, bw = O.svgd_direction(theta.reshape(n, -1), G.reshape(n, -1))
+    assert abs(got["bw"] - bw) <= 1e-12 * abs(bw)
+    np.testing.assert_allclose(got["update"].numpy(), want, rtol=1e-10, atol=1e-12)
