@@ -986,6 +986,114 @@ static int launch_mid4(const float* pre, const float* W, float* dW, const int32_
     return 0;
 }
 
+}  // namespace brn
+#include "bnn_fused.cuh"
+namespace brn {
+
+// Fused noise + weight sampling + TF32 split for layer 1 (P % 4 == 0), sample-group version: one thread = 4 consecutive
+// weights, walking SG consecutive samples.  sigma = softplus(rho) is evaluated once per thread (no separate pass), and the
+// sample-axis noise statistics the closed-form prior / entropy terms need,  e1 = sum_s eps,  e2 = sum_s eps^2,  are
+// accumulated in registers and added to e1/e2 [H*P] with one 16-byte RED each per thread -- the statistics stage no
+// longer has to re-read the noise.
+template <int SG>
+__global__ void __launch_bounds__(256)
+sample_w1_group_kernel(const float* __restrict__ mu, const float* __restrict__ rho, const float* __restrict__ eps_in,
+                       int64_t lde_in, float* __restrict__ eps_out, int64_t lde_out, float* __restrict__ hi,
+                       float* __restrict__ lo, int H, int P, int Hp, int64_t ldP, brn_sample_range r, uint32_t var_id,
+                       float* __restrict__ e1, float* __restrict__ e2) {
+    const int64_t qq = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (qq * 4 >= (int64_t)H * P) return;      // pad rows h in [H, Hp) are never written (their accumulator columns are masked)
+    const int h = (int)((qq * 4) / P), p = (int)((qq * 4) - (int64_t)h * P);
+    const int64_t i = (int64_t)h * P + p;
+    const float4 m = *reinterpret_cast<const float4*>(mu + i);
+    const float4 rh = *reinterpret_cast<const float4*>(rho + i);
+    const float4 sg = make_float4(softplusf(rh.x), softplusf(rh.y), softplusf(rh.z), softplusf(rh.w));
+    float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a1;
+    const int s_begin = blockIdx.y * SG, s_end = min(r.s_local, s_begin + SG);
+    const int64_t o0 = (int64_t)h * ldP + p;
+#pragma unroll 2
+    for (int s = s_begin; s < s_end; ++s) {
+        float4 e;
+        if (eps_in) {
+            e = *reinterpret_cast<const float4*>(eps_in + (int64_t)s * lde_in + i);
+        } else {
+            Normal4 n = philox_normal4(r.seed, r.offset, var_id, (uint32_t)(r.s0 + s), (uint32_t)(i >> 2));
+            e = make_float4(n.v[0], n.v[1], n.v[2], n.v[3]);
+        }
+        *reinterpret_cast<float4*>(eps_out + (int64_t)s * lde_out + i) = e;
+        float4 vh, vl;
+        umma::split_tf32(__fmaf_rn(sg.x, e.x, m.x), vh.x, vl.x);
+        umma::split_tf32(__fmaf_rn(sg.y, e.y, m.y), vh.y, vl.y);
+        umma::split_tf32(__fmaf_rn(sg.z, e.z, m.z), vh.z, vl.z);
+        umma::split_tf32(__fmaf_rn(sg.w, e.w, m.w), vh.w, vl.w);
+        const int64_t o = (int64_t)s * Hp * ldP + o0;
+        *reinterpret_cast<float4*>(hi + o) = vh;
+        *reinterpret_cast<float4*>(lo + o) = vl;
+        a1.x += e.x; a1.y += e.y; a1.z += e.z; a1.w += e.w;
+        a2.x = __fmaf_rn(e.x, e.x, a2.x); a2.y = __fmaf_rn(e.y, e.y, a2.y);
+        a2.z = __fmaf_rn(e.z, e.z, a2.z); a2.w = __fmaf_rn(e.w, e.w, a2.w);
+    }
+    red_add_v4(e1 + i, a1.x, a1.y, a1.z, a1.w);
+    red_add_v4(e2 + i, a2.x, a2.y, a2.z, a2.w);
+}
+
+// e1 = sum_s eps, e2 = sum_s eps^2 from stored noise (shapes the vectorised sampler does not cover)
+__global__ void __launch_bounds__(256)
+eps_stats_kernel(const float* __restrict__ eps, int64_t lde, int64_t numel, int S, float* __restrict__ e1, float* __restrict__ e2) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= numel) return;
+    float a1 = 0.f, a2 = 0.f;
+    for (int s = 0; s < S; ++s) {
+        const float e = eps[(int64_t)s * lde + i];
+        a1 += e;
+        a2 = __fmaf_rn(e, e, a2);
+    }
+    e1[i] += a1;
+    e2[i] += a2;
+}
+
+// layer-1 finalisation of the fused path: gwT / gweT [P][HP] (backward GEMM epilogue) + e1 / e2 [H*P] (sampler) ->
+// closed-form prior / entropy terms, chain rule to (mu, rho), loss.  One thread per weight, element order (h, p).
+__global__ void __launch_bounds__(256)
+bnn_w1_finalize_kernel(brn_mf_var v, const float* __restrict__ gwT, const float* __restrict__ gweT, int HP, int P,
+                       const float* __restrict__ e1, const float* __restrict__ e2, brn_sample_range r, int with_prior,
+                       double* __restrict__ loss) {
+    __shared__ double red[32];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double elbo = 0.0;
+    if (i < v.numel) {
+        const int h = (int)(i / P), p = (int)(i - (int64_t)h * P);
+        const int64_t o = (int64_t)p * HP + h;
+        elbo = mf_finalize_element(v, i, gwT[o], gweT[o], e1[i], e2[i], r, with_prior);
+    }
+    const double tot = block_sum<double>(elbo, red);
+    if (threadIdx.x == 0 && with_prior) atomicAdd(loss, -tot);
+}
+
+template <int HP, int BK>
+static int launch_fwd_mid(const float* Ah, const float* Al, int M, int64_t lda, const float* Bh, const float* Bl, int N, int64_t ldb,
+                          int K, int drain_chunks, const FwdMidParams& fp, cudaStream_t stream) {
+    constexpr int BN = 2 * HP;
+    CUtensorMap tAh, tAl, tBh, tBl;
+    if (int e = make_tmap_2d_f32(&tAh, Ah, M, K, lda, UG_BM, BK)) return e;
+    if (int e = make_tmap_2d_f32(&tAl, Al, M, K, lda, UG_BM, BK)) return e;
+    if (int e = make_tmap_2d_f32(&tBh, Bh, N, K, ldb, BN, BK)) return e;
+    if (int e = make_tmap_2d_f32(&tBl, Bl, N, K, ldb, BN, BK)) return e;
+    const int m_tiles = (M + UG_BM - 1) / UG_BM, n_tiles = (N + BN - 1) / BN, k_chunks = (K + BK - 1) / BK;
+    drain_chunks = drain_chunks * 32 / BK;
+    if (drain_chunks < 1) drain_chunks = 2 * 32 / BK;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int U = m_tiles * n_tiles, grid = U < sms ? U : sms;
+    auto kern = bnn_fwd_mid_kernel<HP, BK>;
+    const int smem = FwdMidSmem<HP, BK>::TOTAL;
+    BRN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid, FM_THREADS, smem, stream>>>(tAh, tAl, tBh, tBl, m_tiles, n_tiles, k_chunks, drain_chunks, fp);
+    BRN_LAUNCH_OK("bnn_fwd_mid_kernel");
+    return 0;
+}
+
 static size_t bnn_mid_smem(int R, int H, int C) {
     return sizeof(float) * ((size_t)R * (H + 1) + (size_t)C * H + H + C + (size_t)R * C);
 }
@@ -997,6 +1105,8 @@ constexpr int BNN_UMMA_NSAMP = 2;    // samples per MMA N tile (N = 208)
 struct BnnWorkspace {
     float *eps, *W, *dW, *pre, *stats, *sigma;
     float *Xh, *Xl, *Xth, *Xtl, *Wh, *Wl, *dph, *dpl;   // tcgen05 variant: TF32-split operands
+    float *gwT, *gweT, *e1, *e2;                        // fused path: sample-axis sums of layer 1 (one block, zeroed per call)
+    size_t fused_stat_floats;
     int64_t ldP, ldB;
     size_t bytes;
     BnnWorkspace(void* base, const BnnLayout& L, int S) {
@@ -1019,6 +1129,12 @@ struct BnnWorkspace {
         const size_t rowsW = (size_t)(S + BNN_UMMA_NSAMP) * BNN_UMMA_HP;
         Wh = take(rowsW * ldP); Wl = take(rowsW * ldP);
         dph = take(rowsW * ldB); dpl = take(rowsW * ldB);
+        const size_t gT = ((size_t)L.P * BNN_UMMA_HP + 63) / 64 * 64, ne = ((size_t)L.H * L.P + 63) / 64 * 64;
+        gwT = take(2 * gT + 2 * ne);                     // contiguous: [gwT | gweT | e1 | e2]
+        gweT = gwT ? gwT + gT : nullptr;
+        e1 = gwT ? gweT + gT : nullptr;
+        e2 = gwT ? e1 + ne : nullptr;
+        fused_stat_floats = 2 * gT + 2 * ne;
         bytes = off;
     }
 };
@@ -1072,6 +1188,77 @@ extern "C" int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int
     // 3.3 % faster than with 2 (profiles/r1g_*) and the whole K3 parity suite, incl. the full C3 shape, stays green.
     int drain = 4;
     if (const char* env = getenv("BRN_UMMA_DRAIN")) drain = atoi(env);
+
+    // ------------------------------------------------------------------------------------------------
+    // fused path (default for the tcgen05 variant; BRN_BNN_MID=4 / 3 select the staged pipelines below, kept for A/B
+    // measurements and tests): sampler (+ noise statistics) -> forward GEMM with the mid stage in its epilogue ->
+    // backward GEMM with the sample-axis reduction in its epilogue -> finalisation.  pre_s and dW1_s never reach HBM.
+    // ------------------------------------------------------------------------------------------------
+    int mid_sel = 5;
+    if (const char* env = getenv("BRN_BNN_MID")) mid_sel = atoi(env);
+    if (use_tc && mid_sel >= 5) {
+        const float inv_S = 1.0f / (float)r->s_total;
+        {
+            StageTimer st("bnn.sample_weights", stream);
+            BRN_CUDA_OK(cudaMemsetAsync(ws.gwT, 0, sizeof(float) * ws.fused_stat_floats, stream));
+            const bool fast = (P % 4 == 0) && ((uintptr_t)vars[0].mu % 16 == 0) && ((uintptr_t)vars[0].rho % 16 == 0) &&
+                              (!vars[0].eps || ((uintptr_t)vars[0].eps % 16 == 0));
+            if (fast) {
+                constexpr int SG = 8;
+                dim3 grid((unsigned)(((int64_t)H * P / 4 + 255) / 256), (unsigned)((S + SG - 1) / SG));
+                sample_w1_group_kernel<SG><<<grid, 256, 0, stream>>>(vars[0].mu, vars[0].rho, vars[0].eps, numels[0], ws.eps + offs[0],
+                                                                     L.ldw, ws.Wh, ws.Wl, H, P, HP, ws.ldP, *r, vars[0].var_id, ws.e1,
+                                                                     ws.e2);
+                BRN_LAUNCH_OK("sample_w1_group_kernel");
+            } else {
+                if (vars[0].eps)
+                    BRN_CUDA_OK(cudaMemcpy2DAsync(ws.eps + offs[0], L.ldw * sizeof(float), vars[0].eps, numels[0] * sizeof(float),
+                                                  numels[0] * sizeof(float), S, cudaMemcpyDeviceToDevice, stream));
+                else if (int e = launch_philox_fill(ws.eps + offs[0], L.ldw, numels[0], vars[0].var_id, *r, stream)) return e;
+                dim3 grid((P + 255) / 256, HP, S);
+                sample_w1_split_kernel<<<grid, 256, 0, stream>>>(vars[0].mu, vars[0].rho, ws.eps + offs[0], L.ldw, ws.Wh, ws.Wl, H, P,
+                                                                 HP, ws.ldP);
+                BRN_LAUNCH_OK("sample_w1_split_kernel");
+                eps_stats_kernel<<<(unsigned)((numels[0] + 255) / 256), 256, 0, stream>>>(ws.eps + offs[0], L.ldw, numels[0], S, ws.e1,
+                                                                                         ws.e2);
+                BRN_LAUNCH_OK("eps_stats_kernel");
+            }
+            if (S % NS) {   // the odd tail tile reads one more sample block: keep it finite
+                BRN_CUDA_OK(cudaMemsetAsync(ws.Wh + (size_t)S * HP * ws.ldP, 0, sizeof(float) * HP * ws.ldP, stream));
+                BRN_CUDA_OK(cudaMemsetAsync(ws.Wl + (size_t)S * HP * ws.ldP, 0, sizeof(float) * HP * ws.ldP, stream));
+                BRN_CUDA_OK(cudaMemsetAsync(ws.dph + (size_t)S * HP * ws.ldB, 0, sizeof(float) * HP * ws.ldB, stream));
+                BRN_CUDA_OK(cudaMemsetAsync(ws.dpl + (size_t)S * HP * ws.ldB, 0, sizeof(float) * HP * ws.ldB, stream));
+            }
+            // small variables: noise, sampled values, and zeroed per-sample gradient slots (accumulated into by the epilogue)
+            if (int e = launch_sample_multi(vars + 1, offs + 1, 3, ws.eps, ws.W, L.ldw, *r, stream, ws.dW)) return e;
+            if (int e = wait_data_ready(stream)) return e;
+            if (int e = launch_split_tf32(X, P, B, P, ws.Xh, ws.Xl, ws.ldP, ws.Xth, ws.Xtl, ws.ldB, stream)) return e;
+        }
+        {
+            StageTimer st("bnn.gemm_fwd", stream);      // forward GEMM + mid in its epilogue
+            FwdMidParams fp{ws.W, ws.dW, y, L, S, inv_S, loss, ws.dph, ws.dpl, ws.ldB};
+            if (int e = launch_fwd_mid<HP, BNN_UMMA_BK>(ws.Xh, ws.Xl, B, ws.ldP, ws.Wh, ws.Wl, S * HP, ws.ldP, P, drain, fp, stream))
+                return e;
+        }
+        {
+            StageTimer st("bnn.gemm_bwd", stream);      // dW1_s = dpre_s^T . X, folded over samples in the epilogue
+            EpiSampleReduce::Params ep{ws.gwT, ws.gweT, ws.eps + offs[0], L.ldw, P, H, HP, S};
+            if (int e = launch_umma_nt<BN, BNN_UMMA_BK, EpiSampleReduce>(ws.Xth, ws.Xtl, P, ws.ldB, ws.dph, ws.dpl, S * HP, ws.ldB, B, 0,
+                                                                         drain, ep, stream, true))
+                return e;
+        }
+        StageTimer st5("bnn.reduce_finalize", stream);
+        {
+            int64_t offs_small[3] = {0, offs[2] - offs[1], offs[3] - offs[1]};
+            if (int e = launch_mf_reduce_finalize_multi(vars + 1, offs_small, 3, L.numel - offs[1], ws.eps + offs[1], L.ldw,
+                                                        ws.dW + offs[1], L.ldw, ws.stats, *r, with_prior, loss, stream, 0))
+                return e;
+        }
+        bnn_w1_finalize_kernel<<<(unsigned)((numels[0] + 255) / 256), 256, 0, stream>>>(vars[0], ws.gwT, ws.gweT, HP, P, ws.e1, ws.e2,
+                                                                                       *r, with_prior, loss);
+        BRN_LAUNCH_OK("bnn_w1_finalize_kernel");
+        return 0;
+    }
 
     // 1. noise + weights.  Noise ends up in ws.eps [S][ldw] and all sampled weights in ws.W, the four variables back to
     //    back inside a row, so stage 5 is one launch over the concatenated range.  Optional (tcgen05 variant, Philox

@@ -176,35 +176,6 @@ struct MfMulti {
     int n;
 };
 
-// closed-form prior / entropy terms and the chain rule to (mu, rho) for one element, given its sample-axis statistics;
-// returns the element's ELBO contribution (prior + entropy), accumulates -d ELBO / d param into the gradient sinks
-__device__ __forceinline__ double mf_finalize_element(const brn_mf_var& v, int64_t i, float gw, float gwe, float e1, float e2,
-                                                      const brn_sample_range& r, int with_prior) {
-    const float mu = v.mu[i], rho = v.rho[i], sg = softplusf(rho);
-    const float inv_S = 1.0f / (float)r.s_total, n = (float)r.s_local, frac = n * inv_S;
-    float dE_dmu = gw * inv_S, dE_dsg = gwe * inv_S;
-    double elbo = 0.0;
-    if (with_prior) {
-        const float log_sg = logf(sg);
-        const float entropy = 0.5f + BRN_HALF_LOG_2PI + log_sg;
-        if (v.tied) {
-            elbo = (double)(-0.5f * e2 * inv_S) + (double)(frac * (entropy - log_sg - BRN_HALF_LOG_2PI));
-        } else {
-            const float a = v.prior_loc[i], b = v.prior_scale[i], inv_b2 = 1.0f / (b * b);
-            const float c0 = mu - a;
-            const float sd2 = n * c0 * c0 + 2.f * c0 * sg * e1 + sg * sg * e2;
-            const float sd = n * c0 + sg * e1;
-            const float sde = c0 * e1 + sg * e2;
-            elbo = (double)(-0.5f * sd2 * inv_b2 * inv_S) + (double)(frac * (entropy - logf(b) - BRN_HALF_LOG_2PI));
-            dE_dmu += -sd * inv_b2 * inv_S;
-            dE_dsg += -sde * inv_b2 * inv_S + frac / sg;
-        }
-    }
-    v.dmu[i] += -dE_dmu;
-    v.drho[i] += -dE_dsg * sigmoidf(rho);
-    return elbo;
-}
-
 constexpr int MF_QUADS = 32, MF_SGROUPS = 8;
 
 // FUSE: the owning CTA also finalises its 128 elements (several variables back to back, MfMulti) instead of storing the
