@@ -12,7 +12,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbrancher_cuda.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _lib = None
 
@@ -32,7 +32,8 @@ class MFVar(ctypes.Structure):
 class SampleRange(ctypes.Structure):
     """struct brn_sample_range"""
     _fields_ = [("s0", ctypes.c_int32), ("s_local", ctypes.c_int32), ("s_total", ctypes.c_int32),
-                ("_pad", ctypes.c_int32), ("seed", ctypes.c_uint64), ("offset", ctypes.c_uint64)]
+                ("_pad", ctypes.c_int32), ("seed", ctypes.c_uint64), ("offset", ctypes.c_uint64),
+                ("offset_dev", ctypes.c_void_p)]
 
 
 VAE_MAX_HIDDEN = 6
@@ -245,9 +246,15 @@ def flat_grad_views(numels, device):
     return flat, views
 
 
-def sample_range(s_total, s0=0, s_local=None, seed=0, offset=0):
+def sample_range(s_total, s0=0, s_local=None, seed=0, offset=0, offset_dev=None):
+    """offset_dev: optional int64 CUDA tensor (1 element) whose value is added to `offset` on the device when noise is drawn."""
     s_local = s_total - s0 if s_local is None else s_local
-    return SampleRange(int(s0), int(s_local), int(s_total), 0, int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1))
+    ptr = None
+    if offset_dev is not None:
+        if not (offset_dev.is_cuda and offset_dev.dtype == torch.int64 and offset_dev.numel() == 1):
+            raise BrancherCudaError("offset_dev must be a 1-element int64 CUDA tensor")
+        ptr = offset_dev.data_ptr()
+    return SampleRange(int(s0), int(s_local), int(s_total), 0, int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1), ptr)
 
 
 def _check_eps(v, r):

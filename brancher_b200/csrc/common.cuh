@@ -100,6 +100,12 @@ __device__ __forceinline__ Normal4 philox_normal4(uint64_t seed, uint64_t offset
     return n;
 }
 
+// counter word 3: the by-value offset plus, when given, an offset the device owns (brn_sample_range.offset_dev) -- lets a
+// CUDA-graph-captured iteration draw fresh noise on every replay without re-recording its kernel arguments
+__device__ __forceinline__ uint64_t philox_offset(const brn_sample_range& r) {
+    return r.offset + (r.offset_dev ? __ldg(reinterpret_cast<const unsigned long long*>(r.offset_dev)) : 0ull);
+}
+
 __device__ __forceinline__ float philox_normal1(uint64_t seed, uint64_t offset, uint32_t var_id, uint32_t s,
                                                 int64_t i) {
     Normal4 n = philox_normal4(seed, offset, var_id, s, (uint32_t)(i >> 2));

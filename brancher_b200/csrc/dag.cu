@@ -103,7 +103,7 @@ dag_elbo_kernel(const brn_dag_op* __restrict__ ops, int n_ops, int n_slots, cons
             case DAG_PARAM: x = params[o.a]; break;
             case DAG_DATA: x = data[(int64_t)b * n_cols + o.a]; break;
             case DAG_EPS:
-                x = eps ? eps[(int64_t)s * n_eps + o.a] : philox_normal1(r.seed, r.offset, (uint32_t)o.a, (uint32_t)(r.s0 + s), 0);
+                x = eps ? eps[(int64_t)s * n_eps + o.a] : philox_normal1(r.seed, philox_offset(r), (uint32_t)o.a, (uint32_t)(r.s0 + s), 0);
                 break;
             case DAG_ADD: x = va + vb; break;
             case DAG_SUB: x = va - vb; break;
@@ -216,7 +216,7 @@ dag_elbo_kernel(const brn_dag_op* __restrict__ ops, int n_ops, int n_slots, cons
 #pragma unroll 4
             for (int i = s_fwd; i < s_fwd + n_eps_ops; ++i) {
                 const Op o = decode(fetch(i));
-                V(o.dst) = eps ? eps[(int64_t)s * n_eps + o.a] : philox_normal1(r.seed, r.offset, (uint32_t)o.a, (uint32_t)(r.s0 + s), 0);
+                V(o.dst) = eps ? eps[(int64_t)s * n_eps + o.a] : philox_normal1(r.seed, philox_offset(r), (uint32_t)o.a, (uint32_t)(r.s0 + s), 0);
             }
             s_fwd += n_eps_ops;
 #pragma unroll 4

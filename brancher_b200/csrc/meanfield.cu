@@ -10,7 +10,7 @@ __global__ void philox_fill_kernel(float* __restrict__ out, int64_t ld, int64_t 
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int s = blockIdx.y;
     if (q * 4 >= numel) return;
-    Normal4 n = philox_normal4(r.seed, r.offset, var_id, (uint32_t)(r.s0 + s), (uint32_t)q);
+    Normal4 n = philox_normal4(r.seed, philox_offset(r), var_id, (uint32_t)(r.s0 + s), (uint32_t)q);
     float* o = out + (int64_t)s * ld + q * 4;
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -75,7 +75,7 @@ mf_finalize_kernel(brn_mf_var v, const float* __restrict__ eps, int64_t lde, con
 #pragma unroll
                     for (int j = 0; j < 4; ++j) e[j] = j < nvalid ? eps[(int64_t)s * lde + q * 4 + j] : 0.f;
                 } else {
-                    Normal4 n = philox_normal4(r.seed, r.offset, v.var_id, (uint32_t)(r.s0 + s), (uint32_t)q);
+                    Normal4 n = philox_normal4(r.seed, philox_offset(r), v.var_id, (uint32_t)(r.s0 + s), (uint32_t)q);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) e[j] = n.v[j];
                 }
@@ -237,7 +237,7 @@ mf_stats_kernel(const float* __restrict__ eps, int64_t lde, const float* __restr
                     for (int j = 0; j < 4; ++j) e[j] = j < nvalid ? eps[(int64_t)s * lde + q * 4 + j] : 0.f;
                 }
             } else {
-                Normal4 n = philox_normal4(r.seed, r.offset, var_id, (uint32_t)(r.s0 + s), (uint32_t)q);
+                Normal4 n = philox_normal4(r.seed, philox_offset(r), var_id, (uint32_t)(r.s0 + s), (uint32_t)q);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) e[j] = j < nvalid ? n.v[j] : 0.f;
             }
@@ -466,7 +466,7 @@ sample_multi_kernel(SampleMulti m, int64_t total, float* __restrict__ eps_out, f
     if (!found) return;
     const int64_t i = g - base;
     const float e = m.eps_in[k] ? m.eps_in[k][(int64_t)s * m.numel[k] + i]
-                                : philox_normal1(r.seed, r.offset, m.var_id[k], (uint32_t)(r.s0 + s), i);
+                                : philox_normal1(r.seed, philox_offset(r), m.var_id[k], (uint32_t)(r.s0 + s), i);
     const int64_t o = (int64_t)s * ld + m.off[k] + i;
     eps_out[o] = e;
     W[o] = __fmaf_rn(softplusf(m.rho[k][i]), e, m.mu[k][i]);

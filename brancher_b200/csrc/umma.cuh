@@ -113,6 +113,28 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, ui
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
         : "memory");
 }
+// kind::f16 with fp16 operands (a_format = b_format = 0), fp32 accumulate: K = 16 elements (32 bytes) per instruction, i.e.
+// the same descriptors / byte strides as tf32 at twice the MACs per instruction.
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+// KIND: 0 = tf32 operands (fp32 words), 1 = fp16 operands (two elements per 32-bit word)
+template <int KIND>
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    if (KIND == 0) mma_tf32_ss(d_tmem, a_desc, b_desc, idesc, accumulate);
+    else mma_f16_ss(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
+template <int KIND>
+__host__ __device__ constexpr uint32_t idesc_kind(int M, int N) { return KIND == 0 ? idesc_tf32(M, N) : idesc_f16(M, N); }
+
 // mbarrier arrives once all previously issued MMAs of this thread have completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
@@ -173,6 +195,9 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 // Host: encode a 2-D fp32 row-major tensor [rows][cols] (row stride ld elements) for TMA tiles of
 // box_rows x box_cols floats (box_cols = 32: 128-byte swizzle, 16: 64-byte swizzle) with zero OOB fill.
 int make_tmap_2d_f32(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                     uint32_t box_cols);
+// The same for a 2-D fp16 tensor: cols / ld in ELEMENTS, box_cols = 64 (128-byte swizzle) or 32 (64-byte swizzle) elements.
+int make_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                      uint32_t box_cols);
 
 }  // namespace brn

@@ -44,6 +44,29 @@ int make_tmap_2d_f32(CUtensorMap* out, const float* base, uint64_t rows, uint64_
     return 0;
 }
 
+int make_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                     uint32_t box_cols) {
+    auto fn = get_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return -4; }
+    if (((uintptr_t)base & 15) || (ld * 2) % 16) {
+        set_error("TMA operand must be 16-byte aligned with a 16-byte multiple row pitch (base=%p ld=%llu halves)", base,
+                  (unsigned long long)ld);
+        return -1;
+    }
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstr[1] = {ld * 2};
+    if (box_cols != 64 && box_cols != 32) { set_error("fp16 TMA box must be 64 or 32 elements wide (got %u)", box_cols); return -1; }
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (fp16) failed with CUresult %d (rows=%llu cols=%llu ld=%llu box=%u)",
+                                       (int)r, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
+        return -4; }
+    return 0;
+}
+
 // hi/lo split of src [rows][cols] (row pitch lds) into dst_hi/dst_lo [rows][ldd]; optionally also the
 // transposed pair [cols][ldt].  Pad columns (>= cols) are not touched (TMA never reads them: the tensor map's
 // extent is `cols`).
@@ -147,6 +170,13 @@ extern "C" int brn_gemm_nt_3xtf32(const float* A, const float* B, float* D, int 
     StageTimer st("gemm.umma", stream);
     if (const char* env = getenv("BRN_UMMA_BK"))
         if (atoi(env) == 32) return launch_umma_nt<224, 32, EpiStore>(Ah, Al, M, ld, Bh, Bl, N, ld, K, 0, drain, ep, stream);
+    if (bn == -208 || bn == -209) {
+        // MMA-rate measurements (profiles/gemm_bn_sweep.py): null epilogue; -209 issues the same byte streams as kind::f16
+        // (the fp32 words read as pairs of halves: numerically meaningless, but twice the MACs per instruction)
+        EpiNull::Params en{D};
+        if (bn == -208) return launch_umma_nt<208, 16, EpiNull>(Ah, Al, M, ld, Bh, Bl, N, ld, K, 0, drain, en, stream);
+        return launch_umma_nt_kind<208, 16, EpiNull, 8, 0, 4, 1>(Ah, Al, M, 2 * ld, Bh, Bl, N, 2 * ld, 2 * K, 0, drain, en, stream);
+    }
     if (bn == 208) return launch_umma_nt<208, 16, EpiStore>(Ah, Al, M, ld, Bh, Bl, N, ld, K, 0, drain, ep, stream);
     if (bn == 256) return launch_umma_nt<256, 16, EpiStore, 16>(Ah, Al, M, ld, Bh, Bl, N, ld, K, 0, drain, ep, stream);
     return launch_umma_nt<224, 16, EpiStore>(Ah, Al, M, ld, Bh, Bl, N, ld, K, 0, drain, ep, stream);

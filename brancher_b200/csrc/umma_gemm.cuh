@@ -88,7 +88,10 @@ struct UnitIter {
 // previous kernel and consumed once (K2: d = y - sigmoid(l)) then crosses HBM as 4 instead of 8 bytes per element.
 // SPLIT is a bit mask: 1 = the A operand, 2 = the B operand arrives plain (tensor map tmBh; tmBl unused).
 // CW = converter warps (2 keep a 16-epilogue-warp kernel at 640 threads = 96 registers per thread).
-template <int BN, int BK, class Epi, int EW = UG_EPI_WARPS, int SPLIT = 0, int CW = 4>
+// KIND: 0 = tf32 operands (fp32 words, 3xTF32), 1 = fp16 operands (hi / lo halves, "3xFP16": the same 11 + 11 mantissa bits
+// per operand as the TF32 pair at twice the MACs per instruction and half the operand bytes; the caller pre-scales the
+// operands by powers of two into the fp16 range and un-scales in the epilogue).  BK counts 32-bit words per chunk row.
+template <int BN, int BK, class Epi, int EW = UG_EPI_WARPS, int SPLIT = 0, int CW = 4, int KIND = 0>
 __global__ void __launch_bounds__(64 + 32 * EW + (SPLIT ? 32 * CW : 0), 1)
 umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                       const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
@@ -99,7 +102,9 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
     constexpr bool SPLIT_A = (SPLIT & 1) != 0, SPLIT_B = (SPLIT & 2) != 0;
     constexpr int UG_CONV_WARPS = CW;
     constexpr int CPT = BN / (EW / 4);             // accumulator columns per epilogue thread
-    static_assert(EW == 8 || EW == 16, "8 or 16 epilogue warps");
+    static_assert(EW == 4 || EW == 8 || EW == 16, "4, 8 or 16 epilogue warps");
+    static_assert(KIND == 0 || SPLIT == 0, "on-the-fly operand splitting exists for tf32 operands only");
+    constexpr int KE = KIND == 0 ? 1 : 2;          // operand elements per 32-bit word
     static_assert(BN <= UG_BUF_COLS && BN % 16 == 0 && CPT % 8 == 0, "unsupported N tile");
     constexpr uint32_t TMEM_COLS = 512;
     extern __shared__ uint8_t smem_raw[];
@@ -137,7 +142,7 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
                     uint8_t* st = smem + stage * SM::STAGE_BYTES;
                     umma::mbar_arrive_expect_tx(&full_bar[stage], SM::STAGE_BYTES - (SPLIT_B ? SM::B_BYTES : 0) -
                                                                       (SPLIT_A ? SM::A_BYTES : 0));
-                    const int k0 = kc * UG_BK;
+                    const int k0 = kc * UG_BK * KE;
                     umma::tma_load_2d(st, &tmAh, &full_bar[stage], k0, m0);
                     if (!SPLIT_A) umma::tma_load_2d(st + SM::A_BYTES, &tmAl, &full_bar[stage], k0, m0);
                     umma::tma_load_2d(st + 2 * SM::A_BYTES, &tmBh, &full_bar[stage], k0, n0);
@@ -150,7 +155,7 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = umma::idesc_tf32(UG_BM, BN);
+            constexpr uint32_t idesc = umma::idesc_kind<KIND>(UG_BM, BN);
             int stage = 0; uint32_t phase = 0, blk = 0;
             for (UnitIter it(m_tiles, n_tiles, k_chunks, mode, split_T, full_units); it.valid(); it.next()) {
                 const int kcb = it.kc_begin(), kce = it.kc_end();
@@ -170,9 +175,9 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
                             const uint32_t ko = ks * 32;           // 8 tf32 = 32 bytes along K inside the swizzle row
                             const uint64_t dah = umma::smem_desc_k<SW>(ah + ko), dal = umma::smem_desc_k<SW>(al + ko);
                             const uint64_t dbh = umma::smem_desc_k<SW>(bh + ko), dbl = umma::smem_desc_k<SW>(bl + ko);
-                            umma::mma_tf32_ss(d_tmem, dal, dbh, idesc, kc != kc0 || ks != 0);
-                            umma::mma_tf32_ss(d_tmem, dah, dbl, idesc, true);
-                            umma::mma_tf32_ss(d_tmem, dah, dbh, idesc, true);
+                            umma::mma_ss<KIND>(d_tmem, dal, dbh, idesc, kc != kc0 || ks != 0);
+                            umma::mma_ss<KIND>(d_tmem, dah, dbl, idesc, true);
+                            umma::mma_ss<KIND>(d_tmem, dah, dbh, idesc, true);
                         }
                         umma::mma_commit(&empty_bar[stage]);       // smem stage reusable once these MMAs retire
                         if (++stage == UG_STAGES) { stage = 0; phase ^= 1; }
@@ -274,16 +279,43 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
 //     out[blk * blk_stride + row * row_stride + col * col_stride]      col < valid(blk), row < rows
 // row_stride == 1 gives the transposed (coalesced across the warp) store both K3 GEMMs use.
 // ------------------------------------------------------------------------------------------------
+// epilogue policy for tile-shape measurements: drains the accumulators and writes nothing
+struct EpiNull {
+    struct Params { float* out; };
+    template <int CPT>
+    static __device__ __forceinline__ void finish(const Params& p, float (&r)[CPT], int row, int blk, bool, int) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) s += r[i];
+        if (s == 1.2345e-30f) p.out[0] = s;      // keeps the drain alive
+    }
+};
+
+// power of two s with m * s in [2^13, 2^14)  (m > 0; 1 for m == 0 or non-finite): the operand scaling of the fp16 kind
+__device__ __forceinline__ float p2_scale(float m) {
+    if (!(m > 0.f) || !(m < 3.0e38f)) return 1.f;
+    int e = (int)((__float_as_uint(m) >> 23) & 0xffu) - 127;
+    e = max(-100, min(100, e));
+    return __uint_as_float((uint32_t)(127 + 13 - e) << 23);
+}
+
 struct EpiStore {
     struct Params {
         float* out; int rows; int64_t row_stride, col_stride, blk_stride;
         int blk_valid;      // valid columns per block ...
         int col_limit;      // ... or, if > 0, total valid columns counted across consecutive blocks
         int total_blks;
+        // fp16 kind: the operands were scaled by p2_scale(*bound_a) and p2_scale(bound_b_mult * *bound_b) (device scalars)
+        const float* bound_a = nullptr; const float* bound_b = nullptr; float bound_b_mult = 1.f;
     };
     template <int CPT>
     static __device__ __forceinline__ void finish(const Params& p, float (&r)[CPT], int row, int blk, bool accumulate, int /*slice*/) {
         if (row >= p.rows || blk >= p.total_blks) return;
+        if (p.bound_a) {
+            const float inv = 1.f / (p2_scale(*p.bound_a) * p2_scale(p.bound_b_mult * *p.bound_b));
+#pragma unroll
+            for (int i = 0; i < CPT; ++i) r[i] *= inv;
+        }
         int valid = p.blk_valid;
         if (p.col_limit > 0) valid = min(CPT, p.col_limit - blk * CPT);
         float* o = p.out + (int64_t)blk * p.blk_stride + (int64_t)row * p.row_stride;
@@ -426,23 +458,28 @@ inline UmmaSplitPlan umma_plan(int M, int N, int K, int sms, bool allow_split) {
 // A (hi/lo) [M][K] pitch lda, B (hi/lo) [N][K] pitch ldb; mode 0: units n-major round-robin over CTAs,
 // mode 1: every CTA keeps one m-tile and strides over n-tiles.  allow_split: the caller has zeroed the output blocks of
 // n-tiles >= umma_plan(...).first_split_ntile (mode 0 only).
-template <int BN, int BK, class Epi, int EW = UG_EPI_WARPS, int SPLIT = 0, int CW = 4>
-inline int launch_umma_nt(const float* Ah, const float* Al, int M, int64_t lda, const float* Bh, const float* Bl, int N,
-                          int64_t ldb, int K, int mode, int drain_chunks, const typename Epi::Params& ep,
-                          cudaStream_t stream, bool allow_split = false) {
+template <int BN, int BK, class Epi, int EW = UG_EPI_WARPS, int SPLIT = 0, int CW = 4, int KIND = 0>
+inline int launch_umma_nt_kind(const void* Ah, const void* Al, int M, int64_t lda, const void* Bh, const void* Bl, int N,
+                               int64_t ldb, int K, int mode, int drain_chunks, const typename Epi::Params& ep,
+                               cudaStream_t stream, bool allow_split = false) {
+    constexpr int KE = KIND == 0 ? 1 : 2;
     CUtensorMap tAh, tAl, tBh, tBl;
-    if (int e = make_tmap_2d_f32(&tAh, Ah, M, K, lda, UG_BM, BK)) return e;
-    if (int e = make_tmap_2d_f32(&tAl, (SPLIT & 1) ? Ah : Al, M, K, lda, UG_BM, BK)) return e;      // SPLIT & 1: unused
-    if (int e = make_tmap_2d_f32(&tBh, Bh, N, K, ldb, BN, BK)) return e;
-    if (int e = make_tmap_2d_f32(&tBl, (SPLIT & 2) ? Bh : Bl, N, K, ldb, BN, BK)) return e;        // SPLIT & 2: unused
-    const int m_tiles = (M + UG_BM - 1) / UG_BM, n_tiles = (N + BN - 1) / BN, k_chunks = (K + BK - 1) / BK;
-    drain_chunks = drain_chunks * 32 / BK;        // `drain_chunks` is given in units of 32 K elements
+    auto mk = [](CUtensorMap* t, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+        return KIND == 0 ? make_tmap_2d_f32(t, static_cast<const float*>(base), rows, cols, ld, box_rows, BK)
+                         : make_tmap_2d_f16(t, base, rows, cols, ld, box_rows, BK * 2);
+    };
+    if (int e = mk(&tAh, Ah, M, K, lda, UG_BM)) return e;
+    if (int e = mk(&tAl, (SPLIT & 1) ? Ah : Al, M, K, lda, UG_BM)) return e;      // SPLIT & 1: unused
+    if (int e = mk(&tBh, Bh, N, K, ldb, BN)) return e;
+    if (int e = mk(&tBl, (SPLIT & 2) ? Bh : Bl, N, K, ldb, BN)) return e;        // SPLIT & 2: unused
+    const int m_tiles = (M + UG_BM - 1) / UG_BM, n_tiles = (N + BN - 1) / BN, k_chunks = (K + BK * KE - 1) / (BK * KE);
+    drain_chunks = drain_chunks * 32 / BK;        // `drain_chunks` is given in units of 32 words of K
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int grid, split_T = 0, full_units = m_tiles * n_tiles;
     if (mode == 0 || mode == 2) {
-        const UmmaSplitPlan pl = umma_plan<BN, BK>(M, N, K, sms, allow_split && mode == 0);
+        const UmmaSplitPlan pl = umma_plan<BN, BK * KE>(M, N, K, sms, allow_split && mode == 0);
         grid = pl.grid; split_T = pl.split_T; full_units = pl.full_units;
     } else {
         int G = sms / m_tiles;
@@ -451,13 +488,21 @@ inline int launch_umma_nt(const float* Ah, const float* Al, int M, int64_t lda, 
         grid = G * m_tiles;
     }
     if (drain_chunks < 1) drain_chunks = 2 * 32 / BK;
-    auto kern = umma_nt_3xtf32_kernel<BN, BK, Epi, EW, SPLIT, CW>;
+    auto kern = umma_nt_3xtf32_kernel<BN, BK, Epi, EW, SPLIT, CW, KIND>;
     const int smem = UmmaSmem<BN, BK>::TOTAL;
     BRN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kern<<<grid, 64 + 32 * EW + (SPLIT ? 32 * CW : 0), smem, stream>>>(tAh, tAl, tBh, tBl, m_tiles, n_tiles, k_chunks, drain_chunks, mode,
                                                          split_T, full_units, ep);
     BRN_LAUNCH_OK("umma_nt_3xtf32_kernel");
     return 0;
+}
+
+template <int BN, int BK, class Epi, int EW = UG_EPI_WARPS, int SPLIT = 0, int CW = 4>
+inline int launch_umma_nt(const float* Ah, const float* Al, int M, int64_t lda, const float* Bh, const float* Bl, int N,
+                          int64_t ldb, int K, int mode, int drain_chunks, const typename Epi::Params& ep,
+                          cudaStream_t stream, bool allow_split = false) {
+    return launch_umma_nt_kind<BN, BK, Epi, EW, SPLIT, CW, 0>(Ah, Al, M, lda, Bh, Bl, N, ldb, K, mode, drain_chunks, ep, stream,
+                                                              allow_split);
 }
 
 }  // namespace brn

@@ -374,7 +374,7 @@ vae_sample_dec0_kernel(const float* __restrict__ mean, const float* __restrict__
         if (row < R) {
             const int s = row / B, b = row % B;
             const float e = eps_in ? eps_in[(int64_t)row * L + l]
-                                   : philox_normal1(r.seed, r.offset, var_id, (uint32_t)(r.s0 + s), (row0_global + b) * L + l);
+                                   : philox_normal1(r.seed, philox_offset(r), var_id, (uint32_t)(r.s0 + s), (row0_global + b) * L + l);
             zz = __fmaf_rn(e, sd[(int64_t)b * L + l], mean[(int64_t)b * L + l]);
             z[(int64_t)row * L + l] = zz;
             epsb[(int64_t)row * L + l] = e;

@@ -34,7 +34,7 @@ wvgd_sample_assign_kernel(const float* __restrict__ loc, const float* __restrict
 #pragma unroll
             for (int j = 0; j < 4; ++j) e[j] = (4 * q + j < d) ? eps_in[vec * d + 4 * q + j] : 0.f;
         } else {
-            Normal4 n4 = philox_normal4(r.seed, r.offset, (uint32_t)(2 * k + draw), (uint32_t)(r.s0 + s), (uint32_t)q);
+            Normal4 n4 = philox_normal4(r.seed, philox_offset(r), (uint32_t)(2 * k + draw), (uint32_t)(r.s0 + s), (uint32_t)q);
 #pragma unroll
             for (int j = 0; j < 4; ++j) e[j] = n4.v[j];
         }

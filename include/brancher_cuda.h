@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define BRN_ABI_VERSION 1
+#define BRN_ABI_VERSION 2
 
 /* One mean-field Normal variational variable  q(w) = N(mu, softplus(rho))  together with the Normal
  * prior p(w) = N(prior_loc, prior_scale) of the same name.
@@ -58,6 +58,8 @@ typedef struct brn_sample_range {
     int32_t  _pad;
     uint64_t seed;      /* Philox key                                     */
     uint64_t offset;    /* Philox counter word 3 (iteration number)       */
+    const uint64_t* offset_dev; /* optional DEVICE scalar added to `offset` when the noise is drawn (NULL: none): a
+                                 * CUDA-graph-captured iteration bumps it on the device instead of re-recording arguments */
 } brn_sample_range;
 
 int         brn_abi_version(void);

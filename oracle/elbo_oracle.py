@@ -44,6 +44,10 @@ def _t(x, dtype, requires_grad=False):
     return t
 
 
+def F_softplus(x):
+    return torch.nn.functional.softplus(x)
+
+
 def softplus_inverse(sigma):
     """rho such that softplus(rho) = sigma, as the reference stores learnable scales
     (geometric_ranges.py:56-57, numpy fp64 then cast to fp32 by utilities.py:241-247)."""
@@ -430,3 +434,77 @@ def wvgd_loss(X, y, theta, loc, rho, eps_elbo, eps_particle, prior=None, dtype=t
         total = total - elbo + ploss
     total.backward()
     return float(total.detach()), {"loc": lc.grad.numpy().copy(), "rho": rh.grad.numpy().copy(), "theta": th.grad.numpy().copy()}, counts
+
+
+# ----------------------------------------------------------------------------------------------
+# Full-size evaluations (BASELINE configs C2 / C4): the same objectives with the gradient written out by hand and the
+# rows streamed in chunks, so that 10^6 rows x 1024 samples fit in host memory (autograd would keep every chunk's
+# [S, rows] logits alive).  Each is pinned against the autograd restatement above at small sizes in
+# tests/test_oracle_golden.py before it is trusted at the configured size.
+# ----------------------------------------------------------------------------------------------
+def logreg_elbo_streamed(X, y, params, eps, prior=None, dtype=torch.float64, row_chunk=65536):
+    """Binomial(1, logits) logistic regression, C = 1.  Same value and gradients as `logreg_elbo` (reference lines cited
+    there): loss = -(mean_s[sum_b (y l - softplus(l)) + log p(w_s)] + H[q]); d/dmu, d/drho through w = mu + softplus(rho) eps,
+    the prior (tied: q's own loc / scale) and the analytic entropy."""
+    mu, rho = (_t(a, dtype) for a in params["weights"])
+    e = _t(eps["weights"], dtype)                                   # [S, 1, F]
+    S, F = e.shape[0], e.shape[-1]
+    sg = F_softplus(rho)
+    w = (mu + sg * e).reshape(S, F)
+    Xt = torch.as_tensor(np.asarray(X))
+    yt = torch.as_tensor(np.asarray(y))
+    ll = torch.zeros(S, dtype=dtype)
+    gw = torch.zeros(S, F, dtype=dtype)
+    with torch.no_grad():
+        for r0 in range(0, Xt.shape[0], row_chunk):
+            xb = Xt[r0:r0 + row_chunk].to(dtype)
+            yb = yt[r0:r0 + row_chunk].to(dtype)
+            L = w @ xb.T                                            # [S, rows]
+            ll += (yb[None, :] * L - torch.nn.functional.softplus(L)).sum(1)
+            gw += (yb[None, :] - torch.sigmoid(L)) @ xb             # d ll_s / d w_s
+    c = 0.5 * math.log(2 * math.pi)
+    e2 = e.reshape(S, -1)
+    muf, sgf, rhof = mu.reshape(-1), sg.reshape(-1), rho.reshape(-1)
+    if prior is None:                                               # tied: log N(w; mu, sg) = -eps^2/2 - log sg - c
+        lp = (-0.5 * e2 * e2 - torch.log(sgf) - c).sum(1)
+        dlp_dmu = torch.zeros_like(muf)
+        dlp_dsg = -1.0 / sgf                                        # per sample; the eps-dependent parts cancel
+        dlp_dsg = dlp_dsg.expand(S, -1)
+        dlp_dmu = dlp_dmu.expand(S, -1)
+    else:
+        a = torch.as_tensor(np.broadcast_to(np.asarray(prior["weights"][0], dtype=np.float64), tuple(mu.shape)).copy()).to(dtype).reshape(-1)
+        b = torch.as_tensor(np.broadcast_to(np.asarray(prior["weights"][1], dtype=np.float64), tuple(mu.shape)).copy()).to(dtype).reshape(-1)
+        d = w - a
+        lp = (-0.5 * d * d / (b * b) - torch.log(b) - c).sum(1)
+        g = -d / (b * b)
+        dlp_dmu, dlp_dsg = g, g * e2
+    ent = (0.5 + c + torch.log(sgf)).sum()
+    loss = -((ll + lp).mean() + ent)
+    dE_dmu = (gw + dlp_dmu).mean(0)
+    dE_dsg = (gw * e2 + dlp_dsg).mean(0) + 1.0 / sgf
+    grads = {"weights_loc": (-dE_dmu).reshape(tuple(mu.shape)).numpy(),
+             "weights_scale": (-dE_dsg * torch.sigmoid(rhof)).reshape(tuple(mu.shape)).numpy()}
+    return float(loss), grads
+
+
+def particles_loss_grad_streamed(X, y, theta, prior=None, dtype=torch.float64, row_chunk=16384):
+    """Binomial(1, logits) particles (C = 1), hand-written gradient, rows streamed: same as `particles_loss_grad`."""
+    th = _t(theta, dtype).reshape(theta.shape[0], -1)               # [n, F]
+    Xt = torch.as_tensor(np.asarray(X))
+    yt = torch.as_tensor(np.asarray(y))
+    ll = torch.zeros((), dtype=dtype)
+    G = torch.zeros_like(th)
+    with torch.no_grad():
+        for r0 in range(0, Xt.shape[0], row_chunk):
+            xb = Xt[r0:r0 + row_chunk].to(dtype)
+            yb = yt[r0:r0 + row_chunk].to(dtype)
+            L = th @ xb.T
+            ll += (yb[None, :] * L - torch.nn.functional.softplus(L)).sum()
+            G -= (yb[None, :] - torch.sigmoid(L)) @ xb
+        loss = -ll
+        if prior is not None:
+            a, b = _t(prior[0], dtype).reshape(-1), _t(prior[1], dtype).reshape(-1)
+            d = th - a
+            loss = loss - (-0.5 * d * d / (b * b) - torch.log(b) - 0.5 * math.log(2 * math.pi)).sum()
+            G += d / (b * b)
+    return float(loss), G.numpy().reshape(np.asarray(theta).shape)

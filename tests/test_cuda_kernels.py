@@ -268,10 +268,10 @@ def test_linear_empty_rows(cu):
                                        (257, 130, 97, 16, 5), (1024, 784, 100, 10, 4), (40, 33, 21, 3, 1),
                                        (130, 37, 5, 2, 4)])
 @pytest.mark.parametrize("tied", [True, False])
-@pytest.mark.parametrize("mid", ["5", "4", "3"])
+@pytest.mark.parametrize("mid", ["5", "4"])
 def test_bnn_tcgen05_variant(cu, monkeypatch, B, P, H, C, S, tied, mid):
     """mid = 5 (default): the mid stage fused into the forward GEMM's epilogue and the sample-axis reduction into the
-    backward GEMM's; 4: staged pipeline, layer 2 on the warp-level tensor cores (mma.sync 3xTF32); 3: the scalar-FMA kernel."""
+    backward GEMM's; 4: staged pipeline (forward GEMM -> mid kernel on mma.sync 3xTF32 -> backward GEMM -> statistics)."""
     from oracle import elbo_oracle as O
     monkeypatch.setenv("BRN_BNN_VARIANT", "tcgen05")
     monkeypatch.setenv("BRN_BNN_MID", mid)
