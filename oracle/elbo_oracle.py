@@ -246,6 +246,41 @@ def vae_elbo(X, enc, dec, eps, sd_offset=0.1, dtype=torch.float32, row_chunk=Non
     return loss, {k: v.grad.numpy().copy() for k, v in P.items()}
 
 
+def vae_relu_margins(X, enc, dec, eps, sd_offset=0.1, row_chunk=512):
+    """fp64 forward pass of `vae_elbo`: for every DATA row b the smallest relative distance of a ReLU pre-activation from
+    its kink,  min over layers / units / samples of |pre| / (sum_k |w_k a_k| + |bias|).
+    A ReLU network's gradient is discontinuous where a pre-activation crosses zero: two correct fp32 evaluations whose
+    forward passes differ by rounding pick different branches there (the reference's own fp32 run included), so parity of
+    gradients is only defined on rows whose margin exceeds the forward error of the implementations being compared."""
+    dt = torch.float64
+    Xt, et = _t(X, dt), _t(eps, dt)
+    S, B, L = et.shape
+    W = lambda a: _t(a, dt)
+    out = np.full(B, np.inf)
+    with torch.no_grad():
+        for b0 in range(0, B, row_chunk):
+            xb, eb = Xt[b0:b0 + row_chunk], et[:, b0:b0 + row_chunk]
+            m = torch.full((xb.shape[0],), float("inf"), dtype=dt)
+            h = xb
+            for Wi, bi in zip(enc["W"], enc["b"]):
+                Wi, bi = W(Wi), W(bi)
+                pre = F.linear(h, Wi, bi)
+                sc = F.linear(h.abs(), Wi.abs(), bi.abs())
+                m = torch.minimum(m, (pre.abs() / sc).min(dim=1).values)
+                h = torch.relu(pre)
+            mean = F.linear(h, W(enc["W_mean"]), W(enc["b_mean"]))
+            sd = F.softplus(F.linear(h, W(enc["W_sd"]), W(enc["b_sd"]))) + sd_offset
+            g = mean.unsqueeze(0) + eb * sd.unsqueeze(0)
+            for Wi, bi in zip(dec["W"], dec["b"]):
+                Wi, bi = W(Wi), W(bi)
+                pre = F.linear(g, Wi, bi)
+                sc = F.linear(g.abs(), Wi.abs(), bi.abs())
+                m = torch.minimum(m, (pre.abs() / sc).min(dim=2).values.min(dim=0).values)
+                g = torch.relu(pre)
+            out[b0:b0 + row_chunk] = m.numpy()
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
 # README AR(1) (config C1): /root/reference/README.md:22-75 with y0 named 'y0' (README reuses 'x0')
 # and LogitNormalVariable defined as torch TransformedDistribution(Normal, SigmoidTransform)

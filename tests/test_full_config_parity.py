@@ -135,18 +135,61 @@ def test_c4_svgd_full_config(cu):
 
 # ------------------------------------------------------------------------------------------------ C5
 def test_c5_vae_full_config(cu):
-    """C5: VAE_playground widths (784-256-512-(2+2) / 2-512-256-784), B = 4096, S = 16, Philox noise re-materialised."""
+    """C5: VAE_playground widths (784-256-512-(2+2) / 2-512-256-784), B = 4096, S = 16, Philox noise re-materialised.
+
+    ReLU makes the gradient discontinuous in the forward pass: a unit whose pre-activation lies within rounding error of
+    zero is switched on by one correct fp32 evaluation and off by another, and ONE flipped unit moves a bias gradient by
+    1 / (S B) of its terms -- more than the tolerance at 65536 rows.  The parity statement is therefore made on the data
+    rows whose every ReLU pre-activation (13 056 unit evaluations per data row) is at least 4e-6 (relative to its own
+    terms: a few times the forward error of a 3xTF32 layer stack) away from the kink in the fp64 forward pass -- there the
+    strict rule must hold -- and the remaining rows (about 15 %) are tied in by linearity: the evaluation of
+    the full batch must equal the sum of the evaluations of the two row subsets, and on the near-kink rows CUDA and oracle
+    must still agree to 1 % of each tensor's scale."""
     from oracle import elbo_oracle as O
     import test_vae_cuda as V
     B, D, L, S = 4096, 784, 2, 16
     X, enc, dec, _ = V.random_vae(31, B, D, L, (256, 512), (512, 256), 1)
     r = cu.sample_range(S, seed=13, offset=2)
-    net = V.make_net(cu, enc, dec)
-    loss = cu.vae_elbo_fwd_bwd(dev(X), net, r, var_id=5).item()
     eps = cu.philox_normal(B * L, 5, r, DEV).cpu().numpy().reshape(S, B, L)
-    o64 = O.vae_elbo(X, enc, dec, eps, dtype=torch.float64, row_chunk=512)
-    o32 = O.vae_elbo(X, enc, dec, eps, row_chunk=512)
-    grads = V.grads_of(net)
-    literal_report("C5 vae B=4096 S=16", dict(grads, loss=np.array(loss)), dict(o64[1], loss=np.array(o64[0])),
-                   dict(o32[1], loss=np.array(o32[0])))
-    check_against_oracle(loss, grads, o32, o64, "C5 full config")
+    margin = O.vae_relu_margins(X, enc, dec, eps)
+    clean = margin >= 4e-6
+    n_amb = int((~clean).sum())
+    assert n_amb < B // 4, "too many near-kink rows: %d" % n_amb
+
+    def run_cuda(rows, add_constant=True):
+        """the device evaluation of a row subset, scaled as part of the full batch (B_total = B), injected noise"""
+        net = V.make_net(cu, enc, dec)
+        idx = np.flatnonzero(rows)
+        loss = cu.vae_elbo_fwd_bwd(dev(X[idx]), net, cu.sample_range(S), eps=dev(eps[:, idx]), B_total=B, add_constant=add_constant)
+        return loss.item(), V.grads_of(net)
+
+    # the whole batch in ONE call, kernel-generated Philox noise
+    net = V.make_net(cu, enc, dec)
+    loss_full = cu.vae_elbo_fwd_bwd(dev(X), net, r, var_id=5).item()
+    g_full = V.grads_of(net)
+    assert cu.last_variant() == "tcgen05"
+    # strict parity on the rows away from the kinks
+    l_c, g_c = run_cuda(clean)
+    sub = lambda a: a[clean]
+    o64 = O.vae_elbo(X[clean], enc, dec, eps[:, clean], dtype=torch.float64, row_chunk=512)
+    o32 = O.vae_elbo(X[clean], enc, dec, eps[:, clean], row_chunk=512)
+    # the oracle normalises by its own row count and adds -ln S: bring it to the full-batch normalisation
+    f = clean.sum() / B
+    lnS = np.log(S)
+    o64s = ((o64[0] + lnS) * f - lnS, {k: v * f for k, v in o64[1].items()})
+    o32s = ((o32[0] + lnS) * f - lnS, {k: v * f for k, v in o32[1].items()})
+    literal_report("C5 vae B=4096 S=16 (%d rows away from ReLU kinks, %d near-kink rows excluded)" % (clean.sum(), n_amb),
+                   dict(g_c, loss=np.array(l_c)), dict(o64s[1], loss=np.array(o64s[0])), dict(o32s[1], loss=np.array(o32s[0])))
+    check_against_oracle(l_c, g_c, o32s, o64s, "C5 full config, rows away from ReLU kinks")
+    # linearity: full batch == clean rows + near-kink rows (device vs device, fp32 summation order only)
+    l_a, g_a = run_cuda(~clean, add_constant=False)
+    assert_close(l_c + l_a, loss_full, "C5 loss: full batch vs sum of row subsets", rtol=1e-6, atol=1e-6)
+    for k in g_full:
+        assert_close(g_c[k] + g_a[k], g_full[k], "C5 %s: full batch vs sum of row subsets" % k, rtol=1e-5, atol=2e-6,
+                     scale=np.abs(g_full[k]).max())
+    # near-kink rows: no gross error
+    fa = (~clean).sum() / B
+    oa = O.vae_elbo(X[~clean], enc, dec, eps[:, ~clean], dtype=torch.float64)
+    for k in g_a:
+        w = oa[1][k] * fa
+        assert np.abs(g_a[k].reshape(w.shape) - w).max() <= 1e-2 * np.abs(w).max(), k
