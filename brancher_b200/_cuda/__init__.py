@@ -61,6 +61,17 @@ class WvgdArgs(ctypes.Structure):
                [(n, ctypes.c_int32) for n in ("P", "S", "d", "rho_per_elem", "biased", "_pad")]
 
 
+class OptTensor(ctypes.Structure):
+    """struct brn_opt_tensor"""
+    _fields_ = [("param", ctypes.c_void_p), ("grad", ctypes.c_void_p), ("m", ctypes.c_void_p), ("v", ctypes.c_void_p)]
+
+
+class OptHyper(ctypes.Structure):
+    """struct brn_opt_hyper"""
+    _fields_ = [("kind", ctypes.c_int32), ("lr", ctypes.c_float), ("momentum", ctypes.c_float), ("weight_decay", ctypes.c_float),
+                ("beta1", ctypes.c_float), ("beta2", ctypes.c_float), ("eps", ctypes.c_float), ("_pad", ctypes.c_int32)]
+
+
 # name -> (restype, argtypes): every symbol include/brancher_cuda.h declares
 SYMBOLS = {
     "brn_abi_version": (ctypes.c_int, []),
@@ -112,6 +123,9 @@ SYMBOLS = {
                                                       ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "brn_wvgd_reduce": (ctypes.c_int, [ctypes.POINTER(WvgdArgs), ctypes.c_void_p]),
+    "brn_opt_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.POINTER(OptHyper),
+                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                    ctypes.c_void_p]),
     "brn_svgd_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
     "brn_svgd_direction": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 5 +
                            [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
@@ -378,14 +392,14 @@ def minibatch_indices(N, B, device, seed=0, offset=0, return_rounds=False):
     return (out, rounds) if return_rounds else out
 
 
-def dag_elbo_fwd_bwd(ops, n_ops, n_slots, params, data, n_rows, eps, n_eps, r, loss=None):
+def dag_elbo_fwd_bwd(ops, n_ops, n_slots, params, data, n_rows, eps, n_eps, r, loss=None, dparams=None):
     """K1.  ops: uint8 CUDA tensor holding n_ops packed `brn_dag_op` records (24 bytes each); params [n_params] fp32;
     data [n_rows, n_cols] fp32 or None; eps [s_local, n_eps] fp32 or None (Philox).  Returns (loss fp64 [1], dparams)."""
     dev = ops.device
     if ops.dtype != torch.uint8 or ops.numel() != 24 * n_ops:
         raise BrancherCudaError("ops must be a uint8 tensor of %d bytes" % (24 * n_ops))
     loss = torch.zeros(1, dtype=torch.float64, device=dev) if loss is None else loss
-    dparams = torch.zeros_like(params)
+    dparams = torch.zeros_like(params) if dparams is None else dparams       # accumulated into (+=): the caller zeroes its own
     n_cols = 0 if data is None else data.shape[1]
     if eps is not None and (eps.shape[0] != r.s_local or eps.shape[1] != n_eps):
         raise BrancherCudaError("eps must be [s_local=%d, n_eps=%d], got %s" % (r.s_local, n_eps, tuple(eps.shape)))
@@ -579,3 +593,45 @@ def gemm_nt_3xtf32(A, B):
     _check(lib().brn_gemm_nt_3xtf32(_ptr(A, what="A"), _ptr(B, what="B"), _ptr(D), M, N, K, ws.data_ptr(), ws.numel(),
                                     _stream(A.device)), "brn_gemm_nt_3xtf32")
     return D
+
+
+
+SGD, ADAM = 0, 1
+
+
+class FusedOptimizer:
+    """brn_opt_step over a fixed set of (parameter, gradient) tensors: ONE update launch for all of them, the finiteness
+    check of the loss, the loss curve and the Philox offset handled on the device (no host synchronisation per iteration).
+    params / grads: lists of contiguous fp32 CUDA tensors whose storage stays put (the parameters are updated in place)."""
+
+    def __init__(self, params, grads, kind, lr, momentum=0.0, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8, curve_len=0):
+        if not params:
+            raise BrancherCudaError("FusedOptimizer: no parameters")
+        dev = params[0].device
+        self.params, self.grads = list(params), list(grads)
+        need_m = kind == ADAM or momentum != 0.0
+        self.m = [torch.zeros_like(p) for p in params] if need_m else [None] * len(params)
+        self.v = [torch.zeros_like(p) for p in params] if kind == ADAM else [None] * len(params)
+        table = (OptTensor * len(params))()
+        prefix = [0]
+        for i, (p, g) in enumerate(zip(params, grads)):
+            if p.numel() != g.numel():
+                raise BrancherCudaError("FusedOptimizer: parameter %d and its gradient differ in size" % i)
+            table[i] = OptTensor(_ptr(p, what="param"), _ptr(g, what="grad"), _ptr(self.m[i]), _ptr(self.v[i]))
+            prefix.append(prefix[-1] + p.numel())
+        self.total = prefix[-1]
+        self.table = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8).to(dev)
+        self.prefix = torch.tensor(prefix, dtype=torch.int64).to(dev)
+        self.hyper = OptHyper(int(kind), float(lr), float(momentum), float(weight_decay), float(betas[0]), float(betas[1]),
+                              float(eps), 0)
+        self.counters = torch.zeros(3, dtype=torch.int64, device=dev)       # successful steps, iterations, skipped
+        self.curve = torch.zeros(max(int(curve_len), 1), dtype=torch.float32, device=dev)
+        self.curve_len = int(curve_len)
+
+    def step(self, loss, offset_dev=None):
+        dev = self.table.device
+        _check(lib().brn_opt_step(self.table.data_ptr(), self.prefix.data_ptr(), len(self.params), self.total,
+                                  ctypes.byref(self.hyper), _ptr(loss, torch.float64, "loss"), self.counters.data_ptr(),
+                                  self.curve.data_ptr() if self.curve_len else None, self.curve_len,
+                                  None if offset_dev is None else _ptr(offset_dev, torch.int64, "offset_dev"), _stream(dev)),
+               "brn_opt_step")

@@ -48,6 +48,11 @@ def perform_inference(joint_model, number_iterations, number_samples=1, optimize
 
     inference_method.check_model_compatibility(joint_model, posterior_model, sampler_model)
 
+    if _fused_loop(joint_model, posterior_model, number_iterations, number_samples, optimizer, opt_params, inference_method,
+                   optimizers_list, input_values, pretraining_iterations):
+        inference_method.post_process(joint_model)
+        return
+
     try:
         from tqdm import tqdm
         iterator = tqdm(range(number_iterations))
@@ -72,6 +77,92 @@ def perform_inference(joint_model, number_iterations, number_samples=1, optimize
     curve = torch.stack(losses).cpu().numpy() if losses else np.zeros((0,))
     joint_model.diagnostics.update({"loss curve": curve})
     inference_method.post_process(joint_model)
+
+
+_FUSED_SGD = {"lr", "momentum", "weight_decay"}
+_FUSED_ADAM = {"lr", "betas", "eps", "weight_decay"}
+fused_loop_enabled = True        # set to False to force the step-by-step loop (tests compare the two)
+last_loop = None                 # "graph" | "eager": which loop the last perform_inference ran
+
+
+def _fused_loop(joint_model, posterior_model, number_iterations, number_samples, optimizer, opt_params, inference_method,
+                optimizers_list, input_values, pretraining_iterations):
+    """The whole iteration -- fused ELBO + gradient evaluation, optimiser step, finiteness check, loss curve, next Philox
+    offset -- captured ONCE in a CUDA graph and replayed `number_iterations` times with no host synchronisation in between
+    (replaces the loop body brancher/inference.py:95-108 and optimizers.py:69-73).  Used when the iteration is
+    static: ReverseKL with the pathwise estimator, a lowered plan with persistent buffers, observations that are fixed
+    tensors (no per-iteration minibatch draw), SGD / Adam with plain hyper-parameters, one process.  Returns False when the
+    step-by-step loop has to run instead."""
+    global last_loop
+    last_loop = "eager"
+    from brancher_b200 import config, lowering, distributed
+    if not fused_loop_enabled or number_iterations <= 0 or config.device.type != "cuda" or distributed.world_size() != 1:
+        return False
+    if type(inference_method) is not ReverseKL or \
+            inference_method.gradient_estimator is not gradient_estimators.PathwiseDerivativeEstimator:
+        return False
+    if input_values or pretraining_iterations or lowering._INJECTED is not None:
+        return False
+    if optimizer == "SGD" and set(opt_params) <= _FUSED_SGD and "lr" in opt_params:
+        kind = 0
+    elif optimizer == "Adam" and set(opt_params) <= _FUSED_ADAM:
+        kind = 1
+    else:
+        return False
+    joint_model.update_observed_submodel()
+    observed = joint_model.observed_submodel
+    if any(getattr(v, "distribution", None) is not None and v.distribution.kind == "empirical" for v in observed._flatten()):
+        return False                              # a fresh minibatch is drawn every iteration
+    plan = lowering.get_plan(joint_model, posterior_model)
+    if not hasattr(plan, "static_evaluation"):
+        return False
+    from brancher_b200 import _cuda as cu
+    empirical = observed._get_sample(1, observed=True, differentiable=False)
+    dev = config.device
+    offset_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+    ev = plan.static_evaluation(number_samples, empirical, offset_dev)
+    if ev is None:
+        return False
+    trainable = [(p, g) for p, g in zip(ev.params, ev.grads) if p.requires_grad]
+    # every parameter the step-by-step loop would update must be covered by the plan's gradients
+    covered = {id(p) for p, _ in trainable}
+    for opt in optimizers_list:
+        for group in opt.optimizer.param_groups:
+            if any(id(p) not in covered for p in group["params"]):
+                return False
+    if not trainable or any(not (p.is_contiguous() and p.dtype == torch.float32) for p, _ in trainable):
+        return False
+    fo = cu.FusedOptimizer([p.detach() for p, _ in trainable], [g for _, g in trainable], kind,
+                           lr=opt_params.get("lr", 1e-3), momentum=opt_params.get("momentum", 0.0),
+                           weight_decay=opt_params.get("weight_decay", 0.0), betas=opt_params.get("betas", (0.9, 0.999)),
+                           eps=opt_params.get("eps", 1e-8), curve_len=number_iterations)
+
+    def iteration():
+        ev.launch()
+        fo.step(ev.loss, offset_dev)
+
+    # first iteration eagerly on a side stream (lazy initialisation must not happen under capture), the rest from a graph
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        iteration()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    if number_iterations > 1:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            iteration()
+        # the capture itself does not execute: (number_iterations - 1) replays follow the eager first iteration
+        for _ in range(number_iterations - 1):
+            graph.replay()
+    counters = fo.counters.cpu().numpy()                 # the ONE synchronisation of the loop
+    curve = fo.curve[:number_iterations].cpu().numpy()
+    for _ in range(number_iterations - 1):               # the step-by-step loop would have consumed one offset per iteration
+        config.next_offset()
+    if counters[2]:
+        warnings.warn("Numerical error, skipped %d samples" % int(counters[2]))
+    joint_model.diagnostics.update({"loss curve": curve})
+    last_loop = "graph"
+    return True
 
 
 class InferenceMethod(ABC):

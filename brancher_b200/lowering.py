@@ -194,7 +194,32 @@ class Plan:
 
         return _FusedELBO.apply(runner, *params)
 
-    def _launch(self, cu, mvars, r, empirical_samples):
+    def static_evaluation(self, number_samples, empirical_samples, offset_dev):
+        """One evaluation as a replayable launch sequence over PERSISTENT buffers (what a CUDA graph captures): returns an
+        object with `.params` (the learnable leaf tensors), `.grads` (views of one flat buffer, aligned with params),
+        `.loss` (fp64 [1]) and `.launch()`.  The Philox offset of replay i is base + offset_dev[0] (read on the device)."""
+        from types import SimpleNamespace
+        from brancher_b200 import _cuda as cu
+        cu.lib()
+        if distributed.world_size() != 1 or _INJECTED is not None:
+            return None
+        r = cu.sample_range(number_samples, seed=config.seed, offset=config.next_offset(), offset_dev=offset_dev)
+        flat, sinks = cu.flat_grad_views([int(np.prod(spec.shape)) for spec in self.latents], config.device)
+        loss = torch.zeros(1, dtype=torch.float64, device=config.device)
+        mvars = [spec.make(cu, i, None, sk) for i, (spec, sk) in enumerate(zip(self.latents, sinks))]
+        params, grads = [], []
+        for spec, v in zip(self.latents, mvars):
+            params += [spec.loc_root.value, spec.scale_root.value]
+            grads += [v.dmu, v.drho]
+
+        def launch():
+            flat.zero_()
+            loss.zero_()
+            self._launch(cu, mvars, r, empirical_samples, loss=loss)
+
+        return SimpleNamespace(params=params, grads=grads, loss=loss, launch=launch)
+
+    def _launch(self, cu, mvars, r, empirical_samples, loss=None):
         raise NotImplementedError
 
 
@@ -213,14 +238,14 @@ class LinearPlan(Plan):
         self.k, self.x_var, self.likelihood, self.C = k, x_var, likelihood, C
         self.latents = [w_spec]
 
-    def _launch(self, cu, mvars, r, empirical):
+    def _launch(self, cu, mvars, r, empirical, loss=None):
         X = _data_matrix(empirical[self.x_var], "x")
         yv = empirical[self.k].reshape(-1)
         if self.likelihood == cu.BERNOULLI:
             y = yv.to(torch.float32).contiguous()
         else:
             y = yv.to(torch.int32).contiguous()
-        return cu.linear_elbo_fwd_bwd(X, y, self.likelihood, mvars[0], self.C, r)
+        return cu.linear_elbo_fwd_bwd(X, y, self.likelihood, mvars[0], self.C, r, loss=loss)
 
 
 class BNNPlan(Plan):
@@ -231,10 +256,10 @@ class BNNPlan(Plan):
         self.k, self.x_var = k, x_var
         self.latents = specs          # weights1, b1, weights2, b2
 
-    def _launch(self, cu, mvars, r, empirical):
+    def _launch(self, cu, mvars, r, empirical, loss=None):
         X = _data_matrix(empirical[self.x_var], "x")
         y = empirical[self.k].reshape(-1).to(torch.int32).contiguous()
-        return cu.bnn_elbo_fwd_bwd(X, y, mvars, r)
+        return cu.bnn_elbo_fwd_bwd(X, y, mvars, r, loss=loss)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -674,6 +699,40 @@ class DagPlan(Plan):
             return loss, [g[i].reshape(p.shape) if p.requires_grad else None for i, p in enumerate(params)]
 
         return _FusedELBO.apply(runner, *params)
+
+    def static_evaluation(self, number_samples, empirical_samples, offset_dev):
+        """see Plan.static_evaluation"""
+        from types import SimpleNamespace
+        from brancher_b200 import _cuda as cu
+        cu.lib()
+        P = self.prog
+        if distributed.world_size() != 1 or _INJECTED is not None or not P.params:
+            return None
+        dev = config.device
+        r = cu.sample_range(number_samples, seed=config.seed, offset=config.next_offset(), offset_dev=offset_dev)
+        if self._ops_dev is None or self._ops_dev.device != dev:
+            self._ops_dev = torch.from_numpy(P.table().view(np.uint8)).to(dev)
+        cols = []
+        for var, rows in zip(P.columns, P.col_rows):
+            t = empirical_samples[var] if var in empirical_samples else _observed_tensor(var)
+            t = t.reshape(-1).to(torch.float32)
+            if t.numel() != rows:
+                raise ValueError("observed %r now has %d rows, the lowered plan expects %d" % (var.name, t.numel(), rows))
+            cols.append(t.expand(self.n_rows) if rows == 1 else t)
+        data = torch.stack(cols, dim=1).contiguous() if cols else None
+        params = list(P.params)
+        dparams = torch.zeros(len(params), dtype=torch.float32, device=dev)
+        loss = torch.zeros(1, dtype=torch.float64, device=dev)
+        flat_params = [p.detach().reshape(-1) for p in params]
+
+        def launch():
+            dparams.zero_()
+            loss.zero_()
+            pvec = torch.cat(flat_params)
+            cu.dag_elbo_fwd_bwd(self._ops_dev, self._ops_dev.numel() // 24, P.n_slots, pvec, data, self.n_rows, None,
+                                len(P.eps_names), r, loss=loss, dparams=dparams)
+
+        return SimpleNamespace(params=params, grads=[dparams[i:i + 1] for i in range(len(params))], loss=loss, launch=launch)
 
 
 def lower(joint, posterior):

@@ -291,6 +291,29 @@ const char* brn_profile_stage(int i, double* total_ms, long long* calls);
 void        brn_profile_reset(void);
 long long   brn_launch_count(void);                    /* kernels launched by this library so far */
 
+/* Fused optimiser step + loop bookkeeping without host synchronisation.
+ * Replaces ProbabilisticOptimizer.update -> torch.optim.<name>.step() (brancher/optimizers.py:69-73) and, of the training
+ * loop, the isfinite check / skip (brancher/inference.py:98,106-107) and the loss-curve bookkeeping (:105-109).
+ * table_dev [n_tensors] and prefix_dev [n_tensors + 1] (first flat element index of each tensor; prefix[n] = total) live in
+ * DEVICE memory.  counters_dev = int64[3]: {successful steps, iterations, skipped iterations}.  If *loss_dev is not finite
+ * the parameters are left untouched.  curve_dev[iteration] = (float)*loss_dev when curve_dev != NULL and iteration <
+ * curve_len.  *offset_dev (optional, see brn_sample_range.offset_dev) is incremented, so the next replay of a captured
+ * iteration draws fresh Philox noise.
+ * kind 0 = SGD (lr, momentum, weight_decay; dampening 0, no Nesterov), kind 1 = Adam (lr, beta1, beta2, eps, L2 weight_decay;
+ * torch.optim.Adam's update, no amsgrad). */
+typedef struct brn_opt_tensor {
+    float* param;        /* [numel] updated in place                                   */
+    const float* grad;   /* [numel]                                                     */
+    float* m;            /* [numel] momentum buffer / Adam exp_avg (may be NULL for plain SGD) */
+    float* v;            /* [numel] Adam exp_avg_sq (NULL for SGD)                      */
+} brn_opt_tensor;
+typedef struct brn_opt_hyper {
+    int32_t kind; float lr, momentum, weight_decay, beta1, beta2, eps; int32_t _pad;
+} brn_opt_hyper;
+int brn_opt_step(const brn_opt_tensor* table_dev, const int64_t* prefix_dev, int n_tensors, int64_t total,
+                 const brn_opt_hyper* hyper, const double* loss_dev, int64_t* counters_dev, float* curve_dev,
+                 int64_t curve_len, uint64_t* offset_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
