@@ -339,6 +339,18 @@ def main_ours(args):
             r = cu.sample_range(S_total, s0=s0, s_local=S_local, seed=args.seed, offset=it)
             gflat.zero_()
             return cu.bnn_elbo_fwd_bwd(Xd, yd, mvars, r, data_ready=data_ready)
+
+        # the product's training loop replays ONE captured iteration (brancher_b200/inference._fused_loop): the same here --
+        # the evaluation is captured once, its Philox offset lives in device memory and is bumped inside the graph
+        offset_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        loss_buf = torch.zeros(1, dtype=torch.float64, device=dev)
+        r_graph = cu.sample_range(S_total, s0=s0, s_local=S_local, seed=args.seed, offset=0, offset_dev=offset_dev)
+
+        def graph_body(Xd=X, yd=y, data_ready=None):
+            gflat.zero_()
+            loss_buf.zero_()
+            cu.bnn_elbo_fwd_bwd(Xd, yd, mvars, r_graph, loss=loss_buf, data_ready=data_ready)
+            offset_dev.add_(1)
     elif wl == "vae":
         # batch rows sharded over ranks (weak scaling: B rows per GPU); every rank evaluates all S samples of its rows;
         # one all-reduce of the flat gradient buffer (669 k floats) + loss
@@ -485,9 +497,45 @@ def main_ours(args):
         loss = reduce_partials(device_step(it, Xd, yd))
         return float(loss.item())          # device -> host read of the step's result
 
+    graph_step = graph_e2e = None
+    launches_per_graph = 0
     if wl == "bnn":
         copy_stream, copy_done = torch.cuda.Stream(dev), torch.cuda.Event()
         Xstage, ystage = torch.empty_like(X), torch.empty_like(y)
+        if not os.environ.get("BRN_BENCH_NO_GRAPH"):
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):                  # lazy initialisation outside the capture
+                graph_body()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize()
+            g_eval = torch.cuda.CUDAGraph()
+            l0 = cu.launch_count()
+            with torch.cuda.graph(g_eval):
+                graph_body()
+            launches_per_graph = cu.launch_count() - l0 + 3          # + the two zero fills and the offset bump
+            def graph_step(it):
+                g_eval.replay()
+                return reduce_partials(loss_buf)
+            # end to end: the minibatch copy from pinned host memory is a branch of the same graph, joined just before the
+            # evaluation's first read of X (brn_set_data_ready_event): noise + weight sampling run under the copy
+            try:
+                g_e2e = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_e2e):
+                    cap = torch.cuda.current_stream(dev)
+                    copy_stream.wait_stream(cap)
+                    with torch.cuda.stream(copy_stream):
+                        Xstage.copy_(Xpin, non_blocking=True)
+                        ystage.copy_(ypin, non_blocking=True)
+                        copy_done.record(copy_stream)
+                    graph_body(Xstage, ystage, data_ready=copy_done)
+                    cap.wait_stream(copy_stream)
+                def graph_e2e(it):
+                    g_e2e.replay()
+                    return float(reduce_partials(loss_buf).item())
+            except Exception as exc:                        # pragma: no cover - falls back to the step-by-step e2e path
+                sys.stderr.write("bench: e2e graph capture failed (%s); using the step-by-step path\n" % exc)
+                graph_e2e = None
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)     # 256 MiB > 126 MB L2
 
     def barrier():
@@ -526,10 +574,12 @@ def main_ours(args):
     # the library (10 records per C3 step) cost ~29 us per step when they sit in that region (measured, profiles/r1z_*), so the
     # stage split and the dominant kernel's duration come from a second, equally long pass with the events enabled; its own
     # total normalises the shares.
-    ms, launches, _ = timed(step, args.steps, args.warmup, profile=False)
+    ms, launches, _ = timed(graph_step or step, args.steps, args.warmup, profile=False)
+    if graph_step:
+        launches = launches_per_graph * args.steps
     ms_prof, _, stages = timed(step, args.steps, 1, profile=True)
     clk = clocks.stop()
-    ms_e2e, _, _ = timed(lambda i: e2e_step(i), max(3, min(args.steps, 50)), 3)
+    ms_e2e, _, _ = timed(graph_e2e or (lambda i: e2e_step(i)), max(3, min(args.steps, 50)), 3)
     n_e2e = max(3, min(args.steps, 50))
 
     if rank == 0:
@@ -541,15 +591,23 @@ def main_ours(args):
         if algo_flops:
             dom = max(algo_flops, key=lambda k: stages.get(k, (0, 0))[0] if k in stages else 0)
             dom_ms, dom_calls = stages.get(dom, (float("nan"), 1))
-            peak = pk["bf16_sustained"] / 2.0 / 3.0
+            # fp32-equivalent tensor rooflines (algorithmic flops counted once).  K3's GEMMs issue three kind::f16 MMAs per
+            # algorithmic MMA on fp16 (hi, lo) pairs -> bf16 peak / 3; the other families issue three kind::tf32 MMAs (half the
+            # bf16 rate) -> bf16 peak / 6.  The kernels run ~0.1 ms each inside a sub-millisecond step at full clocks, so the
+            # BURST figure of MEASURED_PEAKS.json is the denominator; the others are listed for comparison with round 1.
+            den = {"3xfp16_burst": pk["bf16_burst"] / 3.0, "3xtf32_burst": pk["bf16_burst"] / 6.0,
+                   "3xtf32_sustained": pk["bf16_sustained"] / 6.0}
+            key = "3xfp16_burst" if wl == "bnn" else "3xtf32_burst"
+            peak = den[key]
             achieved = algo_flops[dom] / (dom_ms / max(dom_calls, 1) * 1e-3) / 1e12
+            whole = sum(algo_flops.values()) / (ms / args.steps * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak, "traffic": traffic.get(dom),
-                    "peak_note": "fp32-equivalent via 3xTF32 = bf16_tflops_sustained / 2 (TF32 rate) / 3 (split), " + pk["source"],
-                    # whole evaluation (all stages, launch gaps included) against the same tensor roofline
-                    "whole_step": {"algo_flops": sum(algo_flops.values()),
-                                   "achieved": sum(algo_flops.values()) / (ms / args.steps * 1e-3) / 1e12,
-                                   "frac": sum(algo_flops.values()) / (ms / args.steps * 1e-3) / 1e12 / peak},
+                    "peak_note": "fp32-equivalent, %s = bf16_tflops (burst) / %d, %s" % (key, 3 if wl == "bnn" else 6, pk["source"]),
+                    "frac_vs": {k: achieved / v for k, v in den.items()},
+                    # whole evaluation (all stages, launch gaps included) against the same tensor rooflines
+                    "whole_step": {"algo_flops": sum(algo_flops.values()), "achieved": whole, "frac": whole / peak,
+                                   "frac_vs": {k: whole / v for k, v in den.items()}},
                     "stage_share_of_step": stage_share}
         else:
             dom = max(algo_bytes, key=lambda k: stages.get(k, (0, 0))[0] if k in stages else 0)
@@ -565,6 +623,8 @@ def main_ours(args):
                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                "config": {"workload": cfg["name"], "noise": "Philox4x32-10 in-kernel", "l2": "256 MiB flush between timed steps",
+                          "launch": "one CUDA-graph replay per step (the product's training loop replays the same captured "
+                                    "iteration)" if graph_step else "step-by-step launches",
                           "stage_timing": "separate pass of the same K steps with the library's per-stage CUDA events on "
                                           "(%.4f ms/step there); the headline region carries no such events" % (ms_prof / args.steps),
                           "variant": (svgd_out[1] + " (K4a) + simt (K4b)") if wl == "svgd" else cu.last_variant(),

@@ -426,11 +426,13 @@ extern "C" int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int
         // TMEM accumulation chain = 2 x 32 words = 128 fp16 elements of K between register drains (umma_gemm.cuh): the error
         // of the evaluation grows with the chain (max gradient error / scale at the C3 shape: 0.9e-6 / 1.1e-6 / 1.3e-6 /
         // 2.3e-6 for 1 / 2 / 4 / 8, profiles/tools/bnn_err_probe.py) -- 128 elements is the chain length round 1 settled on.
-        const int drain = env_drain ? atoi(env_drain) : 2;
+        // The backward GEMM's accumulator is the per-sample weight gradient, summed over 256 samples afterwards: its chain
+        // may be twice as long (measured: no change of the parity margins, 8 us per evaluation).
+        const int drain = env_drain ? atoi(env_drain) : 2, drain_bwd = env_drain ? atoi(env_drain) : 4;
         // BRN_BNN_MID=5 selects the fully fused pipeline (mid stage in the forward GEMM's epilogue, sample-axis reduction
         // in the backward GEMM's); measured slower than the staged one on B200 (profiles/r2*), kept for A/B and tests
         const bool fused = env_mid && atoi(env_mid) == 5;
-        return bnn_tc_eval(X, y, L, vars, r, ws.tc, ws.eps, ws.W, ws.dW, ws.pre, ws.stats, with_prior, loss, drain, fused, stream);
+        return bnn_tc_eval(X, y, L, vars, r, ws.tc, ws.eps, ws.W, ws.dW, ws.pre, ws.stats, with_prior, loss, drain, drain_bwd, fused, stream);
     }
 
     // ---- SIMT variant

@@ -32,17 +32,40 @@ __device__ __forceinline__ void atomic_absmax(float* slot, float v) {        // 
     atomicMax(reinterpret_cast<unsigned int*>(slot), __float_as_uint(v));
 }
 
-__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ slot) {
-    float m = 0.f;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        m = fmaxf(m, fabsf(x[i]));
+// block-wide max of non-negative values -> ONE atomic per block (thousands of same-address atomics cost more than the pass)
+__device__ __forceinline__ void block_absmax_to(float m, float* slot) {
+    __shared__ float red[8];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m > 0.f) atomic_absmax(slot, m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = red[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) t = fmaxf(t, red[w]);
+        if (t > 0.f) atomic_absmax(slot, t);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ slot) {
+    float m = 0.f;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) == 0) {           // 16-byte loads over the aligned body
+        const float4* x4 = reinterpret_cast<const float4*>(x);
+        for (int64_t q = i; q < n / 4; q += stride) {
+            const float4 v = __ldg(x4 + q);
+            m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+        }
+        for (int64_t j = n / 4 * 4 + i; j < n; j += stride) m = fmaxf(m, fabsf(x[j]));
+    } else {
+        for (; i < n; i += stride) m = fmaxf(m, fabsf(x[i]));
+    }
+    block_absmax_to(m, slot);
 }
 static int launch_absmax(const float* x, int64_t n, float* slot, cudaStream_t stream) {
     if (n <= 0) return 0;
-    const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, 1184);
+    const unsigned grid = (unsigned)std::min<int64_t>((n / 4 + 255) / 256 + 1, 592);
     absmax_kernel<<<grid, 256, 0, stream>>>(x, n, slot);
     BRN_LAUNCH_OK("absmax_kernel");
     return 0;
@@ -58,15 +81,8 @@ bnn_bounds_kernel(const float* __restrict__ mu1, const float* __restrict__ rho1,
         if (i < n1) m1 = fmaxf(m1, fabsf(mu1[i]) + E * softplusf(rho1[i]));
         else m2 = fmaxf(m2, fabsf(mu2[i - n1]) + E * softplusf(rho2[i - n1]));
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
-        m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
-    }
-    if ((threadIdx.x & 31) == 0) {
-        if (m1 > 0.f) atomic_absmax(scal + SC_W1, m1);
-        if (m2 > 0.f) atomic_absmax(scal + SC_W2, m2);
-    }
+    block_absmax_to(m1, scal + SC_W1);
+    block_absmax_to(m2, scal + SC_W2);
 }
 
 // X [rows][cols] fp32 -> fp16 (hi, lo) pairs scaled by x_scale: row-major [rows][ldd] and transposed [cols][ldt]
@@ -1067,8 +1083,8 @@ eps_stats_kernel(const float* __restrict__ eps, int64_t lde, int64_t numel, int 
     e2[i] += a2;
 }
 
-// layer-1 finalisation of the fused path: gwT / gweT [P][HP] (backward GEMM epilogue) + e1 / e2 [H*P] (sampler) ->
-// closed-form prior / entropy terms, chain rule to (mu, rho), loss.  One thread per weight, element order (h, p).
+// layer-1 finalisation: sample-axis sums gw / gwe (HP > 0: stored transposed [P][HP] by the backward GEMM's epilogue; HP == 0:
+// natural [H*P] order) + e1 / e2 [H*P] (sampler) -> closed-form prior / entropy terms, chain rule to (mu, rho), loss.
 __global__ void __launch_bounds__(256)
 bnn_w1_finalize_kernel(brn_mf_var v, const float* __restrict__ gwT, const float* __restrict__ gweT, int HP, int P,
                        const float* __restrict__ e1, const float* __restrict__ e2, brn_sample_range r, int with_prior,
@@ -1078,7 +1094,7 @@ bnn_w1_finalize_kernel(brn_mf_var v, const float* __restrict__ gwT, const float*
     double elbo = 0.0;
     if (i < v.numel) {
         const int h = (int)(i / P), p = (int)(i - (int64_t)h * P);
-        const int64_t o = (int64_t)p * HP + h;
+        const int64_t o = HP > 0 ? (int64_t)p * HP + h : i;
         elbo = mf_finalize_element(v, i, gwT[o], gweT[o], e1[i], e2[i], r, with_prior);
     }
     const double tot = block_sum<double>(elbo, red);
@@ -1145,23 +1161,25 @@ struct BnnTcWorkspace {
 // measurements and tests (BRN_BNN_MID=4).
 static int bnn_tc_eval(const float* X, const int32_t* y, const BnnLayout& L, const brn_mf_var vars[4], const brn_sample_range* r,
                        const BnnTcWorkspace& ws, float* ws_eps, float* ws_W, float* ws_dW, float* ws_pre, float* ws_stats,
-                       int with_prior, double* loss, int drain, bool fused, cudaStream_t stream) {
+                       int with_prior, double* loss, int drain, int drain_bwd, bool fused, cudaStream_t stream) {
     constexpr int HP = BNN_UMMA_HP, NS = BNN_UMMA_NSAMP, BN = HP * NS;
     const int B = L.B, P = L.P, H = L.H, S = r->s_local;
     const int64_t numels[4] = {(int64_t)H * P, H, (int64_t)L.C * H, L.C};
     const int64_t offs[4] = {L.oW1, L.ob1, L.oW2, L.ob2};
     const float inv_S = 1.0f / (float)r->s_total;
+    bool fast_sampler = false;
     {
         StageTimer st("bnn.sample_weights", stream);
         BRN_CUDA_OK(cudaMemsetAsync(ws.scal, 0, sizeof(float) * ws.zero_floats, stream));
         // operand bounds (device scalars): injected noise is not bounded a priori
         if (vars[0].eps) if (int e = launch_absmax(vars[0].eps, (int64_t)S * numels[0], ws.scal + SC_EPS, stream)) return e;
         if (vars[2].eps) if (int e = launch_absmax(vars[2].eps, (int64_t)S * numels[2], ws.scal + SC_EPS, stream)) return e;
-        bnn_bounds_kernel<<<(unsigned)std::min<int64_t>((numels[0] + numels[2] + 255) / 256, 592), 256, 0, stream>>>(
+        bnn_bounds_kernel<<<(unsigned)std::min<int64_t>((numels[0] + numels[2] + 255) / 256, 296), 256, 0, stream>>>(
             vars[0].mu, vars[0].rho, numels[0], vars[2].mu, vars[2].rho, numels[2], ws.scal);
         BRN_LAUNCH_OK("bnn_bounds_kernel");
-        const bool fast = (P % 4 == 0) && ((uintptr_t)vars[0].mu % 16 == 0) && ((uintptr_t)vars[0].rho % 16 == 0) &&
-                          (!vars[0].eps || ((uintptr_t)vars[0].eps % 16 == 0));
+        fast_sampler = (P % 4 == 0) && ((uintptr_t)vars[0].mu % 16 == 0) && ((uintptr_t)vars[0].rho % 16 == 0) &&
+                       (!vars[0].eps || ((uintptr_t)vars[0].eps % 16 == 0));
+        const bool fast = fast_sampler;
         if (fast) {
             constexpr int SG = 8;
             dim3 grid((unsigned)(((int64_t)H * P / 4 + 255) / 256), (unsigned)((S + SG - 1) / SG));
@@ -1206,7 +1224,7 @@ static int bnn_tc_eval(const float* X, const int32_t* y, const BnnLayout& L, con
             StageTimer st("bnn.gemm_bwd", stream);      // dW1_s = dpre_s^T . X, folded over samples in the epilogue
             EpiSampleReduce::Params ep{ws.gwT, ws.gweT, ws_eps + offs[0], L.ldw, P, H, HP, S, ws.scal};
             if (int e = launch_umma_nt_kind<BN, BNN_UMMA_BK, EpiSampleReduce, 8, 0, 4, 1>(ws.Xth, ws.Xtl, P, ws.ldB, ws.dph, ws.dpl, S * HP,
-                                                                                          ws.ldB, B, 0, drain, ep, stream, true))
+                                                                                          ws.ldB, B, 0, drain_bwd, ep, stream, true))
                 return e;
         }
         StageTimer st5("bnn.reduce_finalize", stream);
@@ -1252,7 +1270,7 @@ static int bnn_tc_eval(const float* X, const int32_t* y, const BnnLayout& L, con
         ep.blk_valid = H; ep.col_limit = 0; ep.total_blks = S;
         ep.bound_a = ws.scal + SC_X; ep.bound_b = ws.scal + SC_W2; ep.bound_b_mult = 2.f;
         if (int e = launch_umma_nt_kind<BN, BNN_UMMA_BK, EpiStore, 8, 0, 4, 1>(ws.Xth, ws.Xtl, P, ws.ldB, ws.dph, ws.dpl, S * HP, ws.ldB, B,
-                                                                               0, drain, ep, stream, true))
+                                                                               0, drain_bwd, ep, stream, true))
             return e;
     }
     StageTimer st5("bnn.reduce_finalize", stream);
