@@ -304,7 +304,9 @@ def main_reference(args):
 # our arm
 # ---------------------------------------------------------------------------------------------
 def main_ours(args):
-    from brancher_b200 import _cuda as cu
+    from brancher_b200 import _cuda as cu, distributed
+    if os.environ.get("BRN_BENCH_NCCL_ALLREDUCE"):
+        distributed.oneshot_enabled = False
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -394,7 +396,7 @@ def main_ours(args):
         y = None
         Xpin, ypin = X.cpu().pin_memory(), None
         h2d = Xpin.numel() * 4
-        gflat = torch.zeros(pvec.numel() + 4, device=dev)
+        gflat = torch.zeros((pvec.numel() + 3) // 4 * 4 + 4, device=dev)
         mvars = []
         # algorithmic bytes of one evaluation: program table + parameters + observed row in, gradients + loss out
         algo_bytes = {"dag.fused": float(ops.numel() + 2 * pvec.numel() * 4 + X.numel() * 4 + 8)}
@@ -466,10 +468,8 @@ def main_ours(args):
         buffer the kernels accumulated into (the loss travels as a hi/lo fp32 pair to keep ~fp64 accuracy)."""
         if world == 1:
             return loss
-        hi = loss.float()
-        gflat[-4:-2] = torch.cat([hi, (loss - hi.double()).float()])
-        dist.all_reduce(gflat)
-        return gflat[-4].double() + gflat[-3].double()
+        distributed.all_reduce_flat(gflat, loss)      # one-shot peer-memory kernel (csrc/allreduce.cu); NCCL if unavailable
+        return loss
 
     def step(it):
         return reduce_partials(device_step(it))
@@ -509,14 +509,24 @@ def main_ours(args):
                 graph_body()
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize()
+            red_out = [None]
+
+            def graph_full(*a, **k):
+                graph_body(*a, **k)
+                red_out[0] = reduce_partials(loss_buf)      # world > 1: the one-shot all-reduce kernels are part of the graph
+
+            graph_full()                                    # builds the symmetric buffers (rendezvous) outside the capture
+            torch.cuda.synchronize()
+            can_graph = world == 1 or any(distributed._oneshot.values())
+        if not os.environ.get("BRN_BENCH_NO_GRAPH") and can_graph:
             g_eval = torch.cuda.CUDAGraph()
             l0 = cu.launch_count()
             with torch.cuda.graph(g_eval):
-                graph_body()
+                graph_full()
             launches_per_graph = cu.launch_count() - l0 + 3          # + the two zero fills and the offset bump
             def graph_step(it):
                 g_eval.replay()
-                return reduce_partials(loss_buf)
+                return red_out[0]
             # end to end: the minibatch copy from pinned host memory is a branch of the same graph, joined just before the
             # evaluation's first read of X (brn_set_data_ready_event): noise + weight sampling run under the copy
             try:
@@ -528,11 +538,11 @@ def main_ours(args):
                         Xstage.copy_(Xpin, non_blocking=True)
                         ystage.copy_(ypin, non_blocking=True)
                         copy_done.record(copy_stream)
-                    graph_body(Xstage, ystage, data_ready=copy_done)
+                    graph_full(Xstage, ystage, data_ready=copy_done)
                     cap.wait_stream(copy_stream)
                 def graph_e2e(it):
                     g_e2e.replay()
-                    return float(reduce_partials(loss_buf).item())
+                    return float(red_out[0].item())
             except Exception as exc:                        # pragma: no cover - falls back to the step-by-step e2e path
                 sys.stderr.write("bench: e2e graph capture failed (%s); using the step-by-step path\n" % exc)
                 graph_e2e = None
@@ -568,6 +578,29 @@ def main_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item(), launches, stages
 
+    # strong scaling (C3 shards the MC samples): the SAME global problem, S = 256 samples in total, S / N per GPU
+    strong_step = None
+    if wl == "bnn" and world > 1 and graph_step is not None and cfg["S"] % world == 0:
+        Ss = cfg["S"] // world
+        r_strong = cu.sample_range(cfg["S"], s0=rank * Ss, s_local=Ss, seed=args.seed, offset=0, offset_dev=offset_dev)
+
+        def strong_body():
+            gflat.zero_()
+            loss_buf.zero_()
+            cu.bnn_elbo_fwd_bwd(X, y, mvars, r_strong, loss=loss_buf)
+            offset_dev.add_(1)
+            red_out[0] = reduce_partials(loss_buf)
+
+        strong_body()
+        torch.cuda.synchronize()
+        g_strong = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_strong):
+            strong_body()
+
+        def strong_step(it):
+            g_strong.replay()
+            return red_out[0]
+
     clocks = ClockSampler(local_rank)
     clocks.start()
     # Headline pass: EXACTLY K steps, nothing but the product's own launches in the timed region.  The per-stage CUDA events of
@@ -579,6 +612,7 @@ def main_ours(args):
         launches = launches_per_graph * args.steps
     ms_prof, _, stages = timed(step, args.steps, 1, profile=True)
     clk = clocks.stop()
+    ms_strong = timed(strong_step, args.steps, args.warmup)[0] if strong_step else None
     ms_e2e, _, _ = timed(graph_e2e or (lambda i: e2e_step(i)), max(3, min(args.steps, 50)), 3)
     n_e2e = max(3, min(args.steps, 50))
 
@@ -636,6 +670,13 @@ def main_ours(args):
                        "ms_per_step": ms_e2e / n_e2e},
                "roofline": roof,
                }
+        if ms_strong is not None:
+            out["strong"] = {"global_samples": cfg["S"], "samples_per_gpu": cfg["S"] // world, "ms_per_step": ms_strong / args.steps,
+                             "value": cfg["S"] * cfg["B"] * args.steps / (ms_strong * 1e-3), "unit": UNIT,
+                             "note": "same global problem as the 1-GPU run (S = 256): speed-up = 1-GPU ms_per_step / this"}
+        if world > 1:
+            out["config"]["collective"] = ("one-shot all-reduce over NVLink peer memory (csrc/allreduce.cu), inside the captured "
+                                           "step" if any(distributed._oneshot.values()) else "NCCL all_reduce")
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = run_cpu_baseline(wl, cfg)
         emit(out)

@@ -183,13 +183,16 @@ class Plan:
         params = [p for spec in self.latents for p in spec.parameters()]
 
         def runner():
-            _, sinks = cu.flat_grad_views([int(np.prod(spec.shape)) for spec in self.latents], config.device)
+            flat, sinks = cu.flat_grad_views([int(np.prod(spec.shape)) for spec in self.latents], config.device)
             mvars = [spec.make(cu, i, eps, sk) for i, (spec, eps, sk) in enumerate(zip(self.latents, self._eps(S_local, s0), sinks))]
             loss = self._launch(cu, mvars, r, empirical_samples)
+            if distributed.world_size() > 1:
+                # ONE collective on the flat buffer the kernels accumulated into; the fp64 loss rides in its spare tail as a
+                # (hi, lo) fp32 pair
+                distributed.all_reduce_flat(flat, loss)
             grads = []
             for spec, v in zip(self.latents, mvars):
                 grads += [v.dmu.reshape(spec.loc_root.value.shape), v.drho.reshape(spec.scale_root.value.shape)]
-            loss, grads = distributed.all_reduce_partials(loss, grads)
             return loss, [g if p.requires_grad else None for g, p in zip(grads, params)]
 
         return _FusedELBO.apply(runner, *params)

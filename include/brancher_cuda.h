@@ -314,6 +314,19 @@ int brn_opt_step(const brn_opt_tensor* table_dev, const int64_t* prefix_dev, int
                  const brn_opt_hyper* hyper, const double* loss_dev, int64_t* counters_dev, float* curve_dev,
                  int64_t curve_len, uint64_t* offset_dev, void* stream);
 
+/* One-shot all-reduce (sum) of a small fp32 buffer over peer memory (NVLink / NVSwitch), SURVEY 8e.  The reference has no
+ * collective (single process, brancher/inference.py:50-111 runs on one device); this is the exchange step that finishes a
+ * sample- / row-sharded evaluation: out[i] = sum_r src_r[i], summed in rank order on every rank (bit-identical results).
+ * bufs_dev: DEVICE array [2 * world] of pointers, bufs[p * world + r] = rank r's symmetric buffer of parity p (n floats each,
+ * 16-byte aligned, mapped into this process); flags_dev: DEVICE array [world], flags[r] = rank r's flag array (world
+ * uint64, zero-initialised); state_dev: LOCAL device uint64[2], zero-initialised: {epoch, (ticket, time-out count)}.
+ * loss_inout (optional, device fp64 [1]): the partial loss travels in the buffer's LAST quad (elements n-4, n-3; needs
+ * n % 4 == 0, the caller's src keeps that quad spare) as a (hi, lo) fp32 pair and is returned summed over ranks.
+ * All ranks must issue the same sequence of calls.  Enqueues two kernels; capturable in a CUDA graph. */
+int brn_allreduce_oneshot(const float* src, float* out, int64_t n, float* const* bufs_dev,
+                          unsigned long long* const* flags_dev, int rank, int world, uint64_t* state_dev,
+                          double* loss_inout, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
