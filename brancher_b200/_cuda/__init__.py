@@ -220,6 +220,8 @@ class MeanFieldVar:
         self.mu = mu.detach().reshape(-1).contiguous()
         self.rho = rho.detach().reshape(-1).contiguous()
         self.numel = self.mu.numel()
+        if self.rho.numel() != self.numel:
+            raise BrancherCudaError("MeanFieldVar: rho has %d elements, mu has %d" % (self.rho.numel(), self.numel))
         self.var_id = int(var_id)
         self.tied = prior_loc is None
         dev = self.mu.device
@@ -326,6 +328,10 @@ def linear_elbo_fwd_bwd(X, y, likelihood, w, C, r, with_prior=True, loss=None):
     """K2.  X [N,F] fp32; y [N] fp32 {0,1} (BERNOULLI, C=1) or int32 labels (CATEGORICAL); w MeanFieldVar [C,F]."""
     dev = X.device
     N, F = X.shape
+    if w.numel != C * F:
+        raise BrancherCudaError("linear_elbo_fwd_bwd: weights have %d elements, expected C*F = %d*%d" % (w.numel, C, F))
+    if y.numel() != N:
+        raise BrancherCudaError("linear_elbo_fwd_bwd: y has %d entries for %d rows (labels / targets, not one-hot)" % (y.numel(), N))
     loss = torch.zeros(1, dtype=torch.float64, device=dev) if loss is None else loss
     _check_eps(w, r)
     nbytes = lib().brn_linear_workspace_bytes(N, F, C, r.s_local)
@@ -417,6 +423,10 @@ def linear_particles_loss_grad(X, y, likelihood, theta, C, prior_loc=None, prior
     N, F = X.shape
     n = theta.shape[0]
     theta = theta.reshape(n, -1)
+    if theta.shape[1] != C * F:
+        raise BrancherCudaError("linear_particles_loss_grad: particles have %d elements, expected C*F = %d*%d" % (theta.shape[1], C, F))
+    if y.numel() != N:
+        raise BrancherCudaError("linear_particles_loss_grad: y has %d entries for %d rows" % (y.numel(), N))
     loss = torch.zeros(1, dtype=torch.float64, device=dev) if loss is None else loss
     G = torch.empty_like(theta)
     ydt = torch.float32 if likelihood == BERNOULLI else torch.int32

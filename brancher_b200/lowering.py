@@ -104,6 +104,10 @@ class MeanFieldSpec:
         if self.loc_root is None or self.scale_root is None:
             raise UnsupportedModelError("latent %r: q's loc/scale must be (learnable) roots" % name)
         self.shape = tuple(self.loc_root._value.shape[2:])
+        if self.scale_root._value.numel() != self.loc_root._value.numel():
+            raise UnsupportedModelError("latent %r: q's scale has %d elements, its loc %d -- the mean-field kernels need one "
+                                        "scale per element (pass a scale array of the variable's shape)"
+                                        % (name, self.scale_root._value.numel(), self.loc_root._value.numel()))
         lp = p_var.partial_links
         p_loc_root, p_scale_sp = _as_root(lp["loc"].expr), _softplus_root(lp["scale"].expr)
         p_scale_raw = _as_root(lp["scale"].expr)
@@ -118,11 +122,23 @@ class MeanFieldSpec:
                              and p_scale_sp is not None):
             raise UnsupportedModelError("latent %r: unexpected root-name collision pattern" % name)
         self.tied = tied_loc
-        self.prior_loc = self.prior_scale = None
-        if not self.tied:
-            self.prior_loc = p_loc_root.value.detach()
-            sc = p_scale_root.value.detach()
-            self.prior_scale = torch.nn.functional.softplus(sc) if p_scale_sp is not None else sc
+        self._p_loc_root, self._p_scale_root, self._p_scale_softplus = p_loc_root, p_scale_root, p_scale_sp is not None
+        if not self.tied and (getattr(p_loc_root, "learnable", False) or getattr(p_scale_root, "learnable", False)):
+            # ReverseKL optimises the joint model's learnable parameters too (learnable_model = True); the fused kernels
+            # return no gradient for a prior's own hyper-parameters, so training them silently would freeze them
+            raise UnsupportedModelError("latent %r: learnable hyper-parameters of an untied prior are not lowered" % name)
+
+    # the declared prior is read at EVALUATION time (a constant root may be re-assigned between evaluations)
+    @property
+    def prior_loc(self):
+        return None if self.tied else self._p_loc_root.value.detach()
+
+    @property
+    def prior_scale(self):
+        if self.tied:
+            return None
+        sc = self._p_scale_root.value.detach()
+        return torch.nn.functional.softplus(sc) if self._p_scale_softplus else sc
 
     def parameters(self):
         return [self.loc_root.value, self.scale_root.value]
@@ -738,16 +754,232 @@ class DagPlan(Plan):
         return SimpleNamespace(params=params, grads=[dparams[i:i + 1] for i in range(len(params))], loss=loss, launch=launch)
 
 
+# ---------------------------------------------------------------------------------------------------
+# K5: amortised VAE family (examples/VAE_playground.py:30-80)
+# ---------------------------------------------------------------------------------------------------
+def _module_call(expr):
+    """ModuleCall(nn.Module, [one argument]) -> (module, argument expr) or None"""
+    from brancher_b200.variables import ModuleCall
+    if isinstance(expr, ModuleCall) and isinstance(expr.fn, torch.nn.Module) and len(expr.args) == 1 and not expr.kwargs:
+        return expr.fn, expr.args[0]
+    return None
+
+
+def _index_of(expr, key):
+    """Index(VarRef(var), key) -> var (a DeterministicVariable holding a dict-valued module output) or None"""
+    from brancher_b200.variables import Index
+    if isinstance(expr, Index) and expr.key == key and isinstance(expr.base, VarRef):
+        return expr.base.var
+    return None
+
+
+def _identify_relu_mlp(module, n_in, heads, what):
+    """Recover the layer structure of a user-written nn.Module (its __call__ is opaque Python, functions.py:9-45) for the K5
+    kernels: hidden layers Linear -> ReLU in registration order, then one Linear per requested head.  `heads` maps the
+    module's output keys to a post-processing tag: "id" (the raw head) or "softplus+c" (softplus(head) + constant c, the
+    encoder's sd, VAE_playground.py:44-46).  The hypothesis is VERIFIED numerically on a random probe batch, so a module that
+    computes anything else is rejected instead of silently mis-lowered.  Returns (hidden [(Linear)], {key: Linear}, c)."""
+    linears = [m for m in module.modules() if isinstance(m, torch.nn.Linear)]
+    nh = len(heads)
+    if len(linears) < nh + 1:
+        raise UnsupportedModelError("%s: expected at least %d nn.Linear layers, found %d" % (what, nh + 1, len(linears)))
+    hidden, head_layers = linears[:-nh], linears[-nh:]
+    dims = [n_in] + [l.out_features for l in hidden]
+    if any(l.in_features != d for l, d in zip(hidden, dims[:-1])) or any(h.in_features != dims[-1] for h in head_layers):
+        raise UnsupportedModelError("%s: the nn.Linear layers do not form a chain %s -> heads" % (what, dims))
+    import itertools
+    dev = hidden[0].weight.device
+    g = torch.Generator().manual_seed(1234)
+    probe = torch.rand(6, n_in, generator=g).to(dev)
+    with torch.no_grad():
+        try:
+            out = module(probe.unsqueeze(-1)) if what.startswith("encoder") else module(probe)
+        except Exception as exc:
+            raise UnsupportedModelError("%s: probing the module failed (%s)" % (what, exc))
+        if not isinstance(out, dict) or any(k not in out for k in heads):
+            raise UnsupportedModelError("%s: the module must return a dict with keys %s" % (what, sorted(heads)))
+        h = probe
+        for l in hidden:
+            h = torch.relu(torch.nn.functional.linear(h, l.weight, l.bias))
+        for perm in itertools.permutations(head_layers):
+            ok, c_found = True, 0.0
+            for (key, tag), l in zip(sorted(heads.items()), perm):
+                raw = torch.nn.functional.linear(h, l.weight, l.bias)
+                got = out[key].reshape(raw.shape)
+                if tag == "id":
+                    ok = ok and torch.allclose(got, raw, rtol=1e-5, atol=1e-6)
+                else:
+                    d = got - torch.nn.functional.softplus(raw)
+                    c_found = round(float(d.median()), 6)
+                    ok = ok and float((d - c_found).abs().max()) < 1e-5 and c_found > -1e-6
+            if ok:
+                return hidden, dict(zip(sorted(heads), perm)), max(c_found, 0.0)
+    raise UnsupportedModelError("%s: the module is not a ReLU MLP with linear heads %s (numerical probe mismatch)" % (what, sorted(heads)))
+
+
+class VaePlan:
+    """x ~ Binomial(1, logits = decoder(z)["mean"]), z ~ N(0, I); q: x = minibatch of an EmpiricalVariable,
+    z ~ N(encoder(x)["mean"], encoder(x)["sd"]) -- examples/VAE_playground.py:65-80 -> brn_vae_elbo_fwd_bwd (K5).
+    The same minibatch is shared by all MC samples; gradients land in the nn.Modules' parameters."""
+    family = "vae (K5)"
+
+    def __init__(self, joint, posterior, x_q, z_name, enc, dec):
+        self.joint, self.posterior, self.x_q, self.z_name = joint, posterior, x_q, z_name
+        (self.enc_hidden, enc_heads, self.sd_offset), (self.dec_hidden, dec_heads, _) = enc, dec
+        self.enc_mean, self.enc_sd, self.dec_out = enc_heads["mean"], enc_heads["sd"], dec_heads["mean"]
+        self._net = None
+
+    def layers(self):
+        return list(self.enc_hidden) + [self.enc_mean, self.enc_sd] + list(self.dec_hidden) + [self.dec_out]
+
+    def parameters(self):
+        return [p for l in self.layers() for p in (l.weight, l.bias)]
+
+    def _network(self, cu):
+        key = tuple(p.data_ptr() for p in self.parameters())
+        if self._net is None or self._net_key != key:
+            wb = lambda l: (l.weight, l.bias)
+            self._net = cu.VaeNet([wb(l) for l in self.enc_hidden], wb(self.enc_mean), wb(self.enc_sd),
+                                  [wb(l) for l in self.dec_hidden], wb(self.dec_out), sd_offset=self.sd_offset)
+            self._net_key = key
+        return self._net
+
+    def static_minibatch(self):
+        """True when every evaluation sees the same rows (EmpiricalVariable(indices=...) with constant indices)"""
+        idx = [p for p in self.x_q.parents if p.name.endswith("_indices")]
+        return bool(idx) and all(isinstance(p, RootVariable) for p in idx)
+
+    def _minibatch(self, empirical_samples):
+        # x is observed in q, not in p: the reference draws it as part of the sampler (gradient_estimators.py:41), ONE draw
+        # shared by all MC samples here (SURVEY 8d C5)
+        t = empirical_samples[self.x_q] if self.x_q in empirical_samples else \
+            self.x_q._get_sample(1, observed=False, differentiable=False)[self.x_q]
+        if not torch.is_tensor(t) or t.shape[0] != 1:
+            raise UnsupportedModelError("vae family: the minibatch must be shared by all MC samples (singleton sample axis), got "
+                                        "shape %s" % (tuple(t.shape),))
+        return t.reshape(t.shape[1], -1).to(torch.float32).contiguous()
+
+    def _run(self, cu, net, X, r, eps, loss=None):
+        row0, nb = distributed.shard(X.shape[0])
+        net.zero_grads()
+        loss = cu.vae_elbo_fwd_bwd(X[row0:row0 + nb].contiguous(), net, r, eps=None if eps is None else eps[:, row0:row0 + nb],
+                                   var_id=0, row0=row0, B_total=X.shape[0], add_constant=(distributed.rank() == 0), loss=loss)
+        if distributed.world_size() > 1:
+            distributed.all_reduce_flat(net.flat, loss)
+        return loss
+
+    def elbo(self, number_samples, empirical_samples):
+        if config.device.type != "cuda":
+            raise RuntimeError("brancher_b200 evaluates the ELBO only on CUDA devices (no CPU fallback); "
+                               "config.device is %s" % config.device)
+        from brancher_b200 import _cuda as cu
+        cu.lib()
+        r = cu.sample_range(number_samples, seed=config.seed, offset=config.next_offset())
+        params = self.parameters()
+
+        def runner():
+            net = self._network(cu)
+            X = self._minibatch(empirical_samples)
+            eps = None
+            if _INJECTED is not None:
+                if self.z_name not in _INJECTED:
+                    raise KeyError("inject_noise: no noise given for q variable %r" % self.z_name)
+                eps = torch.as_tensor(_INJECTED[self.z_name], dtype=torch.float32, device=config.device).reshape(
+                    number_samples, X.shape[0], -1)
+            loss = self._run(cu, net, X, r, eps)
+            grads = [g.clone() for pair in net.grads for g in pair]
+            return loss, [g.reshape(p.shape) if p.requires_grad else None for g, p in zip(grads, params)]
+
+        return _FusedELBO.apply(runner, *params)
+
+    def static_evaluation(self, number_samples, empirical_samples, offset_dev):
+        from types import SimpleNamespace
+        from brancher_b200 import _cuda as cu
+        cu.lib()
+        if distributed.world_size() != 1 or _INJECTED is not None or not self.static_minibatch():
+            return None
+        r = cu.sample_range(number_samples, seed=config.seed, offset=config.next_offset(), offset_dev=offset_dev)
+        net = self._network(cu)
+        net.zero_grads()
+        X = self._minibatch(empirical_samples)
+        loss = torch.zeros(1, dtype=torch.float64, device=config.device)
+        params = self.parameters()
+        grads = [g.reshape(-1) if g.is_contiguous() else g for pair in net.grads for g in pair]
+
+        def launch():
+            loss.zero_()
+            self._run(cu, net, X, r, None, loss=loss)
+
+        return SimpleNamespace(params=params, grads=grads, loss=loss, launch=launch)
+
+
+def _lower_vae(joint, posterior):
+    q_by_name = {v.name: v for v in posterior._flatten()}
+    xs = [v for v in joint._flatten() if isinstance(v, RandomVariable) and v.distribution.kind in ("binomial", "bernoulli")]
+    if len(xs) != 1:
+        raise UnsupportedModelError("vae family: exactly one Binomial / Bernoulli likelihood node expected")
+    x = xs[0]
+    if x.distribution.kind == "binomial":
+        tc = _as_root(x.partial_links["total_count"].expr)
+        if tc is None or tc.value.numel() != 1 or float(tc.value.reshape(-1)[0]) != 1.0:
+            raise UnsupportedModelError("vae family: Binomial likelihood is lowered only for total_count=1")
+    if "logits" not in x.partial_links:
+        raise UnsupportedModelError("vae family: the likelihood must be parameterised by logits")
+    dec_out = _index_of(x.partial_links["logits"].expr, "mean")
+    if dec_out is None or getattr(dec_out, "distribution", None) is None or dec_out.distribution.kind != "deterministic":
+        raise UnsupportedModelError("vae family: logits must be DeterministicVariable(decoder(z))['mean']")
+    mc = _module_call(dec_out.partial_links["value"].expr)
+    z = _var(mc[1]) if mc else None
+    if mc is None or z is None or not isinstance(z, RandomVariable) or z.distribution.kind != "normal":
+        raise UnsupportedModelError("vae family: the decoder must be a BrancherFunction(nn.Module) applied to a Normal latent")
+    decoder = mc[0]
+    zl, zs = _as_root(z.partial_links["loc"].expr), (_softplus_root(z.partial_links["scale"].expr) or _as_root(z.partial_links["scale"].expr))
+    if zl is None or zs is None or getattr(zl, "learnable", False) or getattr(zs, "learnable", False):
+        raise UnsupportedModelError("vae family: the latent prior must have constant parameters")
+    sc = torch.nn.functional.softplus(zs.value) if _softplus_root(z.partial_links["scale"].expr) is not None else zs.value
+    if float(zl.value.abs().max()) != 0.0 or float((sc - 1.0).abs().max()) > 1e-6:
+        raise UnsupportedModelError("vae family: only the standard-normal latent prior N(0, I) is lowered")
+    L = int(zl.value.numel())
+    # posterior side
+    qz, qx = q_by_name.get(z.name), q_by_name.get(x.name)
+    if qz is None or qx is None or qz.distribution.kind != "normal" or qx.distribution.kind != "empirical" or not qx.is_observed:
+        raise UnsupportedModelError("vae family: the posterior needs an observed EmpiricalVariable %r and a Normal %r" % (x.name, z.name))
+    enc_out = _index_of(qz.partial_links["loc"].expr, "mean")
+    if enc_out is None or _index_of(qz.partial_links["scale"].expr, "sd") is not enc_out or \
+            enc_out.distribution.kind != "deterministic":
+        raise UnsupportedModelError("vae family: q(z) must be Normal(encoder_output['mean'], encoder_output['sd'])")
+    mc = _module_call(enc_out.partial_links["value"].expr)
+    if mc is None or _var(mc[1]) is not qx:
+        raise UnsupportedModelError("vae family: the encoder must be a BrancherFunction(nn.Module) applied to the EmpiricalVariable")
+    encoder = mc[0]
+    if set(v.name for v in _latent_random_variables(joint)) - {z.name, x.name}:
+        raise UnsupportedModelError("vae family: unexpected additional latent variables")
+    D = int(np.prod(qx.distribution.dataset.shape[1:])) if hasattr(qx.distribution, "dataset") else None
+    if D is None:
+        lin = [m for m in encoder.modules() if isinstance(m, torch.nn.Linear)]
+        D = lin[0].in_features if lin else 0
+    enc = _identify_relu_mlp(encoder, D, {"mean": "id", "sd": "softplus+c"}, "encoder")
+    dec = _identify_relu_mlp(decoder, L, {"mean": "id"}, "decoder")
+    if enc[1]["mean"].out_features != L or dec[1]["mean"].out_features != D:
+        raise UnsupportedModelError("vae family: encoder / decoder widths do not match the data (%d) and latent (%d) sizes" % (D, L))
+    return VaePlan(joint, posterior, qx, z.name, enc, dec)
+
+
+
 def lower(joint, posterior):
-    """Pick the kernel family: the dense families (K2 linear, K3 BNN) by pattern, else the scalar-DAG family (K1)."""
+    """Pick the kernel family: the dense families (K2 linear, K3 BNN) by pattern, the amortised VAE (K5), else the
+    scalar-DAG family (K1)."""
     try:
         return _lower_dense(joint, posterior)
     except UnsupportedModelError as dense_err:
         try:
-            return DagPlan(joint, posterior)
-        except UnsupportedModelError as dag_err:
-            raise UnsupportedModelError("model graph is not recognised by any fused kernel family.\n  dense (K2/K3): %s\n"
-                                        "  scalar DAG (K1): %s" % (dense_err, dag_err)) from None
+            return _lower_vae(joint, posterior)
+        except UnsupportedModelError as vae_err:
+            try:
+                return DagPlan(joint, posterior)
+            except UnsupportedModelError as dag_err:
+                raise UnsupportedModelError("model graph is not recognised by any fused kernel family.\n  dense (K2/K3): %s\n"
+                                            "  vae (K5): %s\n  scalar DAG (K1): %s" % (dense_err, vae_err, dag_err)) from None
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -945,8 +1177,14 @@ def get_particle_plan(joint, particles):
     return plan
 
 
+def _observation_signature(joint):
+    """which variables are observed (and how): a plan bakes this in, so observe() / unobserve() after the first evaluation
+    must not reuse it"""
+    return tuple(sorted((v.name, bool(getattr(v, "has_observed_value", False))) for v in joint._flatten() if v.is_observed))
+
+
 def get_plan(joint, posterior):
-    key = id(posterior)
+    key = (id(posterior), _observation_signature(joint))
     plan = joint._plans.get(key)
     if plan is None or plan.posterior is not posterior:
         plan = lower(joint, posterior)

@@ -197,3 +197,49 @@ def test_wvgd_perform_inference_runs():
     curve = model.diagnostics["loss curve"]
     assert curve.shape == (30,) and np.isfinite(curve).all()
     assert curve[-5:].mean() < curve[:5].mean()
+
+
+@pytest.mark.parametrize("tag,kw", [("vae_small", dict(seed=12, B=6, D=12, L=2, h_enc=(5, 7), h_dec=(7, 5))),
+                                    ("vae_deep", dict(seed=13, B=10, D=20, L=3, h_enc=(9,), h_dec=(6, 8, 5)))])
+def test_vae_same_script_same_numbers(ns, tag, kw):
+    """C5 through the Brancher API (examples/VAE_playground.py:65-80): the model-construction script that produced the golden
+    vectors with the reference -- BrancherFunction(nn.Module) encoder / decoder, Index links -- runs against brancher_b200,
+    lowers to K5 (lowering.VaePlan) and reproduces the reference's loss (incl. the -ln S constant) and every module
+    parameter's gradient."""
+    from brancher_b200 import lowering
+    g = load_golden(tag)
+    model, Q, d = zoo.vae(ns, **kw)
+    d["enc"].to("cuda:0"); d["dec"].to("cuda:0")
+    S = g["eps"]["z"].shape[0]
+    with lowering.inject_noise({"z": g["eps"]["z"]}):
+        loss = ns.inference.ReverseKL().compute_loss(model, model.posterior_model, None, S)
+    assert lowering.get_plan(model, model.posterior_model).family.startswith("vae")
+    loss.backward()
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("make_golden_names", os.path.join(os.path.dirname(__file__), "golden", "make_golden.py"))
+    grads = {}
+    for side, net, heads in (("enc", d["enc"], (("W_mean", "l_mean"), ("W_sd", "l_sd"))), ("dec", d["dec"], (("W_out", "l_out"),))):
+        for i, l in enumerate(net.hidden):
+            grads["%s.W.%d" % (side, i)] = l.weight.grad.cpu().numpy()
+            grads["%s.b.%d" % (side, i)] = l.bias.grad.cpu().numpy()
+        for key, attr in heads:
+            grads["%s.%s" % (side, key)] = getattr(net, attr).weight.grad.cpu().numpy()
+            grads["%s.b%s" % (side, key[1:])] = getattr(net, attr).bias.grad.cpu().numpy()
+    from oracle import elbo_oracle as O
+    from helpers import vae_nets
+    enc, dec = vae_nets(g)
+    o64 = O.vae_elbo(g["raw"]["X"], enc, dec, g["eps"]["z"], dtype=torch.float64)
+    check_against_oracle(float(loss.detach()), grads, (float(g["raw"]["loss"]), g["grad"]), o64, tag + " via API vs reference")
+
+
+def test_vae_perform_inference_runs_and_improves(ns):
+    """the VAE trains through perform_inference (graph-captured loop: K5 evaluation + fused Adam over the modules' parameters)"""
+    from brancher_b200 import config, inference
+    config.set_seed(5)
+    model, Q, d = zoo.vae(ns, 21, B=64, D=30, L=2, h_enc=(16,), h_dec=(16,))
+    d["enc"].to("cuda:0"); d["dec"].to("cuda:0")
+    inference.perform_inference(model, number_iterations=150, number_samples=8, optimizer="Adam", lr=0.01,
+                                inference_method=inference.ReverseKL())
+    curve = np.asarray(model.diagnostics["loss curve"]).reshape(-1)
+    assert inference.last_loop == "graph"
+    assert np.isfinite(curve).all() and curve[-20:].mean() < curve[:20].mean()
