@@ -296,5 +296,14 @@ class WassersteinVariationalGradientDescent(InferenceMethod):
 
     def post_process(self, joint_model):
         """Ensemble weights (inference.py:234-247): softmax over samplers of the log normaliser of the importance weights,
-        log sum_s exp(log p - log q_k) over `number_post_samples` truncated draws -- not lowered yet."""
-        self.weights = None
+        log sum_s exp(log p - log q_k) over `number_post_samples` truncated draws -- evaluated on the device
+        (lowering.WvgdPlan.ensemble_weights).  `weights` is a numpy array as in the reference; `log_normalizers` and
+        `accepted_post` (accepted draws per sampler) are kept for inspection."""
+        from brancher_b200 import lowering
+        plan = lowering.get_wvgd_plan(joint_model, self.particles, self.sampler_model)
+        joint_model.update_observed_submodel()
+        empirical = joint_model.observed_submodel._get_sample(1, observed=True, differentiable=False)
+        w, logZ, counts = plan.ensemble_weights(empirical, self.number_post_samples, self.first_column_only)
+        self.weights = w.cpu().numpy()
+        self.log_normalizers = logZ.cpu().numpy()
+        self.accepted_post = counts.cpu().numpy()

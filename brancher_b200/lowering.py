@@ -1159,6 +1159,68 @@ class WvgdPlan:
         return _WvgdLoss.apply(runner, *params)
 
 
+def _wvgd_ensemble_weights(self, empirical, number_post_samples, first_column_only, chunk=8192, max_redraws=8):
+    """WassersteinVariationalGradientDescent.post_process (inference.py:234-247) on the device: per sampler k the log
+    normaliser of the importance weights of its truncated draws,  logZ_k = log sum_{s accepted} exp(log p(z_ks, data) -
+    log q_k(z_ks))  (get_importance_weights, variables.py:821-841: unnormalised q log-prob, no division by the count), and
+    the ensemble weights softmax_k(logZ_k).  Draws + Voronoi owner: K6a; log-likelihood of every draw: K6b; the masked
+    log-sum-exp over [P, S] is a handful of torch reductions.  A sampler without any accepted draw is re-drawn (the
+    reference loops until one is accepted, transformations.py:28-43).  Returns (weights [P], logZ [P], counts [P])."""
+    from brancher_b200 import _cuda as cu
+    cu.lib()
+    pp = self.pplan
+    n = len(pp.roots)
+    dev = config.device
+    X = _data_matrix(empirical[pp.x_var], "x")
+    yv = empirical[pp.k].reshape(-1)
+    y = yv.to(torch.float32).contiguous() if pp.likelihood == cu.BERNOULLI else yv.to(torch.int32).contiguous()
+    theta = pp.stacked()
+    loc = torch.stack([p.value.detach().reshape(-1) for p in self.loc_roots]).contiguous()
+    scalar = self.scale_roots[0]._value.numel() == 1
+    rho = torch.stack([p.value.detach().reshape(-1) for p in self.scale_roots]).contiguous()
+    rho = rho.reshape(n) if scalar else rho
+    d = loc.shape[1]
+    F_last = d // pp.C
+    injected = None
+    if _INJECTED is not None:
+        injected = torch.as_tensor(_INJECTED["post"], dtype=torch.float32, device=dev).reshape(n, number_post_samples, d)
+    logZ = torch.full((n,), float("-inf"), dtype=torch.float64, device=dev)
+    counts = torch.zeros(n, dtype=torch.int64, device=dev)
+    ids = torch.arange(n, device=dev, dtype=torch.int32)[:, None]
+    sg = torch.nn.functional.softplus(rho).to(torch.float64)
+    log_sg_sum = (torch.log(sg) * (d if scalar else 1)).reshape(n, -1).sum(1)          # sum_i log sigma_ki
+    done, redraws = 0, 0
+    while done < number_post_samples or (injected is None and redraws < max_redraws and bool((counts == 0).any())):
+        S = min(chunk, number_post_samples - done) if done < number_post_samples else min(chunk, number_post_samples)
+        if done >= number_post_samples:
+            redraws += 1
+        eps = None if injected is None else injected[:, done:done + S].contiguous()
+        r = cu.sample_range(S, seed=config.seed, offset=config.next_offset())
+        Z, e, owner = cu.wvgd_sample_assign(loc, rho, theta, S, F_last, r, 0, eps, first_column_only)
+        ll, _ = cu.linear_vectors_loglik_grad(X, y, pp.likelihood, Z.reshape(n * S, d), pp.C, False)
+        logw = ll.reshape(n, S)
+        if not self.tied:          # tied: the prior's roots take sampler k's values, log p(z) == log q_k(z) and the pair cancels
+            c = 0.5 * float(np.log(2 * np.pi))
+            logq = (-0.5 * e.to(torch.float64) ** 2).sum(2) - log_sg_sum[:, None] - d * c
+            pl, ps = pp.prior_loc.to(torch.float64), pp.prior_scale.to(torch.float64)
+            logp = (-0.5 * ((Z.to(torch.float64) - pl) / ps) ** 2 - torch.log(ps) - c).sum(2)
+            logw = logw + logp - logq
+        mask = owner == ids
+        if done >= number_post_samples:                       # re-draw: only for samplers that still have nothing
+            mask = mask & (counts == 0)[:, None]
+        logw = torch.where(mask, logw, torch.full_like(logw, float("-inf")))
+        logZ = torch.logaddexp(logZ, torch.logsumexp(logw, 1))
+        counts = counts + mask.sum(1)
+        done += S if done < number_post_samples else 0
+        if injected is not None and done >= number_post_samples:
+            break
+    weights = torch.softmax(logZ, 0)
+    return weights, logZ, counts
+
+
+WvgdPlan.ensemble_weights = _wvgd_ensemble_weights
+
+
 def get_wvgd_plan(joint, particles, samplers):
     key = ("wvgd",) + tuple(id(p) for p in particles) + tuple(id(s) for s in samplers)
     plan = joint._plans.get(key)

@@ -471,6 +471,38 @@ def wvgd_loss(X, y, theta, loc, rho, eps_elbo, eps_particle, prior=None, dtype=t
     return float(total.detach()), {"loc": lc.grad.numpy().copy(), "rho": rh.grad.numpy().copy(), "theta": th.grad.numpy().copy()}, counts
 
 
+def wvgd_ensemble_weights(X, y, theta, loc, rho, eps, prior=None, dtype=torch.float64, likelihood="categorical",
+                          first_column_only=True):
+    """WassersteinVariationalGradientDescent.post_process (inference.py:234-247) + get_importance_weights
+    (variables.py:821-841): per sampler k, z = loc_k + softplus(rho_k) eps_k [S,C,F], A_k = {s : voronoi_owner(z_s) == k}
+    (rejection with max_itr = 1), logZ_k = log sum_{A_k} exp(log p(z, data) - log q_k(z)) -- the UNNORMALISED q log-prob
+    (normalized=False) and no division by the count; weights = softmax_k(logZ_k).  prior=None: tied mode (log p(z) = log q_k(z)).
+    Returns (weights [n], logZ [n], accepted counts [n])."""
+    Xt = _t(X, dtype)
+    n = len(theta)
+    if likelihood == "categorical":
+        yt = torch.as_tensor(np.asarray(y), dtype=torch.long)
+        loglik = lambda z: D.Categorical(logits=torch.einsum("scf,bf->sbc", z, Xt)).log_prob(yt[None, :]).sum(1)
+    else:
+        yt = _t(y, dtype)
+        loglik = lambda z: D.Binomial(total_count=1, logits=torch.einsum("scf,bf->sbc", z, Xt)[..., 0]).log_prob(yt[None, :]).sum(1)
+    logZ, counts = np.zeros(n), np.zeros(n, np.int64)
+    with torch.no_grad():
+        for k in range(n):
+            lc = _t(loc[k], dtype)
+            sg = F.softplus(_t(rho[k], dtype))
+            q = D.Normal(lc, sg.expand_as(lc))
+            pr = q if prior is None else D.Normal(_t(prior[0], dtype), _t(prior[1], dtype))
+            z = lc + sg * _t(eps[k], dtype)
+            acc = torch.as_tensor(voronoi_owner(z.float().numpy(), np.asarray(theta, np.float32), first_column_only) == k)
+            counts[k] = int(acc.sum())
+            za = z[acc]
+            logw = loglik(za) + pr.log_prob(za).sum((1, 2)) - q.log_prob(za).sum((1, 2))
+            logZ[k] = float(torch.logsumexp(logw, 0)) if counts[k] else -np.inf
+    w = np.exp(logZ - logZ.max())
+    return w / w.sum(), logZ, counts
+
+
 # ----------------------------------------------------------------------------------------------
 # Full-size evaluations (BASELINE configs C2 / C4): the same objectives with the gradient written out by hand and the
 # rows streamed in chunks, so that 10^6 rows x 1024 samples fit in host memory (autograd would keep every chunk's

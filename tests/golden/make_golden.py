@@ -255,10 +255,45 @@ def wvgd(seed, B, F, C, n, S, tag="wvgd_softmax", tied=True):
          loss=float(loss.detach()), grad_loc=g_loc, grad_rho=g_rho, grad_theta=g_theta)
 
 
+def wvgd_post(seed, B, F, C, n, S, tag):
+    """WassersteinVariationalGradientDescent.post_process (inference.py:234-247) through the reference: ensemble weights =
+    softmax over samplers of log sum_s exp(log p(z_ks, data) - log q_k(z_ks)) over the accepted draws of each truncated
+    sampler; the per-sampler log normalisers are recomputed with the same injected noise (variables.py:821-841)."""
+    model, particles, samplers, d = zoo.wvgd_softmax(NS, seed, B, F, C, n)
+    rng = d["rng"]
+    eps = rng.randn(n, S, C, F).astype("float32")
+    used = [0] * n
+    for k, smp in enumerate(samplers):
+        v = [v for v in smp.flatten() if v.name == "weights"][0]
+
+        def f(differentiable, _k=k, **p):
+            used[_k] += 1
+            return p["loc"] + torch.tensor(eps[_k]).reshape(S, 1, C, F) * p["scale"]
+        v.distribution._get_sample = f
+    m = inference.WassersteinVariationalGradientDescent(variational_samplers=samplers, particles=particles, biased=False,
+                                                        number_post_samples=S)
+    model.update_observed_submodel()
+    m.post_process(model)
+    assert used == [1] * n, "a sampler re-drew (no accepted sample): pick another seed %s" % used
+    logZ = []
+    for smp in m.sampler_model:
+        _, lz = model.get_importance_weights(q_samples=smp._get_sample(S, max_itr=1), q_model=smp, for_gradient=False,
+                                             give_normalization=True)
+        logZ.append(lz)
+    by = lambda smp, name: [v for v in smp.flatten() if v.name == name][0]
+    rho = np.stack([by(s_, "weights_scale").link.parameter.detach().numpy().reshape(()) for s_ in samplers])
+    save(tag, X=d["X"], y=d["y"], theta=d["theta"], loc=d["loc"], rho=rho, eps_post=eps, weights=np.asarray(m.weights),
+         logZ=np.asarray(logZ, dtype=np.float64))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "wvgd":
         wvgd(21, B=30, F=4, C=3, n=3, S=20, tag="wvgd_softmax")
         wvgd(22, B=16, F=5, C=2, n=4, S=24, tag="wvgd_softmax4")
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "wvgd_post":
+        wvgd_post(21, B=30, F=4, C=3, n=3, S=64, tag="wvgd_post")
+        wvgd_post(22, B=16, F=5, C=2, n=4, S=48, tag="wvgd_post4")
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "robust":
         scalar_model(zoo.robust_regression, "robust_regression", S=16, transforms={"nu": torch.exp}, seed=14, n=40)
@@ -287,3 +322,5 @@ if __name__ == "__main__":
     vae(13, B=10, D=20, L=3, h_enc=(9,), h_dec=(6, 8, 5), S=4, tag="vae_deep")
     wvgd(21, B=30, F=4, C=3, n=3, S=20, tag="wvgd_softmax")
     wvgd(22, B=16, F=5, C=2, n=4, S=24, tag="wvgd_softmax4")
+    wvgd_post(21, B=30, F=4, C=3, n=3, S=64, tag="wvgd_post")
+    wvgd_post(22, B=16, F=5, C=2, n=4, S=48, tag="wvgd_post4")

@@ -139,12 +139,12 @@ def test_svgd_same_script_same_numbers(ns):
     loss = m.compute_loss(model, particles, None, 1)
     loss.backward()
     raw = np.stack([list(p.flatten())[0].value.grad.detach().cpu().numpy().reshape(3, 5) for p in particles])
-    assert_close(float(loss.detach()), z["loss"], "svgd loss via API", rtol=2e-5, atol=2e-6)
-    assert_close(raw, z["raw_grad"], "svgd raw grads via API", rtol=2e-5, atol=2e-6, scale=np.abs(z["raw_grad"]).max())
+    assert_close(float(loss.detach()), z["loss"], "svgd loss via API", rtol=1e-5, atol=1e-6)
+    assert_close(raw, z["raw_grad"], "svgd raw grads via API", rtol=1e-5, atol=1e-6, scale=np.abs(z["raw_grad"]).max())
     m.correct_gradient(model, particles, None, 1)
     out = np.stack([list(p.flatten())[0].value.grad.detach().cpu().numpy().reshape(3, 5) for p in particles])
     assert abs(float(m.bandwidth) - float(z["bandwidth"])) <= 2e-6 * float(z["bandwidth"])
-    assert_close(out, z["out"], "svgd direction via API", rtol=2e-5, atol=2e-6, scale=np.abs(z["out"]).max())
+    assert_close(out, z["out"], "svgd direction via API", rtol=1e-5, atol=1e-6, scale=np.abs(z["out"]).max())
 
 
 def test_svgd_perform_inference_runs(ns):
@@ -176,13 +176,13 @@ def test_wvgd_api_matches_reference(tag, n, B, F, C, S, seed):
     with lowering.inject_noise({"elbo": g["eps_elbo"], "particle": g["eps_particle"]}):
         loss = m.compute_loss(model, particles, m.sampler_model, S)
     loss.backward()
-    assert_close(float(loss.detach()), g["loss"], tag + " loss", rtol=2e-5, atol=2e-6)
+    assert_close(float(loss.detach()), g["loss"], tag + " loss", rtol=1e-5, atol=1e-6)
     by = lambda mdl, name: [v for v in mdl.flatten() if v.name == name][0]
     got_loc = np.stack([by(s_, "weights_loc").value.grad.cpu().numpy().reshape(C, F) for s_ in samplers])
     got_rho = np.stack([by(s_, "weights_scale").value.grad.cpu().numpy().reshape(()) for s_ in samplers])
     got_th = np.stack([by(p_, "weights").value.grad.cpu().numpy().reshape(C, F) for p_ in particles])
     for got, key in ((got_loc, "grad_loc"), (got_rho, "grad_rho"), (got_th, "grad_theta")):
-        assert_close(got, g[key], tag + " " + key, rtol=2e-5, atol=2e-6, scale=np.abs(g[key]).max())
+        assert_close(got, g[key], tag + " " + key, rtol=1e-5, atol=1e-6, scale=np.abs(g[key]).max())
 
 
 @pytest.mark.gpu
@@ -243,3 +243,37 @@ def test_vae_perform_inference_runs_and_improves(ns):
     curve = np.asarray(model.diagnostics["loss curve"]).reshape(-1)
     assert inference.last_loop == "graph"
     assert np.isfinite(curve).all() and curve[-20:].mean() < curve[:20].mean()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag,n,B,F,C,seed", [("wvgd_post", 3, 30, 4, 3, 21), ("wvgd_post4", 4, 16, 5, 2, 22)])
+def test_wvgd_post_process_matches_reference(tag, n, B, F, C, seed):
+    """WassersteinVariationalGradientDescent.post_process (inference.py:234-247): ensemble weights and the per-sampler log
+    normalisers of the importance weights, on the device, against the LIVE reference's own output on the same injected draws
+    (tests/golden/make_golden.py: wvgd_post) and against the fp64 oracle; then with a declared (untied) prior and with the
+    kernel's own Philox draws (consistency: weights are a distribution, every sampler accepted something)."""
+    import os
+    from helpers import GOLDEN
+    from brancher_b200 import config, lowering
+    from oracle import elbo_oracle as O
+    config.set_device("cuda:0")
+    ns = zoo.namespace("brancher_b200")
+    g = np.load(os.path.join(GOLDEN, tag + ".npz"))
+    S = g["eps_post"].shape[1]
+    model, particles, samplers, d = zoo.wvgd_softmax(ns, seed, B, F, C, n)
+    m = ns.inference.WassersteinVariationalGradientDescent(variational_samplers=samplers, particles=particles, biased=False,
+                                                           number_post_samples=S)
+    m.check_model_compatibility(model, particles, m.sampler_model)
+    with lowering.inject_noise({"post": g["eps_post"]}):
+        m.post_process(model)
+    w64, lz64, c64 = O.wvgd_ensemble_weights(g["X"], g["y"], g["theta"], g["loc"], g["rho"], g["eps_post"])
+    assert (m.accepted_post == c64).all()
+    assert_close(m.log_normalizers, g["logZ"], tag + " logZ vs reference", rtol=1e-5, atol=1e-5)
+    assert_close(m.log_normalizers, lz64, tag + " logZ vs fp64 oracle", rtol=1e-5, atol=1e-5)
+    assert_close(m.weights, g["weights"], tag + " weights vs reference", rtol=1e-4, atol=1e-7)
+    assert_close(m.weights, w64, tag + " weights vs fp64 oracle", rtol=1e-4, atol=1e-7)
+    # Philox draws, many samples, several chunks
+    m.number_post_samples = 20000
+    m.post_process(model)
+    assert m.weights.shape == (n,) and abs(m.weights.sum() - 1) < 1e-6 and (m.accepted_post > 0).all()
+    assert m.accepted_post.sum() <= 20000 * n

@@ -52,10 +52,10 @@ def test_compiled_program_matches_reference_on_cpu(tag):
     for p in plan.prog.params:                               # same initial values (same construction script)
         np.testing.assert_allclose(float(p.detach()), float(g["param"][names[id(p)]]), rtol=1e-6, atol=1e-7)
     loss, grads = interp(plan, names, g)
-    assert_close(loss, g["raw"]["loss"], tag + " loss", rtol=2e-5, atol=2e-6)
+    assert_close(loss, g["raw"]["loss"], tag + " loss", rtol=1e-5, atol=1e-6)
     sc = max(abs(float(v)) for v in g["grad"].values())
     for k, v in g["grad"].items():
-        assert_close(grads[k], v.reshape(()), tag + " grad " + k, rtol=2e-5, atol=2e-6, scale=sc)
+        assert_close(grads[k], v.reshape(()), tag + " grad " + k, rtol=1e-5, atol=1e-6, scale=sc)
 
 
 @pytest.mark.parametrize("tag", sorted(CASES))
@@ -163,13 +163,13 @@ def test_dag_kernel_matches_reference(tag):
         loss = ns.inference.ReverseKL().compute_loss(model, model.posterior_model, None, S)
     loss.backward()
     l64, g64 = interp(plan, names, g)
-    assert_close(float(loss.detach()), g["raw"]["loss"], tag + " loss vs reference", rtol=2e-5, atol=2e-6)
+    assert_close(float(loss.detach()), g["raw"]["loss"], tag + " loss vs reference", rtol=1e-5, atol=1e-6)
     assert_close(float(loss.detach()), l64, tag + " loss vs fp64 interpreter")
     sc = max(abs(float(v)) for v in g["grad"].values())
     for p in plan.prog.params:
         k = names[id(p)]
         got = float(p.grad.reshape(()))
-        assert_close(got, g["grad"][k].reshape(()), tag + " grad %s vs reference" % k, rtol=2e-5, atol=2e-6, scale=sc)
+        assert_close(got, g["grad"][k].reshape(()), tag + " grad %s vs reference" % k, rtol=1e-5, atol=1e-6, scale=sc)
         assert_close(got, g64[k], tag + " grad %s vs fp64 interpreter" % k, scale=sc)
 
 

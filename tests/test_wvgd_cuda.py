@@ -48,9 +48,9 @@ def run(cu, g, prior=None, biased=False, first_column_only=True, philox=False, s
 def test_wvgd_matches_reference(cu, tag):
     g = load(tag)
     loss, dloc, drho, dth, counts = run(cu, g)
-    assert_close(loss, g["loss"], tag + " loss vs reference", rtol=2e-5, atol=2e-6)
+    assert_close(loss, g["loss"], tag + " loss vs reference", rtol=1e-5, atol=1e-6)
     for got, key in ((dloc, "grad_loc"), (drho, "grad_rho"), (dth, "grad_theta")):
-        assert_close(got, g[key], tag + " " + key + " vs reference", rtol=2e-5, atol=2e-6, scale=np.abs(g[key]).max())
+        assert_close(got, g[key], tag + " " + key + " vs reference", rtol=1e-5, atol=1e-6, scale=np.abs(g[key]).max())
 
 
 @pytest.mark.parametrize("tag", GOLD)
