@@ -98,6 +98,9 @@ SYMBOLS = {
     "brn_bnn_elbo_fwd_bwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 4 +
                              [ctypes.POINTER(MFVar), ctypes.POINTER(SampleRange), ctypes.c_void_p, ctypes.c_size_t,
                               ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "brn_bnn_predict": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.POINTER(MFVar), ctypes.POINTER(SampleRange),
+                                       ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_void_p]),
     "brn_linear_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "brn_linear_elbo_fwd_bwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
                                                ctypes.c_int, ctypes.c_int, ctypes.POINTER(MFVar),
@@ -319,6 +322,23 @@ def bnn_elbo_fwd_bwd(X, y, vars4, r, with_prior=True, loss=None, data_ready=None
                                       ws.data_ptr(), ws.numel(), int(with_prior), _ptr(loss, torch.float64),
                                       _stream(dev)), "brn_bnn_elbo_fwd_bwd")
     return loss
+
+
+def bnn_predict(X, vars4, r, labels=True, probs=True):
+    """K3 forward only: posterior-predictive pass for a batch.  Returns (logits [s_local,B,C], labels int32 [s_local,B] or
+    None, probs_mean [B,C] or None: this rank's share of the MC average of softmax(logits))."""
+    dev = X.device
+    B, P = X.shape
+    H, C = vars4[1].numel, vars4[3].numel
+    nbytes = lib().brn_bnn_workspace_bytes(B, P, H, C, r.s_local)
+    ws = _workspace(dev, nbytes)
+    arr = (MFVar * 4)(*[v.struct() for v in vars4])
+    logits = torch.empty((r.s_local, B, C), dtype=torch.float32, device=dev)
+    lab = torch.empty((r.s_local, B), dtype=torch.int32, device=dev) if labels else None
+    pm = torch.zeros((B, C), dtype=torch.float32, device=dev) if probs else None
+    _check(lib().brn_bnn_predict(_ptr(X, what="X"), B, P, H, C, arr, ctypes.byref(r), ws.data_ptr(), ws.numel(), _ptr(logits),
+                                 _ptr(lab, torch.int32), _ptr(pm), _stream(dev)), "brn_bnn_predict")
+    return logits, lab, pm
 
 
 BERNOULLI, CATEGORICAL = 0, 1

@@ -346,6 +346,66 @@ bnn_mid2_kernel(float* __restrict__ pre, const float* __restrict__ W, float* __r
 }
 
 
+// ---------------------------------------------------------------------------------------------------
+// posterior-predictive forward pass: logits of every (posterior sample, data row) in one launch, optional
+// class draws (inverse CDF on a Philox uniform) and the MC average of the class probabilities.
+// One CTA = 128 rows of one sample, one thread per row.  PRE_T: pre is [S][H][B] (tcgen05 variant) else [S][B][H].
+// ---------------------------------------------------------------------------------------------------
+template <bool PRE_T>
+__global__ void __launch_bounds__(128)
+bnn_predict_kernel(const float* __restrict__ pre, const float* __restrict__ W, BnnLayout L, float* __restrict__ logits,
+                   int32_t* __restrict__ labels, float* __restrict__ probs_mean, float inv_S, brn_sample_range r) {
+    extern __shared__ float sm[];
+    const int H = L.H, C = L.C, B = L.B;
+    float* W2s = sm;                 // [C][H]
+    float* b1s = W2s + C * H;        // [H]
+    float* b2s = b1s + H;            // [C]
+    const int s = blockIdx.y, b = blockIdx.x * 128 + threadIdx.x;
+    const float* Ws = W + (int64_t)s * L.ldw;
+    for (int i = threadIdx.x; i < C * H; i += 128) W2s[i] = Ws[L.oW2 + i];
+    for (int i = threadIdx.x; i < H; i += 128) b1s[i] = Ws[L.ob1 + i];
+    for (int i = threadIdx.x; i < C; i += 128) b2s[i] = Ws[L.ob2 + i];
+    __syncthreads();
+    if (b >= B) return;
+    const float* ps = pre + (int64_t)s * B * H;
+    float a[BNN_MAXC];
+#pragma unroll
+    for (int c = 0; c < BNN_MAXC; ++c) a[c] = 0.f;
+    for (int h = 0; h < H; ++h) {
+        const float v = tanhf((PRE_T ? ps[(int64_t)h * B + b] : ps[(int64_t)b * H + h]) + b1s[h]);
+#pragma unroll
+        for (int c = 0; c < BNN_MAXC; ++c)
+            if (c < C) a[c] = __fmaf_rn(W2s[c * H + h], v, a[c]);
+    }
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < BNN_MAXC; ++c)
+        if (c < C) { a[c] += b2s[c]; m = fmaxf(m, a[c]); }
+    float* lo = logits + ((int64_t)s * B + b) * C;
+    float se = 0.f, e[BNN_MAXC];
+#pragma unroll
+    for (int c = 0; c < BNN_MAXC; ++c)
+        if (c < C) { lo[c] = a[c]; e[c] = expf(a[c] - m); se += e[c]; }
+    const float inv = 1.f / se;
+    if (probs_mean) {
+#pragma unroll
+        for (int c = 0; c < BNN_MAXC; ++c)
+            if (c < C) atomicAdd(&probs_mean[(int64_t)b * C + c], e[c] * inv * inv_S);
+    }
+    if (labels) {      // k ~ Categorical(logits) (distributions.py:275-311): inverse CDF on one Philox uniform per (sample, row)
+        const Philox4 u4 = philox4x32_10((uint32_t)(b >> 2), (uint32_t)(r.s0 + s), 4u, (uint32_t)philox_offset(r), (uint32_t)r.seed,
+                                         (uint32_t)(r.seed >> 32) ^ (uint32_t)(philox_offset(r) >> 32));
+        const uint32_t w = (b & 3) == 0 ? u4.x : ((b & 3) == 1 ? u4.y : ((b & 3) == 2 ? u4.z : u4.w));
+        const float u = u01(w) * se;
+        float acc = 0.f;
+        int k = C - 1;
+#pragma unroll
+        for (int c = 0; c < BNN_MAXC; ++c)
+            if (c < C) { acc += e[c]; if (u <= acc && k == C - 1 && c < C - 1) k = c; }
+        labels[(int64_t)s * B + b] = k;
+    }
+}
+
 static size_t bnn_mid_smem(int R, int H, int C) {
     return sizeof(float) * ((size_t)R * (H + 1) + (size_t)C * H + H + C + (size_t)R * C);
 }
@@ -481,4 +541,53 @@ extern "C" int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int
     // 5. reduce over samples + prior/entropy + chain rule: one stats launch for all four variables
     StageTimer st5("bnn.reduce_finalize", stream);
     return launch_mf_reduce_finalize_multi(vars, offs, 4, L.numel, ws.eps, L.ldw, ws.dW, L.ldw, ws.stats, *r, with_prior, loss, stream, 0);
+}
+
+extern "C" int brn_bnn_predict(const float* X, int B, int P, int H, int C, const brn_mf_var vars[4], const brn_sample_range* r,
+                               void* workspace, size_t workspace_bytes, float* logits, int32_t* labels, float* probs_mean,
+                               void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    BRN_CHECK_ARG(X && vars && r && logits, "brn_bnn_predict: NULL pointer");
+    BRN_CHECK_ARG(B > 0 && P > 0 && H > 0 && C > 0 && C <= BNN_MAXC, "brn_bnn_predict: bad shape B=%d P=%d H=%d C=%d", B, P, H, C);
+    BRN_CHECK_ARG(r->s_local >= 0 && r->s_total > 0 && r->s0 >= 0 && r->s0 + r->s_local <= r->s_total,
+                  "bad sample range s0=%d s_local=%d s_total=%d", r->s0, r->s_local, r->s_total);
+    BnnLayout L(B, P, H, C);
+    const int64_t numels[4] = {(int64_t)H * P, H, (int64_t)C * H, C};
+    const int64_t offs[4] = {L.oW1, L.ob1, L.oW2, L.ob2};
+    for (int v = 0; v < 4; ++v) {
+        BRN_CHECK_ARG(vars[v].numel == numels[v], "vars[%d].numel=%lld, expected %lld", v, (long long)vars[v].numel, (long long)numels[v]);
+        BRN_CHECK_ARG(vars[v].mu && vars[v].rho, "vars[%d]: NULL parameter pointer", v);
+    }
+    const int S = r->s_local;
+    if (S == 0) return 0;
+    BnnWorkspace ws(workspace, L, S);
+    BRN_CHECK_ARG(workspace && workspace_bytes >= ws.bytes, "workspace too small: %zu < %zu", workspace_bytes, ws.bytes);
+    const char* env_variant = getenv("BRN_BNN_VARIANT");
+    bool use_tc = (H > BNN_UMMA_HP - 16 && H <= BNN_UMMA_HP);
+    if (env_variant) {
+        if (!strcmp(env_variant, "simt")) use_tc = false;
+        else if (!strcmp(env_variant, "tcgen05") && H <= BNN_UMMA_HP) use_tc = true;
+    }
+    set_variant(use_tc ? "tcgen05" : "simt");
+    if (use_tc) {
+        if (int e = bnn_tc_eval(X, nullptr, L, vars, r, ws.tc, ws.eps, ws.W, ws.dW, ws.pre, ws.stats, 0, nullptr, 2, 4, false, stream, true))
+            return e;
+    } else {
+        if (int e = launch_sample_multi(vars, offs, 4, ws.eps, ws.W, L.ldw, *r, stream)) return e;
+        if (int e = launch_sgemm_batched<true, true>(X, P, 0, ws.W + L.oW1, P, L.ldw, ws.pre, H, (int64_t)B * H, B, H, P, S, stream))
+            return e;
+    }
+    const size_t smem = sizeof(float) * ((size_t)C * H + H + C);
+    BRN_CHECK_ARG(smem <= 200 * 1024, "brn_bnn_predict: hidden width H=%d too large", H);
+    dim3 grid((B + 127) / 128, S);
+    const float inv_S = 1.0f / (float)r->s_total;
+    if (use_tc) {
+        BRN_CUDA_OK(cudaFuncSetAttribute(bnn_predict_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        bnn_predict_kernel<true><<<grid, 128, smem, stream>>>(ws.pre, ws.W, L, logits, labels, probs_mean, inv_S, *r);
+    } else {
+        BRN_CUDA_OK(cudaFuncSetAttribute(bnn_predict_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        bnn_predict_kernel<false><<<grid, 128, smem, stream>>>(ws.pre, ws.W, L, logits, labels, probs_mean, inv_S, *r);
+    }
+    BRN_LAUNCH_OK("bnn_predict_kernel");
+    return 0;
 }

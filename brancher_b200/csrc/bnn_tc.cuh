@@ -1161,7 +1161,7 @@ struct BnnTcWorkspace {
 // measurements and tests (BRN_BNN_MID=4).
 static int bnn_tc_eval(const float* X, const int32_t* y, const BnnLayout& L, const brn_mf_var vars[4], const brn_sample_range* r,
                        const BnnTcWorkspace& ws, float* ws_eps, float* ws_W, float* ws_dW, float* ws_pre, float* ws_stats,
-                       int with_prior, double* loss, int drain, int drain_bwd, bool fused, cudaStream_t stream) {
+                       int with_prior, double* loss, int drain, int drain_bwd, bool fused, cudaStream_t stream, bool forward_only = false) {
     constexpr int HP = BNN_UMMA_HP, NS = BNN_UMMA_NSAMP, BN = HP * NS;
     const int B = L.B, P = L.P, H = L.H, S = r->s_local;
     const int64_t numels[4] = {(int64_t)H * P, H, (int64_t)L.C * H, L.C};
@@ -1213,7 +1213,7 @@ static int bnn_tc_eval(const float* X, const int32_t* y, const BnnLayout& L, con
         split_f16_kernel<<<grid, block, 0, stream>>>(X, P, B, P, ws.Xh, ws.Xl, ws.ldP, ws.Xth, ws.Xtl, ws.ldB, ws.scal);
         BRN_LAUNCH_OK("split_f16_kernel");
     }
-    if (fused) {
+    if (fused && !forward_only) {
         {
             StageTimer st("bnn.gemm_fwd", stream);      // forward GEMM + mid in its epilogue
             FwdMidParams fp{ws_W, ws_dW, y, L, S, inv_S, loss, ws.dph, ws.dpl, ws.ldB, ws.scal};
@@ -1248,6 +1248,7 @@ static int bnn_tc_eval(const float* X, const int32_t* y, const BnnLayout& L, con
                                                                                drain, ep, stream))
             return e;
     }
+    if (forward_only) return 0;          // brn_bnn_predict: pre^T [S][H][B] is all it needs
     {
         StageTimer st("bnn.mid", stream);
         if (int e = launch_mid4<HP>(ws_pre, ws_W, ws_dW, y, L, S, inv_S, loss, ws.dph, ws.dpl, ws.ldB, ws.scal, stream)) return e;

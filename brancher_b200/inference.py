@@ -246,6 +246,44 @@ class SteinVariationalGradientDescent(InferenceMethod):
         pass
 
 
+class MAP(InferenceMethod):
+    """Maximum a posteriori (inference.py:251-274): the posterior model holds one learnable RootVariable per latent,
+    loss = -log p(data, theta).  The point estimate is a one-particle ensemble of the linear family (K4a: one fused launch
+    for the joint log-probability and its gradient), any scalar model goes through the scalar-DAG family (K1)."""
+
+    def __init__(self):
+        self.learnable_model = False
+        self.needs_sampler = False
+        self.learnable_sampler = False
+
+    def _plan(self, joint_model, posterior_model):
+        from brancher_b200 import lowering
+        try:
+            return "particles", lowering.get_particle_plan(joint_model, [posterior_model])
+        except lowering.UnsupportedModelError as particle_err:
+            try:
+                return "dag", lowering.get_plan(joint_model, posterior_model)
+            except lowering.UnsupportedModelError as dag_err:
+                raise lowering.UnsupportedModelError("MAP: the model is lowered neither as a linear-family point estimate (%s) "
+                                                     "nor as a scalar DAG (%s)" % (particle_err, dag_err)) from None
+
+    def check_model_compatibility(self, joint_model, posterior_model, sampler_model):
+        from brancher_b200.variables import RootVariable
+        assert all(isinstance(var, RootVariable) for var in posterior_model.flatten())
+        self._plan(joint_model, posterior_model)
+
+    def compute_loss(self, joint_model, posterior_model, sampler_model, number_samples, input_values={}):
+        kind, plan = self._plan(joint_model, posterior_model)
+        joint_model.update_observed_submodel()
+        empirical = joint_model.observed_submodel._get_sample(1, observed=True, differentiable=False)
+        if kind == "particles":
+            return plan.loss(empirical)
+        return -plan.elbo(1, empirical)          # no q noise, no entropy terms: -ELBO of a point mass is -log p(data, theta)
+
+    def post_process(self, joint_model):
+        pass
+
+
 class WassersteinVariationalGradientDescent(InferenceMethod):
     """WVGD over (sampler, particle) ensembles (inference.py:154-248).  `compute_loss` = sum_k -ELBO(joint, q = sampler k
     truncated to particle k's Voronoi cell) + the importance-weighted squared distance between every particle and its own
@@ -256,7 +294,8 @@ class WassersteinVariationalGradientDescent(InferenceMethod):
     squared-distance cost runs on the GPU); `first_column_only=True` (default) reproduces the reference's numpy cost, which
     for weights of shape [C, F] only sees column 0 (utilities.py:125-126) -- pass False for the full squared distance.
     Deviation: a sampler whose draw has no accepted sample contributes nothing to that term in this evaluation (the
-    reference re-draws until one is accepted, transformations.py:33); `accepted` holds the per-sampler counts."""
+    reference re-draws until one is accepted, transformations.py:33); `accepted` holds the per-sampler counts.
+    `post_process` (ensemble weights) re-draws such samplers as the reference does."""
 
     def __init__(self, variational_samplers, particles, cost_function=None, deviation_statistics=None, biased=False,
                  number_post_samples=20000, gradient_estimator=gradient_estimators.PathwiseDerivativeEstimator,

@@ -280,6 +280,21 @@ class BNNPlan(Plan):
         y = empirical[self.k].reshape(-1).to(torch.int32).contiguous()
         return cu.bnn_elbo_fwd_bwd(X, y, mvars, r, loss=loss)
 
+    def predict(self, X, number_samples):
+        """Batched posterior-predictive pass (replaces the per-image loop around
+        ProbabilisticModel._get_posterior_sample, variables.py:796-812): X [B, P] -> dict(logits [S, B, C],
+        samples int32 [S, B] ~ Categorical(logits), probs [B, C] = MC mean of softmax(logits))."""
+        if config.device.type != "cuda":
+            raise RuntimeError("brancher_b200 evaluates the posterior predictive only on CUDA devices (no CPU fallback)")
+        from brancher_b200 import _cuda as cu
+        cu.lib()
+        X = torch.as_tensor(X, dtype=torch.float32, device=config.device)
+        X = X.reshape(-1, int(np.prod(self.latents[0].shape[1:]))).contiguous()
+        r = cu.sample_range(number_samples, seed=config.seed, offset=config.next_offset())
+        mvars = [spec.make(cu, i, None) for i, spec in enumerate(self.latents)]
+        logits, labels, probs = cu.bnn_predict(X, mvars, r)
+        return {"logits": logits, "samples": labels, "probs": probs, "sample_range": r}
+
 
 # ---------------------------------------------------------------------------------------------------
 def _latent_random_variables(model):

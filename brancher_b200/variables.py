@@ -533,6 +533,20 @@ class ProbabilisticModel(BrancherClass):
                                                           differentiable=differentiable)
         return self._get_sample(number_samples, input_values=post, differentiable=differentiable)
 
+    def get_posterior_predictive(self, number_samples, input_values):
+        """Batched posterior-predictive pass on the GPU for model pairs that lower to the BNN family: `input_values` maps the
+        observed input variable to a batch of rows; returns dict(logits [S, B, C], samples [S, B], probs [B, C]).
+        One launch sequence for the whole batch instead of one graph walk per image and sample
+        (reference: the `_get_posterior_sample` loop of tests/test_MNIST_bayesian_neural_network.py:75-81)."""
+        from brancher_b200 import lowering
+        self.check_posterior_model()
+        plan = lowering.get_plan(self, self.posterior_model)
+        if not hasattr(plan, "predict"):
+            raise lowering.UnsupportedModelError("posterior predictive is lowered for the BNN family only (plan: %s)" % plan.family)
+        if plan.x_var not in input_values:
+            raise KeyError("input_values must hold the model's input variable %r" % plan.x_var.name)
+        return plan.predict(input_values[plan.x_var], number_samples)
+
     def get_posterior_sample(self, number_samples, input_values={}):
         from brancher_b200.pandas_interface import reformat_sample_to_pandas
         formatted = _reformat_sampler_input(input_values, number_samples)

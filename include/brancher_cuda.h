@@ -106,6 +106,16 @@ int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int P, int H, 
                          void* workspace, size_t workspace_bytes, int with_prior,
                          double* loss, void* stream);
 
+/* K3 forward only -- batched posterior-predictive pass of the BNN: for S posterior weight samples and B data
+ * rows, logits[s, b, :] = W2_s tanh(W1_s x_b + b1_s) + b2_s in one launch sequence (same sampler and tensor-core forward
+ * GEMM as the ELBO evaluation), optionally labels[s, b] ~ Categorical(logits[s, b]) (Philox) and
+ * probs_mean[b, c] += (1/S_total) softmax(logits[s, b])[c] (caller-zeroed).
+ * Replaces ProbabilisticModel._get_posterior_sample (brancher/variables.py:796-812) as every evaluation loop of the examples
+ * uses it -- one image and one graph walk at a time (tests/test_MNIST_bayesian_neural_network.py:75-81). */
+int brn_bnn_predict(const float* X, int B, int P, int H, int C, const brn_mf_var vars[4], const brn_sample_range* r,
+                    void* workspace, size_t workspace_bytes, float* logits, int32_t* labels, float* probs_mean,
+                    void* stream);
+
 /* K2 -- (multi-class) Bayesian logistic regression: logits_sbc = sum_f W_scf X_bf, W ~ q mean-field [C,F];
  *   likelihood 0: Bernoulli / Binomial(total_count=1, logits) with y float {0,1}  (C == 1)
  *   likelihood 1: Categorical(logits) with y int32 labels

@@ -277,3 +277,54 @@ def test_wvgd_post_process_matches_reference(tag, n, B, F, C, seed):
     m.post_process(model)
     assert m.weights.shape == (n,) and abs(m.weights.sum() - 1) < 1e-6 and (m.accepted_post > 0).all()
     assert m.accepted_post.sum() <= 20000 * n
+
+
+@pytest.mark.gpu
+def test_map_logistic_regression_matches_oracle():
+    """examples/MAP_logistic_regression.py shape: MAP().compute_loss = -log p(data, theta) and its gradient through K4a vs the
+    fp64 oracle; perform_inference drives it down."""
+    from brancher_b200 import config
+    from oracle import elbo_oracle as O
+    config.set_device("cuda:0")
+    ns = zoo.namespace("brancher_b200")
+    rng = np.random.RandomState(3)
+    B, F, C = 60, 5, 3
+    X = rng.randn(B, F, 1).astype("float32")
+    y = rng.randint(0, C, size=(B,))
+    x = ns.RootVariable(X, "x", is_observed=True)
+    weights = ns.NormalVariable(np.zeros((C, F)), 10 * np.ones((C, F)), "weights")
+    k = ns.CategoricalVariable(logits=ns.BF.matmul(weights, x), name="k")
+    model = ns.ProbabilisticModel([k])
+    k.observe(y)
+    w0 = rng.randn(C, F)
+    point = ns.ProbabilisticModel([ns.RootVariable(w0, name="weights", learnable=True)])
+    model.set_posterior_model(point)
+    m = ns.inference.MAP()
+    m.check_model_compatibility(model, model.posterior_model, None)
+    loss = m.compute_loss(model, model.posterior_model, None, 1)
+    loss.backward()
+    root = [v for v in point.flatten() if v.name == "weights"][0]
+    l64, g64 = O.particles_loss_grad(X[:, :, 0], y, w0[None].astype("f4"), (np.zeros((C, F), "f4"), np.full((C, F), 10.0, "f4")),
+                                     dtype=torch.float64, likelihood="categorical")
+    assert_close(float(loss.detach()), l64, "MAP loss")
+    assert_close(root.value.grad.cpu().numpy().reshape(C, F), g64[0], "MAP gradient", scale=np.abs(g64).max())
+    ns.inference.perform_inference(model, inference_method=ns.inference.MAP(), number_iterations=40, number_samples=1,
+                                   optimizer="SGD", lr=0.01)
+    curve = model.diagnostics["loss curve"]
+    assert curve.shape == (40,) and curve[-1] < curve[0]
+
+
+@pytest.mark.gpu
+def test_posterior_predictive_api():
+    """ProbabilisticModel.get_posterior_predictive: one batched launch sequence for all test rows and posterior samples"""
+    from brancher_b200 import config
+    config.set_device("cuda:0")
+    ns = zoo.namespace("brancher_b200")
+    model, Q, d = zoo.bnn(ns, 1, B=40, P=30, H=100, C=5, q_sigma=0.05, q_mu_scale=0.3)
+    x = [v for v in model._flatten() if v.name == "x"][0]
+    out = model.get_posterior_predictive(12, {x: d["X"][:25]})
+    assert tuple(out["logits"].shape) == (12, 25, 5) and tuple(out["samples"].shape) == (12, 25)
+    p = out["probs"].cpu().numpy()
+    assert p.shape == (25, 5) and np.allclose(p.sum(1), 1.0, atol=1e-5)
+    want = torch.softmax(out["logits"], -1).mean(0).cpu().numpy()
+    np.testing.assert_allclose(p, want, rtol=1e-5, atol=1e-6)

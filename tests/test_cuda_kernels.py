@@ -312,3 +312,31 @@ def test_bnn_variants_agree_philox(cu, monkeypatch):
     for k in out["simt"][1]:
         sc = np.abs(out["simt"][1][k]).max()
         assert_close(out["tcgen05"][1][k], out["simt"][1][k], "grad " + k, rtol=1e-5, atol=2e-6, scale=sc)
+
+
+@pytest.mark.parametrize("B,P,H,C,S,variant", [(300, 50, 100, 10, 6, "tcgen05"), (77, 33, 21, 4, 5, "simt"), (1024, 784, 100, 10, 8, "tcgen05")])
+def test_bnn_predict_matches_forward_oracle(cu, monkeypatch, B, P, H, C, S, variant):
+    """brn_bnn_predict: logits of every (posterior sample, row) vs an fp64 forward pass on the re-materialised
+    Philox weights; probs = MC mean of the softmax; class draws follow the probabilities (distributional check)."""
+    monkeypatch.setenv("BRN_BNN_VARIANT", variant)
+    X, y, params, _, shapes = random_bnn(B + H, B, P, H, C, S)
+    r = cu.sample_range(S, seed=21, offset=4)
+    mv = make_vars(cu, params, None, BNN_NAMES)
+    logits, labels, probs = cu.bnn_predict(dev(X), mv, r)
+    assert cu.last_variant() == variant
+    eps = {n: cu.philox_normal(int(np.prod(shapes[n])), i, r, DEV).cpu().numpy().reshape((S,) + shapes[n]).astype("f8")
+           for i, n in enumerate(BNN_NAMES)}
+    sp = lambda v: np.log1p(np.exp(v.astype("f8")))
+    W = {n: params[n][0].astype("f8")[None] + sp(params[n][1])[None] * eps[n] for n in BNN_NAMES}
+    pre = np.einsum("shp,bp->sbh", W["weights1"], X.astype("f8")) + W["b1"][:, None, :, 0]
+    a = np.einsum("sch,sbh->sbc", W["weights2"], np.tanh(pre)) + W["b2"][:, None, :, 0]
+    assert_close(logits.cpu().numpy(), a, "predict logits", scale=np.abs(a).max())
+    e = np.exp(a - a.max(-1, keepdims=True))
+    pm = (e / e.sum(-1, keepdims=True)).mean(0)
+    assert_close(probs.cpu().numpy(), pm, "predict probs", rtol=1e-5, atol=1e-6)
+    lab = labels.cpu().numpy()
+    assert lab.shape == (S, B) and lab.min() >= 0 and lab.max() < C
+    # class frequencies over all (sample, row) draws vs the mean probability, within 5 sigma
+    freq = np.bincount(lab.reshape(-1), minlength=C) / lab.size
+    want = (e / e.sum(-1, keepdims=True)).reshape(-1, C).mean(0)
+    assert np.all(np.abs(freq - want) <= 5 * np.sqrt(want * (1 - want) / lab.size) + 1e-3), (freq, want)
