@@ -508,6 +508,7 @@ def main_ours(args):
             else:
                 th, gg = theta_local, G
             svgd_out[0], _ = cu.svgd_direction(th, gg, row0=rank * n_local, rows=n_local)
+            svgd_out[1] += " (K4a) + %s (K4b)" % cu.last_variant()
             return loss
     else:
         rows = cfg["N"]
@@ -729,7 +730,7 @@ def main_ours(args):
                                     "iteration)" if graph_step else "step-by-step launches",
                           "stage_timing": "separate pass of the same K steps with the library's per-stage CUDA events on "
                                           "(%.4f ms/step there); the headline region carries no such events" % (ms_prof / args.steps),
-                          "variant": (svgd_out[1] + " (K4a) + simt (K4b)") if wl == "svgd" else cu.last_variant(),
+                          "variant": svgd_out[1] if wl == "svgd" else cu.last_variant(),
                           "global_samples_or_particles": S_total,
                           "sharding": {"bnn": "MC samples", "logreg": "data rows", "svgd": "particles", "vae": "batch rows",
                                        "ar1": "MC samples"}[wl]},

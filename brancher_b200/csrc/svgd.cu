@@ -10,7 +10,8 @@
 // multiset {D2_ij : i != j} is the multiset {D2_ij : i < j} with every element doubled, which has the same median,
 // so the select runs over the m = n(n-1)/2 upper-triangle values.  Non-negative floats order like their bit
 // patterns: three histogram passes (12 + 12 + 8 bits) pin the k-th smallest value, one more pass finds its successor.
-#include "common.cuh"
+#include "umma_gemm.cuh"
+#include <stdlib.h>
 
 namespace brn {
 
@@ -299,12 +300,124 @@ svgd_update_kernel(const float* __restrict__ theta, const float* __restrict__ gr
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// tensor-core variant of the two contractions (tcgen05, 3xTF32):
+//   D2 = |a|^2 + |b|^2 - 2 a.b   -- theta . theta^T through the GEMM, norms and clamp in its epilogue (EpiD2)
+//   out = K . [g - theta / bw | 1] -- the GEMM reads D2 itself; its converter warps turn every element into
+//         exp(-D2 / 2bw) on its way into the tensor core (TRANSFORMS_A), so the kernel matrix K is never materialised;
+//         the appended column of ones delivers rowsum(K) for the attractive term (EpiSvgdOut).
+// ---------------------------------------------------------------------------------------------------
+struct EpiD2 {
+    struct Params { const float* sq; float* D2; int rows, n; int row0; };
+    template <int CPT>
+    static __device__ __forceinline__ void finish(const Params& p, float (&r)[CPT], int row, int blk, bool, int) {
+        if (row >= p.rows) return;
+        const int gi = p.row0 + row, c0 = blk * CPT;
+        const float si = p.sq[gi];
+        float* o = p.D2 + (int64_t)row * p.n + c0;
+#pragma unroll
+        for (int i = 0; i < CPT; i += 4) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = c0 + i + u;
+                float x = 0.f;
+                if (j < p.n && j != gi) x = fmaxf(__fmaf_rn(-2.f, r[i + u], si + p.sq[j]), 0.f);
+                v[u] = x;
+            }
+            if (c0 + i + 3 < p.n && (p.n & 3) == 0) *reinterpret_cast<float4*>(o + i) = make_float4(v[0], v[1], v[2], v[3]);
+            else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (c0 + i + u < p.n) o[i + u] = v[u];
+            }
+        }
+    }
+};
+
+struct EpiSvgdOut {
+    static constexpr bool TRANSFORMS_A = true;
+    struct Params { float* out; const float* theta; const float* bw; int rows, d, row0; };
+    static __device__ __forceinline__ float transform_a_context(const Params& p) { return -0.5f / *p.bw * 1.4426950408889634f; }
+    static __device__ __forceinline__ float transform_a(float ctx, float x) {
+        float e;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * ctx));
+        return e;
+    }
+    // one thread = one particle row and all d + 1 accumulator columns (column d = rowsum of K); K-split slices add up
+    template <int CPT>
+    static __device__ __forceinline__ void finish(const Params& p, float (&r)[CPT], int row, int blk, bool, int) {
+        if (row >= p.rows || blk != 0) return;
+        float rowsum = 0.f;                                            // column d (d < CPT by construction); static indexing only
+#pragma unroll
+        for (int c = 0; c < CPT; ++c)
+            if (c == p.d) rowsum = r[c];
+        const float w = rowsum / *p.bw;
+        const float* th = p.theta + (int64_t)(p.row0 + row) * p.d;
+        float* o = p.out + (int64_t)row * p.d;
+#pragma unroll
+        for (int c = 0; c < CPT; ++c)
+            if (c < p.d) atomicAdd(o + c, __fmaf_rn(th[c], w, r[c]));
+    }
+};
+
+// sq[i] = |theta_i|^2 and the TF32 (hi, lo) pair of theta [n][ld]
+__global__ void __launch_bounds__(128) svgd_prep_theta_kernel(const float* __restrict__ theta, int n, int d, int64_t ld,
+                                                              float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ sq) {
+    const int i = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= n) return;
+    float acc = 0.f;
+    for (int c = lane; c < d; c += 32) {
+        const float x = theta[(int64_t)i * d + c];
+        float h, l;
+        umma::split_tf32(x, h, l);
+        hi[(int64_t)i * ld + c] = h;
+        lo[(int64_t)i * ld + c] = l;
+        acc = __fmaf_rn(x, x, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) sq[i] = acc;
+}
+
+// Vt[c][j] = g[j][c] - theta[j][c] / bw (c < d), Vt[d][j] = 1: the K-major B operand [d + 1][ldn] as a TF32 (hi, lo) pair
+__global__ void __launch_bounds__(256) svgd_prep_v_kernel(const float* __restrict__ theta, const float* __restrict__ grad, int n,
+                                                          int d, const float* __restrict__ bw, float* __restrict__ hi,
+                                                          float* __restrict__ lo, int64_t ldn) {
+    __shared__ float t[32][33];
+    const float inv_bw = 1.0f / *bw;
+    const int j0 = blockIdx.x * 32, c0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int j = j0 + r, c = c0 + tx;
+        float v = 0.f;
+        if (j < n) {
+            if (c < d) v = __fmaf_rn(-theta[(int64_t)j * d + c], inv_bw, grad[(int64_t)j * d + c]);
+            else if (c == d) v = 1.f;
+        }
+        t[r][tx] = v;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int c = c0 + r, j = j0 + tx;
+        if (c <= d && j < n) {
+            float h, l;
+            umma::split_tf32(t[tx][r], h, l);
+            hi[(int64_t)c * ldn + j] = h;
+            lo[(int64_t)c * ldn + j] = l;
+        }
+    }
+}
+
+constexpr int SVGD_TC_BN = 144;        // update GEMM N tile: d + 1 <= 144
+
 struct SvgdWorkspace {
     float* D2;
     unsigned int* hist;
     SelectState* st;
+    float *th_hi, *th_lo, *sq, *vt_hi, *vt_lo;
+    int64_t ldd, ldn;
     size_t bytes;
-    SvgdWorkspace(void* base, int n) {
+    SvgdWorkspace(void* base, int n, int d) {
         size_t off = 0;
         auto take = [&](size_t nbytes) {
             char* p = base ? reinterpret_cast<char*>(base) + off : nullptr;
@@ -314,6 +427,14 @@ struct SvgdWorkspace {
         D2 = reinterpret_cast<float*>(take(sizeof(float) * (size_t)n * n));
         hist = reinterpret_cast<unsigned int*>(take(sizeof(unsigned int) * 4096));
         st = reinterpret_cast<SelectState*>(take(sizeof(SelectState)));
+        // tensor-core variant: theta (hi, lo) [n][ldd], |theta|^2 [n], V^T (hi, lo) [d + 1][ldn]
+        ldd = (d + 3) / 4 * 4;
+        ldn = (n + 3) / 4 * 4;
+        th_hi = reinterpret_cast<float*>(take(sizeof(float) * (size_t)n * ldd));
+        th_lo = reinterpret_cast<float*>(take(sizeof(float) * (size_t)n * ldd));
+        sq = reinterpret_cast<float*>(take(sizeof(float) * (size_t)n));
+        vt_hi = reinterpret_cast<float*>(take(sizeof(float) * (size_t)(d + 1) * ldn));
+        vt_lo = reinterpret_cast<float*>(take(sizeof(float) * (size_t)(d + 1) * ldn));
         bytes = off;
     }
 };
@@ -324,7 +445,7 @@ using namespace brn;
 
 extern "C" size_t brn_svgd_workspace_bytes(int n, int d) {
     if (n <= 0 || d <= 0) return 0;
-    return SvgdWorkspace(nullptr, n).bytes;
+    return SvgdWorkspace(nullptr, n, d).bytes;
 }
 
 extern "C" int brn_svgd_direction(const float* theta, const float* grad, int n, int d, int row0, int rows,
@@ -335,17 +456,35 @@ extern "C" int brn_svgd_direction(const float* theta, const float* grad, int n, 
     BRN_CHECK_ARG(n >= 2 && d > 0, "brn_svgd_direction: need n >= 2 particles and d > 0 (got n=%d d=%d)", n, d);
     BRN_CHECK_ARG(row0 >= 0 && rows >= 0 && row0 + rows <= n, "brn_svgd_direction: bad row range [%d, %d) of %d", row0,
                   row0 + rows, n);
-    SvgdWorkspace ws(workspace, n);
+    SvgdWorkspace ws(workspace, n, d);
     BRN_CHECK_ARG(workspace && workspace_bytes >= ws.bytes, "workspace too small: %zu < %zu", workspace_bytes, ws.bytes);
-    set_variant("simt");
+    // tensor-core variant (tcgen05) for ensembles large enough to fill the tiles; BRN_SVGD_VARIANT=simt|tcgen05 forces one
+    bool use_tc = n >= 512 && n % 4 == 0 && d + 1 <= SVGD_TC_BN && d >= 8;
+    if (const char* env = getenv("BRN_SVGD_VARIANT")) {
+        if (!strcmp(env, "simt")) use_tc = false;
+        else if (!strcmp(env, "tcgen05")) {
+            BRN_CHECK_ARG(d + 1 <= SVGD_TC_BN && n % 4 == 0, "BRN_SVGD_VARIANT=tcgen05 needs d < %d and n %% 4 == 0 (got d=%d n=%d)",
+                          SVGD_TC_BN, d, n);
+            use_tc = true;
+        }
+    }
+    set_variant(use_tc ? "tcgen05" : "simt");
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     {
         StageTimer st("svgd.pairwise_d2", stream);
-        dim3 grid((n + SV_T - 1) / SV_T, (n + SV_T - 1) / SV_T);
-        svgd_d2_kernel<<<grid, 256, 0, stream>>>(theta, n, d, ws.D2);
-        BRN_LAUNCH_OK("svgd_d2_kernel");
+        if (use_tc) {
+            svgd_prep_theta_kernel<<<(n + 3) / 4, 128, 0, stream>>>(theta, n, d, ws.ldd, ws.th_hi, ws.th_lo, ws.sq);
+            BRN_LAUNCH_OK("svgd_prep_theta_kernel");
+            EpiD2::Params ep{ws.sq, ws.D2, n, n, 0};
+            if (int e = launch_umma_nt<208, 16, EpiD2>(ws.th_hi, ws.th_lo, n, ws.ldd, ws.th_hi, ws.th_lo, n, ws.ldd, d, 0, 2, ep, stream))
+                return e;
+        } else {
+            dim3 grid((n + SV_T - 1) / SV_T, (n + SV_T - 1) / SV_T);
+            svgd_d2_kernel<<<grid, 256, 0, stream>>>(theta, n, d, ws.D2);
+            BRN_LAUNCH_OK("svgd_d2_kernel");
+        }
     }
     if (update_bandwidth) {
         StageTimer st("svgd.median_bandwidth", stream);
@@ -369,7 +508,19 @@ extern "C" int brn_svgd_direction(const float* theta, const float* grad, int n, 
         svgd_bandwidth_kernel<<<1, 32, 0, stream>>>(ws.st, k2, n, bandwidth);
         BRN_LAUNCH_OK("svgd_bandwidth_kernel");
     }
-    if (rows > 0) {
+    if (rows > 0 && use_tc) {
+        StageTimer st("svgd.update", stream);
+        dim3 grid((n + 31) / 32, (d + 1 + 31) / 32);
+        svgd_prep_v_kernel<<<grid, 256, 0, stream>>>(theta, grad, n, d, bandwidth, ws.vt_hi, ws.vt_lo, ws.ldn);
+        BRN_LAUNCH_OK("svgd_prep_v_kernel");
+        BRN_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)rows * d, stream));
+        EpiSvgdOut::Params ep{out, theta, bandwidth, rows, d, row0};
+        // A = D2 rows [rows][n] (plain fp32: exponentiated + split by the converter warps), B = V^T [d + 1][n]; K = n is split
+        // over the grid (few output tiles) and the slices accumulate with atomics into the zeroed output
+        if (int e = launch_umma_nt<SVGD_TC_BN, 16, EpiSvgdOut, 4, 1, 4>(ws.D2 + (size_t)row0 * n, nullptr, rows, n, ws.vt_hi, ws.vt_lo,
+                                                                        d + 1, ws.ldn, n, 0, 2, ep, stream, true))
+            return e;
+    } else if (rows > 0) {
         StageTimer st("svgd.update", stream);
         const int row_tiles = (rows + SU_TI - 1) / SU_TI, d_chunks = (d + SU_TD - 1) / SU_TD;
         // ~8 CTAs (32 warps) per SM: with 2 the kernel ran at 7 warps per SM and 9.5 TFLOP/s (profiles/r1n_launches_svgd_summary.txt)

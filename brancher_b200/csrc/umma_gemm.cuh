@@ -14,6 +14,7 @@
 #pragma once
 #include "common.cuh"
 #include "umma.cuh"
+#include <type_traits>
 
 namespace brn {
 
@@ -23,6 +24,14 @@ constexpr int UG_BM = 128;        // rows of A per tile (TMEM lanes)
 // time waiting for the next 86 KB stage (ncu: profiles/r1a_*), the 5-stage ring hides that latency.
 constexpr int UG_BUF_COLS = 256;  // TMEM column stride between the two accumulator buffers
 constexpr int UG_EPI_WARPS = 8;   // epilogue warps: 4 TMEM lane quarters x 2 column halves
+
+// an epilogue policy may declare `static constexpr bool TRANSFORMS_A = true` together with transform_a_context(params) ->
+// float and transform_a(ctx, x) -> float: the converter warps of a SPLIT & 1 kernel then map every A element before
+// splitting it
+template <class Epi, class = void>
+struct epi_transforms_a : std::false_type {};
+template <class Epi>
+struct epi_transforms_a<Epi, std::void_t<decltype(Epi::TRANSFORMS_A)>> : std::bool_constant<Epi::TRANSFORMS_A> {};
 
 template <int BN, int BK>
 struct UmmaSmem {
@@ -190,17 +199,26 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
         // ===================== converter warps (SPLIT_A) =====================
         // 128 threads, A_BYTES / 16 float4 per stage; element-wise and in place, so the swizzle TMA applied is irrelevant
         const int ct = threadIdx.x - 32 * (2 + EW);
+        float a_ctx = 0.f;
+        if constexpr (epi_transforms_a<Epi>::value) a_ctx = Epi::transform_a_context(ep);
+        (void)a_ctx;
         int stage = 0; uint32_t phase = 0;
         for (UnitIter it(m_tiles, n_tiles, k_chunks, mode, split_T, full_units); it.valid(); it.next()) {
             const int kcb = it.kc_begin(), kce = it.kc_end();
             for (int kc = kcb; kc < kce; ++kc) {
                 umma::mbar_wait(&full_bar[stage], phase);
-                auto convert = [&](uint8_t* hi_slot, int slot_bytes) {
+                auto convert = [&](uint8_t* hi_slot, int slot_bytes, bool is_a) {
                     float4* xh = reinterpret_cast<float4*>(hi_slot);
                     float4* xl = reinterpret_cast<float4*>(hi_slot + slot_bytes);
 #pragma unroll 4
                     for (int j = ct; j < slot_bytes / 16; j += 32 * UG_CONV_WARPS) {
-                        const float4 x = xh[j];
+                        float4 x = xh[j];
+                        if constexpr (epi_transforms_a<Epi>::value) {
+                            // element-wise map applied to the A operand on its way into the tensor core (K4b: the RBF kernel
+                            // exp(-D2 / 2bw) is never materialised -- the GEMM reads D2 and multiplies by its exponential)
+                            if (is_a) { x.x = Epi::transform_a(a_ctx, x.x); x.y = Epi::transform_a(a_ctx, x.y);
+                                        x.z = Epi::transform_a(a_ctx, x.z); x.w = Epi::transform_a(a_ctx, x.w); }
+                        }
                         float4 h, l;
                         umma::split_tf32(x.x, h.x, l.x); umma::split_tf32(x.y, h.y, l.y);
                         umma::split_tf32(x.z, h.z, l.z); umma::split_tf32(x.w, h.w, l.w);
@@ -209,8 +227,8 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
                     }
                 };
                 uint8_t* st = smem + stage * SM::STAGE_BYTES;
-                if (SPLIT_A) convert(st, SM::A_BYTES);
-                if (SPLIT_B) convert(st + 2 * SM::A_BYTES, SM::B_BYTES);
+                if (SPLIT_A) convert(st, SM::A_BYTES, true);
+                if (SPLIT_B) convert(st + 2 * SM::A_BYTES, SM::B_BYTES, false);
                 umma::fence_proxy_async();        // generic-proxy writes -> visible to the tensor core's async-proxy reads
                 __syncwarp();
                 if (lane == 0) umma::mbar_arrive(&conv_bar[stage]);

@@ -126,3 +126,25 @@ def test_particles_loss_grad_tcgen05_variant(cu, monkeypatch, N, F, n, force):
     assert cu.last_variant() == "tcgen05"
     assert_close(loss.item(), l64, "particles loss (tcgen05)")
     assert_close(G.cpu().numpy().reshape(g64.shape), g64, "particles grad (tcgen05)", scale=np.abs(g64).max())
+
+
+@pytest.mark.parametrize("n,d,rows", [(512, 128, None), (1000, 33, None), (4096, 128, None), (2048, 100, (512, 700))])
+def test_svgd_direction_tcgen05_variant(cu, monkeypatch, n, d, rows):
+    """K4b on the tensor cores: D2 through the theta.theta^T GEMM (norms in the epilogue), the update as a GEMM whose A
+    operand is exponentiated by the converter warps; exact median unchanged.  Same tolerance as the SIMT variant; a row
+    shard (particles sharded over ranks) equals the corresponding rows of the full update."""
+    from oracle import elbo_oracle as O
+    monkeypatch.setenv("BRN_SVGD_VARIANT", "tcgen05")
+    rng = np.random.RandomState(n + d)
+    theta = rng.randn(n, d).astype("f4")
+    grad = rng.randn(n, d).astype("f4")
+    want, bw64 = O.svgd_direction(theta, grad)
+    if rows is None:
+        out, bw = cu.svgd_direction(dev(theta), dev(grad))
+        sel = slice(None)
+    else:
+        out, bw = cu.svgd_direction(dev(theta), dev(grad), row0=rows[0], rows=rows[1])
+        sel = slice(rows[0], rows[0] + rows[1])
+    assert cu.last_variant() == "tcgen05"
+    assert abs(bw.item() - bw64) <= 2e-6 * bw64, (bw.item(), bw64)
+    assert_close(out.cpu().numpy(), want[sel], "svgd tcgen05 n=%d d=%d" % (n, d), scale=np.abs(want).max())
