@@ -368,6 +368,50 @@ def main_reference(args):
     emit(out)
 
 
+def api_e2e(dev):
+    """What a user of the drop-in API runs: inference.perform_inference(...) wall-clock per iteration, everything included
+    (lowering is cached by a first short call; the timed call covers plan lookup, graph capture, all iterations and the final
+    read-back of the loss curve).  C1 = README AR(1), S = 300, SGD, 500 iterations; C3 = the BNN through the model API."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import model_zoo as zoo
+    from brancher_b200 import config, inference
+    config.set_device(dev)
+    ns = zoo.namespace("brancher_b200")
+    out = {}
+
+    def run(build, iters, S, opt, **kw):
+        model = build()
+        inference.perform_inference(model, number_iterations=3, number_samples=S, optimizer=opt,
+                                    inference_method=inference.ReverseKL(), **kw)          # lowering + first-call costs
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        inference.perform_inference(model, number_iterations=iters, number_samples=S, optimizer=opt,
+                                    inference_method=inference.ReverseKL(), **kw)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        curve = np.asarray(model.diagnostics["loss curve"]).reshape(-1)
+        return dt / iters, inference.last_loop, bool(np.isfinite(curve).all())
+
+    try:
+        import io, contextlib
+        with contextlib.redirect_stderr(io.StringIO()):          # tqdm bars of the step-by-step loop
+            t, loop, ok = run(lambda: zoo.ar1(ns, 6, 20)[0], 500, 300, "SGD", lr=1e-3)
+            out["c1_ar1"] = {"us_per_iteration": 1e6 * t, "iterations": 500, "number_samples": 300, "optimizer": "SGD", "loop": loop,
+                             "finite": ok}
+            inference.fused_loop_enabled = False
+            t, loop, ok = run(lambda: zoo.ar1(ns, 6, 20)[0], 100, 300, "SGD", lr=1e-3)
+            inference.fused_loop_enabled = True
+            out["c1_ar1_stepwise"] = {"us_per_iteration": 1e6 * t, "iterations": 100, "loop": loop}
+            t, loop, ok = run(lambda: zoo.bnn(ns, 0, B=1024, P=784, H=100, C=10)[0], 200, 256, "Adam", lr=1e-3)
+            out["c3_bnn"] = {"ms_per_iteration": 1e3 * t, "iterations": 200, "number_samples": 256, "optimizer": "Adam", "loop": loop,
+                             "finite": ok, "value": 256 * 1024 / t, "unit": UNIT}
+    except Exception as exc:        # pragma: no cover
+        out["error"] = repr(exc)
+    finally:
+        inference.fused_loop_enabled = True
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
@@ -746,6 +790,8 @@ def main_ours(args):
         if world > 1:
             out["config"]["collective"] = ("one-shot all-reduce over NVLink peer memory (csrc/allreduce.cu), inside the captured "
                                            "step" if any(distributed._oneshot.values()) else "NCCL all_reduce")
+        if world == 1 and wl == "bnn" and not args.no_api:
+            out["api_e2e"] = api_e2e(dev)
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = run_cpu_baseline(wl, cfg)
         emit(out)
@@ -762,6 +808,7 @@ if __name__ == "__main__":
     ap.add_argument("--workload", default="bnn", choices=sorted(WORKLOADS))
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-api", action="store_true", help="skip the perform_inference (API-level) timing block")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":
