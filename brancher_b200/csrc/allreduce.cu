@@ -20,62 +20,78 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     return v;
 }
 
-// step 1: src -> this rank's symmetric buffer of the coming epoch's parity
+// ONE kernel: (1) every block copies its slice of src into this rank's symmetric buffer of the coming epoch's parity and
+// arrives on a local counter; (2) block 0 waits for all local blocks, then raises this rank's flag in every peer's flag
+// array; (3) every block waits for all peers' flags of this epoch and sums the peers' buffers in rank order (the loads of
+// one element from all peers are issued together: one NVLink round trip, not `world` of them).  status counts wait
+// time-outs (a dead peer must not hang the GPU).  All blocks are co-resident (grid <= number of SMs).
 // loss != NULL: the fp64 partial loss rides in the buffer's last quad as a (hi, lo) fp32 pair (elements n-4, n-3; the
 // caller's src keeps that quad spare) and comes back summed -- no separate collective, no packing kernels.
-__global__ void __launch_bounds__(256)
-allreduce_stage_kernel(const float* __restrict__ src, float* const* __restrict__ bufs, int rank, int world, int64_t n,
-                       const unsigned long long* __restrict__ epoch, const double* __restrict__ loss) {
-    const unsigned long long e = *epoch + 1ull;
-    float* dst = bufs[(e & 1ull) * world + rank];
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        float v = src[i];
-        if (loss && i >= n - 4) {
-            const double l = *loss;
-            const float hi = (float)l;
-            v = i == n - 4 ? hi : (i == n - 3 ? (float)(l - (double)hi) : 0.f);
-        }
-        dst[i] = v;
-    }
-}
+constexpr int AR_MAX_WORLD = 16;
 
-// step 2: flags, wait, reduce.  status[0] counts wait time-outs (a dead peer must not hang the GPU).
 __global__ void __launch_bounds__(256)
-allreduce_reduce_kernel(float* __restrict__ out, float* const* __restrict__ bufs, unsigned long long* const* __restrict__ flags,
-                        int rank, int world, int64_t n, unsigned long long* __restrict__ epoch, unsigned int* __restrict__ ticket,
-                        unsigned int* __restrict__ status, double* __restrict__ loss) {
+allreduce_oneshot_kernel(const float* __restrict__ src, float* __restrict__ out, float* const* __restrict__ bufs,
+                         unsigned long long* const* __restrict__ flags, int rank, int world, int64_t n,
+                         unsigned long long* __restrict__ epoch, unsigned int* __restrict__ arrive, unsigned int* __restrict__ ticket,
+                         unsigned int* __restrict__ status, double* __restrict__ loss) {
     const unsigned long long e = *epoch + 1ull;
     const int par = (int)(e & 1ull);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     __shared__ int timed_out;
     if (threadIdx.x == 0) timed_out = 0;
-    if (blockIdx.x == 0 && (int)threadIdx.x < world) {
-        __threadfence_system();                                   // the staged copy (previous kernel) is visible before the flag
-        st_release_sys(flags[threadIdx.x] + rank, e);              // peer threadIdx.x: "rank's buffer of epoch e is complete"
+    // (1) stage
+    {
+        float* dst = bufs[par * world + rank];
+        for (int64_t i = tid0; i < n; i += stride) {
+            float v = src[i];
+            if (loss && i >= n - 4) {
+                const double l = *loss;
+                const float hi = (float)l;
+                v = i == n - 4 ? hi : (i == n - 3 ? (float)(l - (double)hi) : 0.f);
+            }
+            dst[i] = v;
+        }
     }
+    __threadfence_system();
     __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(arrive, 1u);
+    // (2) block 0: all local slices staged -> tell every peer
+    if (blockIdx.x == 0) {
+        if (threadIdx.x == 0) {
+            const unsigned int want = (unsigned int)(e * gridDim.x);           // monotone across launches (same grid every call)
+            long long spins = 0;
+            while (*reinterpret_cast<volatile unsigned int*>(arrive) != want && ++spins < (1ll << 26)) {}
+            __threadfence_system();
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < world) st_release_sys(flags[threadIdx.x] + rank, e);
+    }
+    // (3) wait for every peer's flag of this epoch
     if ((int)threadIdx.x < world) {
         const unsigned long long* f = flags[rank] + threadIdx.x;
         long long spins = 0;
         while (ld_acquire_sys(f) < e) {
             if (++spins > (1ll << 24)) { timed_out = 1; break; }   // ~ seconds: give up instead of hanging the device
-            __nanosleep(64);
+            __nanosleep(32);
         }
     }
     __syncthreads();
     if (timed_out && threadIdx.x == 0) atomicAdd(status, 1u);
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t n4 = n / 4;
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
+    for (int64_t q = tid0; q < n4; q += stride) {
+        float4 v[AR_MAX_WORLD];
+#pragma unroll
+        for (int j = 0; j < AR_MAX_WORLD; ++j)
+            if (j < world) v[j] = __ldcv(reinterpret_cast<const float4*>(bufs[par * world + j]) + q);     // never a stale L1 line
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int j = 0; j < world; ++j) {
-            const float4 v = __ldcv(reinterpret_cast<const float4*>(bufs[par * world + j]) + q);     // never from a stale L1 line
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-        }
+#pragma unroll
+        for (int j = 0; j < AR_MAX_WORLD; ++j)
+            if (j < world) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
         reinterpret_cast<float4*>(out)[q] = acc;
         if (loss && q == n4 - 1) *loss = (double)acc.x + (double)acc.y;       // n % 4 == 0 when a loss rides along
     }
-    for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    for (int64_t i = n4 * 4 + tid0; i < n; i += stride) {
         float acc = 0.f;
         for (int j = 0; j < world; ++j) acc += __ldcv(bufs[par * world + j] + i);
         out[i] = acc;
@@ -103,13 +119,18 @@ extern "C" int brn_allreduce_oneshot(const float* src, float* out, int64_t n, fl
                   (long long)n, rank, world);
     BRN_CHECK_ARG(((uintptr_t)out & 15) == 0, "brn_allreduce_oneshot: out must be 16-byte aligned");
     BRN_CHECK_ARG(!loss_inout || (n % 4 == 0 && n >= 4), "brn_allreduce_oneshot: a loss needs n %% 4 == 0 (its (hi, lo) pair uses the last quad)");
+    BRN_CHECK_ARG(world <= AR_MAX_WORLD, "brn_allreduce_oneshot: at most %d ranks (got %d)", AR_MAX_WORLD, world);
     unsigned long long* epoch = reinterpret_cast<unsigned long long*>(state_dev);
     unsigned int* ticket = reinterpret_cast<unsigned int*>(state_dev + 1);
     unsigned int* status = ticket + 1;
-    const unsigned grid = (unsigned)std::min<int64_t>((n / 4 + 255) / 256 + 1, 148);
-    allreduce_stage_kernel<<<grid, 256, 0, stream>>>(src, bufs_dev, rank, world, n, epoch, loss_inout);
-    BRN_LAUNCH_OK("allreduce_stage_kernel");
-    allreduce_reduce_kernel<<<grid, 256, 0, stream>>>(out, bufs_dev, flags_dev, rank, world, n, epoch, ticket, status, loss_inout);
-    BRN_LAUNCH_OK("allreduce_reduce_kernel");
+    unsigned int* arrive = reinterpret_cast<unsigned int*>(state_dev + 2);
+    // the grid is a pure function of n (the arrival counter assumes the same grid on every call of a given state)
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned grid = (unsigned)std::min<int64_t>((n / 4 + 255) / 256 + 1, sms);
+    allreduce_oneshot_kernel<<<grid, 256, 0, stream>>>(src, out, bufs_dev, flags_dev, rank, world, n, epoch, arrive, ticket, status,
+                                                       loss_inout);
+    BRN_LAUNCH_OK("allreduce_oneshot_kernel");
     return 0;
 }

@@ -73,7 +73,7 @@ class OneShotAllReduce:
         flags = [ptrs[r] + 2 * pad * 4 for r in range(self.world)]
         self.bufs_dev = torch.tensor(bufs, dtype=torch.int64, device=device)
         self.flags_dev = torch.tensor(flags, dtype=torch.int64, device=device)
-        self.state = torch.zeros(2, dtype=torch.int64, device=device)
+        self.state = torch.zeros(3, dtype=torch.int64, device=device)
         torch.cuda.synchronize(device)
         dist.barrier()                      # every rank's flags are zero before anybody raises one
 

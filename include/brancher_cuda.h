@@ -329,10 +329,10 @@ int brn_opt_step(const brn_opt_tensor* table_dev, const int64_t* prefix_dev, int
  * sample- / row-sharded evaluation: out[i] = sum_r src_r[i], summed in rank order on every rank (bit-identical results).
  * bufs_dev: DEVICE array [2 * world] of pointers, bufs[p * world + r] = rank r's symmetric buffer of parity p (n floats each,
  * 16-byte aligned, mapped into this process); flags_dev: DEVICE array [world], flags[r] = rank r's flag array (world
- * uint64, zero-initialised); state_dev: LOCAL device uint64[2], zero-initialised: {epoch, (ticket, time-out count)}.
+ * uint64, zero-initialised); state_dev: LOCAL device uint64[3], zero-initialised: {epoch, (ticket, time-out count), arrivals}; at most 16 ranks.
  * loss_inout (optional, device fp64 [1]): the partial loss travels in the buffer's LAST quad (elements n-4, n-3; needs
  * n % 4 == 0, the caller's src keeps that quad spare) as a (hi, lo) fp32 pair and is returned summed over ranks.
- * All ranks must issue the same sequence of calls.  Enqueues two kernels; capturable in a CUDA graph. */
+ * All ranks must issue the same sequence of calls (same n per state).  Enqueues ONE kernel; capturable in a CUDA graph. */
 int brn_allreduce_oneshot(const float* src, float* out, int64_t n, float* const* bufs_dev,
                           unsigned long long* const* flags_dev, int rank, int world, uint64_t* state_dev,
                           double* loss_inout, void* stream);
