@@ -98,9 +98,12 @@ SYMBOLS = {
     "brn_bnn_elbo_fwd_bwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 4 +
                              [ctypes.POINTER(MFVar), ctypes.POINTER(SampleRange), ctypes.c_void_p, ctypes.c_size_t,
                               ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
-    "brn_bnn_predict": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.POINTER(MFVar), ctypes.POINTER(SampleRange),
+    "brn_bnn_predict": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_int] * 5 + [ctypes.POINTER(MFVar), ctypes.POINTER(SampleRange),
                                        ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_void_p]),
+    "brn_bnn_elbo_fwd_bwd_act": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 5 +
+                                 [ctypes.POINTER(MFVar), ctypes.POINTER(SampleRange), ctypes.c_void_p, ctypes.c_size_t,
+                                  ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "brn_linear_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "brn_linear_elbo_fwd_bwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
                                                ctypes.c_int, ctypes.c_int, ctypes.POINTER(MFVar),
@@ -302,7 +305,10 @@ def mf_normal_prior_entropy(var, r, loss=None):
     return loss
 
 
-def bnn_elbo_fwd_bwd(X, y, vars4, r, with_prior=True, loss=None, data_ready=None):
+ACTIVATIONS = {"tanh": 0, "relu": 1, "sigmoid": 2}
+
+
+def bnn_elbo_fwd_bwd(X, y, vars4, r, with_prior=True, loss=None, data_ready=None, activation="tanh"):
     """K3.  X [B,P] fp32, y [B] int32, vars4 = MeanFieldVar for (weights1 [H,P], b1 [H], weights2 [C,H], b2 [C]).
     data_ready: a torch.cuda.Event recorded on the stream that is still copying X / y to the device; the evaluation waits
     for it only before its first read of the minibatch, so noise generation and weight sampling overlap the copy."""
@@ -318,13 +324,13 @@ def bnn_elbo_fwd_bwd(X, y, vars4, r, with_prior=True, loss=None, data_ready=None
     arr = (MFVar * 4)(*[v.struct() for v in vars4])
     if data_ready is not None:
         lib().brn_set_data_ready_event(ctypes.c_void_p(data_ready.cuda_event))
-    _check(lib().brn_bnn_elbo_fwd_bwd(_ptr(X, what="X"), _ptr(y, torch.int32, "y"), B, P, H, C, arr, ctypes.byref(r),
-                                      ws.data_ptr(), ws.numel(), int(with_prior), _ptr(loss, torch.float64),
-                                      _stream(dev)), "brn_bnn_elbo_fwd_bwd")
+    _check(lib().brn_bnn_elbo_fwd_bwd_act(_ptr(X, what="X"), _ptr(y, torch.int32, "y"), B, P, H, C, ACTIVATIONS[activation], arr,
+                                          ctypes.byref(r), ws.data_ptr(), ws.numel(), int(with_prior), _ptr(loss, torch.float64),
+                                          _stream(dev)), "brn_bnn_elbo_fwd_bwd")
     return loss
 
 
-def bnn_predict(X, vars4, r, labels=True, probs=True):
+def bnn_predict(X, vars4, r, labels=True, probs=True, activation="tanh"):
     """K3 forward only: posterior-predictive pass for a batch.  Returns (logits [s_local,B,C], labels int32 [s_local,B] or
     None, probs_mean [B,C] or None: this rank's share of the MC average of softmax(logits))."""
     dev = X.device
@@ -336,7 +342,7 @@ def bnn_predict(X, vars4, r, labels=True, probs=True):
     logits = torch.empty((r.s_local, B, C), dtype=torch.float32, device=dev)
     lab = torch.empty((r.s_local, B), dtype=torch.int32, device=dev) if labels else None
     pm = torch.zeros((B, C), dtype=torch.float32, device=dev) if probs else None
-    _check(lib().brn_bnn_predict(_ptr(X, what="X"), B, P, H, C, arr, ctypes.byref(r), ws.data_ptr(), ws.numel(), _ptr(logits),
+    _check(lib().brn_bnn_predict(_ptr(X, what="X"), B, P, H, C, ACTIVATIONS[activation], arr, ctypes.byref(r), ws.data_ptr(), ws.numel(), _ptr(logits),
                                  _ptr(lab, torch.int32), _ptr(pm), _stream(dev)), "brn_bnn_predict")
     return logits, lab, pm
 

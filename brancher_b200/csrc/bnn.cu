@@ -18,10 +18,20 @@ namespace brn {
 
 constexpr int BNN_MAXC = 16;
 
+// hidden activation (the matcher accepts BF.tanh / BF.relu / BF.sigmoid): value and derivative, the latter from the
+// activation's OUTPUT h, which is all the backward stages keep
+constexpr int ACT_TANH = 0, ACT_RELU = 1, ACT_SIGMOID = 2;
+__device__ __forceinline__ float act_grad_from_h(int act, float h) {
+    return act == ACT_TANH ? __fmaf_rn(-h, h, 1.f) : (act == ACT_RELU ? (h > 0.f ? 1.f : 0.f) : h * (1.f - h));
+}
+__device__ __forceinline__ float act_exact(int act, float x) {        // SIMT variant / predictive pass: libm accuracy
+    return act == ACT_TANH ? tanhf(x) : (act == ACT_RELU ? fmaxf(x, 0.f) : 1.f / (1.f + expf(-x)));
+}
+
 struct BnnLayout {
-    int B, P, H, C;
+    int B, P, H, C, act;
     int64_t oW1, ob1, oW2, ob2, numel, ldw;
-    __host__ __device__ BnnLayout(int B_, int P_, int H_, int C_) : B(B_), P(P_), H(H_), C(C_) {
+    __host__ __device__ BnnLayout(int B_, int P_, int H_, int C_, int act_ = 0) : B(B_), P(P_), H(H_), C(C_), act(act_) {
         oW1 = 0;
         ob1 = (int64_t)H * P;
         oW2 = ob1 + H;
@@ -79,7 +89,7 @@ __global__ void bnn_mid_kernel(float* __restrict__ pre, const float* __restrict_
 #pragma unroll
         for (int c = 0; c < BNN_MAXC; ++c) a[c] = 0.f;
         for (int h = 0; h < H; ++h) {
-            float v = tanhf(tile[r * HP + h] + b1s[h]);
+            float v = act_exact(L.act, tile[r * HP + h] + b1s[h]);
             tile[r * HP + h] = v;
 #pragma unroll
             for (int c = 0; c < BNN_MAXC; ++c)
@@ -132,7 +142,7 @@ __global__ void bnn_mid_kernel(float* __restrict__ pre, const float* __restrict_
 #pragma unroll
             for (int c = 0; c < BNN_MAXC; ++c)
                 if (c < C) dh = __fmaf_rn(da[c], W2s[c * H + h], dh);
-            tile[r * HP + h] = dh * (1.f - hv * hv);
+            tile[r * HP + h] = dh * act_grad_from_h(L.act, hv);
         }
     }
     __syncthreads();
@@ -232,7 +242,7 @@ bnn_mid2_kernel(float* __restrict__ pre, const float* __restrict__ W, float* __r
 #pragma unroll
     for (int c = 0; c < BNN_MAXC; ++c) a[c] = 0.f;
     for (int h = h0; h < h1; ++h) {
-        float v = tanhf(tile[r * HP1 + h] + b1s[h]);
+        float v = act_exact(L.act, tile[r * HP1 + h] + b1s[h]);
         tile[r * HP1 + h] = v;
 #pragma unroll
         for (int c = 0; c < BNN_MAXC; ++c)
@@ -313,7 +323,7 @@ bnn_mid2_kernel(float* __restrict__ pre, const float* __restrict__ W, float* __r
 #pragma unroll
         for (int c = 0; c < BNN_MAXC; ++c)
             if (c < C) dh = __fmaf_rn(da[c], W2s[c * H + h], dh);
-        tile[r * HP1 + h] = dh * (1.f - hv * hv);
+        tile[r * HP1 + h] = dh * act_grad_from_h(L.act, hv);
     }
     __syncthreads();
 
@@ -372,7 +382,7 @@ bnn_predict_kernel(const float* __restrict__ pre, const float* __restrict__ W, B
 #pragma unroll
     for (int c = 0; c < BNN_MAXC; ++c) a[c] = 0.f;
     for (int h = 0; h < H; ++h) {
-        const float v = tanhf((PRE_T ? ps[(int64_t)h * B + b] : ps[(int64_t)b * H + h]) + b1s[h]);
+        const float v = act_exact(L.act, (PRE_T ? ps[(int64_t)h * B + b] : ps[(int64_t)b * H + h]) + b1s[h]);
 #pragma unroll
         for (int c = 0; c < BNN_MAXC; ++c)
             if (c < C) a[c] = __fmaf_rn(W2s[c * H + h], v, a[c]);
@@ -448,13 +458,20 @@ extern "C" size_t brn_bnn_workspace_bytes(int B, int P, int H, int C, int s_loca
 extern "C" int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int P, int H, int C,
                                     const brn_mf_var vars[4], const brn_sample_range* r, void* workspace,
                                     size_t workspace_bytes, int with_prior, double* loss, void* stream_) {
+    return brn_bnn_elbo_fwd_bwd_act(X, y, B, P, H, C, BRN_ACT_TANH, vars, r, workspace, workspace_bytes, with_prior, loss, stream_);
+}
+
+extern "C" int brn_bnn_elbo_fwd_bwd_act(const float* X, const int32_t* y, int B, int P, int H, int C, int activation,
+                                        const brn_mf_var vars[4], const brn_sample_range* r, void* workspace,
+                                        size_t workspace_bytes, int with_prior, double* loss, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     BRN_CHECK_ARG(X && y && vars && r && loss, "brn_bnn_elbo_fwd_bwd: NULL pointer");
+    BRN_CHECK_ARG(activation >= 0 && activation <= 2, "brn_bnn_elbo_fwd_bwd: unknown activation %d", activation);
     BRN_CHECK_ARG(B > 0 && P > 0 && H > 0 && C > 0, "brn_bnn_elbo_fwd_bwd: bad shape B=%d P=%d H=%d C=%d", B, P, H, C);
     BRN_CHECK_ARG(C <= BNN_MAXC, "brn_bnn_elbo_fwd_bwd: C=%d exceeds the supported maximum %d", C, BNN_MAXC);
     BRN_CHECK_ARG(r->s_local >= 0 && r->s_total > 0 && r->s0 >= 0 && r->s0 + r->s_local <= r->s_total,
                   "bad sample range s0=%d s_local=%d s_total=%d", r->s0, r->s_local, r->s_total);
-    BnnLayout L(B, P, H, C);
+    BnnLayout L(B, P, H, C, activation);
     const int64_t numels[4] = {(int64_t)H * P, H, (int64_t)C * H, C};
     const int64_t offs[4] = {L.oW1, L.ob1, L.oW2, L.ob2};
     for (int v = 0; v < 4; ++v) {
@@ -543,15 +560,16 @@ extern "C" int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int
     return launch_mf_reduce_finalize_multi(vars, offs, 4, L.numel, ws.eps, L.ldw, ws.dW, L.ldw, ws.stats, *r, with_prior, loss, stream, 0);
 }
 
-extern "C" int brn_bnn_predict(const float* X, int B, int P, int H, int C, const brn_mf_var vars[4], const brn_sample_range* r,
-                               void* workspace, size_t workspace_bytes, float* logits, int32_t* labels, float* probs_mean,
-                               void* stream_) {
+extern "C" int brn_bnn_predict(const float* X, int B, int P, int H, int C, int activation, const brn_mf_var vars[4],
+                               const brn_sample_range* r, void* workspace, size_t workspace_bytes, float* logits, int32_t* labels,
+                               float* probs_mean, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
+    BRN_CHECK_ARG(activation >= 0 && activation <= 2, "brn_bnn_predict: unknown activation %d", activation);
     BRN_CHECK_ARG(X && vars && r && logits, "brn_bnn_predict: NULL pointer");
     BRN_CHECK_ARG(B > 0 && P > 0 && H > 0 && C > 0 && C <= BNN_MAXC, "brn_bnn_predict: bad shape B=%d P=%d H=%d C=%d", B, P, H, C);
     BRN_CHECK_ARG(r->s_local >= 0 && r->s_total > 0 && r->s0 >= 0 && r->s0 + r->s_local <= r->s_total,
                   "bad sample range s0=%d s_local=%d s_total=%d", r->s0, r->s_local, r->s_total);
-    BnnLayout L(B, P, H, C);
+    BnnLayout L(B, P, H, C, activation);
     const int64_t numels[4] = {(int64_t)H * P, H, (int64_t)C * H, C};
     const int64_t offs[4] = {L.oW1, L.ob1, L.oW2, L.ob2};
     for (int v = 0; v < 4; ++v) {

@@ -168,6 +168,15 @@ __device__ __forceinline__ float tanh_fast(float x) {
     return fabsf(x) < 0.25f ? small : big;
 }
 
+// fast activations for the tensor-core variant (MUFU ex2 / rcp: absolute error ~1e-7)
+__device__ __forceinline__ float act_fast(int act, float x) {
+    if (act == ACT_TANH) return tanh_fast(x);
+    if (act == ACT_RELU) return fmaxf(x, 0.f);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+    return __fdividef(1.f, 1.f + e);
+}
+
 // hi = x rounded to TF32; lo = the exact remainder, NOT re-rounded: mma.sync reads only the TF32 bits of an operand
 // register, i.e. truncates lo (relative error <= 2^-21 of x, sign uncorrelated with x) -- used for mma.sync operands only.
 __device__ __forceinline__ void split_tf32_trunc_lo(float x, float& hi, float& lo) {
@@ -259,7 +268,7 @@ bnn_mid4_kernel(const float* __restrict__ pre, const float* __restrict__ W, floa
             float hi[4], lo[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float v = tanh_fast(hA[k][i] + (i < 2 ? bb.x : bb.y));
+                const float v = act_fast(L.act, hA[k][i] + (i < 2 ? bb.x : bb.y));
                 hA[k][i] = v;
                 split_tf32_trunc_lo(v, hi[i], lo[i]);
             }
@@ -357,10 +366,10 @@ bnn_mid4_kernel(const float* __restrict__ pre, const float* __restrict__ W, floa
             // C fragment: (r0, h0), (r0, h0+1), (r1, h0), (r1, h0+1) with h0 = 8j + 2t  <->  hA[j][0], [2], [1], [3]
             const int h0 = 8 * j + 2 * t;
             float dp[4];
-            dp[0] = (dhh[0] + dcr[0]) * __fmaf_rn(-hA[j][0], hA[j][0], 1.f);
-            dp[1] = (dhh[1] + dcr[1]) * __fmaf_rn(-hA[j][2], hA[j][2], 1.f);
-            dp[2] = (dhh[2] + dcr[2]) * __fmaf_rn(-hA[j][1], hA[j][1], 1.f);
-            dp[3] = (dhh[3] + dcr[3]) * __fmaf_rn(-hA[j][3], hA[j][3], 1.f);
+            dp[0] = (dhh[0] + dcr[0]) * act_grad_from_h(L.act, hA[j][0]);
+            dp[1] = (dhh[1] + dcr[1]) * act_grad_from_h(L.act, hA[j][2]);
+            dp[2] = (dhh[2] + dcr[2]) * act_grad_from_h(L.act, hA[j][1]);
+            dp[3] = (dhh[3] + dcr[3]) * act_grad_from_h(L.act, hA[j][3]);
             __half hi[4], lo[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) split_f16(dp[i] * sD, hi[i], lo[i]);
@@ -643,7 +652,7 @@ bnn_fwd_mid_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         const int hf = ew >> 2;                   // sample of the pair (column half of the tile)
         const int g = lane >> 2, t = lane & 3;
         const int gt = (ew & 3) * 32 + lane;      // thread index inside the sample's 4-warp group
-        const int H = p.L.H, C = p.L.C, B = p.L.B;
+        const int H = p.L.H, C = p.L.C, B = p.L.B, act = p.L.act;
         float* W2s = extra + hf * FS::SAMPLE_FLOATS;
         float* b1s = W2s + FS::W2_FLOATS;
         float* b2s = b1s + HP;
@@ -728,10 +737,10 @@ bnn_fwd_mid_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
 #pragma unroll
                 for (int m = 0; m < 2; ++m) {
                     float* a = acc[m][k];
-                    a[0] = v0 ? tanh_fast(__fmaf_rn(a[0], inv_pre, bb.x)) : 0.f;      // (row g,   h0)
-                    a[1] = v1 ? tanh_fast(__fmaf_rn(a[1], inv_pre, bb.y)) : 0.f;      // (row g,   h0 + 1)
-                    a[2] = v0 ? tanh_fast(__fmaf_rn(a[2], inv_pre, bb.x)) : 0.f;      // (row g+8, h0)
-                    a[3] = v1 ? tanh_fast(__fmaf_rn(a[3], inv_pre, bb.y)) : 0.f;      // (row g+8, h0 + 1)
+                    a[0] = v0 ? act_fast(act, __fmaf_rn(a[0], inv_pre, bb.x)) : 0.f;      // (row g,   h0)
+                    a[1] = v1 ? act_fast(act, __fmaf_rn(a[1], inv_pre, bb.y)) : 0.f;      // (row g,   h0 + 1)
+                    a[2] = v0 ? act_fast(act, __fmaf_rn(a[2], inv_pre, bb.x)) : 0.f;      // (row g+8, h0)
+                    a[3] = v1 ? act_fast(act, __fmaf_rn(a[3], inv_pre, bb.y)) : 0.f;      // (row g+8, h0 + 1)
                     // A fragment (k columns t, t+4 <-> hidden h0, h0+1): (g, h0), (g+8, h0), (g, h0+1), (g+8, h0+1)
                     float hi[4], lo[4];
                     split_tf32_trunc_lo(a[0], hi[0], lo[0]);
@@ -856,7 +865,7 @@ bnn_fwd_mid_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
                         const float* hv = acc[m][j];
                         float dp[4];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) dp[i] = dh[i] * __fmaf_rn(-hv[i], hv[i], 1.f);
+                        for (int i = 0; i < 4; ++i) dp[i] = dh[i] * act_grad_from_h(act, hv[i]);
                         __half hi[4], lo[4];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) split_f16(dp[i] * sD, hi[i], lo[i]);

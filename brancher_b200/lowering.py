@@ -270,15 +270,15 @@ class LinearPlan(Plan):
 class BNNPlan(Plan):
     family = "bnn (K3)"
 
-    def __init__(self, joint, posterior, k, specs, x_var):
+    def __init__(self, joint, posterior, k, specs, x_var, activation="tanh"):
         super().__init__(joint, posterior)
-        self.k, self.x_var = k, x_var
+        self.k, self.x_var, self.activation = k, x_var, activation
         self.latents = specs          # weights1, b1, weights2, b2
 
     def _launch(self, cu, mvars, r, empirical, loss=None):
         X = _data_matrix(empirical[self.x_var], "x")
         y = empirical[self.k].reshape(-1).to(torch.int32).contiguous()
-        return cu.bnn_elbo_fwd_bwd(X, y, mvars, r, loss=loss)
+        return cu.bnn_elbo_fwd_bwd(X, y, mvars, r, loss=loss, activation=self.activation)
 
     def predict(self, X, number_samples):
         """Batched posterior-predictive pass (replaces the per-image loop around
@@ -292,7 +292,7 @@ class BNNPlan(Plan):
         X = X.reshape(-1, int(np.prod(self.latents[0].shape[1:]))).contiguous()
         r = cu.sample_range(number_samples, seed=config.seed, offset=config.next_offset())
         mvars = [spec.make(cu, i, None) for i, spec in enumerate(self.latents)]
-        logits, labels, probs = cu.bnn_predict(X, mvars, r)
+        logits, labels, probs = cu.bnn_predict(X, mvars, r, activation=self.activation)
         return {"logits": logits, "samples": labels, "probs": probs, "sample_range": r}
 
 
@@ -348,14 +348,15 @@ def _lower_dense(joint, posterior):
                 raise UnsupportedModelError("Binomial/Bernoulli logistic regression needs weights of shape [1, F]")
             return LinearPlan(joint, posterior, k, ws, x, cu.CATEGORICAL if kind == "categorical" else cu.BERNOULLI, C)
 
-    # K3: logits = matmul(W2, tanh(matmul(W1, x) + b1)) + b2
+    # K3: logits = matmul(W2, act(matmul(W1, x) + b1)) + b2, act in {tanh, relu, sigmoid}
     if kind == "categorical":
         for outer, b2e in _commutative_add(logits):
             b2 = _var(b2e)
             if not (_is_call(outer, "matmul", 2) and b2 in latents):
                 continue
             W2, hid = _var(outer.args[0]), outer.args[1]
-            if not (W2 in latents and _is_call(hid, "tanh", 1)):
+            act = next((a for a in ("tanh", "relu", "sigmoid") if _is_call(hid, a, 1)), None)
+            if not (W2 in latents and act is not None):
                 continue
             for inner, b1e in _commutative_add(hid.args[0]):
                 b1 = _var(b1e)
@@ -363,7 +364,7 @@ def _lower_dense(joint, posterior):
                     continue
                 W1, x = _var(inner.args[0]), _var(inner.args[1])
                 if W1 in latents and _is_data(x) and len({W1, b1, W2, b2}) == 4 and len(latents) == 4:
-                    return BNNPlan(joint, posterior, k, [spec(W1), spec(b1), spec(W2), spec(b2)], x)
+                    return BNNPlan(joint, posterior, k, [spec(W1), spec(b1), spec(W2), spec(b2)], x, activation=act)
     raise UnsupportedModelError("model graph is not recognised by any fused kernel family "
                                 "(linear K2, bnn K3); likelihood link: %s" % k.partial_links["logits"].string)
 

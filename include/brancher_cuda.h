@@ -105,6 +105,15 @@ int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int P, int H, 
                          const brn_mf_var vars[4], const brn_sample_range* r,
                          void* workspace, size_t workspace_bytes, int with_prior,
                          double* loss, void* stream);
+/* The same with the hidden activation chosen: h = act(W1 x + b1), act in {tanh, relu, sigmoid} -- the link functions
+ * BF.tanh / BF.relu / BF.sigmoid of brancher/functions.py:50-62 inside the BNN link.  brn_bnn_elbo_fwd_bwd == BRN_ACT_TANH. */
+#define BRN_ACT_TANH 0
+#define BRN_ACT_RELU 1
+#define BRN_ACT_SIGMOID 2
+int brn_bnn_elbo_fwd_bwd_act(const float* X, const int32_t* y, int B, int P, int H, int C, int activation,
+                             const brn_mf_var vars[4], const brn_sample_range* r,
+                             void* workspace, size_t workspace_bytes, int with_prior,
+                             double* loss, void* stream);
 
 /* K3 forward only -- batched posterior-predictive pass of the BNN: for S posterior weight samples and B data
  * rows, logits[s, b, :] = W2_s tanh(W1_s x_b + b1_s) + b2_s in one launch sequence (same sampler and tensor-core forward
@@ -112,9 +121,9 @@ int brn_bnn_elbo_fwd_bwd(const float* X, const int32_t* y, int B, int P, int H, 
  * probs_mean[b, c] += (1/S_total) softmax(logits[s, b])[c] (caller-zeroed).
  * Replaces ProbabilisticModel._get_posterior_sample (brancher/variables.py:796-812) as every evaluation loop of the examples
  * uses it -- one image and one graph walk at a time (tests/test_MNIST_bayesian_neural_network.py:75-81). */
-int brn_bnn_predict(const float* X, int B, int P, int H, int C, const brn_mf_var vars[4], const brn_sample_range* r,
-                    void* workspace, size_t workspace_bytes, float* logits, int32_t* labels, float* probs_mean,
-                    void* stream);
+int brn_bnn_predict(const float* X, int B, int P, int H, int C, int activation, const brn_mf_var vars[4],
+                    const brn_sample_range* r, void* workspace, size_t workspace_bytes, float* logits, int32_t* labels,
+                    float* probs_mean, void* stream);
 
 /* K2 -- (multi-class) Bayesian logistic regression: logits_sbc = sum_f W_scf X_bf, W ~ q mean-field [C,F];
  *   likelihood 0: Bernoulli / Binomial(total_count=1, logits) with y float {0,1}  (C == 1)

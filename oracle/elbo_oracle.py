@@ -160,7 +160,7 @@ def logreg_elbo(X, y, params, eps, prior=None, dtype=torch.float32, likelihood="
     return float(loss.detach()), q.grads()
 
 
-def bnn_elbo(X, y, params, eps, prior=None, dtype=torch.float32, sample_chunk=None, with_prior=True):
+def bnn_elbo(X, y, params, eps, prior=None, dtype=torch.float32, sample_chunk=None, with_prior=True, activation="tanh"):
     """One-hidden-layer Bayesian neural network, `development_playgrounds/MNIST_bayesian_neural_network.py:26-57`.
 
     variables "weights1" [H,P], "b1" [H,1], "weights2" [C,H], "b2" [C,1];
@@ -177,7 +177,7 @@ def bnn_elbo(X, y, params, eps, prior=None, dtype=torch.float32, sample_chunk=No
     for s0 in range(0, S, step):
         sl = slice(s0, s0 + step)
         pre = torch.einsum("shp,bp->sbh", w["weights1"][sl], Xt) + w["b1"][sl, :, 0].unsqueeze(1)
-        h = torch.tanh(pre)
+        h = {"tanh": torch.tanh, "relu": torch.relu, "sigmoid": torch.sigmoid}[activation](pre)     # BF.tanh / BF.relu / BF.sigmoid
         a = torch.einsum("sch,sbh->sbc", w["weights2"][sl], h) + w["b2"][sl, :, 0].unsqueeze(1)
         lp = D.Categorical(logits=a).log_prob(yt.unsqueeze(0))      # [s,B]
         lls.append(lp.sum(dim=1))

@@ -91,8 +91,8 @@ NS = zoo.namespace("brancher")          # the model builders are shared with the
 NS.LogitNormalVariable = _LogitNormalVariable
 
 
-def bnn(seed, B, P, H, C, S, q_sigma=0.01, q_mu_scale=0.0, tag="bnn_small"):
-    model, Q, d = zoo.bnn(NS, seed, B, P, H, C, q_sigma, q_mu_scale)
+def bnn(seed, B, P, H, C, S, q_sigma=0.01, q_mu_scale=0.0, tag="bnn_small", activation="tanh"):
+    model, Q, d = zoo.bnn(NS, seed, B, P, H, C, q_sigma, q_mu_scale, activation)
     eps = {n: torch.tensor(d["rng"].randn(S, 1, *s).astype("float32")) for n, s in d["shapes"].items()}
     inject(Q, eps)
     loss, grads, values = loss_and_grads(model, S)
@@ -291,6 +291,10 @@ if __name__ == "__main__":
         wvgd(21, B=30, F=4, C=3, n=3, S=20, tag="wvgd_softmax")
         wvgd(22, B=16, F=5, C=2, n=4, S=24, tag="wvgd_softmax4")
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "bnn_act":
+        bnn(31, B=11, P=14, H=6, C=3, S=5, q_sigma=0.3, q_mu_scale=0.5, tag="bnn_relu", activation="relu")
+        bnn(32, B=10, P=12, H=5, C=4, S=6, q_sigma=0.3, q_mu_scale=0.5, tag="bnn_sigmoid", activation="sigmoid")
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "wvgd_post":
         wvgd_post(21, B=30, F=4, C=3, n=3, S=64, tag="wvgd_post")
         wvgd_post(22, B=16, F=5, C=2, n=4, S=48, tag="wvgd_post4")
@@ -324,3 +328,5 @@ if __name__ == "__main__":
     wvgd(22, B=16, F=5, C=2, n=4, S=24, tag="wvgd_softmax4")
     wvgd_post(21, B=30, F=4, C=3, n=3, S=64, tag="wvgd_post")
     wvgd_post(22, B=16, F=5, C=2, n=4, S=48, tag="wvgd_post4")
+    bnn(31, B=11, P=14, H=6, C=3, S=5, q_sigma=0.3, q_mu_scale=0.5, tag="bnn_relu", activation="relu")
+    bnn(32, B=10, P=12, H=5, C=4, S=6, q_sigma=0.3, q_mu_scale=0.5, tag="bnn_sigmoid", activation="sigmoid")

@@ -26,7 +26,7 @@ def namespace(pkg):
     return ns
 
 
-def bnn(ns, seed, B, P, H, C, q_sigma=0.01, q_mu_scale=0.0):
+def bnn(ns, seed, B, P, H, C, q_sigma=0.01, q_mu_scale=0.0, activation="tanh"):
     """development_playgrounds/MNIST_bayesian_neural_network.py:26-57 on synthetic data."""
     rng = np.random.RandomState(seed)
     X = rng.rand(B, P, 1).astype("float32")
@@ -34,7 +34,7 @@ def bnn(ns, seed, B, P, H, C, q_sigma=0.01, q_mu_scale=0.0):
     x = ns.RootVariable(X, "x", is_observed=True)
     shapes = {"b1": (H, 1), "b2": (C, 1), "weights1": (H, P), "weights2": (C, H)}
     pv = {n: ns.NormalVariable(np.zeros(s), 10 * np.ones(s), n) for n, s in shapes.items()}
-    h = ns.BF.tanh(ns.BF.matmul(pv["weights1"], x) + pv["b1"])
+    h = getattr(ns.BF, activation)(ns.BF.matmul(pv["weights1"], x) + pv["b1"])
     a = ns.BF.matmul(pv["weights2"], h) + pv["b2"]
     k = ns.CategoricalVariable(logits=a, name="k")
     model = ns.ProbabilisticModel([k])

@@ -39,7 +39,10 @@ def params_match(model, g):
 
 
 @pytest.mark.parametrize("tag,kw", [("bnn_small", dict(seed=1, B=12, P=20, H=7, C=4)),
-                                    ("bnn_small_wide", dict(seed=2, B=9, P=16, H=5, C=3, q_sigma=0.3, q_mu_scale=0.5))])
+                                    ("bnn_small_wide", dict(seed=2, B=9, P=16, H=5, C=3, q_sigma=0.3, q_mu_scale=0.5)),
+                                    ("bnn_relu", dict(seed=31, B=11, P=14, H=6, C=3, q_sigma=0.3, q_mu_scale=0.5, activation="relu")),
+                                    ("bnn_sigmoid", dict(seed=32, B=10, P=12, H=5, C=4, q_sigma=0.3, q_mu_scale=0.5,
+                                                         activation="sigmoid"))])
 def test_bnn_same_script_same_numbers(ns, tag, kw):
     from oracle import elbo_oracle as O
     g = load_golden(tag)
@@ -48,7 +51,8 @@ def test_bnn_same_script_same_numbers(ns, tag, kw):
     S = g["eps"]["b1"].shape[0]
     loss, grads = loss_and_grads(ns, model, S, g["eps"])
     names = ["weights1", "b1", "weights2", "b2"]
-    o64 = O.bnn_elbo(g["raw"]["X"], g["raw"]["y"], mf_params(g, names), g["eps"], dtype=torch.float64)
+    o64 = O.bnn_elbo(g["raw"]["X"], g["raw"]["y"], mf_params(g, names), g["eps"], dtype=torch.float64,
+                     activation=kw.get("activation", "tanh"))
     check_against_oracle(loss, grads, (float(g["raw"]["loss"]), g["grad"]), o64, tag + " via API vs reference")
 
 

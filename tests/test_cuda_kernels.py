@@ -78,23 +78,24 @@ def test_mf_prior_entropy(cu, tied, numel, S):
 BNN_NAMES = ["weights1", "b1", "weights2", "b2"]
 
 
-def run_bnn(cu, X, y, params, eps, prior=None, r=None, with_prior=True):
+def run_bnn(cu, X, y, params, eps, prior=None, r=None, with_prior=True, activation="tanh"):
     S = next(iter(eps.values())).shape[0] if eps is not None else r.s_local
     vars4 = make_vars(cu, params, eps, BNN_NAMES, prior)
-    loss = cu.bnn_elbo_fwd_bwd(dev(X), dev(y, torch.int32), vars4, r or cu.sample_range(S), with_prior=with_prior)
+    loss = cu.bnn_elbo_fwd_bwd(dev(X), dev(y, torch.int32), vars4, r or cu.sample_range(S), with_prior=with_prior,
+                               activation=activation)
     return loss.item(), grads_of(vars4, BNN_NAMES, params), vars4
 
 
-@pytest.mark.parametrize("name", ["bnn_small", "bnn_small_wide"])
-def test_bnn_golden(cu, name):
-    """CUDA vs the live reference's own outputs and vs the oracle on the same inputs."""
+@pytest.mark.parametrize("name,act", [("bnn_small", "tanh"), ("bnn_small_wide", "tanh"), ("bnn_relu", "relu"), ("bnn_sigmoid", "sigmoid")])
+def test_bnn_golden(cu, name, act):
+    """CUDA vs the live reference's own outputs and vs the oracle on the same inputs (hidden activation tanh / relu / sigmoid)."""
     from oracle import elbo_oracle as O
     g = load_golden(name)
     params = mf_params(g, BNN_NAMES)
     X, y = g["raw"]["X"], g["raw"]["y"]
-    o32 = O.bnn_elbo(X, y, params, g["eps"])
-    o64 = O.bnn_elbo(X, y, params, g["eps"], dtype=torch.float64)
-    loss, grads, _ = run_bnn(cu, X, y, params, g["eps"])
+    o32 = O.bnn_elbo(X, y, params, g["eps"], activation=act)
+    o64 = O.bnn_elbo(X, y, params, g["eps"], dtype=torch.float64, activation=act)
+    loss, grads, _ = run_bnn(cu, X, y, params, g["eps"], activation=act)
     check_against_oracle(loss, grads, o32, o64, name)
     # and directly against the reference's fp32 numbers, with the reference's measured noise as slack
     ref = (float(g["raw"]["loss"]), g["grad"])
@@ -340,3 +341,26 @@ def test_bnn_predict_matches_forward_oracle(cu, monkeypatch, B, P, H, C, S, vari
     freq = np.bincount(lab.reshape(-1), minlength=C) / lab.size
     want = (e / e.sum(-1, keepdims=True)).reshape(-1, C).mean(0)
     assert np.all(np.abs(freq - want) <= 5 * np.sqrt(want * (1 - want) / lab.size) + 1e-3), (freq, want)
+
+
+@pytest.mark.parametrize("act", ["relu", "sigmoid"])
+@pytest.mark.parametrize("mid", ["4", "5"])
+def test_bnn_tcgen05_activations(cu, monkeypatch, act, mid):
+    """relu / sigmoid hidden units through the tensor-core variant (staged and fused pipelines) vs the fp64 oracle.  Relu: the
+    rows whose pre-activations come within 1e-5 (relative) of the kink are left out of the statement (see the C5 test)."""
+    from oracle import elbo_oracle as O
+    monkeypatch.setenv("BRN_BNN_VARIANT", "tcgen05")
+    monkeypatch.setenv("BRN_BNN_MID", mid)
+    B, P, H, C, S = 200, 64, 100, 7, 4
+    X, y, params, eps, shapes = random_bnn(41, B, P, H, C, S)
+    if act == "relu":          # keep every pre-activation away from zero: shift the biases by the sign of the pre-activation mean
+        W = {n: params[n][0].astype("f8")[None] + np.log1p(np.exp(params[n][1].astype("f8")))[None] * eps[n] for n in BNN_NAMES}
+        pre = np.einsum("shp,bp->sbh", W["weights1"], X.astype("f8")) + W["b1"][:, None, :, 0]
+        keep = np.abs(pre).min(axis=(0, 2)) > 1e-4
+        X, y = X[keep], y[keep]
+        assert keep.sum() > B // 2
+    o32 = O.bnn_elbo(X, y, params, eps, None, activation=act)
+    o64 = O.bnn_elbo(X, y, params, eps, None, dtype=torch.float64, activation=act)
+    loss, grads, _ = run_bnn(cu, X, y, params, eps, None, activation=act)
+    assert cu.last_variant() == "tcgen05"
+    check_against_oracle(loss, grads, o32, o64, "bnn tcgen05 %s mid=%s" % (act, mid))
