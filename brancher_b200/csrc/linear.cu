@@ -247,8 +247,13 @@ static int linear_tc_chunk_rows(int S, int sms) {
     return mt * 128;
 }
 
+}  // namespace brn
+#include "linear_flash.cuh"
+namespace brn {
+
 // TF32-split operands and scratch of the tcgen05 variant (Bernoulli, C == 1); S = weight vectors (MC samples or particles)
 struct LinearTcBuffers {
+    LinearFlashBuffers flash;
     float *Wh, *Wl, *Xh, *Xl, *Xth, *Xtl, *dTh, *dTl, *dWpart;
     int64_t ldF, ldN, ldNB, n_chunks;
     int nb, slices;
@@ -270,6 +275,7 @@ struct LinearTcBuffers {
         Xth = take((size_t)n_chunks * F * ldNB); Xtl = take((size_t)n_chunks * F * ldNB);
         dTh = take((size_t)S * ldNB); dTl = take((size_t)S * ldNB);
         dWpart = take((size_t)slices * S * F);
+        flash.carve(take, S, F, sms);
     }
 };
 
@@ -378,6 +384,16 @@ static int launch_linear_fused(const float* X, const void* y, int likelihood, in
 static int launch_linear_tc(const float* X, const float* y, int64_t N, int F, int S, const float* W, float* dW, float loss_scale,
                             double* loss, const LinearTcBuffers& b, const char* stage_split, const char* stage_fused,
                             cudaStream_t stream) {
+    if (linear_flash_ok(X, N, F, S)) {
+        // one pass over X: logits MMA -> likelihood -> d through shared memory -> gradient MMA (linear_flash.cuh)
+        set_variant("tcgen05-flash");
+        StageTimer st2(stage_fused, stream);
+        if (int e = launch_linear_flash(X, y, N, F, S, W, dW, loss_scale, loss, b.flash, stream)) return e;
+        const int64_t tot = (int64_t)S * F;
+        sum_slices_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(b.flash.part, b.flash.groups, tot, tot, dW);
+        BRN_LAUNCH_OK("sum_slices_kernel");
+        return 0;
+    }
     int drain = 2;
     if (const char* env = getenv("BRN_UMMA_DRAIN")) drain = atoi(env);
     // Operands that cross HBM once are kept as ONE fp32 matrix and split into TF32 (hi, lo) inside the GEMMs by converter warps

@@ -211,6 +211,7 @@ def test_linear_tcgen05_variant(cu, monkeypatch, N, F, S, tied, split_a):
     from oracle import elbo_oracle as O
     monkeypatch.setenv("BRN_LINEAR_VARIANT", "tcgen05")
     monkeypatch.setenv("BRN_LINEAR_SPLIT_A", split_a)
+    monkeypatch.setenv("BRN_LINEAR_FLASH", "0")           # the staged GEMM pair (the one-pass kernel has its own test below)
     rng = np.random.RandomState(N + F + S)
     X = rng.randn(N, F).astype("f4")
     y = rng.randint(0, 2, size=N)
@@ -222,6 +223,28 @@ def test_linear_tcgen05_variant(cu, monkeypatch, N, F, S, tied, split_a):
     loss, grads = run_linear(cu, X, y, params, eps, cu.BERNOULLI, 1, prior)
     assert cu.last_variant() == "tcgen05"
     check_against_oracle(loss, grads, o32, o64, "linear tcgen05 N=%d F=%d S=%d" % (N, F, S))
+
+
+@pytest.mark.parametrize("N,F,S,tied", [(1, 16, 1, True), (63, 32, 3, False), (64, 16, 128, False), (777, 48, 129, True),
+                                         (1000, 128, 70, False), (5000, 128, 300, True), (20000, 64, 130, False),
+                                         (130001, 96, 200, False), (9473, 112, 1000, True)])
+def test_linear_flash_variant(cu, monkeypatch, N, F, S, tied):
+    """K2 in one pass over X (linear_flash.cuh): logits MMA -> Bernoulli likelihood -> d through shared memory -> gradient
+    MMA, fp16 (hi, lo) operand pairs.  Ragged row blocks, ragged vector tiles, one and two 64-feature boxes, more row
+    groups than row blocks."""
+    from oracle import elbo_oracle as O
+    monkeypatch.setenv("BRN_LINEAR_VARIANT", "tcgen05")
+    rng = np.random.RandomState(N + F + S)
+    X = (rng.randn(N, F) * (1 + 3 * rng.rand(1, F))).astype("f4")
+    y = rng.randint(0, 2, size=N)
+    params = {"weights": ((0.3 * rng.randn(1, F)).astype("f4"), (rng.randn(1, F) - 1).astype("f4"))}
+    eps = {"weights": rng.randn(S, 1, F).astype("f4")}
+    prior = None if tied else {"weights": (0.0, 0.5)}
+    o32 = O.logreg_elbo(X, y, params, eps, prior, row_chunk=4096)
+    o64 = O.logreg_elbo(X, y, params, eps, prior, dtype=torch.float64, row_chunk=4096)
+    loss, grads = run_linear(cu, X, y, params, eps, cu.BERNOULLI, 1, prior)
+    assert cu.last_variant() == "tcgen05-flash"
+    check_against_oracle(loss, grads, o32, o64, "linear flash N=%d F=%d S=%d" % (N, F, S))
 
 
 @pytest.mark.parametrize("N,F,S,slabs", [(1000, 16, 9, 3), (20000, 128, 96, 4), (700, 8, 5, 50)])

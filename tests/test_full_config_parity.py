@@ -100,7 +100,7 @@ def test_c2_logreg_full_config(cu):
     w = cu.MeanFieldVar(dev(params["weights"][0]), dev(params["weights"][1]), var_id=0,
                         prior_loc=dev(np.zeros((1, F), "f4")), prior_scale=dev(np.full((1, F), 0.5, "f4")))
     loss = cu.linear_elbo_fwd_bwd(X.to(DEV), y.to(DEV), cu.BERNOULLI, w, 1, r).item()
-    assert cu.last_variant() == "tcgen05"
+    assert cu.last_variant().startswith("tcgen05")
     grads = {"weights_loc": w.dmu.cpu().numpy().reshape(1, F), "weights_scale": w.drho.cpu().numpy().reshape(1, F)}
     literal_report("C2 logreg N=1e6 S=1024", dict(grads, loss=np.array(loss)), dict(o64[1], loss=np.array(o64[0])),
                    dict(o32[1], loss=np.array(o32[0])))
@@ -167,7 +167,7 @@ def test_c5_vae_full_config(cu):
     net = V.make_net(cu, enc, dec)
     loss_full = cu.vae_elbo_fwd_bwd(dev(X), net, r, var_id=5).item()
     g_full = V.grads_of(net)
-    assert cu.last_variant() == "tcgen05"
+    assert cu.last_variant().startswith("tcgen05")
     # strict parity on the rows away from the kinks
     l_c, g_c = run_cuda(clean)
     sub = lambda a: a[clean]

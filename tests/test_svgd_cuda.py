@@ -123,7 +123,7 @@ def test_particles_loss_grad_tcgen05_variant(cu, monkeypatch, N, F, n, force):
     l64, g64 = O.particles_loss_grad(X, y, theta, (pl, ps), dtype=torch.float64, likelihood="binomial")
     loss, G = cu.linear_particles_loss_grad(dev(X), dev(y), cu.BERNOULLI, dev(theta).reshape(n, -1), 1, dev(pl).reshape(-1),
                                             dev(ps).reshape(-1))
-    assert cu.last_variant() == "tcgen05"
+    assert cu.last_variant().startswith("tcgen05")
     assert_close(loss.item(), l64, "particles loss (tcgen05)")
     assert_close(G.cpu().numpy().reshape(g64.shape), g64, "particles grad (tcgen05)", scale=np.abs(g64).max())
 
