@@ -276,6 +276,8 @@ struct LinearTcBuffers {
         dTh = take((size_t)S * ldNB); dTl = take((size_t)S * ldNB);
         dWpart = take((size_t)slices * S * F);
         flash.carve(take, S, F, sms);
+        flash.Xh = reinterpret_cast<__half*>(Xh);        // the one-pass kernel's fp16 pair of X lives in the staged pair's buffers
+        flash.Xl = reinterpret_cast<__half*>(Xl);
     }
 };
 

@@ -11,9 +11,10 @@
 //
 // Replaces the staged pair (logits GEMM -> d^T through HBM -> gradient GEMM): at C2 that pair moved 4 GB of d^T out and
 // back per evaluation and read X twice (row-major and a per-chunk transposed copy).  Operands are fp16 (hi, lo) pairs
-// ("3xFP16", see bnn_tc.cuh): X is read as fp32 straight from the caller's matrix with 1-D bulk copies (a block of 64 rows
-// is one contiguous piece), scaled by a power of two and split by converter warps into the swizzled UMMA layout; W is
-// pre-split (small); d is in (-1, 1) and scaled by 2^13.
+// ("3xFP16", see bnn_tc.cuh), scaled by powers of two: X and W are split once per call by small streaming kernels (X: one
+// read + one write of its own size) and arrive by TMA in the swizzled UMMA layout, four blocks in flight per SM; d is in
+// (-1, 1) and scaled by 2^13.  (A first version converted fp32 X inside the kernel from a 32 KB staging area: with only that
+// much in flight per SM the X feed was latency-bound at ~5000 cycles per block against 1536 of tensor work.)
 // Accuracy: D2's accumulation chain is 128 rows long (two blocks) between round-to-nearest drains into registers.
 #pragma once
 #include <cuda_fp16.h>
@@ -27,23 +28,23 @@ namespace brn {
 constexpr int LF_ROWS = 64;            // rows of X per block (N of MMA1, K of MMA2)
 constexpr int LF_MT = 128;             // weight vectors per CTA tile (M of both MMAs)
 constexpr int LF_FMAX = 128;           // features (K of MMA1, N of MMA2): multiple of 16, at most 128
-constexpr int LF_XSTAGES = 3;          // fp16 images of X blocks: conversion runs up to two blocks ahead of the gradient MMA
-constexpr int LF_HALF = 32;            // rows per fp32 staging buffer (two buffers: one half block each)
-constexpr int LF_THREADS = 512;        // 16 warps: TMA, MMA, 2 idle | 4 converters | 8 epilogue
-constexpr int LF_CONV_WARP0 = 4, LF_EPI_WARP0 = 8;
+constexpr int LF_XSTAGES = 4;          // X blocks (fp16 pair images, 32 KB each) in flight
+constexpr int LF_THREADS = 640;        // 20 warps: TMA, MMA, 2 idle | 16 epilogue
+constexpr int LF_EPI_WARP0 = 4, LF_EPI_WARPS = 16;
+constexpr int LF_EROWS = LF_ROWS / (LF_EPI_WARPS / 4);      // 16 rows of a block per epilogue warp
+constexpr int LF_EFEAT = LF_FMAX / (LF_EPI_WARPS / 4);      // 32 gradient features per epilogue warp
+static_assert(LF_EROWS == 16 && LF_EFEAT == 32, "the TMEM load shapes of the epilogue are written for 16 warps");
 constexpr int LF_D2_CHAIN = 2;         // blocks per D2 accumulation chain
 constexpr float LF_D_SCALE = 8192.f;   // 2^13: |d| < 1
 
 struct LinearFlashSmem {
     static constexpr int W_BYTES = 2 * LF_MT * LF_FMAX * 2;                 // (hi, lo) [128][128] fp16 = 64 KB
-    static constexpr int STG_BYTES = LF_HALF * LF_FMAX * 4;                 // fp32 staging of half an X block = 16 KB
     static constexpr int X16_BYTES = 2 * LF_ROWS * LF_FMAX * 2;             // (hi, lo) [64][128] fp16 = 32 KB
     static constexpr int D_BYTES = 2 * LF_MT * LF_ROWS * 2;                 // (hi, lo) [128][64] fp16 = 32 KB
     static constexpr int off_w = 0;
     static constexpr int off_x16 = off_w + W_BYTES;
     static constexpr int off_d = off_x16 + LF_XSTAGES * X16_BYTES;
-    static constexpr int off_stg = off_d + D_BYTES;
-    static constexpr int TOTAL = off_stg + 2 * STG_BYTES + 1024;            // + alignment slack
+    static constexpr int TOTAL = off_d + D_BYTES + 1024;                    // + alignment slack
     static_assert(TOTAL <= 227 * 1024, "shared memory budget exceeded");
 };
 
@@ -70,21 +71,21 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, 
 }
 
 struct LinearFlashParams {
-    const float* X; const float* y; int64_t N; int F; int S;
+    const float* y; int64_t N; int F; int S;
     const float* scal;            // [0] = max |W|, [1] = max |X|  (device scalars)
     float* part;                  // [groups][S_pad][F] partial gradients (+ d ll / d W), one slice per row group
     int64_t part_stride;          // S_pad * F
     double* loss; float loss_scale;
     int groups;
-    int flags;                    // bit 0: hi x hi product first; bit 1: logits accumulated as two half-K chains (summed in registers)
 };
 
 __global__ void __launch_bounds__(LF_THREADS, 1)
-linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, LinearFlashParams p) {
+linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
+                    const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl, LinearFlashParams p) {
     using SM = LinearFlashSmem;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    __shared__ __align__(8) uint64_t w_full, stg_full[2], stg_empty[2], x_full[LF_XSTAGES], x_empty[LF_XSTAGES],
+    __shared__ __align__(8) uint64_t w_full, x_full[LF_XSTAGES], x_empty[LF_XSTAGES],
         d1_full[2], d1_empty[2], d_full, d_empty, acc2_full[2], acc2_empty[2];
     __shared__ uint32_t tmem_base_slot;
 
@@ -96,14 +97,14 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
 
     if (threadIdx.x == 0) {
         umma::tma_prefetch_desc(&tmWh); umma::tma_prefetch_desc(&tmWl);
+        umma::tma_prefetch_desc(&tmXh); umma::tma_prefetch_desc(&tmXl);
         umma::mbar_init(&w_full, 1);
-        for (int s = 0; s < 2; ++s) { umma::mbar_init(&stg_full[s], 1); umma::mbar_init(&stg_empty[s], 4); }
-        for (int s = 0; s < LF_XSTAGES; ++s) { umma::mbar_init(&x_full[s], 4); umma::mbar_init(&x_empty[s], 1); }
+        for (int s = 0; s < LF_XSTAGES; ++s) { umma::mbar_init(&x_full[s], 1); umma::mbar_init(&x_empty[s], 1); }
         for (int b = 0; b < 2; ++b) {
-            umma::mbar_init(&d1_full[b], 1); umma::mbar_init(&d1_empty[b], 8);
-            umma::mbar_init(&acc2_full[b], 1); umma::mbar_init(&acc2_empty[b], 8);
+            umma::mbar_init(&d1_full[b], 1); umma::mbar_init(&d1_empty[b], LF_EPI_WARPS);
+            umma::mbar_init(&acc2_full[b], 1); umma::mbar_init(&acc2_empty[b], LF_EPI_WARPS);
         }
-        umma::mbar_init(&d_full, 8); umma::mbar_init(&d_empty, 1);
+        umma::mbar_init(&d_full, LF_EPI_WARPS); umma::mbar_init(&d_empty, 1);
         umma::fence_barrier_init();
     }
     if (warp == 1) umma::tmem_alloc(&tmem_base_slot, 512);
@@ -111,32 +112,31 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
     __syncthreads();
     umma::tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
-    const uint32_t t_d1 = tmem_base, t_d2 = tmem_base + 256;        // D1: 2 x (2 half-K chains x 64 columns) at 0 / 128; D2: 2 x 128 at 256 / 384
-    const bool split1 = (p.flags & 2) && F >= 32;
+    const uint32_t t_d1 = tmem_base, t_d2 = tmem_base + 128;        // D1: 2 x 64 columns at 0 / 64; D2: 2 x 128 at 128 / 256
 
-    // register budget per SM sub-partition (one warp of each warpgroup): 40 + 96 + 2 x 184 = 504 <= 512
-    if (warp < LF_CONV_WARP0) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    // register budget: the CTA owns 96 registers x 640 threads (launch bounds); setmaxnreg only moves registers INSIDE that
+    // allocation (asking for more blocks forever), so per warpgroup 32 + 4 x 112 = 480 = 5 x 96
+    if (warp < LF_EPI_WARP0) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     if (warp == 0) {
-        // ===================== producer: W tile once, then the fp32 X blocks =====================
+        // ===================== producer: W tile once, then the X blocks (rows past N are zero-filled by TMA) =====================
         if (lane == 0) {
             umma::mbar_arrive_expect_tx(&w_full, (uint32_t)(2 * FB * LF_MT * 128));
             for (int b = 0; b < FB; ++b) {
                 umma::tma_load_2d(smem + SM::off_w + b * (LF_MT * 128), &tmWh, &w_full, b * 64, st * LF_MT);
                 umma::tma_load_2d(smem + SM::off_w + SM::W_BYTES / 2 + b * (LF_MT * 128), &tmWl, &w_full, b * 64, st * LF_MT);
             }
-            // half block h of every block goes through staging buffer h (a ragged last block may have an empty second half)
+            int stage = 0; uint32_t phase = 0;
             for (int64_t i = 0; i < my_blocks; ++i) {
-                const int64_t r0 = (g + i * p.groups) * LF_ROWS;
-                const int rows = (int)min((int64_t)LF_ROWS, p.N - r0);
-                for (int h = 0; h < 2; ++h) {
-                    const int hr = min(LF_HALF, rows - h * LF_HALF);
-                    if (hr <= 0) break;
-                    umma::mbar_wait(&stg_empty[h], (uint32_t)((i & 1) ^ 1));
-                    const uint32_t bytes = (uint32_t)hr * F * 4;
-                    umma::mbar_arrive_expect_tx(&stg_full[h], bytes);
-                    bulk_copy_g2s(smem + SM::off_stg + h * SM::STG_BYTES, p.X + (r0 + h * LF_HALF) * F, bytes, &stg_full[h]);
+                const int r0 = (int)((g + i * p.groups) * LF_ROWS);
+                umma::mbar_wait_guarded(&x_empty[stage], phase ^ 1);
+                umma::mbar_arrive_expect_tx(&x_full[stage], (uint32_t)(2 * FB * LF_ROWS * 128));
+                uint8_t* xh = smem + SM::off_x16 + stage * SM::X16_BYTES;
+                for (int b = 0; b < FB; ++b) {
+                    umma::tma_load_2d(xh + b * (LF_ROWS * 128), &tmXh, &x_full[stage], b * 64, r0);
+                    umma::tma_load_2d(xh + SM::X16_BYTES / 2 + b * (LF_ROWS * 128), &tmXl, &x_full[stage], b * 64, r0);
                 }
+                if (++stage == LF_XSTAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -147,30 +147,22 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
             const uint32_t wh = umma::smem_u32(smem + SM::off_w), wl = wh + SM::W_BYTES / 2;
             const uint32_t dh = umma::smem_u32(smem + SM::off_d), dl = dh + SM::D_BYTES / 2;
             const int ksteps1 = F / 16;
-            umma::mbar_wait(&w_full, 0);
+            umma::mbar_wait_guarded(&w_full, 0);
             umma::tc_fence_after();
             auto mma1 = [&](int64_t i) {
                 const int stage = (int)(i % LF_XSTAGES), b = (int)(i & 1);
-                umma::mbar_wait(&x_full[stage], (uint32_t)((i / LF_XSTAGES) & 1));
-                umma::mbar_wait(&d1_empty[b], (uint32_t)(((i >> 1) & 1) ^ 1));
+                umma::mbar_wait_guarded(&x_full[stage], (uint32_t)((i / LF_XSTAGES) & 1));
+                umma::mbar_wait_guarded(&d1_empty[b], (uint32_t)(((i >> 1) & 1) ^ 1));
                 umma::tc_fence_after();
                 const uint32_t xh = umma::smem_u32(smem + SM::off_x16 + stage * SM::X16_BYTES), xl = xh + SM::X16_BYTES / 2;
-                const int khalf = split1 ? (ksteps1 + 1) / 2 : ksteps1;
+                const uint32_t d_t = t_d1 + b * 64;
                 for (int ks = 0; ks < ksteps1; ++ks) {
                     const uint32_t ao = (ks >> 2) * (LF_MT * 128) + (ks & 3) * 32, bo = (ks >> 2) * (LF_ROWS * 128) + (ks & 3) * 32;
                     const uint64_t dah = umma::smem_desc_k<128>(wh + ao), dal = umma::smem_desc_k<128>(wl + ao);
                     const uint64_t dbh = umma::smem_desc_k<128>(xh + bo), dbl = umma::smem_desc_k<128>(xl + bo);
-                    const uint32_t d_t = t_d1 + b * 128 + (ks >= khalf ? 64 : 0);
-                    const bool acc = ks != 0 && ks != khalf;
-                    if (p.flags & 1) {
-                        umma::mma_f16_ss(d_t, dah, dbh, idesc1, acc);
-                        umma::mma_f16_ss(d_t, dal, dbh, idesc1, true);
-                        umma::mma_f16_ss(d_t, dah, dbl, idesc1, true);
-                    } else {
-                        umma::mma_f16_ss(d_t, dal, dbh, idesc1, acc);
-                        umma::mma_f16_ss(d_t, dah, dbl, idesc1, true);
-                        umma::mma_f16_ss(d_t, dah, dbh, idesc1, true);
-                    }
+                    umma::mma_f16_ss(d_t, dal, dbh, idesc1, ks != 0);
+                    umma::mma_f16_ss(d_t, dah, dbl, idesc1, true);
+                    umma::mma_f16_ss(d_t, dah, dbh, idesc1, true);
                 }
                 umma::mma_commit(&d1_full[b]);
             };
@@ -181,10 +173,10 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
                 const int stage = (int)(i % LF_XSTAGES);
                 const uint32_t buf = chain & 1;
                 if (i % LF_D2_CHAIN == 0) {
-                    umma::mbar_wait(&acc2_empty[buf], ((chain >> 1) & 1) ^ 1);
+                    umma::mbar_wait_guarded(&acc2_empty[buf], ((chain >> 1) & 1) ^ 1);
                     umma::tc_fence_after();
                 }
-                umma::mbar_wait(&d_full, (uint32_t)(i & 1));
+                umma::mbar_wait_guarded(&d_full, (uint32_t)(i & 1));
                 umma::tc_fence_after();
                 const uint32_t xh = umma::smem_u32(smem + SM::off_x16 + stage * SM::X16_BYTES), xl = xh + SM::X16_BYTES / 2;
                 const uint32_t d_t = t_d2 + buf * 128;
@@ -207,66 +199,13 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
             }
         }
     }
-    } else if (warp < LF_EPI_WARP0) {
-        // ===================== converters: fp32 staging -> scaled fp16 (hi, lo) in the swizzled UMMA layout =====================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
-        const int ct = threadIdx.x - 32 * LF_CONV_WARP0;            // 0..127
-        const float sx = p2_scale(p.scal[1]);
-        const int c = ct & 15, rr = ct >> 4;                        // 16-byte chunk (8 features) of a row, row within a pass of 8
-        const bool c_ok = c < F / 8;
-        const int box = c >> 3, cc = c & 7;
-        int stage = 0; uint32_t phase = 0;
-        for (int64_t i = 0; i < my_blocks; ++i) {
-            const int64_t r0 = (g + i * p.groups) * LF_ROWS;
-            const int rows = (int)min((int64_t)LF_ROWS, p.N - r0);
-            umma::mbar_wait(&x_empty[stage], phase ^ 1);
-            uint8_t* xh = smem + SM::off_x16 + stage * SM::X16_BYTES;
-            uint8_t* xl = xh + SM::X16_BYTES / 2;
-            for (int h = 0; h < 2; ++h) {
-                const int hr = min(LF_HALF, rows - h * LF_HALF);
-                if (hr > 0) umma::mbar_wait(&stg_full[h], (uint32_t)(i & 1));
-                const float* stg = reinterpret_cast<const float*>(smem + SM::off_stg + h * SM::STG_BYTES);
-#pragma unroll
-                for (int it = 0; it < LF_HALF / 8; ++it) {
-                    const int rh = it * 8 + rr, r = h * LF_HALF + rh;           // row within the half / the block
-                    uint4 ph = make_uint4(0u, 0u, 0u, 0u), pl = ph;
-                    if (rh < hr && c_ok) {
-                        const float4 a = *reinterpret_cast<const float4*>(stg + rh * F + c * 8);
-                        const float4 b = *reinterpret_cast<const float4*>(stg + rh * F + c * 8 + 4);
-                        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-                        uint32_t hh[4], ll[4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const float x0 = v[2 * k] * sx, x1 = v[2 * k + 1] * sx;
-                            const __half2 h2 = __floats2half2_rn(x0, x1);
-                            const float2 hf = __half22float2(h2);
-                            const __half2 l2 = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-                            hh[k] = *reinterpret_cast<const uint32_t*>(&h2);
-                            ll[k] = *reinterpret_cast<const uint32_t*>(&l2);
-                        }
-                        ph = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-                        pl = make_uint4(ll[0], ll[1], ll[2], ll[3]);
-                    }
-                    // image of a TMA box [64 rows][64 features] with SWIZZLE_128B: chunk index XOR (row % 8) inside 1024-byte atoms
-                    if (c_ok) {
-                        const int off = box * (LF_ROWS * 128) + r * 128 + ((cc ^ (r & 7)) << 4);
-                        *reinterpret_cast<uint4*>(xh + off) = ph;
-                        *reinterpret_cast<uint4*>(xl + off) = pl;
-                    }
-                }
-                __syncwarp();
-                if (hr > 0 && lane == 0) umma::mbar_arrive(&stg_empty[h]);
-            }
-            umma::fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) umma::mbar_arrive(&x_full[stage]);
-            if (++stage == LF_XSTAGES) { stage = 0; phase ^= 1; }
-        }
     } else {
         // ===================== epilogue: likelihood, d tile, D2 drains =====================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
+        // 16 warps = 4 per TMEM lane quarter; warp (q, part) owns vectors 32 q .. 32 q + 31 and, of every block, rows
+        // 16 part .. + 15 (logits -> d) and features 32 part .. + 31 (gradient accumulator)
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
         const int ew = warp - LF_EPI_WARP0;
-        const int q = warp & 3, hf = ew >> 2;                      // TMEM lane quarter (vectors 32q..), half (rows / features)
+        const int q = warp & 3, part = ew >> 2;
         const int s_local = q * 32 + lane;                          // vector inside the tile = TMEM lane = row of the d tile
         const int s_glob = st * LF_MT + s_local;
         const bool s_ok = s_glob < p.S;
@@ -274,15 +213,30 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         uint8_t* dh = smem + SM::off_d;
         uint8_t* dl = dh + SM::D_BYTES / 2;
-        float r2[64];
+        float r2[LF_EFEAT];
 #pragma unroll
-        for (int c = 0; c < 64; ++c) r2[c] = 0.f;
-        double ll_total = 0.0;      // per-block fp32 sums (32 terms) are added in double: a long fp32 running sum drops the many
+        for (int c = 0; c < LF_EFEAT; ++c) r2[c] = 0.f;
+        double ll_total = 0.0;      // per-block fp32 sums (16 terms) are added in double: a long fp32 running sum drops the many
                                     // near-zero terms of well-classified rows once it is large (error grew linearly with N)
         uint32_t chain = 0;
-        float y_next = 0.f;
+        bool pending = false;       // a finished D2 chain waits to be drained (after the NEXT block's d is on its way)
+        auto drain = [&]() {
+            const uint32_t buf = chain & 1;
+            umma::mbar_wait_guarded(&acc2_full[buf], (chain >> 1) & 1);
+            umma::tc_fence_after();
+            float v[LF_EFEAT];
+            umma::tmem_ld_32x32(t_d2 + lane_addr + buf * 128 + part * LF_EFEAT, v);
+            umma::tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < LF_EFEAT; ++c) r2[c] += v[c];      // round-to-nearest adds in registers
+            umma::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive(&acc2_empty[buf]);
+            ++chain;
+        };
+        float y_next = 0.f;         // lane j < 16 holds y of row 16 part + j, loaded one block ahead (0 past the end)
         if (my_blocks > 0) {
-            const int64_t rn = (int64_t)g * LF_ROWS + hf * 32 + lane;
+            const int64_t rn = (int64_t)g * LF_ROWS + part * LF_EROWS + (lane & (LF_EROWS - 1));
             y_next = rn < p.N ? __ldg(p.y + rn) : 0.f;
         }
         for (int64_t i = 0; i < my_blocks; ++i) {
@@ -290,33 +244,25 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
             const int rows = (int)min((int64_t)LF_ROWS, p.N - r0);
             const int b = (int)(i & 1);
             float ll = 0.f;
-            umma::mbar_wait(&d1_full[b], (uint32_t)((i >> 1) & 1));
+            umma::mbar_wait_guarded(&d1_full[b], (uint32_t)((i >> 1) & 1));
             umma::tc_fence_after();
-            float L[32];
-            umma::tmem_ld_32x32(t_d1 + lane_addr + b * 128 + hf * 32, L);
+            float L[LF_EROWS];
+            umma::tmem_ld_32x16(t_d1 + lane_addr + b * 64 + part * LF_EROWS, L);
             umma::tmem_ld_wait();
-            if (split1) {
-                float L2[32];
-                umma::tmem_ld_32x32(t_d1 + lane_addr + b * 128 + 64 + hf * 32, L2);
-                umma::tmem_ld_wait();
-#pragma unroll
-                for (int c = 0; c < 32; ++c) L[c] += L2[c];
-            }
             umma::tc_fence_before();
             __syncwarp();
             if (lane == 0) umma::mbar_arrive(&d1_empty[b]);
-            // d = y - sigmoid(l), ll += y l - softplus(l) for rows 32 hf .. 32 hf + 31 of the block (MUFU only, as EpiBernoulli).
-            // Lane j holds y of row 32 hf + j (loaded one block ahead; 0 past the end: such rows have X = 0, so d = y - 1/2
-            // would be wrong -- the ragged block takes the predicated path).
-            uint32_t dh_w[16], dl_w[16];
+            // d = y - sigmoid(l), ll += y l - softplus(l) (MUFU only, as EpiBernoulli).  Rows past the end of a ragged last
+            // block have X = 0, where d = y - 1/2 would be wrong: that block takes the predicated path.
+            uint32_t dh_w[LF_EROWS / 2], dl_w[LF_EROWS / 2];
             const float y_lane = y_next;
             if (i + 1 < my_blocks) {
-                const int64_t rn = (g + (i + 1) * p.groups) * LF_ROWS + hf * 32 + lane;
+                const int64_t rn = (g + (i + 1) * p.groups) * LF_ROWS + part * LF_EROWS + (lane & (LF_EROWS - 1));
                 y_next = rn < p.N ? __ldg(p.y + rn) : 0.f;
             }
             auto body = [&](auto ragged) {
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
+                for (int k = 0; k < LF_EROWS / 2; ++k) {
                     float dv[2];
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
@@ -330,7 +276,7 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
                         const float sig = l >= 0.f ? inv : e * inv;
                         const float t = __fmaf_rn(yv, l, -__fmaf_rn(lg, 0.6931471805599453f, fmaxf(l, 0.f)));
                         if (decltype(ragged)::value) {
-                            const bool ok = hf * 32 + 2 * k + u < rows;
+                            const bool ok = part * LF_EROWS + 2 * k + u < rows;
                             dv[u] = ok ? (yv - sig) * LF_D_SCALE : 0.f;
                             if (ok) ll += t;
                         } else {
@@ -347,12 +293,12 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
             };
             if (rows == LF_ROWS) body(std::false_type{}); else body(std::true_type{});
             // the d tile is free once MMA2 of the previous block has retired
-            umma::mbar_wait(&d_empty, (uint32_t)((i & 1) ^ 1));
+            umma::mbar_wait_guarded(&d_empty, (uint32_t)((i & 1) ^ 1));
             // K-major A tile [128 vectors][64 rows] fp16, 128-byte rows, SWIZZLE_128B: this thread owns row s_local and writes
-            // the 4 chunks (8 rows of X each) of its half
+            // the chunks (8 rows of X each) of its rows
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-                const int c = hf * 4 + cc;
+            for (int cc = 0; cc < LF_EROWS / 8; ++cc) {
+                const int c = part * (LF_EROWS / 8) + cc;
                 const int off = s_local * 128 + ((c ^ (s_local & 7)) << 4);
                 *reinterpret_cast<uint4*>(dh + off) = make_uint4(dh_w[4 * cc], dh_w[4 * cc + 1], dh_w[4 * cc + 2], dh_w[4 * cc + 3]);
                 *reinterpret_cast<uint4*>(dl + off) = make_uint4(dl_w[4 * cc], dl_w[4 * cc + 1], dl_w[4 * cc + 2], dl_w[4 * cc + 3]);
@@ -361,34 +307,18 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
             __syncwarp();
             if (lane == 0) umma::mbar_arrive(&d_full);
             ll_total += (double)ll;
-            // D2 chain finished with this block: drain it (round-to-nearest adds in registers)
-            if (i % LF_D2_CHAIN == LF_D2_CHAIN - 1 || i + 1 == my_blocks) {
-                const uint32_t buf = chain & 1;
-                umma::mbar_wait(&acc2_full[buf], (chain >> 1) & 1);
-                umma::tc_fence_after();
-                const uint32_t t0 = t_d2 + lane_addr + buf * 128 + hf * 64;
-                float v[32];
-                umma::tmem_ld_32x32(t0, v);
-                umma::tmem_ld_wait();
-#pragma unroll
-                for (int c = 0; c < 32; ++c) r2[c] += v[c];
-                umma::tmem_ld_32x32(t0 + 32, v);
-                umma::tmem_ld_wait();
-#pragma unroll
-                for (int c = 0; c < 32; ++c) r2[32 + c] += v[c];
-                umma::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) umma::mbar_arrive(&acc2_empty[buf]);
-                ++chain;
-            }
+            // the chain that ended with the PREVIOUS block is drained now, while the tensor core works on this block's d
+            if (pending) { drain(); pending = false; }
+            if (i % LF_D2_CHAIN == LF_D2_CHAIN - 1 || i + 1 == my_blocks) pending = true;
         }
-        // this CTA's share of + d ll / d W for vector s_glob, features 64 hf .. 64 hf + 63
+        if (pending) drain();
+        // this CTA's share of + d ll / d W for vector s_glob, features 32 part .. + 31
         if (s_ok) {
             const float inv2 = 1.f / (LF_D_SCALE * p2_scale(p.scal[1]));
-            float* o = p.part + (int64_t)g * p.part_stride + (int64_t)s_glob * F + hf * 64;
+            float* o = p.part + (int64_t)g * p.part_stride + (int64_t)s_glob * F + part * LF_EFEAT;
 #pragma unroll
-            for (int c = 0; c < 64; c += 4)
-                if (hf * 64 + c < F)
+            for (int c = 0; c < LF_EFEAT; c += 4)
+                if (part * LF_EFEAT + c < F)
                     *reinterpret_cast<float4*>(o + c) = make_float4(r2[c] * inv2, r2[c + 1] * inv2, r2[c + 2] * inv2, r2[c + 3] * inv2);
         }
         double tot = s_ok ? ll_total : 0.0;      // vectors past S are zero rows of the W tile: their terms are not part of the sum
@@ -404,16 +334,29 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
     }
 }
 
-// W [S][F] fp32 -> fp16 (hi, lo) scaled by p2_scale(max |W|)
+// x [n] fp32 -> fp16 (hi, lo) pair of x * p2_scale(*bound)   (n % 8 == 0, x and the outputs 16-byte aligned)
 __global__ void __launch_bounds__(256)
-linear_flash_split_w_kernel(const float* __restrict__ W, int64_t n, const float* __restrict__ scal, __half* __restrict__ hi,
-                            __half* __restrict__ lo) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float x = W[i] * p2_scale(scal[0]);
-    const __half h = __float2half_rn(x);
-    hi[i] = h;
-    lo[i] = __float2half_rn(x - __half2float(h));
+linear_flash_split_kernel(const float* __restrict__ x, int64_t n, const float* __restrict__ bound, __half* __restrict__ hi,
+                          __half* __restrict__ lo) {
+    const float sc = p2_scale(*bound);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n / 8; q += stride) {
+        const float4 a = __ldcs(reinterpret_cast<const float4*>(x) + 2 * q);
+        const float4 b = __ldcs(reinterpret_cast<const float4*>(x) + 2 * q + 1);
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t hh[4], ll[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float x0 = v[2 * k] * sc, x1 = v[2 * k + 1] * sc;
+            const __half2 h2 = __floats2half2_rn(x0, x1);
+            const float2 hf = __half22float2(h2);
+            const __half2 l2 = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+            hh[k] = *reinterpret_cast<const uint32_t*>(&h2);
+            ll[k] = *reinterpret_cast<const uint32_t*>(&l2);
+        }
+        reinterpret_cast<uint4*>(hi)[q] = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+        reinterpret_cast<uint4*>(lo)[q] = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+    }
 }
 
 // slot = max(slot, max |x|) (non-negative floats order like their bit patterns); one atomic per block
@@ -445,6 +388,7 @@ __global__ void __launch_bounds__(256) lf_absmax_kernel(const float* __restrict_
 
 struct LinearFlashBuffers {
     __half *Wh, *Wl;       // [S][F] fp16 pair
+    __half *Xh, *Xl;       // [N][F] fp16 pair (set by the owner: aliases the staged variant's fp32 pair buffers)
     float* scal;           // 64 floats, zeroed per call
     float* part;           // [groups][S][F]
     int groups, tiles;
@@ -463,7 +407,7 @@ struct LinearFlashBuffers {
 static bool linear_flash_ok(const float* X, int64_t N, int F, int S) {
     if (const char* env = getenv("BRN_LINEAR_FLASH"))
         if (!atoi(env)) return false;
-    return N >= 1 && S >= 1 && F % 16 == 0 && F <= LF_FMAX && (reinterpret_cast<uintptr_t>(X) & 15) == 0;
+    return N >= 1 && N < (int64_t)1 << 31 && S >= 1 && F % 16 == 0 && F <= LF_FMAX && (reinterpret_cast<uintptr_t>(X) & 15) == 0;
 }
 
 // dW [S][F] = + d ll / d W, loss += loss_scale * sum ll for S weight vectors W [S][F] over N rows (Bernoulli, C == 1)
@@ -474,19 +418,23 @@ static int launch_linear_flash(const float* X, const float* y, int64_t N, int F,
     BRN_LAUNCH_OK("lf_absmax_kernel");
     lf_absmax_kernel<<<(unsigned)std::min<int64_t>((N * F / 4 + 255) / 256 + 1, 1184), 256, 0, stream>>>(X, N * F, b.scal + 1);
     BRN_LAUNCH_OK("lf_absmax_kernel");
-    linear_flash_split_w_kernel<<<(unsigned)(((int64_t)S * F + 255) / 256), 256, 0, stream>>>(W, (int64_t)S * F, b.scal, b.Wh, b.Wl);
-    BRN_LAUNCH_OK("linear_flash_split_w_kernel");
-    CUtensorMap tWh, tWl;
+    linear_flash_split_kernel<<<(unsigned)std::min<int64_t>(((int64_t)S * F / 8 + 255) / 256 + 1, 1184), 256, 0, stream>>>(
+        W, (int64_t)S * F, b.scal, b.Wh, b.Wl);
+    BRN_LAUNCH_OK("linear_flash_split_kernel");
+    linear_flash_split_kernel<<<(unsigned)std::min<int64_t>((N * F / 8 + 255) / 256 + 1, 2368), 256, 0, stream>>>(X, N * F, b.scal + 1,
+                                                                                                                   b.Xh, b.Xl);
+    BRN_LAUNCH_OK("linear_flash_split_kernel");
+    CUtensorMap tWh, tWl, tXh, tXl;
     if (int e = make_tmap_2d_f16(&tWh, b.Wh, S, F, F, LF_MT, 64)) return e;
     if (int e = make_tmap_2d_f16(&tWl, b.Wl, S, F, F, LF_MT, 64)) return e;
+    if (int e = make_tmap_2d_f16(&tXh, b.Xh, N, F, F, LF_ROWS, 64)) return e;
+    if (int e = make_tmap_2d_f16(&tXl, b.Xl, N, F, F, LF_ROWS, 64)) return e;
     LinearFlashParams p;
-    p.X = X; p.y = y; p.N = N; p.F = F; p.S = S; p.scal = b.scal; p.part = b.part; p.part_stride = (int64_t)S * F;
+    p.y = y; p.N = N; p.F = F; p.S = S; p.scal = b.scal; p.part = b.part; p.part_stride = (int64_t)S * F;
     p.loss = loss; p.loss_scale = loss_scale; p.groups = b.groups;
-    p.flags = 0;
-    if (const char* env = getenv("BRN_LF_FLAGS")) p.flags = atoi(env);
     BRN_CUDA_OK(cudaFuncSetAttribute(linear_flash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LinearFlashSmem::TOTAL));
     dim3 grid(b.tiles, b.groups);
-    linear_flash_kernel<<<grid, LF_THREADS, LinearFlashSmem::TOTAL, stream>>>(tWh, tWl, p);
+    linear_flash_kernel<<<grid, LF_THREADS, LinearFlashSmem::TOTAL, stream>>>(tWh, tWl, tXh, tXl, p);
     BRN_LAUNCH_OK("linear_flash_kernel");
     return 0;
 }

@@ -45,6 +45,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// Bounded variant: no wait of these kernels legitimately lasts seconds, so a protocol error traps (the launch fails
+// loudly) instead of hanging the device.  Costs one register: used where the budget allows.
+__device__ __forceinline__ void mbar_wait_guarded(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins == (1u << 28)) __trap();
+    }
+}
 
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
