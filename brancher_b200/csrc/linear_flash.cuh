@@ -29,11 +29,11 @@ constexpr int LF_ROWS = 64;            // rows of X per block (N of MMA1, K of M
 constexpr int LF_MT = 128;             // weight vectors per CTA tile (M of both MMAs)
 constexpr int LF_FMAX = 128;           // features (K of MMA1, N of MMA2): multiple of 16, at most 128
 constexpr int LF_XSTAGES = 4;          // X blocks (fp16 pair images, 32 KB each) in flight
+constexpr int LF_D1BUF = 3;            // logits accumulators in TMEM: the logits MMA runs two blocks ahead of the gradient MMA
 constexpr int LF_THREADS = 640;        // 20 warps: TMA, MMA, 2 idle | 16 epilogue
 constexpr int LF_EPI_WARP0 = 4, LF_EPI_WARPS = 16;
-constexpr int LF_EROWS = LF_ROWS / (LF_EPI_WARPS / 4);      // 16 rows of a block per epilogue warp
-constexpr int LF_EFEAT = LF_FMAX / (LF_EPI_WARPS / 4);      // 32 gradient features per epilogue warp
-static_assert(LF_EROWS == 16 && LF_EFEAT == 32, "the TMEM load shapes of the epilogue are written for 16 warps");
+constexpr int LF_EROWS = 32;           // rows of a block per epilogue warp (two warps of one group cover a block)
+constexpr int LF_EFEAT = 32;           // gradient features per epilogue warp (all 16 warps drain every chain)
 constexpr int LF_D2_CHAIN = 2;         // blocks per D2 accumulation chain
 constexpr float LF_D_SCALE = 8192.f;   // 2^13: |d| < 1
 
@@ -64,10 +64,27 @@ __host__ __device__ constexpr uint32_t idesc_f16_major(int M, int N, bool b_mn) 
     return (1u << 4) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(umma::smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(umma::smem_u32(bar))
-                 : "memory");
+// packed fp32 pairs (one issue slot for two lanes of work; sm_100)
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
 }
 
 struct LinearFlashParams {
@@ -77,6 +94,7 @@ struct LinearFlashParams {
     int64_t part_stride;          // S_pad * F
     double* loss; float loss_scale;
     int groups;
+    int dbg;                      // timing experiments only (BRN_LF_DBG; results are WRONG when non-zero)
 };
 
 __global__ void __launch_bounds__(LF_THREADS, 1)
@@ -85,8 +103,8 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
     using SM = LinearFlashSmem;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    __shared__ __align__(8) uint64_t w_full, x_full[LF_XSTAGES], x_empty[LF_XSTAGES],
-        d1_full[2], d1_empty[2], d_full, d_empty, acc2_full[2], acc2_empty[2];
+    __shared__ __align__(8) uint64_t w_full, x_full[LF_XSTAGES], x_empty[LF_XSTAGES], d1_full[LF_D1BUF], d1_empty[LF_D1BUF],
+        d_full, d_empty, acc2_full[2], acc2_empty[2];
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -100,11 +118,9 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
         umma::tma_prefetch_desc(&tmXh); umma::tma_prefetch_desc(&tmXl);
         umma::mbar_init(&w_full, 1);
         for (int s = 0; s < LF_XSTAGES; ++s) { umma::mbar_init(&x_full[s], 1); umma::mbar_init(&x_empty[s], 1); }
-        for (int b = 0; b < 2; ++b) {
-            umma::mbar_init(&d1_full[b], 1); umma::mbar_init(&d1_empty[b], LF_EPI_WARPS);
-            umma::mbar_init(&acc2_full[b], 1); umma::mbar_init(&acc2_empty[b], LF_EPI_WARPS);
-        }
-        umma::mbar_init(&d_full, LF_EPI_WARPS); umma::mbar_init(&d_empty, 1);
+        for (int b = 0; b < LF_D1BUF; ++b) { umma::mbar_init(&d1_full[b], 1); umma::mbar_init(&d1_empty[b], LF_EPI_WARPS / 2); }
+        for (int b = 0; b < 2; ++b) { umma::mbar_init(&acc2_full[b], 1); umma::mbar_init(&acc2_empty[b], LF_EPI_WARPS); }
+        umma::mbar_init(&d_full, LF_EPI_WARPS / 2); umma::mbar_init(&d_empty, 1);
         umma::fence_barrier_init();
     }
     if (warp == 1) umma::tmem_alloc(&tmem_base_slot, 512);
@@ -112,7 +128,7 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
     __syncthreads();
     umma::tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
-    const uint32_t t_d1 = tmem_base, t_d2 = tmem_base + 128;        // D1: 2 x 64 columns at 0 / 64; D2: 2 x 128 at 128 / 256
+    const uint32_t t_d1 = tmem_base, t_d2 = tmem_base + 256;        // D1: 3 x 64 columns at 0 / 64 / 128; D2: 2 x 128 at 256 / 384
 
     // register budget: the CTA owns 96 registers x 640 threads (launch bounds); setmaxnreg only moves registers INSIDE that
     // allocation (asking for more blocks forever), so per warpgroup 32 + 4 x 112 = 480 = 5 x 96
@@ -120,7 +136,7 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
         asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     if (warp == 0) {
         // ===================== producer: W tile once, then the X blocks (rows past N are zero-filled by TMA) =====================
-        if (lane == 0) {
+        if (umma::elect_one()) {
             umma::mbar_arrive_expect_tx(&w_full, (uint32_t)(2 * FB * LF_MT * 128));
             for (int b = 0; b < FB; ++b) {
                 umma::tma_load_2d(smem + SM::off_w + b * (LF_MT * 128), &tmWh, &w_full, b * 64, st * LF_MT);
@@ -141,7 +157,9 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // tensor-pipe order: L(0) L(1) | G(0) L(2) | G(1) L(3) | ...   (L = logits MMA of a block, G = its gradient MMA):
+        // while the epilogue turns L(i) into d(i), the pipe works on L(i+1) and G(i-1), L(i+2)
+        if (umma::elect_one()) {
             const uint32_t idesc1 = idesc_f16_major(LF_MT, LF_ROWS, false);
             const uint32_t idesc2 = idesc_f16_major(LF_MT, F, true);
             const uint32_t wh = umma::smem_u32(smem + SM::off_w), wl = wh + SM::W_BYTES / 2;
@@ -150,9 +168,9 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
             umma::mbar_wait_guarded(&w_full, 0);
             umma::tc_fence_after();
             auto mma1 = [&](int64_t i) {
-                const int stage = (int)(i % LF_XSTAGES), b = (int)(i & 1);
+                const int stage = (int)(i % LF_XSTAGES), b = (int)(i % LF_D1BUF);
                 umma::mbar_wait_guarded(&x_full[stage], (uint32_t)((i / LF_XSTAGES) & 1));
-                umma::mbar_wait_guarded(&d1_empty[b], (uint32_t)(((i >> 1) & 1) ^ 1));
+                umma::mbar_wait_guarded(&d1_empty[b], (uint32_t)(((i / LF_D1BUF) & 1) ^ 1));
                 umma::tc_fence_after();
                 const uint32_t xh = umma::smem_u32(smem + SM::off_x16 + stage * SM::X16_BYTES), xl = xh + SM::X16_BYTES / 2;
                 const uint32_t d_t = t_d1 + b * 64;
@@ -160,16 +178,18 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
                     const uint32_t ao = (ks >> 2) * (LF_MT * 128) + (ks & 3) * 32, bo = (ks >> 2) * (LF_ROWS * 128) + (ks & 3) * 32;
                     const uint64_t dah = umma::smem_desc_k<128>(wh + ao), dal = umma::smem_desc_k<128>(wl + ao);
                     const uint64_t dbh = umma::smem_desc_k<128>(xh + bo), dbl = umma::smem_desc_k<128>(xl + bo);
-                    umma::mma_f16_ss(d_t, dal, dbh, idesc1, ks != 0);
-                    umma::mma_f16_ss(d_t, dah, dbl, idesc1, true);
-                    umma::mma_f16_ss(d_t, dah, dbh, idesc1, true);
+                    if (!(p.dbg & 1)) {
+                        umma::mma_f16_ss(d_t, dal, dbh, idesc1, ks != 0);
+                        umma::mma_f16_ss(d_t, dah, dbl, idesc1, true);
+                    }
+                    umma::mma_f16_ss(d_t, dah, dbh, idesc1, (p.dbg & 1) ? ks != 0 : true);
                 }
                 umma::mma_commit(&d1_full[b]);
             };
             if (my_blocks > 0) mma1(0);
+            if (my_blocks > 1) mma1(1);
             uint32_t chain = 0;                       // index of the current D2 accumulation chain
             for (int64_t i = 0; i < my_blocks; ++i) {
-                if (i + 1 < my_blocks) mma1(i + 1);   // keeps the tensor core busy while the epilogue turns L into d
                 const int stage = (int)(i % LF_XSTAGES);
                 const uint32_t buf = chain & 1;
                 if (i % LF_D2_CHAIN == 0) {
@@ -186,9 +206,11 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
                     const uint64_t dbh = smem_desc_mn_sw128(xh + ks * 2048, LF_ROWS * 128, 1024);
                     const uint64_t dbl = smem_desc_mn_sw128(xl + ks * 2048, LF_ROWS * 128, 1024);
                     const bool acc = (i % LF_D2_CHAIN != 0) || ks != 0;
-                    umma::mma_f16_ss(d_t, dal, dbh, idesc2, acc);
-                    umma::mma_f16_ss(d_t, dah, dbl, idesc2, true);
-                    umma::mma_f16_ss(d_t, dah, dbh, idesc2, true);
+                    if (!(p.dbg & 2)) {
+                        umma::mma_f16_ss(d_t, dal, dbh, idesc2, acc);
+                        umma::mma_f16_ss(d_t, dah, dbl, idesc2, true);
+                    }
+                    umma::mma_f16_ss(d_t, dah, dbh, idesc2, (p.dbg & 2) ? acc : true);
                 }
                 umma::mma_commit(&x_empty[stage]);     // X block and d tile are free once these MMAs retire
                 umma::mma_commit(&d_empty);
@@ -196,30 +218,32 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
                     umma::mma_commit(&acc2_full[buf]);
                     ++chain;
                 }
+                if (i + 2 < my_blocks) mma1(i + 2);
             }
         }
     }
     } else {
         // ===================== epilogue: likelihood, d tile, D2 drains =====================
-        // 16 warps = 4 per TMEM lane quarter; warp (q, part) owns vectors 32 q .. 32 q + 31 and, of every block, rows
-        // 16 part .. + 15 (logits -> d) and features 32 part .. + 31 (gradient accumulator)
+        // 16 warps = 4 per TMEM lane quarter q (vectors 32 q .. 32 q + 31 = this warp's lanes).  Two groups of 8 warps take
+        // the blocks alternately (group = block parity), so one group's MUFU-heavy phase overlaps the other's ALU phase;
+        // inside a group, warp half hp owns rows 32 hp .. + 31 of the block.  ALL 16 warps drain every gradient chain
+        // (features 32 part .. + 31).
         asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
         const int ew = warp - LF_EPI_WARP0;
-        const int q = warp & 3, part = ew >> 2;
+        const int q = warp & 3, part = ew >> 2, grp = part & 1, hp = part >> 1;
         const int s_local = q * 32 + lane;                          // vector inside the tile = TMEM lane = row of the d tile
         const int s_glob = st * LF_MT + s_local;
         const bool s_ok = s_glob < p.S;
-        const float inv1 = 1.f / (p2_scale(p.scal[0]) * p2_scale(p.scal[1]));
+        const float inv1 = 1.f / (p2_scale(p.scal[0]) * p2_scale(p.scal[1]));      // logit = D1 * inv1
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         uint8_t* dh = smem + SM::off_d;
         uint8_t* dl = dh + SM::D_BYTES / 2;
         float r2[LF_EFEAT];
 #pragma unroll
         for (int c = 0; c < LF_EFEAT; ++c) r2[c] = 0.f;
-        double ll_total = 0.0;      // per-block fp32 sums (16 terms) are added in double: a long fp32 running sum drops the many
+        double ll_total = 0.0;      // per-block fp32 sums (32 terms) are added in double: a long fp32 running sum drops the many
                                     // near-zero terms of well-classified rows once it is large (error grew linearly with N)
-        uint32_t chain = 0;
-        bool pending = false;       // a finished D2 chain waits to be drained (after the NEXT block's d is on its way)
+        uint32_t chain = 0;         // next gradient chain to drain
         auto drain = [&]() {
             const uint32_t buf = chain & 1;
             umma::mbar_wait_guarded(&acc2_full[buf], (chain >> 1) & 1);
@@ -234,71 +258,98 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
             if (lane == 0) umma::mbar_arrive(&acc2_empty[buf]);
             ++chain;
         };
-        float y_next = 0.f;         // lane j < 16 holds y of row 16 part + j, loaded one block ahead (0 past the end)
-        if (my_blocks > 0) {
-            const int64_t rn = (int64_t)g * LF_ROWS + part * LF_EROWS + (lane & (LF_EROWS - 1));
-            y_next = rn < p.N ? __ldg(p.y + rn) : 0.f;
-        }
-        for (int64_t i = 0; i < my_blocks; ++i) {
+        const int64_t n_chains = (my_blocks + LF_D2_CHAIN - 1) / LF_D2_CHAIN;
+        // lane j holds S * y of row 32 hp + j of this group's next block (0 past the end of the data)
+        auto load_y = [&](int64_t i) {
+            const int64_t rn = (g + i * p.groups) * LF_ROWS + hp * LF_EROWS + lane;
+            return (i < my_blocks && rn < p.N) ? __ldg(p.y + rn) * LF_D_SCALE : 0.f;
+        };
+        float y_next = load_y(grp);
+        const uint64_t c2 = f2_pack(inv1 * 1.4426950408889634f, inv1 * 1.4426950408889634f);
+        const uint64_t one2 = f2_pack(1.f, 1.f), ms2 = f2_pack(-LF_D_SCALE, -LF_D_SCALE), mone2 = f2_pack(-1.f, -1.f);
+        for (int64_t i = grp; i < my_blocks; i += 2) {
             const int64_t r0 = (g + i * p.groups) * LF_ROWS;
             const int rows = (int)min((int64_t)LF_ROWS, p.N - r0);
-            const int b = (int)(i & 1);
-            float ll = 0.f;
-            umma::mbar_wait_guarded(&d1_full[b], (uint32_t)((i >> 1) & 1));
+            const int b = (int)(i % LF_D1BUF);
+            umma::mbar_wait_guarded(&d1_full[b], (uint32_t)((i / LF_D1BUF) & 1));
             umma::tc_fence_after();
             float L[LF_EROWS];
-            umma::tmem_ld_32x16(t_d1 + lane_addr + b * 64 + part * LF_EROWS, L);
+            umma::tmem_ld_32x32(t_d1 + lane_addr + b * 64 + hp * LF_EROWS, L);
             umma::tmem_ld_wait();
             umma::tc_fence_before();
             __syncwarp();
             if (lane == 0) umma::mbar_arrive(&d1_empty[b]);
-            // d = y - sigmoid(l), ll += y l - softplus(l) (MUFU only, as EpiBernoulli).  Rows past the end of a ragged last
-            // block have X = 0, where d = y - 1/2 would be wrong: that block takes the predicated path.
+            const float ys_lane = y_next;
+            y_next = load_y(i + 2);
+            // Per element, with raw accumulator L (logit l = L * inv1), e = exp(-|l|), sig = sigmoid(l):
+            //   d * S = y S - S sig;   ll = y l - max(l, 0) - ln(1 + e)
+            // summed per block as inv1 * (sum(yS L) / S - sum(max(L, 0))) - ln 2 * log2(prod(1 + e))  -- ONE log per 16 elements
+            // (the product of 16 factors in (1, 2] cannot overflow), so 2 MUFU per element instead of 3.  Pairs of elements go
+            // through packed fp32x2 instructions.  Rows past the end of a ragged last block have X = 0 (L = 0), where
+            // d = y - 1/2 would be wrong: that block takes the predicated path.
             uint32_t dh_w[LF_EROWS / 2], dl_w[LF_EROWS / 2];
-            const float y_lane = y_next;
-            if (i + 1 < my_blocks) {
-                const int64_t rn = (g + (i + 1) * p.groups) * LF_ROWS + part * LF_EROWS + (lane & (LF_EROWS - 1));
-                y_next = rn < p.N ? __ldg(p.y + rn) : 0.f;
-            }
+            uint64_t acc_yl = f2_pack(0.f, 0.f), prod = one2;
+            float acc_mx = 0.f;
             auto body = [&](auto ragged) {
 #pragma unroll
                 for (int k = 0; k < LF_EROWS / 2; ++k) {
-                    float dv[2];
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const float yv = __shfl_sync(0xffffffffu, y_lane, 2 * k + u);
-                        const float l = L[2 * k + u] * inv1;
-                        float e, inv, lg;
-                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * fabsf(l)));
-                        const float ope = 1.f + e;
-                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(ope));
-                        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(ope));
-                        const float sig = l >= 0.f ? inv : e * inv;
-                        const float t = __fmaf_rn(yv, l, -__fmaf_rn(lg, 0.6931471805599453f, fmaxf(l, 0.f)));
-                        if (decltype(ragged)::value) {
-                            const bool ok = part * LF_EROWS + 2 * k + u < rows;
-                            dv[u] = ok ? (yv - sig) * LF_D_SCALE : 0.f;
-                            if (ok) ll += t;
-                        } else {
-                            dv[u] = (yv - sig) * LF_D_SCALE;
-                            ll += t;
-                        }
+                    const uint64_t ys2 = f2_pack(__shfl_sync(0xffffffffu, ys_lane, 2 * k), __shfl_sync(0xffffffffu, ys_lane, 2 * k + 1));
+                    const uint64_t L2 = f2_pack(L[2 * k], L[2 * k + 1]);
+                    float a0, a1, e0, e1, i0, i1, r0f, r1f;
+                    f2_unpack(f2_mul(L2, c2), a0, a1);
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(-fabsf(a0)));
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(-fabsf(a1)));
+                    if (decltype(ragged)::value) {
+                        if (hp * LF_EROWS + 2 * k >= rows) e0 = 0.f;
+                        if (hp * LF_EROWS + 2 * k + 1 >= rows) e1 = 0.f;
                     }
-                    const __half2 h2 = __floats2half2_rn(dv[0], dv[1]);
+                    const uint64_t e2 = f2_pack(e0, e1);
+                    const uint64_t ope2 = f2_add(e2, one2);
+                    float o0, o1;
+                    f2_unpack(ope2, o0, o1);
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(i0) : "f"(o0));
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(i1) : "f"(o1));
+                    f2_unpack(f2_mul(e2, f2_pack(i0, i1)), r0f, r1f);           // sigmoid(-|l|)
+                    const bool p0 = L[2 * k] >= 0.f, p1 = L[2 * k + 1] >= 0.f;
+                    const uint64_t sig2 = f2_pack(p0 ? i0 : r0f, p1 ? i1 : r1f);
+                    uint64_t ds2 = f2_fma(sig2, ms2, ys2);                      // S (y - sig)
+                    if (p0) acc_mx += L[2 * k];
+                    if (p1) acc_mx += L[2 * k + 1];
+                    acc_yl = f2_fma(ys2, L2, acc_yl);
+                    prod = f2_mul(prod, ope2);
+                    float d0, d1;
+                    f2_unpack(ds2, d0, d1);
+                    if (decltype(ragged)::value) {
+                        if (hp * LF_EROWS + 2 * k >= rows) d0 = 0.f;
+                        if (hp * LF_EROWS + 2 * k + 1 >= rows) d1 = 0.f;
+                        ds2 = f2_pack(d0, d1);
+                    }
+                    const __half2 h2 = __floats2half2_rn(d0, d1);
                     const float2 hfv = __half22float2(h2);
-                    const __half2 l2 = __floats2half2_rn(dv[0] - hfv.x, dv[1] - hfv.y);
+                    float l0, l1;
+                    f2_unpack(f2_fma(f2_pack(hfv.x, hfv.y), mone2, ds2), l0, l1);
+                    const __half2 l2 = __floats2half2_rn(l0, l1);
                     dh_w[k] = *reinterpret_cast<const uint32_t*>(&h2);
                     dl_w[k] = *reinterpret_cast<const uint32_t*>(&l2);
                 }
             };
-            if (rows == LF_ROWS) body(std::false_type{}); else body(std::true_type{});
-            // the d tile is free once MMA2 of the previous block has retired
+            if (p.dbg & 4) {
+#pragma unroll
+                for (int k = 0; k < LF_EROWS / 2; ++k) { dh_w[k] = __float_as_uint(L[2 * k]) & 0x3fff3fffu; dl_w[k] = __float_as_uint(L[2 * k + 1]) & 0x03ff03ffu; }
+            } else if (rows == LF_ROWS) body(std::false_type{}); else body(std::true_type{});
+            float ay0, ay1, pr0, pr1, lg0, lg1;
+            f2_unpack(acc_yl, ay0, ay1);
+            f2_unpack(prod, pr0, pr1);
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg0) : "f"(pr0));
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg1) : "f"(pr1));
+            const float ll = inv1 * ((ay0 + ay1) * (1.f / LF_D_SCALE) - acc_mx) - 0.6931471805599453f * (lg0 + lg1);
+            // the d tile is free once the gradient MMA of the previous block (the other group's) has retired
             umma::mbar_wait_guarded(&d_empty, (uint32_t)((i & 1) ^ 1));
             // K-major A tile [128 vectors][64 rows] fp16, 128-byte rows, SWIZZLE_128B: this thread owns row s_local and writes
-            // the chunks (8 rows of X each) of its rows
+            // the 4 chunks (8 rows of X each) of its rows
 #pragma unroll
             for (int cc = 0; cc < LF_EROWS / 8; ++cc) {
-                const int c = part * (LF_EROWS / 8) + cc;
+                const int c = hp * (LF_EROWS / 8) + cc;
                 const int off = s_local * 128 + ((c ^ (s_local & 7)) << 4);
                 *reinterpret_cast<uint4*>(dh + off) = make_uint4(dh_w[4 * cc], dh_w[4 * cc + 1], dh_w[4 * cc + 2], dh_w[4 * cc + 3]);
                 *reinterpret_cast<uint4*>(dl + off) = make_uint4(dl_w[4 * cc], dl_w[4 * cc + 1], dl_w[4 * cc + 2], dl_w[4 * cc + 3]);
@@ -307,11 +358,11 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
             __syncwarp();
             if (lane == 0) umma::mbar_arrive(&d_full);
             ll_total += (double)ll;
-            // the chain that ended with the PREVIOUS block is drained now, while the tensor core works on this block's d
-            if (pending) { drain(); pending = false; }
-            if (i % LF_D2_CHAIN == LF_D2_CHAIN - 1 || i + 1 == my_blocks) pending = true;
+            // chains that ended at or before block i - 1 are complete (or about to be): drain them now, while the tensor core
+            // works on this block's d  (chain c covers blocks 2c, 2c + 1)
+            while ((int64_t)chain < n_chains && (int64_t)(chain * LF_D2_CHAIN + LF_D2_CHAIN - 1) < i) drain();
         }
-        if (pending) drain();
+        while ((int64_t)chain < n_chains) drain();
         // this CTA's share of + d ll / d W for vector s_glob, features 32 part .. + 31
         if (s_ok) {
             const float inv2 = 1.f / (LF_D_SCALE * p2_scale(p.scal[1]));
@@ -432,6 +483,8 @@ static int launch_linear_flash(const float* X, const float* y, int64_t N, int F,
     LinearFlashParams p;
     p.y = y; p.N = N; p.F = F; p.S = S; p.scal = b.scal; p.part = b.part; p.part_stride = (int64_t)S * F;
     p.loss = loss; p.loss_scale = loss_scale; p.groups = b.groups;
+    p.dbg = 0;
+    if (const char* env = getenv("BRN_LF_DBG")) p.dbg = atoi(env);
     BRN_CUDA_OK(cudaFuncSetAttribute(linear_flash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LinearFlashSmem::TOTAL));
     dim3 grid(b.tiles, b.groups);
     linear_flash_kernel<<<grid, LF_THREADS, LinearFlashSmem::TOTAL, stream>>>(tWh, tWl, tXh, tXl, p);

@@ -134,6 +134,13 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uin
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
         : "memory");
 }
+// true in exactly one lane of the (converged) warp.  Issuing tcgen05 instructions under this predicate instead of
+// `lane == 0` lets ptxas emit them once: with a plain lane test it wraps every UTCHMMA in an ELECT / BRA.U.ANY loop.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 // KIND: 0 = tf32 operands (fp32 words), 1 = fp16 operands (two elements per 32-bit word)
 template <int KIND>
 __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {

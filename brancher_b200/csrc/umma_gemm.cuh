@@ -141,7 +141,7 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (umma::elect_one()) {
             int stage = 0; uint32_t phase = 0;
             for (UnitIter it(m_tiles, n_tiles, k_chunks, mode, split_T, full_units); it.valid(); it.next()) {
                 const int m0 = it.mt() * UG_BM, n0 = it.nt() * BN;
@@ -163,7 +163,7 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (umma::elect_one()) {      // not `lane == 0`: ptxas then issues each UTCHMMA once instead of inside an ELECT loop
             constexpr uint32_t idesc = umma::idesc_kind<KIND>(UG_BM, BN);
             int stage = 0; uint32_t phase = 0, blk = 0;
             for (UnitIter it(m_tiles, n_tiles, k_chunks, mode, split_T, full_units); it.valid(); it.next()) {
