@@ -94,9 +94,22 @@ struct LinearFlashParams {
     int64_t part_stride;          // S_pad * F
     double* loss; float loss_scale;
     int groups;
-    int dbg;                      // timing experiments only (BRN_LF_DBG; results are WRONG when non-zero)
 };
 
+// tcgen05.mma kind::f16 with both shared-memory descriptors given as (low word, shared high word)
+__device__ __forceinline__ void mma_f16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+
+// KS1 = F / 16 at compile time (the logits MMA loop is then fully unrolled), 0 = any F
+template <int KS1>
 __global__ void __launch_bounds__(LF_THREADS, 1)
 linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
                     const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl, LinearFlashParams p) {
@@ -131,9 +144,9 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
     const uint32_t t_d1 = tmem_base, t_d2 = tmem_base + 256;        // D1: 3 x 64 columns at 0 / 64 / 128; D2: 2 x 128 at 256 / 384
 
     // register budget: the CTA owns 96 registers x 640 threads (launch bounds); setmaxnreg only moves registers INSIDE that
-    // allocation (asking for more blocks forever), so per warpgroup 32 + 4 x 112 = 480 = 5 x 96
+    // allocation (asking for more blocks forever), so per warpgroup 64 + 4 x 104 = 480 = 5 x 96
     if (warp < LF_EPI_WARP0) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp == 0) {
         // ===================== producer: W tile once, then the X blocks (rows past N are zero-filled by TMA) =====================
         if (umma::elect_one()) {
@@ -156,69 +169,70 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        // tensor-pipe order: L(0) L(1) | G(0) L(2) | G(1) L(3) | ...   (L = logits MMA of a block, G = its gradient MMA):
-        // while the epilogue turns L(i) into d(i), the pipe works on L(i+1) and G(i-1), L(i+2)
+        // ===================== logits MMA issuer: L(i) = W . X_i^T -> D1[i % 3] =====================
+        // Two issuing threads (this one and warp 2), because the MMAs are small (32 / 64 tensor cycles each, 36 per block):
+        // a single thread that also waits on five barriers per block was itself the critical path (~420 instructions per
+        // block, 80 % busy).  All descriptors share their high word; the low word is a per-stage base plus a constant.
         if (umma::elect_one()) {
+            constexpr uint32_t HI = 0x40004040u;      // SBO = 1024 B, version 1, SWIZZLE_128B
             const uint32_t idesc1 = idesc_f16_major(LF_MT, LF_ROWS, false);
-            const uint32_t idesc2 = idesc_f16_major(LF_MT, F, true);
-            const uint32_t wh = umma::smem_u32(smem + SM::off_w), wl = wh + SM::W_BYTES / 2;
-            const uint32_t dh = umma::smem_u32(smem + SM::off_d), dl = dh + SM::D_BYTES / 2;
-            const int ksteps1 = F / 16;
+            const uint32_t w_h = (umma::smem_u32(smem + SM::off_w) >> 4) | (1u << 16), w_l = w_h + (SM::W_BYTES / 2 >> 4);
+            const uint32_t x0 = (umma::smem_u32(smem + SM::off_x16) >> 4) | (1u << 16);      // K-major view of X stage 0
+            const int ksteps1 = KS1 > 0 ? KS1 : F / 16;
             umma::mbar_wait_guarded(&w_full, 0);
             umma::tc_fence_after();
-            auto mma1 = [&](int64_t i) {
-                const int stage = (int)(i % LF_XSTAGES), b = (int)(i % LF_D1BUF);
-                umma::mbar_wait_guarded(&x_full[stage], (uint32_t)((i / LF_XSTAGES) & 1));
-                umma::mbar_wait_guarded(&d1_empty[b], (uint32_t)(((i / LF_D1BUF) & 1) ^ 1));
-                umma::tc_fence_after();
-                const uint32_t xh = umma::smem_u32(smem + SM::off_x16 + stage * SM::X16_BYTES), xl = xh + SM::X16_BYTES / 2;
-                const uint32_t d_t = t_d1 + b * 64;
-                for (int ks = 0; ks < ksteps1; ++ks) {
-                    const uint32_t ao = (ks >> 2) * (LF_MT * 128) + (ks & 3) * 32, bo = (ks >> 2) * (LF_ROWS * 128) + (ks & 3) * 32;
-                    const uint64_t dah = umma::smem_desc_k<128>(wh + ao), dal = umma::smem_desc_k<128>(wl + ao);
-                    const uint64_t dbh = umma::smem_desc_k<128>(xh + bo), dbl = umma::smem_desc_k<128>(xl + bo);
-                    if (!(p.dbg & 1)) {
-                        umma::mma_f16_ss(d_t, dal, dbh, idesc1, ks != 0);
-                        umma::mma_f16_ss(d_t, dah, dbl, idesc1, true);
-                    }
-                    umma::mma_f16_ss(d_t, dah, dbh, idesc1, (p.dbg & 1) ? ks != 0 : true);
-                }
-                umma::mma_commit(&d1_full[b]);
-            };
-            if (my_blocks > 0) mma1(0);
-            if (my_blocks > 1) mma1(1);
-            uint32_t chain = 0;                       // index of the current D2 accumulation chain
+            int xs = 0, b1 = 0;                        // X stage / D1 buffer (counters instead of i % 4, i % 3)
+            uint32_t xph = 0, d1ph = 1;                // parity of x_full[xs] / d1_empty[b1] to wait for
             for (int64_t i = 0; i < my_blocks; ++i) {
-                const int stage = (int)(i % LF_XSTAGES);
-                const uint32_t buf = chain & 1;
-                if (i % LF_D2_CHAIN == 0) {
-                    umma::mbar_wait_guarded(&acc2_empty[buf], ((chain >> 1) & 1) ^ 1);
-                    umma::tc_fence_after();
+                umma::mbar_wait_guarded(&x_full[xs], xph);
+                umma::mbar_wait_guarded(&d1_empty[b1], d1ph);
+                umma::tc_fence_after();
+                const uint32_t xk = x0 + xs * (SM::X16_BYTES >> 4);
+                const uint32_t d_t = t_d1 + b1 * 64;
+#pragma unroll
+                for (int ks = 0; ks < (KS1 > 0 ? KS1 : 8); ++ks) {
+                    if (KS1 == 0 && ks >= ksteps1) break;
+                    const uint32_t ao = (ks >> 2) * (LF_MT * 128 >> 4) + (ks & 3) * 2, bo = (ks >> 2) * (LF_ROWS * 128 >> 4) + (ks & 3) * 2;
+                    mma_f16_lohi(d_t, w_l + ao, xk + bo, HI, idesc1, ks != 0);
+                    mma_f16_lohi(d_t, w_h + ao, xk + (SM::X16_BYTES / 2 >> 4) + bo, HI, idesc1, true);
+                    mma_f16_lohi(d_t, w_h + ao, xk + bo, HI, idesc1, true);
                 }
+                umma::mma_commit(&d1_full[b1]);
+                if (++xs == LF_XSTAGES) { xs = 0; xph ^= 1; }
+                if (++b1 == LF_D1BUF) { b1 = 0; d1ph ^= 1; }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== gradient MMA issuer: D2 += d_i . X_i (X block read MN-major) =====================
+        if (umma::elect_one()) {
+            constexpr uint32_t HI = 0x40004040u;
+            const uint32_t idesc2 = idesc_f16_major(LF_MT, F, true);
+            const uint32_t d_h = (umma::smem_u32(smem + SM::off_d) >> 4) | (1u << 16), d_l = d_h + (SM::D_BYTES / 2 >> 4);
+            const uint32_t x0 = (umma::smem_u32(smem + SM::off_x16) >> 4) | ((LF_ROWS * 128 >> 4) << 16);   // MN-major view: LBO = one box
+            int xs = 0;
+            uint32_t chain = 0;                        // index of the current D2 accumulation chain
+            for (int64_t i = 0; i < my_blocks; ++i) {
+                const uint32_t buf = chain & 1;
+                const bool first = (i & (LF_D2_CHAIN - 1)) == 0;
+                if (first) umma::mbar_wait_guarded(&acc2_empty[buf], ((chain >> 1) & 1) ^ 1);
                 umma::mbar_wait_guarded(&d_full, (uint32_t)(i & 1));
                 umma::tc_fence_after();
-                const uint32_t xh = umma::smem_u32(smem + SM::off_x16 + stage * SM::X16_BYTES), xl = xh + SM::X16_BYTES / 2;
+                const uint32_t xm = x0 + xs * (SM::X16_BYTES >> 4);
                 const uint32_t d_t = t_d2 + buf * 128;
+#pragma unroll
                 for (int ks = 0; ks < LF_ROWS / 16; ++ks) {
-                    const uint64_t dah = umma::smem_desc_k<128>(dh + ks * 32), dal = umma::smem_desc_k<128>(dl + ks * 32);
-                    // B = the X block read MN-major: 16 K-indices (rows) = two 1024-byte atoms per k-step
-                    const uint64_t dbh = smem_desc_mn_sw128(xh + ks * 2048, LF_ROWS * 128, 1024);
-                    const uint64_t dbl = smem_desc_mn_sw128(xl + ks * 2048, LF_ROWS * 128, 1024);
-                    const bool acc = (i % LF_D2_CHAIN != 0) || ks != 0;
-                    if (!(p.dbg & 2)) {
-                        umma::mma_f16_ss(d_t, dal, dbh, idesc2, acc);
-                        umma::mma_f16_ss(d_t, dah, dbl, idesc2, true);
-                    }
-                    umma::mma_f16_ss(d_t, dah, dbh, idesc2, (p.dbg & 2) ? acc : true);
+                    // A = d tile, K-major (32 bytes per k-step); B: 16 K-indices (rows of X) = 2 KB per k-step
+                    mma_f16_lohi(d_t, d_l + ks * 2, xm + ks * 128, HI, idesc2, !first || ks != 0);
+                    mma_f16_lohi(d_t, d_h + ks * 2, xm + (SM::X16_BYTES / 2 >> 4) + ks * 128, HI, idesc2, true);
+                    mma_f16_lohi(d_t, d_h + ks * 2, xm + ks * 128, HI, idesc2, true);
                 }
-                umma::mma_commit(&x_empty[stage]);     // X block and d tile are free once these MMAs retire
-                umma::mma_commit(&d_empty);
-                if (i % LF_D2_CHAIN == LF_D2_CHAIN - 1 || i + 1 == my_blocks) {
+                umma::mma_commit(&x_empty[xs]);        // X block and d tile are free once these MMAs retire (the logits MMA of
+                umma::mma_commit(&d_empty);            // this block retired long ago: d was computed from its result)
+                if (!((i + 1) & (LF_D2_CHAIN - 1)) || i + 1 == my_blocks) {
                     umma::mma_commit(&acc2_full[buf]);
                     ++chain;
                 }
-                if (i + 2 < my_blocks) mma1(i + 2);
+                if (++xs == LF_XSTAGES) xs = 0;
             }
         }
     }
@@ -228,7 +242,7 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
         // the blocks alternately (group = block parity), so one group's MUFU-heavy phase overlaps the other's ALU phase;
         // inside a group, warp half hp owns rows 32 hp .. + 31 of the block.  ALL 16 warps drain every gradient chain
         // (features 32 part .. + 31).
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         const int ew = warp - LF_EPI_WARP0;
         const int q = warp & 3, part = ew >> 2, grp = part & 1, hp = part >> 1;
         const int s_local = q * 32 + lane;                          // vector inside the tile = TMEM lane = row of the d tile
@@ -259,19 +273,17 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
             ++chain;
         };
         const int64_t n_chains = (my_blocks + LF_D2_CHAIN - 1) / LF_D2_CHAIN;
-        // lane j holds S * y of row 32 hp + j of this group's next block (0 past the end of the data)
-        auto load_y = [&](int64_t i) {
-            const int64_t rn = (g + i * p.groups) * LF_ROWS + hp * LF_EROWS + lane;
-            return (i < my_blocks && rn < p.N) ? __ldg(p.y + rn) * LF_D_SCALE : 0.f;
-        };
-        float y_next = load_y(grp);
         const uint64_t c2 = f2_pack(inv1 * 1.4426950408889634f, inv1 * 1.4426950408889634f);
         const uint64_t one2 = f2_pack(1.f, 1.f), ms2 = f2_pack(-LF_D_SCALE, -LF_D_SCALE), mone2 = f2_pack(-1.f, -1.f);
+        int b = grp;                                   // D1 buffer of this group's next block: (b + 2) % 3 per step
+        uint32_t d1ph = 0;                             // parity of d1_full[b] to wait for; flips when b wraps
         for (int64_t i = grp; i < my_blocks; i += 2) {
             const int64_t r0 = (g + i * p.groups) * LF_ROWS;
             const int rows = (int)min((int64_t)LF_ROWS, p.N - r0);
-            const int b = (int)(i % LF_D1BUF);
-            umma::mbar_wait_guarded(&d1_full[b], (uint32_t)((i / LF_D1BUF) & 1));
+            // lane j: S * y of row 32 hp + j (0 past the end of the data); issued before the wait so its latency is hidden
+            const int64_t rn = r0 + hp * LF_EROWS + lane;
+            const float y_raw = rn < p.N ? __ldg(p.y + rn) : 0.f;
+            umma::mbar_wait_guarded(&d1_full[b], d1ph);
             umma::tc_fence_after();
             float L[LF_EROWS];
             umma::tmem_ld_32x32(t_d1 + lane_addr + b * 64 + hp * LF_EROWS, L);
@@ -279,8 +291,9 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
             umma::tc_fence_before();
             __syncwarp();
             if (lane == 0) umma::mbar_arrive(&d1_empty[b]);
-            const float ys_lane = y_next;
-            y_next = load_y(i + 2);
+            b += 2;
+            if (b >= LF_D1BUF) { b -= LF_D1BUF; d1ph ^= 1; }
+            const float ys_lane = y_raw * LF_D_SCALE;
             // Per element, with raw accumulator L (logit l = L * inv1), e = exp(-|l|), sig = sigmoid(l):
             //   d * S = y S - S sig;   ll = y l - max(l, 0) - ln(1 + e)
             // summed per block as inv1 * (sum(yS L) / S - sum(max(L, 0))) - ln 2 * log2(prod(1 + e))  -- ONE log per 16 elements
@@ -333,10 +346,7 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
                     dl_w[k] = *reinterpret_cast<const uint32_t*>(&l2);
                 }
             };
-            if (p.dbg & 4) {
-#pragma unroll
-                for (int k = 0; k < LF_EROWS / 2; ++k) { dh_w[k] = __float_as_uint(L[2 * k]) & 0x3fff3fffu; dl_w[k] = __float_as_uint(L[2 * k + 1]) & 0x03ff03ffu; }
-            } else if (rows == LF_ROWS) body(std::false_type{}); else body(std::true_type{});
+            if (rows == LF_ROWS) body(std::false_type{}); else body(std::true_type{});
             float ay0, ay1, pr0, pr1, lg0, lg1;
             f2_unpack(acc_yl, ay0, ay1);
             f2_unpack(prod, pr0, pr1);
@@ -483,11 +493,14 @@ static int launch_linear_flash(const float* X, const float* y, int64_t N, int F,
     LinearFlashParams p;
     p.y = y; p.N = N; p.F = F; p.S = S; p.scal = b.scal; p.part = b.part; p.part_stride = (int64_t)S * F;
     p.loss = loss; p.loss_scale = loss_scale; p.groups = b.groups;
-    p.dbg = 0;
-    if (const char* env = getenv("BRN_LF_DBG")) p.dbg = atoi(env);
-    BRN_CUDA_OK(cudaFuncSetAttribute(linear_flash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LinearFlashSmem::TOTAL));
     dim3 grid(b.tiles, b.groups);
-    linear_flash_kernel<<<grid, LF_THREADS, LinearFlashSmem::TOTAL, stream>>>(tWh, tWl, tXh, tXl, p);
+    if (F == 128) {
+        BRN_CUDA_OK(cudaFuncSetAttribute(linear_flash_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, LinearFlashSmem::TOTAL));
+        linear_flash_kernel<8><<<grid, LF_THREADS, LinearFlashSmem::TOTAL, stream>>>(tWh, tWl, tXh, tXl, p);
+    } else {
+        BRN_CUDA_OK(cudaFuncSetAttribute(linear_flash_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, LinearFlashSmem::TOTAL));
+        linear_flash_kernel<0><<<grid, LF_THREADS, LinearFlashSmem::TOTAL, stream>>>(tWh, tWl, tXh, tXl, p);
+    }
     BRN_LAUNCH_OK("linear_flash_kernel");
     return 0;
 }
