@@ -117,7 +117,7 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) uint64_t w_full, x_full[LF_XSTAGES], x_empty[LF_XSTAGES], d1_full[LF_D1BUF], d1_empty[LF_D1BUF],
-        d_full, d_empty, acc2_full[2], acc2_empty[2];
+        d_full[2], d_empty[2], acc2_full[2], acc2_empty[2];
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -133,7 +133,9 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
         for (int s = 0; s < LF_XSTAGES; ++s) { umma::mbar_init(&x_full[s], 1); umma::mbar_init(&x_empty[s], 1); }
         for (int b = 0; b < LF_D1BUF; ++b) { umma::mbar_init(&d1_full[b], 1); umma::mbar_init(&d1_empty[b], LF_EPI_WARPS / 2); }
         for (int b = 0; b < 2; ++b) { umma::mbar_init(&acc2_full[b], 1); umma::mbar_init(&acc2_empty[b], LF_EPI_WARPS); }
-        umma::mbar_init(&d_full, LF_EPI_WARPS / 2); umma::mbar_init(&d_empty, 1);
+        // the ONE d tile is handed over through barriers indexed by block parity (= epilogue group): with a single barrier
+        // a group running two phases behind would alias on the phase parity now that the two MMA threads are not ordered
+        for (int b = 0; b < 2; ++b) { umma::mbar_init(&d_full[b], LF_EPI_WARPS / 2); umma::mbar_init(&d_empty[b], 1); }
         umma::fence_barrier_init();
     }
     if (warp == 1) umma::tmem_alloc(&tmem_base_slot, 512);
@@ -215,7 +217,7 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
                 const uint32_t buf = chain & 1;
                 const bool first = (i & (LF_D2_CHAIN - 1)) == 0;
                 if (first) umma::mbar_wait_guarded(&acc2_empty[buf], ((chain >> 1) & 1) ^ 1);
-                umma::mbar_wait_guarded(&d_full, (uint32_t)(i & 1));
+                umma::mbar_wait_guarded(&d_full[i & 1], (uint32_t)((i >> 1) & 1));
                 umma::tc_fence_after();
                 const uint32_t xm = x0 + xs * (SM::X16_BYTES >> 4);
                 const uint32_t d_t = t_d2 + buf * 128;
@@ -227,7 +229,7 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
                     mma_f16_lohi(d_t, d_h + ks * 2, xm + ks * 128, HI, idesc2, true);
                 }
                 umma::mma_commit(&x_empty[xs]);        // X block and d tile are free once these MMAs retire (the logits MMA of
-                umma::mma_commit(&d_empty);            // this block retired long ago: d was computed from its result)
+                umma::mma_commit(&d_empty[i & 1]);     // this block retired long ago: d was computed from its result)
                 if (!((i + 1) & (LF_D2_CHAIN - 1)) || i + 1 == my_blocks) {
                     umma::mma_commit(&acc2_full[buf]);
                     ++chain;
@@ -354,7 +356,8 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
             asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg1) : "f"(pr1));
             const float ll = inv1 * ((ay0 + ay1) * (1.f / LF_D_SCALE) - acc_mx) - 0.6931471805599453f * (lg0 + lg1);
             // the d tile is free once the gradient MMA of the previous block (the other group's) has retired
-            umma::mbar_wait_guarded(&d_empty, (uint32_t)((i & 1) ^ 1));
+            // (block i - 1: barrier of the other parity, its use (i - 1) / 2; the first block has nothing to wait for)
+            if (i > 0) umma::mbar_wait_guarded(&d_empty[(i & 1) ^ 1], (uint32_t)(((i - 1) >> 1) & 1));
             // K-major A tile [128 vectors][64 rows] fp16, 128-byte rows, SWIZZLE_128B: this thread owns row s_local and writes
             // the 4 chunks (8 rows of X each) of its rows
 #pragma unroll
@@ -366,7 +369,7 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
             }
             umma::fence_proxy_async();
             __syncwarp();
-            if (lane == 0) umma::mbar_arrive(&d_full);
+            if (lane == 0) umma::mbar_arrive(&d_full[grp]);
             ll_total += (double)ll;
             // chains that ended at or before block i - 1 are complete (or about to be): drain them now, while the tensor core
             // works on this block's d  (chain c covers blocks 2c, 2c + 1)
