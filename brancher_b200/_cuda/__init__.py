@@ -109,6 +109,13 @@ SYMBOLS = {
                                                ctypes.c_int, ctypes.c_int, ctypes.POINTER(MFVar),
                                                ctypes.POINTER(SampleRange), ctypes.c_void_p, ctypes.c_size_t,
                                                ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "brn_linear_prepared_x_bytes": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int]),
+    "brn_linear_prepare_x": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t,
+                                            ctypes.c_void_p]),
+    "brn_linear_elbo_fwd_bwd_px": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
+                                                  ctypes.c_int, ctypes.c_int, ctypes.POINTER(MFVar),
+                                                  ctypes.POINTER(SampleRange), ctypes.c_void_p, ctypes.c_size_t,
+                                                  ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "brn_dag_elbo_fwd_bwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                             ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                             ctypes.POINTER(SampleRange), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
@@ -350,8 +357,34 @@ def bnn_predict(X, vars4, r, labels=True, probs=True, activation="tanh"):
 BERNOULLI, CATEGORICAL = 0, 1
 
 
-def linear_elbo_fwd_bwd(X, y, likelihood, w, C, r, with_prior=True, loss=None):
-    """K2.  X [N,F] fp32; y [N] fp32 {0,1} (BERNOULLI, C=1) or int32 labels (CATEGORICAL); w MeanFieldVar [C,F]."""
+class PreparedX:
+    """The prepared (scaled fp16 pair) form of a fixed data matrix for the one-pass K2 kernel (brn_linear_prepare_x), rebuilt
+    only when the matrix changes: a different tensor, or the same tensor after an in-place write (torch's version counter).
+    The source tensor is kept referenced, so its memory cannot be handed to another tensor while the prepared form is live."""
+
+    def __init__(self):
+        self.buf, self.src, self.version = None, None, None
+
+    def get(self, X, likelihood, C):
+        """pointer-carrying uint8 tensor for `px`, or None when this call has no prepared form"""
+        N, F = X.shape
+        nbytes = lib().brn_linear_prepared_x_bytes(N, F) if (likelihood == BERNOULLI and C == 1) else 0
+        if nbytes == 0 or X.data_ptr() % 16:
+            return None
+        same = (self.src is not None and self.src.data_ptr() == X.data_ptr() and self.src.shape == X.shape
+                and self.src.device == X.device and self.version == X._version)
+        if not same:
+            if self.buf is None or self.buf.numel() < nbytes or self.buf.device != X.device:
+                self.buf = torch.empty(nbytes, dtype=torch.uint8, device=X.device)
+            _check(lib().brn_linear_prepare_x(_ptr(X, what="X"), N, F, self.buf.data_ptr(), self.buf.numel(), _stream(X.device)),
+                   "brn_linear_prepare_x")
+            self.src, self.version = X, X._version
+        return self.buf
+
+
+def linear_elbo_fwd_bwd(X, y, likelihood, w, C, r, with_prior=True, loss=None, prepared=None):
+    """K2.  X [N,F] fp32; y [N] fp32 {0,1} (BERNOULLI, C=1) or int32 labels (CATEGORICAL); w MeanFieldVar [C,F].
+    prepared: a PreparedX kept by the caller across evaluations of the same data matrix (optional)."""
     dev = X.device
     N, F = X.shape
     if w.numel != C * F:
@@ -364,9 +397,10 @@ def linear_elbo_fwd_bwd(X, y, likelihood, w, C, r, with_prior=True, loss=None):
     ws = _workspace(dev, nbytes)
     st = w.struct()
     ydt = torch.float32 if likelihood == BERNOULLI else torch.int32
-    _check(lib().brn_linear_elbo_fwd_bwd(_ptr(X, what="X"), _ptr(y, ydt, "y"), likelihood, N, F, C, ctypes.byref(st),
-                                         ctypes.byref(r), ws.data_ptr(), ws.numel(), int(with_prior),
-                                         _ptr(loss, torch.float64), _stream(dev)), "brn_linear_elbo_fwd_bwd")
+    px = prepared.get(X, likelihood, C) if (prepared is not None and N > 0) else None
+    _check(lib().brn_linear_elbo_fwd_bwd_px(_ptr(X, what="X"), px.data_ptr() if px is not None else None, _ptr(y, ydt, "y"),
+                                            likelihood, N, F, C, ctypes.byref(st), ctypes.byref(r), ws.data_ptr(), ws.numel(),
+                                            int(with_prior), _ptr(loss, torch.float64), _stream(dev)), "brn_linear_elbo_fwd_bwd_px")
     return loss
 
 

@@ -385,12 +385,12 @@ static int launch_linear_fused(const float* X, const void* y, int likelihood, in
 //   with per-slice accumulation (no atomics); finally the slices are summed into dW [S, F] = + d ll / d W.
 static int launch_linear_tc(const float* X, const float* y, int64_t N, int F, int S, const float* W, float* dW, float loss_scale,
                             double* loss, const LinearTcBuffers& b, const char* stage_split, const char* stage_fused,
-                            cudaStream_t stream) {
+                            cudaStream_t stream, const void* px = nullptr) {
     if (linear_flash_ok(X, N, F, S)) {
         // one pass over X: logits MMA -> likelihood -> d through shared memory -> gradient MMA (linear_flash.cuh)
         set_variant("tcgen05-flash");
         StageTimer st2(stage_fused, stream);
-        if (int e = launch_linear_flash(X, y, N, F, S, W, dW, loss_scale, loss, b.flash, stream)) return e;
+        if (int e = launch_linear_flash(X, px, y, N, F, S, W, dW, loss_scale, loss, b.flash, stream)) return e;
         const int64_t tot = (int64_t)S * F;
         sum_slices_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(b.flash.part, b.flash.groups, tot, tot, dW);
         BRN_LAUNCH_OK("sum_slices_kernel");
@@ -559,10 +559,30 @@ extern "C" size_t brn_linear_workspace_bytes(int64_t N, int F, int C, int s_loca
     return LinearWorkspace(nullptr, (int64_t)C * F, s_local, N, F, tc, sms).bytes;
 }
 
+extern "C" size_t brn_linear_prepared_x_bytes(int64_t N, int F) { return linear_prepared_x_bytes(N, F); }
+
+extern "C" int brn_linear_prepare_x(const float* X, int64_t N, int F, void* px, size_t px_bytes, void* stream_) {
+    const size_t need = linear_prepared_x_bytes(N, F);
+    BRN_CHECK_ARG(need > 0, "brn_linear_prepare_x: no prepared form for N=%lld F=%d (needs N >= 1, F a multiple of 16, F <= %d)", (long long)N, F,
+                  LF_FMAX);
+    BRN_CHECK_ARG(X && px && px_bytes >= need, "brn_linear_prepare_x: NULL pointer or buffer too small (%zu < %zu)", px_bytes, need);
+    BRN_CHECK_ARG((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(px) & 255) == 0,
+                  "brn_linear_prepare_x: X must be 16-byte and px 256-byte aligned");
+    return launch_prepare_x(X, N, F, static_cast<float*>(px), prepared_x_hi(px), prepared_x_lo(px, N, F), (cudaStream_t)stream_);
+}
+
 extern "C" int brn_linear_elbo_fwd_bwd(const float* X, const void* y, int likelihood, int64_t N, int F, int C,
                                        const brn_mf_var* w, const brn_sample_range* r, void* workspace,
                                        size_t workspace_bytes, int with_prior, double* loss, void* stream_) {
+    return brn_linear_elbo_fwd_bwd_px(X, nullptr, y, likelihood, N, F, C, w, r, workspace, workspace_bytes, with_prior, loss, stream_);
+}
+
+extern "C" int brn_linear_elbo_fwd_bwd_px(const float* X, const void* px, const void* y, int likelihood, int64_t N, int F, int C,
+                                          const brn_mf_var* w, const brn_sample_range* r, void* workspace,
+                                          size_t workspace_bytes, int with_prior, double* loss, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
+    BRN_CHECK_ARG(!px || (linear_prepared_x_bytes(N, F) > 0 && (reinterpret_cast<uintptr_t>(px) & 255) == 0),
+                  "brn_linear_elbo_fwd_bwd_px: a prepared X does not exist for N=%lld F=%d, or px is not 256-byte aligned", (long long)N, F);
     BRN_CHECK_ARG(w && r && loss, "brn_linear_elbo_fwd_bwd: NULL pointer");
     BRN_CHECK_ARG(N >= 0 && F > 0 && C > 0, "brn_linear_elbo_fwd_bwd: bad shape N=%lld F=%d C=%d", (long long)N, F, C);
     BRN_CHECK_ARG(N == 0 || (X && y), "brn_linear_elbo_fwd_bwd: NULL data pointer");
@@ -597,7 +617,7 @@ extern "C" int brn_linear_elbo_fwd_bwd(const float* X, const void* y, int likeli
     delete st;
     if (N > 0 && use_tc) {
         if (int e = launch_linear_tc(X, reinterpret_cast<const float*>(y), N, F, S, ws.W, ws.dW, -1.0f / (float)r->s_total, loss,
-                                     ws.tc, "linear.split_operands", "linear.fused", stream))
+                                     ws.tc, "linear.split_operands", "linear.fused", stream, px))
             return e;
     } else if (N > 0) {
         StageTimer st2("linear.fused", stream);

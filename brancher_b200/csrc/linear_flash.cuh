@@ -89,7 +89,7 @@ __device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
 
 struct LinearFlashParams {
     const float* y; int64_t N; int F; int S;
-    const float* scal;            // [0] = max |W|, [1] = max |X|  (device scalars)
+    const float* scal_w; const float* scal_x;      // max |W|, max |X|  (device scalars)
     float* part;                  // [groups][S_pad][F] partial gradients (+ d ll / d W), one slice per row group
     int64_t part_stride;          // S_pad * F
     double* loss; float loss_scale;
@@ -146,9 +146,9 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
     const uint32_t t_d1 = tmem_base, t_d2 = tmem_base + 256;        // D1: 3 x 64 columns at 0 / 64 / 128; D2: 2 x 128 at 256 / 384
 
     // register budget: the CTA owns 96 registers x 640 threads (launch bounds); setmaxnreg only moves registers INSIDE that
-    // allocation (asking for more blocks forever), so per warpgroup 64 + 4 x 104 = 480 = 5 x 96
+    // allocation (asking for more blocks forever), so per warpgroup 32 + 4 x 112 = 480 = 5 x 96
     if (warp < LF_EPI_WARP0) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     if (warp == 0) {
         // ===================== producer: W tile once, then the X blocks (rows past N are zero-filled by TMA) =====================
         if (umma::elect_one()) {
@@ -244,13 +244,13 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
         // the blocks alternately (group = block parity), so one group's MUFU-heavy phase overlaps the other's ALU phase;
         // inside a group, warp half hp owns rows 32 hp .. + 31 of the block.  ALL 16 warps drain every gradient chain
         // (features 32 part .. + 31).
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
         const int ew = warp - LF_EPI_WARP0;
         const int q = warp & 3, part = ew >> 2, grp = part & 1, hp = part >> 1;
         const int s_local = q * 32 + lane;                          // vector inside the tile = TMEM lane = row of the d tile
         const int s_glob = st * LF_MT + s_local;
         const bool s_ok = s_glob < p.S;
-        const float inv1 = 1.f / (p2_scale(p.scal[0]) * p2_scale(p.scal[1]));      // logit = D1 * inv1
+        const float inv1 = 1.f / (p2_scale(*p.scal_w) * p2_scale(*p.scal_x));      // logit = D1 * inv1
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         uint8_t* dh = smem + SM::off_d;
         uint8_t* dl = dh + SM::D_BYTES / 2;
@@ -277,14 +277,22 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
         const int64_t n_chains = (my_blocks + LF_D2_CHAIN - 1) / LF_D2_CHAIN;
         const uint64_t c2 = f2_pack(inv1 * 1.4426950408889634f, inv1 * 1.4426950408889634f);
         const uint64_t one2 = f2_pack(1.f, 1.f), ms2 = f2_pack(-LF_D_SCALE, -LF_D_SCALE), mone2 = f2_pack(-1.f, -1.f);
+        float y_next = 0.f;
+        if (grp < my_blocks) {
+            const int64_t rn = (g + (int64_t)grp * p.groups) * LF_ROWS + hp * LF_EROWS + lane;
+            y_next = rn < p.N ? __ldg(p.y + rn) : 0.f;
+        }
         int b = grp;                                   // D1 buffer of this group's next block: (b + 2) % 3 per step
         uint32_t d1ph = 0;                             // parity of d1_full[b] to wait for; flips when b wraps
         for (int64_t i = grp; i < my_blocks; i += 2) {
             const int64_t r0 = (g + i * p.groups) * LF_ROWS;
             const int rows = (int)min((int64_t)LF_ROWS, p.N - r0);
-            // lane j: S * y of row 32 hp + j (0 past the end of the data); issued before the wait so its latency is hidden
-            const int64_t rn = r0 + hp * LF_EROWS + lane;
-            const float y_raw = rn < p.N ? __ldg(p.y + rn) : 0.f;
+            // lane j: y of row 32 hp + j of this block (0 past the end of the data), loaded one block ahead
+            const float y_raw = y_next;
+            {
+                const int64_t rn = r0 + 2 * p.groups * LF_ROWS + hp * LF_EROWS + lane;
+                y_next = (i + 2 < my_blocks && rn < p.N) ? __ldg(p.y + rn) : 0.f;
+            }
             umma::mbar_wait_guarded(&d1_full[b], d1ph);
             umma::tc_fence_after();
             float L[LF_EROWS];
@@ -378,7 +386,7 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
         while ((int64_t)chain < n_chains) drain();
         // this CTA's share of + d ll / d W for vector s_glob, features 32 part .. + 31
         if (s_ok) {
-            const float inv2 = 1.f / (LF_D_SCALE * p2_scale(p.scal[1]));
+            const float inv2 = 1.f / (LF_D_SCALE * p2_scale(*p.scal_x));
             float* o = p.part + (int64_t)g * p.part_stride + (int64_t)s_glob * F + part * LF_EFEAT;
 #pragma unroll
             for (int c = 0; c < LF_EFEAT; c += 4)
@@ -474,27 +482,51 @@ static bool linear_flash_ok(const float* X, int64_t N, int F, int S) {
     return N >= 1 && N < (int64_t)1 << 31 && S >= 1 && F % 16 == 0 && F <= LF_FMAX && (reinterpret_cast<uintptr_t>(X) & 15) == 0;
 }
 
-// dW [S][F] = + d ll / d W, loss += loss_scale * sum ll for S weight vectors W [S][F] over N rows (Bernoulli, C == 1)
-static int launch_linear_flash(const float* X, const float* y, int64_t N, int F, int S, const float* W, float* dW, float loss_scale,
-                               double* loss, const LinearFlashBuffers& b, cudaStream_t stream) {
+// A prepared X: [64 floats: [0] = max |X|] [Xh: N * F fp16] [Xl: N * F fp16]  (brn_linear_prepare_x)
+constexpr size_t LF_PX_HEADER = 256;
+static size_t linear_prepared_x_bytes(int64_t N, int F) {
+    if (N < 1 || N >= (int64_t)1 << 31 || F % 16 != 0 || F > LF_FMAX || F < 16) return 0;
+    return LF_PX_HEADER + 2 * ((size_t)N * F * 2 + 255) / 256 * 256;
+}
+static __half* prepared_x_hi(const void* px) { return reinterpret_cast<__half*>(const_cast<char*>(static_cast<const char*>(px)) + LF_PX_HEADER); }
+static __half* prepared_x_lo(const void* px, int64_t N, int F) {
+    return reinterpret_cast<__half*>(const_cast<char*>(static_cast<const char*>(px)) + LF_PX_HEADER + ((size_t)N * F * 2 + 255) / 256 * 256);
+}
+// max |X| and the scaled fp16 (hi, lo) pair of X: one read for the bound, one read + one write of X's own size for the pair
+static int launch_prepare_x(const float* X, int64_t N, int F, float* bound, __half* hi, __half* lo, cudaStream_t stream) {
+    BRN_CUDA_OK(cudaMemsetAsync(bound, 0, sizeof(float), stream));
+    lf_absmax_kernel<<<(unsigned)std::min<int64_t>((N * F / 4 + 255) / 256 + 1, 1184), 256, 0, stream>>>(X, N * F, bound);
+    BRN_LAUNCH_OK("lf_absmax_kernel");
+    linear_flash_split_kernel<<<(unsigned)std::min<int64_t>((N * F / 8 + 255) / 256 + 1, 2368), 256, 0, stream>>>(X, N * F, bound, hi, lo);
+    BRN_LAUNCH_OK("linear_flash_split_kernel");
+    return 0;
+}
+
+// dW [S][F] = + d ll / d W, loss += loss_scale * sum ll for S weight vectors W [S][F] over N rows (Bernoulli, C == 1).
+// px: a prepared X (the caller keeps it while X does not change: a training loop over fixed data then reads X once per
+// evaluation, as fp16 pairs, instead of three times), or NULL: X is split into the workspace on every call.
+static int launch_linear_flash(const float* X, const void* px, const float* y, int64_t N, int F, int S, const float* W, float* dW,
+                               float loss_scale, double* loss, const LinearFlashBuffers& b, cudaStream_t stream) {
     BRN_CUDA_OK(cudaMemsetAsync(b.scal, 0, 64 * sizeof(float), stream));
     lf_absmax_kernel<<<(unsigned)std::min<int64_t>(((int64_t)S * F / 4 + 255) / 256 + 1, 148), 256, 0, stream>>>(W, (int64_t)S * F, b.scal);
-    BRN_LAUNCH_OK("lf_absmax_kernel");
-    lf_absmax_kernel<<<(unsigned)std::min<int64_t>((N * F / 4 + 255) / 256 + 1, 1184), 256, 0, stream>>>(X, N * F, b.scal + 1);
     BRN_LAUNCH_OK("lf_absmax_kernel");
     linear_flash_split_kernel<<<(unsigned)std::min<int64_t>(((int64_t)S * F / 8 + 255) / 256 + 1, 1184), 256, 0, stream>>>(
         W, (int64_t)S * F, b.scal, b.Wh, b.Wl);
     BRN_LAUNCH_OK("linear_flash_split_kernel");
-    linear_flash_split_kernel<<<(unsigned)std::min<int64_t>((N * F / 8 + 255) / 256 + 1, 2368), 256, 0, stream>>>(X, N * F, b.scal + 1,
-                                                                                                                   b.Xh, b.Xl);
-    BRN_LAUNCH_OK("linear_flash_split_kernel");
+    const __half *Xh = b.Xh, *Xl = b.Xl;
+    const float* scal_x = b.scal + 1;
+    if (px) {
+        Xh = prepared_x_hi(px); Xl = prepared_x_lo(px, N, F); scal_x = static_cast<const float*>(px);
+    } else if (int e = launch_prepare_x(X, N, F, b.scal + 1, b.Xh, b.Xl, stream)) {
+        return e;
+    }
     CUtensorMap tWh, tWl, tXh, tXl;
     if (int e = make_tmap_2d_f16(&tWh, b.Wh, S, F, F, LF_MT, 64)) return e;
     if (int e = make_tmap_2d_f16(&tWl, b.Wl, S, F, F, LF_MT, 64)) return e;
-    if (int e = make_tmap_2d_f16(&tXh, b.Xh, N, F, F, LF_ROWS, 64)) return e;
-    if (int e = make_tmap_2d_f16(&tXl, b.Xl, N, F, F, LF_ROWS, 64)) return e;
+    if (int e = make_tmap_2d_f16(&tXh, Xh, N, F, F, LF_ROWS, 64)) return e;
+    if (int e = make_tmap_2d_f16(&tXl, Xl, N, F, F, LF_ROWS, 64)) return e;
     LinearFlashParams p;
-    p.y = y; p.N = N; p.F = F; p.S = S; p.scal = b.scal; p.part = b.part; p.part_stride = (int64_t)S * F;
+    p.y = y; p.N = N; p.F = F; p.S = S; p.scal_w = b.scal; p.scal_x = scal_x; p.part = b.part; p.part_stride = (int64_t)S * F;
     p.loss = loss; p.loss_scale = loss_scale; p.groups = b.groups;
     dim3 grid(b.tiles, b.groups);
     if (F == 128) {

@@ -256,15 +256,18 @@ class LinearPlan(Plan):
         super().__init__(joint, posterior)
         self.k, self.x_var, self.likelihood, self.C = k, x_var, likelihood, C
         self.latents = [w_spec]
+        self._prepared_x = None      # fp16-pair form of a fixed observed matrix, rebuilt when the matrix changes
 
     def _launch(self, cu, mvars, r, empirical, loss=None):
         X = _data_matrix(empirical[self.x_var], "x")
+        if self._prepared_x is None:
+            self._prepared_x = cu.PreparedX()
         yv = empirical[self.k].reshape(-1)
         if self.likelihood == cu.BERNOULLI:
             y = yv.to(torch.float32).contiguous()
         else:
             y = yv.to(torch.int32).contiguous()
-        return cu.linear_elbo_fwd_bwd(X, y, self.likelihood, mvars[0], self.C, r, loss=loss)
+        return cu.linear_elbo_fwd_bwd(X, y, self.likelihood, mvars[0], self.C, r, loss=loss, prepared=self._prepared_x)
 
 
 class BNNPlan(Plan):

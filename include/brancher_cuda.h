@@ -137,6 +137,21 @@ int brn_linear_elbo_fwd_bwd(const float* X, const void* y, int likelihood, int64
                             void* workspace, size_t workspace_bytes, int with_prior,
                             double* loss, void* stream);
 
+/* K2 with a PREPARED data matrix.  The one-pass tcgen05 kernel (Bernoulli, C == 1, F a multiple of 16, F <= 128) reads X as a
+ * power-of-two-scaled fp16 (hi, lo) pair.  brn_linear_elbo_fwd_bwd builds that pair on every call (one extra read of X for
+ * the bound, one read + one write for the pair); an inference loop over a FIXED observed matrix -- the reference's
+ * perform_inference over model.observe(data), brancher/inference.py:95-108 -- prepares it once and passes it to every
+ * evaluation.  The caller owns `px` and must prepare it again whenever the contents of X change.
+ *   brn_linear_prepared_x_bytes: size of the prepared form, 0 when it does not exist for this shape
+ *   brn_linear_elbo_fwd_bwd_px:  px == NULL behaves exactly like brn_linear_elbo_fwd_bwd; a prepared X is ignored (X is
+ *                                used) whenever the call does not take the one-pass kernel */
+size_t brn_linear_prepared_x_bytes(int64_t N, int F);
+int brn_linear_prepare_x(const float* X, int64_t N, int F, void* px, size_t px_bytes, void* stream);
+int brn_linear_elbo_fwd_bwd_px(const float* X, const void* px, const void* y, int likelihood, int64_t N, int F, int C,
+                               const brn_mf_var* w, const brn_sample_range* r,
+                               void* workspace, size_t workspace_bytes, int with_prior,
+                               double* loss, void* stream);
+
 /* K1 -- generic scalar-DAG ELBO: fused reparameterised sampling + log-probs + reduction over samples and data rows +
  * backward, for models whose variables are scalars (README.md:22-75 AR(1); examples/logNormal_normal.py;
  * examples/multivariate_regression.py).  The host flattens (joint, posterior) into a straight-line SSA program;

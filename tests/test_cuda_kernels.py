@@ -247,6 +247,50 @@ def test_linear_flash_variant(cu, monkeypatch, N, F, S, tied):
     check_against_oracle(loss, grads, o32, o64, "linear flash N=%d F=%d S=%d" % (N, F, S))
 
 
+def test_linear_prepared_x(cu, monkeypatch):
+    """brn_linear_prepare_x + brn_linear_elbo_fwd_bwd_px: the prepared fp16-pair form of a fixed data matrix gives the same
+    numbers as the per-call path, is rebuilt after an in-place write to X (version counter) and for another tensor, and is
+    ignored where the one-pass kernel does not apply (categorical likelihood, F not a multiple of 16)."""
+    from oracle import elbo_oracle as O
+    monkeypatch.setenv("BRN_LINEAR_VARIANT", "tcgen05")
+    rng = np.random.RandomState(11)
+    N, F, S = 3000, 64, 40
+    X = rng.randn(N, F).astype("f4")
+    y = rng.randint(0, 2, size=N)
+    params = {"weights": ((0.3 * rng.randn(1, F)).astype("f4"), (rng.randn(1, F) - 1).astype("f4"))}
+    eps = {"weights": rng.randn(S, 1, F).astype("f4")}
+    prior = {"weights": (0.0, 0.5)}
+    Xd, yd = dev(X), dev(y.astype("f4"))
+    prep = cu.PreparedX()
+
+    def run(Xt):
+        (w,) = make_vars(cu, params, eps, ["weights"], prior)
+        loss = cu.linear_elbo_fwd_bwd(Xt, yd, cu.BERNOULLI, w, 1, cu.sample_range(S), prepared=prep).item()
+        return loss, grads_of([w], ["weights"], params)
+
+    for scale in (1.0, 1.0, 3.0):          # second pass reuses the prepared form; third follows an in-place change of X
+        if scale != 1.0:
+            Xd.mul_(scale)
+        buf_before = prep.buf.data_ptr() if prep.buf is not None else None
+        ver_before = prep.version
+        loss, grads = run(Xd)
+        assert cu.last_variant() == "tcgen05-flash"
+        Xs = (X * np.float32(scale)).astype("f4")
+        o32 = O.logreg_elbo(Xs, y, params, eps, prior)
+        o64 = O.logreg_elbo(Xs, y, params, eps, prior, dtype=torch.float64)
+        check_against_oracle(loss, grads, o32, o64, "prepared X (scale %g)" % scale)
+        if scale == 1.0 and buf_before is not None:
+            assert prep.version == ver_before and prep.buf.data_ptr() == buf_before      # reused, not rebuilt
+    X2 = rng.randn(N, F).astype("f4")                                                    # another tensor: rebuilt
+    loss, grads = run(dev(X2))
+    check_against_oracle(loss, grads, O.logreg_elbo(X2, y, params, eps, prior),
+                         O.logreg_elbo(X2, y, params, eps, prior, dtype=torch.float64), "prepared X (new tensor)")
+    assert prep.get(dev(rng.randn(50, 20).astype("f4")), cu.BERNOULLI, 1) is None        # F % 16 != 0: no prepared form
+    assert prep.get(Xd, cu.CATEGORICAL, 3) is None
+    with pytest.raises(cu.BrancherCudaError):
+        cu._check(cu.lib().brn_linear_prepare_x(Xd.data_ptr(), N, F, prep.buf.data_ptr(), 16, None), "brn_linear_prepare_x")
+
+
 @pytest.mark.parametrize("N,F,S,slabs", [(1000, 16, 9, 3), (20000, 128, 96, 4), (700, 8, 5, 50)])
 def test_linear_host_fed_pipeline(cu, N, F, S, slabs):
     """linear_elbo_fwd_bwd_host: pinned host rows copied slab by slab on a side stream while the previous slab is being
