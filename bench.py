@@ -536,7 +536,8 @@ def main_ours(args):
         h2d = Xpin.numel() * 4 + ypin.numel() * 4
         units_per_rank = n_local * Bv
         algo_flops = {"particles.loglik_grad": 4.0 * n_local * Bv * F, "svgd.update": 2.0 * n_local * n_total * (F + 1),
-                      "svgd.pairwise_d2": 3.0 * n_total * n_total * F}
+                      # the distance matrix is sharded by rows (replicated only under BRN_BENCH_SVGD_REPLICATED)
+                      "svgd.pairwise_d2": 3.0 * (n_total if os.environ.get("BRN_BENCH_SVGD_REPLICATED") else n_local) * n_total * F}
         mvars = []
         gflat = torch.zeros(4, device=dev)
         theta_all = torch.empty((n_total, F), device=dev)
@@ -547,13 +548,17 @@ def main_ours(args):
         def device_step(it, Xd=X, yd=y):
             loss, G = cu.linear_particles_loss_grad(Xd, yd, cu.BERNOULLI, theta_local, 1, pl, ps)
             svgd_out[1] = cu.last_variant()
-            if world > 1:
-                dist.all_gather_into_tensor(theta_all, theta_local)
-                dist.all_gather_into_tensor(G_all, G)
-                th, gg = theta_all, G_all
+            if world > 1 and not os.environ.get("BRN_BENCH_SVGD_REPLICATED"):
+                # all-gather of (theta, G), then the median selection sharded by rows: 5 small NCCL collectives
+                svgd_out[0], _ = distributed.svgd_direction_sharded(theta_local, G)
             else:
-                th, gg = theta_local, G
-            svgd_out[0], _ = cu.svgd_direction(th, gg, row0=rank * n_local, rows=n_local)
+                if world > 1:
+                    dist.all_gather_into_tensor(theta_all, theta_local)
+                    dist.all_gather_into_tensor(G_all, G)
+                    th, gg = theta_all, G_all
+                else:
+                    th, gg = theta_local, G
+                svgd_out[0], _ = cu.svgd_direction(th, gg, row0=rank * n_local, rows=n_local)
             svgd_out[1] += " (K4a) + %s (K4b)" % cu.last_variant()
             return loss
     else:

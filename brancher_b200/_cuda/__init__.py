@@ -116,6 +116,10 @@ SYMBOLS = {
                                                   ctypes.c_int, ctypes.c_int, ctypes.POINTER(MFVar),
                                                   ctypes.POINTER(SampleRange), ctypes.c_void_p, ctypes.c_size_t,
                                                   ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "brn_svgd_sharded_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "brn_svgd_sharded_offsets": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int] + [ctypes.POINTER(ctypes.c_size_t)] * 4),
+    "brn_svgd_sharded_phase": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 5 +
+                               [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "brn_dag_elbo_fwd_bwd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                             ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                             ctypes.POINTER(SampleRange), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
@@ -513,6 +517,53 @@ def svgd_direction(theta, grad, row0=0, rows=None, bandwidth=None):
     _check(lib().brn_svgd_direction(_ptr(theta, what="theta"), _ptr(grad, what="grad"), n, d, row0, rows, int(update),
                                     _ptr(bw), _ptr(out), ws.data_ptr(), ws.numel(), _stream(dev)), "brn_svgd_direction")
     return out, bw
+
+
+class ShardedSvgd:
+    """K4b for ONE rank's particle rows [row0, row0 + rows) of n (brn_svgd_sharded_phase).  The rank keeps only its rows of
+    the distance matrix; between the phases the caller adds `hist` (phases 0-2), then `cnt_le` (SUM) and `next` (MIN) over the
+    ranks -- svgd_direction_sharded does that with torch.distributed; the tests drive several instances on one device."""
+
+    def __init__(self, theta, grad, row0, rows, workspace=None):
+        n, d = theta.shape
+        self.theta, self.grad, self.n, self.d, self.row0, self.rows = theta, grad, n, d, int(row0), int(rows)
+        dev = theta.device
+        nbytes = lib().brn_svgd_sharded_workspace_bytes(n, d, self.rows)
+        if nbytes == 0:
+            raise BrancherCudaError("ShardedSvgd: bad shape n=%d d=%d rows=%d" % (n, d, rows))
+        self.ws = _workspace(dev, nbytes) if workspace is None else workspace
+        offs = [ctypes.c_size_t() for _ in range(4)]
+        _check(lib().brn_svgd_sharded_offsets(n, d, self.rows, *[ctypes.byref(o) for o in offs]), "brn_svgd_sharded_offsets")
+        h0, hb, c0, x0 = [o.value for o in offs]
+        self.hist = self.ws[h0:h0 + hb].view(torch.int32)           # counts < n^2 / 2 < 2^31
+        self.cnt_le = self.ws[c0:c0 + 8].view(torch.int64)
+        self.next = self.ws[x0:x0 + 4].view(torch.int32)            # bit pattern of a non-negative float: orders like the float
+        self.bw = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.out = torch.empty((self.rows, d), dtype=torch.float32, device=dev)
+
+    def phase(self, k):
+        _check(lib().brn_svgd_sharded_phase(_ptr(self.theta, what="theta"), _ptr(self.grad, what="grad"), self.n, self.d, self.row0,
+                                            self.rows, int(k), _ptr(self.bw), _ptr(self.out), self.ws.data_ptr(), self.ws.numel(),
+                                            _stream(self.theta.device)), "brn_svgd_sharded_phase")
+
+
+def svgd_direction_sharded(theta, grad, row0, rows, group=None):
+    """K4b with the median selection sharded over the ranks of `group`: theta, grad [n, d] = ALL particles (all-gathered),
+    this rank updates rows [row0, row0 + rows).  Five small collectives (3 x 16 KB histogram, 8 + 4 bytes) replace the
+    replicated n^2 selection.  Returns (out [rows, d], bandwidth [1]) -- the same numbers as svgd_direction(...)."""
+    import torch.distributed as dist
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    sh = ShardedSvgd(theta, grad, row0, rows)
+    for k in range(3):
+        sh.phase(k)
+        if multi:
+            dist.all_reduce(sh.hist, group=group)
+    sh.phase(3)
+    if multi:
+        dist.all_reduce(sh.cnt_le, group=group)
+        dist.all_reduce(sh.next, op=dist.ReduceOp.MIN, group=group)
+    sh.phase(4)
+    return sh.out, sh.bw
 
 
 def linear_vectors_loglik_grad(X, y, likelihood, V, C, want_grad=True):

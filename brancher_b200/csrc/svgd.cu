@@ -12,6 +12,7 @@
 // patterns: three histogram passes (12 + 12 + 8 bits) pin the k-th smallest value, one more pass finds its successor.
 #include "umma_gemm.cuh"
 #include <stdlib.h>
+#include <cstddef>
 
 namespace brn {
 
@@ -70,9 +71,11 @@ struct SelectState {
     uint32_t next;               // pass 4: min{v > selected} (bit pattern)
 };
 
-// histogram of bits [shift, shift+nbits) over upper-triangle elements whose higher bits equal state->prefix
-__global__ void __launch_bounds__(256) svgd_select_hist_kernel(const float* __restrict__ D2, int n, int shift, int nbits,
-                                                               int first, const SelectState* __restrict__ st,
+// histogram of bits [shift, shift+nbits) over the upper-triangle elements (j > i) of rows [row0, row0 + rows) whose higher bits
+// equal state->prefix.  D2 points at row `row0` (row pitch n): the whole matrix (row0 = 0, rows = n) or one rank's row shard,
+// whose partial histograms add up to the full one because every row belongs to exactly one rank.
+__global__ void __launch_bounds__(256) svgd_select_hist_kernel(const float* __restrict__ D2, int n, int row0, int rows, int shift,
+                                                               int nbits, int first, const SelectState* __restrict__ st,
                                                                unsigned int* __restrict__ hist) {
     extern __shared__ unsigned int sh[];
     const int nb = 1 << nbits;
@@ -82,12 +85,13 @@ __global__ void __launch_bounds__(256) svgd_select_hist_kernel(const float* __re
     const int hshift = shift + nbits;
     // rows are dealt round-robin to the CTAs; a row's upper-triangle part (j > i) is read coalesced -- the lower triangle is
     // never touched and no index division is needed
-    // (rows q and n-2-q are handled together: their upper-triangle lengths add up to n-1, which balances the CTAs)
-    for (int q2 = 2 * blockIdx.x; q2 < n - 1; q2 += 2 * gridDim.x)
+    // (local rows q and rows-1-q are handled together: their upper-triangle lengths add up to a constant, which balances the CTAs)
+    for (int q = blockIdx.x; 2 * q < rows; q += gridDim.x)
     for (int h = 0; h < 2; ++h) {
-        const int i = h == 0 ? q2 / 2 : n - 2 - q2 / 2;
-        if (h == 1 && i <= q2 / 2) continue;
-        const float* row = D2 + (int64_t)i * n;
+        const int li = h == 0 ? q : rows - 1 - q;
+        if (h == 1 && li <= q) continue;
+        const int i = row0 + li;
+        const float* row = D2 + (int64_t)li * n;
         for (int jb = i + 1; jb < n; jb += blockDim.x) {      // warp-uniform trip count: the ballot below needs all lanes
             const int j = jb + threadIdx.x;
             bool take = false;
@@ -180,16 +184,17 @@ __global__ void __launch_bounds__(SCAN_THREADS) svgd_select_scan_kernel(int shif
     for (int b = t; b < nb; b += SCAN_THREADS) hist[b] = 0u;
 }
 
-// pass 4: count of values <= selected and the smallest value above it
-__global__ void __launch_bounds__(256) svgd_select_succ_kernel(const float* __restrict__ D2, int n, SelectState* st) {
+// pass 4: count of values <= selected and the smallest value above it (same row range convention as the histogram)
+__global__ void __launch_bounds__(256) svgd_select_succ_kernel(const float* __restrict__ D2, int n, int row0, int rows, SelectState* st) {
     const uint32_t sel = st->prefix;
     unsigned long long cnt = 0ull;
     uint32_t nxt = 0x7f800000u;
-    for (int q2 = 2 * blockIdx.x; q2 < n - 1; q2 += 2 * gridDim.x)
+    for (int q = blockIdx.x; 2 * q < rows; q += gridDim.x)
     for (int h = 0; h < 2; ++h) {
-        const int i = h == 0 ? q2 / 2 : n - 2 - q2 / 2;
-        if (h == 1 && i <= q2 / 2) continue;
-        const float* row = D2 + (int64_t)i * n;
+        const int li = h == 0 ? q : rows - 1 - q;
+        if (h == 1 && li <= q) continue;
+        const int i = row0 + li;
+        const float* row = D2 + (int64_t)li * n;
         for (int j = i + 1 + threadIdx.x; j < n; j += blockDim.x) {
             const uint32_t v = __float_as_uint(row[j]);
             if (v <= sel) ++cnt;
@@ -417,15 +422,20 @@ struct SvgdWorkspace {
     float *th_hi, *th_lo, *sq, *vt_hi, *vt_lo;
     int64_t ldd, ldn;
     size_t bytes;
-    SvgdWorkspace(void* base, int n, int d) {
+    size_t hist_off, st_off;
+    // d2_rows: rows of D2 kept (n for the replicated evaluation, the rank's shard for the sharded one)
+    SvgdWorkspace(void* base, int n, int d, int d2_rows = -1) {
+        if (d2_rows < 0) d2_rows = n;
         size_t off = 0;
         auto take = [&](size_t nbytes) {
             char* p = base ? reinterpret_cast<char*>(base) + off : nullptr;
             off += (nbytes + 255) / 256 * 256;
             return p;
         };
-        D2 = reinterpret_cast<float*>(take(sizeof(float) * (size_t)n * n));
+        D2 = reinterpret_cast<float*>(take(sizeof(float) * (size_t)(d2_rows > 0 ? d2_rows : 1) * n));
+        hist_off = off;
         hist = reinterpret_cast<unsigned int*>(take(sizeof(unsigned int) * 4096));
+        st_off = off;
         st = reinterpret_cast<SelectState*>(take(sizeof(SelectState)));
         // tensor-core variant: theta (hi, lo) [n][ldd], |theta|^2 [n], V^T (hi, lo) [d + 1][ldn]
         ldd = (d + 3) / 4 * 4;
@@ -497,13 +507,13 @@ extern "C" int brn_svgd_direction(const float* theta, const float* grad, int n, 
         const int hgrid = (int)hblocks;
         const int shifts[3] = {20, 8, 0}, nbits[3] = {12, 12, 8};
         for (int lv = 0; lv < 3; ++lv) {
-            svgd_select_hist_kernel<<<hgrid, 256, sizeof(unsigned int) << nbits[lv], stream>>>(ws.D2, n, shifts[lv], nbits[lv],
+            svgd_select_hist_kernel<<<hgrid, 256, sizeof(unsigned int) << nbits[lv], stream>>>(ws.D2, n, 0, n, shifts[lv], nbits[lv],
                                                                                              lv == 0, ws.st, ws.hist);
             BRN_LAUNCH_OK("svgd_select_hist_kernel");
             svgd_select_scan_kernel<<<1, SCAN_THREADS, 0, stream>>>(shifts[lv], nbits[lv], lv == 0, k1, ws.st, ws.hist);
             BRN_LAUNCH_OK("svgd_select_scan_kernel");
         }
-        svgd_select_succ_kernel<<<hgrid, 256, 0, stream>>>(ws.D2, n, ws.st);
+        svgd_select_succ_kernel<<<hgrid, 256, 0, stream>>>(ws.D2, n, 0, n, ws.st);
         BRN_LAUNCH_OK("svgd_select_succ_kernel");
         svgd_bandwidth_kernel<<<1, 32, 0, stream>>>(ws.st, k2, n, bandwidth);
         BRN_LAUNCH_OK("svgd_bandwidth_kernel");
@@ -534,6 +544,107 @@ extern "C" int brn_svgd_direction(const float* theta, const float* grad, int n, 
         dim3 grid(row_tiles, d_chunks, splits);
         svgd_update_kernel<<<grid, 128, 0, stream>>>(theta, grad, ws.D2, n, d, row0, rows, bandwidth, out, j_per_split);
         BRN_LAUNCH_OK("svgd_update_kernel");
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K4b sharded over ranks (particles = rows): a rank keeps only ITS rows of D2 ([rows][n]), histograms its rows' part of the
+// upper triangle, and the ranks add their histograms between the select passes -- the one real exchange step of the path.
+// The collectives are the caller's (torch.distributed / NCCL on the buffers named by brn_svgd_sharded_offsets); this entry
+// runs the device work between them:
+//   phase 0: D2 rows, level-0 histogram                          -> all-reduce(SUM) hist
+//   phase 1: scan level 0, level-1 histogram                     -> all-reduce(SUM) hist
+//   phase 2: scan level 1, level-2 histogram                     -> all-reduce(SUM) hist
+//   phase 3: scan level 2, successor pass (partial cnt_le, next) -> all-reduce(SUM) cnt_le, all-reduce(MIN) next
+//   phase 4: bandwidth, update of the local rows
+// Every rank ends with the bandwidth of the replicated evaluation bit for bit (integer histograms, identical scans).
+extern "C" size_t brn_svgd_sharded_workspace_bytes(int n, int d, int rows) {
+    if (n <= 0 || d <= 0 || rows < 0 || rows > n) return 0;
+    return SvgdWorkspace(nullptr, n, d, rows).bytes;
+}
+
+extern "C" int brn_svgd_sharded_offsets(int n, int d, int rows, size_t* hist_off, size_t* hist_bytes, size_t* cnt_le_off,
+                                        size_t* next_off) {
+    BRN_CHECK_ARG(n > 0 && d > 0 && rows >= 0 && rows <= n && hist_off && hist_bytes && cnt_le_off && next_off,
+                  "brn_svgd_sharded_offsets: bad arguments");
+    SvgdWorkspace ws(nullptr, n, d, rows);
+    *hist_off = ws.hist_off;
+    *hist_bytes = sizeof(unsigned int) * 4096;
+    *cnt_le_off = ws.st_off + offsetof(SelectState, cnt_le);
+    *next_off = ws.st_off + offsetof(SelectState, next);
+    return 0;
+}
+
+extern "C" int brn_svgd_sharded_phase(const float* theta, const float* grad, int n, int d, int row0, int rows, int phase,
+                                      float* bandwidth, float* out, void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    BRN_CHECK_ARG(theta && grad && bandwidth && (out || rows == 0), "brn_svgd_sharded_phase: NULL pointer");
+    BRN_CHECK_ARG(n >= 2 && d > 0, "brn_svgd_sharded_phase: need n >= 2 particles and d > 0 (got n=%d d=%d)", n, d);
+    BRN_CHECK_ARG(row0 >= 0 && rows >= 0 && row0 + rows <= n, "brn_svgd_sharded_phase: bad row range [%d, %d) of %d", row0, row0 + rows, n);
+    BRN_CHECK_ARG(phase >= 0 && phase <= 4, "brn_svgd_sharded_phase: phase %d (0..4)", phase);
+    BRN_CHECK_ARG(n % 4 == 0 && d + 1 <= SVGD_TC_BN && d >= 8,
+                  "brn_svgd_sharded_phase: the sharded evaluation runs on the tensor-core kernels (n %% 4 == 0, 8 <= d < %d; got n=%d d=%d)",
+                  SVGD_TC_BN, n, d);
+    SvgdWorkspace ws(workspace, n, d, rows);
+    BRN_CHECK_ARG(workspace && workspace_bytes >= ws.bytes, "workspace too small: %zu < %zu", workspace_bytes, ws.bytes);
+    set_variant("tcgen05");
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned long long m = (unsigned long long)n * (unsigned long long)(n - 1) / 2ull;
+    const unsigned long long k1 = (m - 1ull) / 2ull, k2 = m / 2ull;
+    int64_t hblocks = ((int64_t)rows * n + 255) / 256;
+    if (hblocks > (int64_t)sms * 8) hblocks = (int64_t)sms * 8;
+    if (hblocks < 1) hblocks = 1;
+    const int hgrid = (int)hblocks;
+    const int shifts[3] = {20, 8, 0}, nbits[3] = {12, 12, 8};
+    if (phase == 0) {
+        StageTimer st("svgd.pairwise_d2", stream);
+        svgd_prep_theta_kernel<<<(n + 3) / 4, 128, 0, stream>>>(theta, n, d, ws.ldd, ws.th_hi, ws.th_lo, ws.sq);
+        BRN_LAUNCH_OK("svgd_prep_theta_kernel");
+        if (rows > 0) {
+            EpiD2::Params ep{ws.sq, ws.D2, rows, n, row0};
+            if (int e = launch_umma_nt<208, 16, EpiD2>(ws.th_hi + (size_t)row0 * ws.ldd, ws.th_lo + (size_t)row0 * ws.ldd, rows, ws.ldd,
+                                                      ws.th_hi, ws.th_lo, n, ws.ldd, d, 0, 2, ep, stream))
+                return e;
+        }
+        BRN_CUDA_OK(cudaMemsetAsync(ws.hist, 0, sizeof(unsigned int) * 4096, stream));
+    }
+    if (phase <= 3) {
+        StageTimer st("svgd.median_bandwidth", stream);
+        if (phase >= 1) {
+            const int lv = phase - 1;
+            svgd_select_scan_kernel<<<1, SCAN_THREADS, 0, stream>>>(shifts[lv], nbits[lv], lv == 0, k1, ws.st, ws.hist);
+            BRN_LAUNCH_OK("svgd_select_scan_kernel");
+        }
+        if (phase <= 2) {
+            if (rows > 0) {
+                svgd_select_hist_kernel<<<hgrid, 256, sizeof(unsigned int) << nbits[phase], stream>>>(ws.D2, n, row0, rows, shifts[phase],
+                                                                                                   nbits[phase], phase == 0, ws.st, ws.hist);
+                BRN_LAUNCH_OK("svgd_select_hist_kernel");
+            }
+        } else if (rows > 0) {
+            svgd_select_succ_kernel<<<hgrid, 256, 0, stream>>>(ws.D2, n, row0, rows, ws.st);
+            BRN_LAUNCH_OK("svgd_select_succ_kernel");
+        }
+        return 0;
+    }
+    {
+        StageTimer st("svgd.median_bandwidth", stream);
+        svgd_bandwidth_kernel<<<1, 32, 0, stream>>>(ws.st, k2, n, bandwidth);
+        BRN_LAUNCH_OK("svgd_bandwidth_kernel");
+    }
+    if (rows > 0) {
+        StageTimer st("svgd.update", stream);
+        dim3 grid((n + 31) / 32, (d + 1 + 31) / 32);
+        svgd_prep_v_kernel<<<grid, 256, 0, stream>>>(theta, grad, n, d, bandwidth, ws.vt_hi, ws.vt_lo, ws.ldn);
+        BRN_LAUNCH_OK("svgd_prep_v_kernel");
+        BRN_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)rows * d, stream));
+        EpiSvgdOut::Params ep{out, theta, bandwidth, rows, d, row0};
+        if (int e = launch_umma_nt<SVGD_TC_BN, 16, EpiSvgdOut, 4, 1, 4>(ws.D2, nullptr, rows, n, ws.vt_hi, ws.vt_lo, d + 1, ws.ldn, n, 0, 2,
+                                                                        ep, stream, true))
+            return e;
     }
     return 0;
 }

@@ -118,3 +118,20 @@ def all_reduce_flat(flat, loss=None):
     if loss is not None:
         loss.copy_((flat[-4].to(torch.float64) + flat[-3].to(torch.float64)).reshape(loss.shape))
     return flat
+
+
+def svgd_direction_sharded(theta_local, grad_local, group=None):
+    """K4b for particles sharded over the ranks (equal shards): all-gather of (theta, grad), then the exact-median selection
+    sharded by rows -- each rank histograms its own rows of the pairwise distances and the histograms are added
+    (_cuda.svgd_direction_sharded).  Returns (update of the LOCAL particles [n_local, d], bandwidth [1], identical on all ranks).
+    Replaces SteinVariationalGradientDescent.correct_gradient (brancher/inference.py:301-324) for an ensemble spread over GPUs."""
+    from brancher_b200 import _cuda as cu
+    w, r = world_size(), rank()
+    n_local, d = theta_local.shape
+    if w == 1:
+        return cu.svgd_direction(theta_local, grad_local)
+    theta_all = torch.empty((w * n_local, d), dtype=theta_local.dtype, device=theta_local.device)
+    grad_all = torch.empty_like(theta_all)
+    dist.all_gather_into_tensor(theta_all, theta_local.contiguous(), group=group)
+    dist.all_gather_into_tensor(grad_all, grad_local.contiguous(), group=group)
+    return cu.svgd_direction_sharded(theta_all, grad_all, r * n_local, n_local, group=group)

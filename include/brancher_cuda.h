@@ -227,6 +227,22 @@ size_t brn_svgd_workspace_bytes(int n, int d);
 int brn_svgd_direction(const float* theta, const float* grad, int n, int d, int row0, int rows, int update_bandwidth,
                        float* bandwidth, float* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* K4b sharded over ranks (one rank = a contiguous block of particle rows): the rank keeps only its rows of the distance
+ * matrix, histograms its rows' part of the upper triangle, and the ranks ADD their histograms between the passes of the
+ * exact median selection -- the one real exchange step of this path (brancher/inference.py:317-324 computes the median over
+ * all pairs).  The collectives belong to the caller (NCCL through torch.distributed in the product); this entry runs the
+ * device work between them, on the buffers whose byte offsets inside `workspace` brn_svgd_sharded_offsets reports:
+ *   phase 0: D2 rows + level-0 histogram                       -> caller: all-reduce SUM of hist (4096 x uint32)
+ *   phase 1, 2: scan of the previous level + next histogram    -> caller: all-reduce SUM of hist
+ *   phase 3: last scan + successor pass                        -> caller: all-reduce SUM of cnt_le (uint64), MIN of next (uint32
+ *                                                                 bit pattern of a non-negative float)
+ *   phase 4: bandwidth (identical on every rank, bit for bit the replicated one) + update of the local rows -> out [rows, d]
+ * theta, grad: ALL n particles (all-gathered by the caller).  Needs n % 4 == 0 and 8 <= d <= 143 (tensor-core kernels). */
+size_t brn_svgd_sharded_workspace_bytes(int n, int d, int rows);
+int brn_svgd_sharded_offsets(int n, int d, int rows, size_t* hist_off, size_t* hist_bytes, size_t* cnt_le_off, size_t* next_off);
+int brn_svgd_sharded_phase(const float* theta, const float* grad, int n, int d, int row0, int rows, int phase,
+                           float* bandwidth, float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* K5 -- amortised variational auto-encoder (examples/VAE_playground.py:30-80):
  *   encoder  h_0 = relu(W_0 x + b_0), ..., h_last ; mean = W_mean h_last + b_mean ; sd = softplus(W_sd h_last + b_sd) + sd_offset
  *   Qz = Normal(mean, sd) (amortised: its parameters are links, not roots), z = mean + sd*eps      (Normal.rsample)

@@ -148,3 +148,49 @@ def test_svgd_direction_tcgen05_variant(cu, monkeypatch, n, d, rows):
     assert cu.last_variant() == "tcgen05"
     assert abs(bw.item() - bw64) <= 2e-6 * bw64, (bw.item(), bw64)
     assert_close(out.cpu().numpy(), want[sel], "svgd tcgen05 n=%d d=%d" % (n, d), scale=np.abs(want).max())
+
+
+@pytest.mark.parametrize("n,d,shards", [(1024, 128, [(0, 1024)]), (2048, 64, [(0, 1024), (1024, 1024)]),
+                                        (1536, 100, [(0, 256), (256, 768), (1024, 512)]), (1024, 32, [(0, 1024), (1024, 0)])])
+def test_svgd_sharded_median_equals_replicated(cu, n, d, shards):
+    """K4b sharded over ranks (brn_svgd_sharded_phase): every rank histograms only ITS rows of the distance matrix and the
+    histograms are added between the select passes.  The ranks are played by several ShardedSvgd instances on one device
+    (the additions torch.distributed performs in the product are done here by hand): the bandwidth must equal the replicated
+    evaluation's BIT FOR BIT on every rank, and the concatenated row blocks must equal its update (and the oracle's)."""
+    from oracle import elbo_oracle as O
+    rng = np.random.RandomState(n + d)
+    theta = rng.randn(n, d).astype("f4")
+    theta[5] = theta[17]                                   # duplicate particles: zero distances, ties in the selection
+    grad = rng.randn(n, d).astype("f4")
+    th, gg = dev(theta), dev(grad)
+    full, bw_full = cu.svgd_direction(th, gg)
+    full, bw_full = full.clone(), bw_full.clone()
+    ranks = []
+    for row0, rows in shards:
+        nbytes = cu.lib().brn_svgd_sharded_workspace_bytes(n, d, rows)
+        ranks.append(cu.ShardedSvgd(th, gg, row0, rows, workspace=torch.empty(nbytes, dtype=torch.uint8, device=th.device)))
+    for k in range(3):
+        for r in ranks:
+            r.phase(k)
+        tot = sum(r.hist.clone() for r in ranks)
+        for r in ranks:
+            r.hist.copy_(tot)
+    for r in ranks:
+        r.phase(3)
+    cnt = sum(r.cnt_le.clone() for r in ranks)
+    nxt = torch.stack([r.next.clone() for r in ranks]).min(dim=0).values
+    for r in ranks:
+        r.cnt_le.copy_(cnt)
+        r.next.copy_(nxt)
+        r.phase(4)
+    for r in ranks:
+        assert r.bw.item() == bw_full.item(), (r.bw.item(), bw_full.item())
+    out = torch.cat([r.out for r in ranks if r.rows > 0]).cpu().numpy()
+    want, bw64 = O.svgd_direction(theta, grad)
+    assert abs(bw_full.item() - bw64) <= 2e-6 * bw64
+    assert_close(out, full.cpu().numpy(), "sharded vs replicated update", scale=np.abs(want).max())
+    assert_close(out, want, "sharded update vs oracle", scale=np.abs(want).max())
+    # the single-process driver (no process group: no collectives) is the one-rank case
+    o1, b1 = cu.svgd_direction_sharded(th, gg, 0, n)
+    assert b1.item() == bw_full.item()
+    assert_close(o1.cpu().numpy(), want, "svgd_direction_sharded (one rank)", scale=np.abs(want).max())
