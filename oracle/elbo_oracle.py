@@ -378,6 +378,43 @@ def svgd_direction(theta, grad, dtype=np.float64):
     return out.astype(dtype), float(bw)
 
 
+def svgd_median_radix_sharded(d2, shards, sum_over_ranks=None, min_over_ranks=None):
+    """The exact-median selection of update_bandwidth (inference.py:317-324: np.median over all pairwise distances) restated
+    the way the row-sharded K4b evaluates it (csrc/svgd.cu, brn_svgd_sharded_phase): the order statistic(s) of the fp32 bit
+    patterns of the n(n-1)/2 upper-triangle squared distances by three radix passes (bits 31..20, 19..8, 7..0) plus a
+    successor pass, where every rank only looks at ITS rows [row0, row0 + rows) and the 4096-bin histograms (then the
+    (count <= selected, smallest value above) pair) are combined over the ranks.
+
+    d2 [n, n] float32 squared distances; shards = this process's list of (row0, rows) blocks (all blocks of all ranks partition
+    the rows); sum_over_ranks / min_over_ranks combine an int64 array over the ranks (identity when None: single process
+    holding every shard).  Returns the median DISTANCE as np.float32 arithmetic does: (sqrt(v_k1) + sqrt(v_k2)) / 2."""
+    d2 = np.ascontiguousarray(d2, dtype=np.float32)
+    n = d2.shape[0]
+    bits = d2.view(np.uint32)
+    mine = np.concatenate([bits[i, i + 1:] for row0, rows in shards for i in range(row0, row0 + rows)] + [np.zeros(0, np.uint32)])
+    m = n * (n - 1) // 2
+    k1, k2 = (m - 1) // 2, m // 2
+    ident = lambda a: a
+    sum_over_ranks = sum_over_ranks or ident
+    min_over_ranks = min_over_ranks or ident
+    prefix, rank = np.uint32(0), k1
+    for shift, nbits in ((20, 12), (8, 12), (0, 8)):
+        hshift = shift + nbits
+        sel = mine if hshift >= 32 else mine[(mine >> np.uint32(hshift)) == (prefix >> np.uint32(hshift))]
+        hist = np.bincount(((sel >> np.uint32(shift)) & np.uint32((1 << nbits) - 1)).astype(np.int64), minlength=1 << nbits)
+        hist = sum_over_ranks(hist.astype(np.int64))
+        cum = np.cumsum(hist)
+        b = int(np.searchsorted(cum, rank, side="right"))
+        rank -= int(cum[b - 1]) if b > 0 else 0
+        prefix = np.uint32(prefix | np.uint32(b << shift))
+    cnt_le = sum_over_ranks(np.array([np.count_nonzero(mine <= prefix)], np.int64))[0]
+    above = mine[mine > prefix]
+    nxt = min_over_ranks(np.array([above.min() if above.size else 0x7f800000], np.int64))[0]
+    v1 = np.array([prefix], np.uint32).view(np.float32)[0]
+    v2 = v1 if cnt_le >= k2 + 1 else np.array([nxt], np.uint32).view(np.float32)[0]
+    return np.float32(0.5) * (np.sqrt(v1) + np.sqrt(v2))
+
+
 def svgd_direction_loops(theta, grad):
     """Literal O(n^2) loop transcription of the index pattern in inference.py:301-324 for tiny n,
     used only to pin `svgd_direction`'s vectorised algebra (fp64 numpy)."""

@@ -102,8 +102,23 @@ def _svgd_worker(rank, world, port, out):
     mine = torch.tensor(full[p0:p0 + cnt])                            # ... and its own rows of the update
     rows = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(rows, mine)
+    # the row-sharded median selection (brn_svgd_sharded_phase): this rank histograms only its rows, the histograms are added
+    # by all-reduce -- every rank must end with np.median of ALL pairwise distances
+    th32 = th_all.numpy().astype("f4")
+    d2 = ((th32[:, None] - th32[None]) ** 2).sum(-1).astype("f4")
+
+    def red(op):
+        def f(a):
+            t = torch.tensor(a)
+            dist.all_reduce(t, op=op)
+            return t.numpy()
+        return f
+    med = O.svgd_median_radix_sharded(d2, [(p0, cnt)], red(dist.ReduceOp.SUM), red(dist.ReduceOp.MIN))
+    meds = [None] * world
+    dist.all_gather_object(meds, float(med))
     if rank == 0:
-        torch.save({"update": torch.cat(rows), "bw": bw}, out)
+        torch.save({"update": torch.cat(rows), "bw": bw, "medians": meds,
+                    "median_want": float(np.median(np.sqrt(d2[np.triu_indices(n, 1)])))}, out)
     dist.destroy_process_group()
 
 
@@ -119,3 +134,4 @@ def test_two_rank_particle_sharding_matches_single_process(tmp_path):
     want, bw = O.svgd_direction(theta.reshape(n, -1), G.reshape(n, -1))
     assert abs(got["bw"] - bw) <= 1e-12 * abs(bw)
     np.testing.assert_allclose(got["update"].numpy(), want, rtol=1e-10, atol=1e-12)
+    assert got["medians"] == [got["median_want"]] * 2        # sharded radix selection == np.median, identical on both ranks
