@@ -727,6 +727,16 @@ def main_ours(args):
             g_strong.replay()
             return red_out[0]
 
+    if wl == "svgd" and world > 1 and cfg["n"] % (4 * world) == 0:
+        # strong scaling of C4: the SAME ensemble (n = 4096 particles in total) split over the ranks
+        n_s = cfg["n"] // world
+        theta_s = theta_local[:n_s].contiguous()
+
+        def strong_step(it):
+            loss, G = cu.linear_particles_loss_grad(X, y, cu.BERNOULLI, theta_s, 1, pl, ps)
+            distributed.svgd_direction_sharded(theta_s, G)
+            return loss
+
     clocks = ClockSampler(local_rank)
     clocks.start()
     # Headline pass: EXACTLY K steps, nothing but the product's own launches in the timed region.  The per-stage CUDA events of
@@ -799,9 +809,11 @@ def main_ours(args):
                }
         out["config"].update(extra_config)
         if ms_strong is not None:
-            out["strong"] = {"global_samples": cfg["S"], "samples_per_gpu": cfg["S"] // world, "ms_per_step": ms_strong / args.steps,
-                             "value": cfg["S"] * cfg["B"] * args.steps / (ms_strong * 1e-3), "unit": UNIT,
-                             "note": "same global problem as the 1-GPU run (S = 256): speed-up = 1-GPU ms_per_step / this"}
+            g_units = cfg["n"] if wl == "svgd" else cfg["S"]
+            out["strong"] = {"global_samples": g_units, "samples_per_gpu": g_units // world, "ms_per_step": ms_strong / args.steps,
+                             "value": g_units * cfg["B"] * args.steps / (ms_strong * 1e-3), "unit": UNIT,
+                             "note": "same global problem as the 1-GPU run (%s): speed-up = 1-GPU ms_per_step / this"
+                                     % ("n = %d particles" % g_units if wl == "svgd" else "S = %d" % g_units)}
         if world > 1:
             out["config"]["collective"] = ("one-shot all-reduce over NVLink peer memory (csrc/allreduce.cu), inside the captured "
                                            "step" if any(distributed._oneshot.values()) else "NCCL all_reduce")
