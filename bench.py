@@ -820,8 +820,13 @@ def main_ours(args):
                              "note": "same global problem as the 1-GPU run (%s): speed-up = 1-GPU ms_per_step / this"
                                      % ("n = %d particles" % g_units if wl == "svgd" else "S = %d" % g_units)}
         if world > 1:
-            out["config"]["collective"] = ("one-shot all-reduce over NVLink peer memory (csrc/allreduce.cu), inside the captured "
-                                           "step" if any(distributed._oneshot.values()) else "NCCL all_reduce")
+            if wl == "svgd":
+                out["config"]["collective"] = ("NCCL: all-gather of (theta, G), then the row-sharded exact median: 3 histogram all-reduces "
+                                               "(16 KB) + count / successor all-reduces" if not os.environ.get("BRN_BENCH_SVGD_REPLICATED")
+                                               else "NCCL all-gather of (theta, G); distance matrix and median replicated on every rank")
+            else:
+                out["config"]["collective"] = ("one-shot all-reduce over NVLink peer memory (csrc/allreduce.cu), inside the captured "
+                                               "step" if any(distributed._oneshot.values()) else "NCCL all_reduce")
         if world == 1 and wl == "bnn" and not args.no_api:
             out["api_e2e"] = api_e2e(dev)
         if world == 1 and not args.no_cpu_baseline:
