@@ -148,9 +148,17 @@ def _fused_loop(joint_model, posterior_model, number_iterations, number_samples,
         iteration()
     torch.cuda.current_stream(dev).wait_stream(side)
     if number_iterations > 1:
+        # capture_begin / capture_end directly: the torch.cuda.graph context manager runs gc.collect() and empties the caching
+        # allocator on entry -- tens of milliseconds of host time on a large Python heap, paid by every perform_inference call
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            iteration()
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            graph.capture_begin()
+            try:
+                iteration()
+            finally:
+                graph.capture_end()
+        torch.cuda.current_stream(dev).wait_stream(side)
         # the capture itself does not execute: (number_iterations - 1) replays follow the eager first iteration
         for _ in range(number_iterations - 1):
             graph.replay()
