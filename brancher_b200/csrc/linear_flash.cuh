@@ -124,7 +124,7 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
     const int st = blockIdx.x, g = blockIdx.y;                      // vector tile, row group
     const int F = p.F, FB = (F + 63) / 64;                          // 64-feature boxes
     const int64_t n_blocks = (p.N + LF_ROWS - 1) / LF_ROWS;
-    const int64_t my_blocks = g < n_blocks ? (n_blocks - g + p.groups - 1) / p.groups : 0;
+    const int my_blocks = g < n_blocks ? (int)((n_blocks - g + p.groups - 1) / p.groups) : 0;     // N < 2^31: fits an int
 
     if (threadIdx.x == 0) {
         umma::tma_prefetch_desc(&tmWh); umma::tma_prefetch_desc(&tmWl);
@@ -158,8 +158,8 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
                 umma::tma_load_2d(smem + SM::off_w + SM::W_BYTES / 2 + b * (LF_MT * 128), &tmWl, &w_full, b * 64, st * LF_MT);
             }
             int stage = 0; uint32_t phase = 0;
-            for (int64_t i = 0; i < my_blocks; ++i) {
-                const int r0 = (int)((g + i * p.groups) * LF_ROWS);
+            for (int i = 0; i < my_blocks; ++i) {
+                const int r0 = (g + i * p.groups) * LF_ROWS;
                 umma::mbar_wait_guarded(&x_empty[stage], phase ^ 1);
                 umma::mbar_arrive_expect_tx(&x_full[stage], (uint32_t)(2 * FB * LF_ROWS * 128));
                 uint8_t* xh = smem + SM::off_x16 + stage * SM::X16_BYTES;
@@ -185,7 +185,7 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
             umma::tc_fence_after();
             int xs = 0, b1 = 0;                        // X stage / D1 buffer (counters instead of i % 4, i % 3)
             uint32_t xph = 0, d1ph = 1;                // parity of x_full[xs] / d1_empty[b1] to wait for
-            for (int64_t i = 0; i < my_blocks; ++i) {
+            for (int i = 0; i < my_blocks; ++i) {
                 umma::mbar_wait_guarded(&x_full[xs], xph);
                 umma::mbar_wait_guarded(&d1_empty[b1], d1ph);
                 umma::tc_fence_after();
@@ -213,7 +213,7 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
             const uint32_t x0 = (umma::smem_u32(smem + SM::off_x16) >> 4) | ((LF_ROWS * 128 >> 4) << 16);   // MN-major view: LBO = one box
             int xs = 0;
             uint32_t chain = 0;                        // index of the current D2 accumulation chain
-            for (int64_t i = 0; i < my_blocks; ++i) {
+            for (int i = 0; i < my_blocks; ++i) {
                 const uint32_t buf = chain & 1;
                 const bool first = (i & (LF_D2_CHAIN - 1)) == 0;
                 if (first) umma::mbar_wait_guarded(&acc2_empty[buf], ((chain >> 1) & 1) ^ 1);
@@ -274,25 +274,20 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
             if (lane == 0) umma::mbar_arrive(&acc2_empty[buf]);
             ++chain;
         };
-        const int64_t n_chains = (my_blocks + LF_D2_CHAIN - 1) / LF_D2_CHAIN;
+        const int n_chains = (my_blocks + LF_D2_CHAIN - 1) / LF_D2_CHAIN;
         const uint64_t c2 = f2_pack(inv1 * 1.4426950408889634f, inv1 * 1.4426950408889634f);
         const uint64_t one2 = f2_pack(1.f, 1.f), ms2 = f2_pack(-LF_D_SCALE, -LF_D_SCALE), mone2 = f2_pack(-1.f, -1.f);
-        float y_next = 0.f;
-        if (grp < my_blocks) {
-            const int64_t rn = (g + (int64_t)grp * p.groups) * LF_ROWS + hp * LF_EROWS + lane;
-            y_next = rn < p.N ? __ldg(p.y + rn) : 0.f;
-        }
         int b = grp;                                   // D1 buffer of this group's next block: (b + 2) % 3 per step
         uint32_t d1ph = 0;                             // parity of d1_full[b] to wait for; flips when b wraps
-        for (int64_t i = grp; i < my_blocks; i += 2) {
-            const int64_t r0 = (g + i * p.groups) * LF_ROWS;
+        const int row_step = 2 * p.groups * LF_ROWS;
+        int64_t r0 = (int64_t)(g + grp * p.groups) * LF_ROWS;      // first row of this group's current block
+        for (int i = grp; i < my_blocks; i += 2, r0 += row_step) {
             const int rows = (int)min((int64_t)LF_ROWS, p.N - r0);
-            // lane j: y of row 32 hp + j of this block (0 past the end of the data), loaded one block ahead
-            const float y_raw = y_next;
-            {
-                const int64_t rn = r0 + 2 * p.groups * LF_ROWS + hp * LF_EROWS + lane;
-                y_next = (i + 2 < my_blocks && rn < p.N) ? __ldg(p.y + rn) : 0.f;
-            }
+            // lane j: y of row 32 hp + j of this block (0 past the end of the data).  Issued before the accumulator wait and
+            // first used after the TMEM load: no register lives across iterations (a prefetched value got spilled, and the
+            // spill store waited for the load)
+            const int64_t rn = r0 + hp * LF_EROWS + lane;
+            const float y_raw = rn < p.N ? __ldg(p.y + rn) : 0.f;
             umma::mbar_wait_guarded(&d1_full[b], d1ph);
             umma::tc_fence_after();
             float L[LF_EROWS];
@@ -375,15 +370,15 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
                 *reinterpret_cast<uint4*>(dh + off) = make_uint4(dh_w[4 * cc], dh_w[4 * cc + 1], dh_w[4 * cc + 2], dh_w[4 * cc + 3]);
                 *reinterpret_cast<uint4*>(dl + off) = make_uint4(dl_w[4 * cc], dl_w[4 * cc + 1], dl_w[4 * cc + 2], dl_w[4 * cc + 3]);
             }
+            ll_total += (double)ll;
             umma::fence_proxy_async();
             __syncwarp();
             if (lane == 0) umma::mbar_arrive(&d_full[grp]);
-            ll_total += (double)ll;
             // chains that ended at or before block i - 1 are complete (or about to be): drain them now, while the tensor core
             // works on this block's d  (chain c covers blocks 2c, 2c + 1)
-            while ((int64_t)chain < n_chains && (int64_t)(chain * LF_D2_CHAIN + LF_D2_CHAIN - 1) < i) drain();
+            while ((int)chain < n_chains && (int)(chain * LF_D2_CHAIN + LF_D2_CHAIN - 1) < i) drain();
         }
-        while ((int64_t)chain < n_chains) drain();
+        while ((int)chain < n_chains) drain();
         // this CTA's share of + d ll / d W for vector s_glob, features 32 part .. + 31
         if (s_ok) {
             const float inv2 = 1.f / (LF_D_SCALE * p2_scale(*p.scal_x));
