@@ -28,7 +28,7 @@ namespace brn {
 constexpr int LF_ROWS = 64;            // rows of X per block (N of MMA1, K of MMA2)
 constexpr int LF_MT = 128;             // weight vectors per CTA tile (M of both MMAs)
 constexpr int LF_FMAX = 128;           // features (K of MMA1, N of MMA2): multiple of 16, at most 128
-constexpr int LF_XSTAGES = 4;          // X blocks (fp16 pair images, 32 KB each) in flight
+constexpr int LF_XSTAGES_SMEM_D = 4;   // X blocks (fp16 pair images, 32 KB each) in flight; 5 when the d tile lives in TMEM
 constexpr int LF_D1BUF = 3;            // logits accumulators in TMEM: the logits MMA runs two blocks ahead of the gradient MMA
 constexpr int LF_THREADS = 640;        // 20 warps: TMA, MMA, 2 idle | 16 epilogue
 constexpr int LF_EPI_WARP0 = 4, LF_EPI_WARPS = 16;
@@ -37,13 +37,15 @@ constexpr int LF_EFEAT = 32;           // gradient features per epilogue warp (a
 constexpr int LF_D2_CHAIN = 2;         // blocks per D2 accumulation chain
 constexpr float LF_D_SCALE = 8192.f;   // 2^13: |d| < 1
 
+template <int DTMEM>
 struct LinearFlashSmem {
+    static constexpr int XSTAGES = DTMEM ? LF_XSTAGES_SMEM_D + 1 : LF_XSTAGES_SMEM_D;
     static constexpr int W_BYTES = 2 * LF_MT * LF_FMAX * 2;                 // (hi, lo) [128][128] fp16 = 64 KB
     static constexpr int X16_BYTES = 2 * LF_ROWS * LF_FMAX * 2;             // (hi, lo) [64][128] fp16 = 32 KB
-    static constexpr int D_BYTES = 2 * LF_MT * LF_ROWS * 2;                 // (hi, lo) [128][64] fp16 = 32 KB
+    static constexpr int D_BYTES = DTMEM ? 0 : 2 * LF_MT * LF_ROWS * 2;     // (hi, lo) [128][64] fp16 = 32 KB (shared-memory d tile)
     static constexpr int off_w = 0;
     static constexpr int off_x16 = off_w + W_BYTES;
-    static constexpr int off_d = off_x16 + LF_XSTAGES * X16_BYTES;
+    static constexpr int off_d = off_x16 + XSTAGES * X16_BYTES;
     static constexpr int TOTAL = off_d + D_BYTES + 1024;                    // + alignment slack
     static_assert(TOTAL <= 227 * 1024, "shared memory budget exceeded");
 };
@@ -108,12 +110,35 @@ __device__ __forceinline__ void mma_f16_lohi(uint32_t d_tmem, uint32_t a_lo, uin
         : "memory");
 }
 
-// KS1 = F / 16 at compile time (the logits MMA loop is then fully unrolled), 0 = any F
-template <int KS1>
+// tcgen05.mma kind::f16 with the A operand in TENSOR MEMORY (lane = row of A, one 32-bit column = two consecutive K elements)
+__device__ __forceinline__ void mma_f16_ts_lohi(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t hi, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(hi), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+// registers -> TMEM: thread i of the warp writes lane (lane_base + i), 16 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+                   "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// KS1 = F / 16 at compile time (the logits MMA loop is then fully unrolled), 0 = any F.
+// DTMEM: the d tile (A operand of the gradient MMA) lives in tensor memory (64 columns: hi pair words, lo pair words) instead of
+// shared memory -- the epilogue thread that owns TMEM lane s writes row s with tcgen05.st: no shared-memory round trip, no
+// generic -> async proxy fence, half the shared-memory operand reads of the gradient MMA.
+template <int KS1, int DTMEM>
 __global__ void __launch_bounds__(LF_THREADS, 1)
 linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
                     const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl, LinearFlashParams p) {
-    using SM = LinearFlashSmem;
+    using SM = LinearFlashSmem<DTMEM>;
+    constexpr int LF_XSTAGES = SM::XSTAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) uint64_t w_full, x_full[LF_XSTAGES], x_empty[LF_XSTAGES], d1_full[LF_D1BUF], d1_empty[LF_D1BUF],
@@ -144,6 +169,7 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
     umma::tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
     const uint32_t t_d1 = tmem_base, t_d2 = tmem_base + 256;        // D1: 3 x 64 columns at 0 / 64 / 128; D2: 2 x 128 at 256 / 384
+    const uint32_t t_dt = tmem_base + 192;                          // d tile (DTMEM): hi words at 192..223, lo words at 224..255
 
     // register budget: the CTA owns 96 registers x 640 threads (launch bounds); setmaxnreg only moves registers INSIDE that
     // allocation (asking for more blocks forever), so per warpgroup 32 + 4 x 112 = 480 = 5 x 96
@@ -224,9 +250,15 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
 #pragma unroll
                 for (int ks = 0; ks < LF_ROWS / 16; ++ks) {
                     // A = d tile, K-major (32 bytes per k-step); B: 16 K-indices (rows of X) = 2 KB per k-step
-                    mma_f16_lohi(d_t, d_l + ks * 2, xm + ks * 128, HI, idesc2, !first || ks != 0);
-                    mma_f16_lohi(d_t, d_h + ks * 2, xm + (SM::X16_BYTES / 2 >> 4) + ks * 128, HI, idesc2, true);
-                    mma_f16_lohi(d_t, d_h + ks * 2, xm + ks * 128, HI, idesc2, true);
+                    if (DTMEM) {      // 16 K elements = 8 columns per k-step
+                        mma_f16_ts_lohi(d_t, t_dt + 32 + ks * 8, xm + ks * 128, HI, idesc2, !first || ks != 0);
+                        mma_f16_ts_lohi(d_t, t_dt + ks * 8, xm + (SM::X16_BYTES / 2 >> 4) + ks * 128, HI, idesc2, true);
+                        mma_f16_ts_lohi(d_t, t_dt + ks * 8, xm + ks * 128, HI, idesc2, true);
+                    } else {
+                        mma_f16_lohi(d_t, d_l + ks * 2, xm + ks * 128, HI, idesc2, !first || ks != 0);
+                        mma_f16_lohi(d_t, d_h + ks * 2, xm + (SM::X16_BYTES / 2 >> 4) + ks * 128, HI, idesc2, true);
+                        mma_f16_lohi(d_t, d_h + ks * 2, xm + ks * 128, HI, idesc2, true);
+                    }
                 }
                 umma::mma_commit(&x_empty[xs]);        // X block and d tile are free once these MMAs retire (the logits MMA of
                 umma::mma_commit(&d_empty[i & 1]);     // this block retired long ago: d was computed from its result)
@@ -361,6 +393,14 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
             // the d tile is free once the gradient MMA of the previous block (the other group's) has retired
             // (block i - 1: barrier of the other parity, its use (i - 1) / 2; the first block has nothing to wait for)
             if (i > 0) umma::mbar_wait_guarded(&d_empty[(i & 1) ^ 1], (uint32_t)(((i - 1) >> 1) & 1));
+            if (DTMEM) {
+                // this thread owns TMEM lane s_local = row s of the A operand; column = pair of block rows (2k, 2k + 1)
+                umma::tc_fence_after();
+                tmem_st_32x16(t_dt + lane_addr + hp * (LF_EROWS / 2), dh_w);
+                tmem_st_32x16(t_dt + 32 + lane_addr + hp * (LF_EROWS / 2), dl_w);
+                tmem_st_wait();
+                umma::tc_fence_before();
+            } else {
             // K-major A tile [128 vectors][64 rows] fp16, 128-byte rows, SWIZZLE_128B: this thread owns row s_local and writes
             // the 4 chunks (8 rows of X each) of its rows
 #pragma unroll
@@ -370,8 +410,9 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
                 *reinterpret_cast<uint4*>(dh + off) = make_uint4(dh_w[4 * cc], dh_w[4 * cc + 1], dh_w[4 * cc + 2], dh_w[4 * cc + 3]);
                 *reinterpret_cast<uint4*>(dl + off) = make_uint4(dl_w[4 * cc], dl_w[4 * cc + 1], dl_w[4 * cc + 2], dl_w[4 * cc + 3]);
             }
-            ll_total += (double)ll;
             umma::fence_proxy_async();
+            }
+            ll_total += (double)ll;
             __syncwarp();
             if (lane == 0) umma::mbar_arrive(&d_full[grp]);
             // chains that ended at or before block i - 1 are complete (or about to be): drain them now, while the tensor core
@@ -524,12 +565,17 @@ static int launch_linear_flash(const float* X, const void* px, const float* y, i
     p.y = y; p.N = N; p.F = F; p.S = S; p.scal_w = b.scal; p.scal_x = scal_x; p.part = b.part; p.part_stride = (int64_t)S * F;
     p.loss = loss; p.loss_scale = loss_scale; p.groups = b.groups;
     dim3 grid(b.tiles, b.groups);
+    int dtmem = 1;
+    if (const char* env = getenv("BRN_LINEAR_DTMEM")) dtmem = atoi(env) != 0;
+    auto launch = [&](auto kern, int smem_bytes) -> int {
+        BRN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        kern<<<grid, LF_THREADS, smem_bytes, stream>>>(tWh, tWl, tXh, tXl, p);
+        return 0;
+    };
     if (F == 128) {
-        BRN_CUDA_OK(cudaFuncSetAttribute(linear_flash_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, LinearFlashSmem::TOTAL));
-        linear_flash_kernel<8><<<grid, LF_THREADS, LinearFlashSmem::TOTAL, stream>>>(tWh, tWl, tXh, tXl, p);
+        if (int e = dtmem ? launch(linear_flash_kernel<8, 1>, LinearFlashSmem<1>::TOTAL) : launch(linear_flash_kernel<8, 0>, LinearFlashSmem<0>::TOTAL)) return e;
     } else {
-        BRN_CUDA_OK(cudaFuncSetAttribute(linear_flash_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, LinearFlashSmem::TOTAL));
-        linear_flash_kernel<0><<<grid, LF_THREADS, LinearFlashSmem::TOTAL, stream>>>(tWh, tWl, tXh, tXl, p);
+        if (int e = dtmem ? launch(linear_flash_kernel<0, 1>, LinearFlashSmem<1>::TOTAL) : launch(linear_flash_kernel<0, 0>, LinearFlashSmem<0>::TOTAL)) return e;
     }
     BRN_LAUNCH_OK("linear_flash_kernel");
     return 0;
