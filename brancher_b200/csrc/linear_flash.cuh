@@ -46,7 +46,9 @@ struct LinearFlashSmem {
     static constexpr int off_w = 0;
     static constexpr int off_x16 = off_w + W_BYTES;
     static constexpr int off_d = off_x16 + XSTAGES * X16_BYTES;
-    static constexpr int TOTAL = off_d + D_BYTES + 1024;                    // + alignment slack
+    static constexpr int off_y = off_d + D_BYTES;                           // y of the block in each X stage: 64 floats
+    static constexpr int Y_BYTES = LF_ROWS * 4;
+    static constexpr int TOTAL = off_y + XSTAGES * Y_BYTES + 1024;          // + alignment slack
     static_assert(TOTAL <= 227 * 1024, "shared memory budget exceeded");
 };
 
@@ -64,6 +66,12 @@ __device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t addr, uint32_t l
 // kind::f16, fp16 operands, fp32 accumulate; b_mn: B operand is MN-major
 __host__ __device__ constexpr uint32_t idesc_f16_major(int M, int N, bool b_mn) {
     return (1u << 4) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(umma::smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(umma::smem_u32(bar))
+                 : "memory");
 }
 
 // packed fp32 pairs (one issue slot for two lanes of work; sm_100)
@@ -96,6 +104,7 @@ struct LinearFlashParams {
     int64_t part_stride;          // S_pad * F
     double* loss; float loss_scale;
     int groups;
+    int y_bulk;                   // y is 16-byte aligned: full blocks of it travel with the X block (bulk copy) into shared memory
 };
 
 // tcgen05.mma kind::f16 with both shared-memory descriptors given as (low word, shared high word)
@@ -187,7 +196,9 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
             for (int i = 0; i < my_blocks; ++i) {
                 const int r0 = (g + i * p.groups) * LF_ROWS;
                 umma::mbar_wait_guarded(&x_empty[stage], phase ^ 1);
-                umma::mbar_arrive_expect_tx(&x_full[stage], (uint32_t)(2 * FB * LF_ROWS * 128));
+                const bool ycopy = p.y_bulk && (int64_t)r0 + LF_ROWS <= p.N;      // full block: its 64 targets ride along
+                umma::mbar_arrive_expect_tx(&x_full[stage], (uint32_t)(2 * FB * LF_ROWS * 128 + (ycopy ? SM::Y_BYTES : 0)));
+                if (ycopy) bulk_copy_g2s(smem + SM::off_y + stage * SM::Y_BYTES, p.y + r0, SM::Y_BYTES, &x_full[stage]);
                 uint8_t* xh = smem + SM::off_x16 + stage * SM::X16_BYTES;
                 for (int b = 0; b < FB; ++b) {
                     umma::tma_load_2d(xh + b * (LF_ROWS * 128), &tmXh, &x_full[stage], b * 64, r0);
@@ -309,17 +320,24 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
         const int n_chains = (my_blocks + LF_D2_CHAIN - 1) / LF_D2_CHAIN;
         const uint64_t c2 = f2_pack(inv1 * 1.4426950408889634f, inv1 * 1.4426950408889634f);
         const uint64_t one2 = f2_pack(1.f, 1.f), ms2 = f2_pack(-LF_D_SCALE, -LF_D_SCALE), mone2 = f2_pack(-1.f, -1.f);
+        int xs = grp % LF_XSTAGES;                     // X stage (and y slot) of this group's next block
         int b = grp;                                   // D1 buffer of this group's next block: (b + 2) % 3 per step
         uint32_t d1ph = 0;                             // parity of d1_full[b] to wait for; flips when b wraps
         const int row_step = 2 * p.groups * LF_ROWS;
         int64_t r0 = (int64_t)(g + grp * p.groups) * LF_ROWS;      // first row of this group's current block
         for (int i = grp; i < my_blocks; i += 2, r0 += row_step) {
             const int rows = (int)min((int64_t)LF_ROWS, p.N - r0);
-            // lane j: y of row 32 hp + j of this block (0 past the end of the data).  Issued before the accumulator wait and
-            // first used after the TMEM load: no register lives across iterations (a prefetched value got spilled, and the
-            // spill store waited for the load)
-            const int64_t rn = r0 + hp * LF_EROWS + lane;
-            const float y_raw = rn < p.N ? __ldg(p.y + rn) : 0.f;
+            // targets of the block: from shared memory when they came with the X block (full block, aligned y), else lane j
+            // loads y of row 32 hp + j (0 past the end of the data) before the accumulator wait and shuffles broadcast it
+            const bool y_smem = p.y_bulk && rows == LF_ROWS;
+            const float* ysm = reinterpret_cast<const float*>(smem + SM::off_y + xs * SM::Y_BYTES) + hp * LF_EROWS;
+            xs += 2;
+            if (xs >= LF_XSTAGES) xs -= LF_XSTAGES;
+            float y_raw = 0.f;
+            if (!y_smem) {
+                const int64_t rn = r0 + hp * LF_EROWS + lane;
+                y_raw = rn < p.N ? __ldg(p.y + rn) : 0.f;
+            }
             umma::mbar_wait_guarded(&d1_full[b], d1ph);
             umma::tc_fence_after();
             float L[LF_EROWS];
@@ -340,10 +358,17 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
             uint32_t dh_w[LF_EROWS / 2], dl_w[LF_EROWS / 2];
             uint64_t acc_yl = f2_pack(0.f, 0.f), prod = one2;
             float acc_mx = 0.f;
-            auto body = [&](auto ragged) {
+            const uint64_t s2 = f2_pack(LF_D_SCALE, LF_D_SCALE);
+            auto body = [&](auto ragged, auto from_smem) {
 #pragma unroll
                 for (int k = 0; k < LF_EROWS / 2; ++k) {
-                    const uint64_t ys2 = f2_pack(__shfl_sync(0xffffffffu, ys_lane, 2 * k), __shfl_sync(0xffffffffu, ys_lane, 2 * k + 1));
+                    uint64_t ys2;
+                    if (decltype(from_smem)::value) {
+                        const float2 yv = *reinterpret_cast<const float2*>(ysm + 2 * k);      // same address in every lane: broadcast
+                        ys2 = f2_mul(f2_pack(yv.x, yv.y), s2);
+                    } else {
+                        ys2 = f2_pack(__shfl_sync(0xffffffffu, ys_lane, 2 * k), __shfl_sync(0xffffffffu, ys_lane, 2 * k + 1));
+                    }
                     const uint64_t L2 = f2_pack(L[2 * k], L[2 * k + 1]);
                     float a0, a1, e0, e1, i0, i1, r0f, r1f;
                     f2_unpack(f2_mul(L2, c2), a0, a1);
@@ -383,7 +408,9 @@ linear_flash_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_const
                     dl_w[k] = *reinterpret_cast<const uint32_t*>(&l2);
                 }
             };
-            if (rows == LF_ROWS) body(std::false_type{}); else body(std::true_type{});
+            if (y_smem) body(std::false_type{}, std::true_type{});
+            else if (rows == LF_ROWS) body(std::false_type{}, std::false_type{});
+            else body(std::true_type{}, std::false_type{});
             float ay0, ay1, pr0, pr1, lg0, lg1;
             f2_unpack(acc_yl, ay0, ay1);
             f2_unpack(prod, pr0, pr1);
@@ -564,6 +591,8 @@ static int launch_linear_flash(const float* X, const void* px, const float* y, i
     LinearFlashParams p;
     p.y = y; p.N = N; p.F = F; p.S = S; p.scal_w = b.scal; p.scal_x = scal_x; p.part = b.part; p.part_stride = (int64_t)S * F;
     p.loss = loss; p.loss_scale = loss_scale; p.groups = b.groups;
+    p.y_bulk = (reinterpret_cast<uintptr_t>(y) & 15) == 0;
+    if (const char* env = getenv("BRN_LINEAR_Y_BULK")) p.y_bulk = p.y_bulk && atoi(env) != 0;
     dim3 grid(b.tiles, b.groups);
     int dtmem = 1;
     if (const char* env = getenv("BRN_LINEAR_DTMEM")) dtmem = atoi(env) != 0;

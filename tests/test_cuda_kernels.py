@@ -228,12 +228,17 @@ def test_linear_tcgen05_variant(cu, monkeypatch, N, F, S, tied, split_a):
 @pytest.mark.parametrize("N,F,S,tied", [(1, 16, 1, True), (63, 32, 3, False), (64, 16, 128, False), (777, 48, 129, True),
                                          (1000, 128, 70, False), (5000, 128, 300, True), (20000, 64, 130, False),
                                          (130001, 96, 200, False), (9473, 112, 1000, True)])
-def test_linear_flash_variant(cu, monkeypatch, N, F, S, tied):
+@pytest.mark.parametrize("mode", ["default", "y_ldg", "d_smem"])
+def test_linear_flash_variant(cu, monkeypatch, N, F, S, tied, mode):
     """K2 in one pass over X (linear_flash.cuh): logits MMA -> Bernoulli likelihood -> d through shared memory -> gradient
     MMA, fp16 (hi, lo) operand pairs.  Ragged row blocks, ragged vector tiles, one and two 64-feature boxes, more row
-    groups than row blocks."""
+    groups than row blocks.  Modes: the default (d tile in tensor memory, targets through shared memory) and the two fallbacks."""
     from oracle import elbo_oracle as O
     monkeypatch.setenv("BRN_LINEAR_VARIANT", "tcgen05")
+    if mode == "y_ldg":          # targets loaded per lane + shuffles instead of riding along with the X block (the unaligned-y path)
+        monkeypatch.setenv("BRN_LINEAR_Y_BULK", "0")
+    if mode == "d_smem":         # d tile through shared memory instead of tensor memory
+        monkeypatch.setenv("BRN_LINEAR_DTMEM", "0")
     rng = np.random.RandomState(N + F + S)
     X = (rng.randn(N, F) * (1 + 3 * rng.rand(1, F))).astype("f4")
     y = rng.randint(0, 2, size=N)
