@@ -98,6 +98,24 @@ def _fused_loop(joint_model, posterior_model, number_iterations, number_samples,
     from brancher_b200 import config, lowering, distributed
     if not fused_loop_enabled or number_iterations <= 0 or config.device.type != "cuda" or distributed.world_size() != 1:
         return False
+    # the cyclic garbage collector is held off for the duration of the loop set-up and the replays: a full collection over a
+    # large heap (every Brancher variable is a small object graph) costs ~100 ms when it happens to trigger here -- measured as
+    # one perform_inference call in five taking 219 ms instead of 104 ms (profiles/tools/api_probe.py)
+    import gc
+    gc_was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        return _fused_loop_body(joint_model, posterior_model, number_iterations, number_samples, optimizer, opt_params,
+                                inference_method, optimizers_list, input_values, pretraining_iterations)
+    finally:
+        if gc_was_enabled:
+            gc.enable()
+
+
+def _fused_loop_body(joint_model, posterior_model, number_iterations, number_samples, optimizer, opt_params, inference_method,
+                     optimizers_list, input_values, pretraining_iterations):
+    global last_loop
+    from brancher_b200 import config, lowering, distributed
     if type(inference_method) is not ReverseKL or \
             inference_method.gradient_estimator is not gradient_estimators.PathwiseDerivativeEstimator:
         return False
