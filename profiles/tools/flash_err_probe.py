@@ -1,5 +1,6 @@
-"""Probe: signed loss / gradient error of the one-pass K2 kernel (linear_flash.cuh) against the fp64 oracle for each
-BRN_LF_FLAGS setting, at a C2-shaped problem.  Usage: python profiles/tools/flash_err_probe.py [N] [S]"""
+"""Probe: signed loss / gradient error of the K2 variants (staged GEMM pair, one-pass kernel with its fallbacks) against the fp64
+oracle at a C2-shaped problem.  Usage: python profiles/tools/flash_err_probe.py [N] [S]
+(This probe found the loss error that grew linearly with N: a per-thread fp32 running sum of the log-likelihood.)"""
 import os, sys
 import numpy as np
 import torch
@@ -21,8 +22,8 @@ r = cu.sample_range(S, seed=3, offset=5)
 eps = {"weights": cu.philox_normal(F, 0, r, DEV).cpu().numpy().reshape(S, 1, F)}
 l64, g64 = O.logreg_elbo_streamed(X.numpy(), y.numpy(), params, eps, prior)
 Xd, yd = X.to(DEV), y.to(DEV)
-for env in ({"BRN_LINEAR_FLASH": "0"}, {"BRN_LF_FLAGS": "0"}, {"BRN_LF_FLAGS": "1"}, {"BRN_LF_FLAGS": "2"}, {"BRN_LF_FLAGS": "3"}):
-    for k in ("BRN_LINEAR_FLASH", "BRN_LF_FLAGS"):
+for env in ({"BRN_LINEAR_FLASH": "0"}, {}, {"BRN_LINEAR_DTMEM": "0"}, {"BRN_LINEAR_Y_BULK": "0"}):
+    for k in ("BRN_LINEAR_FLASH", "BRN_LINEAR_DTMEM", "BRN_LINEAR_Y_BULK"):
         os.environ.pop(k, None)
     os.environ.update(env)
     w = cu.MeanFieldVar(torch.tensor(params["weights"][0], device=DEV), torch.tensor(params["weights"][1], device=DEV), var_id=0,
