@@ -267,6 +267,17 @@ struct EpiMask {
         const int valid = row_ok ? min(CPT, p.cols - c0) : 0;
         const int lane = threadIdx.x & 31;
         const float* mk = p.mask + (int64_t)(row_ok ? row : 0) * p.ldm + c0;
+        // full, aligned block (the common case): the thread's row segment of the mask is fetched as float4, FOUR groups (16
+        // elements) ahead of use -- with per-element loads on demand the data-gradient GEMMs ran at 17-26 % tensor activity
+        // (profiles/r2f_ncu_full_vae_summary.txt), as EpiBern did before the same change
+        const bool fast = valid == CPT && (reinterpret_cast<uintptr_t>(mk) & 15) == 0;
+        constexpr int NG = CPT / 4;
+        const float4* m4 = reinterpret_cast<const float4*>(mk);
+        float4 mn[4];
+        if (fast) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) mn[q] = q < NG ? __ldg(m4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
         for (int i0 = 0; i0 < CPT; i0 += 32) {
             float d32[32];
@@ -274,9 +285,19 @@ struct EpiMask {
             for (int i = 0; i < 32; i += 4) {
                 float v[4] = {0.f, 0.f, 0.f, 0.f};
                 if (i0 + i < CPT && i0 + i < valid) {
+                    if (fast) {
+                        const int gq = (i0 + i) / 4;                // compile-time: the loops are fully unrolled
+                        const float4 mc = mn[gq & 3];
+                        if (gq + 4 < NG) mn[gq & 3] = __ldg(m4 + gq + 4);
+                        v[0] = mc.x > 0.f ? r[i0 + i] : 0.f;
+                        v[1] = mc.y > 0.f ? r[i0 + i + 1] : 0.f;
+                        v[2] = mc.z > 0.f ? r[i0 + i + 2] : 0.f;
+                        v[3] = mc.w > 0.f ? r[i0 + i + 3] : 0.f;
+                    } else {
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         if (i0 + i + j < valid) v[j] = __ldg(mk + i0 + i + j) > 0.f ? r[i0 + i + j] : 0.f;
+                    }
                     const int col = i0 + i;
                     if (p.plain) {
                         float* o = p.plain + (int64_t)row * p.ldp + c0 + col;
