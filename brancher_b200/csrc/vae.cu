@@ -323,8 +323,13 @@ struct EpiMask {
     }
 };
 
-// N tile: the narrowest instantiated width that covers N in ceil(N / 208) tiles
+// N tile: 128 with SIXTEEN epilogue warps when N is a multiple of 128 (every hidden width of C5: the epilogues -- bias / ReLU /
+// mask / split stores -- are the bound of these GEMMs, and twice the warps at half the columns per thread hide their latency);
+// otherwise the narrowest instantiated width that covers N in ceil(N / 208) tiles, eight epilogue warps.
+// BRN_VAE_EW16=0 restores the round-1 choice for A/B runs.
 static int pick_bn(int N) {
+    static const bool ew16 = [] { const char* e = getenv("BRN_VAE_EW16"); return !(e && atoi(e) == 0); }();
+    if (ew16 && N % 128 == 0) return -128;
     const int nt = (N + 207) / 208, per = (N + nt - 1) / nt;
     return per <= 128 ? 128 : (per <= 176 ? 176 : 208);
 }
@@ -334,6 +339,7 @@ static int launch_gemm(const float* Ah, const float* Al, int M, int64_t lda, con
                        int K, int mode, const typename Epi::Params& ep, cudaStream_t stream, bool allow_split = false) {
     switch (pick_bn(N)) {
         // every A operand of K5 (activations, gradients; row-major or transposed) is one plain fp32 matrix: SPLIT = 1
+        case -128: return launch_umma_nt<128, VAE_BK, Epi, 16, 1, 2>(Ah, nullptr, M, lda, Bh, Bl, N, ldb, K, mode, 2, ep, stream, allow_split);
         case 128: return launch_umma_nt<128, VAE_BK, Epi, UG_EPI_WARPS, 1, 2>(Ah, nullptr, M, lda, Bh, Bl, N, ldb, K, mode, 2, ep, stream,
                                                                            allow_split);
         case 176: return launch_umma_nt<176, VAE_BK, Epi, UG_EPI_WARPS, 1, 2>(Ah, nullptr, M, lda, Bh, Bl, N, ldb, K, mode, 2, ep, stream,
@@ -769,7 +775,7 @@ extern "C" int brn_vae_elbo_fwd_bwd(const float* X, int B, int64_t row0, int64_t
     // gW = dpre^T . a_in   (K = rows: few output tiles, so the K range is split over the SMs with atomic partial sums)
     auto weight_grad = [&](const VaeAct& dcur, const VaeAct& a_in, int64_t rows, const brn_dense_layer& l, float* gW) {
         EpiStore::Params ep;
-        const int bn = pick_bn(l.n_in), cpt = bn / 2;
+        const int tile = pick_bn(l.n_in), bn = tile < 0 ? -tile : tile, cpt = bn / (tile < 0 ? 4 : 2);      // columns per epilogue thread
         ep.out = gW; ep.rows = l.n_out; ep.row_stride = l.n_in; ep.col_stride = 1; ep.blk_stride = cpt; ep.blk_valid = cpt;
         ep.col_limit = l.n_in; ep.total_blks = (l.n_in + cpt - 1) / cpt;
         return launch_gemm<EpiStore>(dcur.t_hi, dcur.t_lo, l.n_out, dcur.ldt, a_in.t_hi, a_in.t_lo, l.n_in, a_in.ldt, (int)rows, 0, ep,
