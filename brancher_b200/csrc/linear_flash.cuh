@@ -52,17 +52,6 @@ struct LinearFlashSmem {
     static_assert(TOTAL <= 227 * 1024, "shared memory budget exceeded");
 };
 
-// MN-major shared-memory descriptor, SWIZZLE_128B: 128-byte rows run along MN (64 fp16), 8 consecutive K indices form one
-// 1024-byte swizzle atom; LBO = byte distance between 64-element blocks along MN, SBO = between 8-index groups along K.
-__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;               // SWIZZLE_128B
-    return d;
-}
 // kind::f16, fp16 operands, fp32 accumulate; b_mn: B operand is MN-major
 __host__ __device__ constexpr uint32_t idesc_f16_major(int M, int N, bool b_mn) {
     return (1u << 4) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);

@@ -100,6 +100,21 @@ __device__ __forceinline__ uint64_t smem_desc_k(uint32_t addr) {
     return d;
 }
 __device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t addr) { return smem_desc_k<128>(addr); }
+// MN-major operand, SWIZZLE_128B: the image TMA leaves for a box [K rows][128 bytes along MN] -- 128-byte rows run along MN
+// (32 tf32 / 64 fp16 elements), 8 consecutive K indices form one 1024-byte swizzle atom.  LBO = byte distance between
+// consecutive 128-byte column blocks along MN (= one box), SBO = between 8-row groups along K (1024 when they are adjacent).
+// 16-bit operands: layout 2 = SWIZZLE_128B (8-row atoms).  32-bit (tf32) operands can only be read MN-major through layout 1 =
+// SWIZZLE_128B_BASE32B: 128-byte rows whose 32-byte chunks are XOR-ed with (row % 4), 4-row atoms of 512 bytes -- the image
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B produces (CUTLASS: "for mn-major tf32 operands, SW128_32B is the only available smem layout").
+__device__ __forceinline__ uint64_t smem_desc_mn(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = 2) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)layout << 61;
+    return d;
+}
 
 // Instruction descriptor for kind::tf32, fp32 accumulate, K-major A and B, dense.
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
@@ -110,6 +125,9 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
            | ((uint32_t)(N >> 3) << 17)   // n_dim              bits [17,23)
            | ((uint32_t)(M >> 4) << 24);  // m_dim              bits [24,29)
 }
+
+// the same with both operands MN-major (bits 15 / 16)
+__host__ __device__ constexpr uint32_t idesc_tf32_mn(int M, int N) { return idesc_tf32(M, N) | (1u << 15) | (1u << 16); }
 
 // D[tmem] (+)= A[smem] * B[smem]^T, issued by ONE thread.
 __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
@@ -210,7 +228,7 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 // Host: encode a 2-D fp32 row-major tensor [rows][cols] (row stride ld elements) for TMA tiles of
 // box_rows x box_cols floats (box_cols = 32: 128-byte swizzle, 16: 64-byte swizzle) with zero OOB fill.
 int make_tmap_2d_f32(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
-                     uint32_t box_cols);
+                     uint32_t box_cols, bool atom32 = false);
 // The same for a 2-D fp16 tensor: cols / ld in ELEMENTS, box_cols = 64 (128-byte swizzle) or 32 (64-byte swizzle) elements.
 int make_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                      uint32_t box_cols);

@@ -2,6 +2,7 @@
 // run time -- no link-time libcuda dependency), the TF32 hi/lo splitter, and a plain GEMM entry point
 // (brn_gemm_nt_3xtf32) used by the tests to validate the tensor-core path in isolation.
 #include "umma_gemm.cuh"
+#include <stdio.h>
 
 #include <cudaTypedefs.h>
 #include <stdlib.h>
@@ -21,7 +22,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 int make_tmap_2d_f32(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
-                     uint32_t box_cols) {
+                     uint32_t box_cols, bool atom32) {
     auto fn = get_encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return -4; }
     if (((uintptr_t)base & 15) || (ld * sizeof(float)) % 16) {
@@ -35,7 +36,9 @@ int make_tmap_2d_f32(CUtensorMap* out, const float* base, uint64_t rows, uint64_
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    // atom32: 128-byte swizzle at 32-byte granularity, the layout tf32 operands need to be read MN-major
+                    atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : (box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B),
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu ld=%llu box=%u)",
@@ -176,6 +179,20 @@ extern "C" int brn_gemm_nt_3xtf32(const float* A, const float* B, float* D, int 
         EpiNull::Params en{D};
         if (bn == -208) return launch_umma_nt<208, 16, EpiNull>(Ah, Al, M, ld, Bh, Bl, N, ld, K, 0, drain, en, stream);
         return launch_umma_nt_kind<208, 16, EpiNull, 8, 0, 4, 1>(Ah, Al, M, 2 * ld, Bh, Bl, N, 2 * ld, 2 * K, 0, drain, en, stream);
+    }
+    if (bn == -300) {
+        // MN-major operands (launch_umma_tn_plain): D = At^T . Bt for the transposed plain copies At [K][M], Bt [K][N]
+        const size_t ldm = pad4((size_t)M), ldn = pad4((size_t)N);
+        float *At = base, *Bt = At + (size_t)K * ldm;
+        BRN_CHECK_ARG((size_t)K * (ldm + ldn) * sizeof(float) + 4096 <= workspace_bytes, "workspace too small for the MN-major test");
+        if (int e = launch_transpose_f32(A, K, M, K, At, ldm, stream)) return e;
+        if (int e = launch_transpose_f32(B, K, N, K, Bt, ldn, stream)) return e;
+        int dbg[3] = {0, 0, 0};
+        if (const char* env = getenv("BRN_MN_DESC")) sscanf(env, "%d,%d,%d", &dbg[0], &dbg[1], &dbg[2]);
+        BRN_CUDA_OK(cudaMemcpyToSymbolAsync(g_mn_desc_dbg, dbg, sizeof(dbg), 0, cudaMemcpyHostToDevice, stream));
+        constexpr int cptm = 64;
+        ep.blk_stride = cptm; ep.blk_valid = cptm; ep.total_blks = (N + cptm - 1) / cptm;
+        return launch_umma_tn_plain<128, 16, EpiStore, 8, 4>(At, M, ldm, Bt, N, ldn, K, 0, drain, ep, stream);
     }
     if (bn == 208) return launch_umma_nt<208, 16, EpiStore>(Ah, Al, M, ld, Bh, Bl, N, ld, K, 0, drain, ep, stream);
     if (bn == 256) return launch_umma_nt<256, 16, EpiStore, 16>(Ah, Al, M, ld, Bh, Bl, N, ld, K, 0, drain, ep, stream);

@@ -19,6 +19,8 @@
 namespace brn {
 
 constexpr int UG_BM = 128;        // rows of A per tile (TMEM lanes)
+// MN-major descriptor parameters {K-step stride, LBO, SBO} in bytes; 0 = the defaults (development knob of the stand-alone GEMM)
+static __device__ int g_mn_desc_dbg[3] = {0, 0, 0};
 // BK = fp32 elements per K chunk = one swizzle row: 32 (128 B, 2-stage ring) or 16 (64 B swizzle, 5-stage ring).  The
 // finer chunk keeps 4 loads in flight while one is consumed: the 2-stage ring left the tensor pipe idle ~35 % of the
 // time waiting for the next 86 KB stage (ncu: profiles/r1a_*), the 5-stage ring hides that latency.
@@ -100,7 +102,11 @@ struct UnitIter {
 // KIND: 0 = tf32 operands (fp32 words, 3xTF32), 1 = fp16 operands (hi / lo halves, "3xFP16": the same 11 + 11 mantissa bits
 // per operand as the TF32 pair at twice the MACs per instruction and half the operand bytes; the caller pre-scales the
 // operands by powers of two into the fp16 range and un-scales in the epilogue).  BK counts 32-bit words per chunk row.
-template <int BN, int BK, class Epi, int EW = UG_EPI_WARPS, int SPLIT = 0, int CW = 4, int KIND = 0>
+// MAJOR: 0 = both operands K-major (A [M][K], B [N][K]); 1 = both MN-major (A [K][M], B [K][N], i.e. D = A^T B for two
+// row-major matrices that share their ROW index as the contraction index -- a weight gradient sum_r d[r, m] a[r, n] read
+// straight from the row-major activations, no transposed copies).  MN-major stages hold BM/32 resp. BN/32 TMA boxes of
+// [BK rows][32 columns] (SWIZZLE_128B); tf32 operands only.
+template <int BN, int BK, class Epi, int EW = UG_EPI_WARPS, int SPLIT = 0, int CW = 4, int KIND = 0, int MAJOR = 0>
 __global__ void __launch_bounds__(64 + 32 * EW + (SPLIT ? 32 * CW : 0), 1)
 umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                       const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
@@ -113,6 +119,7 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
     constexpr int CPT = BN / (EW / 4);             // accumulator columns per epilogue thread
     static_assert(EW == 4 || EW == 8 || EW == 16, "4, 8 or 16 epilogue warps");
     static_assert(KIND == 0 || SPLIT == 0, "on-the-fly operand splitting exists for tf32 operands only");
+    static_assert(MAJOR == 0 || (KIND == 0 && BN % 32 == 0 && BK % 8 == 0), "MN-major operands: tf32, N tile a multiple of 32 columns");
     constexpr int KE = KIND == 0 ? 1 : 2;          // operand elements per 32-bit word
     static_assert(BN <= UG_BUF_COLS && BN % 16 == 0 && CPT % 8 == 0, "unsupported N tile");
     constexpr uint32_t TMEM_COLS = 512;
@@ -152,11 +159,25 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
                     umma::mbar_arrive_expect_tx(&full_bar[stage], SM::STAGE_BYTES - (SPLIT_B ? SM::B_BYTES : 0) -
                                                                       (SPLIT_A ? SM::A_BYTES : 0));
                     const int k0 = kc * UG_BK * KE;
+                    if constexpr (MAJOR == 1) {
+                        // boxes of [BK rows of K][32 columns of M / N]; columns past the matrix are zero-filled
+                        constexpr int BOX = UG_BK * 128;
+                        for (int b = 0; b < UG_BM / 32; ++b) {
+                            umma::tma_load_2d(st + b * BOX, &tmAh, &full_bar[stage], m0 + 32 * b, k0);
+                            if (!SPLIT_A) umma::tma_load_2d(st + SM::A_BYTES + b * BOX, &tmAl, &full_bar[stage], m0 + 32 * b, k0);
+                        }
+                        for (int b = 0; b < BN / 32; ++b) {
+                            umma::tma_load_2d(st + 2 * SM::A_BYTES + b * BOX, &tmBh, &full_bar[stage], n0 + 32 * b, k0);
+                            if (!SPLIT_B)
+                                umma::tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES + b * BOX, &tmBl, &full_bar[stage], n0 + 32 * b, k0);
+                        }
+                    } else {
                     umma::tma_load_2d(st, &tmAh, &full_bar[stage], k0, m0);
                     if (!SPLIT_A) umma::tma_load_2d(st + SM::A_BYTES, &tmAl, &full_bar[stage], k0, m0);
                     umma::tma_load_2d(st + 2 * SM::A_BYTES, &tmBh, &full_bar[stage], k0, n0);
                     if (!SPLIT_B)
                         umma::tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES, &tmBl, &full_bar[stage], k0, n0);
+                    }
                     if (++stage == UG_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -164,7 +185,7 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (umma::elect_one()) {      // not `lane == 0`: ptxas then issues each UTCHMMA once instead of inside an ELECT loop
-            constexpr uint32_t idesc = umma::idesc_kind<KIND>(UG_BM, BN);
+            constexpr uint32_t idesc = MAJOR == 1 ? umma::idesc_tf32_mn(UG_BM, BN) : umma::idesc_kind<KIND>(UG_BM, BN);
             int stage = 0; uint32_t phase = 0, blk = 0;
             for (UnitIter it(m_tiles, n_tiles, k_chunks, mode, split_T, full_units); it.valid(); it.next()) {
                 const int kcb = it.kc_begin(), kce = it.kc_end();
@@ -181,9 +202,13 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
                         const uint32_t ah = st, al = st + SM::A_BYTES, bh = st + 2 * SM::A_BYTES, bl = bh + SM::B_BYTES;
 #pragma unroll
                         for (int ks = 0; ks < UG_BK / 8; ++ks) {
-                            const uint32_t ko = ks * 32;           // 8 tf32 = 32 bytes along K inside the swizzle row
-                            const uint64_t dah = umma::smem_desc_k<SW>(ah + ko), dal = umma::smem_desc_k<SW>(al + ko);
-                            const uint64_t dbh = umma::smem_desc_k<SW>(bh + ko), dbl = umma::smem_desc_k<SW>(bl + ko);
+                            const uint32_t BOX = MAJOR == 1 && g_mn_desc_dbg[1] ? g_mn_desc_dbg[1] : UG_BK * 128;
+                            const uint32_t SBO_ = MAJOR == 1 && g_mn_desc_dbg[2] ? g_mn_desc_dbg[2] : 512;       // 4-row atoms
+                            const uint32_t ko = MAJOR == 1 ? ks * (g_mn_desc_dbg[0] ? g_mn_desc_dbg[0] : 1024) : ks * 32;   // 8 K indices: one 8-row atom / 32 bytes of a row
+                            const uint64_t dah = MAJOR == 1 ? umma::smem_desc_mn(ah + ko, BOX, SBO_, 1) : umma::smem_desc_k<SW>(ah + ko);
+                            const uint64_t dal = MAJOR == 1 ? umma::smem_desc_mn(al + ko, BOX, SBO_, 1) : umma::smem_desc_k<SW>(al + ko);
+                            const uint64_t dbh = MAJOR == 1 ? umma::smem_desc_mn(bh + ko, BOX, SBO_, 1) : umma::smem_desc_k<SW>(bh + ko);
+                            const uint64_t dbl = MAJOR == 1 ? umma::smem_desc_mn(bl + ko, BOX, SBO_, 1) : umma::smem_desc_k<SW>(bl + ko);
                             umma::mma_ss<KIND>(d_tmem, dal, dbh, idesc, kc != kc0 || ks != 0);
                             umma::mma_ss<KIND>(d_tmem, dah, dbl, idesc, true);
                             umma::mma_ss<KIND>(d_tmem, dah, dbh, idesc, true);
@@ -521,6 +546,30 @@ inline int launch_umma_nt(const float* Ah, const float* Al, int M, int64_t lda, 
                           cudaStream_t stream, bool allow_split = false) {
     return launch_umma_nt_kind<BN, BK, Epi, EW, SPLIT, CW, 0>(Ah, Al, M, lda, Bh, Bl, N, ldb, K, mode, drain_chunks, ep, stream,
                                                               allow_split);
+}
+
+// D [M][N] = sum_k A[k][m] B[k][n]: A [K][M] pitch lda and B [K][N] pitch ldb, both plain fp32 row-major (split into TF32 pairs
+// by the converter warps: SPLIT = 3), read MN-major.  mode / allow_split as launch_umma_nt.
+template <int BN, int BK, class Epi, int EW = UG_EPI_WARPS, int CW = 4>
+inline int launch_umma_tn_plain(const float* A, int M, int64_t lda, const float* B, int N, int64_t ldb, int K, int mode,
+                                int drain_chunks, const typename Epi::Params& ep, cudaStream_t stream, bool allow_split = false) {
+    CUtensorMap tA, tB;
+    if (int e = make_tmap_2d_f32(&tA, A, K, M, lda, BK, 32, true)) return e;
+    if (int e = make_tmap_2d_f32(&tB, B, K, N, ldb, BK, 32, true)) return e;
+    const int m_tiles = (M + UG_BM - 1) / UG_BM, n_tiles = (N + BN - 1) / BN, k_chunks = (K + BK - 1) / BK;
+    drain_chunks = drain_chunks * 32 / BK;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const UmmaSplitPlan pl = umma_plan<BN, BK>(M, N, K, sms, allow_split && mode == 0);
+    if (drain_chunks < 1) drain_chunks = 2 * 32 / BK;
+    auto kern = umma_nt_3xtf32_kernel<BN, BK, Epi, EW, 3, CW, 0, 1>;
+    const int smem = UmmaSmem<BN, BK>::TOTAL;
+    BRN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<pl.grid, 64 + 32 * EW + 32 * CW, smem, stream>>>(tA, tA, tB, tB, m_tiles, n_tiles, k_chunks, drain_chunks, mode, pl.split_T,
+                                                          pl.full_units, ep);
+    BRN_LAUNCH_OK("umma_nt_3xtf32_kernel (MN-major)");
+    return 0;
 }
 
 }  // namespace brn

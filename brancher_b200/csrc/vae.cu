@@ -121,7 +121,7 @@ struct EpiDense {
         const int valid = min(CPT, p.cols - c0);
         float* rh = p.rm_hi + (int64_t)row * p.ld + c0;
         float* rl = p.rm_lo ? p.rm_lo + (int64_t)row * p.ld + c0 : nullptr;
-        float* th = p.t_hi + (int64_t)c0 * p.ldt + row;
+        float* th = p.t_hi ? p.t_hi + (int64_t)c0 * p.ldt + row : nullptr;      // NULL: no transposed copy (MN-major weight gradient)
         float* tl = p.t_lo ? p.t_lo + (int64_t)c0 * p.ldt + row : nullptr;
 #pragma unroll
         for (int i = 0; i < CPT; i += 4) {
@@ -129,7 +129,7 @@ struct EpiDense {
                 float v[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) v[j] = (i + j < valid) ? fmaxf(r[i + j] + __ldg(p.bias + c0 + i + j), 0.f) : 0.f;
-                store_split4(v, valid - i, rh + i, rl ? rl + i : nullptr, th + (int64_t)i * p.ldt,
+                store_split4(v, valid - i, rh + i, rl ? rl + i : nullptr, th ? th + (int64_t)i * p.ldt : nullptr,
                              tl ? tl + (int64_t)i * p.ldt : nullptr, p.ldt);
             }
         }
@@ -158,7 +158,7 @@ struct EpiBern {
         const float* x = p.X + (int64_t)(row_ok ? row % p.B : 0) * p.ldx + c0;
         float* rh = p.rm_hi + (int64_t)row * p.ld + c0;
         float* rl = p.rm_lo ? p.rm_lo + (int64_t)row * p.ld + c0 : nullptr;
-        float* th = p.t_hi + (int64_t)c0 * p.ldt + row;
+        float* th = p.t_hi ? p.t_hi + (int64_t)c0 * p.ldt + row : nullptr;      // NULL: no transposed copy (MN-major weight gradient)
         float* tl = p.t_lo ? p.t_lo + (int64_t)c0 * p.ldt + row : nullptr;
         float ll = 0.f;
         if (valid == CPT && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
@@ -200,7 +200,7 @@ struct EpiBern {
                                 ll += __fmaf_rn(xv, l, -__fmaf_rn(lg, 0.6931471805599453f, fmaxf(l, 0.f)));
                                 v[j] = xv - sig;
                             }
-                            store_split4(v, 4, rh + i, rl ? rl + i : nullptr, th + (int64_t)i * p.ldt,
+                            store_split4(v, 4, rh + i, rl ? rl + i : nullptr, th ? th + (int64_t)i * p.ldt : nullptr,
                                          tl ? tl + (int64_t)i * p.ldt : nullptr, p.ldt);
                         }
 #pragma unroll
@@ -233,7 +233,7 @@ struct EpiBern {
                             v[j] = xv - sig;
                         }
                     }
-                    store_split4(v, valid - i0 - i, rh + i0 + i, rl ? rl + i0 + i : nullptr, th + (int64_t)(i0 + i) * p.ldt,
+                    store_split4(v, valid - i0 - i, rh + i0 + i, rl ? rl + i0 + i : nullptr, th ? th + (int64_t)(i0 + i) * p.ldt : nullptr,
                                  tl ? tl + (int64_t)(i0 + i) * p.ldt : nullptr, p.ldt);
                 }
 #pragma unroll
@@ -310,7 +310,7 @@ struct EpiMask {
                     } else {
                         store_split4(v, valid - col, p.rm_hi + (int64_t)row * p.ld + c0 + col,
                                      p.rm_lo ? p.rm_lo + (int64_t)row * p.ld + c0 + col : nullptr,
-                                     p.t_hi + (int64_t)(c0 + col) * p.ldt + row,
+                                     p.t_hi ? p.t_hi + (int64_t)(c0 + col) * p.ldt + row : nullptr,
                                      p.t_lo ? p.t_lo + (int64_t)(c0 + col) * p.ldt + row : nullptr, p.ldt);
                     }
                 }
@@ -418,6 +418,7 @@ vae_sample_dec0_kernel(const float* __restrict__ mean, const float* __restrict__
             a0.rm_hi[(int64_t)row * a0.ld + j] = dec0_value(zs + rr * L, V0, c0, L, j);       // row-major copy: plain fp32
         }
     }
+    if (a0.t_hi)
     for (int idx = tid; idx < 32 * h0; idx += 256) {            // transposed copy: consecutive threads -> consecutive rows
         const int j = idx >> 5, rr = idx & 31, row = r0 + rr;
         if (row < R) {
@@ -558,7 +559,7 @@ vae_heads_bwd_kernel(const float* __restrict__ dmean, const float* __restrict__ 
         __syncwarp();
         for (int i = 0; i < 32; ++i) {
             const int jj = c0 + i, b = b0 + lane;
-            if (jj < h && b < B) {
+            if (jj < h && b < B && dpre.t_hi) {
                 dpre.t_hi[(int64_t)jj * dpre.ldt + b] = tile[w][lane][i];
             }
         }
@@ -742,12 +743,23 @@ extern "C" int brn_vae_elbo_fwd_bwd(const float* X, int B, int64_t row0, int64_t
     BRN_CUDA_OK(cudaMemsetAsync(ws.zero_begin, 0, ws.zero_bytes, stream));
     double* acc_ll = ws.acc, *acc_lpz = ws.acc + 1, *acc_ent = ws.acc + 2;
 
+    // Weight gradients read the row-major activations / gradients MN-major (launch_umma_tn_plain): no transposed copy of any
+    // activation or gradient tensor is written (BRN_VAE_WGRAD_MN=0 restores the round-1 transposed K-major operands).
+    bool wgrad_mn = true;
+    if (const char* env = getenv("BRN_VAE_WGRAD_MN")) wgrad_mn = atoi(env) != 0;
+    if (wgrad_mn) {
+        auto drop_t = [](VaeAct& a) { a.t_hi = nullptr; a.t_lo = nullptr; };
+        drop_t(ws.Xa); drop_t(ws.dL);
+        for (int i = 0; i < m->n_enc; ++i) { drop_t(ws.enc_a[i]); drop_t(ws.enc_d[i]); }
+        for (int i = 0; i < m->n_dec; ++i) { drop_t(ws.dec_a[i]); if (i > 0) drop_t(ws.dec_d[i]); }
+    }
     // 0. TF32-split operands: X and every weight matrix a GEMM reads, in both K-major layouts
     {
         StageTimer st("vae.split_operands", stream);
         BRN_CUDA_OK(cudaMemcpy2DAsync(ws.Xa.rm_hi, ws.Xa.ld * sizeof(float), X, D * sizeof(float), D * sizeof(float), B,
                                       cudaMemcpyDeviceToDevice, stream));         // plain row-major copy with the padded pitch
-        if (int e = launch_split_tf32(X, D, B, D, nullptr, nullptr, ws.Xa.ld, ws.Xa.t_hi, ws.Xa.t_lo, ws.Xa.ldt, stream)) return e;
+        if (!wgrad_mn)
+            if (int e = launch_split_tf32(X, D, B, D, nullptr, nullptr, ws.Xa.ld, ws.Xa.t_hi, ws.Xa.t_lo, ws.Xa.ldt, stream)) return e;
         auto wsplit = [&](const brn_dense_layer& l, VaeWeights& w) {
             return launch_split_tf32(l.W, l.n_in, l.n_out, l.n_in, w.hi, w.lo, w.ld, w.t_hi, w.t_lo, w.ldt, stream);
         };
@@ -775,6 +787,22 @@ extern "C" int brn_vae_elbo_fwd_bwd(const float* X, int B, int64_t row0, int64_t
     // gW = dpre^T . a_in   (K = rows: few output tiles, so the K range is split over the SMs with atomic partial sums)
     auto weight_grad = [&](const VaeAct& dcur, const VaeAct& a_in, int64_t rows, const brn_dense_layer& l, float* gW) {
         EpiStore::Params ep;
+        if (wgrad_mn) {
+            constexpr int cpt = 64;        // columns per epilogue thread of every variant below
+            ep.out = gW; ep.rows = l.n_out; ep.row_stride = l.n_in; ep.col_stride = 1; ep.blk_stride = cpt; ep.blk_valid = cpt;
+            ep.col_limit = l.n_in; ep.total_blks = (l.n_in + cpt - 1) / cpt;
+            // N tile 256 with sixteen epilogue and eight converter warps where the layer's input width allows it (measured at C5:
+            // 1.745 ms per evaluation against 1.78 with 128-column tiles); BRN_VAE_WGRAD_TILE = 0 | 1 | 2 forces a variant
+            static const int tile = [] { const char* e = getenv("BRN_VAE_WGRAD_TILE"); return e ? atoi(e) : 2; }();
+            if (tile == 1)
+                return launch_umma_tn_plain<128, VAE_BK, EpiStore, UG_EPI_WARPS, 8>(dcur.rm_hi, l.n_out, dcur.ld, a_in.rm_hi, l.n_in, a_in.ld,
+                                                                                    (int)rows, 0, 2, ep, stream, true);
+            if (tile == 2 && l.n_in % 256 == 0)
+                return launch_umma_tn_plain<256, VAE_BK, EpiStore, 16, 8>(dcur.rm_hi, l.n_out, dcur.ld, a_in.rm_hi, l.n_in, a_in.ld,
+                                                                          (int)rows, 0, 2, ep, stream, true);
+            return launch_umma_tn_plain<128, VAE_BK, EpiStore, UG_EPI_WARPS, 4>(dcur.rm_hi, l.n_out, dcur.ld, a_in.rm_hi, l.n_in, a_in.ld,
+                                                                                (int)rows, 0, 2, ep, stream, true);
+        }
         const int tile = pick_bn(l.n_in), bn = tile < 0 ? -tile : tile, cpt = bn / (tile < 0 ? 4 : 2);      // columns per epilogue thread
         ep.out = gW; ep.rows = l.n_out; ep.row_stride = l.n_in; ep.col_stride = 1; ep.blk_stride = cpt; ep.blk_valid = cpt;
         ep.col_limit = l.n_in; ep.total_blks = (l.n_in + cpt - 1) / cpt;
