@@ -339,7 +339,12 @@ static int launch_gemm(const float* Ah, const float* Al, int M, int64_t lda, con
                        int K, int mode, const typename Epi::Params& ep, cudaStream_t stream, bool allow_split = false) {
     switch (pick_bn(N)) {
         // every A operand of K5 (activations, gradients; row-major or transposed) is one plain fp32 matrix: SPLIT = 1
-        case -128: return launch_umma_nt<128, VAE_BK, Epi, 16, 1, 2>(Ah, nullptr, M, lda, Bh, Bl, N, ldb, K, mode, 2, ep, stream, allow_split);
+        case -128: {
+            // converter warps (they split the plain fp32 A tile into the TF32 pair inside the stage): 2 by default; BRN_VAE_CW=4
+            static const int cw = [] { const char* e = getenv("BRN_VAE_CW"); return e ? atoi(e) : 2; }();
+            if (cw == 4) return launch_umma_nt<128, VAE_BK, Epi, 16, 1, 4>(Ah, nullptr, M, lda, Bh, Bl, N, ldb, K, mode, 2, ep, stream, allow_split);
+            return launch_umma_nt<128, VAE_BK, Epi, 16, 1, 2>(Ah, nullptr, M, lda, Bh, Bl, N, ldb, K, mode, 2, ep, stream, allow_split);
+        }
         case 128: return launch_umma_nt<128, VAE_BK, Epi, UG_EPI_WARPS, 1, 2>(Ah, nullptr, M, lda, Bh, Bl, N, ldb, K, mode, 2, ep, stream,
                                                                            allow_split);
         case 176: return launch_umma_nt<176, VAE_BK, Epi, UG_EPI_WARPS, 1, 2>(Ah, nullptr, M, lda, Bh, Bl, N, ldb, K, mode, 2, ep, stream,
