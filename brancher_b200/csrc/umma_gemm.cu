@@ -187,9 +187,6 @@ extern "C" int brn_gemm_nt_3xtf32(const float* A, const float* B, float* D, int 
         BRN_CHECK_ARG((size_t)K * (ldm + ldn) * sizeof(float) + 4096 <= workspace_bytes, "workspace too small for the MN-major test");
         if (int e = launch_transpose_f32(A, K, M, K, At, ldm, stream)) return e;
         if (int e = launch_transpose_f32(B, K, N, K, Bt, ldn, stream)) return e;
-        int dbg[3] = {0, 0, 0};
-        if (const char* env = getenv("BRN_MN_DESC")) sscanf(env, "%d,%d,%d", &dbg[0], &dbg[1], &dbg[2]);
-        BRN_CUDA_OK(cudaMemcpyToSymbolAsync(g_mn_desc_dbg, dbg, sizeof(dbg), 0, cudaMemcpyHostToDevice, stream));
         constexpr int cptm = 64;
         ep.blk_stride = cptm; ep.blk_valid = cptm; ep.total_blks = (N + cptm - 1) / cptm;
         return launch_umma_tn_plain<128, 16, EpiStore, 8, 4>(At, M, ldm, Bt, N, ldn, K, 0, drain, ep, stream);

@@ -19,8 +19,6 @@
 namespace brn {
 
 constexpr int UG_BM = 128;        // rows of A per tile (TMEM lanes)
-// MN-major descriptor parameters {K-step stride, LBO, SBO} in bytes; 0 = the defaults (development knob of the stand-alone GEMM)
-static __device__ int g_mn_desc_dbg[3] = {0, 0, 0};
 // BK = fp32 elements per K chunk = one swizzle row: 32 (128 B, 2-stage ring) or 16 (64 B swizzle, 5-stage ring).  The
 // finer chunk keeps 4 loads in flight while one is consumed: the 2-stage ring left the tensor pipe idle ~35 % of the
 // time waiting for the next 86 KB stage (ncu: profiles/r1a_*), the 5-stage ring hides that latency.
@@ -202,9 +200,9 @@ umma_nt_3xtf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
                         const uint32_t ah = st, al = st + SM::A_BYTES, bh = st + 2 * SM::A_BYTES, bl = bh + SM::B_BYTES;
 #pragma unroll
                         for (int ks = 0; ks < UG_BK / 8; ++ks) {
-                            const uint32_t BOX = MAJOR == 1 && g_mn_desc_dbg[1] ? g_mn_desc_dbg[1] : UG_BK * 128;
-                            const uint32_t SBO_ = MAJOR == 1 && g_mn_desc_dbg[2] ? g_mn_desc_dbg[2] : 512;       // 4-row atoms
-                            const uint32_t ko = MAJOR == 1 ? ks * (g_mn_desc_dbg[0] ? g_mn_desc_dbg[0] : 1024) : ks * 32;   // 8 K indices: one 8-row atom / 32 bytes of a row
+                            // MN-major: LBO = one box, SBO = one 4-row atom (512 B), 8 K indices per MMA = two atoms = 1024 B
+                            constexpr uint32_t BOX = UG_BK * 128, SBO_ = 512;
+                            const uint32_t ko = MAJOR == 1 ? ks * 1024 : ks * 32;   // K-major: 8 tf32 = 32 bytes along the swizzle row
                             const uint64_t dah = MAJOR == 1 ? umma::smem_desc_mn(ah + ko, BOX, SBO_, 1) : umma::smem_desc_k<SW>(ah + ko);
                             const uint64_t dal = MAJOR == 1 ? umma::smem_desc_mn(al + ko, BOX, SBO_, 1) : umma::smem_desc_k<SW>(al + ko);
                             const uint64_t dbh = MAJOR == 1 ? umma::smem_desc_mn(bh + ko, BOX, SBO_, 1) : umma::smem_desc_k<SW>(bh + ko);
