@@ -3,8 +3,9 @@
 //
 //   per 64-row block of X (CTA = one tile of 128 weight vectors x a strided set of row blocks):
 //     MMA1   L[s, r]   = sum_f W[s, f] X[r, f]              M = 128 vectors, N = 64 rows,  K = F   (D1 in TMEM, 64 columns)
-//     epilogue         d = y_r - sigmoid(L), ll += y L - softplus(L); d -> fp16 (hi, lo) pair, written to shared memory
-//                      as the K-major A operand of MMA2 (the thread that owns vector s writes row s: no transposition)
+//     epilogue         d = y_r - sigmoid(L), ll += y L - softplus(L); d -> fp16 (hi, lo) pair, written with tcgen05.st to
+//                      TENSOR memory as the A operand of MMA2 (the thread that owns TMEM lane s writes row s: no
+//                      transposition; DTMEM = 0 keeps the round-trip through a K-major shared-memory tile)
 //     MMA2   dW[s, f] += sum_r d[s, r] X[r, f]             M = 128 vectors, N = F,        K = 64 rows (D2 in TMEM, F columns)
 //   The SAME shared-memory image of the X block serves MMA1 as a K-major B operand (K = f, contiguous) and MMA2 as an
 //   MN-major B operand (N = f contiguous, K = rows): no transposed copy of X exists anywhere.
@@ -12,10 +13,12 @@
 // Replaces the staged pair (logits GEMM -> d^T through HBM -> gradient GEMM): at C2 that pair moved 4 GB of d^T out and
 // back per evaluation and read X twice (row-major and a per-chunk transposed copy).  Operands are fp16 (hi, lo) pairs
 // ("3xFP16", see bnn_tc.cuh), scaled by powers of two: X and W are split once per call by small streaming kernels (X: one
-// read + one write of its own size) and arrive by TMA in the swizzled UMMA layout, four blocks in flight per SM; d is in
-// (-1, 1) and scaled by 2^13.  (A first version converted fp32 X inside the kernel from a 32 KB staging area: with only that
+// read + one write of its own size, or once per data matrix: brn_linear_prepare_x) and arrive by TMA in the swizzled UMMA
+// layout, five blocks in flight per SM, the block's targets y riding along (bulk copy); d is in (-1, 1) and scaled by 2^13.  (A first version converted fp32 X inside the kernel from a 32 KB staging area: with only that
 // much in flight per SM the X feed was latency-bound at ~5000 cycles per block against 1536 of tensor work.)
 // Accuracy: D2's accumulation chain is 128 rows long (two blocks) between round-to-nearest drains into registers.
+// Warp roles (20 warps): 0 = TMA producer, 1 = logits-MMA issuer, 2 = gradient-MMA issuer, 3 idle, 4-19 = epilogue in two
+// groups of 8 that take the blocks alternately.  TMEM: D1 3 x 64 columns, d 64, D2 2 x 128.  History: profiles/r2f_flash_history.txt.
 #pragma once
 #include <cuda_fp16.h>
 #include "umma_gemm.cuh"
@@ -30,7 +33,7 @@ constexpr int LF_MT = 128;             // weight vectors per CTA tile (M of both
 constexpr int LF_FMAX = 128;           // features (K of MMA1, N of MMA2): multiple of 16, at most 128
 constexpr int LF_XSTAGES_SMEM_D = 4;   // X blocks (fp16 pair images, 32 KB each) in flight; 5 when the d tile lives in TMEM
 constexpr int LF_D1BUF = 3;            // logits accumulators in TMEM: the logits MMA runs two blocks ahead of the gradient MMA
-constexpr int LF_THREADS = 640;        // 20 warps: TMA, MMA, 2 idle | 16 epilogue
+constexpr int LF_THREADS = 640;        // 20 warps: TMA, 2 MMA issuers, 1 idle | 16 epilogue
 constexpr int LF_EPI_WARP0 = 4, LF_EPI_WARPS = 16;
 constexpr int LF_EROWS = 32;           // rows of a block per epilogue warp (two warps of one group cover a block)
 constexpr int LF_EFEAT = 32;           // gradient features per epilogue warp (all 16 warps drain every chain)
